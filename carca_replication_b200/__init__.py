@@ -1,0 +1,21 @@
+"""carca_replication_b200 — B200 (sm_100a) implementation of CARCA's hot path.
+
+Drop-in for the reference's `src` package on that path: same module / function names
+(`abstract`, `carca`, `train`, `utils`), same signatures, same `state_dict` layout.  All compute
+runs in libcarca_b200.so (hand-written CUDA, C ABI in include/carca_b200.h); there is no CPU or
+PyTorch fallback.
+"""
+from . import abstract, carca, train, utils  # noqa: F401
+from .attrs import ItemAttrTable  # noqa: F401
+from .carca import (  # noqa: F401
+    CARCA, AllEmbedding, BinaryCrossEntropy, CrossAttentionBlock, DotProduct, IdentityEncoding,
+    LearnableEncoding, MultiHeadAttention, PositionalEncoding, SelfAttentionBlock,
+)
+from .train import compute_HR, compute_NDCG, evaluate  # noqa: F401
+from .utils import get_mask, to  # noqa: F401
+
+__all__ = [
+    "CARCA", "AllEmbedding", "BinaryCrossEntropy", "CrossAttentionBlock", "DotProduct", "IdentityEncoding",
+    "LearnableEncoding", "MultiHeadAttention", "PositionalEncoding", "SelfAttentionBlock", "ItemAttrTable",
+    "compute_HR", "compute_NDCG", "evaluate", "get_mask", "to",
+]

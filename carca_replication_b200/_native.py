@@ -1,0 +1,160 @@
+"""ctypes binding of libcarca_b200.so (C ABI declared in include/carca_b200.h).
+
+The library is the product: there is no Python/torch fallback.  If it is missing, or a tensor
+is not on a CUDA device, the call raises.  torch supplies device memory and the current stream
+only; tensors cross the boundary as raw pointers + sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcarca_b200.so")
+
+_LIB = None
+
+vp, i32, i64, u32, u64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
+
+
+class AttrSource(C.Structure):
+    _fields_ = [("kind", i32), ("csr_rowptr", vp), ("csr_cols", vp), ("csr_vals", vp), ("dense", vp)]
+
+
+class EmbedParams(C.Structure):
+    _fields_ = [("n_items", i32), ("d", i32), ("g", i32), ("n_attrs", i32), ("n_ctx", i32),
+                ("items_embed", vp), ("feats_w", vp), ("feats_wT", vp), ("feats_b", vp),
+                ("joint_w", vp), ("joint_b", vp), ("pos", vp), ("pos_len", i32)]
+
+
+class EmbedGrads(C.Structure):
+    _fields_ = [(n, vp) for n in ("items_embed", "feats_w", "feats_b", "joint_w", "joint_b", "pos")]
+
+
+BLOCK_PARAM_NAMES = ("ln1_g", "ln1_b", "wq", "bq", "wk", "bk", "wv", "bv", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2")
+BLOCK_SAVED_NAMES = ("qn", "mean1", "rstd1", "Q", "K", "V", "s", "mean2", "rstd2", "s2", "a1")
+CROSS_PARAM_NAMES = ("wq", "bq", "wk", "bk", "wv", "bv", "wf", "bf")
+CROSS_SAVED_NAMES = ("Q", "K", "V", "s")
+
+
+class BlockParams(C.Structure):
+    _fields_ = [(n, vp) for n in BLOCK_PARAM_NAMES]
+
+
+class BlockSaved(C.Structure):
+    _fields_ = [(n, vp) for n in BLOCK_SAVED_NAMES]
+
+
+class CrossParams(C.Structure):
+    _fields_ = [(n, vp) for n in CROSS_PARAM_NAMES]
+
+
+class CrossSaved(C.Structure):
+    _fields_ = [(n, vp) for n in CROSS_SAVED_NAMES]
+
+
+P = C.POINTER
+
+# name -> argtypes (restype is always int unless noted); mirrors include/carca_b200.h one to one
+SIGNATURES = {
+    "carca_abi_version": [],
+    "carca_transpose": [vp, vp, i32, i32, i32, vp],
+    "carca_padding_mask": [vp, vp, i64, vp],
+    "carca_embed_fwd": [vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32, vp],
+    "carca_embed_bwd": [P(EmbedGrads), vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32,
+                        vp, vp, vp, vp],
+    "carca_dropout": [vp, vp, i64, f32, u64, u32, vp],
+    "carca_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp],
+    "carca_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "carca_linear_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "carca_linear_bwd_input": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "carca_linear_bwd_weight": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "carca_attention_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, u64, u32, vp],
+    "carca_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, u64, u32,
+                            vp],
+    "carca_sa_block_fwd": [vp, P(BlockSaved), vp, vp, P(BlockParams), i32, i32, i32, i32, i32, f32, u64, i32, vp],
+    "carca_sa_block_bwd": [vp, P(BlockParams), vp, vp, vp, P(BlockParams), P(BlockSaved), i32, i32, i32, i32, i32,
+                           f32, u64, i32, vp, vp],
+    "carca_dot_score_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp],
+    "carca_dot_score_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp],
+    "carca_cross_score_fwd": [vp, P(CrossSaved), vp, vp, vp, vp, P(CrossParams), i32, i32, i32, i32, i32, i32, i32,
+                              f32, u64, u32, i64, i32, vp],
+    "carca_cross_score_bwd": [vp, vp, P(CrossParams), vp, vp, P(CrossSaved), vp, vp, vp, vp, P(CrossParams), i32,
+                              i32, i32, i32, i32, i32, i32, f32, u64, u32, i64, i32, vp, vp],
+    "carca_bce_sums": [vp, vp, vp, vp, i64, f32, vp],
+    "carca_bce_finalize": [vp, vp, vp],
+    "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
+    "carca_rank_metrics": [vp, vp, vp, vp, i32, i32, i64, i64, i32, vp],
+}
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    """Attach argtypes/restypes; raises AttributeError if the library lacks a declared symbol."""
+    lib.carca_last_error.restype = C.c_char_p
+    lib.carca_last_error.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    return lib
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m carca_replication_b200.build` "
+                "(nvcc, sm_100a). carca_replication_b200 has no CPU or PyTorch fallback.")
+        loaded = bind(C.CDLL(LIB_PATH))
+        got = loaded.carca_abi_version()
+        if got != 1:
+            raise RuntimeError(f"libcarca_b200.so ABI version {got}, expected 1")
+        _LIB = loaded
+    return _LIB
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point; non-zero return -> RuntimeError with the library's message."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.carca_last_error().decode()}")
+
+
+def require_device(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("carca_replication_b200 runs on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"expected a contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def i32p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if t.dtype != torch.int32 or not t.is_contiguous():
+        raise RuntimeError(f"expected a contiguous int32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def anyp(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise RuntimeError("expected a contiguous tensor")
+    return t.data_ptr()

@@ -1,0 +1,273 @@
+"""CARCA model classes backed by the sm_100a kernels.
+
+Class names, constructor signatures, `forward` signatures and `state_dict` keys/shapes follow the
+reference's `src/carca.py` so that `scripts/training.py:165-174` and `src/train.py` run against
+them unchanged and checkpoints move both ways.  The torch `nn.Embedding / nn.Linear / nn.Conv1d /
+nn.LayerNorm` objects below are parameter containers only (they give the reference's key names and
+initialisation); their `forward` is never called — every op runs in libcarca_b200.so via `ops`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from .abstract import Decoder, Embedding, Encoder, Encoding, Model
+from .attrs import ItemAttrTable
+from .utils import get_mask
+
+
+def _xavier(layer: nn.Module, zero_bias: bool = True) -> nn.Module:
+    nn.init.xavier_uniform_(layer.weight)
+    if zero_bias and getattr(layer, "bias", None) is not None:
+        nn.init.zeros_(layer.bias)
+    return layer
+
+
+# ------------------------------------------------------------------------------- positional encodings
+class IdentityEncoding(Encoding):
+    """No positional signal — the script default (src/carca.py:34-39)."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x
+
+    def table(self, seq_len: int) -> Optional[Tensor]:
+        return None
+
+
+class LearnableEncoding(Encoding):
+    """Learned [max_len, d] table added to profile embeddings (src/carca.py:15-31).
+    Inside AllEmbedding the add is fused into the embedding kernel's epilogue."""
+
+    def __init__(self, d: int, max_len: int):
+        super().__init__()
+        self.max_len = max_len
+        self.encoding = _xavier(nn.Embedding(max_len, d))
+
+    def table(self, seq_len: int) -> Tensor:
+        return self.encoding.weight
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x + self.encoding.weight[: x.size(1)].unsqueeze(0)
+
+
+class PositionalEncoding(Encoding):
+    """Fixed sinusoidal table, buffer `pe` [1, max_len, d] (src/carca.py:43-60)."""
+
+    def __init__(self, d_model: int, max_len: int):
+        super().__init__()
+        pos = torch.arange(max_len, dtype=torch.float32).unsqueeze(1)
+        freq = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(1, max_len, d_model)
+        pe[0, :, 0::2] = torch.sin(pos * freq)
+        pe[0, :, 1::2] = torch.cos(pos * freq)
+        self.register_buffer("pe", pe)
+
+    def table(self, seq_len: int) -> Tensor:
+        return self.pe[0]
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x + self.pe[:, : x.size(1), :]
+
+
+# ------------------------------------------------------------------------------- embedding
+class AllEmbedding(Embedding):
+    """Item id + attribute + context embedding (src/carca.py:66-95), one fused op.
+
+    `a` may be the dense [B, N, A] tensor of the reference API, an `ItemAttrTable`, or None when a
+    table was attached with `set_attr_table` (device-resident attributes, ids + context only).
+    """
+
+    def __init__(self, n_items: int, d: int, g: int, n_ctx: int, n_attrs: int, enc: Encoding):
+        super().__init__()
+        self.d = d
+        self.enc = enc
+        self.items_embed = _xavier(nn.Embedding(n_items, d, padding_idx=0))
+        self.feats_embed = _xavier(nn.Linear(n_ctx + n_attrs, g))
+        self.joint_embed = _xavier(nn.Linear(g + d, d))
+        with torch.no_grad():
+            self.items_embed.weight[0].zero_()           # padding row (src/carca.py:81)
+        self._attr_table: List[ItemAttrTable] = []       # kept out of _modules / state_dict
+
+    def set_attr_table(self, table: Optional[ItemAttrTable]) -> "AllEmbedding":
+        self._attr_table = [] if table is None else [table]
+        return self
+
+    @property
+    def attr_table(self) -> Optional[ItemAttrTable]:
+        return self._attr_table[0] if self._attr_table else None
+
+    def _apply(self, fn, *args, **kwargs):
+        for t in self._attr_table:                        # follow .to(device) / .cuda()
+            t._apply(fn, *args, **kwargs)
+        return super()._apply(fn, *args, **kwargs)
+
+    def forward(self, x: Tensor, a: Union[Tensor, ItemAttrTable, None], c: Tensor, mask: Tensor,
+                target: bool) -> Tensor:
+        table = a if isinstance(a, ItemAttrTable) else (self.attr_table if a is None else None)
+        dense = a if isinstance(a, Tensor) else None
+        pos, foreign_enc = None, False
+        if not target:
+            if hasattr(self.enc, "table"):
+                pos = self.enc.table(x.shape[1])
+            else:
+                foreign_enc = True                        # a user-supplied Encoding plug-in
+        kernel_mask = torch.ones_like(mask) if foreign_enc else mask
+        e = ops.EmbedFn.apply(x, c, kernel_mask, dense, self.items_embed.weight, self.feats_embed.weight,
+                              self.feats_embed.bias, self.joint_embed.weight, self.joint_embed.bias, pos, table,
+                              bool(target))
+        if foreign_enc:
+            e = self.enc.forward(e) * mask.unsqueeze(2)
+        return e
+
+
+# ------------------------------------------------------------------------------- attention
+class MultiHeadAttention(nn.Module):
+    """Masked multi-head attention without output projection (src/carca.py:204-265)."""
+
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float):
+        super().__init__()
+        assert embed_dim % num_heads == 0.0, "Embedding dim must be divisible by number of heads"
+        self.d = embed_dim
+        self.H = num_heads
+        self.WQ = _xavier(nn.Linear(embed_dim, embed_dim))
+        self.WK = _xavier(nn.Linear(embed_dim, embed_dim))
+        self.WV = _xavier(nn.Linear(embed_dim, embed_dim))
+        self.softmax = nn.Softmax(dim=-1)        # kept for module-tree parity; unused
+        self.dropout = nn.Dropout(p=dropout)
+        self._site = ops.SITE_DECODER_ATTN
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, q_mask: Tensor, k_mask: Tensor,
+                causal: int = None, return_w: bool = False):
+        Q = ops.LinearFn.apply(query, self.WQ.weight, self.WQ.bias)
+        K = ops.LinearFn.apply(key, self.WK.weight, self.WK.bias)
+        V = ops.LinearFn.apply(value, self.WV.weight, self.WV.bias)
+        p = self.dropout.p if self.training else 0.0
+        out, w = ops.AttentionCoreFn.apply(Q, K, V, q_mask, k_mask, self.H, causal, p, ops.current_seed(),
+                                           self._site, bool(return_w))
+        if return_w:
+            B, H, Lq, Lk = w.shape                      # reference layout: heads stacked on the batch dim
+            return w.permute(1, 0, 2, 3).reshape(H * B, Lq, Lk), out
+        return out
+
+
+# ------------------------------------------------------------------------------- encoder / decoders
+class SelfAttentionBlock(Encoder):
+    """LN -> causal MHA (+LN(x)) -> LN -> pointwise FFN (+) (src/carca.py:272-318), one C call."""
+
+    def __init__(self, d: int, H: int, p: float, residual: bool):
+        super().__init__()
+        self.residual = residual
+        self.norm1 = nn.LayerNorm(normalized_shape=d)
+        self.attn = MultiHeadAttention(embed_dim=d, num_heads=H, dropout=p)
+        self.norm2 = nn.LayerNorm(normalized_shape=d)
+        self.ffn_1 = _xavier(nn.Conv1d(in_channels=d, out_channels=d, kernel_size=1))
+        self.lrelu = nn.LeakyReLU()
+        self.dropout1 = nn.Dropout(p=p)
+        self.ffn_2 = _xavier(nn.Conv1d(in_channels=d, out_channels=d, kernel_size=1))
+        self.dropout2 = nn.Dropout(p=p)
+        self._block_index = 0                            # set by CARCA: selects the dropout sites
+
+    def _params(self) -> Tuple[Tensor, ...]:
+        a = self.attn
+        return (self.norm1.weight, self.norm1.bias, a.WQ.weight, a.WQ.bias, a.WK.weight, a.WK.bias, a.WV.weight,
+                a.WV.bias, self.norm2.weight, self.norm2.bias, self.ffn_1.weight, self.ffn_1.bias,
+                self.ffn_2.weight, self.ffn_2.bias)
+
+    def forward(self, x: Tensor, mask: Tensor) -> Tensor:
+        p = self.dropout1.p if self.training else 0.0
+        return ops.SABlockFn.apply(x, mask, self.attn.H, bool(self.residual), p, ops.current_seed(),
+                                   self._block_index, *self._params())
+
+
+class CrossAttentionBlock(Decoder):
+    """Targets attend over the encoded profile, then Linear(d->1) + sigmoid (src/carca.py:322-349).
+    Always returns [B, T] (the reference's squeeze() drops the batch dim when B == 1, :346)."""
+
+    def __init__(self, d: int, H: int, p: float, residual: bool):
+        super().__init__()
+        self.residual = residual
+        self.attn = MultiHeadAttention(embed_dim=d, num_heads=H, dropout=p)
+        self.ffn = _xavier(nn.Linear(in_features=d, out_features=1))
+        self.sig = nn.Sigmoid()
+        self._site = ops.SITE_DECODER_ATTN               # + target index, set by CARCA per call
+
+    def forward(self, o: Tensor, o_mask: Tensor, p: Tensor, p_mask: Tensor) -> Tensor:
+        a = self.attn
+        p_drop = a.dropout.p if self.training else 0.0
+        return ops.CrossScoreFn.apply(o, o_mask, p, p_mask, a.H, bool(self.residual), bool(self.training), p_drop,
+                                      ops.current_seed(), self._site, a.WQ.weight, a.WQ.bias, a.WK.weight,
+                                      a.WK.bias, a.WV.weight, a.WV.bias, self.ffn.weight, self.ffn.bias)
+
+
+class DotProduct(Decoder):
+    """sigmoid(<profile, target>): position-wise in training, last profile position in eval
+    (src/carca.py:352-365) — the script's default decoder."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.sig = nn.Sigmoid()
+
+    def forward(self, o: Tensor, o_mask: Tensor, p: Tensor, p_mask: Tensor) -> Tensor:
+        return ops.DotScoreFn.apply(o, p, bool(self.training))
+
+
+# ------------------------------------------------------------------------------- model
+class CARCA(Model):
+    """mask -> embed(profile) -> dropout -> encoder blocks -> LayerNorm -> per target tuple
+    embed + decode -> concat (src/carca.py:401-431)."""
+
+    def __init__(self, d: int, p: float, emb: Embedding, enc: Iterable[Encoder], dec: Decoder):
+        super().__init__()
+        self.embeds = emb
+        self.dropout = nn.Dropout(p=p)
+        self.encoder = enc
+        self.norm = nn.LayerNorm(normalized_shape=d)
+        self.decoder = dec
+        for i, blk in enumerate(enc):
+            if isinstance(blk, SelfAttentionBlock):
+                blk._block_index = i
+
+    def encode(self, profile) -> Tuple[Tensor, Tensor]:
+        p_x, p_a, p_c = profile
+        p_mask = get_mask(p_x)
+        p_e = self.embeds.forward(p_x, p_a, p_c, p_mask, False)
+        if self.training and self.dropout.p > 0.0:
+            p_e = ops.DropoutFn.apply(p_e, self.dropout.p, ops.current_seed(), ops.SITE_EMBED)
+        for block in self.encoder:
+            p_e = block.forward(p_e, p_mask)
+        p_e = ops.LayerNormFn.apply(p_e, self.norm.weight, self.norm.bias)
+        return p_e, p_mask
+
+    def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
+                targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:
+        with ops.forward_seed():
+            p_e, p_mask = self.encode(profile)
+            y_preds = []
+            for t_idx, (o_x, o_a, o_c) in enumerate(targets):
+                o_mask = get_mask(o_x)
+                o_e = self.embeds.forward(o_x, o_a, o_c, o_mask, True)
+                if isinstance(self.decoder, CrossAttentionBlock):
+                    self.decoder._site = ops.SITE_DECODER_ATTN + t_idx
+                y_preds.append(self.decoder.forward(o_e, o_mask, p_e, p_mask))
+            return y_preds[0] if len(y_preds) == 1 else torch.cat(y_preds, dim=-1)
+
+
+# ------------------------------------------------------------------------------- loss
+class BinaryCrossEntropy(nn.Module):
+    """Masked mean of -(t log(y+eps) + (1-t) log(1-y+eps)) (src/carca.py:437-444).
+
+    `reduce_sums` (set by the data-parallel wrapper) all-reduces the two partial sums so every rank
+    normalises by the global mask count, as a single-process run on the whole batch would.
+    """
+
+    def __init__(self):
+        super().__init__()
+        self.reduce_sums = None
+
+    def forward(self, y_pred: Tensor, y_true: Tensor, mask: Tensor, eps: float = 1e-8) -> Tensor:
+        return ops.BCEFn.apply(y_pred, y_true, mask, eps, self.reduce_sums)

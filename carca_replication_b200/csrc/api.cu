@@ -1,0 +1,526 @@
+// extern "C" entry points of libcarca_b200.so (declared in include/carca_b200.h).
+// Each composes the kernels of this directory on the caller's stream; nothing here allocates,
+// synchronises or falls back to the host.
+#include "../../include/carca_b200.h"
+
+#include <cmath>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "embed.cuh"
+#include "gemm.cuh"
+#include "layernorm.cuh"
+#include "score.cuh"
+
+using namespace carca;
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int warp_rows_grid(long long rows) { return (int)ceil_div_ll(rows, 8); }  // 8 warps / 256-thread CTA
+
+// y = x w^T + b with the optional fused epilogue pieces
+int linear(float* y, const float* x, const float* w, const float* b, int M, int N, int K, long long ldw,
+           cudaStream_t st, int act = 0, const DropCfg* drop = nullptr, const float* R = nullptr,
+           int accumulate = 0, const float* row_mask = nullptr, const int* a_rows = nullptr, long long lda = -1,
+           float alpha = 1.0f, int r_mod = 0) {
+  GemmArgs g = gemm_defaults(x, w, y, M, N, K);
+  g.ldb = ldw;
+  g.lda = lda < 0 ? K : lda;
+  g.bias = b;
+  g.act = act;
+  if (drop) g.drop = *drop;
+  g.R = R;
+  g.ldr = N;
+  g.r_mod = r_mod;
+  g.accumulate = accumulate;
+  g.row_mask = row_mask;
+  g.a_rows = a_rows;
+  g.alpha = alpha;
+  return launch_gemm(g, st);
+}
+
+// dx[M,K] (=|+=) alpha * dy[M,N] w[N,K] (+ R)
+int linear_dx(float* dx, const float* dy, const float* w, int M, int N, int K, long long ldw, cudaStream_t st,
+              int accumulate = 0, float alpha = 1.0f, const float* R = nullptr) {
+  GemmArgs g = gemm_defaults(dy, w, dx, M, K, N);
+  g.lda = N;
+  g.transB = 0;
+  g.ldb = ldw;
+  g.ldc = K;
+  g.accumulate = accumulate;
+  g.alpha = alpha;
+  g.R = R;
+  g.ldr = K;
+  return launch_gemm(g, st);
+}
+
+// dw[N,K] (ld lddw) += alpha * dy[P,N]^T x[rows(P),K]
+int linear_dw(float* dw, const float* dy, const float* x, int P, int N, int K, long long lddw, long long ldx,
+              cudaStream_t st, const int* x_rows = nullptr, float alpha = 1.0f) {
+  GemmArgs g = gemm_defaults(dy, x, dw, N, K, P);
+  g.transA = 1;
+  g.lda = N;
+  g.transB = 0;
+  g.ldb = ldx;
+  g.b_rows = x_rows;
+  g.ldc = lddw;
+  g.accumulate = 1;
+  g.alpha = alpha;
+  return launch_gemm(g, st);
+}
+
+int colsum(float* out, const float* X, int M, int N, long long ldx, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  const int rows_per_block = 256;
+  dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block)), block(32, 8);
+  auto k = colsum_kernel;
+  CARCA_LAUNCH(k, grid, block, 0, st, out, X, M, N, ldx, rows_per_block);
+  return check_launch("colsum");
+}
+
+int transpose(float* dst, const float* src, int R, int Cc, long long ld_src, long long ld_dst, int accumulate,
+              cudaStream_t st) {
+  if (R <= 0 || Cc <= 0) return 0;
+  dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32)), block(32, 8);
+  auto k = transpose_kernel;
+  CARCA_LAUNCH(k, grid, block, 0, st, dst, src, R, Cc, ld_src, ld_dst, accumulate);
+  return check_launch("transpose");
+}
+
+int scale_rows(float* Y, const float* X, const float* rs, DropCfg drop, long long rows, int N, cudaStream_t st) {
+  const long long total = rows * N;
+  if (total <= 0) return 0;
+  auto k = scale_rows_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, st, Y, X, rs, drop, total, N);
+  return check_launch("scale_rows");
+}
+
+int layernorm_fwd(float* y, float* mean, float* rstd, const float* x, const float* g, const float* b, int rows,
+                  int d, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  auto k = layernorm_fwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid(rows)), dim3(256), 0, st, y, mean, rstd, x, g, b, rows, d);
+  return check_launch("layernorm_fwd");
+}
+
+int layernorm_bwd(float* dx, float* dg, float* db, const float* dy, const float* x, const float* mean,
+                  const float* rstd, const float* g, int rows, int d, int acc, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const int warps = 8;
+  const int grid = min(warp_rows_grid(rows), 148 * 4);
+  const size_t smem = sizeof(float) * 2 * warps * (size_t)d;
+  if (smem > 48 * 1024) return fail(-2, "layernorm_bwd: d=%d too large for the shared partials", d);
+  auto k = layernorm_bwd_kernel;
+  CARCA_LAUNCH(k, dim3(grid), dim3(256), smem, st, dx, dg, db, dy, x, mean, rstd, g, rows, d, acc);
+  return check_launch("layernorm_bwd");
+}
+
+#ifndef CARCA_EMU
+template <class K>
+int allow_smem(K kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  if (bytes > 227 * 1024) return fail(-2, "attention: %zu bytes of shared memory exceed 227 KB", bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail(-3, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  return 0;
+}
+#else
+template <class K>
+int allow_smem(K, size_t) { return 0; }
+#endif
+
+AttnArgs attn_args(const float* Q, const float* K, const float* V, const float* qm, const float* km, int B, int H,
+                   int Lq, int Lk, int d, int causal_on, int diag, float p, uint64_t seed, uint32_t site) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = Q; a.K = K; a.V = V;
+  a.q_mask = qm; a.k_mask = km;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dh = d / H;
+  a.ldq = d; a.ldk = d; a.ldo = d;
+  a.causal = causal_on; a.diag = diag;
+  a.sqrt_dh = (float)std::sqrt((double)(d / H));
+  a.drop = make_drop(p, seed, site);
+  return a;
+}
+
+int attention_fwd(AttnArgs a, cudaStream_t st) {
+  if (a.B <= 0 || a.Lq <= 0) return 0;
+  if (a.Lk > kAttnMaxChunks * 32) return fail(-2, "attention: Lk=%d > %d unsupported", a.Lk, kAttnMaxChunks * 32);
+  const size_t smem = attention_fwd_smem(a.Lk, a.dh);
+  auto k = attention_fwd_kernel;
+  TRY(allow_smem(k, smem));
+  // enough CTAs to fill the machine: split the query rows when B*H is small
+  int chunks = 1;
+  while ((long long)a.B * a.H * chunks < 2 * 148 && ceil_div(a.Lq, chunks) > kAttnWarps) chunks *= 2;
+  a.rows_per_cta = ceil_div(a.Lq, chunks);
+  dim3 grid(a.B * a.H, ceil_div(a.Lq, a.rows_per_cta));
+  CARCA_LAUNCH(k, grid, dim3(kAttnWarps * 32), smem, st, a);
+  return check_launch("attention_fwd");
+}
+
+int attention_bwd(AttnArgs a, cudaStream_t st) {
+  if (a.B <= 0 || a.Lq <= 0) return 0;
+  if (a.Lk > kAttnMaxChunks * 32) return fail(-2, "attention: Lk=%d > %d unsupported", a.Lk, kAttnMaxChunks * 32);
+  const size_t smem = attention_bwd_smem(a.Lq, a.Lk, a.dh);
+  auto k = attention_bwd_kernel;
+  TRY(allow_smem(k, smem));
+  CARCA_LAUNCH(k, dim3(a.B * a.H), dim3(kAttnWarps * 32), smem, st, a);
+  return check_launch("attention_bwd");
+}
+
+__global__ void __launch_bounds__(256) lrelu_drop_bwd_kernel(float* __restrict__ g, const float* __restrict__ a1,
+                                                             DropCfg drop, long long n) {
+  // g <- g * dropfactor * LeakyReLU'(pre-activation); a1 = dropout(LeakyReLU(.)) keeps its sign
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float f = drop_factor(drop, (unsigned long long)i);
+  g[i] = g[i] * f * (a1[i] > 0.f ? 1.0f : kLeakySlope);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* carca_last_error(void) { return err_buf(); }
+int carca_abi_version(void) { return CARCA_B200_ABI_VERSION; }
+
+int carca_transpose(float* dst, const float* src, int rows, int cols, int accumulate, void* stream) {
+  return transpose(dst, src, rows, cols, cols, rows, accumulate, S(stream));
+}
+
+int carca_padding_mask(float* mask, const int32_t* ids, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  auto k = padding_mask_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, S(stream), mask, ids, (long long)n);
+  return check_launch("padding_mask");
+}
+
+int carca_dropout(float* y, const float* x, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  CARCA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f outside [0,1)", p);
+  return scale_rows(y, x, nullptr, make_drop(p, seed, site), n, 1, S(stream));
+}
+
+// ------------------------------------------------------------------------------------ embedding
+int carca_embed_fwd(float* e, float* q_out, const carca_embed_params* w, const carca_attr_source* at,
+                    const int32_t* x, const float* ctx, const float* mask, int n_rows, int n_cols, int is_target,
+                    void* stream) {
+  cudaStream_t st = S(stream);
+  const int P = n_rows * n_cols;
+  if (P <= 0) return 0;
+  const int d = w->d, g = w->g, A = w->n_attrs, C = w->n_ctx;
+  CARCA_REQUIRE(q_out != nullptr, "embed_fwd: q_out is required");
+  if (at->kind == CARCA_ATTR_CSR) {
+    CARCA_REQUIRE(w->feats_wT != nullptr, "embed_fwd: CSR attributes need feats_wT");
+    auto k = feat_csr_fwd_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, q_out, x, at->csr_rowptr, at->csr_cols,
+                 at->csr_vals, ctx, w->feats_wT, w->feats_b, mask, P, g, A, C);
+    TRY(check_launch("feat_csr_fwd"));
+  } else if (at->kind == CARCA_ATTR_TABLE || at->kind == CARCA_ATTR_DENSE) {
+    const int* rows = at->kind == CARCA_ATTR_TABLE ? x : nullptr;
+    TRY(linear(q_out, at->dense, w->feats_w, w->feats_b, P, g, A, A + C, st, 0, nullptr, nullptr, 0, nullptr, rows,
+               A));
+    if (C > 0) TRY(linear(q_out, ctx, w->feats_w + A, nullptr, P, g, C, A + C, st, 0, nullptr, nullptr, 1));
+  } else {
+    return fail(-2, "embed_fwd: unknown attribute source kind %d", at->kind);
+  }
+  const float sqrt_d = (float)std::sqrt((double)d);
+  // e = sqrt(d) * E[x] Wj[:, :d]^T
+  TRY(linear(e, w->items_embed, w->joint_w, nullptr, P, d, d, d + g, st, 0, nullptr, nullptr, 0, nullptr, x, d,
+             sqrt_d));
+  // e = mask * (e + q Wj[:, d:]^T + bj (+ pos))
+  const float* pos = (!is_target && w->pos) ? w->pos : nullptr;
+  if (pos) CARCA_REQUIRE(n_cols <= w->pos_len, "embed_fwd: sequence length %d > positional table %d", n_cols,
+                         w->pos_len);
+  TRY(linear(e, q_out, w->joint_w + d, w->joint_b, P, d, g, d + g, st, 0, nullptr, pos, 1, mask, nullptr, g, 1.0f,
+             pos ? n_cols : 0));
+  return 0;
+}
+
+int carca_embed_bwd(const carca_embed_grads* gr, const float* de, const float* q_saved, const carca_embed_params* w,
+                    const carca_attr_source* at, const int32_t* x, const float* ctx, const float* mask, int n_rows,
+                    int n_cols, int is_target, float* scratch_pd, float* scratch_pg, float* scratch_wT,
+                    void* stream) {
+  cudaStream_t st = S(stream);
+  const int P = n_rows * n_cols;
+  if (P <= 0) return 0;
+  const int d = w->d, g = w->g, A = w->n_attrs, C = w->n_ctx;
+  const float sqrt_d = (float)std::sqrt((double)d);
+  float* dem = scratch_pd;
+  float* dz = scratch_pd + (long long)P * d;
+  float* dq = scratch_pg;
+  const DropCfg nodrop = make_drop(0.f, 0ull, 0u);
+  TRY(scale_rows(dem, de, mask, nodrop, P, d, st));                               // de * mask  (:94)
+  if (!is_target && w->pos && gr->pos) TRY(colsum(gr->pos, dem, n_rows, n_cols * d, (long long)n_cols * d, st));
+  TRY(colsum(gr->joint_b, dem, P, d, d, st));
+  TRY(linear_dw(gr->joint_w, dem, w->items_embed, P, d, d, d + g, d, st, x, sqrt_d));   // dWj[:, :d]
+  TRY(linear_dw(gr->joint_w + d, dem, q_saved, P, d, g, d + g, g, st));                 // dWj[:, d:]
+  TRY(linear_dx(dq, dem, w->joint_w + d, P, d, g, d + g, st));                          // dq [P,g]
+  TRY(linear_dx(dz, dem, w->joint_w, P, d, d, d + g, st, 0, sqrt_d));                   // dz [P,d]
+  {
+    auto k = scatter_add_rows_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, gr->items_embed, dz, x, P, d);
+    TRY(check_launch("scatter_add_rows"));
+  }
+  TRY(colsum(gr->feats_b, dq, P, g, g, st));
+  if (C > 0) TRY(linear_dw(gr->feats_w + A, dq, ctx, P, g, C, A + C, C, st));           // dWf[:, A:]
+  if (at->kind == CARCA_ATTR_CSR) {
+    CARCA_REQUIRE(scratch_wT != nullptr, "embed_bwd: CSR attributes need scratch_wT");
+    auto k = feat_csr_bwd_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, scratch_wT, dq, x, at->csr_rowptr, at->csr_cols,
+                 at->csr_vals, mask, P, g);
+    TRY(check_launch("feat_csr_bwd"));
+    TRY(transpose(gr->feats_w, scratch_wT, A, g, g, A + C, 1, st));                     // dWf[:, :A] += dWT^T
+  } else if (at->kind == CARCA_ATTR_TABLE || at->kind == CARCA_ATTR_DENSE) {
+    const int* rows = at->kind == CARCA_ATTR_TABLE ? x : nullptr;
+    TRY(linear_dw(gr->feats_w, dq, at->dense, P, g, A, A + C, A, st, rows));
+  } else {
+    return fail(-2, "embed_bwd: unknown attribute source kind %d", at->kind);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ layernorm / linear
+int carca_layernorm_fwd(float* y, float* mean, float* rstd, const float* x, const float* gamma, const float* beta,
+                        int rows, int d, void* stream) {
+  return layernorm_fwd(y, mean, rstd, x, gamma, beta, rows, d, S(stream));
+}
+
+int carca_layernorm_bwd(float* dx, float* dgamma, float* dbeta, const float* dy, const float* x, const float* mean,
+                        const float* rstd, const float* gamma, int rows, int d, int accumulate_dx, void* stream) {
+  return layernorm_bwd(dx, dgamma, dbeta, dy, x, mean, rstd, gamma, rows, d, accumulate_dx, S(stream));
+}
+
+int carca_linear_fwd(float* y, const float* x, const float* w, const float* bias, int M, int N, int K, int act_leaky,
+                     void* stream) {
+  return linear(y, x, w, bias, M, N, K, K, S(stream), act_leaky ? 1 : 0);
+}
+
+int carca_linear_bwd_input(float* dx, const float* dy, const float* w, int M, int N, int K, int accumulate,
+                           void* stream) {
+  return linear_dx(dx, dy, w, M, N, K, K, S(stream), accumulate);
+}
+
+int carca_linear_bwd_weight(float* dw, float* db, const float* dy, const float* x, int M, int N, int K,
+                            void* stream) {
+  TRY(linear_dw(dw, dy, x, M, N, K, K, K, S(stream)));
+  if (db) TRY(colsum(db, dy, M, N, N, S(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ attention
+int carca_attention_fwd(float* O, float* W_out, const float* Q, const float* K, const float* V, const float* q_mask,
+                        const float* k_mask, int B, int H, int Lq, int Lk, int d, int causal_on, int diag,
+                        float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  CARCA_REQUIRE(H > 0 && d % H == 0, "Embedding dim must be divisible by number of heads");  // src/carca.py:208
+  AttnArgs a = attn_args(Q, K, V, q_mask, k_mask, B, H, Lq, Lk, d, causal_on, diag, p_drop, seed, site);
+  a.O = O;
+  a.W = W_out;
+  return attention_fwd(a, S(stream));
+}
+
+int carca_attention_bwd(float* dQ, float* dK, float* dV, const float* dO, const float* Q, const float* K,
+                        const float* V, const float* q_mask, const float* k_mask, int B, int H, int Lq, int Lk,
+                        int d, int causal_on, int diag, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  CARCA_REQUIRE(H > 0 && d % H == 0, "Embedding dim must be divisible by number of heads");
+  AttnArgs a = attn_args(Q, K, V, q_mask, k_mask, B, H, Lq, Lk, d, causal_on, diag, p_drop, seed, site);
+  a.dO = dO; a.dQ = dQ; a.dK = dK; a.dV = dV;
+  return attention_bwd(a, S(stream));
+}
+
+// ------------------------------------------------------------------------------------ SelfAttentionBlock
+int carca_sa_block_fwd(float* out, const carca_block_saved* sv, const float* x, const float* mask,
+                       const carca_block_params* w, int B, int L, int d, int H, int residual, float p_drop,
+                       uint64_t seed, int block_index, void* stream) {
+  cudaStream_t st = S(stream);
+  CARCA_REQUIRE(H > 0 && d % H == 0, "Embedding dim must be divisible by number of heads");
+  const int P = B * L;
+  if (P <= 0) return 0;
+  const uint32_t s_attn = 1 + 3 * block_index, s_f1 = 2 + 3 * block_index, s_f2 = 3 + 3 * block_index;
+  TRY(layernorm_fwd(sv->qn, sv->mean1, sv->rstd1, x, w->ln1_g, w->ln1_b, P, d, st));            // :298
+  TRY(linear(sv->Q, sv->qn, w->wq, w->bq, P, d, d, d, st));                                      // :238
+  TRY(linear(sv->K, x, w->wk, w->bk, P, d, d, d, st));                                           // :239 (raw x)
+  TRY(linear(sv->V, x, w->wv, w->bv, P, d, d, d, st));                                           // :240
+  AttnArgs a = attn_args(sv->Q, sv->K, sv->V, mask, mask, B, H, L, L, d, 1, 0, p_drop, seed, s_attn);  // :299
+  a.O = sv->s;
+  a.resid = residual ? sv->qn : nullptr;                                                         // :302
+  TRY(attention_fwd(a, st));
+  TRY(layernorm_fwd(sv->s2, sv->mean2, sv->rstd2, sv->s, w->ln2_g, w->ln2_b, P, d, st));         // :304
+  const DropCfg d1 = make_drop(p_drop, seed, s_f1), d2 = make_drop(p_drop, seed, s_f2);
+  TRY(linear(sv->a1, sv->s2, w->w1, w->b1, P, d, d, d, st, 1, &d1));                             // :307-309
+  TRY(linear(out, sv->a1, w->w2, w->b2, P, d, d, d, st, 0, &d2, residual ? sv->s2 : nullptr));   // :311-316
+  return 0;
+}
+
+int carca_sa_block_bwd(float* dx, const carca_block_grads* gr, const float* dout, const float* x, const float* mask,
+                       const carca_block_params* w, const carca_block_saved* sv, int B, int L, int d, int H,
+                       int residual, float p_drop, uint64_t seed, int block_index, float* scratch4, void* stream) {
+  cudaStream_t st = S(stream);
+  const int P = B * L;
+  if (P <= 0) return 0;
+  const long long n = (long long)P * d;
+  float* t0 = scratch4;
+  float* t1 = t0 + n;
+  float* t2 = t1 + n;
+  float* t3 = t2 + n;
+  const uint32_t s_attn = 1 + 3 * block_index, s_f1 = 2 + 3 * block_index, s_f2 = 3 + 3 * block_index;
+  const DropCfg d1 = make_drop(p_drop, seed, s_f1), d2 = make_drop(p_drop, seed, s_f2);
+  // ---- FFN
+  const float* df2 = dout;
+  if (p_drop > 0.f) {
+    TRY(scale_rows(t0, dout, nullptr, d2, n, 1, st));
+    df2 = t0;
+  }
+  TRY(linear_dw(gr->w2, df2, sv->a1, P, d, d, d, d, st));
+  TRY(colsum(gr->b2, df2, P, d, d, st));
+  TRY(linear_dx(t1, df2, w->w2, P, d, d, d, st));                          // d a1
+  {
+    auto k = lrelu_drop_bwd_kernel;
+    CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, st, t1, sv->a1, d1, n);
+    TRY(check_launch("lrelu_drop_bwd"));                                   // t1 = d f1
+  }
+  TRY(linear_dw(gr->w1, t1, sv->s2, P, d, d, d, d, st));
+  TRY(colsum(gr->b1, t1, P, d, d, st));
+  TRY(linear_dx(t2, t1, w->w1, P, d, d, d, st, 0, 1.0f, residual ? dout : nullptr));   // d s2
+  // ---- LN2
+  TRY(layernorm_bwd(t0, gr->ln2_g, gr->ln2_b, t2, sv->s, sv->mean2, sv->rstd2, w->ln2_g, P, d, 0, st));  // t0 = d s
+  // ---- attention
+  AttnArgs a = attn_args(sv->Q, sv->K, sv->V, mask, mask, B, H, L, L, d, 1, 0, p_drop, seed, s_attn);
+  a.dO = t0; a.dQ = t1; a.dK = t2; a.dV = t3;
+  TRY(attention_bwd(a, st));
+  TRY(linear_dw(gr->wq, t1, sv->qn, P, d, d, d, d, st));
+  TRY(colsum(gr->bq, t1, P, d, d, st));
+  TRY(linear_dw(gr->wk, t2, x, P, d, d, d, d, st));
+  TRY(colsum(gr->bk, t2, P, d, d, st));
+  TRY(linear_dw(gr->wv, t3, x, P, d, d, d, d, st));
+  TRY(colsum(gr->bv, t3, P, d, d, st));
+  // d qn = dQ WQ (+ d s through the residual) -> in place over t0
+  TRY(linear_dx(t0, t1, w->wq, P, d, d, d, st, residual ? 1 : 0));
+  TRY(linear_dx(dx, t2, w->wk, P, d, d, d, st, 0));
+  TRY(linear_dx(dx, t3, w->wv, P, d, d, d, st, 1));
+  // ---- LN1
+  TRY(layernorm_bwd(dx, gr->ln1_g, gr->ln1_b, t0, x, sv->mean1, sv->rstd1, w->ln1_g, P, d, 1, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ decoders
+int carca_dot_score_fwd(float* y, const float* p, const float* o, int B, int T, int Lp, int d, int per_position,
+                        int64_t ldy, int col0, void* stream) {
+  if ((long long)B * T <= 0) return 0;
+  if (per_position) CARCA_REQUIRE(T == Lp, "dot_score: training mode needs T == L (%d vs %d)", T, Lp);
+  auto k = dot_score_fwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, S(stream), y, p, o, B, T, Lp, d,
+               per_position, (long long)ldy, col0);
+  return check_launch("dot_score_fwd");
+}
+
+int carca_dot_score_bwd(float* d_o, float* d_p, const float* dy, const float* y, const float* p, const float* o,
+                        int B, int T, int Lp, int d, int per_position, int64_t ldy, int col0, void* stream) {
+  if ((long long)B * T <= 0) return 0;
+  auto k = dot_score_bwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, S(stream), d_o, d_p, dy, y, p, o, B, T, Lp,
+               d, per_position, (long long)ldy, col0);
+  return check_launch("dot_score_bwd");
+}
+
+int carca_cross_score_fwd(float* y, const carca_cross_saved* sv, const float* o, const float* o_mask, const float* p,
+                          const float* p_mask, const carca_cross_params* w, int B, int T, int Lp, int d, int H,
+                          int residual, int training, float p_drop, uint64_t seed, uint32_t site, int64_t ldy,
+                          int col0, void* stream) {
+  cudaStream_t st = S(stream);
+  CARCA_REQUIRE(H > 0 && d % H == 0, "Embedding dim must be divisible by number of heads");
+  if ((long long)B * T <= 0) return 0;
+  TRY(linear(sv->Q, o, w->wq, w->bq, B * T, d, d, d, st));
+  TRY(linear(sv->K, p, w->wk, w->bk, B * Lp, d, d, d, st));
+  TRY(linear(sv->V, p, w->wv, w->bv, B * Lp, d, d, d, st));
+  AttnArgs a = attn_args(sv->Q, sv->K, sv->V, o_mask, p_mask, B, H, T, Lp, d, training ? 1 : 0, -1, p_drop, seed,
+                         site);                                                          // :339-340
+  a.O = sv->s;
+  a.resid = residual ? o : nullptr;                                                      // :343
+  TRY(attention_fwd(a, st));
+  auto k = rowdot_sigmoid_fwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, st, y, sv->s, w->wf, w->bf, B, T, d,
+               (long long)ldy, col0);                                                    // :345-347
+  return check_launch("rowdot_sigmoid_fwd");
+}
+
+int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* gr, const float* dy, const float* y,
+                          const carca_cross_saved* sv, const float* o, const float* o_mask, const float* p,
+                          const float* p_mask, const carca_cross_params* w, int B, int T, int Lp, int d, int H,
+                          int residual, int training, float p_drop, uint64_t seed, uint32_t site, int64_t ldy,
+                          int col0, float* scratch4, void* stream) {
+  cudaStream_t st = S(stream);
+  if ((long long)B * T <= 0) return 0;
+  const long long n = (long long)max(B * T, B * Lp) * d;
+  float* ds = scratch4;
+  float* dQ = ds + n;
+  float* dK = dQ + n;
+  float* dV = dK + n;
+  {
+    const int warps = 8;
+    const int grid = min(warp_rows_grid((long long)B * T), 148 * 4);
+    const size_t smem = sizeof(float) * ((size_t)warps * d + warps);
+    CARCA_REQUIRE(smem <= 48 * 1024, "cross_score_bwd: d=%d too large", d);
+    auto k = rowdot_sigmoid_bwd_kernel;
+    CARCA_LAUNCH(k, dim3(grid), dim3(256), smem, st, ds, gr->wf, gr->bf, dy, y, sv->s, w->wf, B, T, d,
+                 (long long)ldy, col0);
+    TRY(check_launch("rowdot_sigmoid_bwd"));
+  }
+  AttnArgs a = attn_args(sv->Q, sv->K, sv->V, o_mask, p_mask, B, H, T, Lp, d, training ? 1 : 0, -1, p_drop, seed,
+                         site);
+  a.dO = ds; a.dQ = dQ; a.dK = dK; a.dV = dV;
+  TRY(attention_bwd(a, st));
+  TRY(linear_dw(gr->wq, dQ, o, B * T, d, d, d, d, st));
+  TRY(colsum(gr->bq, dQ, B * T, d, d, st));
+  TRY(linear_dw(gr->wk, dK, p, B * Lp, d, d, d, d, st));
+  TRY(colsum(gr->bk, dK, B * Lp, d, d, st));
+  TRY(linear_dw(gr->wv, dV, p, B * Lp, d, d, d, d, st));
+  TRY(colsum(gr->bv, dV, B * Lp, d, d, st));
+  TRY(linear_dx(d_o, dQ, w->wq, B * T, d, d, d, st, 0, 1.0f, residual ? ds : nullptr));
+  TRY(linear_dx(d_p, dK, w->wk, B * Lp, d, d, d, st, 1));
+  TRY(linear_dx(d_p, dV, w->wv, B * Lp, d, d, d, st, 1));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ loss / metrics
+int carca_bce_sums(float* sums, const float* y_pred, const int32_t* y_true, const float* mask, int64_t n, float eps,
+                   void* stream) {
+  if (n <= 0) return 0;
+  const int grid = (int)min((long long)148 * 8, ceil_div_ll(n, 256));
+  auto k = bce_sums_kernel;
+  CARCA_LAUNCH(k, dim3(grid), dim3(256), 0, S(stream), sums, y_pred, y_true, mask, (long long)n, eps);
+  return check_launch("bce_sums");
+}
+
+int carca_bce_finalize(float* loss, const float* sums, void* stream) {
+  auto k = bce_finalize_kernel;
+  CARCA_LAUNCH(k, dim3(1), dim3(32), 0, S(stream), loss, sums);
+  return check_launch("bce_finalize");
+}
+
+int carca_bce_bwd(float* dy, const float* grad_out, const float* sums, const float* y_pred, const int32_t* y_true,
+                  const float* mask, int64_t n, float eps, void* stream) {
+  if (n <= 0) return 0;
+  auto k = bce_bwd_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, S(stream), dy, grad_out, sums, y_pred, y_true,
+               mask, (long long)n, eps);
+  return check_launch("bce_bwd");
+}
+
+int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, const int32_t* y_true, int B, int T,
+                       int64_t ldy, int64_t ldt, int k, void* stream) {
+  if (B <= 0) return 0;
+  const int grid = min(148 * 4, ceil_div(B, 8));
+  auto kern = rank_metrics_kernel;
+  CARCA_LAUNCH(kern, dim3(grid), dim3(256), 0, S(stream), acc, first_rank, y_pred, y_true, B, T, (long long)ldy,
+               (long long)ldt, k);
+  return check_launch("rank_metrics");
+}
+
+}  // extern "C"

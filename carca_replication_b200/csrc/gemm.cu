@@ -1,0 +1,75 @@
+// Host launcher for the general fp32 GEMM (see gemm.cuh).
+#include "gemm.cuh"
+
+namespace carca {
+
+static char g_err[512] = {0};
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(-3, "%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+GemmArgs gemm_defaults(const float* A, const float* B, float* C, int M, int N, int K) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = K;
+  g.lda = K; g.ldb = K; g.ldc = N;
+  g.transA = 0; g.transB = 1;
+  g.alpha = 1.0f;
+  g.drop = make_drop(0.f, 0ull, 0u);
+  g.ldr = N;
+  return g;
+}
+
+int launch_gemm(GemmArgs g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  constexpr int BK = 16;
+  int BM, BN;
+  if (g.N > 64 && g.M > 64) { BM = 128; BN = 128; }
+  else if (g.M >= 128 * 148) { BM = 128; BN = 64; }
+  else { BM = 64; BN = 64; }
+  const int tm = ceil_div(g.M, BM), tn = ceil_div(g.N, BN);
+  int splits = 1;
+  if (g.transA && g.K > 8 * BK) {
+    // weight gradients: tiny [N',K'] output, reduction over every position -> split-K
+    const int want = max(1, (2 * 148) / (tm * tn));
+    splits = min(want, ceil_div(g.K, 8 * BK));
+  }
+  int kps = ceil_div(ceil_div(max(g.K, 1), splits), BK) * BK;
+  splits = ceil_div(max(g.K, 1), kps);
+  g.k_per_split = kps;
+  if (splits > 1) {
+    if (g.bias || g.act || g.R || g.row_mask || g.drop.p > 0.f)
+      return fail(-2, "gemm: epilogue options are not available with split-K");
+    if (!g.accumulate) {
+      if (g.ldc != g.N) return fail(-2, "gemm: split-K needs a dense C");
+      cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.N, stream);
+    }
+  }
+  dim3 grid(tn, tm, splits), block(256);
+  if (BM == 128 && BN == 128) {
+    auto k = gemm_kernel<128, 128, 8, 8>;
+    CARCA_LAUNCH(k, grid, block, 0, stream, g);
+  } else if (BM == 128) {
+    auto k = gemm_kernel<128, 64, 8, 4>;
+    CARCA_LAUNCH(k, grid, block, 0, stream, g);
+  } else {
+    auto k = gemm_kernel<64, 64, 4, 4>;
+    CARCA_LAUNCH(k, grid, block, 0, stream, g);
+  }
+  return check_launch("gemm");
+}
+
+}  // namespace carca

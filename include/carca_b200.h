@@ -1,0 +1,228 @@
+/*
+ * carca_b200.h — C ABI of libcarca_b200.so, the B200 (sm_100a) implementation of CARCA's
+ * forward/backward + candidate-scoring hot path.
+ *
+ * Reference: r-papso/carca-replication.  Every entry point names the reference interface
+ * (file:line, relative to the reference root) it replaces.  The reference is pure Python over
+ * torch ATen ops; the binding a maintainer adds is a ctypes stub, and the
+ * in-tree host mirror of the reference's classes is carca_replication_b200/ (Python).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in `_host`.  Row-major, fp32,
+ *    int32 ids (0 = padding), fp32 0/1 masks — the reference's tensor conventions
+ *    (src/data.py:100-107, src/utils.py:6-7).
+ *  - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work; nothing synchronises
+ *    except the *_host entry points, which say so.
+ *  - Return value: 0 on success, negative on error; carca_last_error() returns the message.
+ *    There is no CPU fallback: without a CUDA device every compute call fails.
+ *  - Dropout uses a counter-based Philox4x32-10 stream keyed by (seed, site, element index)
+ *    so the backward pass regenerates the forward mask (csrc/common.cuh, oracle/philox.py).
+ */
+#ifndef CARCA_B200_H
+#define CARCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARCA_B200_ABI_VERSION 1
+
+const char* carca_last_error(void);
+int carca_abi_version(void);
+
+/* ------------------------------------------------------------------ attribute source */
+enum { CARCA_ATTR_CSR = 0, CARCA_ATTR_TABLE = 1, CARCA_ATTR_DENSE = 2 };
+
+/* Where a position's attribute vector a[p, 0:A] comes from.
+ *  CSR   : item -> sparse row (multi-hot / sparse attributes), device-resident, indexed by id
+ *  TABLE : item -> dense row of `dense` [n_items, A]           (src/data.py:28-35 `attrs`)
+ *  DENSE : `dense` is the per-position tensor [P, A] the reference API passes
+ *          (src/abstract.py:22 `a`, materialised by src/data.py:119-131)                      */
+typedef struct {
+  int kind;
+  const int32_t* csr_rowptr; /* [n_items + 1] */
+  const int32_t* csr_cols;   /* [nnz] in [0, A) */
+  const float* csr_vals;     /* [nnz] */
+  const float* dense;
+} carca_attr_source;
+
+/* ------------------------------------------------------------------ AllEmbedding */
+/* Parameters of AllEmbedding (src/carca.py:67-83), state_dict layout kept:
+ *   items_embed.weight [n_items, d]; feats_embed.weight [g, A+C], bias [g];
+ *   joint_embed.weight [d, d+g], bias [d].                                                   */
+typedef struct {
+  int n_items, d, g, n_attrs, n_ctx;
+  const float* items_embed;
+  const float* feats_w;
+  const float* feats_wT; /* [A+C, g] transposed copy made by carca_transpose (CSR path only) */
+  const float* feats_b;
+  const float* joint_w;
+  const float* joint_b;
+  const float* pos;      /* optional positional table [pos_len, d] added to non-target rows */
+  int pos_len;
+} carca_embed_params;
+
+typedef struct {
+  float* items_embed;
+  float* feats_w;
+  float* feats_b;
+  float* joint_w;
+  float* joint_b;
+  float* pos;            /* optional, [pos_len, d] */
+} carca_embed_grads;
+
+/* dst[c, r] (= | +=) src[r, c] */
+int carca_transpose(float* dst, const float* src, int rows, int cols, int accumulate, void* stream);
+
+/* mask[i] = ids[i] != 0           replaces get_mask, src/utils.py:6-7 */
+int carca_padding_mask(float* mask, const int32_t* ids, int64_t n, void* stream);
+
+/* e[p,:] = mask[p] * ( Wj [ sqrt(d) E[x_p] | Wf [a_p | c_p] + bf ] + bj (+ pos[p % n_cols]) )
+ * replaces AllEmbedding.forward, src/carca.py:85-95.
+ *   x [P] ids, ctx [P, C], mask [P]; P = n_rows * n_cols positions (n_cols = sequence length,
+ *   used only for the positional table); is_target != 0 skips the positional add (:91-92).
+ *   q_out [P, g] receives the attribute/context projection (saved for the backward; required). */
+int carca_embed_fwd(float* e, float* q_out, const carca_embed_params* w, const carca_attr_source* attrs,
+                    const int32_t* x, const float* ctx, const float* mask, int n_rows, int n_cols,
+                    int is_target, void* stream);
+
+/* Accumulates parameter gradients of carca_embed_fwd into `grads` (caller zero-initialises).
+ * de [P, d] is the upstream gradient; scratch_pd [2P, d] and scratch_pg [P, g] are workspaces;
+ * scratch_wT [A, g] (CSR only) must be zero-initialised.  Row 0 of items_embed gets no gradient
+ * (padding_idx=0, src/carca.py:73).                                                         */
+int carca_embed_bwd(const carca_embed_grads* grads, const float* de, const float* q_saved,
+                    const carca_embed_params* w, const carca_attr_source* attrs, const int32_t* x,
+                    const float* ctx, const float* mask, int n_rows, int n_cols, int is_target,
+                    float* scratch_pd, float* scratch_pg, float* scratch_wT, void* stream);
+
+/* ------------------------------------------------------------------ dropout (nn.Dropout) */
+/* y = x * keep/(1-p) with the Philox stream (site, seed); also its own backward (apply to dy).
+ * replaces self.dropout(p_e), src/carca.py:416                                              */
+int carca_dropout(float* y, const float* x, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm */
+/* replaces nn.LayerNorm(d).forward, src/carca.py:298,304,421 (eps 1e-5, affine) */
+int carca_layernorm_fwd(float* y, float* mean, float* rstd, const float* x, const float* gamma,
+                        const float* beta, int rows, int d, void* stream);
+int carca_layernorm_bwd(float* dx, float* dgamma, float* dbeta, const float* dy, const float* x,
+                        const float* mean, const float* rstd, const float* gamma, int rows, int d,
+                        int accumulate_dx, void* stream);
+
+/* ------------------------------------------------------------------ linear layers */
+/* y[M,N] = act(alpha * x[M,K] w[N,K]^T + bias) — nn.Linear / Conv1d(k=1), src/carca.py:238-240,307,311 */
+int carca_linear_fwd(float* y, const float* x, const float* w, const float* bias, int M, int N, int K,
+                     int act_leaky, void* stream);
+/* dx[M,K] (= | +=) dy[M,N] w[N,K] */
+int carca_linear_bwd_input(float* dx, const float* dy, const float* w, int M, int N, int K, int accumulate,
+                           void* stream);
+/* dw[N,K] += dy[M,N]^T x[M,K];  db[N] += colsum(dy)  (db may be NULL) */
+int carca_linear_bwd_weight(float* dw, float* db, const float* dy, const float* x, int M, int N, int K,
+                            void* stream);
+
+/* ------------------------------------------------------------------ attention core */
+/* Masked multi-head attention after the projections; replaces src/carca.py:242-260.
+ *   Q [B,Lq,d], K,V [B,Lk,d], heads = column slices of width d/H, q_mask [B,Lq], k_mask [B,Lk];
+ *   causal_on/diag: tril(diagonal=diag) (0 self, -1 cross-train, off cross-eval; :299,:339);
+ *   W_out optional [B,H,Lq,Lk] = weights after the mask, before dropout (return_w, :262-263).  */
+int carca_attention_fwd(float* O, float* W_out, const float* Q, const float* K, const float* V,
+                        const float* q_mask, const float* k_mask, int B, int H, int Lq, int Lk, int d,
+                        int causal_on, int diag, float p_drop, uint64_t seed, uint32_t site, void* stream);
+int carca_attention_bwd(float* dQ, float* dK, float* dV, const float* dO, const float* Q, const float* K,
+                        const float* V, const float* q_mask, const float* k_mask, int B, int H, int Lq,
+                        int Lk, int d, int causal_on, int diag, float p_drop, uint64_t seed, uint32_t site,
+                        void* stream);
+
+/* ------------------------------------------------------------------ SelfAttentionBlock */
+/* state_dict layout kept (src/carca.py:279-289): norm1/norm2 {weight,bias}[d],
+ * attn.WQ/WK/WV {weight [d,d], bias [d]}, ffn_1/ffn_2 {weight [d,d,1], bias [d]}.          */
+typedef struct {
+  const float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+} carca_block_params;
+typedef struct {
+  float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+} carca_block_grads;
+/* Activations kept for the backward; every buffer is [B*L, d] unless noted. */
+typedef struct {
+  float *qn;          /* LN1(x) */
+  float *mean1, *rstd1; /* [B*L] */
+  float *Q, *K, *V;
+  float *s;           /* attention (+ residual), the LN2 input */
+  float *mean2, *rstd2; /* [B*L] */
+  float *s2;          /* LN2 output */
+  float *a1;          /* dropout(LeakyReLU(ffn_1(s2))) */
+} carca_block_saved;
+
+/* out = SelfAttentionBlock(x, mask); replaces src/carca.py:297-318.
+ * x,out [B,L,d]; mask [B,L]; dropout sites 1+3*block, 2+3*block, 3+3*block when p_drop>0.   */
+int carca_sa_block_fwd(float* out, const carca_block_saved* saved, const float* x, const float* mask,
+                       const carca_block_params* w, int B, int L, int d, int H, int residual, float p_drop,
+                       uint64_t seed, int block_index, void* stream);
+/* dx [B,L,d] (overwritten); parameter grads accumulated into `grads`; scratch: 4 buffers [B*L,d] */
+int carca_sa_block_bwd(float* dx, const carca_block_grads* grads, const float* dout, const float* x,
+                       const float* mask, const carca_block_params* w, const carca_block_saved* saved, int B,
+                       int L, int d, int H, int residual, float p_drop, uint64_t seed, int block_index,
+                       float* scratch4, void* stream);
+
+/* ------------------------------------------------------------------ decoders */
+/* y[b, col0+t] = sigmoid(<p[b, per_position ? t : Lp-1], o[b,t]>); replaces DotProduct.forward,
+ * src/carca.py:358-365 (per_position = self.training).  y has row stride ldy (the concatenated
+ * [B, sum T] output of CARCA.forward, src/carca.py:431).                                     */
+int carca_dot_score_fwd(float* y, const float* p, const float* o, int B, int T, int Lp, int d,
+                        int per_position, int64_t ldy, int col0, void* stream);
+/* d_o overwritten; d_p accumulated (+=) */
+int carca_dot_score_bwd(float* d_o, float* d_p, const float* dy, const float* y, const float* p,
+                        const float* o, int B, int T, int Lp, int d, int per_position, int64_t ldy, int col0,
+                        void* stream);
+
+/* CrossAttentionBlock (src/carca.py:323-336): attn.WQ/WK/WV {weight,bias}, ffn {weight [1,d], bias [1]} */
+typedef struct {
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wf, *bf;
+} carca_cross_params;
+typedef struct {
+  float *wq, *bq, *wk, *bk, *wv, *bv, *wf, *bf;
+} carca_cross_grads;
+typedef struct {
+  float *Q;  /* [B*T, d] */
+  float *K;  /* [B*Lp, d] */
+  float *V;  /* [B*Lp, d] */
+  float *s;  /* [B*T, d] attention (+ residual) */
+} carca_cross_saved;
+
+/* y[b, col0+t] = sigmoid(ffn(MHA(o, p, p) (+ o))); replaces CrossAttentionBlock.forward,
+ * src/carca.py:338-349.  causal -1 when training (:339).  Output is always [B, T]
+ * (the reference's squeeze() collapse for B == 1, :346, is deliberately not reproduced).     */
+int carca_cross_score_fwd(float* y, const carca_cross_saved* saved, const float* o, const float* o_mask,
+                          const float* p, const float* p_mask, const carca_cross_params* w, int B, int T,
+                          int Lp, int d, int H, int residual, int training, float p_drop, uint64_t seed,
+                          uint32_t site, int64_t ldy, int col0, void* stream);
+/* d_o overwritten, d_p accumulated; scratch4: 4 buffers of max(B*T, B*Lp)*d floats */
+int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* grads, const float* dy,
+                          const float* y, const carca_cross_saved* saved, const float* o, const float* o_mask,
+                          const float* p, const float* p_mask, const carca_cross_params* w, int B, int T,
+                          int Lp, int d, int H, int residual, int training, float p_drop, uint64_t seed,
+                          uint32_t site, int64_t ldy, int col0, float* scratch4, void* stream);
+
+/* ------------------------------------------------------------------ loss */
+/* sums[0] += sum(ell * mask), sums[1] += sum(mask); replaces src/carca.py:442-443 numerators.
+ * y_true int32.  Under data parallelism `sums` is all-reduced before finalize.   */
+int carca_bce_sums(float* sums, const float* y_pred, const int32_t* y_true, const float* mask, int64_t n,
+                   float eps, void* stream);
+int carca_bce_finalize(float* loss, const float* sums, void* stream);
+/* dy = grad_out * mask / sums[1] * (-t/(y+eps) + (1-t)/(1-y+eps)) */
+int carca_bce_bwd(float* dy, const float* grad_out, const float* sums, const float* y_pred,
+                  const int32_t* y_true, const float* mask, int64_t n, float eps, void* stream);
+
+/* ------------------------------------------------------------------ ranking metrics */
+/* acc[0] += hits@k, acc[1] += sum 1/log2(rank+2) over labelled candidates with rank < k,
+ * acc[2] += B (fp64 device accumulators); replaces compute_HR / compute_NDCG,
+ * src/train.py:15-32, incl. torch's stable tie order.  first_rank [B] optional (rank of the
+ * first labelled candidate of each row).                                                     */
+int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, const int32_t* y_true, int B,
+                       int T, int64_t ldy, int64_t ldt, int k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARCA_B200_H */

@@ -21,3 +21,23 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def emu_backend(monkeypatch):
+    """Runs the product's Python glue + kernel logic on CPU tensors through tools/emu (a
+    development emulator of the CUDA execution model).  Test-only: the product loader never
+    selects it; this fixture swaps it in by monkeypatching for the duration of one test."""
+    import ctypes
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = mod.build()
+    from carca_replication_b200 import _native as N
+
+    monkeypatch.setattr(N, "_LIB", N.bind(ctypes.CDLL(path)))
+    monkeypatch.setattr(N, "require_device", lambda *t: None)
+    monkeypatch.setattr(N, "stream", lambda: 0)
+    return "cpu"

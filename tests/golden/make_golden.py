@@ -185,13 +185,19 @@ def run_mha_cases(seed):
 
 
 def run_metric_cases(seed):
-    """BCE + HR/NDCG incl. ties with the positive (train.py:15-32, carca.py:441-444)."""
+    """BCE + HR/NDCG incl. ties with the positive (train.py:15-32, carca.py:441-444).
+
+    torch.sort is not stable by default, so the reference's order inside a group of tied scores
+    is implementation-defined (observed here: a 4-way tie that includes the positive does NOT come
+    out in index order).  Parity is therefore "up to ties" (north_star): `HR`/`NDCG` are pinned on
+    tie-free scores, and the tie rule the kernels implement — the STABLE one, ties keep index
+    order, so a positive in column 0 wins — is pinned by `*_stable`, the reference formulas run
+    with sort(stable=True) on rows with small and massive tie groups.
+    """
     rng = np.random.default_rng(seed)
     B, T, k = 64, 101, 10
     y = rng.random((B, T)).astype(np.float32)
     y[:8, 0] = 0.999                      # easy hits
-    y[8:16, 1:4] = y[8:16, 0:1]           # ties with the positive: stable sort favours column 0
-    y[16:20] = 0.5                        # everything tied
     y[20:24, 0] = 0.0                     # positive last
     yt = np.zeros((B, T), np.int32)
     yt[:, 0] = 1
@@ -205,8 +211,19 @@ def run_metric_cases(seed):
     loss.backward()
     out["loss"] = loss.detach().numpy().copy()
     out["dy"] = yv.grad.numpy().copy()
+
+    y2 = y.copy()
+    y2[8:16, 1:4] = y2[8:16, 0:1]         # 4-way ties with the positive
+    y2[16:20] = 0.5                       # every candidate tied
+    y2[24:28, :50] = 0.75                 # 50-way tie that includes the positive
+    _, order = torch.sort(t(y2), descending=True, stable=True)
+    top = torch.gather(t(yt), 1, order)[:, :k]
+    out["y_pred_ties"] = y2
+    out["HR_stable"] = np.array(top.sum().item(), np.float64)
+    out["NDCG_stable"] = np.array((1.0 / torch.log2(torch.nonzero(top)[:, 1] + 2)).sum().item(), np.float64)
     np.savez_compressed(os.path.join(OUT, "metrics_ops.npz"), **out)
-    print(f"metrics_ops: HR {float(out['HR'])} NDCG {float(out['NDCG']):.4f} loss {float(out['loss']):.6f}")
+    print(f"metrics_ops: HR {float(out['HR'])} NDCG {float(out['NDCG']):.4f} loss {float(out['loss']):.6f} "
+          f"HR_stable {float(out['HR_stable'])}")
 
 
 BASE = dict(n_items=120, A=37, C=6, d=64, g=48, H=2, n_blocks=2, L=12, T=21, p=0.0, k=10,

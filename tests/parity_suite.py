@@ -1,0 +1,166 @@
+"""Parity checks shared by the GPU tests (tests/test_gpu_*.py, real kernels on a B200) and the
+CPU emulator tests (tests/test_emu_*.py, same kernels' logic under tools/emu).  `device` is
+"cuda" or "cpu"."""
+import io
+import json
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from helpers import (FP32_RTOL, GOLDEN, batch_of, grad_err, grad_floor, load_case, oracle_cfg, rel_err,
+                     topk_equal_up_to_ties)
+
+import carca_replication_b200 as cb
+from carca_replication_b200 import ops
+
+
+def build_model(cfg, sd, device, p=None):
+    p = cfg["p"] if p is None else p
+    if cfg["encoding"] == "identity":
+        enc = cb.IdentityEncoding()
+    elif cfg["encoding"] == "learnable":
+        enc = cb.LearnableEncoding(cfg["d"], cfg["L"])
+    else:
+        enc = cb.PositionalEncoding(cfg["d"], cfg["L"])
+    emb = cb.AllEmbedding(cfg["n_items"], cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
+    blocks = nn.ModuleList([cb.SelfAttentionBlock(cfg["d"], cfg["H"], p, cfg["residual_sa"])
+                            for _ in range(cfg["n_blocks"])])
+    dec = cb.CrossAttentionBlock(cfg["d"], cfg["H"], p, cfg["residual_ca"]) if cfg["decoder"] == "ca" \
+        else cb.DotProduct()
+    model = cb.CARCA(d=cfg["d"], p=p, emb=emb, enc=blocks, dec=dec)
+    model.load_state_dict(sd, strict=True)          # state_dict keys/shapes == the reference's
+    return model.to(device)
+
+
+def _attr_arg(mode, z, model, a_dense, device):
+    """dense: the reference API tensor; csr/table: device-resident ItemAttrTable + a=None."""
+    if mode == "dense":
+        return a_dense.to(device)
+    table = cb.ItemAttrTable.from_dense(z["attr_table"], sparse=(mode == "csr")).to(device)
+    model.embeds.set_attr_table(table)
+    return None
+
+
+def check_eval(name, device, mode="dense"):
+    cfg, sd, z = load_case(name)
+    model = build_model(cfg, sd, device).eval()
+    p_x, p_a, p_c, o_x, o_a, o_c, y_true = batch_of(z, "eval")
+    pa = _attr_arg(mode, z, model, p_a, device)
+    oa = None if pa is None else o_a.to(device)
+    with torch.no_grad():
+        y = model.forward(profile=(p_x.to(device), pa, p_c.to(device)), targets=[(o_x.to(device), oa, o_c.to(device))])
+        o_mask = cb.get_mask(o_x.to(device))
+        loss = cb.BinaryCrossEntropy().forward(y, y_true.to(device), o_mask)
+        hr = cb.compute_HR(y, y_true.to(device), cfg["k"])
+        ndcg = cb.compute_NDCG(y, y_true.to(device), cfg["k"])
+    ref = z["eval/y_pred"]
+    assert tuple(y.shape) == ref.shape
+    assert rel_err(y.cpu().numpy(), ref) < FP32_RTOL                       # fp32 scores within 1e-4 rel
+    assert topk_equal_up_to_ties(y.cpu().numpy(), ref, cfg["k"], tol=1e-6)  # top-10 identical up to ties
+    assert hr == float(z["eval/HR"])
+    assert round(ndcg, 3) == round(float(z["eval/NDCG"]), 3)
+    assert abs(loss.item() - float(z["eval/loss"])) < 1e-4 * max(1.0, abs(float(z["eval/loss"])))
+
+
+def _train_pass(model, batch, device, mode, z):
+    p_x, p_a, p_c, o_x, o_a, o_c, y_true = batch
+    L = p_x.shape[1]
+    pa = _attr_arg(mode, z, model, p_a, device)
+    o_ad = None if pa is None else o_a.to(device)
+    o_xd, o_cd = o_x.to(device), o_c.to(device)
+    tg = [(o_xd[:, :L], None if o_ad is None else o_ad[:, :L], o_cd[:, :L]),
+          (o_xd[:, L:], None if o_ad is None else o_ad[:, L:], o_cd[:, L:])]
+    model.train()
+    model.zero_grad()
+    y = model.forward(profile=(p_x.to(device), pa, p_c.to(device)), targets=tg)
+    loss = cb.BinaryCrossEntropy().forward(y, y_true.to(device), cb.get_mask(o_xd))
+    loss.backward()
+    return y, loss
+
+
+def check_train(name, device, mode="dense", gtol=2e-4):
+    cfg, sd, z = load_case(name)
+    model = build_model(cfg, sd, device)
+    y, loss = _train_pass(model, batch_of(z, "train"), device, mode, z)
+    assert rel_err(y.detach().cpu().numpy(), z["train/y_pred"]) < FP32_RTOL
+    assert abs(loss.item() - float(z["train/loss"])) < 1e-4 * max(1.0, abs(float(z["train/loss"])))
+    for k, prm in model.named_parameters():
+        ref = z["train/grad/" + k]
+        got = np.zeros_like(ref) if prm.grad is None else prm.grad.cpu().numpy()
+        assert got.shape == ref.shape, k
+        assert grad_err(got, ref, grad_floor(k)) < gtol, (k, grad_err(got, ref, grad_floor(k)))
+    assert float(model.embeds.items_embed.weight.grad[0].abs().max()) == 0.0   # padding_idx row
+
+
+def check_train_dropout(name, device, p=0.3, seed=20240607, mode="dense", gtol=3e-4):
+    """Train step with dropout ON: the oracle replays the kernels' Philox keep/drop decisions."""
+    from oracle import carca_oracle as O
+
+    cfg, sd, z = load_case(name)
+    batch = batch_of(z, "train")
+    oc = oracle_cfg(cfg, p_drop=p, seed=seed)
+    sdo = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k != "embeds.enc.pe") for k, v in sd.items()}
+    y_ref = O.carca_forward(sdo, oc, batch[:3], O.train_step_targets(*batch[3:6]), training=True)
+    loss_ref = O.masked_bce(y_ref, batch[6], O.padding_mask(batch[3]))
+    loss_ref.backward()
+    model = build_model(cfg, sd, device, p=p)
+    ops.set_dropout_seed(seed)
+    try:
+        y, loss = _train_pass(model, batch, device, mode, z)
+    finally:
+        ops.set_dropout_seed(None)
+    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().numpy()) < FP32_RTOL
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    for k, prm in model.named_parameters():
+        ref = sdo[k].grad
+        ref = torch.zeros_like(sdo[k]) if ref is None else ref
+        got = torch.zeros_like(prm) if prm.grad is None else prm.grad
+        e = grad_err(got.cpu().numpy(), ref.numpy(), grad_floor(k))
+        assert e < gtol, (k, e)
+
+
+def check_mha(tag, device):
+    z = np.load(f"{GOLDEN}/mha_ops.npz")
+    c = json.loads(str(z[f"{tag}/cfg"]))
+    mha = cb.MultiHeadAttention(c["d"], c["H"], 0.0)
+    mha.load_state_dict({k[len(tag) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{tag}/sd/")})
+    mha = mha.to(device).eval()
+    q, kv = torch.from_numpy(z[f"{tag}/q"]).to(device), torch.from_numpy(z[f"{tag}/kv"]).to(device)
+    qm, km = torch.from_numpy(z[f"{tag}/q_mask"]).to(device), torch.from_numpy(z[f"{tag}/k_mask"]).to(device)
+    with torch.no_grad():
+        w, o = mha.forward(q, kv, kv, qm, km, causal=c["causal"], return_w=True)
+    np.testing.assert_allclose(w.cpu().numpy(), z[f"{tag}/w"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(o.cpu().numpy(), z[f"{tag}/out"], rtol=1e-4, atol=1e-5)
+    assert np.all(o.cpu().numpy()[0] == 0.0) and np.all(o.cpu().numpy()[1] == 0.0)   # dead rows exactly 0
+
+
+def check_metrics(device):
+    z = np.load(f"{GOLDEN}/metrics_ops.npz")
+    y, yt, m, k = (torch.from_numpy(z["y_pred"]).to(device), torch.from_numpy(z["y_true"]).to(device),
+                   torch.from_numpy(z["mask"]).to(device), int(z["k"]))
+    assert cb.compute_HR(y, yt, k) == float(z["HR"])
+    assert abs(cb.compute_NDCG(y, yt, k) - float(z["NDCG"])) < 1e-4
+    y_ties = torch.from_numpy(z["y_pred_ties"]).to(device)      # massive ties: stable (index-order) rule
+    assert cb.compute_HR(y_ties, yt, k) == float(z["HR_stable"])
+    assert abs(cb.compute_NDCG(y_ties, yt, k) - float(z["NDCG_stable"])) < 1e-4
+    yv = y.clone().requires_grad_(True)
+    loss = cb.BinaryCrossEntropy().forward(yv, yt, m)
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    np.testing.assert_allclose(yv.grad.cpu().numpy(), z["dy"], rtol=1e-4, atol=1e-8)
+
+
+def check_pickle_and_shapes(device):
+    cfg, sd, z = load_case("single_user_ca")
+    model = build_model(cfg, sd, device).eval()
+    buf = io.BytesIO()
+    torch.save(model, buf)                                   # src/train.py:124 pickles the module
+    buf.seek(0)
+    clone = torch.load(buf, weights_only=False)
+    p_x, p_a, p_c, o_x, o_a, o_c, _ = [t.to(device) for t in batch_of(z, "eval")]
+    with torch.no_grad():
+        y1 = model.forward((p_x, p_a, p_c), [(o_x, o_a, o_c)])
+        y2 = clone.forward((p_x, p_a, p_c), [(o_x, o_a, o_c)])
+    assert tuple(y1.shape) == (1, cfg["T"])                  # [B, T] even for B == 1
+    assert torch.equal(y1, y2)

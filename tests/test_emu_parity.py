@@ -1,0 +1,35 @@
+"""CPU-side check of the kernels' logic and the Python/ctypes glue through the development
+emulator (tools/emu).  Small cases only; the real parity gate is tests/test_gpu_parity.py."""
+import pytest
+
+import parity_suite as S
+
+
+@pytest.mark.parametrize("name,mode", [("beauty_ca", "dense"), ("beauty_dot", "csr"), ("men_ca", "table"),
+                                       ("learnable_ca", "csr"), ("noresid_ca", "dense")])
+def test_eval(emu_backend, name, mode):
+    S.check_eval(name, emu_backend, mode)
+
+
+@pytest.mark.parametrize("name,mode", [("beauty_ca", "csr"), ("beauty_dot", "dense"), ("men_ca", "table"),
+                                       ("sinus_dot", "csr"), ("learnable_ca", "dense"), ("noresid_dot", "csr")])
+def test_train(emu_backend, name, mode):
+    S.check_train(name, emu_backend, mode)
+
+
+@pytest.mark.parametrize("name", ["beauty_ca", "beauty_dot"])
+def test_train_dropout(emu_backend, name):
+    S.check_train_dropout(name, emu_backend, mode="csr")
+
+
+@pytest.mark.parametrize("tag", ["self", "cross_eval", "cross_train"])
+def test_mha(emu_backend, tag):
+    S.check_mha(tag, emu_backend)
+
+
+def test_metrics(emu_backend):
+    S.check_metrics(emu_backend)
+
+
+def test_pickle_and_shapes(emu_backend):
+    S.check_pickle_and_shapes(emu_backend)

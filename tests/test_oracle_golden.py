@@ -62,6 +62,7 @@ def test_metrics_and_bce_match_reference():
                    int(z["k"]))
     assert O.hit_count(y, yt, k) == float(z["HR"])
     assert abs(O.ndcg_sum(y, yt, k) - float(z["NDCG"])) < 1e-5
+    assert "HR_stable" in z.files and float(z["HR_stable"]) >= float(z["HR"])
     yv = y.clone().requires_grad_(True)
     loss = O.masked_bce(yv, yt, m)
     loss.backward()
