@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — CARCA hot path on B200: eval users/sec (1 positive + 100 negatives per user,
+forward + BCE + HR@10/NDCG@10), Beauty-shaped synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one evaluate() batch body (src/train.py:42-51) over `--batch` users per GPU.
+  value : users/s with the step's inputs already resident in HBM (device-timed, CUDA events)
+  e2e   : same metric through the public API from pinned HOST buffers: per step the ids/context
+          H2D copies, forward, metrics and the D2H read of the accumulators are inside the timed region
+  roofline / ops : per C-ABI op device time measured live with CUDA events, against MEASURED_PEAKS.json
+  cpu_baseline : the oracle port of the reference timed on this box's host cores (bounded sample)
+  train : fwd + BCE + bwd + Adam step seqs/s at the reference's batch size (256 per GPU)
+`--impl reference` times the reference's CPU path (oracle port, all host threads) on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="beauty", choices=["beauty", "men", "tiny"])
+    ap.add_argument("--decoder", default="ca", choices=["ca", "dot"])
+    ap.add_argument("--batch", type=int, default=8192, help="users per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=256)
+    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--rotate", type=int, default=8, help="distinct input batches cycled through")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if (args.impl == "ours") else "gloo"
+        if args.impl == "ours":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+# --------------------------------------------------------------------------------- reference arm (CPU)
+def dense_batch(table, b):
+    """The dense [B, N, A] attribute tensors the reference API consumes (src/data.py:119-131)."""
+    return (b["p_x"], table.gather_dense(b["p_x"]), b["p_c"], b["o_x"], table.gather_dense(b["o_x"]), b["o_c"],
+            b["y_true"])
+
+
+def oracle_config(shape, decoder):
+    from oracle.carca_oracle import OracleConfig
+
+    return OracleConfig(d=shape.d, n_heads=shape.n_heads, n_blocks=shape.n_blocks, decoder=decoder, p_drop=0.0)
+
+
+def time_cpu_eval(shape, decoder, sd, table, B, steps, warmup):
+    """users/s of the reference's evaluate() body on the host cores (oracle port, all threads)."""
+    from carca_replication_b200 import synth
+    from oracle import carca_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    cfg = oracle_config(shape, decoder)
+    batches = [dense_batch(table, synth.make_eval_batch(shape, B, seed=100 + i)) for i in range(2)]
+    for i in range(warmup):
+        O.eval_batch(sd, cfg, batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.eval_batch(sd, cfg, batches[i % 2])
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps
+
+
+def run_reference(args):
+    from carca_replication_b200 import synth
+
+    rank, world, _ = dist_setup(args)
+    if rank != 0:
+        return
+    shape = synth.SHAPES[args.shape]
+    model = synth.build_model(shape, args.decoder, p=0.5)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    table = synth.make_attr_table(shape)
+    B = args.cpu_batch
+    ups, sec = time_cpu_eval(shape, args.decoder, sd, table, B, args.steps, max(1, min(args.warmup, 2)))
+    cores = os.cpu_count()
+    sample = f"{args.steps} batches of {B} users (dense [B,N,A] attributes pre-materialised, loader excluded)"
+    print(json.dumps({
+        "impl": "reference", "metric": "eval_users_per_sec", "value": ups, "unit": "users/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, shape, B),
+        "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ups, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def workload_config(args, shape, batch):
+    return {"workload": f"{shape.name}-shaped CARCA eval: 1+{shape.n_targets - 1} candidates/user, maxlen "
+                        f"{shape.seq_len}, d={shape.d}, g={shape.g}, H={shape.n_heads}, {shape.n_blocks} blocks, "
+                        f"A={shape.n_attrs} {shape.attr_kind}, C={shape.n_ctx}, decoder={args.decoder}",
+            "users_per_gpu_per_step": batch, "items": shape.n_items, "k": 10}
+
+
+# --------------------------------------------------------------------------------- our arm (B200)
+def run_ours(args):
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import build as B_, ops, synth
+
+    rank, world, local = dist_setup(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    B_.build()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    shape = synth.SHAPES[args.shape]
+    B, K, W = args.batch, args.steps, args.warmup
+    model = synth.build_model(shape, args.decoder, p=0.5)
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    table_cpu = synth.make_attr_table(shape)
+    table = synth.make_attr_table(shape).to(dev)
+    model = model.to(dev).eval()
+    model.embeds.set_attr_table(table)
+    loss_fn = cb.BinaryCrossEntropy()
+
+    names = ("p_x", "p_c", "o_x", "o_c", "y_true")
+    host = [synth.make_eval_batch(shape, B, seed=1000 * rank + i) for i in range(args.rotate)]
+    host = [{k: b[k].pin_memory() for k in names} for b in host]
+    devb = [{k: b[k].to(dev) for k in names} for b in host]
+    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in names)
+
+    acc = torch.zeros(3, dtype=torch.float64, device=dev)
+    loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def step(b):
+        y = model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
+        loss_sum.add_(loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"])))
+        ops.rank_metrics_(acc, y, b["y_true"], 10)
+        return y
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(world)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        # ---- value: inputs resident in HBM
+        for i in range(W):
+            step(devb[i % args.rotate])
+        launches0 = N.lib().carca_launch_count()
+        with ClockSampler(local) as clocks:
+            ms_dev = timed(lambda i: step(devb[i % args.rotate]), K)
+        launches = N.lib().carca_launch_count() - launches0
+        hr_ndcg = (acc / acc[2].clamp(min=1)).tolist()
+
+        # ---- e2e: pinned host buffers -> H2D -> forward -> metrics -> D2H of the accumulators
+        stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        stats_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+
+        def e2e_step(i):
+            hb = host[i % args.rotate]
+            b = {k: hb[k].to(dev, non_blocking=True) for k in names}
+            step(b)
+            stats[:3].copy_(acc)
+            stats[3] = loss_sum
+            stats_host.copy_(stats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller reads the metrics every step
+
+        for i in range(W):
+            e2e_step(i)
+        ms_e2e = timed(e2e_step, K)
+
+        # ---- per-op device time (CUDA events around each C-ABI op), rotating inputs
+        op_ms = op_breakdown(model, loss_fn, devb, acc, shape, args, K)
+
+    users_per_step = B * world
+    value = users_per_step * K / (ms_dev / 1e3)
+    e2e = users_per_step * K / (ms_e2e / 1e3)
+    pk = peaks()
+    roof, ops_table = roofline(op_ms, shape, B, args.decoder, pk)
+
+    out = {
+        "metric": "eval_users_per_sec", "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(workload_config(args, shape, B),
+                                            attrs="device-resident item->attribute table (CSR for multi-hot), "
+                                                  "ids + context per step",
+                                            l2=f"{args.rotate} distinct input batches rotated "
+                                               f"({args.rotate * h2d_bytes / 1e6:.0f} MB) and >1 GB of activations "
+                                               "written per step, both larger than the 126 MB L2"),
+        "e2e": {"value": e2e, "unit": "users/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,
+                "ms_per_step": ms_e2e / K, "api": "CARCA.forward + BinaryCrossEntropy + rank metrics, pinned host "
+                                                  "ids/context in, accumulators out"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
+        "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1],
+    }
+
+    if world == 1 and rank == 0:
+        if not args.no_train:
+            out["train"] = time_train(shape, args, dev, table)
+        if not args.no_cpu_baseline:
+            cb_B = args.cpu_batch
+            ups, sec = time_cpu_eval(shape, args.decoder, sd_cpu, table_cpu, cb_B, 3, 1)
+            out["cpu_baseline"] = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"3 batches of {cb_B} users after 1 warm-up, dense attributes "
+                                             "pre-materialised (reference API), loader excluded",
+                                   "ms_per_batch": sec * 1e3}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def op_breakdown(model, loss_fn, devb, acc, shape, args, K):
+    """Average device ms of each op of one eval step, measured with CUDA events (rotating inputs)."""
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import ops
+
+    stages = ["embed_profile", "encoder_blocks", "final_norm", "embed_targets", "decoder", "bce", "rank_metrics"]
+    ev = {s: [] for s in stages}
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    for i in range(K):
+        b = devb[i % len(devb)]
+        with ops.forward_seed():
+            t = [mark()]
+            p_mask = cb.get_mask(b["p_x"])
+            p_e = model.embeds.forward(b["p_x"], None, b["p_c"], p_mask, False)
+            t.append(mark())
+            for blk in model.encoder:
+                p_e = blk.forward(p_e, p_mask)
+            t.append(mark())
+            p_e = ops.LayerNormFn.apply(p_e, model.norm.weight, model.norm.bias)
+            t.append(mark())
+            o_mask = cb.get_mask(b["o_x"])
+            o_e = model.embeds.forward(b["o_x"], None, b["o_c"], o_mask, True)
+            t.append(mark())
+            y = model.decoder.forward(o_e, o_mask, p_e, p_mask)
+            t.append(mark())
+            loss_fn.forward(y, b["y_true"], o_mask)
+            t.append(mark())
+            ops.rank_metrics_(acc, y, b["y_true"], 10)
+            t.append(mark())
+        torch.cuda.synchronize()
+        for s, a, c in zip(stages, t[:-1], t[1:]):
+            ev[s].append(a.elapsed_time(c))
+    return {s: sum(v) / len(v) for s, v in ev.items()}
+
+
+def roofline(op_ms, shape, B, decoder, pk):
+    """Algorithmic bytes / flops per op (all L positions counted) over measured time."""
+    L, T, d, g, C, nb = shape.seq_len, shape.n_targets, shape.d, shape.g, shape.n_ctx, shape.n_blocks
+    attr_b = 36 if shape.attr_kind == "multihot" else 4 * shape.n_attrs
+    pos_b = 4 + 4 * d + attr_b + 4 * C + 4 * d                       # id + item row + attrs + ctx + e written
+    flops = {
+        "encoder_blocks": nb * (10 * L * d * d + 4 * L * L * d),
+        "decoder": (2 * T * d * d + 4 * L * d * d + 4 * T * L * d + 2 * T * d) if decoder == "ca" else 2 * T * d,
+    }
+    bytes_ = {
+        "embed_profile": L * pos_b, "embed_targets": T * pos_b, "final_norm": 2 * L * d * 4,
+        "bce": T * 12, "rank_metrics": T * 8,
+    }
+    table = {}
+    for op, ms in op_ms.items():
+        row = {"ms": ms}
+        if op in flops:
+            tf = flops[op] * B / (ms * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=tf, unit="TFLOP/s", peak=pk["bf16_tflops_sustained"],
+                       frac=tf / pk["bf16_tflops_sustained"])
+        else:
+            gb = bytes_[op] * B / (ms * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=gb, unit="GB/s", peak=pk["hbm_gbs"], frac=gb / pk["hbm_gbs"])
+        table[op] = row
+    dom = max(op_ms, key=op_ms.get)
+    r = table[dom]
+    roof = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+            "frac": r["frac"], "traffic": None, "peak_source": pk["source"], "share_of_step": op_ms[dom] / sum(op_ms.values())}
+    return roof, table
+
+
+def time_train(shape, args, dev, table):
+    """fwd + BCE + bwd + Adam seqs/s at the reference batch size (src/train.py:84-97), dropout 0.5."""
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import synth
+
+    Bt = args.train_batch
+    model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
+    model.embeds.set_attr_table(table)
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    loss_fn = cb.BinaryCrossEntropy()
+    L = shape.seq_len
+    batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + i).items()} for i in range(4)]
+
+    def one(b):
+        o_x, o_c = b["o_x"], b["o_c"]
+        optim.zero_grad()
+        y = model.forward(profile=(b["p_x"], None, b["p_c"]),
+                          targets=[(o_x[:, :L], None, o_c[:, :L]), (o_x[:, L:], None, o_c[:, L:])])
+        loss = loss_fn.forward(y, b["y_true"], cb.get_mask(o_x))
+        loss.backward()
+        optim.step()
+        return loss
+
+    for i in range(3):
+        one(batches[i % 4])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    n = max(args.steps, 5)
+    e0.record()
+    for i in range(n):
+        loss = one(batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": Bt / (ms * 1e-3), "unit": "seqs/s", "batch_per_gpu": Bt, "ms_per_step": ms,
+            "final_loss": float(loss.item()), "optimizer": "torch.optim.Adam (stock)", "dropout": 0.5}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

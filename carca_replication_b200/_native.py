@@ -61,6 +61,7 @@ P = C.POINTER
 # name -> argtypes (restype is always int unless noted); mirrors include/carca_b200.h one to one
 SIGNATURES = {
     "carca_abi_version": [],
+    "carca_launch_count": [],
     "carca_transpose": [vp, vp, i32, i32, i32, vp],
     "carca_padding_mask": [vp, vp, i64, vp],
     "carca_embed_fwd": [vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32, vp],
@@ -99,6 +100,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.carca_launch_count.restype = C.c_int64
     return lib
 
 

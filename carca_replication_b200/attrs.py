@@ -74,9 +74,14 @@ class ItemAttrTable(nn.Module):
             return self.dense.cpu()[flat].reshape(*ids.shape, self.n_attrs)
         out = torch.zeros((flat.numel(), self.n_attrs), dtype=torch.float32)
         rp, cl, vl = self.rowptr.cpu().long(), self.cols.cpu().long(), self.vals.cpu()
-        for r, it in enumerate(flat.tolist()):
-            s, e = int(rp[it]), int(rp[it + 1])
-            out[r, cl[s:e]] = vl[s:e]
+        starts = rp[flat]
+        counts = rp[flat + 1] - starts
+        total = int(counts.sum())
+        if total:
+            row = torch.repeat_interleave(torch.arange(flat.numel()), counts)
+            within = torch.arange(total) - torch.repeat_interleave(counts.cumsum(0) - counts, counts)
+            src = torch.repeat_interleave(starts, counts) + within
+            out[row, cl[src]] = vl[src]
         return out.reshape(*ids.shape, self.n_attrs)
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:  # pragma: no cover - convenience only

@@ -190,6 +190,7 @@ extern "C" {
 
 const char* carca_last_error(void) { return err_buf(); }
 int carca_abi_version(void) { return CARCA_B200_ABI_VERSION; }
+int64_t carca_launch_count(void) { return (int64_t)launch_count(); }
 
 int carca_transpose(float* dst, const float* src, int rows, int cols, int accumulate, void* stream) {
   return transpose(dst, src, rows, cols, cols, rows, accumulate, S(stream));

@@ -22,7 +22,8 @@ constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default, src/carca.py:279
 // ---- error reporting: entry points return 0 or a negative code; text via carca_last_error()
 char* err_buf();
 int fail(int code, const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what);   // call once after every kernel launch (also counts it)
+long long launch_count();
 
 #define CARCA_REQUIRE(cond, ...)                      \
   do {                                                \

@@ -14,7 +14,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(-3, "%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
   return 0;

@@ -31,6 +31,8 @@ extern "C" {
 
 const char* carca_last_error(void);
 int carca_abi_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+int64_t carca_launch_count(void);
 
 /* ------------------------------------------------------------------ attribute source */
 enum { CARCA_ATTR_CSR = 0, CARCA_ATTR_TABLE = 1, CARCA_ATTR_DENSE = 2 };

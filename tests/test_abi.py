@@ -19,7 +19,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     lib_path = B.build()                      # nvcc cross-compiles for sm_100a without a GPU
     lib = ctypes.CDLL(lib_path)
     names = _declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 20
     for name in names:
         assert hasattr(lib, name), f"{name} declared in carca_b200.h but not exported"
     assert lib.carca_abi_version() == 1
