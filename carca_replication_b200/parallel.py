@@ -1,0 +1,117 @@
+"""Data parallelism over users: one process per GPU, torch.distributed (NCCL over
+NVLink; gloo in the CPU tests) for the only two exchanges the path has:
+
+  * training — ONE all-reduce per step of a flat fp32 bucket holding every parameter gradient,
+    plus the 2-float BCE partial sums so that each rank normalises its loss by the GLOBAL mask
+    count (the reference divides by sum(mask) of the whole batch, src/carca.py:443; per-rank means
+    would weight users differently);
+  * evaluation — ONE all-reduce of the 5 metric accumulators at the end of evaluate().
+
+Users are independent units (nothing in CARCA.forward mixes batch rows), so no other collective
+exists: weights, the item table and the attribute table are replicated.  The reference has no
+counterpart (single device); this wraps the model so the reference-style loop stays unchanged:
+
+    dp = UserDataParallel(model)                 # after dist.init_process_group
+    train(dp.module, dp.shard_loader(...), ..., loss_fn=dp.loss_fn, is_main=dp.rank == 0)
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .carca import BinaryCrossEntropy
+
+
+class ShardedLoader:
+    """Wraps a loader of GLOBAL batches; yields this rank's slice of each (keeps len() for train())."""
+
+    def __init__(self, dp: "UserDataParallel", loader: Iterable):
+        self.dp, self.loader = dp, loader
+
+    def __len__(self) -> int:
+        return len(self.loader)
+
+    def __iter__(self):
+        for batch in self.loader:
+            yield self.dp.shard(batch)
+
+
+class UserDataParallel:
+    def __init__(self, module: torch.nn.Module, process_group=None, broadcast: bool = True):
+        if not dist.is_initialized():
+            raise RuntimeError("UserDataParallel needs torch.distributed to be initialised")
+        self.module = module
+        self.group = process_group
+        self.rank = dist.get_rank(process_group)
+        self.world = dist.get_world_size(process_group)
+        self.params: List[Tensor] = [p for p in module.parameters() if p.requires_grad]
+        self._sizes = [p.numel() for p in self.params]
+        self._bucket: Optional[Tensor] = None
+        self._queued = False
+        self.loss_fn = BinaryCrossEntropy()
+        self.loss_fn.reduce_sums = self._allreduce_sum
+        if broadcast:
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=0, group=process_group)
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    # -------------------------------------------------------------- gradient exchange
+    def _on_grad(self, _param: Tensor) -> None:
+        """First gradient of a backward pass queues the end-of-backward bucket all-reduce."""
+        if not self._queued:
+            self._queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._reduce_grads)
+
+    def _reduce_grads(self) -> None:
+        self._queued = False
+        if self.world == 1:
+            return
+        dev = self.params[0].device
+        if self._bucket is None or self._bucket.device != dev:
+            self._bucket = torch.empty(sum(self._sizes), dtype=torch.float32, device=dev)
+        views = self._bucket.split(self._sizes)
+        for p, v in zip(self.params, views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad.reshape(-1))
+        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM, group=self.group)   # the one collective
+        for p, v in zip(self.params, views):
+            if p.grad is None:
+                p.grad = v.reshape(p.shape).clone()
+            else:
+                p.grad.copy_(v.reshape(p.shape))
+
+    def _allreduce_sum(self, t: Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    # -------------------------------------------------------------- sharding helpers
+    def shard(self, batch: Sequence[Optional[Tensor]]) -> tuple:
+        """This rank's contiguous slice of a global batch (dim 0), B/G users each."""
+        out = []
+        for t in batch:
+            if t is None:
+                out.append(None)
+                continue
+            n = t.shape[0]
+            lo, hi = (n * self.rank) // self.world, (n * (self.rank + 1)) // self.world
+            out.append(t[lo:hi])
+        return tuple(out)
+
+    def shard_loader(self, loader: Iterable) -> "ShardedLoader":
+        return ShardedLoader(self, loader)
+
+    # -------------------------------------------------------------- evaluation
+    def evaluate(self, loader: Iterable, device, k: int, sharded: bool = False):
+        """evaluate() over the global loader: each rank scores its slice of every batch, the
+        accumulators are all-reduced once.  Returns the same triple as src/train.py:35-53 except
+        that the loss is the mean over (rank, batch) pairs."""
+        from .train import evaluate
+
+        it = loader if sharded else self.shard_loader(loader)
+        return evaluate(self.module, it, device, k, reduce_fn=self._allreduce_sum)
