@@ -270,13 +270,14 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, K)
 
         # ---- per-op device time (CUDA events around each C-ABI op), rotating inputs
-        op_ms = op_breakdown(model, loss_fn, devb, acc, shape, args, K)
+        op_ms, op_ms_per_op_path = op_breakdown(model, loss_fn, devb, acc, shape, args, K)
 
     users_per_step = B * world
     value = users_per_step * K / (ms_dev / 1e3)
     e2e = users_per_step * K / (ms_e2e / 1e3)
     pk = peaks()
     roof, ops_table = roofline(op_ms, shape, B, args.decoder, pk)
+    _, per_op_table = roofline(op_ms_per_op_path, shape, B, args.decoder, pk)
 
     out = {
         "metric": "eval_users_per_sec", "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -291,6 +292,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / K, "api": "CARCA.forward + BinaryCrossEntropy + rank metrics, pinned host "
                                                   "ids/context in, accumulators out"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
+        "ops_per_op_path": per_op_table,
         "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1],
     }
 
@@ -309,20 +311,26 @@ def run_ours(args):
 
 
 def op_breakdown(model, loss_fn, devb, acc, shape, args, K):
-    """Average device ms of each op of one eval step, measured with CUDA events (rotating inputs)."""
+    """Average device ms of each op of one eval step, measured with CUDA events (rotating inputs).
+    Returns (stages of the path the step really takes, stages of the per-op path for comparison)."""
     import carca_replication_b200 as cb
     from carca_replication_b200 import ops
-
-    stages = ["embed_profile", "encoder_blocks", "final_norm", "embed_targets", "decoder", "bce", "rank_metrics"]
-    ev = {s: [] for s in stages}
 
     def mark():
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
-    for i in range(K):
-        b = devb[i % len(devb)]
+    def run(stages, body):
+        ev = {s: [] for s in stages}
+        for i in range(K):
+            t = body(devb[i % len(devb)])
+            torch.cuda.synchronize()
+            for s, a, c in zip(stages, t[:-1], t[1:]):
+                ev[s].append(a.elapsed_time(c))
+        return {s: sum(v) / len(v) for s, v in ev.items()}
+
+    def per_op(b):
         with ops.forward_seed():
             t = [mark()]
             p_mask = cb.get_mask(b["p_x"])
@@ -342,10 +350,27 @@ def op_breakdown(model, loss_fn, devb, acc, shape, args, K):
             t.append(mark())
             ops.rank_metrics_(acc, y, b["y_true"], 10)
             t.append(mark())
-        torch.cuda.synchronize()
-        for s, a, c in zip(stages, t[:-1], t[1:]):
-            ev[s].append(a.elapsed_time(c))
-    return {s: sum(v) / len(v) for s, v in ev.items()}
+        return t
+
+    def fused(b):
+        t = [mark()]
+        y = model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
+        t.append(mark())
+        loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+        t.append(mark())
+        ops.rank_metrics_(acc, y, b["y_true"], 10)
+        t.append(mark())
+        return t
+
+    modular = run(["embed_profile", "encoder_blocks", "final_norm", "embed_targets", "decoder", "bce",
+                   "rank_metrics"], per_op)
+    b0 = devb[0]
+    if model._fused_eval_applies((b0["p_x"], None, b0["p_c"]), [(b0["o_x"], None, b0["o_c"])]):
+        return run(["fused_forward", "bce", "rank_metrics"], fused), modular
+    return modular, modular
+
+
+FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 148 SMs x 128 lanes x FMA at 1965 MHz = 74.4
 
 
 def roofline(op_ms, shape, B, decoder, pk):
@@ -353,10 +378,9 @@ def roofline(op_ms, shape, B, decoder, pk):
     L, T, d, g, C, nb = shape.seq_len, shape.n_targets, shape.d, shape.g, shape.n_ctx, shape.n_blocks
     attr_b = 36 if shape.attr_kind == "multihot" else 4 * shape.n_attrs
     pos_b = 4 + 4 * d + attr_b + 4 * C + 4 * d                       # id + item row + attrs + ctx + e written
-    flops = {
-        "encoder_blocks": nb * (10 * L * d * d + 4 * L * L * d),
-        "decoder": (2 * T * d * d + 4 * L * d * d + 4 * T * L * d + 2 * T * d) if decoder == "ca" else 2 * T * d,
-    }
+    enc = nb * (10 * L * d * d + 4 * L * L * d)
+    dec = (2 * T * d * d + 4 * L * d * d + 4 * T * L * d + 2 * T * d) if decoder == "ca" else 2 * T * d
+    flops = {"encoder_blocks": enc, "decoder": dec, "fused_forward": enc + dec + 2 * (L + T) * C * d}
     bytes_ = {
         "embed_profile": L * pos_b, "embed_targets": T * pos_b, "final_norm": 2 * L * d * 4,
         "bce": T * 12, "rank_metrics": T * 8,
@@ -367,7 +391,7 @@ def roofline(op_ms, shape, B, decoder, pk):
         if op in flops:
             tf = flops[op] * B / (ms * 1e-3) / 1e12
             row.update(bound="tensor", achieved=tf, unit="TFLOP/s", peak=pk["bf16_tflops_sustained"],
-                       frac=tf / pk["bf16_tflops_sustained"])
+                       frac=tf / pk["bf16_tflops_sustained"], frac_of_fp32_ffma_peak=tf / FP32_FFMA_PEAK_TFLOPS)
         else:
             gb = bytes_[op] * B / (ms * 1e-3) / 1e9
             row.update(bound="hbm", achieved=gb, unit="GB/s", peak=pk["hbm_gbs"], frac=gb / pk["hbm_gbs"])
@@ -375,7 +399,12 @@ def roofline(op_ms, shape, B, decoder, pk):
     dom = max(op_ms, key=op_ms.get)
     r = table[dom]
     roof = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
-            "frac": r["frac"], "traffic": None, "peak_source": pk["source"], "share_of_step": op_ms[dom] / sum(op_ms.values())}
+            "frac": r["frac"], "traffic": None, "peak_source": pk["source"],
+            "share_of_step": op_ms[dom] / sum(op_ms.values())}
+    if "frac_of_fp32_ffma_peak" in r:
+        roof["note"] = ("fp32 CUDA-core (FFMA) kernel measured against the bf16 tensor peak; against the "
+                        f"{FP32_FFMA_PEAK_TFLOPS:.1f} TFLOP/s fp32 FFMA peak the fraction is "
+                        f"{r['frac_of_fp32_ffma_peak']:.3f}")
     return roof, table
 
 

@@ -56,6 +56,12 @@ class CrossSaved(C.Structure):
     _fields_ = [(n, vp) for n in CROSS_SAVED_NAMES]
 
 
+class ModelParams(C.Structure):
+    _fields_ = [("embed", EmbedParams), ("n_blocks", i32), ("n_heads", i32), ("residual_sa", i32),
+                ("residual_ca", i32), ("decoder_kind", i32), ("blocks", C.POINTER(BlockParams)), ("norm_g", vp),
+                ("norm_b", vp), ("cross", CrossParams)]
+
+
 P = C.POINTER
 
 # name -> argtypes (restype is always int unless noted); mirrors include/carca_b200.h one to one
@@ -89,6 +95,9 @@ SIGNATURES = {
     "carca_bce_finalize": [vp, vp, vp],
     "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
     "carca_rank_metrics": [vp, vp, vp, vp, i32, i32, i64, i64, i32, vp],
+    "carca_eval_plan_floats": [P(ModelParams)],
+    "carca_eval_prepare": [vp, vp, P(ModelParams), P(AttrSource), vp],
+    "carca_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, vp],
 }
 
 
@@ -101,6 +110,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         fn.argtypes = args
         fn.restype = C.c_int
     lib.carca_launch_count.restype = C.c_int64
+    lib.carca_eval_plan_floats.restype = C.c_int64
     return lib
 
 
@@ -132,6 +142,10 @@ def require_device(*tensors: Optional[torch.Tensor]) -> None:
         if t is not None and not t.is_cuda:
             raise RuntimeError("carca_replication_b200 runs on CUDA tensors only (no CPU fallback); "
                                f"got a tensor on {t.device}")
+
+
+def is_device_tensor(t: torch.Tensor) -> bool:
+    return t.is_cuda
 
 
 def stream() -> int:

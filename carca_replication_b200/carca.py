@@ -243,8 +243,30 @@ class CARCA(Model):
         p_e = ops.LayerNormFn.apply(p_e, self.norm.weight, self.norm.bias)
         return p_e, p_mask
 
+    use_fused_eval = True   # class default; set False on an instance to force the per-op path
+
+    def _fused_eval_applies(self, profile, targets) -> bool:
+        """Inference (eval mode, no autograd), device-resident attributes, shape in the fused range."""
+        if self.training or torch.is_grad_enabled() or not self.use_fused_eval or not targets:
+            return False
+        emb = self.embeds
+        if not isinstance(emb, AllEmbedding):
+            return False
+        for a in [profile[1]] + [t[1] for t in targets]:
+            if isinstance(a, Tensor) or (a is None and emb.attr_table is None):
+                return False
+        if any(isinstance(t[1], ItemAttrTable) and t[1] is not (profile[1] or emb.attr_table) for t in targets):
+            return False
+        from . import fused
+        from . import _native
+        return _native.is_device_tensor(profile[0]) and fused.supported(self, profile[0].shape[1],
+                                                                        profile[2].shape[-1])
+
     def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:
+        if self._fused_eval_applies(profile, targets):
+            from . import fused
+            return fused.forward(self, profile, targets)
         with ops.forward_seed():
             p_e, p_mask = self.encode(profile)
             y_preds = []

@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "embed.cuh"
+#include "fused_eval.cuh"
 #include "gemm.cuh"
 #include "layernorm.cuh"
 #include "score.cuh"
@@ -522,6 +523,122 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
   CARCA_LAUNCH(kern, dim3(grid), dim3(256), 0, S(stream), acc, first_rank, y_pred, y_true, B, T, (long long)ldy,
                (long long)ldt, k);
   return check_launch("rank_metrics");
+}
+
+// ------------------------------------------------------------------------------------ fused inference
+namespace {
+struct PlanLayout {
+  long long tfold, mc, blocks, cross, total;
+};
+PlanLayout plan_layout(const carca_model_params* m) {
+  PlanLayout p;
+  const long long d = m->embed.d;
+  p.tfold = 0;
+  p.mc = p.tfold + (long long)m->embed.n_items * d;
+  p.blocks = p.mc + d * 8;
+  p.cross = p.blocks + (long long)m->n_blocks * 5 * d * d;
+  p.total = p.cross + (m->decoder_kind == 1 ? 3 * d * d : 0);
+  return p;
+}
+}  // namespace
+
+int64_t carca_eval_plan_floats(const carca_model_params* m) { return plan_layout(m).total; }
+
+int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* m, const carca_attr_source* at,
+                       void* stream) {
+  cudaStream_t st = S(stream);
+  const carca_embed_params* w = &m->embed;
+  const int n = w->n_items, d = w->d, g = w->g, A = w->n_attrs, C = w->n_ctx;
+  CARCA_REQUIRE(C <= 8, "eval_prepare: at most 8 context features (got %d)", C);
+  const PlanLayout pl = plan_layout(m);
+  float* T = plan + pl.tfold;
+  // q[i] = Wf[:, :A] attrs[i] + bf   (no context: it is folded into Mc)
+  if (at->kind == CARCA_ATTR_CSR) {
+    CARCA_REQUIRE(w->feats_wT != nullptr, "eval_prepare: CSR attributes need feats_wT");
+    auto k = feat_csr_fwd_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(n)), dim3(256), 0, st, scratch_q, (const int*)nullptr, at->csr_rowptr,
+                 at->csr_cols, at->csr_vals, (const float*)nullptr, w->feats_wT, w->feats_b, (const float*)nullptr, n,
+                 g, A, 0);
+    TRY(check_launch("feat_csr_fwd(fold)"));
+  } else if (at->kind == CARCA_ATTR_TABLE) {
+    TRY(linear(scratch_q, at->dense, w->feats_w, w->feats_b, n, g, A, A + C, st, 0, nullptr, nullptr, 0, nullptr,
+               nullptr, A));
+  } else {
+    return fail(-2, "eval_prepare: needs a device-resident attribute table (CSR or TABLE)");
+  }
+  const float sqrt_d = (float)std::sqrt((double)d);
+  TRY(linear(T, w->items_embed, w->joint_w, nullptr, n, d, d, d + g, st, 0, nullptr, nullptr, 0, nullptr, nullptr, d,
+             sqrt_d));
+  TRY(linear(T, scratch_q, w->joint_w + d, w->joint_b, n, d, g, d + g, st, 0, nullptr, nullptr, 1, nullptr, nullptr,
+             g));
+  // Mc[o][c] = sum_j Wj[o][d + j] Wf[j][A + c], stored with row stride 8
+  cudaMemsetAsync(plan + pl.mc, 0, sizeof(float) * d * 8, st);
+  if (C > 0) {
+    GemmArgs gm = gemm_defaults(w->joint_w + d, w->feats_w + A, plan + pl.mc, d, C, g);
+    gm.lda = d + g;
+    gm.transB = 0;
+    gm.ldb = A + C;
+    gm.ldc = 8;
+    TRY(launch_gemm(gm, st));
+  }
+  for (int b = 0; b < m->n_blocks; ++b) {
+    const carca_block_params& bp = m->blocks[b];
+    float* dst = plan + pl.blocks + (long long)b * 5 * d * d;
+    const float* src[5] = {bp.wq, bp.wk, bp.wv, bp.w1, bp.w2};
+    for (int i = 0; i < 5; ++i) TRY(transpose(dst + (long long)i * d * d, src[i], d, d, d, d, 0, st));
+  }
+  if (m->decoder_kind == 1) {
+    float* dst = plan + pl.cross;
+    const float* src[3] = {m->cross.wq, m->cross.wk, m->cross.wv};
+    for (int i = 0; i < 3; ++i) TRY(transpose(dst + (long long)i * d * d, src[i], d, d, d, d, 0, st));
+  }
+  return 0;
+}
+
+int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                       const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                       int T, void* stream) {
+  const int d = m->embed.d, H = m->n_heads;
+  if (d != FD || L > FLP || L < 1 || m->embed.n_ctx > 8 || m->n_blocks > FMAXB || H < 1 ||
+      FD % H != 0 || (FD / H) % 4 != 0)
+    return fail(-4, "eval_forward: fused kernel supports d=64, L<=52, C<=8, <=8 blocks, dh%%4==0 (got d=%d L=%d C=%d "
+                    "blocks=%d H=%d)", d, L, m->embed.n_ctx, m->n_blocks, H);
+  if (B <= 0 || T <= 0) return 0;
+  const PlanLayout pl = plan_layout(m);
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Tfold = plan + pl.tfold;
+  a.Mc = plan + pl.mc;
+  a.pos = m->embed.pos;
+  if (a.pos) CARCA_REQUIRE(L <= m->embed.pos_len, "eval_forward: sequence length %d > positional table %d", L,
+                           m->embed.pos_len);
+  a.p_x = p_x; a.p_c = p_c; a.o_x = o_x; a.o_c = o_c;
+  a.y = y; a.ldy = ldy; a.col0 = col0;
+  a.B = B; a.L = L; a.T = T; a.C = 8; a.H = H;
+  a.n_blocks = m->n_blocks;
+  a.residual_sa = m->residual_sa; a.residual_ca = m->residual_ca; a.decoder = m->decoder_kind;
+  for (int b = 0; b < m->n_blocks; ++b) {
+    const carca_block_params& bp = m->blocks[b];
+    const float* wt = plan + pl.blocks + (long long)b * 5 * d * d;
+    FusedBlockW& f = a.blk[b];
+    f.ln1_g = bp.ln1_g; f.ln1_b = bp.ln1_b; f.ln2_g = bp.ln2_g; f.ln2_b = bp.ln2_b;
+    f.bq = bp.bq; f.bk = bp.bk; f.bv = bp.bv; f.b1 = bp.b1; f.b2 = bp.b2;
+    f.wqT = wt; f.wkT = wt + d * d; f.wvT = wt + 2 * d * d; f.w1T = wt + 3 * d * d; f.w2T = wt + 4 * d * d;
+  }
+  a.fn_g = m->norm_g; a.fn_b = m->norm_b;
+  if (m->decoder_kind == 1) {
+    const float* wt = plan + pl.cross;
+    a.dwqT = wt; a.dwkT = wt + d * d; a.dwvT = wt + 2 * d * d;
+    a.dbq = m->cross.bq; a.dbk = m->cross.bk; a.dbv = m->cross.bv; a.dwf = m->cross.wf; a.dbf = m->cross.bf;
+  }
+  // the kernel indexes Mc with row stride 8 and reads C context values per position
+  a.C = m->embed.n_ctx;
+  const size_t smem = sizeof(FusedSmem);
+  auto k = fused_eval_kernel;
+  TRY(allow_smem(k, smem));
+  const int n_tiles = ceil_div(B, FU);
+  CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(FTHREADS), smem, S(stream), a);
+  return check_launch("fused_eval");
 }
 
 }  // extern "C"

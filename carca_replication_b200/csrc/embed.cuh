@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) feat_csr_fwd_kernel(
     for (int j = lane; j < g; j += kWarp) out[j] = 0.f;
     return;
   }
-  const int item = items[p];
+  const int item = items ? items[p] : p;   // items == null: position p IS item p (table folding)
   const int e0 = rowptr[item], e1 = rowptr[item + 1];
   for (int j0 = 0; j0 < g; j0 += 4 * kWarp) {
     float acc[4];

@@ -1,0 +1,137 @@
+"""Whole-model inference path: carca_eval_prepare + carca_eval_forward (one fused kernel).
+
+Used by CARCA.forward when the model is in eval mode under torch.no_grad(), every sub-module is one
+of this package's classes, attributes come from a device-resident ItemAttrTable and the shape is in
+the fused kernel's range (d = 64, L <= 52, C <= 8, <= 8 blocks).  Anything else keeps the per-op
+entry points.  The "plan" (folded item table + transposed projection weights) is rebuilt only when
+a parameter changes (tracked through tensor versions), e.g. once per evaluate() during training.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+from .attrs import ItemAttrTable
+from .ops import _attr_source, _c, _embed_params, _struct, as_f32, as_ids
+
+_plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+MAX_L, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 8, 8, 64
+
+
+def supported(model, seq_len: int, n_ctx: int) -> bool:
+    from . import carca as M
+
+    emb, dec = model.embeds, model.decoder
+    if not isinstance(emb, M.AllEmbedding) or not hasattr(emb.enc, "table"):
+        return False
+    blocks = list(model.encoder)
+    if not blocks or len(blocks) > MAX_BLOCKS or not all(isinstance(b, M.SelfAttentionBlock) for b in blocks):
+        return False
+    H = blocks[0].attn.H
+    if any(b.attn.H != H or bool(b.residual) != bool(blocks[0].residual) for b in blocks):
+        return False
+    if isinstance(dec, M.CrossAttentionBlock):
+        if dec.attn.H != H:
+            return False
+    elif not isinstance(dec, M.DotProduct):
+        return False
+    d = emb.d
+    return d == WIDTH and seq_len <= MAX_L and n_ctx <= MAX_CTX and d % H == 0 and (d // H) % 4 == 0
+
+
+def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int):
+    """carca_model_params + the Python objects that must stay alive while it is used."""
+    from . import carca as M
+
+    emb = model.embeds
+    E, Wf, bf = _c(emb.items_embed.weight), _c(emb.feats_embed.weight), _c(emb.feats_embed.bias)
+    Wj, bj = _c(emb.joint_embed.weight), _c(emb.joint_embed.bias)
+    A = Wf.shape[1] - n_ctx
+    pos = emb.enc.table(MAX_L)
+    pos = None if pos is None else _c(pos)
+    blocks = list(model.encoder)
+    arr = (N.BlockParams * len(blocks))()
+    keep: List = [E, Wf, bf, Wj, bj, pos, WfT, arr]
+    for i, b in enumerate(blocks):
+        ps = tuple(_c(t) for t in b._params())
+        keep.append(ps)
+        for name, t in zip(N.BLOCK_PARAM_NAMES, ps):
+            setattr(arr[i], name, N.f32p(t))
+    m = N.ModelParams()
+    m.embed = _embed_params(E, Wf, WfT, bf, Wj, bj, pos, A, n_ctx)
+    m.n_blocks, m.n_heads = len(blocks), blocks[0].attn.H
+    m.residual_sa = int(bool(blocks[0].residual))
+    m.blocks = C.cast(arr, C.POINTER(N.BlockParams))
+    ng, nb = _c(model.norm.weight), _c(model.norm.bias)
+    keep += [ng, nb]
+    m.norm_g, m.norm_b = N.f32p(ng), N.f32p(nb)
+    dec = model.decoder
+    if isinstance(dec, M.CrossAttentionBlock):
+        a = dec.attn
+        cp = tuple(_c(t) for t in (a.WQ.weight, a.WQ.bias, a.WK.weight, a.WK.bias, a.WV.weight, a.WV.bias,
+                                   dec.ffn.weight, dec.ffn.bias))
+        keep.append(cp)
+        m.decoder_kind, m.residual_ca = 1, int(bool(dec.residual))
+        m.cross = _struct(N.CrossParams, N.CROSS_PARAM_NAMES, cp)
+    else:
+        m.decoder_kind, m.residual_ca = 0, 0
+    return m, keep
+
+
+def _version_key(model, table: ItemAttrTable) -> Tuple:
+    return (id(table),) + tuple((p.data_ptr(), p._version) for p in model.parameters()) + \
+        tuple((b.data_ptr(), b._version) for b in model.buffers())
+
+
+def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
+    """Inference plan for the model's current weights (cached until a parameter changes)."""
+    key = _version_key(model, table)
+    hit = _plans.get(model)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    emb = model.embeds
+    dev = emb.items_embed.weight.device
+    Wf = _c(emb.feats_embed.weight)
+    g, AC = Wf.shape
+    WfT = None
+    if table.is_sparse:
+        WfT = torch.empty((AC, g), dtype=torch.float32, device=dev)
+        N.call("carca_transpose", N.f32p(WfT), N.f32p(Wf), g, AC, 0, N.stream())
+    m, keep = _model_params(model, table, WfT, n_ctx)
+    n_floats = N.lib().carca_eval_plan_floats(C.byref(m))
+    plan = torch.empty(n_floats, dtype=torch.float32, device=dev)
+    scratch = torch.empty((emb.items_embed.weight.shape[0], g), dtype=torch.float32, device=dev)
+    src = _attr_source(table, None)
+    N.call("carca_eval_prepare", N.f32p(plan), N.f32p(scratch), C.byref(m), C.byref(src), N.stream())
+    del keep
+    _plans[model] = (key, plan)
+    return plan
+
+
+def forward(model, profile, targets: Sequence) -> Tensor:
+    """CARCA.forward in eval mode (src/carca.py:411-431) through the fused kernel -> [B, sum(T)]."""
+    p_x, p_a, p_c = profile
+    table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
+    N.require_device(p_x, p_c)
+    p_x, p_c = as_ids(p_x), as_f32(p_c)
+    B, L = p_x.shape
+    n_ctx = p_c.shape[-1]
+    if len(targets) == 1:
+        o_x, o_c = as_ids(targets[0][0]), as_f32(targets[0][2])
+    else:   # eval-mode decoders score every candidate independently, so tuples simply concatenate
+        o_x = torch.cat([as_ids(t[0]) for t in targets], dim=1)
+        o_c = torch.cat([as_f32(t[2]) for t in targets], dim=1)
+    T = o_x.shape[1]
+    plan = eval_plan(model, table, n_ctx)
+    m, keep = _model_params(model, table, None, n_ctx)
+    y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
+    N.call("carca_eval_forward", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
+           N.i32p(o_x), N.f32p(o_c), B, L, T, N.stream())
+    del keep
+    return y

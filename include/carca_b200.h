@@ -224,6 +224,40 @@ int carca_bce_bwd(float* dy, const float* grad_out, const float* sums, const flo
 int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, const int32_t* y_true, int B,
                        int T, int64_t ldy, int64_t ldt, int k, void* stream);
 
+/* ------------------------------------------------------------------ whole-model inference */
+/* Every parameter of a CARCA model (src/carca.py:401-409) in its state_dict layout.
+ * `blocks` is a HOST array of n_blocks entries; decoder_kind 0 = DotProduct, 1 = CrossAttentionBlock. */
+typedef struct {
+  carca_embed_params embed;
+  int n_blocks, n_heads, residual_sa, residual_ca, decoder_kind;
+  const carca_block_params* blocks;
+  const float *norm_g, *norm_b;
+  carca_cross_params cross;
+} carca_model_params;
+
+/* Size in floats of the inference plan built by carca_eval_prepare. */
+int64_t carca_eval_plan_floats(const carca_model_params* m);
+
+/* Builds the inference plan for the current weights (call again whenever they change):
+ *   - folded item table  T[i] = Wj [ sqrt(d) E[i] | Wf_a attrs[i] + bf ] + bj        [n_items, d]
+ *   - folded context map Mc   = Wj[:, d:] Wf[:, A:]                                   [d, 8]
+ *     so that AllEmbedding.forward (src/carca.py:85-95) becomes e = mask * (T[x] + Mc c (+ pos)),
+ *     an exact re-association of the two bias-only linears (no nonlinearity between them);
+ *   - the projection weights of every block / the decoder transposed to [in, out].
+ * attrs must be CARCA_ATTR_CSR or CARCA_ATTR_TABLE (a device-resident item table).
+ * scratch_q: [n_items, g] floats.                                                            */
+int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* m, const carca_attr_source* attrs,
+                       void* stream);
+
+/* y[b, col0 + t] = CARCA.forward(profile, [targets]) in eval mode (src/carca.py:411-431), one fused
+ * kernel: embedding gather -> encoder blocks -> final LayerNorm -> decoder, activations never
+ * leave the SM.  p_x [B,L], p_c [B,L,C], o_x [B,T], o_c [B,T,C].  Supported: d == 64, L <= 52,
+ * C <= 8, n_blocks <= 8, n_heads in {1,2,4,8,16}; returns -4 (and sets the message) otherwise so
+ * the caller can use the per-op entry points instead.                                         */
+int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                       const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                       int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,4 +40,5 @@ def emu_backend(monkeypatch):
     monkeypatch.setattr(N, "_LIB", N.bind(ctypes.CDLL(path)))
     monkeypatch.setattr(N, "require_device", lambda *t: None)
     monkeypatch.setattr(N, "stream", lambda: 0)
+    monkeypatch.setattr(N, "is_device_tensor", lambda t: True)
     return "cpu"

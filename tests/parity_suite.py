@@ -54,6 +54,25 @@ def check_eval(name, device, mode="dense"):
         loss = cb.BinaryCrossEntropy().forward(y, y_true.to(device), o_mask)
         hr = cb.compute_HR(y, y_true.to(device), cfg["k"])
         ndcg = cb.compute_NDCG(y, y_true.to(device), cfg["k"])
+    if mode != "dense":
+        from carca_replication_b200 import _native as N
+        from carca_replication_b200 import fused
+
+        if fused.supported(model, cfg["L"], cfg["C"]):
+            # second call: plan cached -> the whole forward is exactly one kernel launch
+            n0 = N.lib().carca_launch_count()
+            with torch.no_grad():
+                y_again = model.forward(profile=(p_x.to(device), pa, p_c.to(device)),
+                                        targets=[(o_x.to(device), oa, o_c.to(device))])
+            assert N.lib().carca_launch_count() - n0 == 1
+            assert torch.equal(y, y_again)
+            model.use_fused_eval = False                  # per-op kernels on the same inputs
+            with torch.no_grad():
+                y_mod = model.forward(profile=(p_x.to(device), pa, p_c.to(device)),
+                                      targets=[(o_x.to(device), oa, o_c.to(device))])
+            model.use_fused_eval = True
+            assert N.lib().carca_launch_count() - n0 > 10
+            assert rel_err(y.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL
     ref = z["eval/y_pred"]
     assert tuple(y.shape) == ref.shape
     assert rel_err(y.cpu().numpy(), ref) < FP32_RTOL                       # fp32 scores within 1e-4 rel
@@ -164,3 +183,29 @@ def check_pickle_and_shapes(device):
         y2 = clone.forward((p_x, p_a, p_c), [(o_x, o_a, o_c)])
     assert tuple(y1.shape) == (1, cfg["T"])                  # [B, T] even for B == 1
     assert torch.equal(y1, y2)
+
+
+def check_fused_vs_modular(device, shape_name="tiny", B=5, T=None, decoder="ca", all_valid=False, seed=11):
+    """Fused one-kernel inference vs the per-op kernels on seeded synthetic data (any T, incl.
+    candidate chunks beyond one 104-row tile and a ragged last user tile)."""
+    import dataclasses
+
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import fused, synth
+
+    shape = synth.SHAPES[shape_name]
+    if T is not None:
+        shape = dataclasses.replace(shape, n_targets=T)
+    model = synth.build_model(shape, decoder, p=0.5, seed=seed).to(device).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=seed).to(device))
+    b = {k: v.to(device) for k, v in synth.make_eval_batch(shape, B, seed=seed, all_valid=all_valid).items()}
+    assert fused.supported(model, shape.seq_len, shape.n_ctx)
+    with torch.no_grad():
+        y_f = model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])])
+        model.use_fused_eval = False
+        y_m = model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])])
+        model.use_fused_eval = True
+    assert tuple(y_f.shape) == (B, shape.n_targets)
+    assert rel_err(y_f.cpu().numpy(), y_m.cpu().numpy()) < FP32_RTOL
+    assert topk_equal_up_to_ties(y_f.cpu().numpy(), y_m.cpu().numpy(), 10, tol=1e-6)
+    return y_f

@@ -33,3 +33,12 @@ def test_metrics(emu_backend):
 
 def test_pickle_and_shapes(emu_backend):
     S.check_pickle_and_shapes(emu_backend)
+
+
+@pytest.mark.parametrize("decoder,B,T", [("ca", 3, 230), ("dot", 2, 21), ("ca", 1, 105)])
+def test_fused_eval_vs_per_op_kernels(emu_backend, decoder, B, T):
+    S.check_fused_vs_modular(emu_backend, "tiny", B=B, T=T, decoder=decoder)
+
+
+def test_fused_eval_single_user_fixture(emu_backend):
+    S.check_eval("single_user_ca", emu_backend, "csr")

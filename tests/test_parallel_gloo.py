@@ -35,6 +35,7 @@ def _use_emulator():
     N._LIB = N.bind(ctypes.CDLL(mod.build()))
     N.require_device = lambda *t: None
     N.stream = lambda: 0
+    N.is_device_tensor = lambda t: True
 
 
 def _worker(rank, world, port, name):
