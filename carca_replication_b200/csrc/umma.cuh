@@ -108,6 +108,33 @@ __device__ __forceinline__ void mma_tf32_k(uint32_t d_tmem, uint32_t a_saddr, ui
   }
 }
 
+// Same with the A operand read from TMEM (lane = row, one 32-bit column per k element)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// B operand stored MN-major, no swizzle: [K/8][N/4][8 k][4 n] floats; one K = 8 step is one k group.
+//   sbo = next 16-byte n chunk (128 B), lbo = next k group (N_total * 32 B)
+__host__ __device__ __forceinline__ uint32_t idesc_tf32_bmn(int n) { return idesc_tf32(n) | (1u << 16); }
+
+// ---- registers -> TMEM: this warp's 32 lanes, 8 consecutive columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- TMEM -> registers: this warp's 32 lanes (rows 32*(warp%4) ..), 8 consecutive columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];

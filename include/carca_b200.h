@@ -259,11 +259,12 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
                        int T, void* stream);
 
 /* ------------------------------------------------------------------ tensor-core self test */
-/* C[128,N] = A[128,K] B[N,K]^T on the tcgen05 tensor cores (tf32; split != 0 uses the 3xTF32
- * fp32-grade split), operands staged in shared memory, accumulator in TMEM.  status[0] = 1 if an
+/* C[128,N] = A[128,K] B[N,K]^T on the tcgen05 tensor cores (tf32), accumulator in TMEM.
+ * mode bits: 1 = 3xTF32 fp32-grade split; 2 = A operand read from TMEM (written by tcgen05.st)
+ * instead of shared memory; 4 = B operand stored MN-major instead of K-major.  status[0] = 1 if an
  * mbarrier wait timed out (the kernel never hangs).  N % 16 == 0, K % 8 == 0.  Known-answer test of
  * the primitives in csrc/umma.cuh that the fused kernels build on. */
-int carca_umma_selftest(float* C, const float* A, const float* B, int N, int K, int split, int32_t* status,
+int carca_umma_selftest(float* C, const float* A, const float* B, int N, int K, int mode, int32_t* status,
                         void* stream);
 
 #ifdef __cplusplus
