@@ -126,3 +126,71 @@ extern "C" int carca_umma_selftest(float* C, const float* A, const float* B, int
   return carca::fail(-5, "umma_selftest: tcgen05 is not available under the CPU emulator");
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// Layout probe: the host supplies raw shared-memory images of both operands plus every descriptor
+// field, so operand layouts can be explored from Python without recompiling.
+namespace carca {
+#ifndef CARCA_EMU
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(float* __restrict__ C, const float* __restrict__ a_img,
+                                                            int a_floats, const float* __restrict__ b_img, int b_floats,
+                                                            int N, int ksteps, uint32_t a_lbo, uint32_t a_sbo,
+                                                            uint32_t a_step, uint32_t b_lbo, uint32_t b_sbo,
+                                                            uint32_t b_step, uint32_t idesc, int* __restrict__ status) {
+  CARCA_DYN_SMEM(float, sm);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  float* a_s = sm;
+  float* b_s = sm + ((a_floats + 255) / 256) * 256;
+  const int tid = threadIdx.x, warp = tid / 32;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) umma::mbar_init(&bar, 1);
+  for (int e = tid; e < a_floats; e += 128) a_s[e] = a_img[e];
+  for (int e = tid; e < b_floats; e += 128) b_s[e] = b_img[e];
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    for (int ks = 0; ks < ksteps; ++ks)
+      umma::mma_tf32(tmem, umma::smem_desc(umma::smem_u32(a_s) + ks * a_step, a_lbo, a_sbo),
+                     umma::smem_desc(umma::smem_u32(b_s) + ks * b_step, b_lbo, b_sbo), idesc, ks > 0);
+    umma::commit(&bar);
+  }
+  const bool ok = umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  if (!ok) {
+    if (tid == 0) status[0] = 1;
+  } else {
+    for (int c0 = 0; c0 < N; c0 += 8) {
+      float v[8];
+      umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) C[tid * N + c0 + j] = v[j];
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tmem, 256);
+}
+#endif
+}  // namespace carca
+
+extern "C" int carca_umma_probe(float* C, const float* a_img, int a_floats, const float* b_img, int b_floats, int N,
+                                int ksteps, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_lbo,
+                                uint32_t b_sbo, uint32_t b_step, uint32_t idesc, int32_t* status, void* stream) {
+#ifndef CARCA_EMU
+  using namespace carca;
+  const size_t smem = sizeof(float) * (size_t)(((a_floats + 255) / 256) * 256 + b_floats);
+  if (smem > 200 * 1024) return fail(-2, "umma_probe: images do not fit in shared memory");
+  auto k = umma_probe_kernel;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemsetAsync(status, 0, sizeof(int), reinterpret_cast<cudaStream_t>(stream));
+  k<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(C, a_img, a_floats, b_img, b_floats, N, ksteps, a_lbo, a_sbo,
+                                                              a_step, b_lbo, b_sbo, b_step, idesc, status);
+  return check_launch("umma_probe");
+#else
+  return carca::fail(-5, "umma_probe: tcgen05 is not available under the CPU emulator");
+#endif
+}
