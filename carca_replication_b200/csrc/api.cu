@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "embed.cuh"
 #include "fused_eval.cuh"
+#include "fused_eval_tc.cuh"
 #include "gemm.cuh"
 #include "layernorm.cuh"
 #include "score.cuh"
@@ -528,8 +529,9 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
 // ------------------------------------------------------------------------------------ fused inference
 namespace {
 struct PlanLayout {
-  long long tfold, mc, blocks, cross, total;
+  long long tfold, mc, blocks, cross, tc_blocks, tc_cross, total;
 };
+constexpr long long kTcPacked = 2 * 18 * 64 * 4;   // floats of one packed tensor-core weight (hi | lo)
 PlanLayout plan_layout(const carca_model_params* m) {
   PlanLayout p;
   const long long d = m->embed.d;
@@ -537,7 +539,10 @@ PlanLayout plan_layout(const carca_model_params* m) {
   p.mc = p.tfold + (long long)m->embed.n_items * d;
   p.blocks = p.mc + d * 8;
   p.cross = p.blocks + (long long)m->n_blocks * 5 * d * d;
-  p.total = p.cross + (m->decoder_kind == 1 ? 3 * d * d : 0);
+  p.tc_blocks = p.cross + (m->decoder_kind == 1 ? 3 * d * d : 0);
+  const bool tc = d == 64;   // packed operands of the tcgen05 kernel (fused_eval_tc.cuh)
+  p.tc_cross = p.tc_blocks + (tc ? (long long)m->n_blocks * 5 * kTcPacked : 0);
+  p.total = p.tc_cross + ((tc && m->decoder_kind == 1) ? 3 * kTcPacked : 0);
   return p;
 }
 }  // namespace
@@ -592,26 +597,101 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
     const float* src[3] = {m->cross.wq, m->cross.wk, m->cross.wv};
     for (int i = 0; i < 3; ++i) TRY(transpose(dst + (long long)i * d * d, src[i], d, d, d, d, 0, st));
   }
+#ifndef CARCA_EMU
+  if (d == 64) {   // K-major tf32 operands (hi | lo) with the bias folded in as an extra K step
+    auto pk = pack_weight_tc_kernel;
+    for (int b = 0; b < m->n_blocks; ++b) {
+      const carca_block_params& bp = m->blocks[b];
+      const float* ws[5] = {bp.wq, bp.wk, bp.wv, bp.w1, bp.w2};
+      const float* bs[5] = {bp.bq, bp.bk, bp.bv, bp.b1, bp.b2};
+      for (int i = 0; i < 5; ++i) {
+        CARCA_LAUNCH(pk, dim3(5), dim3(256), 0, st, plan + pl.tc_blocks + ((long long)b * 5 + i) * kTcPacked, ws[i],
+                     bs[i]);
+        TRY(check_launch("pack_weight_tc"));
+      }
+    }
+    if (m->decoder_kind == 1) {
+      const float* ws[3] = {m->cross.wq, m->cross.wk, m->cross.wv};
+      const float* bs[3] = {m->cross.bq, m->cross.bk, m->cross.bv};
+      for (int i = 0; i < 3; ++i) {
+        CARCA_LAUNCH(pk, dim3(5), dim3(256), 0, st, plan + pl.tc_cross + (long long)i * kTcPacked, ws[i], bs[i]);
+        TRY(check_launch("pack_weight_tc"));
+      }
+    }
+  }
+#endif
   return 0;
 }
 
-int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
-                       const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                       int T, void* stream) {
+#ifndef CARCA_EMU
+static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                           const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                           int T, int32_t* status, float* dbg, int dbg_stage, void* stream) {
+  const PlanLayout pl = plan_layout(m);
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Tfold = plan + pl.tfold;
+  a.Mc = plan + pl.mc;
+  a.pos = m->embed.pos;
+  a.p_x = p_x; a.p_c = p_c; a.o_x = o_x; a.o_c = o_c;
+  a.y = y; a.ldy = ldy; a.col0 = col0;
+  a.B = B; a.L = L; a.T = T; a.C = m->embed.n_ctx; a.H = m->n_heads;
+  a.n_blocks = m->n_blocks;
+  a.residual_sa = m->residual_sa; a.residual_ca = m->residual_ca; a.decoder = m->decoder_kind;
+  for (int b = 0; b < m->n_blocks; ++b) {
+    const carca_block_params& bp = m->blocks[b];
+    const float* wt = plan + pl.tc_blocks + (long long)b * 5 * kTcPacked;
+    TcBlockW& f = a.blk[b];
+    f.ln1_g = bp.ln1_g; f.ln1_b = bp.ln1_b; f.ln2_g = bp.ln2_g; f.ln2_b = bp.ln2_b;
+    f.wq = wt; f.wk = wt + kTcPacked; f.wv = wt + 2 * kTcPacked; f.w1 = wt + 3 * kTcPacked; f.w2 = wt + 4 * kTcPacked;
+  }
+  a.fn_g = m->norm_g; a.fn_b = m->norm_b;
+  if (m->decoder_kind == 1) {
+    const float* wt = plan + pl.tc_cross;
+    a.dwq = wt; a.dwk = wt + kTcPacked; a.dwv = wt + 2 * kTcPacked;
+    a.dwf = m->cross.wf; a.dbf = m->cross.bf;
+  }
+  a.status = status;
+  a.dbg = dbg;
+  a.dbg_stage = dbg_stage;
+  const size_t smem = sizeof(TcSmem);
+  auto k = fused_eval_tc_kernel;
+  TRY(allow_smem(k, smem));
+  const int n_tiles = ceil_div(B, 2);
+  CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+  return check_launch("fused_eval_tc");
+}
+#endif
+
+int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream) {
   const int d = m->embed.d, H = m->n_heads;
-  if (d != FD || L > FLP || L < 1 || m->embed.n_ctx > 8 || m->n_blocks > FMAXB || H < 1 ||
-      FD % H != 0 || (FD / H) % 4 != 0)
-    return fail(-4, "eval_forward: fused kernel supports d=64, L<=52, C<=8, <=8 blocks, dh%%4==0 (got d=%d L=%d C=%d "
-                    "blocks=%d H=%d)", d, L, m->embed.n_ctx, m->n_blocks, H);
+  const bool common_ok = d == FD && L >= 1 && m->embed.n_ctx <= 8 && m->n_blocks <= FMAXB && H >= 1 && FD % H == 0;
+  const bool ffma_ok = common_ok && L <= FLP && (FD / H) % 4 == 0;
+#ifndef CARCA_EMU
+  const bool tc_ok = common_ok && L <= 64 && (H == 2 || H == 4) && status != nullptr;
+#else
+  const bool tc_ok = false;
+#endif
+  if (variant == 2 && !tc_ok) return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=64, H in {2,4}, status");
+  if (variant == 1 && !ffma_ok) return fail(-4, "eval_forward: FFMA kernel needs d=64, L<=52, dh%%4==0");
+  if (!ffma_ok && !tc_ok)
+    return fail(-4, "eval_forward: fused kernels support d=64, L<=64, C<=8, <=8 blocks (got d=%d L=%d C=%d blocks=%d "
+                    "H=%d)", d, L, m->embed.n_ctx, m->n_blocks, H);
+  if (m->embed.pos) CARCA_REQUIRE(L <= m->embed.pos_len, "eval_forward: sequence length %d > positional table %d", L,
+                                  m->embed.pos_len);
   if (B <= 0 || T <= 0) return 0;
+#ifndef CARCA_EMU
+  if (variant == 2 || (variant == 0 && tc_ok))
+    return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, stream);
+#endif
   const PlanLayout pl = plan_layout(m);
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.Tfold = plan + pl.tfold;
   a.Mc = plan + pl.mc;
   a.pos = m->embed.pos;
-  if (a.pos) CARCA_REQUIRE(L <= m->embed.pos_len, "eval_forward: sequence length %d > positional table %d", L,
-                           m->embed.pos_len);
   a.p_x = p_x; a.p_c = p_c; a.o_x = o_x; a.o_c = o_c;
   a.y = y; a.ldy = ldy; a.col0 = col0;
   a.B = B; a.L = L; a.T = T; a.C = 8; a.H = H;
@@ -639,6 +719,13 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
   const int n_tiles = ceil_div(B, FU);
   CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(FTHREADS), smem, S(stream), a);
   return check_launch("fused_eval");
+}
+
+int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                       const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                       int T, void* stream) {
+  // FFMA kernel unless the caller supplies a status word (carca_eval_forward_opts) for the tensor-core one
+  return carca_eval_forward_opts(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, 1, nullptr, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -21,7 +21,11 @@ from .ops import _attr_source, _c, _embed_params, _struct, as_f32, as_ids
 
 _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
-MAX_L, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 8, 8, 64
+# kernel variant: 0 = best available (tensor-core kernel when the shape allows), 1 = fp32 FFMA
+# kernel, 2 = tcgen05 tensor-core kernel.  CARCA_FUSED_VARIANT overrides (benchmark comparisons).
+VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "1"))
+
+MAX_L, MAX_L_TC, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 64, 8, 8, 64
 
 
 def supported(model, seq_len: int, n_ctx: int) -> bool:
@@ -42,7 +46,11 @@ def supported(model, seq_len: int, n_ctx: int) -> bool:
     elif not isinstance(dec, M.DotProduct):
         return False
     d = emb.d
-    return d == WIDTH and seq_len <= MAX_L and n_ctx <= MAX_CTX and d % H == 0 and (d // H) % 4 == 0
+    if d != WIDTH or n_ctx > MAX_CTX or d % H != 0:
+        return False
+    ffma = seq_len <= MAX_L and (d // H) % 4 == 0
+    tc = seq_len <= MAX_L_TC and H in (2, 4) and N.is_device_tensor(emb.items_embed.weight)
+    return ffma or tc
 
 
 def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int):
@@ -94,7 +102,7 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
     key = _version_key(model, table)
     hit = _plans.get(model)
     if hit is not None and hit[0] == key:
-        return hit[1]
+        return hit[1], hit[2]
     emb = model.embeds
     dev = emb.items_embed.weight.device
     Wf = _c(emb.feats_embed.weight)
@@ -110,11 +118,19 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
     src = _attr_source(table, None)
     N.call("carca_eval_prepare", N.f32p(plan), N.f32p(scratch), C.byref(m), C.byref(src), N.stream())
     del keep
-    _plans[model] = (key, plan)
-    return plan
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _plans[model] = (key, plan, status)
+    return plan, status
 
 
-def forward(model, profile, targets: Sequence) -> Tensor:
+def mma_timed_out(model) -> bool:
+    """True if a tensor-core completion wait ever timed out for this model's plan (device sync)."""
+    hit = _plans.get(model)
+    return bool(hit is not None and int(hit[2].item()) != 0)
+
+
+def forward(model, profile, targets: Sequence, variant: Optional[int] = None, dbg: Optional[Tensor] = None,
+            dbg_stage: int = 0) -> Tensor:
     """CARCA.forward in eval mode (src/carca.py:411-431) through the fused kernel -> [B, sum(T)]."""
     p_x, p_a, p_c = profile
     table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
@@ -128,10 +144,11 @@ def forward(model, profile, targets: Sequence) -> Tensor:
         o_x = torch.cat([as_ids(t[0]) for t in targets], dim=1)
         o_c = torch.cat([as_f32(t[2]) for t in targets], dim=1)
     T = o_x.shape[1]
-    plan = eval_plan(model, table, n_ctx)
+    plan, status = eval_plan(model, table, n_ctx)
     m, keep = _model_params(model, table, None, n_ctx)
     y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
-    N.call("carca_eval_forward", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
-           N.i32p(o_x), N.f32p(o_c), B, L, T, N.stream())
+    N.call("carca_eval_forward_opts", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
+           N.i32p(o_x), N.f32p(o_c), B, L, T, VARIANT if variant is None else int(variant), N.i32p(status),
+           None if dbg is None else N.f32p(dbg), int(dbg_stage), N.stream())
     del keep
     return y

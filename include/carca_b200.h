@@ -258,6 +258,16 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
                        const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
                        int T, void* stream);
 
+/* Same call with the kernel variant chosen explicitly: 0 = best available, 1 = fp32 FFMA kernel
+ * (L <= 52), 2 = tcgen05 tensor-core kernel (L <= 64, n_heads in {2,4}; activations in TMEM,
+ * 3xTF32 fp32-grade MMAs).  status (device int32[1], required for variant 2) is set to 1 if an
+ * MMA completion wait timed out.  dbg (optional device [128,64]) receives the intermediate
+ * activation `dbg_stage` of the first tile (10*block + {1: LN1, 2: Q, 3: K, 4: V, 5: attention +
+ * residual, 9: block output}, 100: final LayerNorm) for stage-by-stage validation.            */
+int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core self test */
 /* C[128,N] = A[128,K] B[N,K]^T on the tcgen05 tensor cores (tf32), accumulator in TMEM.
  * mode bits: 1 = 3xTF32 fp32-grade split; 2 = A operand read from TMEM (written by tcgen05.st)
@@ -266,6 +276,12 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
  * the primitives in csrc/umma.cuh that the fused kernels build on. */
 int carca_umma_selftest(float* C, const float* A, const float* B, int N, int K, int mode, int32_t* status,
                         void* stream);
+
+/* Layout probe for the same primitives: raw shared-memory images of both operands and every
+ * descriptor field come from the host (tools/probe_umma_layout.py).  Development aid. */
+int carca_umma_probe(float* C, const float* a_img, int a_floats, const float* b_img, int b_floats, int N,
+                     int ksteps, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_lbo, uint32_t b_sbo,
+                     uint32_t b_step, uint32_t idesc, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }
