@@ -23,7 +23,7 @@ _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 # kernel variant: 0 = best available (tensor-core kernel when the shape allows), 1 = fp32 FFMA
 # kernel, 2 = tcgen05 tensor-core kernel.  CARCA_FUSED_VARIANT overrides (benchmark comparisons).
-VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "1"))
+VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "0"))
 
 MAX_L, MAX_L_TC, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 64, 8, 8, 64
 
