@@ -655,10 +655,16 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.dbg = dbg;
   a.dbg_stage = dbg_stage;
   const size_t smem = sizeof(TcSmem);
-  auto k = fused_eval_tc_kernel;
-  TRY(allow_smem(k, smem));
   const int n_tiles = ceil_div(B, 2);
-  CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+  if (m->n_heads == 2) {
+    auto k = fused_eval_tc_kernel<2>;
+    TRY(allow_smem(k, smem));
+    CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+  } else {
+    auto k = fused_eval_tc_kernel<4>;
+    TRY(allow_smem(k, smem));
+    CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+  }
   return check_launch("fused_eval_tc");
 }
 #endif

@@ -1,25 +1,33 @@
-// Tensor-core (tcgen05) version of the fused inference forward for d = 64, L <= 64, heads of
-// width 16 or 32.  Same contract as fused_eval_kernel (fused_eval.cuh); reference path replaced:
+// Tensor-core (tcgen05) version of the fused inference forward for d = 64, L <= 64, 2 or 4 heads.
+// Same contract as fused_eval_kernel (fused_eval.cuh); reference path replaced:
 // CARCA.forward in eval mode, src/carca.py:411-431 with :85-95, :228-265, :297-318, :338-365.
 //
-// Design (per CTA: 2 users = 128 rows, one TMEM lane per row, 256 threads = 2 threads per row,
-// each owning 32 of the 64 feature columns):
-//   * ACTIVATIONS LIVE IN TENSOR MEMORY.  Every [128 x 64] activation is a block of 64 TMEM
-//     columns; LayerNorm, softmax, bias/activation epilogues are thread-local row operations on
-//     registers loaded with tcgen05.ld and written back with tcgen05.st.  Activations never touch
-//     shared memory or HBM.
+// Design (per CTA: 2 users = 128 rows, one TMEM lane per row, 256 threads = 2 threads per row):
+//   * ACTIVATIONS LIVE IN TENSOR MEMORY AND REGISTERS.  Every [128 x 64] MMA operand / accumulator
+//     is a block of 64 TMEM columns; LayerNorm, softmax, bias/activation epilogues are row
+//     operations on registers loaded with one wide tcgen05.ld and written back with tcgen05.st.
+//     Activations never touch shared memory or HBM.
 //   * every projection / QK^T / PV product is a tcgen05.mma with M = 128, the A operand read
 //     straight from TMEM, the B operand (weights, K, V) from shared memory in the K-major
 //     no-swizzle layout of umma.cuh, accumulating into other TMEM columns.
 //   * fp32-grade accuracy on the tf32 tensor cores via the 3xTF32 split (hi*hi + lo*hi + hi*lo);
 //     biases ride along as one extra K step against a constant [1,0,..] column block.
+//   * feature ownership: thread (row, half) owns, for every head h, columns
+//     h*DH + half*DH/2 .. + DH/2 of a 64-wide activation (DH = 64 / heads).  With that split the
+//     per-head attention output lands on the thread that holds the residual, so LN1 -> attention
+//     residual -> LN2 and FFN residual -> next LN1 run register to register.
+//   * the two heads of a pair are processed together: both score MMAs, one softmax phase, both
+//     PV MMAs — two completion waits per pair instead of four.
 //   * shared memory holds only B operands: a 2-slot weight ring (cp.async prefetch), K (64 KB),
-//     V (2 users x 16.6 KB x hi/lo, K-major over keys with a padded chunk stride so the
-//     thread-per-key scalar stores are bank-conflict free).
+//     V (K-major over keys, rows = (head, user, feature), padded chunk stride so the thread-per-key
+//     scalar stores are bank-conflict free), plus the small LayerNorm / context tables.
 // TMEM column map: X_HI 0, X_LO 64, QN_HI 128, QN_LO 192, ACC_Q 256, ACC_K 320, ACC_V 384, ONES 448.
+//   self-attention : scores/P of the pair's heads at 0..127 and 320..447, O at 128.. (+ (h%2)*2*DH)
+//   cross-attention: scores/P_hi at 0..63 / 64..127, P_lo at 320.. / 384.., O at 128 + h*DH
 #pragma once
 #include "common.cuh"
 #include "fused_eval.cuh"
+#include "tmem_io.cuh"
 #include "umma.cuh"
 
 #ifndef CARCA_EMU
@@ -27,8 +35,9 @@ namespace carca {
 
 constexpr int TC_THREADS = 256;
 constexpr int TC_WFLOATS = 18 * 64 * 4;              // packed weight: 16 k-chunks + 2 bias chunks, hi or lo
-constexpr int TC_VLBO = 64 * 16 + 16;                // bytes between key chunks of the V operand (padded)
-constexpr int TC_VUSER = 16 * (TC_VLBO / 4);         // floats per user per hi/lo
+constexpr int TC_VLBO = 128 * 16 + 16;               // bytes between key chunks of the V operand (padded)
+constexpr int TC_VFLOATS = 16 * (TC_VLBO / 4);       // floats of one V image (hi or lo): 16 chunks of 4 keys
+constexpr int TC_LNROWS = 4 * FMAXB + 2;
 enum { C_XHI = 0, C_XLO = 64, C_QNHI = 128, C_QNLO = 192, C_ACCQ = 256, C_ACCK = 320, C_ACCV = 384, C_ONES = 448 };
 
 struct TcBlockW {
@@ -53,111 +62,131 @@ struct TcArgs {
   const float *dwq, *dwk, *dwv;                      // packed decoder projections
   const float *dwf, *dbf;
   int* status;                                       // [0] set to 1 if an MMA wait timed out
-  float* dbg;                                        // optional [128, 64] dump of the stage `dbg_stage`
-  int dbg_stage;
+  float* dbg;                                        // optional [128, 64]: activation `dbg_stage` of tile 0,
+  int dbg_stage;                                     //   or (dbg_stage == -1) phase clock ticks of tile 0
 };
 
 struct TcSmem {
   float w[2][2 * TC_WFLOATS];                        // weight ring: [slot][hi | lo]
   float k_hi[16 * 128 * 4];
   float k_lo[16 * 128 * 4];
-  float v_hi[2 * TC_VUSER];
-  float v_lo[2 * TC_VUSER];
-  float mc[64 * 8];
-  float xch[4][2][128];
+  float v_hi[TC_VFLOATS];
+  float v_lo[TC_VFLOATS];
+  float mct[8][64];                                  // folded context map, [context k][feature]
+  float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
+  float dwf[64];
+  float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
   float plast[2][64];
-  float pmask[128];
-  float tmask[128];
   int pid[128];
-  int tid_[128];
-  uint64_t bar;
+  int oid[128];
+  uint32_t kbits[2][2];                              // valid-key bits: [user][key half]
+  uint64_t bar[2];
   uint32_t tmem_slot;
 };
 
 struct TcCtx {
   TcSmem* s;
-  uint32_t tmem;       // TMEM base
-  uint32_t lane_base;  // this warp's lane quarter << 16
-  int row, half, tid;
-  uint32_t phase;      // mbarrier phase parity
+  uint32_t tmem;       // TMEM base + this warp's lane quarter
+  int row, half, tid, pair_bar;
+  uint32_t nwait;      // completion waits so far (selects barrier and parity)
+  uint32_t ncommit;    // commits so far (meaningful on the issuing thread)
   int xslot;
   int* status;
 };
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t[8];
-    umma::tmem_ld8(taddr + 8 * i, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[8 * i + j] = t[j];
+struct TcTicks { long long* out; int n; };
+__device__ __forceinline__ void tick(TcTicks& t, int label) {
+  if (t.out && t.n < 2000) {
+    t.out[2 * t.n] = label;
+    t.out[2 * t.n + 1] = clock64();
+    ++t.n;
   }
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+
+template <int H>
+struct Own {   // feature ownership of thread (row, half): v[h * N2 + c] <-> feature h*DH + half*N2 + c
+  static constexpr int DH = 64 / H, N2 = DH / 2;
+  __device__ static __forceinline__ int f0(int h, int half) { return h * DH + half * N2; }
+};
+
+template <int H>
+__device__ __forceinline__ void ld_feat(const TcCtx& c, int col, float (&v)[32]) {
+  const uint32_t b = c.tmem + col + c.half * Own<H>::N2;
+  if constexpr (H == 2) umma::tmem_ld_2x16(b, b + 32, v);
+  else umma::tmem_ld_4x8(b, b + 16, b + 32, b + 48, v);
+}
+template <int H>
+__device__ __forceinline__ void st_feat(const TcCtx& c, int col, const float (&v)[32]) {
+  const uint32_t b = c.tmem + col + c.half * Own<H>::N2;
+  if constexpr (H == 2) {
+    umma::tmem_st_x16(b, v, 0);
+    umma::tmem_st_x16(b + 32, v, 16);
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = v[8 * i + j];
-    umma::tmem_st8(taddr + 8 * i, t);
+    for (int h = 0; h < 4; ++h) umma::tmem_st_x8(b + 16 * h, v, 8 * h);
   }
 }
-// store a half row as a tf32 operand pair: hi = the fp32 value, lo = its tf32 remainder
+// store as a tf32 operand pair: hi = the fp32 value (the tensor core reads its top 19 bits),
+// lo = the remainder
+template <int H>
 __device__ __forceinline__ void st_operand(const TcCtx& c, int col_hi, int col_lo, const float (&v)[32]) {
   float lo[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) lo[j] = umma::tf32_lo(v[j]);
-  tmem_st32(c.tmem + c.lane_base + col_hi + 32 * c.half, v);
-  tmem_st32(c.tmem + c.lane_base + col_lo + 32 * c.half, lo);
-}
-__device__ __forceinline__ void ld_half(const TcCtx& c, int col, float (&v)[32]) {
-  tmem_ld32(c.tmem + c.lane_base + col + 32 * c.half, v);
+  st_feat<H>(c, col_hi, v);
+  st_feat<H>(c, col_lo, lo);
 }
 
 // all TMEM / shared-memory writes of every thread become visible to the MMA issued afterwards
-__device__ __forceinline__ void publish(TcCtx& c) {
+__device__ __forceinline__ void publish() {
   umma::tmem_st_wait();
   umma::fence_smem_to_async();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
 }
-// the issuing thread commits; everyone waits for the MMAs to land in TMEM
-__device__ __forceinline__ void commit_and_wait(TcCtx& c) {
-  if (c.tid == 0) umma::commit(&c.s->bar);
-  if (!umma::mbar_wait(&c.s->bar, c.phase & 1u)) c.status[0] = 1;
-  c.phase++;
+// Completion tracking: commits alternate between two mbarriers so that a barrier is re-armed only
+// after a CTA-wide sync that every thread reaches past its previous wait on it.
+__device__ __forceinline__ void commit(TcCtx& c) {   // issuing thread only
+  umma::commit(&c.s->bar[c.ncommit & 1u]);
+  c.ncommit++;
+}
+__device__ __forceinline__ void wait_mma(TcCtx& c) {
+  const uint32_t n = c.nwait++;
+  if (!umma::mbar_wait(&c.s->bar[n & 1u], (n >> 1) & 1u)) c.status[0] = 1;
   umma::fence_after_sync();
 }
-// combine a per-row partial of the two half-row threads (sum or max)
-template <bool MAX>
-__device__ __forceinline__ float row_combine(TcCtx& c, float v) {
-  float* x = &c.s->xch[c.xslot][0][0];
-  x[c.half * 128 + c.row] = v;
-  __syncthreads();
-  const float o = x[(c.half ^ 1) * 128 + c.row];
-  c.xslot = (c.xslot + 1) & 3;
-  return MAX ? fmaxf(v, o) : v + o;
+// the two threads of a row swap a pair of partial results (64-thread named barrier per warp pair)
+__device__ __forceinline__ float2 pair_exchange(TcCtx& c, float2 mine) {
+  float2* x = &c.s->xch[c.xslot][0][0];
+  x[c.half * 128 + c.row] = mine;
+  asm volatile("bar.sync %0, 64;" ::"r"(c.pair_bar) : "memory");
+  const float2 o = x[(c.half ^ 1) * 128 + c.row];
+  c.xslot ^= 1;
+  return o;
 }
 
 // ---- MMA issue helpers (one thread) ---------------------------------------------------------
-// D[d_col .. d_col+N) (=) A(tmem, K cols at a_hi/a_lo) x B(smem hi/lo)^T, 3xTF32
-__device__ __forceinline__ void issue_3x(uint32_t tmem, int d_col, int a_hi, int a_lo, uint32_t b_hi, uint32_t b_lo,
-                                         int N, int K, uint32_t b_lbo, bool first) {
+// D[d .. d+N) (=) A(tmem, 8*ksteps cols at a_hi / a_lo) x B(smem hi / lo)^T, 3xTF32
+__device__ __forceinline__ void issue_3x(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int N,
+                                         int ksteps, uint32_t b_lbo, bool first) {
   const uint32_t idesc = umma::idesc_tf32(N);
+  const uint64_t dhi = umma::smem_desc(b_hi, b_lbo, 128), dlo = umma::smem_desc(b_lo, b_lbo, 128);
+  const uint64_t step = (uint64_t)((2u * b_lbo) >> 4);
+#pragma unroll 1
   for (int p = 0; p < 3; ++p) {
-    const int a = (p == 1) ? a_lo : a_hi;
-    const uint32_t b = (p == 2) ? b_lo : b_hi;
-    for (int ks = 0; ks < K / 8; ++ks)
-      umma::mma_tf32_ts(tmem + d_col, tmem + a + 8 * ks, umma::smem_desc(b + ks * 2 * b_lbo, b_lbo, 128), idesc,
-                        !(first && p == 0 && ks == 0));
+    const uint32_t a = (p == 1) ? a_lo : a_hi;
+    const uint64_t b = (p == 2) ? dlo : dhi;
+#pragma unroll 1
+    for (int ks = 0; ks < ksteps; ++ks)
+      umma::mma_tf32_ts(d, a + 8 * ks, b + ks * step, idesc, !(first && p == 0 && ks == 0));
   }
 }
 // projection with a packed weight (bias folded in as K step 8 against the ONES block)
 __device__ __forceinline__ void issue_proj(uint32_t tmem, int d_col, int a_hi, int a_lo, const float* w_slot) {
   const uint32_t b_hi = umma::smem_u32(w_slot), b_lo = umma::smem_u32(w_slot + TC_WFLOATS);
   const uint32_t lbo = 64 * 16;
-  issue_3x(tmem, d_col, a_hi, a_lo, b_hi, b_lo, 64, 64, lbo, true);
+  issue_3x(tmem + d_col, tmem + a_hi, tmem + a_lo, b_hi, b_lo, 64, 8, lbo, true);
   const uint32_t idesc = umma::idesc_tf32(64);
   umma::mma_tf32_ts(tmem + d_col, tmem + C_ONES, umma::smem_desc(b_hi + 16 * lbo, lbo, 128), idesc, true);
   umma::mma_tf32_ts(tmem + d_col, tmem + C_ONES, umma::smem_desc(b_lo + 16 * lbo, lbo, 128), idesc, true);
@@ -166,149 +195,215 @@ __device__ __forceinline__ void issue_proj(uint32_t tmem, int d_col, int a_hi, i
 // ---- weight ring: cp.async global -> shared, 36,864 bytes per packed weight ---------------------
 __device__ __forceinline__ void weight_prefetch(TcCtx& c, int slot, const float* __restrict__ w) {
   const uint32_t dst = umma::smem_u32(c.s->w[slot]);
+#pragma unroll 1
   for (int i = c.tid; i < 2 * TC_WFLOATS / 4; i += TC_THREADS)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(w + i * 4) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void weight_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void weight_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-// LayerNorm of the half rows held in v (two-pass, as torch), gamma/beta from global
-__device__ __forceinline__ void layernorm_rows(TcCtx& c, float (&v)[32], const float* __restrict__ g,
-                                               const float* __restrict__ b) {
+// LayerNorm of the row whose 64 features are split over the two threads of the pair: local two-pass
+// statistics combined with Chan's formula (one exchange); gamma/beta rows in shared memory
+template <int H>
+__device__ __forceinline__ void layernorm_rows(TcCtx& c, float (&v)[32], const float* g, const float* b) {
+  constexpr int N2 = Own<H>::N2;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) s += v[j];
-  const float mean = row_combine<false>(c, s) / 64.0f;
-  float q = 0.f;
+  const float ml = s * (1.0f / 32.0f);
+  float m2 = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const float d = v[j] - mean;
-    q = fmaf(d, d, q);
+    const float d = v[j] - ml;
+    m2 = fmaf(d, d, m2);
   }
-  const float rstd = 1.0f / sqrtf(row_combine<false>(c, q) / 64.0f + kLnEps);
+  const float2 o = pair_exchange(c, make_float2(s, m2));
+  const float mean = (s + o.x) * (1.0f / 64.0f);
+  const float dl = (s - o.x) * (1.0f / 32.0f);
+  const float var = (m2 + o.y + 16.0f * dl * dl) * (1.0f / 64.0f);
+  const float rstd = 1.0f / sqrtf(var + kLnEps);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * __ldg(g + 32 * c.half + j) + __ldg(b + 32 * c.half + j);
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2 / 4; ++q) {
+      const int f = Own<H>::f0(h, c.half) + 4 * q;
+      const float4 gg = *reinterpret_cast<const float4*>(g + f);
+      const float4 bb = *reinterpret_cast<const float4*>(b + f);
+      float* x = &v[h * N2 + 4 * q];
+      x[0] = (x[0] - mean) * rstd * gg.x + bb.x;
+      x[1] = (x[1] - mean) * rstd * gg.y + bb.y;
+      x[2] = (x[2] - mean) * rstd * gg.z + bb.z;
+      x[3] = (x[3] - mean) * rstd * gg.w + bb.w;
+    }
 }
 
-// e = mask * (Tfold[id] + Mc ctx (+ pos)) for this thread's half row
-__device__ __forceinline__ void embed_row(const TcArgs& a, const TcCtx& c, int id, float m, const float* ctx,
-                                          const float* pos_row, float (&v)[32]) {
-  if (m == 0.f) {
+// e = mask * (Tfold[id] + Mc ctx (+ pos)) for this thread's features
+template <int H>
+__device__ __forceinline__ void embed_row(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ ctx,
+                                          const float* __restrict__ pos_row, float (&v)[32]) {
+  constexpr int N2 = Own<H>::N2;
+  if (id == 0) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     return;
   }
-  const float4* t = reinterpret_cast<const float4*>(a.Tfold + (long long)id * 64 + 32 * c.half);
+  float cv[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 x = __ldg(t + i);
-    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-  }
-  for (int k = 0; k < a.C; ++k) {
-    const float cv = ctx[k];
+  for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? __ldg(ctx + k) : 0.f;
+  const float* t = a.Tfold + (long long)id * 64;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaf(c.s->mc[(32 * c.half + j) * 8 + k], cv, v[j]);
-  }
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2 / 4; ++q) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(t + Own<H>::f0(h, c.half) + 4 * q));
+      float* o = &v[h * N2 + 4 * q];
+      o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    }
   if (pos_row) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += pos_row[32 * c.half + j];
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int q = 0; q < N2 / 4; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(pos_row + Own<H>::f0(h, c.half) + 4 * q));
+        float* o = &v[h * N2 + 4 * q];
+        o[0] += x.x; o[1] += x.y; o[2] += x.z; o[3] += x.w;
+      }
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= m;
-}
-
-__device__ __forceinline__ void dump_stage(const TcArgs& a, TcCtx& c, int stage, int col) {
-  if (a.dbg && a.dbg_stage == stage && blockIdx.x == 0) {
-    float v[32];
-    ld_half(c, col, v);
+  for (int k = 0; k < 8; ++k) {
+    if (k < a.C) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a.dbg[c.row * 64 + 32 * c.half + j] = v[j];
-  }
-}
-
-// K operand: this thread's half row of the accumulator at `col` -> shared K-major chunks (hi/lo)
-__device__ __forceinline__ void store_k_operand(TcCtx& c, int col) {
-  float v[32];
-  ld_half(c, col, v);
+      for (int h = 0; h < H; ++h)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int kc = 8 * c.half + i;
-    const float4 hi = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    const float4 lo = make_float4(umma::tf32_lo(hi.x), umma::tf32_lo(hi.y), umma::tf32_lo(hi.z), umma::tf32_lo(hi.w));
-    reinterpret_cast<float4*>(c.s->k_hi)[kc * 128 + c.row] = hi;
-    reinterpret_cast<float4*>(c.s->k_lo)[kc * 128 + c.row] = lo;
-  }
-}
-// V operand: K-major over keys, [user][key/4][feature][key%4] with the padded chunk stride
-__device__ __forceinline__ void store_v_operand(TcCtx& c, int col) {
-  float v[32];
-  ld_half(c, col, v);
-  const int u = c.row / 64, j = c.row % 64;
-  float* hi = c.s->v_hi + u * TC_VUSER + (j / 4) * (TC_VLBO / 4) + (j % 4);
-  float* lo = c.s->v_lo + u * TC_VUSER + (j / 4) * (TC_VLBO / 4) + (j % 4);
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    const int f = 32 * c.half + t;
-    hi[f * 4] = v[t];
-    lo[f * 4] = umma::tf32_lo(v[t]);
-  }
-}
-
-// One attention head.  Queries: the 128 tile rows (ACC_Q hi / QN_LO lo, head columns h*dh..).
-//   SELF : keys of both users (N = 128), row m uses its own user's 64 score columns, causal.
-//   CROSS: keys of user `ku` only (N = 64), no causal mask, query mask = tmask.
-// P overwrites the score columns region-locally; O_h lands at o_col (+ user * dh for SELF).
-template <bool CROSS>
-__device__ __forceinline__ void attention_head_tc(const TcArgs& a, TcCtx& c, int h, int dh, int ku, int s_col,
-                                                  int p_hi_col, int p_lo_col, int o_col, float sqrt_dh) {
-  TcSmem& s = *c.s;
-  const int L = a.L;
-  // ---- scores
-  if (c.tid == 0) {
-    const uint32_t koff = (uint32_t)(h * dh / 4) * 2048u + (CROSS ? (uint32_t)ku * 64u * 16u : 0u);
-    issue_3x(c.tmem, s_col, C_ACCQ + h * dh, C_QNLO + h * dh, umma::smem_u32(s.k_hi) + koff,
-             umma::smem_u32(s.k_lo) + koff, CROSS ? 64 : 128, dh, 2048u, true);
-  }
-  commit_and_wait(c);
-  // ---- masked softmax over this row's 64 keys, 32 per thread
-  const int u = CROSS ? ku : c.row / 64;
-  const int i = c.row % 64;
-  float v[32];
-  tmem_ld32(c.tmem + c.lane_base + s_col + (CROSS ? 0 : 64 * (c.row / 64)) + 32 * c.half, v);
-  const float qm = CROSS ? s.tmask[c.row] : s.pmask[c.row];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    const int j = 32 * c.half + t;
-    const bool ok = qm != 0.f && j < L && s.pmask[u * 64 + j] != 0.f && (CROSS || j <= i);
-    v[t] = ok ? v[t] / sqrt_dh : -INFINITY;
-    mx = fmaxf(mx, v[t]);
-  }
-  mx = row_combine<true>(c, mx);
-  float sum = 0.f;
-#pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    v[t] = (v[t] == -INFINITY) ? 0.f : expf(v[t] - mx);
-    sum += v[t];
-  }
-  sum = row_combine<false>(c, sum);
-  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-#pragma unroll
-  for (int t = 0; t < 32; ++t) v[t] *= inv;
-  st_operand(c, p_hi_col, p_lo_col, v);
-  publish(c);
-  // ---- O_h = P V_h  (SELF: once per user's V; each row later picks its own user's result)
-  if (c.tid == 0) {
-    for (int vu = CROSS ? ku : 0; vu <= (CROSS ? ku : 1); ++vu) {
-      const uint32_t voff = (uint32_t)(vu * TC_VUSER) * 4u + (uint32_t)(h * dh) * 16u;
-      issue_3x(c.tmem, o_col + (CROSS ? 0 : vu * dh), p_hi_col, p_lo_col, umma::smem_u32(s.v_hi) + voff,
-               umma::smem_u32(s.v_lo) + voff, dh, 64, (uint32_t)TC_VLBO, true);
+        for (int q = 0; q < N2 / 4; ++q) {
+          const float4 m = *reinterpret_cast<const float4*>(&c.s->mct[k][Own<H>::f0(h, c.half) + 4 * q]);
+          float* o = &v[h * N2 + 4 * q];
+          o[0] = fmaf(m.x, cv[k], o[0]); o[1] = fmaf(m.y, cv[k], o[1]);
+          o[2] = fmaf(m.z, cv[k], o[2]); o[3] = fmaf(m.w, cv[k], o[3]);
+        }
     }
   }
-  commit_and_wait(c);
 }
 
+template <int H>
+__device__ __forceinline__ void dump_regs(const TcArgs& a, const TcCtx& c, bool on, int stage, const float (&v)[32]) {
+  if (on && a.dbg_stage == stage) {
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int q = 0; q < Own<H>::N2; ++q) a.dbg[c.row * 64 + Own<H>::f0(h, c.half) + q] = v[h * Own<H>::N2 + q];
+  }
+}
+template <int H>
+__device__ __forceinline__ void dump_tmem(const TcArgs& a, const TcCtx& c, bool on, int stage, int col) {
+  if (on && a.dbg_stage == stage) {
+    float v[32];
+    ld_feat<H>(c, col, v);
+    dump_regs<H>(a, c, true, stage, v);
+  }
+}
+
+// K operand: this thread's features of the accumulator at `col` -> shared K-major chunks (hi/lo)
+template <int H>
+__device__ __forceinline__ void store_k_operand(TcCtx& c, int col) {
+  constexpr int N2 = Own<H>::N2;
+  float v[32];
+  ld_feat<H>(c, col, v);
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2 / 4; ++q) {
+      const int kc = Own<H>::f0(h, c.half) / 4 + q;
+      const float* x = &v[h * N2 + 4 * q];
+      const float4 hi = make_float4(x[0], x[1], x[2], x[3]);
+      const float4 lo = make_float4(umma::tf32_lo(hi.x), umma::tf32_lo(hi.y), umma::tf32_lo(hi.z), umma::tf32_lo(hi.w));
+      reinterpret_cast<float4*>(c.s->k_hi)[kc * 128 + c.row] = hi;
+      reinterpret_cast<float4*>(c.s->k_lo)[kc * 128 + c.row] = lo;
+    }
+}
+// V operand: K-major over keys, [key / 4][(head, user, feature in head)][key % 4], padded chunk stride
+template <int H>
+__device__ __forceinline__ void store_v_operand(TcCtx& c, int col) {
+  constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
+  float v[32];
+  ld_feat<H>(c, col, v);
+  const int u = c.row / 64, j = c.row % 64;
+  const int base = (j / 4) * (TC_VLBO / 4) + (j % 4);
+  float* hi = c.s->v_hi + base;
+  float* lo = c.s->v_lo + base;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2; ++q) {
+      const int r = h * 2 * DH + u * DH + c.half * N2 + q;
+      const float x = v[h * N2 + q];
+      hi[r * 4] = x;
+      lo[r * 4] = umma::tf32_lo(x);
+    }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Masked softmax of this thread's 32 key columns for the two heads of a pair, result stored as the
+// tf32 operand pair P.  bits: allowed keys; sc = log2(e) / sqrt(dh) (scores are scaled AFTER the
+// additive mask in the reference, src/carca.py:253-254: a masked key stays at -inf either way, and a
+// fully masked row is exactly 0, :256).
+__device__ __forceinline__ void softmax_pair(TcCtx& c, uint32_t bits, float sc, uint32_t s0, uint32_t s1, uint32_t p0hi,
+                                             uint32_t p0lo, uint32_t p1hi, uint32_t p1lo) {
+  float v0[32], v1[32];
+  umma::tmem_ld_1x32(s0, v0);
+  umma::tmem_ld_1x32(s1, v1);
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const bool ok = (bits >> t) & 1u;
+    v0[t] = ok ? v0[t] * sc : -INFINITY;
+    v1[t] = ok ? v1[t] * sc : -INFINITY;
+    m0 = fmaxf(m0, v0[t]);
+    m1 = fmaxf(m1, v1[t]);
+  }
+  float2 o = pair_exchange(c, make_float2(m0, m1));
+  m0 = fmaxf(m0, o.x);
+  m1 = fmaxf(m1, o.y);
+  m0 = (m0 == -INFINITY) ? 0.f : m0;
+  m1 = (m1 == -INFINITY) ? 0.f : m1;
+  float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    v0[t] = ex2_approx(v0[t] - m0);
+    v1[t] = ex2_approx(v1[t] - m1);
+    z0 += v0[t];
+    z1 += v1[t];
+  }
+  o = pair_exchange(c, make_float2(z0, z1));
+  z0 += o.x;
+  z1 += o.y;
+  const float i0 = z0 > 0.f ? 1.0f / z0 : 0.f, i1 = z1 > 0.f ? 1.0f / z1 : 0.f;
+  float lo[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    v0[t] *= i0;
+    lo[t] = umma::tf32_lo(v0[t]);
+  }
+  umma::tmem_st_x32(p0hi, v0, 0);
+  umma::tmem_st_x32(p0lo, lo, 0);
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    v1[t] *= i1;
+    lo[t] = umma::tf32_lo(v1[t]);
+  }
+  umma::tmem_st_x32(p1hi, v1, 0);
+  umma::tmem_st_x32(p1lo, lo, 0);
+}
+
+template <int H>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
+  constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
   CARCA_DYN_SMEM(unsigned char, raw);
   TcSmem& s = *reinterpret_cast<TcSmem*>(raw);
   TcCtx c;
@@ -317,127 +412,213 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   const int w = c.tid / 32;
   c.row = 32 * (w % 4) + (c.tid % 32);
   c.half = w / 4;
-  c.lane_base = (uint32_t)(32 * (w % 4)) << 16;
-  c.phase = 0;
+  c.pair_bar = 1 + (w % 4);
+  c.nwait = 0;
+  c.ncommit = 0;
   c.xslot = 0;
   c.status = a.status;
-  const int L = a.L, dh = 64 / a.H;
-  const float sqrt_dh = sqrtf((float)dh);
+  const int L = a.L;
+  const float sc = 1.4426950408889634f / sqrtf((float)DH);
+  const bool issuer = c.tid == 0;
 
   if (w == 0) umma::tmem_alloc(&s.tmem_slot, 512);
-  if (c.tid == 0) umma::mbar_init(&s.bar, 1);
-  for (int i = c.tid; i < 64 * 8; i += TC_THREADS) s.mc[i] = a.Mc[i];
+  if (c.tid == 0) {
+    umma::mbar_init(&s.bar[0], 1);
+    umma::mbar_init(&s.bar[1], 1);
+  }
+  for (int i = c.tid; i < 64 * 8; i += TC_THREADS) s.mct[i % 8][i / 8] = a.Mc[i];
+  for (int i = c.tid; i < (4 * a.n_blocks + 2) * 64; i += TC_THREADS) {
+    const int r = i / 64, f = i % 64;
+    const float* src;
+    if (r < 4 * a.n_blocks) {
+      const TcBlockW& wb = a.blk[r / 4];
+      src = (r % 4 == 0) ? wb.ln1_g : (r % 4 == 1) ? wb.ln1_b : (r % 4 == 2) ? wb.ln2_g : wb.ln2_b;
+    } else {
+      src = (r == 4 * a.n_blocks) ? a.fn_g : a.fn_b;
+    }
+    s.ln[r][f] = src[f];
+  }
+  if (c.tid < 64) s.dwf[c.tid] = a.decoder == 1 ? a.dwf[c.tid] : 0.f;
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  c.tmem = s.tmem_slot;
+  const uint32_t tmem0 = s.tmem_slot;                 // lane 0 (MMA operand / accumulator addresses)
+  c.tmem = tmem0 + ((uint32_t)(32 * (w % 4)) << 16);  // this warp's lane quarter
   if (c.half == 0) {   // constant [1,0,0,0,0,0,0,0] column block: the A operand of every bias step
     float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    umma::tmem_st8(c.tmem + c.lane_base + C_ONES, ones);
+    umma::tmem_st8(c.tmem + C_ONES, ones);
   }
 
+  TcTicks tk;
+  tk.out = (a.dbg && a.dbg_stage == -1 && blockIdx.x == 0 && c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;
+  tk.n = 0;
   const int n_tiles = (a.B + 1) / 2;
+  const int n_chunks = (a.T + 127) / 128;
+  const int u = c.row / 64, i = c.row % 64;
+#pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int user0 = tile * 2;
-    const int u = c.row / 64, i = c.row % 64;
+    const bool dbg_on = a.dbg != nullptr && tile == 0;
     __syncthreads();
+    tick(tk, 0);
     if (c.half == 0) {
       int id = 0;
       if (user0 + u < a.B && i < L) id = a.p_x[(long long)(user0 + u) * L + i];
       s.pid[c.row] = id;
-      s.pmask[c.row] = id != 0 ? 1.f : 0.f;
+      const uint32_t bits = __ballot_sync(kFull, id != 0);
+      if ((c.tid & 31) == 0) s.kbits[u][w & 1] = bits;
+    } else {   // candidate ids of the first decoder chunk (user 0, targets 0..127)
+      s.oid[c.row] = (c.row < a.T) ? a.o_x[(long long)user0 * a.T + c.row] : 0;
     }
     weight_prefetch(c, 0, a.blk[0].wq);
     weight_prefetch(c, 1, a.blk[0].wk);
     __syncthreads();
-    {   // profile embedding (src/carca.py:415) -> X
-      float v[32];
-      const float* ctx = a.p_c + ((long long)(user0 + u) * L + i) * a.C;
-      embed_row(a, c, s.pid[c.row], s.pmask[c.row], ctx, a.pos ? a.pos + (long long)i * 64 : nullptr, v);
-      st_operand(c, C_XHI, C_XLO, v);
-      umma::tmem_st_wait();   // LN1 below reads these columns back
+    const int my_pid = s.pid[c.row];
+    // allowed keys of this thread's key half in self-attention: valid, causal (j <= i), query valid
+    uint32_t self_bits = 0;
+    if (my_pid != 0) {
+      const int top = i - 32 * c.half;   // keys t of this half with t <= top
+      const uint32_t causal = top >= 31 ? 0xffffffffu : (top < 0 ? 0u : ((2u << top) - 1u));
+      self_bits = s.kbits[u][c.half] & causal;
     }
+    float v[32];   // the activation this thread carries from phase to phase
+    {              // profile embedding (src/carca.py:415)
+      const float* ctx = a.p_c + ((long long)(user0 + u) * L + i) * a.C;
+      embed_row<H>(a, c, my_pid, ctx, a.pos ? a.pos + (long long)i * 64 : nullptr, v);
+    }
+    tick(tk, 1);
 
+#pragma unroll 1
     for (int b = 0; b < a.n_blocks; ++b) {
       const TcBlockW& wb = a.blk[b];
-      {   // LN1 (:298) -> QN
-        float v[32];
-        ld_half(c, C_XHI, v);
-        layernorm_rows(c, v, wb.ln1_g, wb.ln1_b);
-        st_operand(c, C_QNHI, C_QNLO, v);
+      st_operand<H>(c, C_XHI, C_XLO, v);                        // block input: operand of K and V
+      layernorm_rows<H>(c, v, s.ln[4 * b], s.ln[4 * b + 1]);    // LN1 (:298); v = qn from here on
+      st_operand<H>(c, C_QNHI, C_QNLO, v);
+      weight_wait<0>();
+      publish();
+      tick(tk, 2);
+      dump_regs<H>(a, c, dbg_on, 1 + 10 * b, v);
+      // Q from LN1(x), K from raw x (:238-239), separate completion events
+      if (issuer) {
+        issue_proj(tmem0, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
+        commit(c);
+        issue_proj(tmem0, C_ACCK, C_XHI, C_XLO, s.w[1]);
+        commit(c);
       }
-      weight_wait_all();
-      publish(c);
-      dump_stage(a, c, 1 + 10 * b, C_QNHI);
-      // Q from LN1(x), K from raw x (:238-239); V's weights are loaded while these run
-      if (c.tid == 0) {
-        issue_proj(c.tmem, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
-        issue_proj(c.tmem, C_ACCK, C_XHI, C_XLO, s.w[1]);
-      }
-      commit_and_wait(c);
+      wait_mma(c);                                              // Q done: slot 0 is free
       weight_prefetch(c, 0, wb.wv);
-      weight_wait_all();
-      publish(c);
-      if (c.tid == 0) issue_proj(c.tmem, C_ACCV, C_XHI, C_XLO, s.w[0]);
-      // overlap with the V projection: K operand to shared memory, Q remainder to QN_LO
+      {   // tf32 remainder of Q (the A operand of the score products) -> QN_LO
+        float q[32];
+        ld_feat<H>(c, C_ACCQ, q);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) q[j] = umma::tf32_lo(q[j]);
+        st_feat<H>(c, C_QNLO, q);
+      }
+      tick(tk, 3);
+      wait_mma(c);                                              // K done: slot 1 is free
       weight_prefetch(c, 1, wb.w1);
-      store_k_operand(c, C_ACCK);
-      {
-        float v[32], lo[32];
-        ld_half(c, C_ACCQ, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) lo[j] = umma::tf32_lo(v[j]);
-        tmem_st32(c.tmem + c.lane_base + C_QNLO + 32 * c.half, lo);
+      store_k_operand<H>(c, C_ACCK);
+      weight_wait<1>();                                         // WV landed (W1 may still be in flight)
+      publish();
+      tick(tk, 4);
+      if (issuer) {
+        issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);        // V (:240)
+        commit(c);
       }
-      commit_and_wait(c);
-      dump_stage(a, c, 2 + 10 * b, C_ACCQ);
-      dump_stage(a, c, 3 + 10 * b, C_ACCK);
-      dump_stage(a, c, 4 + 10 * b, C_ACCV);
-      store_v_operand(c, C_ACCV);
+      wait_mma(c);
+      tick(tk, 5);
+      dump_tmem<H>(a, c, dbg_on, 2 + 10 * b, C_ACCQ);
+      dump_tmem<H>(a, c, dbg_on, 3 + 10 * b, C_ACCK);
+      dump_tmem<H>(a, c, dbg_on, 4 + 10 * b, C_ACCV);
+      store_v_operand<H>(c, C_ACCV);
       weight_prefetch(c, 0, wb.w2);
-      if (!a.residual_sa) {   // no residual: the attention output replaces LN1(x)
-        float z[32];
+      if (!a.residual_sa) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = 0.f;
-        tmem_st32(c.tmem + c.lane_base + C_QNHI + 32 * c.half, z);
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      publish(c);
-      for (int h = 0; h < a.H; ++h) {
-        attention_head_tc<false>(a, c, h, dh, 0, C_XHI, C_XHI, C_XLO, C_ACCV, sqrt_dh);
-        // s[:, head cols] = LN1(x) + O_h   (in place in QN_HI; :302)
-        const int n = dh / 2;   // columns per thread
-        const int src = C_ACCV + u * dh + c.half * n, dst = C_QNHI + h * dh + c.half * n;
-        for (int c0 = 0; c0 < n; c0 += 8) {
-          float o[8], q[8];
-          umma::tmem_ld8(c.tmem + c.lane_base + src + c0, o);
-          umma::tmem_ld8(c.tmem + c.lane_base + dst + c0, q);
+      publish();
+      tick(tk, 6);
+      // ---- causal self-attention (:299), two heads per round; v accumulates qn + O (:302)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) q[j] += o[j];
-          umma::tmem_st8(c.tmem + c.lane_base + dst + c0, q);
+      for (int hp = 0; hp < H; hp += 2) {
+        if (issuer) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int h = hp + e;
+            const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u;
+            issue_3x(tmem0 + (e ? C_ACCK : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                     umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 128, DH / 8, 2048u, true);
+          }
+          commit(c);
         }
-        publish(c);
-      }
-      dump_stage(a, c, 5 + 10 * b, C_QNHI);
-      float s2[32];
-      {   // LN2 (:304) -> X (operand of ffn_1 and the FFN residual)
-        ld_half(c, C_QNHI, s2);
-        layernorm_rows(c, s2, wb.ln2_g, wb.ln2_b);
-        st_operand(c, C_XHI, C_XLO, s2);
-      }
-      weight_wait_all();
-      publish(c);
-      if (c.tid == 0) issue_proj(c.tmem, C_ACCQ, C_XHI, C_XLO, s.w[1]);    // ffn_1 (:307)
-      commit_and_wait(c);
-      {
-        float v[32];
-        ld_half(c, C_ACCQ, v);
+        wait_mma(c);
+        tick(tk, 20);
+        {
+          const uint32_t r0 = c.tmem + C_XHI, r1 = c.tmem + C_ACCK, k = 32 * c.half;
+          softmax_pair(c, self_bits, sc, r0 + 64 * u + k, r1 + 64 * u + k, r0 + k, r0 + 64 + k, r1 + k, r1 + 64 + k);
+        }
+        publish();
+        tick(tk, 21);
+        if (issuer) {   // O_h = P_h V_h for both users' V at once (each row keeps its own user's columns)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : kLeakySlope * v[j];   // LeakyReLU (:308)
-        st_operand(c, C_QNHI, C_QNLO, v);
+          for (int e = 0; e < 2; ++e) {
+            const int h = hp + e;
+            const uint32_t p = tmem0 + (e ? C_ACCK : C_XHI);
+            const uint32_t voff = (uint32_t)(h * 2 * DH) * 16u;
+            issue_3x(tmem0 + C_QNHI + e * 2 * DH, p, p + 64, umma::smem_u32(s.v_hi) + voff,
+                     umma::smem_u32(s.v_lo) + voff, 2 * DH, 8, (uint32_t)TC_VLBO, true);
+          }
+          commit(c);
+        }
+        wait_mma(c);
+        tick(tk, 22);
+        {
+          const uint32_t o0 = c.tmem + C_QNHI + u * DH + c.half * N2;
+          if constexpr (H == 2) {
+            float o[32];
+            umma::tmem_ld_2x16(o0, o0 + 2 * DH, o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += o[j];
+          } else {
+            float o[16];
+            umma::tmem_ld_2x8(o0, o0 + 2 * DH, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[hp * N2 + j] += o[j];
+          }
+        }
+        if (hp + 2 < H) {   // the next round's PV overwrites O: every thread must have read it
+          umma::fence_before_sync();
+          __syncthreads();
+          umma::fence_after_sync();
+        }
       }
-      publish(c);
-      if (c.tid == 0) issue_proj(c.tmem, C_ACCK, C_QNHI, C_QNLO, s.w[0]);  // ffn_2 (:311)
-      commit_and_wait(c);
+      dump_regs<H>(a, c, dbg_on, 5 + 10 * b, v);
+      layernorm_rows<H>(c, v, s.ln[4 * b + 2], s.ln[4 * b + 3]);   // LN2 (:304); v = s2 from here on
+      st_operand<H>(c, C_XHI, C_XLO, v);
+      weight_wait<0>();
+      publish();
+      tick(tk, 7);
+      if (issuer) {
+        issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);       // ffn_1 (:307)
+        commit(c);
+      }
+      wait_mma(c);
+      tick(tk, 8);
+      {
+        float f[32];
+        ld_feat<H>(c, C_ACCQ, f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : kLeakySlope * f[j];   // LeakyReLU (:308)
+        st_operand<H>(c, C_QNHI, C_QNLO, f);
+      }
+      publish();
+      tick(tk, 9);
+      if (issuer) {
+        issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);     // ffn_2 (:311)
+        commit(c);
+      }
+      wait_mma(c);
+      tick(tk, 10);
       // next weights: the following block's WQ/WK, or the decoder's WK/WV
       if (b + 1 < a.n_blocks) {
         weight_prefetch(c, 0, a.blk[b + 1].wq);
@@ -446,100 +627,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         weight_prefetch(c, 0, a.dwk);
         weight_prefetch(c, 1, a.dwv);
       }
-      {   // block output (+ LN2 residual, :316) -> X for the next block
-        float v[32];
-        ld_half(c, C_ACCK, v);
-        if (a.residual_sa) {
+      {   // block output (+ LN2 residual, :316): the next block's input
+        float f[32];
+        ld_feat<H>(c, C_ACCK, f);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += s2[j];
-        }
-        st_operand(c, C_XHI, C_XLO, v);
+        for (int j = 0; j < 32; ++j) v[j] = a.residual_sa ? v[j] + f[j] : f[j];
       }
-      publish(c);
-      dump_stage(a, c, 9 + 10 * b, C_XHI);
+      dump_regs<H>(a, c, dbg_on, 9 + 10 * b, v);
+      tick(tk, 11);
     }
 
-    {   // final LayerNorm (:421) -> QN (operand of the decoder's K/V projections)
-      float v[32];
-      ld_half(c, C_XHI, v);
-      layernorm_rows(c, v, a.fn_g, a.fn_b);
-      st_operand(c, C_QNHI, C_QNLO, v);
-      if (i == L - 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s.plast[u][32 * c.half + j] = v[j];
-      }
-    }
-    weight_wait_all();
-    publish(c);
-    dump_stage(a, c, 100, C_QNHI);
-
+    layernorm_rows<H>(c, v, s.ln[4 * a.n_blocks], s.ln[4 * a.n_blocks + 1]);   // final LayerNorm (:421)
+    dump_regs<H>(a, c, dbg_on, 100, v);
     if (a.decoder == 1) {   // keys / values of the encoded profile (:239-240 with p as key and value)
-      if (c.tid == 0) {
-        issue_proj(c.tmem, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
-        issue_proj(c.tmem, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
+      st_operand<H>(c, C_QNHI, C_QNLO, v);
+      weight_wait<0>();
+      publish();
+      tick(tk, 12);
+      if (issuer) {
+        issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
+        issue_proj(tmem0, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
+        commit(c);
       }
-      commit_and_wait(c);
+      wait_mma(c);
       weight_prefetch(c, 0, a.dwq);
-      store_k_operand(c, C_ACCK);
-      store_v_operand(c, C_ACCV);
-      weight_wait_all();
-      publish(c);
+      store_k_operand<H>(c, C_ACCK);
+      store_v_operand<H>(c, C_ACCV);
+      weight_wait<0>();
+      tick(tk, 13);
+    } else if (i == L - 1) {   // dot decoder: only the last profile position is used (:362)
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int q = 0; q < N2; ++q) s.plast[u][Own<H>::f0(h, c.half) + q] = v[h * N2 + q];
     }
 
-    for (int du = 0; du < 2; ++du) {
+#pragma unroll 1
+    for (int q = 0; q < 2 * n_chunks; ++q) {
+      const int du = q / n_chunks, t0 = (q % n_chunks) * 128;
       if (user0 + du >= a.B) break;
-      for (int t0 = 0; t0 < a.T; t0 += 128) {
-        const int nq = min(128, a.T - t0);
-        __syncthreads();
-        if (c.half == 0) {
-          int id = 0;
-          if (c.row < nq) id = a.o_x[(long long)(user0 + du) * a.T + t0 + c.row];
-          s.tid_[c.row] = id;
-          s.tmask[c.row] = id != 0 ? 1.f : 0.f;
-        }
-        __syncthreads();
-        float e[32];   // target embedding half row (:426), also the residual of the decoder
-        {
-          const float* ctx = a.o_c + ((long long)(user0 + du) * a.T + t0 + min(c.row, nq - 1)) * a.C;
-          embed_row(a, c, s.tid_[c.row], s.tmask[c.row], ctx, nullptr, e);
-        }
-        float acc = 0.f;
-        if (a.decoder == 1) {
-          st_operand(c, C_XHI, C_XLO, e);
-          publish(c);
-          if (c.tid == 0) issue_proj(c.tmem, C_ACCQ, C_XHI, C_XLO, s.w[0]);   // Q of the targets
-          commit_and_wait(c);
-          {
-            float v[32], lo[32];
-            ld_half(c, C_ACCQ, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) lo[j] = umma::tf32_lo(v[j]);
-            tmem_st32(c.tmem + c.lane_base + C_QNLO + 32 * c.half, lo);
-          }
-          publish(c);
-          for (int h = 0; h < a.H; ++h)
-            attention_head_tc<true>(a, c, h, dh, du, C_ACCK, C_QNHI, C_XLO, C_ACCV + h * dh, sqrt_dh);
-          float o[32];   // s = attention (+ o) (:340-343); y = sigmoid(<s, wf> + bf) (:345-347)
-          ld_half(c, C_ACCV, o);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sv = o[j] + (a.residual_ca ? e[j] : 0.f);
-            acc = fmaf(sv, __ldg(a.dwf + 32 * c.half + j), acc);
-          }
-          acc = row_combine<false>(c, acc) + __ldg(a.dbf);
-        } else {   // dot product with the last profile position (:362)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc = fmaf(e[j], s.plast[du][32 * c.half + j], acc);
-          acc = row_combine<false>(c, acc);
-        }
-        if (c.half == 0 && c.row < nq)
-          a.y[(long long)(user0 + du) * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
+      const int nq = min(128, a.T - t0);
+      __syncthreads();   // s.oid holds this chunk's ids; K/V/plast stores are visible
+      const int oid = s.oid[c.row];
+      float e[32];       // target embedding (:426), also the residual of the decoder
+      {
+        const float* ctx = a.o_c + ((long long)(user0 + du) * a.T + t0 + min(c.row, nq - 1)) * a.C;
+        embed_row<H>(a, c, oid, ctx, nullptr, e);
       }
+      tick(tk, 14);
+      float acc = 0.f;
+      if (a.decoder == 1) {
+        st_operand<H>(c, C_XHI, C_XLO, e);
+        publish();
+        if (issuer) {
+          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[0]);   // Q of the targets
+          commit(c);
+        }
+      } else {
+        __syncthreads();
+      }
+      if (q + 1 < 2 * n_chunks && c.half == 1) {   // ids of the next chunk (s.oid was consumed above)
+        const int du1 = (q + 1) / n_chunks, t1 = ((q + 1) % n_chunks) * 128;
+        int id = 0;
+        if (user0 + du1 < a.B && t1 + c.row < a.T) id = a.o_x[(long long)(user0 + du1) * a.T + t1 + c.row];
+        s.oid[c.row] = id;
+      }
+      if (a.decoder == 1) {
+        wait_mma(c);
+        tick(tk, 15);
+        {
+          float qv[32];
+          ld_feat<H>(c, C_ACCQ, qv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) qv[j] = umma::tf32_lo(qv[j]);
+          st_feat<H>(c, C_QNLO, qv);
+        }
+        publish();
+        const uint32_t cross_bits = oid != 0 ? s.kbits[du][c.half] : 0u;
+#pragma unroll
+        for (int hp = 0; hp < H; hp += 2) {
+          if (issuer) {
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee) {
+              const int h = hp + ee;
+              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)du * 64u * 16u;
+              issue_3x(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                       umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 64, DH / 8, 2048u, true);
+            }
+            commit(c);
+          }
+          wait_mma(c);
+          tick(tk, 20);
+          {
+            const uint32_t k = 32 * c.half;
+            softmax_pair(c, cross_bits, sc, c.tmem + C_XHI + k, c.tmem + C_XLO + k, c.tmem + C_XHI + k,
+                         c.tmem + C_ACCK + k, c.tmem + C_XLO + k, c.tmem + C_ACCV + k);
+          }
+          publish();
+          tick(tk, 21);
+          if (issuer) {
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee) {
+              const int h = hp + ee;
+              const uint32_t voff = (uint32_t)(h * 2 * DH + du * DH) * 16u;
+              issue_3x(tmem0 + C_QNHI + h * DH, tmem0 + (ee ? C_XLO : C_XHI), tmem0 + (ee ? C_ACCV : C_ACCK),
+                       umma::smem_u32(s.v_hi) + voff, umma::smem_u32(s.v_lo) + voff, DH, 8, (uint32_t)TC_VLBO, true);
+            }
+            commit(c);
+          }
+          wait_mma(c);
+          tick(tk, 22);
+        }
+        {   // s = attention (+ o) (:340-343); y = sigmoid(<s, wf> + bf) (:345-347)
+          float o[32];
+          ld_feat<H>(c, C_QNHI, o);
+#pragma unroll
+          for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int qq = 0; qq < N2; ++qq) {
+              const float sv = o[h * N2 + qq] + (a.residual_ca ? e[h * N2 + qq] : 0.f);
+              acc = fmaf(sv, s.dwf[Own<H>::f0(h, c.half) + qq], acc);
+            }
+        }
+        acc += pair_exchange(c, make_float2(acc, 0.f)).x;
+        acc += __ldg(a.dbf);
+      } else {   // dot product with the last profile position (:362)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], s.plast[du][Own<H>::f0(h, c.half) + qq], acc);
+        acc += pair_exchange(c, make_float2(acc, 0.f)).x;
+      }
+      if (c.half == 0 && c.row < nq)
+        a.y[(long long)(user0 + du) * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
+      tick(tk, 23);
     }
+    tk.out = nullptr;   // first tile only
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (w == 0) umma::tmem_free(c.tmem, 512);
+  if (w == 0) umma::tmem_free(tmem0, 512);
 }
 
 // Packs W [64 out, 64 in] (+ bias [64]) into the K-major B operand of umma.cuh with the bias as

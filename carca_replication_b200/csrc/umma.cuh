@@ -58,6 +58,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: returns false (never hangs) if the phase does not complete.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int max_spins = 4000000) {
+#pragma unroll 1
   for (int i = 0; i < max_spins; ++i)
     if (mbar_try(bar, parity)) return true;
   return false;
