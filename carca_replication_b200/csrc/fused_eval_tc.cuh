@@ -147,9 +147,8 @@ __device__ __forceinline__ void publish() {
 }
 // Completion tracking: commits alternate between two mbarriers so that a barrier is re-armed only
 // after a CTA-wide sync that every thread reaches past its previous wait on it.
-__device__ __forceinline__ void commit(TcCtx& c) {   // issuing thread only
-  umma::commit(&c.s->bar[c.ncommit & 1u]);
-  c.ncommit++;
+__device__ __forceinline__ void commit(TcCtx& c, uint32_t ahead = 0) {   // elected lane of the issuing warp
+  umma::commit(&c.s->bar[(c.ncommit + ahead) & 1u]);
 }
 __device__ __forceinline__ void wait_mma(TcCtx& c) {
   const uint32_t n = c.nwait++;
@@ -168,26 +167,27 @@ __device__ __forceinline__ float2 pair_exchange(TcCtx& c, float2 mine) {
 
 // ---- MMA issue helpers (one thread) ---------------------------------------------------------
 // D[d .. d+N) (=) A(tmem, 8*ksteps cols at a_hi / a_lo) x B(smem hi / lo)^T, 3xTF32
-__device__ __forceinline__ void issue_3x(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int N,
-                                         int ksteps, uint32_t b_lbo, bool first) {
-  const uint32_t idesc = umma::idesc_tf32(N);
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_3x(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                         uint32_t b_lbo) {
+  constexpr uint32_t idesc = umma::idesc_tf32(N);
   const uint64_t dhi = umma::smem_desc(b_hi, b_lbo, 128), dlo = umma::smem_desc(b_lo, b_lbo, 128);
   const uint64_t step = (uint64_t)((2u * b_lbo) >> 4);
-#pragma unroll 1
+#pragma unroll
   for (int p = 0; p < 3; ++p) {
     const uint32_t a = (p == 1) ? a_lo : a_hi;
     const uint64_t b = (p == 2) ? dlo : dhi;
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks)
-      umma::mma_tf32_ts(d, a + 8 * ks, b + ks * step, idesc, !(first && p == 0 && ks == 0));
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      umma::mma_tf32_ts(d, a + 8 * ks, b + ks * step, idesc, !(p == 0 && ks == 0));
   }
 }
 // projection with a packed weight (bias folded in as K step 8 against the ONES block)
 __device__ __forceinline__ void issue_proj(uint32_t tmem, int d_col, int a_hi, int a_lo, const float* w_slot) {
   const uint32_t b_hi = umma::smem_u32(w_slot), b_lo = umma::smem_u32(w_slot + TC_WFLOATS);
   const uint32_t lbo = 64 * 16;
-  issue_3x(tmem + d_col, tmem + a_hi, tmem + a_lo, b_hi, b_lo, 64, 8, lbo, true);
-  const uint32_t idesc = umma::idesc_tf32(64);
+  issue_3x<64, 8>(tmem + d_col, tmem + a_hi, tmem + a_lo, b_hi, b_lo, lbo);
+  constexpr uint32_t idesc = umma::idesc_tf32(64);
   umma::mma_tf32_ts(tmem + d_col, tmem + C_ONES, umma::smem_desc(b_hi + 16 * lbo, lbo, 128), idesc, true);
   umma::mma_tf32_ts(tmem + d_col, tmem + C_ONES, umma::smem_desc(b_lo + 16 * lbo, lbo, 128), idesc, true);
 }
@@ -419,7 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   c.status = a.status;
   const int L = a.L;
   const float sc = 1.4426950408889634f / sqrtf((float)DH);
-  const bool issuer = c.tid == 0;
+  // MMAs are issued by one elected lane of warp 0; the branch on the warp index is warp-uniform so
+  // descriptors stay in uniform registers (a divergent `tid == 0` branch costs a waterfall loop per MMA)
+  const bool issuer_warp = __shfl_sync(kFull, w, 0) == 0;
 
   if (w == 0) umma::tmem_alloc(&s.tmem_slot, 512);
   if (c.tid == 0) {
@@ -499,11 +501,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 2);
       dump_regs<H>(a, c, dbg_on, 1 + 10 * b, v);
       // Q from LN1(x), K from raw x (:238-239), separate completion events
-      if (issuer) {
-        issue_proj(tmem0, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
-        commit(c);
-        issue_proj(tmem0, C_ACCK, C_XHI, C_XLO, s.w[1]);
-        commit(c);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          issue_proj(tmem0, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
+          commit(c, 0);
+          issue_proj(tmem0, C_ACCK, C_XHI, C_XLO, s.w[1]);
+          commit(c, 1);
+        }
+        c.ncommit += 2;
       }
       wait_mma(c);                                              // Q done: slot 0 is free
       weight_prefetch(c, 0, wb.wv);
@@ -521,9 +526,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<1>();                                         // WV landed (W1 may still be in flight)
       publish();
       tick(tk, 4);
-      if (issuer) {
-        issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);        // V (:240)
-        commit(c);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);        // V (:240)
+          commit(c);
+        }
+        c.ncommit++;
       }
       wait_mma(c);
       tick(tk, 5);
@@ -541,15 +549,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       // ---- causal self-attention (:299), two heads per round; v accumulates qn + O (:302)
 #pragma unroll
       for (int hp = 0; hp < H; hp += 2) {
-        if (issuer) {
+        if (issuer_warp) {
+          if (umma::elect_one()) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int h = hp + e;
-            const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u;
-            issue_3x(tmem0 + (e ? C_ACCK : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
-                     umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 128, DH / 8, 2048u, true);
+            for (int e = 0; e < 2; ++e) {
+              const int h = hp + e;
+              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u;
+              issue_3x<128, DH / 8>(tmem0 + (e ? C_ACCK : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                                    umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
+            }
+            commit(c);
           }
-          commit(c);
+          c.ncommit++;
         }
         wait_mma(c);
         tick(tk, 20);
@@ -559,16 +570,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
         publish();
         tick(tk, 21);
-        if (issuer) {   // O_h = P_h V_h for both users' V at once (each row keeps its own user's columns)
+        if (issuer_warp) {   // O_h = P_h V_h for both users' V at once (each row keeps its own user's columns)
+          if (umma::elect_one()) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int h = hp + e;
-            const uint32_t p = tmem0 + (e ? C_ACCK : C_XHI);
-            const uint32_t voff = (uint32_t)(h * 2 * DH) * 16u;
-            issue_3x(tmem0 + C_QNHI + e * 2 * DH, p, p + 64, umma::smem_u32(s.v_hi) + voff,
-                     umma::smem_u32(s.v_lo) + voff, 2 * DH, 8, (uint32_t)TC_VLBO, true);
+            for (int e = 0; e < 2; ++e) {
+              const int h = hp + e;
+              const uint32_t p = tmem0 + (e ? C_ACCK : C_XHI);
+              const uint32_t voff = (uint32_t)(h * 2 * DH) * 16u;
+              issue_3x<2 * DH, 8>(tmem0 + C_QNHI + e * 2 * DH, p, p + 64, umma::smem_u32(s.v_hi) + voff,
+                                  umma::smem_u32(s.v_lo) + voff, (uint32_t)TC_VLBO);
+            }
+            commit(c);
           }
-          commit(c);
+          c.ncommit++;
         }
         wait_mma(c);
         tick(tk, 22);
@@ -598,9 +612,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<0>();
       publish();
       tick(tk, 7);
-      if (issuer) {
-        issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);       // ffn_1 (:307)
-        commit(c);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);       // ffn_1 (:307)
+          commit(c);
+        }
+        c.ncommit++;
       }
       wait_mma(c);
       tick(tk, 8);
@@ -613,9 +630,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
       publish();
       tick(tk, 9);
-      if (issuer) {
-        issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);     // ffn_2 (:311)
-        commit(c);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);     // ffn_2 (:311)
+          commit(c);
+        }
+        c.ncommit++;
       }
       wait_mma(c);
       tick(tk, 10);
@@ -644,10 +664,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<0>();
       publish();
       tick(tk, 12);
-      if (issuer) {
-        issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
-        issue_proj(tmem0, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
-        commit(c);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
+          issue_proj(tmem0, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
+          commit(c);
+        }
+        c.ncommit++;
       }
       wait_mma(c);
       weight_prefetch(c, 0, a.dwq);
@@ -679,9 +702,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       if (a.decoder == 1) {
         st_operand<H>(c, C_XHI, C_XLO, e);
         publish();
-        if (issuer) {
-          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[0]);   // Q of the targets
-          commit(c);
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[0]);   // Q of the targets
+            commit(c);
+          }
+          c.ncommit++;
         }
       } else {
         __syncthreads();
@@ -706,15 +732,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         const uint32_t cross_bits = oid != 0 ? s.kbits[du][c.half] : 0u;
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
-          if (issuer) {
+          if (issuer_warp) {
+            if (umma::elect_one()) {
 #pragma unroll
-            for (int ee = 0; ee < 2; ++ee) {
-              const int h = hp + ee;
-              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)du * 64u * 16u;
-              issue_3x(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
-                       umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 64, DH / 8, 2048u, true);
+              for (int ee = 0; ee < 2; ++ee) {
+                const int h = hp + ee;
+                const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)du * 64u * 16u;
+                issue_3x<64, DH / 8>(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                                     umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
+              }
+              commit(c);
             }
-            commit(c);
+            c.ncommit++;
           }
           wait_mma(c);
           tick(tk, 20);
@@ -725,15 +754,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           }
           publish();
           tick(tk, 21);
-          if (issuer) {
+          if (issuer_warp) {
+            if (umma::elect_one()) {
 #pragma unroll
-            for (int ee = 0; ee < 2; ++ee) {
-              const int h = hp + ee;
-              const uint32_t voff = (uint32_t)(h * 2 * DH + du * DH) * 16u;
-              issue_3x(tmem0 + C_QNHI + h * DH, tmem0 + (ee ? C_XLO : C_XHI), tmem0 + (ee ? C_ACCV : C_ACCK),
-                       umma::smem_u32(s.v_hi) + voff, umma::smem_u32(s.v_lo) + voff, DH, 8, (uint32_t)TC_VLBO, true);
+              for (int ee = 0; ee < 2; ++ee) {
+                const int h = hp + ee;
+                const uint32_t voff = (uint32_t)(h * 2 * DH + du * DH) * 16u;
+                issue_3x<DH, 8>(tmem0 + C_QNHI + h * DH, tmem0 + (ee ? C_XLO : C_XHI), tmem0 + (ee ? C_ACCV : C_ACCK),
+                                umma::smem_u32(s.v_hi) + voff, umma::smem_u32(s.v_lo) + voff, (uint32_t)TC_VLBO);
+              }
+              commit(c);
             }
-            commit(c);
+            c.ncommit++;
           }
           wait_mma(c);
           tick(tk, 22);

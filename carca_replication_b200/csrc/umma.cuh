@@ -24,6 +24,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_lo(float x) { return x - tf32_hi(x); }
 
+// one lane of a converged warp (the branch taken around it must be warp-uniform)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // ---- TMEM allocation (one full warp), address written to a shared slot
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int columns) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
@@ -80,7 +92,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;          // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 // tf32 x tf32 -> f32, both operands K-major, M = 128
-__host__ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
