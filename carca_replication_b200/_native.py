@@ -99,6 +99,8 @@ SIGNATURES = {
     "carca_eval_prepare": [vp, vp, P(ModelParams), P(AttrSource), vp],
     "carca_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, vp],
     "carca_eval_forward_opts": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
+    "carca_eval_forward_catalog": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
+    "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
 }

@@ -626,7 +626,7 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
 #ifndef CARCA_EMU
 static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                           int T, int32_t* status, float* dbg, int dbg_stage, void* stream) {
+                           int T, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user, void* stream) {
   const PlanLayout pl = plan_layout(m);
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -654,6 +654,9 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.status = status;
   a.dbg = dbg;
   a.dbg_stage = dbg_stage;
+  a.cat_lo = cat_lo;
+  a.oc_user = ctx_per_user ? m->embed.n_ctx : (long long)T * m->embed.n_ctx;
+  a.oc_tgt = ctx_per_user ? 0 : m->embed.n_ctx;
   const size_t smem = sizeof(TcSmem);
   const int n_tiles = ceil_div(B, 2);
   if (m->n_heads == 2) {
@@ -669,9 +672,10 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
 }
 #endif
 
-int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream) {
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user,
+                            void* stream) {
   const int d = m->embed.d, H = m->n_heads;
   const bool common_ok = d == FD && L >= 1 && m->embed.n_ctx <= 8 && m->n_blocks <= FMAXB && H >= 1 && FD % H == 0;
   const bool ffma_ok = common_ok && L <= FLP && (FD / H) % 4 == 0;
@@ -690,7 +694,8 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
   if (B <= 0 || T <= 0) return 0;
 #ifndef CARCA_EMU
   if (variant == 2 || (variant == 0 && tc_ok))
-    return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, stream);
+    return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, cat_lo,
+                           ctx_per_user, stream);
 #endif
   const PlanLayout pl = plan_layout(m);
   FusedArgs a;
@@ -719,12 +724,42 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
   }
   // the kernel indexes Mc with row stride 8 and reads C context values per position
   a.C = m->embed.n_ctx;
+  a.cat_lo = cat_lo;
+  a.oc_user = ctx_per_user ? m->embed.n_ctx : (long long)T * m->embed.n_ctx;
+  a.oc_tgt = ctx_per_user ? 0 : m->embed.n_ctx;
   const size_t smem = sizeof(FusedSmem);
   auto k = fused_eval_kernel;
   TRY(allow_smem(k, smem));
   const int n_tiles = ceil_div(B, FU);
   CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(FTHREADS), smem, S(stream), a);
   return check_launch("fused_eval");
+}
+
+int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream) {
+  // variant bit 8: o_c holds one context row per user ([B, C], e.g. the base of an expanded [B,T,C] view)
+  return eval_forward_any(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, variant & 0xff, status, dbg, dbg_stage,
+                          0, (variant >> 8) & 1, stream);
+}
+
+int carca_eval_forward_catalog(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                               const int32_t* p_x, const float* p_c, const float* ctx_user, int32_t item_lo,
+                               int n_cand, int B, int L, int variant, int32_t* status, void* stream) {
+  CARCA_REQUIRE(item_lo >= 1 && n_cand >= 0 && (long long)item_lo + n_cand <= m->embed.n_items,
+                "eval_forward_catalog: item range [%d, %d) outside the item table [1, %d)", item_lo, item_lo + n_cand,
+                m->embed.n_items);
+  return eval_forward_any(y, ldy, col0, plan, m, p_x, p_c, nullptr, ctx_user, B, L, n_cand, variant, status, nullptr,
+                          0, item_lo, 1, stream);
+}
+
+int carca_catalog_rank_count(int32_t* count, const float* y, int64_t ldy, const float* y_pos, const int32_t* pos_item,
+                             int32_t item_lo, int B, int n_cand, void* stream) {
+  if (B <= 0 || n_cand <= 0) return 0;
+  auto k = catalog_rank_count_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid(B)), dim3(256), 0, S(stream), count, y, (long long)ldy, y_pos, pos_item, item_lo,
+               B, n_cand);
+  return check_launch("catalog_rank_count");
 }
 
 int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,

@@ -56,6 +56,8 @@ struct FusedArgs {
   FusedBlockW blk[FMAXB];
   const float *fn_g, *fn_b;
   const float *dwqT, *dbq, *dwkT, *dbk, *dwvT, *dbv, *dwf, *dbf;
+  int cat_lo;           // > 0: full-catalog mode — candidate t of every user is item cat_lo + t
+  long long oc_user, oc_tgt;   // strides (floats) of o_c over users / candidates ([B,T,C]: T*C, C; per-user rows: C, 0)
 };
 
 struct FusedSmem {
@@ -177,7 +179,7 @@ __device__ __forceinline__ void layernorm_T(float* __restrict__ out_T, const flo
 __device__ __forceinline__ void gather_embed(float* __restrict__ out_T, const FusedArgs& a, const FusedSmem& s,
                                              const int* __restrict__ ids, const float* __restrict__ msk,
                                              const float* __restrict__ ctx_base, int rows_per_user,
-                                             long long ctx_user_stride, bool add_pos) {
+                                             long long ctx_user_stride, bool add_pos, int ctx_pos_stride) {
   // tile row r belongs to user r / rows_per_user at sequence position r % rows_per_user; ids/msk are
   // already laid out per tile row and ctx_base points at the first user's first position.
   const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -190,7 +192,7 @@ __device__ __forceinline__ void gather_embed(float* __restrict__ out_T, const Fu
       const float* trow = a.Tfold + (long long)id * FD;
       v0 = trow[lane];
       v1 = trow[lane + 32];
-      const float* ctx = ctx_base + (long long)u * ctx_user_stride + (long long)pos_in_user * a.C;
+      const float* ctx = ctx_base + (long long)u * ctx_user_stride + (long long)pos_in_user * ctx_pos_stride;
       for (int c = 0; c < a.C; ++c) {
         const float cv = ctx[c];
         v0 = fmaf(s.mc[lane * 8 + c], cv, v0);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) fused_eval_kernel(const FusedArgs
     __syncthreads();
     // ---- embedding of the profile (src/carca.py:415; dropout :416 is identity in eval)
     gather_embed(R0, a, s, s.pid, s.pmask, a.p_c + (long long)user0 * L * a.C, FLP, (long long)L * a.C,
-                 a.pos != nullptr);
+                 a.pos != nullptr, a.C);
     ring_commit(ring, s);   // slot 0 <- block 0 WQ^T
     __syncthreads();
 
@@ -440,13 +442,14 @@ __global__ void __launch_bounds__(FTHREADS, 1) fused_eval_kernel(const FusedArgs
         __syncthreads();
         for (int r = tid; r < FRP; r += FTHREADS) {
           int id = 0;
-          if (r < nq) id = a.o_x[(long long)(user0 + u) * a.T + t0 + r];
+          if (r < nq) id = a.cat_lo > 0 ? a.cat_lo + t0 + r : a.o_x[(long long)(user0 + u) * a.T + t0 + r];
           s.tid_[r] = id;
           s.tmask[r] = id != 0 ? 1.f : 0.f;
         }
         __syncthreads();
         // target embeddings (:426, no positional encoding) -> R0 transposed
-        gather_embed(R0, a, s, s.tid_, s.tmask, a.o_c + ((long long)(user0 + u) * a.T + t0) * a.C, FRP, 0, false);
+        gather_embed(R0, a, s, s.tid_, s.tmask, a.o_c + (long long)(user0 + u) * a.oc_user + (long long)t0 * a.oc_tgt,
+                     FRP, 0, false, (int)a.oc_tgt);
         __syncthreads();
         if (a.decoder == 1) {
           project<OUT_T, false, false>(R2, R0, s.w[ring.slot], a.dbq, nullptr);   // Q of the targets

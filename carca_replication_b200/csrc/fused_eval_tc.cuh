@@ -64,7 +64,9 @@ struct TcArgs {
   int* status;                                       // [0] set to 1 if an MMA wait timed out
   float* dbg;                                        // optional [128, 64]: activation `dbg_stage` of tile 0,
   int dbg_stage;                                     //   or (dbg_stage == -1) phase clock ticks of tile 0
-};
+  int cat_lo;                                        // > 0: full-catalog mode — candidate t is item cat_lo + t
+  long long oc_user, oc_tgt;                         // strides (floats) of o_c over users / candidates ([B,T,C]: T*C, C;
+};                                                   //   one row per user, e.g. an expanded view or catalog mode: C, 0)
 
 struct TcSmem {
   float w[2][2 * TC_WFLOATS];                        // weight ring: [slot][hi | lo]
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       const uint32_t bits = __ballot_sync(kFull, id != 0);
       if ((c.tid & 31) == 0) s.kbits[u][w & 1] = bits;
     } else {   // candidate ids of the first decoder chunk (user 0, targets 0..127)
-      s.oid[c.row] = (c.row < a.T) ? a.o_x[(long long)user0 * a.T + c.row] : 0;
+      s.oid[c.row] = (c.row < a.T) ? (a.cat_lo > 0 ? a.cat_lo + c.row : a.o_x[(long long)user0 * a.T + c.row]) : 0;
     }
     weight_prefetch(c, 0, a.blk[0].wq);
     weight_prefetch(c, 1, a.blk[0].wk);
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       const int oid = s.oid[c.row];
       float e[32];       // target embedding (:426), also the residual of the decoder
       {
-        const float* ctx = a.o_c + ((long long)(user0 + du) * a.T + t0 + min(c.row, nq - 1)) * a.C;
+        const float* ctx = a.o_c + (long long)(user0 + du) * a.oc_user + (long long)(t0 + min(c.row, nq - 1)) * a.oc_tgt;
         embed_row<H>(a, c, oid, ctx, nullptr, e);
       }
       tick(tk, 14);
@@ -715,7 +717,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       if (q + 1 < 2 * n_chunks && c.half == 1) {   // ids of the next chunk (s.oid was consumed above)
         const int du1 = (q + 1) / n_chunks, t1 = ((q + 1) % n_chunks) * 128;
         int id = 0;
-        if (user0 + du1 < a.B && t1 + c.row < a.T) id = a.o_x[(long long)(user0 + du1) * a.T + t1 + c.row];
+        if (user0 + du1 < a.B && t1 + c.row < a.T)
+          id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)(user0 + du1) * a.T + t1 + c.row];
         s.oid[c.row] = id;
       }
       if (a.decoder == 1) {

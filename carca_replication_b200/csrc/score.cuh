@@ -205,4 +205,27 @@ __global__ void __launch_bounds__(256) rank_metrics_kernel(double* __restrict__ 
   }
 }
 
+// Full-catalog ranking: count[b] += #{j : y[b,j] > y_pos[b]  or  (y[b,j] == y_pos[b] and item_lo + j < pos_item[b])},
+// i.e. how many items of this shard a stable descending sort (src/train.py:16) places before the
+// positive.  One warp per user, coalesced row reads.
+__global__ void __launch_bounds__(256) catalog_rank_count_kernel(int* __restrict__ count, const float* __restrict__ y,
+                                                                 long long ldy, const float* __restrict__ y_pos,
+                                                                 const int* __restrict__ pos_item, int item_lo, int B,
+                                                                 int n) {
+  const int b = blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+  if (b >= B) return;
+  const int lane = threadIdx.x % kWarp;
+  const float yp = y_pos[b];
+  const int pi = pos_item[b];
+  const float* row = y + (long long)b * ldy;
+  int c = 0;
+  for (int j = lane; j < n; j += kWarp) {
+    const float v = row[j];
+    c += (v > yp) || (v == yp && item_lo + j < pi);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+  if (lane == 0 && c) atomicAdd(count + b, c);
+}
+
 }  // namespace carca

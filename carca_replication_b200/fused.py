@@ -138,8 +138,15 @@ def forward(model, profile, targets: Sequence, variant: Optional[int] = None, db
     p_x, p_c = as_ids(p_x), as_f32(p_c)
     B, L = p_x.shape
     n_ctx = p_c.shape[-1]
+    per_user_ctx = False
     if len(targets) == 1:
-        o_x, o_c = as_ids(targets[0][0]), as_f32(targets[0][2])
+        o_x, o_c = as_ids(targets[0][0]), targets[0][2]
+        if o_c.dim() == 3 and o_c.stride(1) == 0 and o_c.stride(2) == 1 and o_c.shape[1] > 1:
+            # [B,T,C] expanded from one context row per user (the positive's context given to every
+            # sampled negative, src/data.py:185): read the [B,C] base, never materialise the copies
+            o_c, per_user_ctx = as_f32(o_c[:, 0, :]), True
+        else:
+            o_c = as_f32(o_c)
     else:   # eval-mode decoders score every candidate independently, so tuples simply concatenate
         o_x = torch.cat([as_ids(t[0]) for t in targets], dim=1)
         o_c = torch.cat([as_f32(t[2]) for t in targets], dim=1)
@@ -147,8 +154,29 @@ def forward(model, profile, targets: Sequence, variant: Optional[int] = None, db
     plan, status = eval_plan(model, table, n_ctx)
     m, keep = _model_params(model, table, None, n_ctx)
     y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
+    v = (VARIANT if variant is None else int(variant)) | (0x100 if per_user_ctx else 0)
     N.call("carca_eval_forward_opts", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
-           N.i32p(o_x), N.f32p(o_c), B, L, T, VARIANT if variant is None else int(variant), N.i32p(status),
+           N.i32p(o_x), N.f32p(o_c), B, L, T, v, N.i32p(status),
            None if dbg is None else N.f32p(dbg), int(dbg_stage), N.stream())
+    del keep
+    return y
+
+
+def forward_catalog(model, profile, ctx_user: Tensor, item_lo: int, n_cand: int,
+                    variant: Optional[int] = None) -> Tensor:
+    """Scores of the contiguous item range [item_lo, item_lo + n_cand) for every user -> [B, n_cand]
+    (carca_eval_forward_catalog; eval-mode CARCA.forward over candidate chunks, src/carca.py:424-431)."""
+    p_x, p_a, p_c = profile
+    table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
+    N.require_device(p_x, p_c, ctx_user)
+    p_x, p_c, ctx_user = as_ids(p_x), as_f32(p_c), as_f32(ctx_user)
+    B, L = p_x.shape
+    n_ctx = p_c.shape[-1]
+    plan, status = eval_plan(model, table, n_ctx)
+    m, keep = _model_params(model, table, None, n_ctx)
+    y = torch.empty((B, n_cand), dtype=torch.float32, device=p_x.device)
+    N.call("carca_eval_forward_catalog", N.f32p(y), n_cand, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
+           N.f32p(ctx_user), int(item_lo), int(n_cand), B, L, VARIANT if variant is None else int(variant),
+           N.i32p(status), N.stream())
     del keep
     return y

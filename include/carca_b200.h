@@ -263,10 +263,31 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
  * 3xTF32 fp32-grade MMAs).  status (device int32[1], required for variant 2) is set to 1 if an
  * MMA completion wait timed out.  dbg (optional device [128,64]) receives the intermediate
  * activation `dbg_stage` of the first tile (10*block + {1: LN1, 2: Q, 3: K, 4: V, 5: attention +
- * residual, 9: block output}, 100: final LayerNorm) for stage-by-stage validation.            */
+ * residual, 9: block output}, 100: final LayerNorm) for stage-by-stage validation.
+ * variant | 0x100: o_c is [B, C], one context row per user shared by all of the user's candidates
+ * (what src/data.py:185 builds; lets the host pass the base of an expanded [B,T,C] view).      */
 int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
                             int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream);
+
+/* ------------------------------------------------------------------ full-catalog scoring */
+/* Scores every item of the contiguous id range [item_lo, item_lo + n_cand) (an item-table shard)
+ * for every user: y[b, col0 + j] = CARCA.forward(profile_b, [(item_lo + j, ., ctx_user_b)]) in eval
+ * mode.  ctx_user [B, C] is one context row per user, used for all of that user's candidates (the
+ * positive's context, as src/data.py:185 gives the sampled negatives).  The reference has no such
+ * mode; by construction it equals model.forward(profile, targets=[chunk_1, ..]) over candidate
+ * chunks (src/carca.py:424-431).  Same kernels, plan, variants and limits as carca_eval_forward_opts;
+ * no candidate id / context tensors are read.                                                   */
+int carca_eval_forward_catalog(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
+                               const int32_t* p_x, const float* p_c, const float* ctx_user, int32_t item_lo,
+                               int n_cand, int B, int L, int variant, int32_t* status, void* stream);
+
+/* count[b] += number of candidates j of this shard that a stable descending sort (src/train.py:16)
+ * ranks before the positive: y[b,j] > y_pos[b], or equal with item_lo + j < pos_item[b].  Summed
+ * over shards (all-reduce under item-table sharding) it is the positive's rank: hit = rank < k,
+ * ndcg = 1 / log2(rank + 2) (src/train.py:18-21, :27-32).                                        */
+int carca_catalog_rank_count(int32_t* count, const float* y, int64_t ldy, const float* y_pos, const int32_t* pos_item,
+                             int32_t item_lo, int B, int n_cand, void* stream);
 
 /* ------------------------------------------------------------------ tensor-core self test */
 /* C[128,N] = A[128,K] B[N,K]^T on the tcgen05 tensor cores (tf32), accumulator in TMEM.

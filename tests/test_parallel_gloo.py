@@ -82,3 +82,25 @@ def _worker(rank, world, port, name):
 @pytest.mark.parametrize("name", ["beauty_ca", "beauty_dot"])
 def test_two_rank_gradients_and_metrics_match_single_process(name):
     mp.spawn(_worker, args=(2, _free_port(), name), nprocs=2, join=True)
+
+
+def _catalog_worker(rank, world, port, decoder):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _use_emulator()
+        import catalog_suite as S
+        from carca_replication_b200 import catalog
+
+        assert catalog.shard_bounds(300, 0, 2) == (1, 150) and catalog.shard_bounds(300, 1, 2) == (150, 300)
+        got, ref = S.check_catalog("cpu", "tiny", decoder, B=6)      # item table sharded over the 2 ranks
+        assert got.shape == ref.shape
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_two_rank_item_sharded_full_catalog_ranks_match_oracle(decoder):
+    mp.spawn(_catalog_worker, args=(2, _free_port(), decoder), nprocs=2, join=True)
