@@ -98,8 +98,10 @@ SIGNATURES = {
     "carca_eval_plan_floats": [P(ModelParams)],
     "carca_eval_prepare": [vp, vp, P(ModelParams), P(AttrSource), vp],
     "carca_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, vp],
-    "carca_eval_forward_opts": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
-    "carca_eval_forward_catalog": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
+    "carca_eval_forward_opts": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp,
+                                vp],
+    "carca_eval_scratch_bytes": [i32],
+    "carca_eval_forward_catalog": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
@@ -116,6 +118,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         fn.restype = C.c_int
     lib.carca_launch_count.restype = C.c_int64
     lib.carca_eval_plan_floats.restype = C.c_int64
+    lib.carca_eval_scratch_bytes.restype = C.c_int64
     return lib
 
 
@@ -128,8 +131,8 @@ def lib() -> C.CDLL:
                 "(nvcc, sm_100a). carca_replication_b200 has no CPU or PyTorch fallback.")
         loaded = bind(C.CDLL(LIB_PATH))
         got = loaded.carca_abi_version()
-        if got != 1:
-            raise RuntimeError(f"libcarca_b200.so ABI version {got}, expected 1")
+        if got != 2:
+            raise RuntimeError(f"libcarca_b200.so ABI version {got}, expected 2")
         _LIB = loaded
     return _LIB
 

@@ -626,7 +626,8 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
 #ifndef CARCA_EMU
 static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                           int T, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user, void* stream) {
+                           int T, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user, void* scratch,
+                           void* stream) {
   const PlanLayout pl = plan_layout(m);
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -657,8 +658,22 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.cat_lo = cat_lo;
   a.oc_user = ctx_per_user ? m->embed.n_ctx : (long long)T * m->embed.n_ctx;
   a.oc_tgt = ctx_per_user ? 0 : m->embed.n_ctx;
+  // pack the valid profile rows into 64-row bins; scratch: row_src | row_seg (B + 1 bins of 64 rows each: a
+  // tile is two bins, so an odd bin count reads one empty bin past the last) | n_bins
+  const long long rows = ((long long)B + 1) * 64;
+  int* row_src = reinterpret_cast<int*>(scratch);
+  int* row_seg = row_src + rows;
+  int* n_bins = row_seg + rows;
+  cudaMemsetAsync(row_src, 0xff, sizeof(int) * (size_t)rows, S(stream));
+  cudaMemsetAsync(n_bins, 0, sizeof(int), S(stream));
+  {
+    auto pk = pack_rows_kernel;
+    CARCA_LAUNCH(pk, dim3(ceil_div(B, 128)), dim3(128), 0, S(stream), row_src, row_seg, n_bins, p_x, B, L);
+    TRY(check_launch("pack_rows"));
+  }
+  a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
   const size_t smem = sizeof(TcSmem);
-  const int n_tiles = ceil_div(B, 2);
+  const int n_tiles = ceil_div(B, 2);   // upper bound; the kernel reads the packed tile count from n_bins
   if (m->n_heads == 2) {
     auto k = fused_eval_tc_kernel<2>;
     TRY(allow_smem(k, smem));
@@ -675,16 +690,17 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
 static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
                             int T, int variant, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user,
-                            void* stream) {
+                            void* scratch, void* stream) {
   const int d = m->embed.d, H = m->n_heads;
   const bool common_ok = d == FD && L >= 1 && m->embed.n_ctx <= 8 && m->n_blocks <= FMAXB && H >= 1 && FD % H == 0;
   const bool ffma_ok = common_ok && L <= FLP && (FD / H) % 4 == 0;
 #ifndef CARCA_EMU
-  const bool tc_ok = common_ok && L <= 64 && (H == 2 || H == 4) && status != nullptr;
+  const bool tc_ok = common_ok && L <= 64 && (H == 2 || H == 4) && status != nullptr && scratch != nullptr;
 #else
   const bool tc_ok = false;
 #endif
-  if (variant == 2 && !tc_ok) return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=64, H in {2,4}, status");
+  if (variant == 2 && !tc_ok)
+    return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=64, H in {2,4}, status and scratch");
   if (variant == 1 && !ffma_ok) return fail(-4, "eval_forward: FFMA kernel needs d=64, L<=52, dh%%4==0");
   if (!ffma_ok && !tc_ok)
     return fail(-4, "eval_forward: fused kernels support d=64, L<=64, C<=8, <=8 blocks (got d=%d L=%d C=%d blocks=%d "
@@ -695,7 +711,7 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
 #ifndef CARCA_EMU
   if (variant == 2 || (variant == 0 && tc_ok))
     return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, cat_lo,
-                           ctx_per_user, stream);
+                           ctx_per_user, scratch, stream);
 #endif
   const PlanLayout pl = plan_layout(m);
   FusedArgs a;
@@ -735,22 +751,25 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
   return check_launch("fused_eval");
 }
 
+int64_t carca_eval_scratch_bytes(int B) { return (int64_t)sizeof(int) * (2ll * (B + 1) * 64 + 4); }
+
 int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream) {
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* scratch,
+                            void* stream) {
   // variant bit 8: o_c holds one context row per user ([B, C], e.g. the base of an expanded [B,T,C] view)
   return eval_forward_any(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, variant & 0xff, status, dbg, dbg_stage,
-                          0, (variant >> 8) & 1, stream);
+                          0, (variant >> 8) & 1, scratch, stream);
 }
 
 int carca_eval_forward_catalog(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                                const int32_t* p_x, const float* p_c, const float* ctx_user, int32_t item_lo,
-                               int n_cand, int B, int L, int variant, int32_t* status, void* stream) {
+                               int n_cand, int B, int L, int variant, int32_t* status, void* scratch, void* stream) {
   CARCA_REQUIRE(item_lo >= 1 && n_cand >= 0 && (long long)item_lo + n_cand <= m->embed.n_items,
                 "eval_forward_catalog: item range [%d, %d) outside the item table [1, %d)", item_lo, item_lo + n_cand,
                 m->embed.n_items);
   return eval_forward_any(y, ldy, col0, plan, m, p_x, p_c, nullptr, ctx_user, B, L, n_cand, variant, status, nullptr,
-                          0, item_lo, 1, stream);
+                          0, item_lo, 1, scratch, stream);
 }
 
 int carca_catalog_rank_count(int32_t* count, const float* y, int64_t ldy, const float* y_pos, const int32_t* pos_item,
@@ -766,7 +785,8 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
                        const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
                        int T, void* stream) {
   // FFMA kernel unless the caller supplies a status word (carca_eval_forward_opts) for the tensor-core one
-  return carca_eval_forward_opts(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, 1, nullptr, nullptr, 0, stream);
+  return carca_eval_forward_opts(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, 1, nullptr, nullptr, 0, nullptr,
+                                 stream);
 }
 
 }  // extern "C"

@@ -66,7 +66,9 @@ struct TcArgs {
   int dbg_stage;                                     //   or (dbg_stage == -1) phase clock ticks of tile 0
   int cat_lo;                                        // > 0: full-catalog mode — candidate t is item cat_lo + t
   long long oc_user, oc_tgt;                         // strides (floats) of o_c over users / candidates ([B,T,C]: T*C, C;
-};                                                   //   one row per user, e.g. an expanded view or catalog mode: C, 0)
+                                                     //   one row per user, e.g. an expanded view or catalog mode: C, 0)
+  const int *row_src, *row_seg, *n_bins;             // packed profile rows (pack_rows_kernel)
+};
 
 struct TcSmem {
   float w[2][2 * TC_WFLOATS];                        // weight ring: [slot][hi | lo]
@@ -78,10 +80,11 @@ struct TcSmem {
   float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
   float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
-  float plast[2][64];
-  int pid[128];
   int oid[128];
-  uint32_t kbits[2][2];                              // valid-key bits: [user][key half]
+  int ulist[128];                                    // segments of the tile: first row | length << 8
+  int uuser[128];                                    //   and their users
+  uint32_t kbits[2][2];                              // valid-key bits: [bin][key half]
+  uint32_t headbits[4];                              // rows that start a segment
   uint64_t bar[2];
   uint32_t tmem_slot;
 };
@@ -240,28 +243,46 @@ __device__ __forceinline__ void layernorm_rows(TcCtx& c, float (&v)[32], const f
     }
 }
 
-// e = mask * (Tfold[id] + Mc ctx (+ pos)) for this thread's features
+__device__ __forceinline__ float ldg_now(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_now4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// e = mask * (Tfold[id] + Mc ctx (+ pos)) for this thread's features, in two steps so that the
+// global loads of the next chunk can stay in flight behind the current chunk's MMAs
 template <int H>
-__device__ __forceinline__ void embed_row(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ ctx,
-                                          const float* __restrict__ pos_row, float (&v)[32]) {
+__device__ __forceinline__ void embed_load(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ ctx,
+                                           float (&v)[32], float (&cv)[8]) {
+  constexpr int N2 = Own<H>::N2;
+  if (id == 0) return;
+  // volatile asm loads: issued HERE (the compiler would otherwise sink plain loads to their first use)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? ldg_now(ctx + k) : 0.f;
+  const float* t = a.Tfold + (long long)id * 64;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2 / 4; ++q) {
+      const float4 x = ldg_now4(t + Own<H>::f0(h, c.half) + 4 * q);
+      float* o = &v[h * N2 + 4 * q];
+      o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    }
+}
+template <int H>
+__device__ __forceinline__ void embed_finish(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ pos_row,
+                                             float (&v)[32], const float (&cv)[8]) {
   constexpr int N2 = Own<H>::N2;
   if (id == 0) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     return;
   }
-  float cv[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? __ldg(ctx + k) : 0.f;
-  const float* t = a.Tfold + (long long)id * 64;
-#pragma unroll
-  for (int h = 0; h < H; ++h)
-#pragma unroll
-    for (int q = 0; q < N2 / 4; ++q) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(t + Own<H>::f0(h, c.half) + 4 * q));
-      float* o = &v[h * N2 + 4 * q];
-      o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
-    }
   if (pos_row) {
 #pragma unroll
     for (int h = 0; h < H; ++h)
@@ -287,22 +308,31 @@ __device__ __forceinline__ void embed_row(const TcArgs& a, const TcCtx& c, int i
     }
   }
 }
+// bits lo..hi (inclusive, clipped to 0..31)
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi) {
+  lo = max(lo, 0);
+  hi = min(hi, 31);
+  return hi < lo ? 0u : ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+}
 
+// stage dumps: rows of the first two users, written at [user][position][feature] of dbg [2, 64, 64]
 template <int H>
-__device__ __forceinline__ void dump_regs(const TcArgs& a, const TcCtx& c, bool on, int stage, const float (&v)[32]) {
+__device__ __forceinline__ void dump_regs(const TcArgs& a, const TcCtx& c, bool on, int stage, int ru, int rp,
+                                          const float (&v)[32]) {
   if (on && a.dbg_stage == stage) {
 #pragma unroll
     for (int h = 0; h < H; ++h)
 #pragma unroll
-      for (int q = 0; q < Own<H>::N2; ++q) a.dbg[c.row * 64 + Own<H>::f0(h, c.half) + q] = v[h * Own<H>::N2 + q];
+      for (int q = 0; q < Own<H>::N2; ++q)
+        a.dbg[(ru * 64 + rp) * 64 + Own<H>::f0(h, c.half) + q] = v[h * Own<H>::N2 + q];
   }
 }
 template <int H>
-__device__ __forceinline__ void dump_tmem(const TcArgs& a, const TcCtx& c, bool on, int stage, int col) {
-  if (on && a.dbg_stage == stage) {
+__device__ __forceinline__ void dump_tmem(const TcArgs& a, const TcCtx& c, bool on, int stage, int ru, int rp, int col) {
+  if (a.dbg != nullptr && a.dbg_stage == stage) {   // warp-uniform: tcgen05.ld is a collective
     float v[32];
     ld_feat<H>(c, col, v);
-    dump_regs<H>(a, c, true, stage, v);
+    dump_regs<H>(a, c, on, stage, ru, rp, v);
   }
 }
 
@@ -351,18 +381,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Masked softmax of this thread's 32 key columns for the two heads of a pair, result stored as the
+template <int W>
+__device__ __forceinline__ void tmem_ld_w(uint32_t a, float (&v)[W]) {
+  if constexpr (W == 8) umma::tmem_ld_1x8(a, v);
+  else if constexpr (W == 16) umma::tmem_ld_1x16(a, v);
+  else umma::tmem_ld_1x32(a, v);
+}
+template <int W>
+__device__ __forceinline__ void tmem_st_w(uint32_t a, const float (&v)[W]) {
+  if constexpr (W == 8) umma::tmem_st_x8(a, v, 0);
+  else if constexpr (W == 16) umma::tmem_st_x16(a, v, 0);
+  else umma::tmem_st_x32(a, v, 0);
+}
+
+// Masked softmax of this thread's W key columns for the two heads of a pair, result stored as the
 // tf32 operand pair P.  bits: allowed keys; sc = log2(e) / sqrt(dh) (scores are scaled AFTER the
 // additive mask in the reference, src/carca.py:253-254: a masked key stays at -inf either way, and a
-// fully masked row is exactly 0, :256).
+// fully masked row is exactly 0, :256).  The two threads of a row cover 2W consecutive keys.
+template <int W>
 __device__ __forceinline__ void softmax_pair(TcCtx& c, uint32_t bits, float sc, uint32_t s0, uint32_t s1, uint32_t p0hi,
                                              uint32_t p0lo, uint32_t p1hi, uint32_t p1lo) {
-  float v0[32], v1[32];
-  umma::tmem_ld_1x32(s0, v0);
-  umma::tmem_ld_1x32(s1, v1);
+  float v0[W], v1[W];
+  tmem_ld_w<W>(s0, v0);
+  tmem_ld_w<W>(s1, v1);
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < W; ++t) {
     const bool ok = (bits >> t) & 1u;
     v0[t] = ok ? v0[t] * sc : -INFINITY;
     v1[t] = ok ? v1[t] * sc : -INFINITY;
@@ -376,7 +420,7 @@ __device__ __forceinline__ void softmax_pair(TcCtx& c, uint32_t bits, float sc, 
   m1 = (m1 == -INFINITY) ? 0.f : m1;
   float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < W; ++t) {
     v0[t] = ex2_approx(v0[t] - m0);
     v1[t] = ex2_approx(v1[t] - m1);
     z0 += v0[t];
@@ -386,21 +430,21 @@ __device__ __forceinline__ void softmax_pair(TcCtx& c, uint32_t bits, float sc, 
   z0 += o.x;
   z1 += o.y;
   const float i0 = z0 > 0.f ? 1.0f / z0 : 0.f, i1 = z1 > 0.f ? 1.0f / z1 : 0.f;
-  float lo[32];
+  float lo[W];
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < W; ++t) {
     v0[t] *= i0;
     lo[t] = umma::tf32_lo(v0[t]);
   }
-  umma::tmem_st_x32(p0hi, v0, 0);
-  umma::tmem_st_x32(p0lo, lo, 0);
+  tmem_st_w<W>(p0hi, v0);
+  tmem_st_w<W>(p0lo, lo);
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
+  for (int t = 0; t < W; ++t) {
     v1[t] *= i1;
     lo[t] = umma::tf32_lo(v1[t]);
   }
-  umma::tmem_st_x32(p1hi, v1, 0);
-  umma::tmem_st_x32(p1lo, lo, 0);
+  tmem_st_w<W>(p1hi, v1);
+  tmem_st_w<W>(p1lo, lo);
 }
 
 template <int H>
@@ -456,39 +500,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   TcTicks tk;
   tk.out = (a.dbg && a.dbg_stage == -1 && blockIdx.x == 0 && c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;
   tk.n = 0;
-  const int n_tiles = (a.B + 1) / 2;
+  const int n_tiles = (a.n_bins[0] + 1) / 2;
   const int n_chunks = (a.T + 127) / 128;
-  const int u = c.row / 64, i = c.row % 64;
+  const int u = c.row / 64, i = c.row % 64;   // bin (64-row half of the tile) and row within it
+  float* const plast = s.k_hi;                // dot decoder: last-position vectors per segment (K is unused there)
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int user0 = tile * 2;
-    const bool dbg_on = a.dbg != nullptr && tile == 0;
     __syncthreads();
     tick(tk, 0);
+    // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
+    const int src = a.row_src[(long long)tile * 128 + c.row];
+    const int seg = src >= 0 ? a.row_seg[(long long)tile * 128 + c.row] : 0;
+    const int ru = src >> 6, rp = src & 63;
+    const int seg0 = seg & 0xff, seglen = (seg >> 8) & 0xff;
+    const int my_pid = src >= 0 ? a.p_x[(long long)ru * L + rp] : 0;
+    const bool head = src >= 0 && i == seg0;
+    const bool dbg_row = a.dbg != nullptr && a.dbg_stage > 0 && src >= 0 && ru < 2;
     if (c.half == 0) {
-      int id = 0;
-      if (user0 + u < a.B && i < L) id = a.p_x[(long long)(user0 + u) * L + i];
-      s.pid[c.row] = id;
-      const uint32_t bits = __ballot_sync(kFull, id != 0);
-      if ((c.tid & 31) == 0) s.kbits[u][w & 1] = bits;
-    } else {   // candidate ids of the first decoder chunk (user 0, targets 0..127)
-      s.oid[c.row] = (c.row < a.T) ? (a.cat_lo > 0 ? a.cat_lo + c.row : a.o_x[(long long)user0 * a.T + c.row]) : 0;
+      const uint32_t bits = __ballot_sync(kFull, my_pid != 0);
+      const uint32_t hb = __ballot_sync(kFull, head);
+      if ((c.tid & 31) == 0) {
+        s.kbits[u][w & 1] = bits;
+        s.headbits[w] = hb;
+      }
     }
     weight_prefetch(c, 0, a.blk[0].wq);
     weight_prefetch(c, 1, a.blk[0].wk);
     __syncthreads();
-    const int my_pid = s.pid[c.row];
-    // allowed keys of this thread's key half in self-attention: valid, causal (j <= i), query valid
-    uint32_t self_bits = 0;
-    if (my_pid != 0) {
-      const int top = i - 32 * c.half;   // keys t of this half with t <= top
-      const uint32_t causal = top >= 31 ? 0xffffffffu : (top < 0 ? 0u : ((2u << top) - 1u));
-      self_bits = s.kbits[u][c.half] & causal;
+    // segment list of the tile (one entry per user): index = number of segment heads before this one
+    const int head_row = 64 * u + seg0;
+    int seg_idx = __popc(s.headbits[head_row >> 5] & ((1u << (head_row & 31)) - 1u));
+    for (int q = 0; q < (head_row >> 5); ++q) seg_idx += __popc(s.headbits[q]);
+    const int n_seg = __popc(s.headbits[0]) + __popc(s.headbits[1]) + __popc(s.headbits[2]) + __popc(s.headbits[3]);
+    if (c.half == 0 && head) {
+      s.ulist[seg_idx] = c.row | (seglen << 8);
+      s.uuser[seg_idx] = ru;
     }
+    // allowed keys of this thread's key half in self-attention: own segment, causal (j <= i), valid
+    // key, valid query
+    const uint32_t self_bits = my_pid != 0 ? (s.kbits[u][c.half] & range_mask(seg0 - 32 * c.half, i - 32 * c.half)) : 0u;
     float v[32];   // the activation this thread carries from phase to phase
     {              // profile embedding (src/carca.py:415)
-      const float* ctx = a.p_c + ((long long)(user0 + u) * L + i) * a.C;
-      embed_row<H>(a, c, my_pid, ctx, a.pos ? a.pos + (long long)i * 64 : nullptr, v);
+      float cv[8];
+      embed_load<H>(a, c, my_pid, a.p_c + ((long long)ru * L + rp) * a.C, v, cv);
+      embed_finish<H>(a, c, my_pid, a.pos ? a.pos + (long long)rp * 64 : nullptr, v, cv);
     }
     tick(tk, 1);
 
@@ -501,7 +556,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<0>();
       publish();
       tick(tk, 2);
-      dump_regs<H>(a, c, dbg_on, 1 + 10 * b, v);
+      dump_regs<H>(a, c, dbg_row, 1 + 10 * b, ru, rp, v);
       // Q from LN1(x), K from raw x (:238-239), separate completion events
       if (issuer_warp) {
         if (umma::elect_one()) {
@@ -530,16 +585,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 4);
       if (issuer_warp) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);        // V (:240)
+          issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);      // V (:240)
           commit(c);
         }
         c.ncommit++;
       }
       wait_mma(c);
       tick(tk, 5);
-      dump_tmem<H>(a, c, dbg_on, 2 + 10 * b, C_ACCQ);
-      dump_tmem<H>(a, c, dbg_on, 3 + 10 * b, C_ACCK);
-      dump_tmem<H>(a, c, dbg_on, 4 + 10 * b, C_ACCV);
+      dump_tmem<H>(a, c, dbg_row, 2 + 10 * b, ru, rp, C_ACCQ);
+      dump_tmem<H>(a, c, dbg_row, 3 + 10 * b, ru, rp, C_ACCK);
+      dump_tmem<H>(a, c, dbg_row, 4 + 10 * b, ru, rp, C_ACCV);
       store_v_operand<H>(c, C_ACCV);
       weight_prefetch(c, 0, wb.w2);
       if (!a.residual_sa) {
@@ -568,11 +623,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         tick(tk, 20);
         {
           const uint32_t r0 = c.tmem + C_XHI, r1 = c.tmem + C_ACCK, k = 32 * c.half;
-          softmax_pair(c, self_bits, sc, r0 + 64 * u + k, r1 + 64 * u + k, r0 + k, r0 + 64 + k, r1 + k, r1 + 64 + k);
+          softmax_pair<32>(c, self_bits, sc, r0 + 64 * u + k, r1 + 64 * u + k, r0 + k, r0 + 64 + k, r1 + k, r1 + 64 + k);
         }
         publish();
         tick(tk, 21);
-        if (issuer_warp) {   // O_h = P_h V_h for both users' V at once (each row keeps its own user's columns)
+        if (issuer_warp) {   // O_h = P_h V_h for both bins' V at once (each row keeps its own bin's columns)
           if (umma::elect_one()) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -608,7 +663,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           umma::fence_after_sync();
         }
       }
-      dump_regs<H>(a, c, dbg_on, 5 + 10 * b, v);
+      dump_regs<H>(a, c, dbg_row, 5 + 10 * b, ru, rp, v);
       layernorm_rows<H>(c, v, s.ln[4 * b + 2], s.ln[4 * b + 3]);   // LN2 (:304); v = s2 from here on
       st_operand<H>(c, C_XHI, C_XLO, v);
       weight_wait<0>();
@@ -616,7 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 7);
       if (issuer_warp) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);       // ffn_1 (:307)
+          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);     // ffn_1 (:307)
           commit(c);
         }
         c.ncommit++;
@@ -634,7 +689,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 9);
       if (issuer_warp) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);     // ffn_2 (:311)
+          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);   // ffn_2 (:311)
           commit(c);
         }
         c.ncommit++;
@@ -655,12 +710,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = a.residual_sa ? v[j] + f[j] : f[j];
       }
-      dump_regs<H>(a, c, dbg_on, 9 + 10 * b, v);
+      dump_regs<H>(a, c, dbg_row, 9 + 10 * b, ru, rp, v);
       tick(tk, 11);
     }
 
     layernorm_rows<H>(c, v, s.ln[4 * a.n_blocks], s.ln[4 * a.n_blocks + 1]);   // final LayerNorm (:421)
-    dump_regs<H>(a, c, dbg_on, 100, v);
+    dump_regs<H>(a, c, dbg_row, 100, ru, rp, v);
     if (a.decoder == 1) {   // keys / values of the encoded profile (:239-240 with p as key and value)
       st_operand<H>(c, C_QNHI, C_QNLO, v);
       weight_wait<0>();
@@ -674,34 +729,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
         c.ncommit++;
       }
+    }
+    // candidate ids of the first decoder chunk (first segment of the tile, targets 0..127)
+    if (c.half == 1) {
+      const int usr = s.uuser[0];
+      s.oid[c.row] = (c.row < a.T) ? (a.cat_lo > 0 ? a.cat_lo + c.row : a.o_x[(long long)usr * a.T + c.row]) : 0;
+    }
+    if (a.decoder == 1) {
       wait_mma(c);
       weight_prefetch(c, 0, a.dwq);
       store_k_operand<H>(c, C_ACCK);
       store_v_operand<H>(c, C_ACCV);
       weight_wait<0>();
       tick(tk, 13);
-    } else if (i == L - 1) {   // dot decoder: only the last profile position is used (:362)
+    } else if (src >= 0 && rp == L - 1) {   // dot decoder: only the last profile position is used (:362)
 #pragma unroll
       for (int h = 0; h < H; ++h)
 #pragma unroll
-        for (int q = 0; q < N2; ++q) s.plast[u][Own<H>::f0(h, c.half) + q] = v[h * N2 + q];
+        for (int q = 0; q < N2; ++q) plast[seg_idx * 64 + Own<H>::f0(h, c.half) + q] = v[h * N2 + q];
     }
 
+    // ---- decoder: one [128 candidates x 64 keys of the user's bin] problem per (segment, chunk)
+    __syncthreads();   // s.oid, K/V/plast stores are visible
+    const int n_iter = n_seg * n_chunks;
+    int oid = s.oid[c.row];
+    float e[32], cv[8];
+    {
+      const int usr = s.uuser[0];
+      embed_load<H>(a, c, oid, a.o_c + (long long)usr * a.oc_user + (long long)min(c.row, a.T - 1) * a.oc_tgt, e, cv);
+    }
 #pragma unroll 1
-    for (int q = 0; q < 2 * n_chunks; ++q) {
-      const int du = q / n_chunks, t0 = (q % n_chunks) * 128;
-      if (user0 + du >= a.B) break;
+    for (int q = 0; q < n_iter; ++q) {
+      const int si = q / n_chunks, t0 = (q % n_chunks) * 128;
       const int nq = min(128, a.T - t0);
-      __syncthreads();   // s.oid holds this chunk's ids; K/V/plast stores are visible
-      const int oid = s.oid[c.row];
-      float e[32];       // target embedding (:426), also the residual of the decoder
-      {
-        const float* ctx = a.o_c + (long long)(user0 + du) * a.oc_user + (long long)(t0 + min(c.row, nq - 1)) * a.oc_tgt;
-        embed_row<H>(a, c, oid, ctx, nullptr, e);
-      }
+      const int usr = s.uuser[si], ul = s.ulist[si];
+      const int ubin = (ul & 0xff) >> 6, useg0 = ul & 63, ulen = ul >> 8;
+      embed_finish<H>(a, c, oid, nullptr, e, cv);   // target embedding (:426)
       tick(tk, 14);
       float acc = 0.f;
+      const int q1 = q + 1;
+      const int si1 = q1 / n_chunks, t1 = (q1 % n_chunks) * 128;
       if (a.decoder == 1) {
+        if (a.residual_ca) {   // residual term of the score: <o, wf> (:343,:345), o itself is not kept
+#pragma unroll
+          for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], s.dwf[Own<H>::f0(h, c.half) + qq], acc);
+        }
         st_operand<H>(c, C_XHI, C_XLO, e);
         publish();
         if (issuer_warp) {
@@ -711,17 +785,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           }
           c.ncommit++;
         }
-      } else {
-        __syncthreads();
-      }
-      if (q + 1 < 2 * n_chunks && c.half == 1) {   // ids of the next chunk (s.oid was consumed above)
-        const int du1 = (q + 1) / n_chunks, t1 = ((q + 1) % n_chunks) * 128;
-        int id = 0;
-        if (user0 + du1 < a.B && t1 + c.row < a.T)
-          id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)(user0 + du1) * a.T + t1 + c.row];
-        s.oid[c.row] = id;
-      }
-      if (a.decoder == 1) {
+        // key window of this segment: the thread pair covers 2W consecutive keys starting at kw0 (multiple of
+        // 8) that contain [useg0, useg0 + ulen); softmax and PV touch only that window
+        const int wl = ((useg0 + ulen + 7) & ~7) - (useg0 & ~7);
+        const int W = wl <= 16 ? 8 : (wl <= 32 ? 16 : 32);
+        const int kw0 = min(useg0 & ~7, 64 - 2 * W);
+        uint32_t cross_bits = 0;
+        if (oid != 0) {
+          const unsigned long long valid = ((unsigned long long)s.kbits[ubin][1] << 32) | s.kbits[ubin][0];
+          const unsigned long long segm = (ulen >= 64 ? ~0ull : ((1ull << ulen) - 1ull)) << useg0;
+          cross_bits = (uint32_t)((valid & segm) >> (kw0 + c.half * W));
+          if (W < 32) cross_bits &= (1u << W) - 1u;
+        }
+        if (q1 < n_iter && c.half == 1) {   // ids of the next chunk (s.oid was consumed before the publish)
+          const int usr1 = s.uuser[si1];
+          int id = 0;
+          if (t1 + c.row < a.T) id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)usr1 * a.T + t1 + c.row];
+          s.oid[c.row] = id;
+        }
         wait_mma(c);
         tick(tk, 15);
         {
@@ -732,7 +813,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           st_feat<H>(c, C_QNLO, qv);
         }
         publish();
-        const uint32_t cross_bits = oid != 0 ? s.kbits[du][c.half] : 0u;
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
           if (issuer_warp) {
@@ -740,7 +820,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
               for (int ee = 0; ee < 2; ++ee) {
                 const int h = hp + ee;
-                const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)du * 64u * 16u;
+                const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)ubin * 64u * 16u;
                 issue_3x<64, DH / 8>(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
                                      umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
               }
@@ -748,12 +828,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             }
             c.ncommit++;
           }
+          // gather of the next chunk's candidate rows: in flight while this chunk's attention runs
+          if (hp == 0 && q1 < n_iter) {
+            oid = s.oid[c.row];
+            const int usr1 = s.uuser[si1];
+            embed_load<H>(a, c, oid,
+                          a.o_c + (long long)usr1 * a.oc_user + (long long)min(t1 + c.row, a.T - 1) * a.oc_tgt, e, cv);
+          }
           wait_mma(c);
           tick(tk, 20);
           {
-            const uint32_t k = 32 * c.half;
-            softmax_pair(c, cross_bits, sc, c.tmem + C_XHI + k, c.tmem + C_XLO + k, c.tmem + C_XHI + k,
-                         c.tmem + C_ACCK + k, c.tmem + C_XLO + k, c.tmem + C_ACCV + k);
+            const uint32_t k = kw0 + W * c.half;
+            const uint32_t t = c.tmem + k;
+            if (W == 8) softmax_pair<8>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
+            else if (W == 16) softmax_pair<16>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
+            else softmax_pair<32>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
           }
           publish();
           tick(tk, 21);
@@ -762,9 +851,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
               for (int ee = 0; ee < 2; ++ee) {
                 const int h = hp + ee;
-                const uint32_t voff = (uint32_t)(h * 2 * DH + du * DH) * 16u;
-                issue_3x<DH, 8>(tmem0 + C_QNHI + h * DH, tmem0 + (ee ? C_XLO : C_XHI), tmem0 + (ee ? C_ACCV : C_ACCK),
-                                umma::smem_u32(s.v_hi) + voff, umma::smem_u32(s.v_lo) + voff, (uint32_t)TC_VLBO);
+                // keys kw0 .. kw0 + 2W of the bin: P columns from kw0, V key chunks from kw0 / 4
+                const uint32_t voff = (uint32_t)(h * 2 * DH + ubin * DH) * 16u + (uint32_t)(kw0 / 4) * (uint32_t)TC_VLBO;
+                const uint32_t d = tmem0 + C_QNHI + h * DH;
+                const uint32_t phi = tmem0 + (ee ? C_XLO : C_XHI) + kw0, plo = tmem0 + (ee ? C_ACCV : C_ACCK) + kw0;
+                const uint32_t vh = umma::smem_u32(s.v_hi) + voff, vl = umma::smem_u32(s.v_lo) + voff;
+                if (W == 8) issue_3x<DH, 2>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
+                else if (W == 16) issue_3x<DH, 4>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
+                else issue_3x<DH, 8>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
               }
               commit(c);
             }
@@ -779,10 +873,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
           for (int h = 0; h < H; ++h)
 #pragma unroll
-            for (int qq = 0; qq < N2; ++qq) {
-              const float sv = o[h * N2 + qq] + (a.residual_ca ? e[h * N2 + qq] : 0.f);
-              acc = fmaf(sv, s.dwf[Own<H>::f0(h, c.half) + qq], acc);
-            }
+            for (int qq = 0; qq < N2; ++qq) acc = fmaf(o[h * N2 + qq], s.dwf[Own<H>::f0(h, c.half) + qq], acc);
         }
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
         acc += __ldg(a.dbf);
@@ -790,11 +881,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
-          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], s.plast[du][Own<H>::f0(h, c.half) + qq], acc);
+          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], plast[si * 64 + Own<H>::f0(h, c.half) + qq], acc);
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
+        __syncthreads();   // every thread has consumed s.oid / e of this chunk
+        if (q1 < n_iter) {
+          const int usr1 = s.uuser[si1];
+          if (c.half == 1) {
+            int id = 0;
+            if (t1 + c.row < a.T) id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)usr1 * a.T + t1 + c.row];
+            s.oid[c.row] = id;
+          }
+          __syncthreads();
+          oid = s.oid[c.row];
+          embed_load<H>(a, c, oid, a.o_c + (long long)usr1 * a.oc_user + (long long)min(t1 + c.row, a.T - 1) * a.oc_tgt,
+                        e, cv);
+        }
       }
       if (c.half == 0 && c.row < nq)
-        a.y[(long long)(user0 + du) * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
+        a.y[(long long)usr * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
       tick(tk, 23);
     }
     tk.out = nullptr;   // first tile only
@@ -802,6 +906,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   umma::fence_before_sync();
   __syncthreads();
   if (w == 0) umma::tmem_free(tmem0, 512);
+}
+
+// Packs the valid profile positions of every user into 64-row bins (two bins = one 128-row tile of
+// the kernel above).  Beauty-shaped profiles are mostly left padding (src/data.py:112-113, mean ~8
+// of 50 positions valid): padded rows never influence a valid row (they are masked as keys,
+// src/carca.py:246-251) and only valid rows (ca decoder: keys/values; dot decoder: position L-1)
+// are read by the decoder, so the encoder runs on valid rows only.  A user's rows stay contiguous
+// and in sequence order inside one bin (causal mask = row order); position L-1 is always included
+// (the dot decoder reads it even when it is padding, src/carca.py:362).
+//   row_src[bin*64 + r] = user*64 + position (or -1), row_seg = segment start | length << 8.
+// One 128-thread block packs 128 consecutive users (next-fit) and claims its bins with one atomicAdd.
+__global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
+                                                        int* __restrict__ n_bins, const int* __restrict__ p_x, int B,
+                                                        int L) {
+  __shared__ int cnt[128], bin_of[128], start_of[128], base;
+  const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
+  int n = 0;
+  if (usr < B) {
+    const int* x = p_x + (long long)usr * L;
+    for (int j = 0; j < L; ++j) n += (x[j] != 0) || (j == L - 1);
+  }
+  cnt[t] = n;
+  __syncthreads();
+  if (t == 0) {
+    int bin = 0, fill = 0;
+    const int users = min(128, B - blockIdx.x * 128);
+    for (int q = 0; q < users; ++q) {
+      if (fill + cnt[q] > 64) {
+        ++bin;
+        fill = 0;
+      }
+      bin_of[q] = bin;
+      start_of[q] = fill;
+      fill += cnt[q];
+    }
+    base = atomicAdd(n_bins, bin + 1);
+  }
+  __syncthreads();
+  if (usr < B) {
+    const int* x = p_x + (long long)usr * L;
+    const long long o = (long long)(base + bin_of[t]) * 64;
+    int r = start_of[t];
+    const int seg = start_of[t] | (n << 8);
+    for (int j = 0; j < L; ++j) {
+      if (x[j] != 0 || j == L - 1) {
+        row_src[o + r] = usr * 64 + j;
+        row_seg[o + r] = seg;
+        ++r;
+      }
+    }
+  }
 }
 
 // Packs W [64 out, 64 in] (+ bias [64]) into the K-major B operand of umma.cuh with the bias as

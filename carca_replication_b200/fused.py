@@ -123,6 +123,23 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
     return plan, status
 
 
+_scratch_cache: dict = {}
+
+
+def _scratch(B: int, device) -> Tensor:
+    """Row-packing scratch of the tensor-core kernel (carca_eval_scratch_bytes), reused per batch size.
+    Calls on one stream are ordered, so a single buffer per (device, B) is enough."""
+    key = (str(device), int(B))
+    buf = _scratch_cache.get(key)
+    if buf is None:
+        if len(_scratch_cache) > 8:
+            _scratch_cache.clear()
+        nbytes = int(N.lib().carca_eval_scratch_bytes(int(B)))
+        buf = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
 def mma_timed_out(model) -> bool:
     """True if a tensor-core completion wait ever timed out for this model's plan (device sync)."""
     hit = _plans.get(model)
@@ -157,7 +174,7 @@ def forward(model, profile, targets: Sequence, variant: Optional[int] = None, db
     v = (VARIANT if variant is None else int(variant)) | (0x100 if per_user_ctx else 0)
     N.call("carca_eval_forward_opts", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
            N.i32p(o_x), N.f32p(o_c), B, L, T, v, N.i32p(status),
-           None if dbg is None else N.f32p(dbg), int(dbg_stage), N.stream())
+           None if dbg is None else N.f32p(dbg), int(dbg_stage), _scratch(B, p_x.device).data_ptr(), N.stream())
     del keep
     return y
 
@@ -177,6 +194,6 @@ def forward_catalog(model, profile, ctx_user: Tensor, item_lo: int, n_cand: int,
     y = torch.empty((B, n_cand), dtype=torch.float32, device=p_x.device)
     N.call("carca_eval_forward_catalog", N.f32p(y), n_cand, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
            N.f32p(ctx_user), int(item_lo), int(n_cand), B, L, VARIANT if variant is None else int(variant),
-           N.i32p(status), N.stream())
+           N.i32p(status), _scratch(B, p_x.device).data_ptr(), N.stream())
     del keep
     return y

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CARCA_B200_ABI_VERSION 1
+#define CARCA_B200_ABI_VERSION 2
 
 const char* carca_last_error(void);
 int carca_abi_version(void);
@@ -268,7 +268,14 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
  * (what src/data.py:185 builds; lets the host pass the base of an expanded [B,T,C] view).      */
 int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* stream);
+                            int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* scratch,
+                            void* stream);
+
+/* Bytes of device scratch the tensor-core kernel needs for a batch of B users (variant 0 / 2): it
+ * first packs the VALID profile positions of every user into 64-row bins — Beauty-shaped profiles
+ * are mostly left padding (src/data.py:112-113) and padded rows influence nothing the decoder reads
+ * (src/carca.py:246-251) — so the encoder runs on valid rows only.                              */
+int64_t carca_eval_scratch_bytes(int B);
 
 /* ------------------------------------------------------------------ full-catalog scoring */
 /* Scores every item of the contiguous id range [item_lo, item_lo + n_cand) (an item-table shard)
@@ -280,7 +287,7 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
  * no candidate id / context tensors are read.                                                   */
 int carca_eval_forward_catalog(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                                const int32_t* p_x, const float* p_c, const float* ctx_user, int32_t item_lo,
-                               int n_cand, int B, int L, int variant, int32_t* status, void* stream);
+                               int n_cand, int B, int L, int variant, int32_t* status, void* scratch, void* stream);
 
 /* count[b] += number of candidates j of this shard that a stable descending sort (src/train.py:16)
  * ranks before the positive: y[b,j] > y_pos[b], or equal with item_lo + j < pos_item[b].  Summed

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 20
     for name in names:
         assert hasattr(lib, name), f"{name} declared in carca_b200.h but not exported"
-    assert lib.carca_abi_version() == 1
+    assert lib.carca_abi_version() == 2
 
 
 def test_python_binding_covers_the_header():
