@@ -529,20 +529,25 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
 // ------------------------------------------------------------------------------------ fused inference
 namespace {
 struct PlanLayout {
-  long long tfold, mc, blocks, cross, tc_blocks, tc_cross, total;
+  long long tfold, mc, blocks, cross, tc_blocks, tc_cross, tq, tw, mcq, mcw, total;
 };
 constexpr long long kTcPacked = 2 * 18 * 64 * 4;   // floats of one packed tensor-core weight (hi | lo)
 PlanLayout plan_layout(const carca_model_params* m) {
   PlanLayout p;
-  const long long d = m->embed.d;
+  const long long d = m->embed.d, n = m->embed.n_items;
   p.tfold = 0;
-  p.mc = p.tfold + (long long)m->embed.n_items * d;
+  p.mc = p.tfold + n * d;
   p.blocks = p.mc + d * 8;
   p.cross = p.blocks + (long long)m->n_blocks * 5 * d * d;
   p.tc_blocks = p.cross + (m->decoder_kind == 1 ? 3 * d * d : 0);
   const bool tc = d == 64;   // packed operands of the tcgen05 kernel (fused_eval_tc.cuh)
+  const bool tcx = tc && m->decoder_kind == 1;
   p.tc_cross = p.tc_blocks + (tc ? (long long)m->n_blocks * 5 * kTcPacked : 0);
-  p.total = p.tc_cross + ((tc && m->decoder_kind == 1) ? 3 * kTcPacked : 0);
+  p.tq = p.tc_cross + (tcx ? 3 * kTcPacked : 0);
+  p.tw = p.tq + (tcx ? n * 64 : 0);
+  p.mcq = p.tw + (tcx ? (n + 3) / 4 * 4 : 0);
+  p.mcw = p.mcq + (tcx ? 64 * 8 : 0);
+  p.total = p.mcw + (tcx ? 8 : 0);
   return p;
 }
 }  // namespace
@@ -617,6 +622,23 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
         CARCA_LAUNCH(pk, dim3(5), dim3(256), 0, st, plan + pl.tc_cross + (long long)i * kTcPacked, ws[i], bs[i]);
         TRY(check_launch("pack_weight_tc"));
       }
+      // candidate-side folds of the decoder (exact re-associations of linear maps, like the item table):
+      //   TQ[i] = WQ T[i] + bq  (the query of candidate i before its context term),  tw[i] = <T[i], wf>,
+      //   McQ = WQ Mc,  mcw = wf Mc,  so Q = TQ[x] + McQ c  and  <o, wf> = tw[x] + <mcw, c>.
+      TRY(linear(plan + pl.tq, T, m->cross.wq, m->cross.bq, n, 64, 64, 64, st));
+      TRY(linear(plan + pl.tw, T, m->cross.wf, nullptr, n, 1, 64, 64, st));
+      {
+        GemmArgs gm = gemm_defaults(m->cross.wq, plan + pl.mc, plan + pl.mcq, 64, 8, 64);
+        gm.transB = 0;
+        gm.ldb = 8;
+        gm.ldc = 8;
+        TRY(launch_gemm(gm, st));
+        GemmArgs gw = gemm_defaults(m->cross.wf, plan + pl.mc, plan + pl.mcw, 1, 8, 64);
+        gw.transB = 0;
+        gw.ldb = 8;
+        gw.ldc = 8;
+        TRY(launch_gemm(gw, st));
+      }
     }
   }
 #endif
@@ -649,8 +671,9 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.fn_g = m->norm_g; a.fn_b = m->norm_b;
   if (m->decoder_kind == 1) {
     const float* wt = plan + pl.tc_cross;
-    a.dwq = wt; a.dwk = wt + kTcPacked; a.dwv = wt + 2 * kTcPacked;
+    a.dwk = wt + kTcPacked; a.dwv = wt + 2 * kTcPacked;
     a.dwf = m->cross.wf; a.dbf = m->cross.bf;
+    a.TQ = plan + pl.tq; a.tw = plan + pl.tw; a.McQ = plan + pl.mcq; a.mcw = plan + pl.mcw;
   }
   a.status = status;
   a.dbg = dbg;

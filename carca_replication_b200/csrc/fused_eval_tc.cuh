@@ -59,8 +59,10 @@ struct TcArgs {
   int B, L, T, C, H, n_blocks, residual_sa, residual_ca, decoder;
   TcBlockW blk[FMAXB];
   const float *fn_g, *fn_b;
-  const float *dwq, *dwk, *dwv;                      // packed decoder projections
+  const float *dwk, *dwv;                            // packed decoder K / V projections
   const float *dwf, *dbf;
+  const float *TQ, *tw;                              // folded candidate tables: WQ T[i] + bq [n_items, 64], <T[i], wf> [n_items]
+  const float *McQ, *mcw;                            //   and their context maps: WQ Mc [64, 8], wf Mc [8]
   int* status;                                       // [0] set to 1 if an MMA wait timed out
   float* dbg;                                        // optional [128, 64]: activation `dbg_stage` of tile 0,
   int dbg_stage;                                     //   or (dbg_stage == -1) phase clock ticks of tile 0
@@ -77,6 +79,8 @@ struct TcSmem {
   float v_hi[TC_VFLOATS];
   float v_lo[TC_VFLOATS];
   float mct[8][64];                                  // folded context map, [context k][feature]
+  float mcqt[8][64];                                 // the same through the decoder's WQ
+  float mcw[8];                                      //   and through its ffn weight
   float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
   float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
@@ -88,6 +92,8 @@ struct TcSmem {
   uint64_t bar[2];
   uint32_t tmem_slot;
 };
+
+static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB of shared memory a CTA can have");
 
 struct TcCtx {
   TcSmem* s;
@@ -248,6 +254,11 @@ __device__ __forceinline__ float ldg_now(const float* p) {
   asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ int ldg_now_i(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float4 ldg_now4(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -257,14 +268,14 @@ __device__ __forceinline__ float4 ldg_now4(const float* p) {
 // e = mask * (Tfold[id] + Mc ctx (+ pos)) for this thread's features, in two steps so that the
 // global loads of the next chunk can stay in flight behind the current chunk's MMAs
 template <int H>
-__device__ __forceinline__ void embed_load(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ ctx,
-                                           float (&v)[32], float (&cv)[8]) {
+__device__ __forceinline__ void embed_load(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ table,
+                                           const float* __restrict__ ctx, float (&v)[32], float (&cv)[8]) {
   constexpr int N2 = Own<H>::N2;
   if (id == 0) return;
   // volatile asm loads: issued HERE (the compiler would otherwise sink plain loads to their first use)
 #pragma unroll
   for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? ldg_now(ctx + k) : 0.f;
-  const float* t = a.Tfold + (long long)id * 64;
+  const float* t = table + (long long)id * 64;
 #pragma unroll
   for (int h = 0; h < H; ++h)
 #pragma unroll
@@ -275,8 +286,8 @@ __device__ __forceinline__ void embed_load(const TcArgs& a, const TcCtx& c, int 
     }
 }
 template <int H>
-__device__ __forceinline__ void embed_finish(const TcArgs& a, const TcCtx& c, int id, const float* __restrict__ pos_row,
-                                             float (&v)[32], const float (&cv)[8]) {
+__device__ __forceinline__ void embed_finish(const TcArgs& a, const TcCtx& c, int id, const float (*ctab)[64],
+                                             const float* __restrict__ pos_row, float (&v)[32], const float (&cv)[8]) {
   constexpr int N2 = Own<H>::N2;
   if (id == 0) {
 #pragma unroll
@@ -300,7 +311,7 @@ __device__ __forceinline__ void embed_finish(const TcArgs& a, const TcCtx& c, in
       for (int h = 0; h < H; ++h)
 #pragma unroll
         for (int q = 0; q < N2 / 4; ++q) {
-          const float4 m = *reinterpret_cast<const float4*>(&c.s->mct[k][Own<H>::f0(h, c.half) + 4 * q]);
+          const float4 m = *reinterpret_cast<const float4*>(&ctab[k][Own<H>::f0(h, c.half) + 4 * q]);
           float* o = &v[h * N2 + 4 * q];
           o[0] = fmaf(m.x, cv[k], o[0]); o[1] = fmaf(m.y, cv[k], o[1]);
           o[2] = fmaf(m.z, cv[k], o[2]); o[3] = fmaf(m.w, cv[k], o[3]);
@@ -487,6 +498,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     s.ln[r][f] = src[f];
   }
   if (c.tid < 64) s.dwf[c.tid] = a.decoder == 1 ? a.dwf[c.tid] : 0.f;
+  if (a.decoder == 1) {
+    for (int i = c.tid; i < 64 * 8; i += TC_THREADS) s.mcqt[i % 8][i / 8] = a.McQ[i];
+    if (c.tid < 8) s.mcw[c.tid] = a.mcw[c.tid];
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -542,8 +557,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     float v[32];   // the activation this thread carries from phase to phase
     {              // profile embedding (src/carca.py:415)
       float cv[8];
-      embed_load<H>(a, c, my_pid, a.p_c + ((long long)ru * L + rp) * a.C, v, cv);
-      embed_finish<H>(a, c, my_pid, a.pos ? a.pos + (long long)rp * 64 : nullptr, v, cv);
+      embed_load<H>(a, c, my_pid, a.Tfold, a.p_c + ((long long)ru * L + rp) * a.C, v, cv);
+      embed_finish<H>(a, c, my_pid, s.mct, a.pos ? a.pos + (long long)rp * 64 : nullptr, v, cv);
     }
     tick(tk, 1);
 
@@ -730,17 +745,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         c.ncommit++;
       }
     }
-    // candidate ids of the first decoder chunk (first segment of the tile, targets 0..127)
-    if (c.half == 1) {
-      const int usr = s.uuser[0];
-      s.oid[c.row] = (c.row < a.T) ? (a.cat_lo > 0 ? a.cat_lo + c.row : a.o_x[(long long)usr * a.T + c.row]) : 0;
-    }
     if (a.decoder == 1) {
       wait_mma(c);
-      weight_prefetch(c, 0, a.dwq);
       store_k_operand<H>(c, C_ACCK);
       store_v_operand<H>(c, C_ACCV);
-      weight_wait<0>();
       tick(tk, 13);
     } else if (src >= 0 && rp == L - 1) {   // dot decoder: only the last profile position is used (:362)
 #pragma unroll
@@ -749,70 +757,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         for (int q = 0; q < N2; ++q) plast[seg_idx * 64 + Own<H>::f0(h, c.half) + q] = v[h * N2 + q];
     }
 
-    // ---- decoder: one [128 candidates x 64 keys of the user's bin] problem per (segment, chunk)
+    // ---- decoder: one [128 candidates x 64 keys of the user's bin] problem per (segment, chunk).
+    // Software pipeline over iterations q: candidate ids of q+2 are loaded into a register, ids of q+1 sit in
+    // s.oid, and the table rows of q+1 are gathered into registers while the MMAs of q run.
+    // cross-attention: the candidate's query comes from the folded table TQ (= WQ e + bq, carca_eval_prepare),
+    // so an iteration is  Q -> TMEM, scores MMA, softmax, PV MMA, <O, wf> + <e, wf> + bf  (src/carca.py:338-347).
+    const bool ca = a.decoder == 1;
+    const float* const tab = ca ? a.TQ : a.Tfold;
+    const float(*const ctab)[64] = ca ? s.mcqt : s.mct;
+    auto cand_id = [&](int usr, int t) -> int {
+      return t < a.T ? (a.cat_lo > 0 ? a.cat_lo + t : ldg_now_i(a.o_x + (long long)usr * a.T + t)) : 0;
+    };
+    auto gather = [&](int id, int usr, int t, float(&e)[32], float(&cv)[8], float& twv) {
+      embed_load<H>(a, c, id, tab, a.o_c + (long long)usr * a.oc_user + (long long)min(t, a.T - 1) * a.oc_tgt, e, cv);
+      if (ca && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
+    };
+    if (c.half == 1) s.oid[c.row] = cand_id(s.uuser[0], c.row);
     __syncthreads();   // s.oid, K/V/plast stores are visible
     const int n_iter = n_seg * n_chunks;
     int oid = s.oid[c.row];
-    float e[32], cv[8];
-    {
-      const int usr = s.uuser[0];
-      embed_load<H>(a, c, oid, a.o_c + (long long)usr * a.oc_user + (long long)min(c.row, a.T - 1) * a.oc_tgt, e, cv);
+    __syncthreads();   // s.oid is rewritten at the top of iteration 0
+    float e[32], cv[8], twv = 0.f;
+    gather(oid, s.uuser[0], c.row, e, cv, twv);
+    int si = 0, ch = 0, idn = 0;
+    if (c.half == 1 && n_iter > 1) {
+      const int s1 = n_chunks > 1 ? 0 : 1, c1 = n_chunks > 1 ? 1 : 0;
+      idn = cand_id(s.uuser[s1], c1 * 128 + c.row);
     }
 #pragma unroll 1
     for (int q = 0; q < n_iter; ++q) {
-      const int si = q / n_chunks, t0 = (q % n_chunks) * 128;
+      const int t0 = ch * 128;
       const int nq = min(128, a.T - t0);
       const int usr = s.uuser[si], ul = s.ulist[si];
       const int ubin = (ul & 0xff) >> 6, useg0 = ul & 63, ulen = ul >> 8;
-      embed_finish<H>(a, c, oid, nullptr, e, cv);   // target embedding (:426)
+      int si1 = si, ch1 = ch + 1;
+      if (ch1 == n_chunks) { ch1 = 0; ++si1; }
+      int si2 = si1, ch2 = ch1 + 1;
+      if (ch2 == n_chunks) { ch2 = 0; ++si2; }
+      const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
+      embed_finish<H>(a, c, oid, ctab, nullptr, e, cv);   // candidate embedding (:426), or its query for `ca`
       tick(tk, 14);
       float acc = 0.f;
-      const int q1 = q + 1;
-      const int si1 = q1 / n_chunks, t1 = (q1 % n_chunks) * 128;
-      if (a.decoder == 1) {
-        if (a.residual_ca) {   // residual term of the score: <o, wf> (:343,:345), o itself is not kept
-#pragma unroll
-          for (int h = 0; h < H; ++h)
-#pragma unroll
-            for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], s.dwf[Own<H>::f0(h, c.half) + qq], acc);
-        }
-        st_operand<H>(c, C_XHI, C_XLO, e);
-        publish();
-        if (issuer_warp) {
-          if (umma::elect_one()) {
-            issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[0]);   // Q of the targets
-            commit(c);
-          }
-          c.ncommit++;
-        }
+      uint32_t cross_bits = 0;
+      int W = 32, kw0 = 0;
+      if (ca) {
         // key window of this segment: the thread pair covers 2W consecutive keys starting at kw0 (multiple of
         // 8) that contain [useg0, useg0 + ulen); softmax and PV touch only that window
         const int wl = ((useg0 + ulen + 7) & ~7) - (useg0 & ~7);
-        const int W = wl <= 16 ? 8 : (wl <= 32 ? 16 : 32);
-        const int kw0 = min(useg0 & ~7, 64 - 2 * W);
-        uint32_t cross_bits = 0;
+        W = wl <= 16 ? 8 : (wl <= 32 ? 16 : 32);
+        kw0 = min(useg0 & ~7, 64 - 2 * W);
         if (oid != 0) {
           const unsigned long long valid = ((unsigned long long)s.kbits[ubin][1] << 32) | s.kbits[ubin][0];
           const unsigned long long segm = (ulen >= 64 ? ~0ull : ((1ull << ulen) - 1ull)) << useg0;
           cross_bits = (uint32_t)((valid & segm) >> (kw0 + c.half * W));
           if (W < 32) cross_bits &= (1u << W) - 1u;
-        }
-        if (q1 < n_iter && c.half == 1) {   // ids of the next chunk (s.oid was consumed before the publish)
-          const int usr1 = s.uuser[si1];
-          int id = 0;
-          if (t1 + c.row < a.T) id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)usr1 * a.T + t1 + c.row];
-          s.oid[c.row] = id;
-        }
-        wait_mma(c);
-        tick(tk, 15);
-        {
-          float qv[32];
-          ld_feat<H>(c, C_ACCQ, qv);
+          if (a.residual_ca && c.half == 0) {   // residual term <o, wf> (:343,:345) from the folded tables
+            acc = twv;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) qv[j] = umma::tf32_lo(qv[j]);
-          st_feat<H>(c, C_QNLO, qv);
+            for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
+          }
         }
-        publish();
+        st_operand<H>(c, C_ACCQ, C_QNLO, e);
+      } else {   // dot product with the last profile position (:362)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], plast[si * 64 + Own<H>::f0(h, c.half) + qq], acc);
+      }
+      if (c.half == 1) {   // s.oid <- ids of q+1 (every thread read the ids of q one sync ago); fetch ids of q+2
+        s.oid[c.row] = has1 ? idn : 0;
+        if (has2) idn = cand_id(s.uuser[si2], ch2 * 128 + c.row);
+      }
+      if (ca) publish();
+      else __syncthreads();
+      if (ca) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
           if (issuer_warp) {
@@ -829,17 +847,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             c.ncommit++;
           }
           // gather of the next chunk's candidate rows: in flight while this chunk's attention runs
-          if (hp == 0 && q1 < n_iter) {
+          if (hp == 0 && has1) {
             oid = s.oid[c.row];
-            const int usr1 = s.uuser[si1];
-            embed_load<H>(a, c, oid,
-                          a.o_c + (long long)usr1 * a.oc_user + (long long)min(t1 + c.row, a.T - 1) * a.oc_tgt, e, cv);
+            gather(oid, s.uuser[si1], ch1 * 128 + c.row, e, cv, twv);
           }
           wait_mma(c);
           tick(tk, 20);
           {
-            const uint32_t k = kw0 + W * c.half;
-            const uint32_t t = c.tmem + k;
+            const uint32_t t = c.tmem + kw0 + W * c.half;
             if (W == 8) softmax_pair<8>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
             else if (W == 16) softmax_pair<16>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
             else softmax_pair<32>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
@@ -873,33 +888,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
           for (int h = 0; h < H; ++h)
 #pragma unroll
-            for (int qq = 0; qq < N2; ++qq) acc = fmaf(o[h * N2 + qq], s.dwf[Own<H>::f0(h, c.half) + qq], acc);
+            for (int qq = 0; qq < N2 / 4; ++qq) {
+              const float4 wv = *reinterpret_cast<const float4*>(&s.dwf[Own<H>::f0(h, c.half) + 4 * qq]);
+              const float* oo = &o[h * N2 + 4 * qq];
+              acc = fmaf(oo[0], wv.x, acc); acc = fmaf(oo[1], wv.y, acc);
+              acc = fmaf(oo[2], wv.z, acc); acc = fmaf(oo[3], wv.w, acc);
+            }
         }
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
         acc += __ldg(a.dbf);
-      } else {   // dot product with the last profile position (:362)
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], plast[si * 64 + Own<H>::f0(h, c.half) + qq], acc);
+      } else {
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
-        __syncthreads();   // every thread has consumed s.oid / e of this chunk
-        if (q1 < n_iter) {
-          const int usr1 = s.uuser[si1];
-          if (c.half == 1) {
-            int id = 0;
-            if (t1 + c.row < a.T) id = a.cat_lo > 0 ? a.cat_lo + t1 + c.row : a.o_x[(long long)usr1 * a.T + t1 + c.row];
-            s.oid[c.row] = id;
-          }
-          __syncthreads();
+        if (has1) {
           oid = s.oid[c.row];
-          embed_load<H>(a, c, oid, a.o_c + (long long)usr1 * a.oc_user + (long long)min(t1 + c.row, a.T - 1) * a.oc_tgt,
-                        e, cv);
+          gather(oid, s.uuser[si1], ch1 * 128 + c.row, e, cv, twv);
         }
+        __syncthreads();   // s.oid is rewritten at the top of the next iteration
       }
       if (c.half == 0 && c.row < nq)
         a.y[(long long)usr * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
       tick(tk, 23);
+      si = si1;
+      ch = ch1;
     }
     tk.out = nullptr;   // first tile only
   }

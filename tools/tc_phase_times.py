@@ -4,10 +4,10 @@ import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from carca_replication_b200 import fused, synth
 LABELS = {0: "tile start", 1: "ids + profile embed", 2: "x store + LN1 + publish", 3: "Q MMA wait + Q lo",
-          4: "K MMA wait + K store + publish", 5: "V MMA", 6: "V store + publish", 20: "  scores MMA (head pair)",
+          4: "K MMA wait + K store + publish", 5: "V MMA", 6: "V store + publish", 20: "  Q->TMEM/publish + scores MMA (head pair)",
           21: "  softmax pair + publish", 22: "  PV MMA (head pair)", 7: "O read + LN2 + publish", 8: "ffn_1 MMA",
           9: "LeakyReLU + publish", 10: "ffn_2 MMA", 11: "block out", 12: "final LN + publish",
-          13: "dec K,V proj + store", 14: "target embed", 15: "target publish + Q MMA", 23: "score + sigmoid + store"}
+          13: "dec K,V proj + store", 14: "loop top + candidate finish", 15: "(unused)", 23: "score + sigmoid + store"}
 decoder = sys.argv[1] if len(sys.argv) > 1 else "ca"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 dev = "cuda"
