@@ -483,19 +483,24 @@ def time_catalog(model, shape, args, dev):
 
 
 def time_train(shape, args, dev, table):
-    """fwd + BCE + bwd + Adam seqs/s at the reference batch size (src/train.py:84-97), dropout 0.5."""
+    """fwd + BCE + bwd + Adam seqs/s (src/train.py:84-97), dropout 0.5, at the reference batch size: the whole
+    step body replayed as one CUDA graph (carca_replication_b200/graph.py) and, for comparison, eagerly;
+    plus the eager step at a large batch (GPU-bound regime)."""
     import carca_replication_b200 as cb
     from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
 
-    Bt = args.train_batch
-    model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
-    model.embeds.set_attr_table(table)
-    optim = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
-    loss_fn = cb.BinaryCrossEntropy()
     L = shape.seq_len
-    batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + i).items()} for i in range(4)]
+    loss_fn = cb.BinaryCrossEntropy()
 
-    def one(b):
+    def setup(Bt, capturable):
+        model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
+        model.embeds.set_attr_table(table)
+        optim = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), capturable=capturable)
+        batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + i).items()} for i in range(4)]
+        return model, optim, batches
+
+    def eager_step(model, optim, b):
         o_x, o_c = b["o_x"], b["o_c"]
         optim.zero_grad()
         y = model.forward(profile=(b["p_x"], None, b["p_c"]),
@@ -505,19 +510,33 @@ def time_train(shape, args, dev, table):
         optim.step()
         return loss
 
-    for i in range(3):
-        one(batches[i % 4])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    def clock(fn, n):
+        for i in range(3):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            loss = fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, float(loss.item())
+
     n = max(args.steps, 5)
-    e0.record()
-    for i in range(n):
-        loss = one(batches[i % 4])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    return {"value": Bt / (ms * 1e-3), "unit": "seqs/s", "batch_per_gpu": Bt, "ms_per_step": ms,
-            "final_loss": float(loss.item()), "optimizer": "torch.optim.Adam (stock)", "dropout": 0.5}
+    Bt = args.train_batch
+    model, optim, batches = setup(Bt, True)
+    step = GraphedTrainStep(model, optim, batches[0])
+    ms_g, loss_g = clock(lambda i: step(batches[i % 4]), 4 * n)
+    model, optim, batches = setup(Bt, False)
+    ms_e, loss_e = clock(lambda i: eager_step(model, optim, batches[i % 4]), n)
+    Bl = 4096
+    model, optim, batches = setup(Bl, False)
+    ms_l, _ = clock(lambda i: eager_step(model, optim, batches[i % 4]), n)
+    return {"value": Bt / (ms_g * 1e-3), "unit": "seqs/s", "batch_per_gpu": Bt, "ms_per_step": ms_g,
+            "mode": "whole step (zero_grad, fwd, BCE, bwd, Adam) replayed as one CUDA graph", "final_loss": loss_g,
+            "optimizer": "torch.optim.Adam (stock, capturable)", "dropout": 0.5,
+            "eager": {"value": Bt / (ms_e * 1e-3), "ms_per_step": ms_e, "final_loss": loss_e},
+            "eager_large_batch": {"value": Bl / (ms_l * 1e-3), "batch_per_gpu": Bl, "ms_per_step": ms_l}}
 
 
 if __name__ == "__main__":

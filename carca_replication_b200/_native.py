@@ -68,6 +68,7 @@ P = C.POINTER
 SIGNATURES = {
     "carca_abi_version": [],
     "carca_launch_count": [],
+    "carca_set_seed_source": [vp],
     "carca_transpose": [vp, vp, i32, i32, i32, vp],
     "carca_padding_mask": [vp, vp, i64, vp],
     "carca_embed_fwd": [vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32, vp],
@@ -117,6 +118,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         fn.argtypes = args
         fn.restype = C.c_int
     lib.carca_launch_count.restype = C.c_int64
+    lib.carca_set_seed_source.restype = None
     lib.carca_eval_plan_floats.restype = C.c_int64
     lib.carca_eval_scratch_bytes.restype = C.c_int64
     return lib

@@ -22,9 +22,19 @@ using namespace carca;
     if (_rc != 0) return _rc; \
   } while (0)
 
+namespace carca {
+void set_seed_source(const unsigned long long* p);
+}
+
 namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// dropout configuration of a kernel launch: host seed (+ the optional device seed word)
+inline DropCfg drop_cfg(float p, unsigned long long seed, unsigned site) {
+  DropCfg c = make_drop(p, seed, site);
+  c.seed_dev = seed_source();
+  return c;
+}
 inline int warp_rows_grid(long long rows) { return (int)ceil_div_ll(rows, 8); }  // 8 warps / 256-thread CTA
 
 // y = x w^T + b with the optional fused epilogue pieces
@@ -148,7 +158,7 @@ AttnArgs attn_args(const float* Q, const float* K, const float* V, const float* 
   a.ldq = d; a.ldk = d; a.ldo = d;
   a.causal = causal_on; a.diag = diag;
   a.sqrt_dh = (float)std::sqrt((double)(d / H));
-  a.drop = make_drop(p, seed, site);
+  a.drop = drop_cfg(p, seed, site);
   return a;
 }
 
@@ -193,6 +203,9 @@ extern "C" {
 const char* carca_last_error(void) { return err_buf(); }
 int carca_abi_version(void) { return CARCA_B200_ABI_VERSION; }
 int64_t carca_launch_count(void) { return (int64_t)launch_count(); }
+void carca_set_seed_source(const uint64_t* device_seed) {
+  set_seed_source(reinterpret_cast<const unsigned long long*>(device_seed));
+}
 
 int carca_transpose(float* dst, const float* src, int rows, int cols, int accumulate, void* stream) {
   return transpose(dst, src, rows, cols, cols, rows, accumulate, S(stream));
@@ -207,7 +220,7 @@ int carca_padding_mask(float* mask, const int32_t* ids, int64_t n, void* stream)
 
 int carca_dropout(float* y, const float* x, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
   CARCA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f outside [0,1)", p);
-  return scale_rows(y, x, nullptr, make_drop(p, seed, site), n, 1, S(stream));
+  return scale_rows(y, x, nullptr, drop_cfg(p, seed, site), n, 1, S(stream));
 }
 
 // ------------------------------------------------------------------------------------ embedding
@@ -355,7 +368,7 @@ int carca_sa_block_fwd(float* out, const carca_block_saved* sv, const float* x, 
   a.resid = residual ? sv->qn : nullptr;                                                         // :302
   TRY(attention_fwd(a, st));
   TRY(layernorm_fwd(sv->s2, sv->mean2, sv->rstd2, sv->s, w->ln2_g, w->ln2_b, P, d, st));         // :304
-  const DropCfg d1 = make_drop(p_drop, seed, s_f1), d2 = make_drop(p_drop, seed, s_f2);
+  const DropCfg d1 = drop_cfg(p_drop, seed, s_f1), d2 = drop_cfg(p_drop, seed, s_f2);
   TRY(linear(sv->a1, sv->s2, w->w1, w->b1, P, d, d, d, st, 1, &d1));                             // :307-309
   TRY(linear(out, sv->a1, w->w2, w->b2, P, d, d, d, st, 0, &d2, residual ? sv->s2 : nullptr));   // :311-316
   return 0;
@@ -373,7 +386,7 @@ int carca_sa_block_bwd(float* dx, const carca_block_grads* gr, const float* dout
   float* t2 = t1 + n;
   float* t3 = t2 + n;
   const uint32_t s_attn = 1 + 3 * block_index, s_f1 = 2 + 3 * block_index, s_f2 = 3 + 3 * block_index;
-  const DropCfg d1 = make_drop(p_drop, seed, s_f1), d2 = make_drop(p_drop, seed, s_f2);
+  const DropCfg d1 = drop_cfg(p_drop, seed, s_f1), d2 = drop_cfg(p_drop, seed, s_f2);
   // ---- FFN
   const float* df2 = dout;
   if (p_drop > 0.f) {

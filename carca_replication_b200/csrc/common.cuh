@@ -23,6 +23,7 @@ constexpr float kLnEps = 1e-5f;        // nn.LayerNorm default, src/carca.py:279
 char* err_buf();
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);   // call once after every kernel launch (also counts it)
+const unsigned long long* seed_source();   // device word set by carca_set_seed_source (or null)
 long long launch_count();
 
 #define CARCA_REQUIRE(cond, ...)                      \
@@ -66,6 +67,8 @@ struct DropCfg {
   float scale;             // 1/(1-p)
   unsigned seed_lo, seed_hi;
   unsigned site;
+  const unsigned long long* seed_dev;   // optional device word XOR-ed into the seed when the kernel runs, so a
+                                        // captured CUDA graph draws a fresh mask on every replay (carca_set_seed_source)
 };
 
 __host__ __device__ __forceinline__ DropCfg make_drop(float p, unsigned long long seed, unsigned site) {
@@ -75,14 +78,21 @@ __host__ __device__ __forceinline__ DropCfg make_drop(float p, unsigned long lon
   c.seed_lo = (unsigned)seed;
   c.seed_hi = (unsigned)(seed >> 32);
   c.site = site;
+  c.seed_dev = nullptr;
   return c;
 }
 
 // keep-scale for flat element index `elem` of the site's tensor: 0 (dropped) or 1/(1-p)
 __host__ __device__ __forceinline__ float drop_factor(const DropCfg& c, unsigned long long elem) {
   if (c.p <= 0.f) return 1.0f;
+  unsigned k0 = c.seed_lo, k1 = c.seed_hi;
+  if (c.seed_dev) {
+    const unsigned long long x = *c.seed_dev;
+    k0 ^= (unsigned)x;
+    k1 ^= (unsigned)(x >> 32);
+  }
   const unsigned long long ctr = elem >> 2;
-  const Philox4 r = philox4x32_10((unsigned)ctr, (unsigned)(ctr >> 32), c.site, 0u, c.seed_lo, c.seed_hi);
+  const Philox4 r = philox4x32_10((unsigned)ctr, (unsigned)(ctr >> 32), c.site, 0u, k0, k1);
   const unsigned lane = (unsigned)(elem & 3ull);
   const unsigned word = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
   const float u = (float)(word >> 8) * 5.9604644775390625e-08f;  // 2^-24

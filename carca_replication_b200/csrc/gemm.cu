@@ -14,6 +14,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static const unsigned long long* g_seed_dev = nullptr;
+const unsigned long long* seed_source() { return g_seed_dev; }
+void set_seed_source(const unsigned long long* p) { g_seed_dev = p; }
+
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 

@@ -34,6 +34,11 @@ int carca_abi_version(void);
 /* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
 int64_t carca_launch_count(void);
 
+/* Optional device-resident seed word: while set (non-NULL), every dropout site XORs *device_seed into its
+ * seed when the kernel RUNS, so a training step captured in a CUDA graph draws fresh masks on every replay
+ * (increment the word inside the graph).  Process-wide; NULL restores host-only seeds.               */
+void carca_set_seed_source(const uint64_t* device_seed);
+
 /* ------------------------------------------------------------------ attribute source */
 enum { CARCA_ATTR_CSR = 0, CARCA_ATTR_TABLE = 1, CARCA_ATTR_DENSE = 2 };
 

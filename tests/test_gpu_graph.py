@@ -1,0 +1,64 @@
+"""CUDA-graph train step vs the eager step on a B200 (same weights, same batches)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_graphed_step_matches_eager_without_dropout(decoder):
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
+
+    dev = "cuda"
+    shape = synth.TINY
+    table = synth.make_attr_table(shape, seed=3).to(dev)
+    batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, 32, seed=50 + i).items()} for i in range(4)]
+
+    def fresh():
+        m = synth.build_model(shape, decoder, p=0.0, seed=3).to(dev).train()
+        m.embeds.set_attr_table(table)
+        return m, torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.98), capturable=True)
+
+    m1, o1 = fresh()
+    sd0 = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    step = GraphedTrainStep(m1, o1, batches[0], warmup=2)
+    # the warm-up / capture steps moved the weights: restart both sides from the same state
+    m1.load_state_dict(sd0)
+    for st in o1.state.values():          # the captured kernels reference THESE tensors: reset them in place
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    m2, o2 = fresh()
+    m2.load_state_dict(sd0)
+    L = shape.seq_len
+    loss_fn = cb.BinaryCrossEntropy()
+    for b in batches:
+        l1 = step(b).clone()
+        o2.zero_grad()
+        y = m2.forward((b["p_x"], None, b["p_c"]), [(b["o_x"][:, :L], None, b["o_c"][:, :L]),
+                                                    (b["o_x"][:, L:], None, b["o_c"][:, L:])])
+        l2 = loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+        l2.backward()
+        o2.step()
+        assert abs(l1.item() - l2.item()) < 1e-5 * max(1.0, abs(l2.item()))
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if k.endswith("WK.bias"):
+            continue      # its gradient is pure summation noise (softmax shift invariance), which Adam turns into +-lr steps
+        assert torch.allclose(p1, p2, rtol=1e-3, atol=2e-5), k
+
+
+def test_graphed_step_draws_new_dropout_masks_every_replay():
+    from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
+
+    dev = "cuda"
+    shape = synth.TINY
+    m = synth.build_model(shape, "ca", p=0.5, seed=3).to(dev).train()
+    m.embeds.set_attr_table(synth.make_attr_table(shape, seed=3).to(dev))
+    opt = torch.optim.Adam(m.parameters(), lr=0.0, capturable=True)      # lr 0: weights stay put
+    b = {k: v.to(dev) for k, v in synth.make_train_batch(shape, 32, seed=9).items()}
+    step = GraphedTrainStep(m, opt, b)
+    losses = {round(step(b).item(), 7) for _ in range(6)}
+    assert len(losses) >= 5          # same data, same weights: only the masks differ
