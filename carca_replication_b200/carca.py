@@ -259,8 +259,11 @@ class CARCA(Model):
             return False
         from . import fused
         from . import _native
-        return _native.is_device_tensor(profile[0]) and fused.supported(self, profile[0].shape[1],
-                                                                        profile[2].shape[-1])
+        if not (_native.is_device_tensor(profile[0]) and fused.supported(self, profile[0].shape[1],
+                                                                         profile[2].shape[-1])):
+            return False
+        # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin
+        return fused.fits_packed(profile[0])
 
     def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:

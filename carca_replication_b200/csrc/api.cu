@@ -704,7 +704,7 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   cudaMemsetAsync(n_bins, 0, sizeof(int), S(stream));
   {
     auto pk = pack_rows_kernel;
-    CARCA_LAUNCH(pk, dim3(ceil_div(B, 128)), dim3(128), 0, S(stream), row_src, row_seg, n_bins, p_x, B, L);
+    CARCA_LAUNCH(pk, dim3(ceil_div(B, 128)), dim3(128), 0, S(stream), row_src, row_seg, n_bins, status, p_x, B, L);
     TRY(check_launch("pack_rows"));
   }
   a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
@@ -731,15 +731,15 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
   const bool common_ok = d == FD && L >= 1 && m->embed.n_ctx <= 8 && m->n_blocks <= FMAXB && H >= 1 && FD % H == 0;
   const bool ffma_ok = common_ok && L <= FLP && (FD / H) % 4 == 0;
 #ifndef CARCA_EMU
-  const bool tc_ok = common_ok && L <= 64 && (H == 2 || H == 4) && status != nullptr && scratch != nullptr;
+  const bool tc_ok = common_ok && L <= 256 && (H == 2 || H == 4) && status != nullptr && scratch != nullptr;
 #else
   const bool tc_ok = false;
 #endif
   if (variant == 2 && !tc_ok)
-    return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=64, H in {2,4}, status and scratch");
+    return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=256, H in {2,4}, status and scratch");
   if (variant == 1 && !ffma_ok) return fail(-4, "eval_forward: FFMA kernel needs d=64, L<=52, dh%%4==0");
   if (!ffma_ok && !tc_ok)
-    return fail(-4, "eval_forward: fused kernels support d=64, L<=64, C<=8, <=8 blocks (got d=%d L=%d C=%d blocks=%d "
+    return fail(-4, "eval_forward: fused kernels support d=64, L<=256, C<=8, <=8 blocks (got d=%d L=%d C=%d blocks=%d "
                     "H=%d)", d, L, m->embed.n_ctx, m->n_blocks, H);
   if (m->embed.pos) CARCA_REQUIRE(L <= m->embed.pos_len, "eval_forward: sequence length %d > positional table %d", L,
                                   m->embed.pos_len);

@@ -1,4 +1,5 @@
-// Tensor-core (tcgen05) version of the fused inference forward for d = 64, L <= 64, 2 or 4 heads.
+// Tensor-core (tcgen05) version of the fused inference forward for d = 64, 2 or 4 heads, L <= 256 with at
+// most 64 non-padding positions per user.
 // Same contract as fused_eval_kernel (fused_eval.cuh); reference path replaced:
 // CARCA.forward in eval mode, src/carca.py:411-431 with :85-95, :228-265, :297-318, :338-365.
 //
@@ -526,11 +527,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
     const int src = a.row_src[(long long)tile * 128 + c.row];
     const int seg = src >= 0 ? a.row_seg[(long long)tile * 128 + c.row] : 0;
-    const int ru = src >> 6, rp = src & 63;
+    const int ru = src >> 8, rp = src & 255;
     const int seg0 = seg & 0xff, seglen = (seg >> 8) & 0xff;
     const int my_pid = src >= 0 ? a.p_x[(long long)ru * L + rp] : 0;
     const bool head = src >= 0 && i == seg0;
-    const bool dbg_row = a.dbg != nullptr && a.dbg_stage > 0 && src >= 0 && ru < 2;
+    const bool dbg_row = a.dbg != nullptr && a.dbg_stage > 0 && src >= 0 && ru < 2 && rp < 64;
     if (c.half == 0) {
       const uint32_t bits = __ballot_sync(kFull, my_pid != 0);
       const uint32_t hb = __ballot_sync(kFull, head);
@@ -925,17 +926,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 // are read by the decoder, so the encoder runs on valid rows only.  A user's rows stay contiguous
 // and in sequence order inside one bin (causal mask = row order); position L-1 is always included
 // (the dot decoder reads it even when it is padding, src/carca.py:362).
-//   row_src[bin*64 + r] = user*64 + position (or -1), row_seg = segment start | length << 8.
+//   row_src[bin*64 + r] = user*256 + position (or -1), row_seg = segment start | length << 8.
 // One 128-thread block packs 128 consecutive users (next-fit) and claims its bins with one atomicAdd.
 __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
-                                                        int* __restrict__ n_bins, const int* __restrict__ p_x, int B,
-                                                        int L) {
+                                                        int* __restrict__ n_bins, int* __restrict__ status,
+                                                        const int* __restrict__ p_x, int B, int L) {
   __shared__ int cnt[128], bin_of[128], start_of[128], base;
   const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
   int n = 0;
   if (usr < B) {
     const int* x = p_x + (long long)usr * L;
     for (int j = 0; j < L; ++j) n += (x[j] != 0) || (j == L - 1);
+  }
+  int skip = 0;   // a bin holds 64 rows: longer profiles (possible only when L > 64) keep their LAST 64 rows
+  if (n > 64) {   // and are flagged — the caller must route such batches to the per-op kernels
+    skip = n - 64;
+    n = 64;
+    if (status) atomicOr(status, 2);
   }
   cnt[t] = n;
   __syncthreads();
@@ -961,7 +968,11 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
     const int seg = start_of[t] | (n << 8);
     for (int j = 0; j < L; ++j) {
       if (x[j] != 0 || j == L - 1) {
-        row_src[o + r] = usr * 64 + j;
+        if (skip > 0) {
+          --skip;
+          continue;
+        }
+        row_src[o + r] = usr * 256 + j;
         row_seg[o + r] = seg;
         ++r;
       }

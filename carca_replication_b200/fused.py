@@ -25,7 +25,8 @@ _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 # kernel, 2 = tcgen05 tensor-core kernel.  CARCA_FUSED_VARIANT overrides (benchmark comparisons).
 VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "0"))
 
-MAX_L, MAX_L_TC, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 64, 8, 8, 64
+MAX_L, MAX_L_TC, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 256, 8, 8, 64
+BIN_ROWS = 64      # rows of one packed bin of the tensor-core kernel: the most valid positions a user may have
 
 
 def supported(model, seq_len: int, n_ctx: int) -> bool:
@@ -53,6 +54,17 @@ def supported(model, seq_len: int, n_ctx: int) -> bool:
     return ffma or tc
 
 
+def fits_packed(p_x: Tensor) -> bool:
+    """Tensor-core kernel precondition for L > 64: every user has at most 64 rows after packing
+    (its non-padding positions plus position L-1).  One small reduction + device->host read; never
+    needed for L <= 64."""
+    L = p_x.shape[1]
+    if L <= BIN_ROWS:
+        return True
+    rows = (p_x != 0).sum(dim=1) + (p_x[:, -1] == 0).to(torch.int64)
+    return int(rows.max().item()) <= BIN_ROWS if rows.numel() else True
+
+
 def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int):
     """carca_model_params + the Python objects that must stay alive while it is used."""
     from . import carca as M
@@ -61,7 +73,7 @@ def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int
     E, Wf, bf = _c(emb.items_embed.weight), _c(emb.feats_embed.weight), _c(emb.feats_embed.bias)
     Wj, bj = _c(emb.joint_embed.weight), _c(emb.joint_embed.bias)
     A = Wf.shape[1] - n_ctx
-    pos = emb.enc.table(MAX_L)
+    pos = emb.enc.table(MAX_L_TC)
     pos = None if pos is None else _c(pos)
     blocks = list(model.encoder)
     arr = (N.BlockParams * len(blocks))()
@@ -143,7 +155,7 @@ def _scratch(B: int, device) -> Tensor:
 def mma_timed_out(model) -> bool:
     """True if a tensor-core completion wait ever timed out for this model's plan (device sync)."""
     hit = _plans.get(model)
-    return bool(hit is not None and int(hit[2].item()) != 0)
+    return bool(hit is not None and (int(hit[2].item()) & 1) != 0)
 
 
 def forward(model, profile, targets: Sequence, variant: Optional[int] = None, dbg: Optional[Tensor] = None,

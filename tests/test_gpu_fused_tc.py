@@ -67,3 +67,42 @@ def test_tc_kernel_is_the_default_and_two_launches():
         assert N.lib().carca_launch_count() - n0 == 2      # row packing + the fused forward
         y2 = fused.forward(model, prof, tgt, variant=2)
     assert torch.equal(y0, y1) and torch.equal(y1, y2)       # variant 0 picks the tensor-core kernel
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+@pytest.mark.parametrize("L", [100, 200])
+def test_long_windows_use_the_packed_kernel_when_profiles_fit_a_bin(decoder, L):
+    """maxlen 100 / 200 (BASELINE configs[4]): Beauty-like users have few valid positions, which the
+    tensor-core kernel packs; a batch with a longer profile falls back to the per-op kernels."""
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import fused, synth
+
+    dev = "cuda"
+    shape = dataclasses.replace(synth.BEAUTY, seq_len=L, n_items=4000, n_attrs=300)
+    model = synth.build_model(shape, decoder, p=0.5, seed=6).to(dev).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=6).to(dev))
+    b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, 40, seed=6).items()}
+    n_valid = (b["p_x"] != 0).sum(1)
+    keep = n_valid <= 64                                   # users that fit a bin
+    assert int(keep.sum()) >= 30
+    short = {k: v[keep].contiguous() for k, v in b.items()}
+    prof, tgt = (short["p_x"], None, short["p_c"]), [(short["o_x"], None, short["o_c"])]
+    with torch.no_grad():
+        assert model._fused_eval_applies(prof, tgt)
+        model.forward(prof, tgt)                               # builds the plan
+        n0 = N.lib().carca_launch_count()
+        y = model.forward(prof, tgt)
+        assert N.lib().carca_launch_count() - n0 == 2          # row packing + one fused launch
+        model.use_fused_eval = False
+        y_mod = model.forward(prof, tgt)
+        model.use_fused_eval = True
+    assert not fused.mma_timed_out(model)
+    assert rel_err(y.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL
+    assert topk_equal_up_to_ties(y.cpu().numpy(), y_mod.cpu().numpy(), 10, tol=1e-6)
+    # one user with every position valid: does not fit a 64-row bin -> per-op path, same API
+    full = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, 3, seed=7, all_valid=True).items()}
+    profl, tgtl = (full["p_x"], None, full["p_c"]), [(full["o_x"], None, full["o_c"])]
+    with torch.no_grad():
+        assert not model._fused_eval_applies(profl, tgtl)
+        yl = model.forward(profl, tgtl)
+    assert tuple(yl.shape) == (3, shape.n_targets) and torch.isfinite(yl).all()

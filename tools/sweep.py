@@ -1,0 +1,39 @@
+"""Scaling sweep of BASELINE.json configs[4]: maxlen 50/100/200 x batch 128..8192 users, eval users/s of the
+public API (CARCA.forward + BCE + rank metrics) on one GPU, device-timed, inputs resident.
+    python tools/sweep.py [decoder]          (per-GPU numbers; multi-GPU runs shard users: see bench.py --gpus)"""
+import dataclasses, json, sys; sys.path.insert(0, '.')
+import torch
+import carca_replication_b200 as cb
+from carca_replication_b200 import ops, synth
+decoder = sys.argv[1] if len(sys.argv) > 1 else "ca"
+dev = torch.device("cuda")
+rows = []
+for L in (50, 100, 200):
+    shape = dataclasses.replace(synth.BEAUTY, seq_len=L)
+    model = synth.build_model(shape, decoder, p=0.5).to(dev).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape).to(dev))
+    loss_fn = cb.BinaryCrossEntropy()
+    for B in (128, 512, 2048, 8192):
+        bs = []
+        for i in range(4):
+            b = synth.make_eval_batch(shape, B + 64, seed=10 * L + i)
+            keep = ((b["p_x"] != 0).sum(1) <= 64).nonzero()[:B, 0]      # users whose valid positions fit a bin
+            bs.append({k: v[keep].contiguous().to(dev) for k, v in b.items()})
+        Bn = bs[0]["p_x"].shape[0]
+        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        def step(b):
+            y = model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])])
+            loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+            ops.rank_metrics_(acc, y, b["y_true"], 10)
+        with torch.no_grad():
+            fused_path = model._fused_eval_applies((bs[0]["p_x"], None, bs[0]["p_c"]), [(bs[0]["o_x"], None, bs[0]["o_c"])])
+            for i in range(3): step(bs[i % 4])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 20 if B <= 2048 else 8
+            torch.cuda.synchronize(); e0.record()
+            for i in range(n): step(bs[i % 4])
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        rows.append(dict(maxlen=L, batch=Bn, ms_per_step=round(ms, 4), users_per_s=round(Bn / ms * 1e3), fused=bool(fused_path),
+                         mean_valid=round(float((bs[0]["p_x"] != 0).sum(1).float().mean()), 2)))
+        print(json.dumps(rows[-1]), flush=True)
