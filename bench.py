@@ -215,6 +215,10 @@ def run_ours(args):
     host = [{k: b[k].pin_memory() for k in names} for b in host]
     devb = [{k: b[k].to(dev) for k in names} for b in host]
     dev_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in names)
+    # every candidate of a user carries the positive's context (src/data.py:185): CARCA.forward is given the
+    # [B,T,C] tensor as an expanded view of one row per user, which the kernels read per user
+    for b in devb:
+        b["o_c"] = b["o_c"][:, :1, :].contiguous().expand(-1, b["o_x"].shape[1], -1)
 
     acc = torch.zeros(3, dtype=torch.float64, device=dev)
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)

@@ -82,8 +82,10 @@ struct TcSmem {
   float mct[8][64];                                  // folded context map, [context k][feature]
   float mcqt[8][64];                                 // the same through the decoder's WQ
   float mcw[8];                                      //   and through its ffn weight
-  float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
-  float dwf[64];
+  float cvec[2][64];                                 // per-user context term of the candidates (double-buffered)
+  float cw[4];                                       //   and of the score residual ([2] used; keeps 16-byte alignment)
+  alignas(16) float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
+  alignas(16) float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
   int oid[128];
   int ulist[128];                                    // segments of the tile: first row | length << 8
@@ -274,8 +276,10 @@ __device__ __forceinline__ void embed_load(const TcArgs& a, const TcCtx& c, int 
   constexpr int N2 = Own<H>::N2;
   if (id == 0) return;
   // volatile asm loads: issued HERE (the compiler would otherwise sink plain loads to their first use)
+  if (ctx) {   // null: the context term comes from a per-user vector (embed_finish_user)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? ldg_now(ctx + k) : 0.f;
+    for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? ldg_now(ctx + k) : 0.f;
+  }
   const float* t = table + (long long)id * 64;
 #pragma unroll
   for (int h = 0; h < H; ++h)
@@ -319,6 +323,20 @@ __device__ __forceinline__ void embed_finish(const TcArgs& a, const TcCtx& c, in
         }
     }
   }
+}
+// same when every row of the tile shares one context row: add the precomputed map of that row
+template <int H>
+__device__ __forceinline__ void embed_finish_user(const TcCtx& c, int id, const float* cvec, float (&v)[32]) {
+  constexpr int N2 = Own<H>::N2;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int q = 0; q < N2 / 4; ++q) {
+      const float4 m = *reinterpret_cast<const float4*>(cvec + Own<H>::f0(h, c.half) + 4 * q);
+      float* o = &v[h * N2 + 4 * q];
+      o[0] = id ? o[0] + m.x : 0.f; o[1] = id ? o[1] + m.y : 0.f;
+      o[2] = id ? o[2] + m.z : 0.f; o[3] = id ? o[3] + m.w : 0.f;
+    }
 }
 // bits lo..hi (inclusive, clipped to 0..31)
 __device__ __forceinline__ uint32_t range_mask(int lo, int hi) {
@@ -769,10 +787,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     auto cand_id = [&](int usr, int t) -> int {
       return t < a.T ? (a.cat_lo > 0 ? a.cat_lo + t : ldg_now_i(a.o_x + (long long)usr * a.T + t)) : 0;
     };
+    // one context row per user (expanded [B,T,C] view / catalog mode): its map is computed once per iteration
+    // by 65 threads instead of per row
+    const bool uctx = a.oc_tgt == 0;
     auto gather = [&](int id, int usr, int t, float(&e)[32], float(&cv)[8], float& twv) {
-      embed_load<H>(a, c, id, tab, a.o_c + (long long)usr * a.oc_user + (long long)min(t, a.T - 1) * a.oc_tgt, e, cv);
+      embed_load<H>(a, c, id, tab,
+                    uctx ? nullptr : a.o_c + (long long)usr * a.oc_user + (long long)min(t, a.T - 1) * a.oc_tgt, e, cv);
       if (ca && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
     };
+    auto user_ctx = [&](int usr, int slot) {
+      const float* cu = a.o_c + (long long)usr * a.oc_user;
+      if (c.tid < 96) {   // warps 0-2 (warp-uniform): 64 feature threads + one thread for the residual weight
+        float cu_[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cu_[k] = k < a.C ? __ldg(cu + k) : 0.f;   // all loads in flight together
+        if (c.tid < 64) {
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v = fmaf(ctab[k][c.tid], cu_[k], v);
+          s.cvec[slot][c.tid] = v;
+        } else if (c.tid == 64 && ca) {
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v = fmaf(s.mcw[k], cu_[k], v);
+          s.cw[slot] = v;
+        }
+      }
+    };
+    if (uctx) user_ctx(s.uuser[0], 0);
     if (c.half == 1) s.oid[c.row] = cand_id(s.uuser[0], c.row);
     __syncthreads();   // s.oid, K/V/plast stores are visible
     const int n_iter = n_seg * n_chunks;
@@ -796,7 +838,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       int si2 = si1, ch2 = ch1 + 1;
       if (ch2 == n_chunks) { ch2 = 0; ++si2; }
       const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
-      embed_finish<H>(a, c, oid, ctab, nullptr, e, cv);   // candidate embedding (:426), or its query for `ca`
+      // candidate embedding (:426), or its query for `ca`
+      if (uctx) embed_finish_user<H>(c, oid, s.cvec[q & 1], e);
+      else embed_finish<H>(a, c, oid, ctab, nullptr, e, cv);
       tick(tk, 14);
       float acc = 0.f;
       uint32_t cross_bits = 0;
@@ -814,8 +858,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           if (W < 32) cross_bits &= (1u << W) - 1u;
           if (a.residual_ca && c.half == 0) {   // residual term <o, wf> (:343,:345) from the folded tables
             acc = twv;
+            if (uctx) {
+              acc += s.cw[q & 1];
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
+              for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
+            }
           }
         }
         st_operand<H>(c, C_ACCQ, C_QNLO, e);
@@ -831,6 +879,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
       if (ca) publish();
       else __syncthreads();
+      if (uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);   // visible after this iteration's next CTA sync
       if (ca) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) catalog_rank_count_kernel(int* __restrict
   int c = 0;
   for (int j = lane; j < n; j += kWarp) {
     const float v = row[j];
-    c += (v > yp) || (v == yp && item_lo + j < pi);
+    const int item = item_lo + j;
+    c += item != pi && ((v > yp) || (v == yp && item < pi));   // the positive never outranks itself
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);

@@ -170,7 +170,7 @@ def forward(model, profile, targets: Sequence, variant: Optional[int] = None, db
     per_user_ctx = False
     if len(targets) == 1:
         o_x, o_c = as_ids(targets[0][0]), targets[0][2]
-        if o_c.dim() == 3 and o_c.stride(1) == 0 and o_c.stride(2) == 1 and o_c.shape[1] > 1:
+        if o_c.dim() == 3 and o_c.stride(2) == 1 and (o_c.shape[1] == 1 or o_c.stride(1) == 0):
             # [B,T,C] expanded from one context row per user (the positive's context given to every
             # sampled negative, src/data.py:185): read the [B,C] base, never materialise the copies
             o_c, per_user_ctx = as_f32(o_c[:, 0, :]), True

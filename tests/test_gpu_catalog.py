@@ -47,4 +47,7 @@ def test_expanded_candidate_context_is_read_per_user():
         y_dense = model.forward(prof, [(b["o_x"], None, b["o_c"])])
         base = b["o_c"][:, :1, :].contiguous()
         y_exp = model.forward(prof, [(b["o_x"], None, base.expand(-1, b["o_x"].shape[1], -1))])
-    assert torch.equal(y_dense, y_exp)
+    from helpers import rel_err
+
+    # same scores; the per-user context term is summed in a different order (cvec first), hence not bit-equal
+    assert rel_err(y_exp.cpu().numpy(), y_dense.cpu().numpy()) < 1e-5
