@@ -338,6 +338,7 @@ def run_ours(args):
             out["train"] = time_train(shape, args, dev, table)
         if not args.no_catalog:
             out["catalog"] = time_catalog(model, shape, args, dev)
+            out["device_pipeline"] = time_device_pipeline(model, shape, args, dev)
         if not args.no_cpu_baseline:
             cb_B = args.cpu_batch
             ups, sec = time_cpu_eval(shape, args.decoder, sd_cpu, table_cpu, cb_B, 3, 1)
@@ -484,6 +485,37 @@ def time_catalog(model, shape, args, dev):
     return {"value": Bc / (ms * 1e-3), "unit": "users/s", "users": Bc, "items": shape.n_items - 1, "ms": ms,
             "scores_per_s": Bc * (shape.n_items - 1) / (ms * 1e-3), "hr10": float((r < 10).double().mean().item()),
             "mean_rank": float(r.mean().item())}
+
+
+def time_device_pipeline(model, shape, args, dev):
+    """evaluate() fed by the device-side loader (carca_replication_b200/device_data.py): windows, sampled
+    negatives and labels are built on the GPU from a resident interaction log, so no batch crosses PCIe.
+    The reference's host loader builds ~500 users/s."""
+    import numpy as np
+
+    import carca_replication_b200 as cb
+    from carca_replication_b200.device_data import DeviceInteractions, DeviceLoader
+
+    rng = np.random.default_rng(99)
+    U = shape.n_users
+    lens = np.clip(np.rint(rng.lognormal(1.8, 0.7, size=U)), 4, 300).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(lens)])
+    items = rng.integers(1, shape.n_items, size=int(rowptr[-1])).astype(np.int32)
+    ctx = rng.random((int(rowptr[-1]), shape.n_ctx), dtype=np.float32)
+    log = DeviceInteractions(torch.from_numpy(rowptr), torch.from_numpy(items), torch.from_numpy(ctx)).to(dev)
+    loader = DeviceLoader(log, shape.n_items, shape.seq_len, shape.n_targets - 1, "test", batch_size=args.batch)
+    cb.evaluate(model, loader, dev, 10)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    hr, ndcg, loss = cb.evaluate(model, loader, dev, 10)
+    e1.record()
+    torch.cuda.synchronize()
+    n = int(loader.users.numel())
+    ms = e0.elapsed_time(e1)
+    return {"value": n / (ms * 1e-3), "unit": "users/s", "users": n, "ms": ms, "hr10": hr,
+            "what": "evaluate(model, DeviceLoader(...)) over every test user of a Beauty-sized log: batch "
+                    "construction + forward + loss + metrics on the device, one D2H read"}
 
 
 def time_train(shape, args, dev, table):

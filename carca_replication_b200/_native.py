@@ -62,6 +62,10 @@ class ModelParams(C.Structure):
                 ("norm_b", vp), ("cross", CrossParams)]
 
 
+class Interactions(C.Structure):
+    _fields_ = [("rowptr", vp), ("items", vp), ("ctx", vp), ("n_users", i32), ("n_ctx", i32)]
+
+
 P = C.POINTER
 
 # name -> argtypes (restype is always int unless noted); mirrors include/carca_b200.h one to one
@@ -96,6 +100,8 @@ SIGNATURES = {
     "carca_bce_finalize": [vp, vp, vp],
     "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
     "carca_rank_metrics": [vp, vp, vp, vp, i32, i32, i64, i64, i32, vp],
+    "carca_build_eval_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, i32, i32, u64, vp],
+    "carca_build_train_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, u64, vp],
     "carca_eval_plan_floats": [P(ModelParams)],
     "carca_eval_prepare": [vp, vp, P(ModelParams), P(AttrSource), vp],
     "carca_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, vp],

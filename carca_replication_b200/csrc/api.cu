@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "attention.cuh"
+#include "batch.cuh"
 #include "common.cuh"
 #include "embed.cuh"
 #include "fused_eval.cuh"
@@ -537,6 +538,44 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
   CARCA_LAUNCH(kern, dim3(grid), dim3(256), 0, S(stream), acc, first_rank, y_pred, y_true, B, T, (long long)ldy,
                (long long)ldt, k);
   return check_launch("rank_metrics");
+}
+
+// ------------------------------------------------------------------------------------ batch construction
+namespace {
+int check_log(const carca_interactions* lg, int L, int n_neg) {
+  CARCA_REQUIRE(lg && lg->rowptr && lg->items && lg->ctx, "build_batch: incomplete interaction log");
+  CARCA_REQUIRE(L >= 1 && n_neg <= kMaxNeg, "build_batch: at most %d sampled negatives per user (got %d)", kMaxNeg, n_neg);
+  return 0;
+}
+InteractionLog as_log(const carca_interactions* lg) {
+  InteractionLog l;
+  l.rowptr = lg->rowptr; l.items = lg->items; l.ctx = lg->ctx; l.n_users = lg->n_users; l.n_ctx = lg->n_ctx;
+  return l;
+}
+}  // namespace
+
+int carca_build_eval_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c_user, int32_t* y_true,
+                           const carca_interactions* log, const int32_t* users, int B, int L, int T, int n_items,
+                           int mode, int test, uint64_t seed, void* stream) {
+  if (B <= 0) return 0;
+  CARCA_REQUIRE(mode == 1 || mode == 2, "build_eval_batch: mode must be 1 (val) or 2 (test)");
+  CARCA_REQUIRE(T >= 1, "build_eval_batch: T counts the positive, so T >= 1");
+  TRY(check_log(log, L, T - 1));
+  auto k = build_eval_batch_kernel;
+  CARCA_LAUNCH(k, dim3(ceil_div(B, 4)), dim3(128), 0, S(stream), p_x, p_c, o_x, o_c_user, y_true, as_log(log), users, B,
+               L, T, n_items, mode, test, (unsigned long long)seed);
+  return check_launch("build_eval_batch");
+}
+
+int carca_build_train_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c, int32_t* y_true,
+                            const carca_interactions* log, const int32_t* users, int B, int L, int n_items, int test,
+                            uint64_t seed, void* stream) {
+  if (B <= 0) return 0;
+  TRY(check_log(log, L, L));
+  auto k = build_train_batch_kernel;
+  CARCA_LAUNCH(k, dim3(ceil_div(B, 4)), dim3(128), 0, S(stream), p_x, p_c, o_x, o_c, y_true, as_log(log), users, B, L,
+               n_items, test, (unsigned long long)seed);
+  return check_launch("build_train_batch");
 }
 
 // ------------------------------------------------------------------------------------ fused inference

@@ -229,6 +229,36 @@ int carca_bce_bwd(float* dy, const float* grad_out, const float* sums, const flo
 int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, const int32_t* y_true, int B,
                        int T, int64_t ldy, int64_t ldt, int k, void* stream);
 
+/* ------------------------------------------------------------------ batch construction */
+/* The users' interaction log on the device, CSR over users: items of user u (chronological) are
+ * items[rowptr[u] .. rowptr[u+1]) and ctx[j, :] is the context of interaction j — what
+ * load_profiles / load_ctx return (src/data.py:17-50), flattened once.                          */
+typedef struct {
+  const int32_t* rowptr; /* [n_users + 1] */
+  const int32_t* items;  /* [nnz] */
+  const float* ctx;      /* [nnz, n_ctx] */
+  int n_users, n_ctx;
+} carca_interactions;
+
+/* One evaluation batch for `users` [B]: replaces CARCADataset.__getitem__ -> get_test_sequences
+ * (src/data.py:140-192, pad_profile :53-74, sample_negatives :77-87) + default_collate.
+ *   p_x [B,L] left-padded window, p_c [B,L,C], o_x [B,T] = positive | T-1 sampled negatives,
+ *   o_c_user [B,C] = the positive's context (every candidate carries it, :185; pass it to
+ *   CARCA.forward as an expanded [B,T,C] view), y_true [B,T] = [1, 0, ...].
+ * mode 1 = val, 2 = test; test = the `test` flag of CARCADataset.  Windows, padding, positives,
+ * contexts and labels equal the reference's; negatives are uniform over [1, n_items-1], distinct and
+ * outside the user's whole profile like the reference's, drawn from Philox(seed, user) instead of
+ * Python's `random`.  Users whose profile is too short for the mode get all-zero rows.          */
+int carca_build_eval_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c_user, int32_t* y_true,
+                           const carca_interactions* log, const int32_t* users, int B, int L, int T, int n_items,
+                           int mode, int test, uint64_t seed, void* stream);
+
+/* One training batch: replaces get_train_sequences (src/data.py:90-137).  o_x [B,2L] = next items |
+ * negatives, o_c [B,2L,C] (negatives take the positive's context, :130), y_true [B,2L]. */
+int carca_build_train_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c, int32_t* y_true,
+                            const carca_interactions* log, const int32_t* users, int B, int L, int n_items, int test,
+                            uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------ whole-model inference */
 /* Every parameter of a CARCA model (src/carca.py:401-409) in its state_dict layout.
  * `blocks` is a HOST array of n_blocks entries; decoder_kind 0 = DotProduct, 1 = CrossAttentionBlock. */
