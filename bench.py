@@ -333,6 +333,18 @@ def run_ours(args):
         "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1],
     }
 
+    # worst case for the row packing: every profile position valid (one user per 64-row bin)
+    with torch.no_grad():
+        full = [{k: v.to(dev) for k, v in synth.make_eval_batch(shape, B, seed=5000 + i, all_valid=True).items()}
+                for i in range(2)]
+        for b in full:
+            b["o_c"] = b["o_c"][:, :1, :].contiguous().expand(-1, b["o_x"].shape[1], -1)
+        for i in range(2):
+            step(full[i % 2])
+        ms_full = timed(lambda i: step(full[i % 2]), max(3, K // 2)) / max(3, K // 2)
+    out["all_valid_profiles"] = {"value": users_per_step / (ms_full / 1e3), "unit": "users/s", "ms_per_step": ms_full,
+                                 "what": "same step with all 50 profile positions valid (no padding to skip)"}
+
     if world == 1 and rank == 0:
         if not args.no_train:
             out["train"] = time_train(shape, args, dev, table)

@@ -70,7 +70,8 @@ struct TcArgs {
   int cat_lo;                                        // > 0: full-catalog mode — candidate t is item cat_lo + t
   long long oc_user, oc_tgt;                         // strides (floats) of o_c over users / candidates ([B,T,C]: T*C, C;
                                                      //   one row per user, e.g. an expanded view or catalog mode: C, 0)
-  const int *row_src, *row_seg, *n_bins;             // packed profile rows (pack_rows_kernel)
+  const int *row_src, *row_seg;                      // packed profile rows (pack_rows_kernel)
+  int* n_bins;                                       // [0] bins written by the packing pass, [1] tile scheduler counter
 };
 
 struct TcSmem {
@@ -92,6 +93,7 @@ struct TcSmem {
   int uuser[128];                                    //   and their users
   uint32_t kbits[2][2];                              // valid-key bits: [bin][key half]
   uint32_t headbits[4];                              // rows that start a segment
+  int next_tile;                                     // dynamic tile scheduler
   uint64_t bar[2];
   uint32_t tmem_slot;
 };
@@ -538,9 +540,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   const int n_chunks = (a.T + 127) / 128;
   const int u = c.row / 64, i = c.row % 64;   // bin (64-row half of the tile) and row within it
   float* const plast = s.k_hi;                // dot decoder: last-position vectors per segment (K is unused there)
+  // tiles cost 62K cycles + 7K per user they hold: CTAs take the next tile from a global counter instead of
+  // a fixed stride, which evens out the last wave (a.n_bins[1], zeroed by the host before the launch)
+  int tile = blockIdx.x;
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();
+  for (bool first = true;; first = false) {
+    __syncthreads();   // every thread is done with the previous tile (and has read s.next_tile)
+    if (!first) tile = s.next_tile;
+    if (tile >= n_tiles) break;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
     const int src = a.row_src[(long long)tile * 128 + c.row];
@@ -561,6 +568,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     weight_prefetch(c, 0, a.blk[0].wq);
     weight_prefetch(c, 1, a.blk[0].wk);
     __syncthreads();
+    if (c.tid == 0) s.next_tile = (int)gridDim.x + atomicAdd(a.n_bins + 1, 1);   // read at the next loop top
     // segment list of the tile (one entry per user): index = number of segment heads before this one
     const int head_row = 64 * u + seg0;
     int seg_idx = __popc(s.headbits[head_row >> 5] & ((1u << (head_row & 31)) - 1u));
@@ -879,7 +887,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
       if (ca) publish();
       else __syncthreads();
-      if (uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);   // visible after this iteration's next CTA sync
+      if (!ca && uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);   // visible after this iteration's next CTA sync
       if (ca) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
@@ -896,7 +904,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             }
             c.ncommit++;
           }
-          // gather of the next chunk's candidate rows: in flight while this chunk's attention runs
+          // next iteration's context map and candidate rows: in flight while this chunk's attention runs (issued
+          // after the MMAs so that the issuing warp does not wait on them first)
+          if (hp == 0 && uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);
           if (hp == 0 && has1) {
             oid = s.oid[c.row];
             gather(oid, s.uuser[si1], ch1 * 128 + c.row, e, cv, twv);

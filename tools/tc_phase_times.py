@@ -15,7 +15,9 @@ shape = synth.BEAUTY
 model = synth.build_model(shape, decoder).to(dev).eval()
 model.embeds.set_attr_table(synth.make_attr_table(shape).to(dev))
 b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, B, seed=1).items()}
-prof, tgt = (b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])]
+# one context row per user, handed over as an expanded [B,T,C] view (what bench.py and the device loader do)
+o_c = b["o_c"][:, :1, :].contiguous().expand(-1, b["o_x"].shape[1], -1)
+prof, tgt = (b["p_x"], None, b["p_c"]), [(b["o_x"], None, o_c)]
 with torch.no_grad():
     for _ in range(3):
         fused.forward(model, prof, tgt, variant=2)
