@@ -70,7 +70,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -464,9 +464,12 @@ def roofline(op_ms, shape, B, decoder, pk):
     if "frac_of_fp32_ffma_peak" in r:
         from carca_replication_b200 import fused
         if dom == "fused_forward" and fused.VARIANT != 1:
-            roof["note"] = ("tcgen05 kind::tf32 kernel, fp32-grade via the 3xTF32 split: the tensor pipe executes 3x "
-                            "the algorithmic FLOPs counted here; peak is the measured dense bf16 cuBLAS rate "
-                            "(tf32 runs at half of it), so frac understates pipe occupancy by ~6x")
+            roof["note"] = ("tcgen05 kind::tf32 kernel, fp32-grade via the 3xTF32 split (3 MMAs per fp32 product). "
+                            "achieved = algorithmic FLOPs (all 50 profile positions per user, as the reference "
+                            "executes them) / measured time; the kernel runs the encoder on valid positions only "
+                            "(all_valid_profiles is the no-padding case). peak is the measured dense bf16 cuBLAS "
+                            "rate; the kernel is bound by the row operations between small dependent MMAs, not "
+                            "by tensor or HBM throughput (profiles/r01/README.md)")
         else:
             roof["note"] = ("fp32 CUDA-core (FFMA) kernel measured against the bf16 tensor peak; against the "
                             f"{FP32_FFMA_PEAK_TFLOPS:.1f} TFLOP/s fp32 FFMA peak the fraction is "
