@@ -8,14 +8,17 @@ PyTorch fallback.
 from . import abstract, carca, train, utils  # noqa: F401
 from .attrs import ItemAttrTable  # noqa: F401
 from .carca import (  # noqa: F401
-    CARCA, AllEmbedding, BinaryCrossEntropy, CrossAttentionBlock, DotProduct, IdentityEncoding,
-    LearnableEncoding, MultiHeadAttention, PositionalEncoding, SelfAttentionBlock,
+    CARCA, AllEmbedding, AttrCtxEmbedding, AttrEmbedding, BinaryCrossEntropy, CrossAttentionBlock, DotProduct,
+    IdEmbedding, IdentityEncoding, LearnableEncoding, MLPIdEmbedding, MultiHeadAttention, PositionalEncoding,
+    SelfAttentionBlock, WeightedDotProduct,
 )
+from .knn import KNN  # noqa: F401
 from .train import compute_HR, compute_NDCG, evaluate  # noqa: F401
 from .utils import get_mask, to  # noqa: F401
 
 __all__ = [
-    "CARCA", "AllEmbedding", "BinaryCrossEntropy", "CrossAttentionBlock", "DotProduct", "IdentityEncoding",
+    "CARCA", "AllEmbedding", "AttrCtxEmbedding", "AttrEmbedding", "IdEmbedding", "MLPIdEmbedding",
+    "WeightedDotProduct", "KNN", "BinaryCrossEntropy", "CrossAttentionBlock", "DotProduct", "IdentityEncoding",
     "LearnableEncoding", "MultiHeadAttention", "PositionalEncoding", "SelfAttentionBlock", "ItemAttrTable",
     "compute_HR", "compute_NDCG", "evaluate", "get_mask", "to",
 ]

@@ -78,6 +78,15 @@ SIGNATURES = {
     "carca_embed_fwd": [vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32, vp],
     "carca_embed_bwd": [P(EmbedGrads), vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32,
                         vp, vp, vp, vp],
+    "carca_feats_fwd": [vp, P(EmbedParams), P(AttrSource), vp, vp, i32, vp],
+    "carca_feats_bwd": [vp, vp, vp, P(EmbedParams), P(AttrSource), vp, vp, i32, vp, vp],
+    "carca_gather_rows_fwd": [vp, vp, vp, f32, i32, i32, vp],
+    "carca_gather_rows_bwd": [vp, vp, vp, f32, i32, i32, vp],
+    "carca_pos_mask_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "carca_pos_mask_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "carca_wdot_score_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i64, i32, vp],
+    "carca_wdot_score_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i64, i32, vp],
+    "carca_knn_score": [vp, vp, vp, i32, i32, i32, i32, i64, i32, vp],
     "carca_dropout": [vp, vp, i64, f32, u64, u32, vp],
     "carca_layernorm_fwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp],
     "carca_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -125,6 +125,104 @@ class AllEmbedding(Embedding):
         return e
 
 
+class _VariantEmbedding(Embedding):
+    """Shared tail of the ablation embeddings: positional encoding of profile rows, then the mask."""
+
+    def _finish(self, e: Tensor, mask: Tensor, target: bool) -> Tensor:
+        pos = None
+        if not target:
+            if hasattr(self.enc, "table"):
+                pos = self.enc.table(e.shape[1])
+            else:                                         # a user-supplied Encoding plug-in
+                return self.enc.forward(ops.PosMaskFn.apply(e, None, torch.ones_like(mask))) * mask.unsqueeze(2)
+        return ops.PosMaskFn.apply(e, pos, mask)
+
+
+class _AttrSourceMixin:
+    def set_attr_table(self, table: Optional[ItemAttrTable]):
+        self._attr_table = [] if table is None else [table]
+        return self
+
+    @property
+    def attr_table(self) -> Optional[ItemAttrTable]:
+        return self._attr_table[0] if self._attr_table else None
+
+    def _apply(self, fn, *args, **kwargs):
+        for t in self._attr_table:
+            t._apply(fn, *args, **kwargs)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _split(self, a):
+        table = a if isinstance(a, ItemAttrTable) else (self.attr_table if a is None else None)
+        return table, (a if isinstance(a, Tensor) else None)
+
+
+class AttrCtxEmbedding(_AttrSourceMixin, _VariantEmbedding):
+    """Attributes + context only: Lin_{g->d}(Lin_{A+C->g}([a | c])) (src/carca.py:98-122)."""
+
+    def __init__(self, d: int, g: int, n_ctx: int, n_attrs: int, enc: Encoding):
+        super().__init__()
+        self.d, self.enc = d, enc
+        self.feats_embed = _xavier(nn.Linear(n_ctx + n_attrs, g))
+        self.joint_embed = _xavier(nn.Linear(g, d))
+        self._attr_table: List[ItemAttrTable] = []
+
+    def forward(self, x: Tensor, a, c: Tensor, mask: Tensor, target: bool) -> Tensor:
+        table, dense = self._split(a)
+        q = ops.FeatsFn.apply(x, c, dense, self.feats_embed.weight, self.feats_embed.bias, table)
+        e = ops.LinearFn.apply(q, self.joint_embed.weight, self.joint_embed.bias)
+        return self._finish(e, mask, target)
+
+
+class AttrEmbedding(_AttrSourceMixin, _VariantEmbedding):
+    """Attributes only: Lin_{g->d}(Lin_{A->g}(a)) (src/carca.py:125-149)."""
+
+    def __init__(self, d: int, g: int, n_attrs: int, enc: Encoding):
+        super().__init__()
+        self.d, self.enc = d, enc
+        self.feats_embed = _xavier(nn.Linear(n_attrs, g))
+        self.joint_embed = _xavier(nn.Linear(g, d))
+        self._attr_table: List[ItemAttrTable] = []
+
+    def forward(self, x: Tensor, a, c: Tensor, mask: Tensor, target: bool) -> Tensor:
+        table, dense = self._split(a)
+        q = ops.FeatsFn.apply(x, None, dense, self.feats_embed.weight, self.feats_embed.bias, table)
+        e = ops.LinearFn.apply(q, self.joint_embed.weight, self.joint_embed.bias)
+        return self._finish(e, mask, target)
+
+
+class IdEmbedding(_VariantEmbedding):
+    """Item ids only: sqrt(d) * Emb[x] (src/carca.py:152-171)."""
+
+    def __init__(self, n_items: int, d: int, enc: Encoding):
+        super().__init__()
+        self.d, self.enc = d, enc
+        self.items_embed = _xavier(nn.Embedding(n_items, d, padding_idx=0))
+        with torch.no_grad():
+            self.items_embed.weight[0].zero_()
+
+    def forward(self, x: Tensor, a, c: Tensor, mask: Tensor, target: bool) -> Tensor:
+        e = ops.GatherRowsFn.apply(x, self.items_embed.weight, self.d ** 0.5)
+        return self._finish(e, mask, target)
+
+
+class MLPIdEmbedding(_VariantEmbedding):
+    """Lin_{g->d}(sqrt(d) * Emb_g[x]) (src/carca.py:174-198)."""
+
+    def __init__(self, n_items: int, d: int, g: int, enc: Encoding):
+        super().__init__()
+        self.d, self.enc = d, enc
+        self.items_embed = _xavier(nn.Embedding(n_items, g, padding_idx=0))
+        self.feats_embed = _xavier(nn.Linear(g, d))
+        with torch.no_grad():
+            self.items_embed.weight[0].zero_()
+
+    def forward(self, x: Tensor, a, c: Tensor, mask: Tensor, target: bool) -> Tensor:
+        z = ops.GatherRowsFn.apply(x, self.items_embed.weight, self.d ** 0.5)
+        e = ops.LinearFn.apply(z, self.feats_embed.weight, self.feats_embed.bias)
+        return self._finish(e, mask, target)
+
+
 # ------------------------------------------------------------------------------- attention
 class MultiHeadAttention(nn.Module):
     """Masked multi-head attention without output projection (src/carca.py:204-265)."""
@@ -214,6 +312,20 @@ class DotProduct(Decoder):
 
     def forward(self, o: Tensor, o_mask: Tensor, p: Tensor, p_mask: Tensor) -> Tensor:
         return ops.DotScoreFn.apply(o, p, bool(self.training))
+
+
+class WeightedDotProduct(Decoder):
+    """Dot product with profile position i scaled by sum_{j<=i} gamma^j, optional L2 normalisation of both
+    sides (src/carca.py:368-395; the reference's [L,L] weight tensor only ever yields that per-position
+    scalar).  `device` is accepted for signature compatibility (scripts/training.py:98)."""
+
+    def __init__(self, gamma: float, seq_len: int, normalize: bool, device: str = "cuda"):
+        super().__init__()
+        self.gamma, self.seq_len, self.norm = float(gamma), int(seq_len), bool(normalize)
+        self.sig = nn.Sigmoid()
+
+    def forward(self, o: Tensor, o_mask: Tensor, p: Tensor, p_mask: Tensor) -> Tensor:
+        return ops.WDotScoreFn.apply(o, p, bool(self.training), self.gamma, self.norm)
 
 
 # ------------------------------------------------------------------------------- model

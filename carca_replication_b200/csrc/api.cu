@@ -14,6 +14,7 @@
 #include "gemm.cuh"
 #include "layernorm.cuh"
 #include "score.cuh"
+#include "variants.cuh"
 
 using namespace carca;
 
@@ -225,14 +226,10 @@ int carca_dropout(float* y, const float* x, int64_t n, float p, uint64_t seed, u
 }
 
 // ------------------------------------------------------------------------------------ embedding
-int carca_embed_fwd(float* e, float* q_out, const carca_embed_params* w, const carca_attr_source* at,
-                    const int32_t* x, const float* ctx, const float* mask, int n_rows, int n_cols, int is_target,
-                    void* stream) {
-  cudaStream_t st = S(stream);
-  const int P = n_rows * n_cols;
-  if (P <= 0) return 0;
-  const int d = w->d, g = w->g, A = w->n_attrs, C = w->n_ctx;
-  CARCA_REQUIRE(q_out != nullptr, "embed_fwd: q_out is required");
+// q = Wf [a | c] + bf for P positions (the first linear of every attribute embedding, src/carca.py:86,113,138)
+static int feats_forward(float* q_out, const carca_embed_params* w, const carca_attr_source* at, const int32_t* x,
+                         const float* ctx, const float* mask, int P, cudaStream_t st) {
+  const int g = w->g, A = w->n_attrs, C = w->n_ctx;
   if (at->kind == CARCA_ATTR_CSR) {
     CARCA_REQUIRE(w->feats_wT != nullptr, "embed_fwd: CSR attributes need feats_wT");
     auto k = feat_csr_fwd_kernel;
@@ -247,6 +244,54 @@ int carca_embed_fwd(float* e, float* q_out, const carca_embed_params* w, const c
   } else {
     return fail(-2, "embed_fwd: unknown attribute source kind %d", at->kind);
   }
+  return 0;
+}
+
+// d feats_w, d feats_b from dq [P, g]
+static int feats_backward(float* d_feats_w, float* d_feats_b, const float* dq, const carca_embed_params* w,
+                          const carca_attr_source* at, const int32_t* x, const float* ctx, const float* mask, int P,
+                          float* scratch_wT, cudaStream_t st) {
+  const int g = w->g, A = w->n_attrs, C = w->n_ctx;
+  TRY(colsum(d_feats_b, dq, P, g, g, st));
+  if (C > 0) TRY(linear_dw(d_feats_w + A, dq, ctx, P, g, C, A + C, C, st));           // dWf[:, A:]
+  if (at->kind == CARCA_ATTR_CSR) {
+    CARCA_REQUIRE(scratch_wT != nullptr, "embed_bwd: CSR attributes need scratch_wT");
+    auto k = feat_csr_bwd_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, scratch_wT, dq, x, at->csr_rowptr, at->csr_cols,
+                 at->csr_vals, mask, P, g);
+    TRY(check_launch("feat_csr_bwd"));
+    TRY(transpose(d_feats_w, scratch_wT, A, g, g, A + C, 1, st));                     // dWf[:, :A] += dWT^T
+  } else if (at->kind == CARCA_ATTR_TABLE || at->kind == CARCA_ATTR_DENSE) {
+    const int* rows = at->kind == CARCA_ATTR_TABLE ? x : nullptr;
+    TRY(linear_dw(d_feats_w, dq, at->dense, P, g, A, A + C, A, st, rows));
+  } else {
+    return fail(-2, "embed_bwd: unknown attribute source kind %d", at->kind);
+  }
+  return 0;
+}
+
+int carca_feats_fwd(float* q, const carca_embed_params* w, const carca_attr_source* at, const int32_t* x,
+                    const float* ctx, int P, void* stream) {
+  if (P <= 0) return 0;
+  return feats_forward(q, w, at, x, ctx, nullptr, P, S(stream));
+}
+
+int carca_feats_bwd(float* d_feats_w, float* d_feats_b, const float* dq, const carca_embed_params* w,
+                    const carca_attr_source* at, const int32_t* x, const float* ctx, int P, float* scratch_wT,
+                    void* stream) {
+  if (P <= 0) return 0;
+  return feats_backward(d_feats_w, d_feats_b, dq, w, at, x, ctx, nullptr, P, scratch_wT, S(stream));
+}
+
+int carca_embed_fwd(float* e, float* q_out, const carca_embed_params* w, const carca_attr_source* at,
+                    const int32_t* x, const float* ctx, const float* mask, int n_rows, int n_cols, int is_target,
+                    void* stream) {
+  cudaStream_t st = S(stream);
+  const int P = n_rows * n_cols;
+  if (P <= 0) return 0;
+  const int d = w->d, g = w->g;
+  CARCA_REQUIRE(q_out != nullptr, "embed_fwd: q_out is required");
+  TRY(feats_forward(q_out, w, at, x, ctx, mask, P, st));
   const float sqrt_d = (float)std::sqrt((double)d);
   // e = sqrt(d) * E[x] Wj[:, :d]^T
   TRY(linear(e, w->items_embed, w->joint_w, nullptr, P, d, d, d + g, st, 0, nullptr, nullptr, 0, nullptr, x, d,
@@ -267,7 +312,7 @@ int carca_embed_bwd(const carca_embed_grads* gr, const float* de, const float* q
   cudaStream_t st = S(stream);
   const int P = n_rows * n_cols;
   if (P <= 0) return 0;
-  const int d = w->d, g = w->g, A = w->n_attrs, C = w->n_ctx;
+  const int d = w->d, g = w->g;
   const float sqrt_d = (float)std::sqrt((double)d);
   float* dem = scratch_pd;
   float* dz = scratch_pd + (long long)P * d;
@@ -285,22 +330,72 @@ int carca_embed_bwd(const carca_embed_grads* gr, const float* de, const float* q
     CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, gr->items_embed, dz, x, P, d);
     TRY(check_launch("scatter_add_rows"));
   }
-  TRY(colsum(gr->feats_b, dq, P, g, g, st));
-  if (C > 0) TRY(linear_dw(gr->feats_w + A, dq, ctx, P, g, C, A + C, C, st));           // dWf[:, A:]
-  if (at->kind == CARCA_ATTR_CSR) {
-    CARCA_REQUIRE(scratch_wT != nullptr, "embed_bwd: CSR attributes need scratch_wT");
-    auto k = feat_csr_bwd_kernel;
-    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, scratch_wT, dq, x, at->csr_rowptr, at->csr_cols,
-                 at->csr_vals, mask, P, g);
-    TRY(check_launch("feat_csr_bwd"));
-    TRY(transpose(gr->feats_w, scratch_wT, A, g, g, A + C, 1, st));                     // dWf[:, :A] += dWT^T
-  } else if (at->kind == CARCA_ATTR_TABLE || at->kind == CARCA_ATTR_DENSE) {
-    const int* rows = at->kind == CARCA_ATTR_TABLE ? x : nullptr;
-    TRY(linear_dw(gr->feats_w, dq, at->dense, P, g, A, A + C, A, st, rows));
-  } else {
-    return fail(-2, "embed_bwd: unknown attribute source kind %d", at->kind);
-  }
+  return feats_backward(gr->feats_w, gr->feats_b, dq, w, at, x, ctx, mask, P, scratch_wT, st);
+}
+
+// ------------------------------------------------------------------------------------ module variants (N3)
+int carca_gather_rows_fwd(float* out, const float* table, const int32_t* ids, float alpha, int P, int d,
+                          void* stream) {
+  if (P <= 0) return 0;
+  auto k = gather_rows_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, S(stream), out, table, ids, alpha, P, d);
+  return check_launch("gather_rows");
+}
+
+int carca_gather_rows_bwd(float* d_table, const float* d_out, const int32_t* ids, float alpha, int P, int d,
+                          void* stream) {
+  if (P <= 0) return 0;
+  auto k = scatter_add_rows_scaled_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, S(stream), d_table, d_out, ids, alpha, P, d);
+  return check_launch("scatter_add_rows_scaled");
+}
+
+int carca_pos_mask_fwd(float* out, const float* in, const float* pos, const float* mask, int n_rows, int n_cols,
+                       int d, void* stream) {
+  const long long total = (long long)n_rows * n_cols * d;
+  if (total <= 0) return 0;
+  auto k = pos_mask_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, S(stream), out, in, pos, mask, total, d,
+               n_cols);
+  return check_launch("pos_mask");
+}
+
+int carca_pos_mask_bwd(float* d_in, float* d_pos, const float* d_out, const float* mask, int n_rows, int n_cols,
+                       int d, void* stream) {
+  const long long P = (long long)n_rows * n_cols;
+  if (P <= 0) return 0;
+  TRY(scale_rows(d_in, d_out, mask, make_drop(0.f, 0ull, 0u), P, d, S(stream)));
+  if (d_pos) TRY(colsum(d_pos, d_in, n_rows, n_cols * d, (long long)n_cols * d, S(stream)));
   return 0;
+}
+
+int carca_wdot_score_fwd(float* y, const float* p, const float* o, int B, int T, int Lp, int d, int per_position,
+                         float gamma, int normalize, int64_t ldy, int col0, void* stream) {
+  if ((long long)B * T <= 0) return 0;
+  if (per_position) CARCA_REQUIRE(T == Lp, "wdot_score: training mode needs T == L (%d vs %d)", T, Lp);
+  auto k = wdot_score_fwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, S(stream), y, p, o, B, T, Lp, d, per_position,
+               gamma, normalize, (long long)ldy, col0);
+  return check_launch("wdot_score_fwd");
+}
+
+int carca_wdot_score_bwd(float* d_o, float* d_p, const float* dy, const float* y, const float* p, const float* o,
+                         int B, int T, int Lp, int d, int per_position, float gamma, int normalize, int64_t ldy,
+                         int col0, void* stream) {
+  if ((long long)B * T <= 0) return 0;
+  auto k = wdot_score_bwd_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, S(stream), d_o, d_p, dy, y, p, o, B, T, Lp, d,
+               per_position, gamma, normalize, (long long)ldy, col0);
+  return check_launch("wdot_score_bwd");
+}
+
+int carca_knn_score(float* y, const float* p_a, const float* o_a, int B, int T, int Lp, int A, int64_t ldy, int col0,
+                    void* stream) {
+  if ((long long)B * T <= 0) return 0;
+  auto k = knn_score_kernel;
+  CARCA_LAUNCH(k, dim3(warp_rows_grid((long long)B * T)), dim3(256), 0, S(stream), y, p_a, o_a, B, T, Lp, A,
+               (long long)ldy, col0);
+  return check_launch("knn_score");
 }
 
 // ------------------------------------------------------------------------------------ layernorm / linear

@@ -464,3 +464,148 @@ def rank_metrics_(acc: Tensor, y_pred: Tensor, y_true: Tensor, k: int, first_ran
     B, T = y_pred.shape
     N.call("carca_rank_metrics", acc.data_ptr(), None if first_rank is None else N.i32p(first_rank),
            y_pred.data_ptr(), y_true.data_ptr(), B, T, y_pred.stride(0), y_true.stride(0), int(k), N.stream())
+
+
+# ------------------------------------------------------------------------------- module variants
+class FeatsFn(torch.autograd.Function):
+    """q = Wf [a | c] + bf (src/carca.py:113, :138): dense `a` tensor or the device-resident ItemAttrTable."""
+
+    @staticmethod
+    def forward(ctx, x, c, a_dense, Wf, bf, table):
+        N.require_device(x, c, a_dense, Wf)
+        P = x.numel()
+        g = Wf.shape[0]
+        Cn = 0 if c is None else c.shape[-1]
+        A = Wf.shape[1] - Cn
+        x = as_ids(x)
+        c = None if c is None else as_f32(c)
+        a_dense = None if a_dense is None else as_f32(a_dense)
+        if a_dense is None and table is None:
+            raise RuntimeError("attribute embedding: attributes missing (pass the dense tensor or register an ItemAttrTable)")
+        sparse = a_dense is None and table.is_sparse
+        Wfc, bfc = _c(Wf), _c(bf)
+        WfT = None
+        if sparse:
+            WfT = torch.empty((A + Cn, g), dtype=torch.float32, device=Wf.device)
+            N.call("carca_transpose", N.f32p(WfT), N.f32p(Wfc), g, A + Cn, 0, N.stream())
+        q = torch.empty((*x.shape, g), dtype=torch.float32, device=Wf.device)
+        prm = N.EmbedParams()
+        prm.g, prm.n_attrs, prm.n_ctx = g, A, Cn
+        prm.feats_w, prm.feats_b = N.f32p(Wfc), N.f32p(bfc)
+        prm.feats_wT = None if WfT is None else N.f32p(WfT)
+        src = _attr_source(table, a_dense)
+        N.call("carca_feats_fwd", N.f32p(q), C.byref(prm), C.byref(src), N.i32p(x), N.f32p(c), P, N.stream())
+        ctx.save_for_backward(x, c, a_dense, Wfc, bfc)
+        ctx.table, ctx.sparse = table, sparse
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        x, c, a_dense, Wf, bf = ctx.saved_tensors
+        P = x.numel()
+        g = Wf.shape[0]
+        Cn = 0 if c is None else c.shape[-1]
+        A = Wf.shape[1] - Cn
+        dq = as_f32(dq)
+        gWf, gbf = torch.zeros_like(Wf), torch.zeros_like(bf)
+        prm = N.EmbedParams()
+        prm.g, prm.n_attrs, prm.n_ctx = g, A, Cn
+        prm.feats_w, prm.feats_b = N.f32p(Wf), N.f32p(bf)
+        src = _attr_source(ctx.table, a_dense)
+        s_wT = torch.zeros((A, g), dtype=torch.float32, device=Wf.device) if ctx.sparse else None
+        N.call("carca_feats_bwd", N.f32p(gWf), N.f32p(gbf), N.f32p(dq), C.byref(prm), C.byref(src), N.i32p(x),
+               N.f32p(c), P, N.f32p(s_wT), N.stream())
+        return None, None, None, gWf, gbf, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """alpha * nn.Embedding(x) with padding_idx = 0 (src/carca.py:161-162, :187-188)."""
+
+    @staticmethod
+    def forward(ctx, x, E, alpha):
+        N.require_device(x, E)
+        x, Ec = as_ids(x), _c(E)
+        d = E.shape[1]
+        out = torch.empty((*x.shape, d), dtype=torch.float32, device=E.device)
+        N.call("carca_gather_rows_fwd", N.f32p(out), N.f32p(Ec), N.i32p(x), float(alpha), x.numel(), d, N.stream())
+        ctx.save_for_backward(x)
+        ctx.shape, ctx.alpha = tuple(E.shape), float(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        dout = as_f32(dout)
+        gE = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        N.call("carca_gather_rows_bwd", N.f32p(gE), N.f32p(dout), N.i32p(x), ctx.alpha, x.numel(), ctx.shape[1],
+               N.stream())
+        return None, gE, None
+
+
+class PosMaskFn(torch.autograd.Function):
+    """(e + pos[position]) * mask: positional encoding of profile rows + the final mask of every embedding."""
+
+    @staticmethod
+    def forward(ctx, e, pos, mask):
+        N.require_device(e, mask)
+        e, mask = as_f32(e), as_f32(mask)
+        n_rows, n_cols, d = e.shape
+        posc = None if pos is None else _c(pos)
+        if posc is not None and posc.shape[0] < n_cols:
+            raise RuntimeError(f"sequence length {n_cols} > positional table {posc.shape[0]}")
+        out = torch.empty_like(e)
+        N.call("carca_pos_mask_fwd", N.f32p(out), N.f32p(e), N.f32p(posc), N.f32p(mask), n_rows, n_cols, d, N.stream())
+        ctx.save_for_backward(mask)
+        ctx.pos_shape = None if pos is None else tuple(pos.shape)
+        ctx.dims = (n_rows, n_cols, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        n_rows, n_cols, d = ctx.dims
+        dout = as_f32(dout)
+        de = torch.empty_like(dout)
+        gpos = None if ctx.pos_shape is None else torch.zeros(ctx.pos_shape, dtype=torch.float32, device=dout.device)
+        N.call("carca_pos_mask_bwd", N.f32p(de), N.f32p(gpos), N.f32p(dout), N.f32p(mask), n_rows, n_cols, d, N.stream())
+        return de, gpos, None
+
+
+class WDotScoreFn(torch.autograd.Function):
+    """WeightedDotProduct.forward (src/carca.py:377-395)."""
+
+    @staticmethod
+    def forward(ctx, o, p, per_position, gamma, normalize):
+        N.require_device(o, p)
+        o, p = as_f32(o), as_f32(p)
+        B, T, d = o.shape
+        Lp = p.shape[1]
+        y = torch.empty((B, T), dtype=torch.float32, device=o.device)
+        N.call("carca_wdot_score_fwd", N.f32p(y), N.f32p(p), N.f32p(o), B, T, Lp, d, int(bool(per_position)),
+               float(gamma), int(bool(normalize)), T, 0, N.stream())
+        ctx.save_for_backward(o, p, y)
+        ctx.cfg = (int(bool(per_position)), float(gamma), int(bool(normalize)))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        o, p, y = ctx.saved_tensors
+        B, T, d = o.shape
+        Lp = p.shape[1]
+        per_position, gamma, normalize = ctx.cfg
+        dy = as_f32(dy)
+        d_o = torch.empty_like(o)
+        d_p = torch.zeros_like(p)
+        N.call("carca_wdot_score_bwd", N.f32p(d_o), N.f32p(d_p), N.f32p(dy), N.f32p(y), N.f32p(p), N.f32p(o), B, T, Lp,
+               d, per_position, gamma, normalize, T, 0, N.stream())
+        return d_o, d_p, None, None, None
+
+
+def knn_scores(p_a: Tensor, o_a: Tensor) -> Tensor:
+    """KNN.forward (src/knn.py:14-21) for one target tuple: <attributes of the last profile item, candidate attributes>."""
+    N.require_device(p_a, o_a)
+    p_a, o_a = as_f32(p_a), as_f32(o_a)
+    B, T, A = o_a.shape
+    y = torch.empty((B, T), dtype=torch.float32, device=o_a.device)
+    N.call("carca_knn_score", N.f32p(y), N.f32p(p_a), N.f32p(o_a), B, T, p_a.shape[1], A, T, 0, N.stream())
+    return y

@@ -104,6 +104,43 @@ int carca_embed_bwd(const carca_embed_grads* grads, const float* de, const float
                     const float* ctx, const float* mask, int n_rows, int n_cols, int is_target,
                     float* scratch_pd, float* scratch_pg, float* scratch_wT, void* stream);
 
+/* ------------------------------------------------------------------ embedding / decoder variants */
+/* q [P, g] = Wf [a | c] + bf — the attribute(/context) projection shared by AllEmbedding, AttrCtxEmbedding
+ * and AttrEmbedding (src/carca.py:86, :113, :138; n_ctx = 0 and ctx = NULL for AttrEmbedding).
+ * Uses feats_w / feats_wT / feats_b, g, n_attrs, n_ctx of `w`.                                         */
+int carca_feats_fwd(float* q, const carca_embed_params* w, const carca_attr_source* attrs, const int32_t* x,
+                    const float* ctx, int P, void* stream);
+/* d feats_w [g, A+C], d feats_b [g] accumulated from dq [P, g]; scratch_wT [A, g] zero-initialised (CSR only) */
+int carca_feats_bwd(float* d_feats_w, float* d_feats_b, const float* dq, const carca_embed_params* w,
+                    const carca_attr_source* attrs, const int32_t* x, const float* ctx, int P, float* scratch_wT,
+                    void* stream);
+
+/* out[p,:] = alpha * table[ids[p],:] — nn.Embedding lookup with the sqrt(d) scale of IdEmbedding / MLPIdEmbedding
+ * (src/carca.py:161-162, :187-188); backward scatter-adds alpha * d_out into d_table, skipping id 0 (padding_idx). */
+int carca_gather_rows_fwd(float* out, const float* table, const int32_t* ids, float alpha, int P, int d, void* stream);
+int carca_gather_rows_bwd(float* d_table, const float* d_out, const int32_t* ids, float alpha, int P, int d,
+                          void* stream);
+
+/* out = (in + pos[position]) * mask — positional encoding of non-target rows (pos may be NULL) and the final mask
+ * of every embedding (e.g. src/carca.py:116-120).  in/out [n_rows, n_cols, d], mask [n_rows, n_cols].
+ * Backward: d_in = d_out * mask; d_pos [n_cols, d] += column sums (d_pos may be NULL).                 */
+int carca_pos_mask_fwd(float* out, const float* in, const float* pos, const float* mask, int n_rows, int n_cols, int d,
+                       void* stream);
+int carca_pos_mask_bwd(float* d_in, float* d_pos, const float* d_out, const float* mask, int n_rows, int n_cols, int d,
+                       void* stream);
+
+/* WeightedDotProduct.forward (src/carca.py:377-395): profile position i is scaled by sum_{j<=i} gamma^j, both sides
+ * optionally L2-normalised, then sigmoid(<p, o>) or (<p, o> + 1) / 2.  Same layout rules as carca_dot_score_*.  */
+int carca_wdot_score_fwd(float* y, const float* p, const float* o, int B, int T, int Lp, int d, int per_position,
+                         float gamma, int normalize, int64_t ldy, int col0, void* stream);
+int carca_wdot_score_bwd(float* d_o, float* d_p, const float* dy, const float* y, const float* p, const float* o, int B,
+                         int T, int Lp, int d, int per_position, float gamma, int normalize, int64_t ldy, int col0,
+                         void* stream);
+
+/* KNN.forward (src/knn.py:14-21): y[b, col0 + t] = <p_a[b, Lp-1, :], o_a[b, t, :]> on the dense attribute tensors */
+int carca_knn_score(float* y, const float* p_a, const float* o_a, int B, int T, int Lp, int A, int64_t ldy, int col0,
+                    void* stream);
+
 /* ------------------------------------------------------------------ dropout (nn.Dropout) */
 /* y = x * keep/(1-p) with the Philox stream (site, seed); also its own backward (apply to dy).
  * replaces self.dropout(p_e), src/carca.py:416                                              */

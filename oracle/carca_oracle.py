@@ -67,6 +67,8 @@ class OracleConfig:
     seed: int = 0                 # dropout stream seed (ours, see oracle/philox.py)
     learnable_pos: bool = False   # embeds.enc.encoding.weight present
     sinus_pos: bool = False       # embeds.enc.pe present
+    embedding: str = "all"        # "all" | "id" | "mlpid" | "attr" | "attrctx"  (scripts/training.py:78-89)
+    gamma: float = 0.9            # WeightedDotProduct (decoder "wdot" / "wdot_norm")
 
 
 class Dropper:
@@ -106,12 +108,26 @@ def embed_all(sd: Dict[str, Tensor], ids: Tensor, attrs: Tensor, ctx: Tensor, ma
     (+ positional encoding for the profile only);  e *= mask.
     """
     d = cfg.d
-    feats = torch.cat((attrs, ctx), dim=-1)                                   # :86
-    q = F.linear(feats, sd["embeds.feats_embed.weight"], sd["embeds.feats_embed.bias"])
-    z = F.embedding(ids.long(), sd["embeds.items_embed.weight"])             # :87
-    z = z * (d ** 0.5)                                                        # :88
-    e = F.linear(torch.cat((z, q), dim=-1), sd["embeds.joint_embed.weight"],
-                 sd["embeds.joint_embed.bias"])                               # :89
+    if cfg.embedding == "all":
+        feats = torch.cat((attrs, ctx), dim=-1)                               # :86
+        q = F.linear(feats, sd["embeds.feats_embed.weight"], sd["embeds.feats_embed.bias"])
+        z = F.embedding(ids.long(), sd["embeds.items_embed.weight"])         # :87
+        z = z * (d ** 0.5)                                                    # :88
+        e = F.linear(torch.cat((z, q), dim=-1), sd["embeds.joint_embed.weight"],
+                     sd["embeds.joint_embed.bias"])                           # :89
+    elif cfg.embedding == "attrctx":                                          # AttrCtxEmbedding.forward, :112-114
+        q = F.linear(torch.cat((attrs, ctx), dim=-1), sd["embeds.feats_embed.weight"], sd["embeds.feats_embed.bias"])
+        e = F.linear(q, sd["embeds.joint_embed.weight"], sd["embeds.joint_embed.bias"])
+    elif cfg.embedding == "attr":                                             # AttrEmbedding.forward, :139-141
+        q = F.linear(attrs, sd["embeds.feats_embed.weight"], sd["embeds.feats_embed.bias"])
+        e = F.linear(q, sd["embeds.joint_embed.weight"], sd["embeds.joint_embed.bias"])
+    elif cfg.embedding == "id":                                               # IdEmbedding.forward, :163-165
+        e = F.embedding(ids.long(), sd["embeds.items_embed.weight"]) * (d ** 0.5)
+    elif cfg.embedding == "mlpid":                                            # MLPIdEmbedding.forward, :189-192
+        z = F.embedding(ids.long(), sd["embeds.items_embed.weight"]) * (d ** 0.5)
+        e = F.linear(z, sd["embeds.feats_embed.weight"], sd["embeds.feats_embed.bias"])
+    else:
+        raise ValueError(f"Unknown embedding type: {cfg.embedding}")
     if not is_target:                                                         # :91-92
         if cfg.learnable_pos:                                                 # :25-31
             e = e + sd["embeds.enc.encoding.weight"][: e.size(1)].unsqueeze(0)
@@ -196,6 +212,19 @@ def dot_scores(o: Tensor, p: Tensor, training: bool) -> Tensor:
     return torch.sigmoid(y)
 
 
+def weighted_dot_scores(o: Tensor, p: Tensor, training: bool, gamma: float, normalize: bool) -> Tensor:
+    """WeightedDotProduct.forward, src/carca.py:377-395 (the [L,L,1] weight of :373-374 rebuilt here)."""
+    L = p.size(1)
+    W = (gamma ** torch.arange(0, L).unsqueeze(0).repeat(L, 1)).tril().unsqueeze(-1)   # :373-374
+    pw = p.unsqueeze(2).repeat(1, 1, L, 1)                                    # :378
+    p = torch.sum(pw * W, dim=2)                                              # :379
+    if normalize:
+        p = F.normalize(p, dim=2)                                             # :382
+        o = F.normalize(o, dim=2)                                             # :383
+    y = torch.sum(p * o, dim=-1) if training else torch.sum(p[:, -1:, :] * o, dim=-1)   # :385-388
+    return (y + 1.0) / 2.0 if normalize else torch.sigmoid(y)                 # :390-393
+
+
 # ----------------------------------------------------------------------------- model
 def encode_profile(sd, cfg: OracleConfig, profile, training: bool, drop: Dropper) -> Tuple[Tensor, Tensor]:
     """src/carca.py:412-421 — mask, embed, dropout, blocks, final LayerNorm."""
@@ -223,6 +252,8 @@ def carca_forward(sd: Dict[str, Tensor], cfg: OracleConfig, profile: Tuple[Tenso
                                        SITE_DECODER_ATTN + t_idx)
         elif cfg.decoder == "dot":
             y = dot_scores(o_e, p_e, training)
+        elif cfg.decoder in ("wdot", "wdot_norm"):
+            y = weighted_dot_scores(o_e, p_e, training, cfg.gamma, cfg.decoder == "wdot_norm")
         else:
             raise ValueError(f"Unknown decoder type: {cfg.decoder}")
         ys.append(y)                                                          # :428-429

@@ -20,9 +20,11 @@ import torch.nn as nn
 REF = os.environ.get("CARCA_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
 from src.carca import (  # noqa: E402
-    CARCA, AllEmbedding, BinaryCrossEntropy, CrossAttentionBlock, DotProduct, IdentityEncoding,
-    LearnableEncoding, MultiHeadAttention, PositionalEncoding, SelfAttentionBlock,
+    CARCA, AllEmbedding, AttrCtxEmbedding, AttrEmbedding, BinaryCrossEntropy, CrossAttentionBlock, DotProduct,
+    IdEmbedding, IdentityEncoding, LearnableEncoding, MLPIdEmbedding, MultiHeadAttention, PositionalEncoding,
+    SelfAttentionBlock, WeightedDotProduct,
 )
+from src.knn import KNN  # noqa: E402
 from src.train import compute_HR, compute_NDCG  # noqa: E402
 from src.utils import get_mask  # noqa: E402
 
@@ -37,11 +39,25 @@ def build_reference(cfg, seed):
         enc = LearnableEncoding(cfg["d"], cfg["L"])
     else:
         enc = PositionalEncoding(cfg["d"], cfg["L"])
-    emb = AllEmbedding(cfg["n_items"], cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
+    kind = cfg.get("embedding", "all")           # scripts/training.py:78-89
+    if kind == "all":
+        emb = AllEmbedding(cfg["n_items"], cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
+    elif kind == "id":
+        emb = IdEmbedding(cfg["n_items"], cfg["d"], enc)
+    elif kind == "mlpid":
+        emb = MLPIdEmbedding(cfg["n_items"], cfg["d"], cfg["g"], enc)
+    elif kind == "attr":
+        emb = AttrEmbedding(cfg["d"], cfg["g"], cfg["A"], enc)
+    else:
+        emb = AttrCtxEmbedding(cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
     blocks = nn.ModuleList([SelfAttentionBlock(cfg["d"], cfg["H"], cfg["p"], cfg["residual_sa"])
                             for _ in range(cfg["n_blocks"])])
-    dec = (CrossAttentionBlock(cfg["d"], cfg["H"], cfg["p"], cfg["residual_ca"])
-           if cfg["decoder"] == "ca" else DotProduct())
+    if cfg["decoder"] == "ca":
+        dec = CrossAttentionBlock(cfg["d"], cfg["H"], cfg["p"], cfg["residual_ca"])
+    elif cfg["decoder"] == "dot":
+        dec = DotProduct()
+    else:                                        # scripts/training.py:97-98
+        dec = WeightedDotProduct(cfg["gamma"], cfg["L"], cfg["decoder"] == "wdot_norm", "cpu")
     model = CARCA(d=cfg["d"], p=cfg["p"], emb=emb, enc=blocks, dec=dec)
     # zero biases / unit LayerNorms would hide bias bugs: perturb them
     g = torch.Generator().manual_seed(seed + 1)
@@ -49,7 +65,8 @@ def build_reference(cfg, seed):
         for name, prm in model.named_parameters():
             if name.endswith("bias") or ".norm" in name or name.startswith("norm."):
                 prm.add_(0.1 * torch.randn(prm.shape, generator=g))
-        model.embeds.items_embed.weight[0].zero_()
+        if hasattr(model.embeds, "items_embed"):
+            model.embeds.items_embed.weight[0].zero_()
     return model
 
 
@@ -244,10 +261,42 @@ CASES = {
     "single_user_ca": (dict(n_blocks=1), [5], [4]),
 }
 
+# module variants: written by `python tests/golden/make_golden.py variants`
+VARIANT_CASES = {
+    "idemb_dot": (dict(embedding="id", decoder="dot", encoding="learnable", n_blocks=1), [12, 5, 1, 0, 9], [12, 4, 1, 0, 7]),
+    "mlpid_ca": (dict(embedding="mlpid", n_blocks=1), [12, 3, 7], [10, 2, 5]),
+    "attr_dot": (dict(embedding="attr", decoder="dot", n_blocks=1), [12, 5, 0, 9], [12, 4, 0, 7]),
+    "attrctx_ca": (dict(embedding="attrctx", encoding="positional", n_blocks=1), [12, 3, 7], [10, 2, 5]),
+    "attrctx_dense_ca": (dict(embedding="attrctx", n_blocks=1, n_items=90, A=24, attr_kind="dense"),
+                          [12, 2, 6], [8, 3, 9]),
+    "wdot_all": (dict(decoder="wdot", gamma=0.3, d=32, g=16, H=1, n_blocks=1), [12, 5, 1, 9], [12, 4, 1, 7]),
+    "wdotnorm_all": (dict(decoder="wdot_norm", gamma=0.8, n_blocks=1), [12, 5, 1, 9], [12, 4, 1, 7]),
+}
+
+
+def run_knn_case(seed):
+    rng = np.random.default_rng(seed)
+    B, L, T, A = 5, 7, 11, 13
+    p_a = rng.random((B, L, A)).astype(np.float32)
+    o_a1, o_a2 = rng.random((B, T, A)).astype(np.float32), rng.random((B, 3, A)).astype(np.float32)
+    z = torch.zeros(1)
+    with torch.no_grad():
+        y = KNN().forward((z, t(p_a), z), [(z, t(o_a1), z), (z, t(o_a2), z)])
+    np.savez_compressed(os.path.join(OUT, "knn_ops.npz"), p_a=p_a, o_a1=o_a1, o_a2=o_a2, y=y.numpy())
+    print("knn_ops: ok")
+
+
 if __name__ == "__main__":
-    for i, (name, (over, le, lt)) in enumerate(CASES.items()):
-        cfg = dict(BASE)
-        cfg.update(over)
-        run_case(name, cfg, le, lt, seed=1234 + i)
-    run_mha_cases(77)
-    run_metric_cases(78)
+    if "variants" in sys.argv:
+        for i, (name, (over, le, lt)) in enumerate(VARIANT_CASES.items()):
+            cfg = dict(BASE)
+            cfg.update(over)
+            run_case(name, cfg, le, lt, seed=4321 + i)
+        run_knn_case(79)
+    else:
+        for i, (name, (over, le, lt)) in enumerate(CASES.items()):
+            cfg = dict(BASE)
+            cfg.update(over)
+            run_case(name, cfg, le, lt, seed=1234 + i)
+        run_mha_cases(77)
+        run_metric_cases(78)

@@ -8,7 +8,9 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 MODEL_CASES = ["beauty_ca", "beauty_dot", "men_ca", "men_dot_d128", "noresid_dot", "noresid_ca",
-               "learnable_ca", "sinus_dot", "single_user_ca"]
+               "learnable_ca", "sinus_dot", "single_user_ca",
+               # non-default module variants
+               "idemb_dot", "mlpid_ca", "attr_dot", "attrctx_ca", "attrctx_dense_ca", "wdot_all", "wdotnorm_all"]
 
 # north_star: fp32 scores within 1e-4 relative
 FP32_RTOL = 1e-4
@@ -31,7 +33,8 @@ def oracle_cfg(cfg, **over):
 
     kw = dict(d=cfg["d"], n_heads=cfg["H"], n_blocks=cfg["n_blocks"], decoder=cfg["decoder"],
               residual_sa=cfg["residual_sa"], residual_ca=cfg["residual_ca"], p_drop=cfg["p"],
-              learnable_pos=cfg["encoding"] == "learnable", sinus_pos=cfg["encoding"] == "positional")
+              learnable_pos=cfg["encoding"] == "learnable", sinus_pos=cfg["encoding"] == "positional",
+              embedding=cfg.get("embedding", "all"), gamma=cfg.get("gamma", 0.9))
     kw.update(over)
     return OracleConfig(**kw)
 

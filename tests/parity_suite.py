@@ -23,11 +23,25 @@ def build_model(cfg, sd, device, p=None):
         enc = cb.LearnableEncoding(cfg["d"], cfg["L"])
     else:
         enc = cb.PositionalEncoding(cfg["d"], cfg["L"])
-    emb = cb.AllEmbedding(cfg["n_items"], cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
+    kind = cfg.get("embedding", "all")               # the constructor calls of scripts/training.py:78-89
+    if kind == "all":
+        emb = cb.AllEmbedding(cfg["n_items"], cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
+    elif kind == "id":
+        emb = cb.IdEmbedding(cfg["n_items"], cfg["d"], enc)
+    elif kind == "mlpid":
+        emb = cb.MLPIdEmbedding(cfg["n_items"], cfg["d"], cfg["g"], enc)
+    elif kind == "attr":
+        emb = cb.AttrEmbedding(cfg["d"], cfg["g"], cfg["A"], enc)
+    else:
+        emb = cb.AttrCtxEmbedding(cfg["d"], cfg["g"], cfg["C"], cfg["A"], enc)
     blocks = nn.ModuleList([cb.SelfAttentionBlock(cfg["d"], cfg["H"], p, cfg["residual_sa"])
                             for _ in range(cfg["n_blocks"])])
-    dec = cb.CrossAttentionBlock(cfg["d"], cfg["H"], p, cfg["residual_ca"]) if cfg["decoder"] == "ca" \
-        else cb.DotProduct()
+    if cfg["decoder"] == "ca":
+        dec = cb.CrossAttentionBlock(cfg["d"], cfg["H"], p, cfg["residual_ca"])
+    elif cfg["decoder"] == "dot":
+        dec = cb.DotProduct()
+    else:
+        dec = cb.WeightedDotProduct(cfg["gamma"], cfg["L"], cfg["decoder"] == "wdot_norm", device)
     model = cb.CARCA(d=cfg["d"], p=p, emb=emb, enc=blocks, dec=dec)
     model.load_state_dict(sd, strict=True)          # state_dict keys/shapes == the reference's
     return model.to(device)
@@ -38,7 +52,8 @@ def _attr_arg(mode, z, model, a_dense, device):
     if mode == "dense":
         return a_dense.to(device)
     table = cb.ItemAttrTable.from_dense(z["attr_table"], sparse=(mode == "csr")).to(device)
-    model.embeds.set_attr_table(table)
+    if hasattr(model.embeds, "set_attr_table"):           # the id-only embeddings take no attributes
+        model.embeds.set_attr_table(table)
     return None
 
 
@@ -110,7 +125,8 @@ def check_train(name, device, mode="dense", gtol=2e-4):
         got = np.zeros_like(ref) if prm.grad is None else prm.grad.cpu().numpy()
         assert got.shape == ref.shape, k
         assert grad_err(got, ref, grad_floor(k)) < gtol, (k, grad_err(got, ref, grad_floor(k)))
-    assert float(model.embeds.items_embed.weight.grad[0].abs().max()) == 0.0   # padding_idx row
+    if hasattr(model.embeds, "items_embed"):
+        assert float(model.embeds.items_embed.weight.grad[0].abs().max()) == 0.0   # padding_idx row
 
 
 def check_train_dropout(name, device, p=0.3, seed=20240607, mode="dense", gtol=3e-4):
@@ -169,6 +185,15 @@ def check_metrics(device):
     loss.backward()
     assert abs(loss.item() - float(z["loss"])) < 1e-5
     np.testing.assert_allclose(yv.grad.cpu().numpy(), z["dy"], rtol=1e-4, atol=1e-8)
+
+
+def check_knn(device):
+    """KNN baseline (src/knn.py:8-21) against the fixture of the real reference."""
+    z = np.load(f"{GOLDEN}/knn_ops.npz")
+    p_a, o1, o2 = (torch.from_numpy(z[k]).to(device) for k in ("p_a", "o_a1", "o_a2"))
+    zero = torch.zeros(1, device=device)
+    y = cb.KNN().forward((zero, p_a, zero), [(zero, o1, zero), (zero, o2, zero)])
+    np.testing.assert_allclose(y.cpu().numpy(), z["y"], rtol=1e-5, atol=1e-6)
 
 
 def check_pickle_and_shapes(device):

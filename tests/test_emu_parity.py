@@ -42,3 +42,21 @@ def test_fused_eval_vs_per_op_kernels(emu_backend, decoder, B, T):
 
 def test_fused_eval_single_user_fixture(emu_backend):
     S.check_eval("single_user_ca", emu_backend, "csr")
+
+
+VARIANTS = [("idemb_dot", "dense"), ("mlpid_ca", "dense"), ("attr_dot", "csr"), ("attrctx_ca", "dense"),
+            ("attrctx_dense_ca", "table"), ("wdot_all", "csr"), ("wdotnorm_all", "dense")]
+
+
+@pytest.mark.parametrize("name,mode", VARIANTS)
+def test_module_variants_eval(emu_backend, name, mode):
+    S.check_eval(name, emu_backend, mode)
+
+
+@pytest.mark.parametrize("name,mode", VARIANTS)
+def test_module_variants_train(emu_backend, name, mode):
+    S.check_train(name, emu_backend, mode)
+
+
+def test_knn(emu_backend):
+    S.check_knn(emu_backend)

@@ -40,6 +40,10 @@ def test_metrics_and_bce_vs_reference_fixture():
     S.check_metrics(DEV)
 
 
+def test_knn_baseline_vs_reference_fixture():
+    S.check_knn(DEV)
+
+
 def test_pickle_roundtrip_and_b1_shape():
     S.check_pickle_and_shapes(DEV)
 
