@@ -250,7 +250,7 @@ def run_ours(args):
 
     with torch.no_grad():
         # ---- value: inputs resident in HBM
-        for i in range(W):
+        for i in range(max(W, args.rotate)):        # every rotated batch is touched once before the clock starts
             step(devb[i % args.rotate])
         launches0 = N.lib().carca_launch_count()
         clocks = ClockSampler(local)

@@ -842,16 +842,17 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
     TRY(check_launch("pack_rows"));
   }
   a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
+  a.chunk_slices = max(1, ceil_div(ceil_div(T, 128), 16));   // <= 16 candidate chunks per work item
   const size_t smem = sizeof(TcSmem);
-  const int n_tiles = ceil_div(B, 2);   // upper bound; the kernel reads the packed tile count from n_bins
+  const long long n_tiles = (long long)ceil_div(B, 2) * a.chunk_slices;   // upper bound on the work items
   if (m->n_heads == 2) {
     auto k = fused_eval_tc_kernel<2>;
     TRY(allow_smem(k, smem));
-    CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+    CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   } else {
     auto k = fused_eval_tc_kernel<4>;
     TRY(allow_smem(k, smem));
-    CARCA_LAUNCH(k, dim3(min(n_tiles, 148)), dim3(TC_THREADS), smem, S(stream), a);
+    CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   }
   return check_launch("fused_eval_tc");
 }

@@ -72,6 +72,8 @@ struct TcArgs {
                                                      //   one row per user, e.g. an expanded view or catalog mode: C, 0)
   const int *row_src, *row_seg;                      // packed profile rows (pack_rows_kernel)
   int* n_bins;                                       // [0] bins written by the packing pass, [1] tile scheduler counter
+  int chunk_slices;                                  // work item = (tile, one of this many slices of the candidate chunks):
+                                                     //   long candidate lists (full catalog) are spread over CTAs
 };
 
 struct TcSmem {
@@ -536,8 +538,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   TcTicks tk;
   tk.out = (a.dbg && a.dbg_stage == -1 && blockIdx.x == 0 && c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;
   tk.n = 0;
-  const int n_tiles = (a.n_bins[0] + 1) / 2;
-  const int n_chunks = (a.T + 127) / 128;
+  const int n_slices = max(1, a.chunk_slices);
+  const int n_tiles = ((a.n_bins[0] + 1) / 2) * n_slices;   // work items: every slice re-encodes its tile (cheap next
+  const int n_chunks = (a.T + 127) / 128;                    // to >= 16 candidate chunks per user) and scores its chunks
+  const int chunks_per_slice = (n_chunks + n_slices - 1) / n_slices;
   const int u = c.row / 64, i = c.row % 64;   // bin (64-row half of the tile) and row within it
   float* const plast = s.k_hi;                // dot decoder: last-position vectors per segment (K is unused there)
   // tiles cost 62K cycles + 7K per user they hold: CTAs take the next tile from a global counter instead of
@@ -548,10 +552,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     __syncthreads();   // every thread is done with the previous tile (and has read s.next_tile)
     if (!first) tile = s.next_tile;
     if (tile >= n_tiles) break;
+    const int c_lo = (tile % n_slices) * chunks_per_slice, c_hi = min(n_chunks, c_lo + chunks_per_slice);
+    const long long trow0 = (long long)(tile / n_slices) * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
-    const int src = a.row_src[(long long)tile * 128 + c.row];
-    const int seg = src >= 0 ? a.row_seg[(long long)tile * 128 + c.row] : 0;
+    const int src = a.row_src[trow0 + c.row];
+    const int seg = src >= 0 ? a.row_seg[trow0 + c.row] : 0;
     const int ru = src >> 8, rp = src & 255;
     const int seg0 = seg & 0xff, seglen = (seg >> 8) & 0xff;
     const int my_pid = src >= 0 ? a.p_x[(long long)ru * L + rp] : 0;
@@ -823,16 +829,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
     };
     if (uctx) user_ctx(s.uuser[0], 0);
-    if (c.half == 1) s.oid[c.row] = cand_id(s.uuser[0], c.row);
+    if (c.half == 1) s.oid[c.row] = cand_id(s.uuser[0], c_lo * 128 + c.row);
     __syncthreads();   // s.oid, K/V/plast stores are visible
-    const int n_iter = n_seg * n_chunks;
+    const int n_iter = n_seg * max(0, c_hi - c_lo);
     int oid = s.oid[c.row];
     __syncthreads();   // s.oid is rewritten at the top of iteration 0
     float e[32], cv[8], twv = 0.f;
-    gather(oid, s.uuser[0], c.row, e, cv, twv);
-    int si = 0, ch = 0, idn = 0;
+    gather(oid, s.uuser[0], c_lo * 128 + c.row, e, cv, twv);
+    int si = 0, ch = c_lo, idn = 0;
     if (c.half == 1 && n_iter > 1) {
-      const int s1 = n_chunks > 1 ? 0 : 1, c1 = n_chunks > 1 ? 1 : 0;
+      const int s1 = c_hi - c_lo > 1 ? 0 : 1, c1 = c_hi - c_lo > 1 ? c_lo + 1 : c_lo;
       idn = cand_id(s.uuser[s1], c1 * 128 + c.row);
     }
 #pragma unroll 1
@@ -842,9 +848,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       const int usr = s.uuser[si], ul = s.ulist[si];
       const int ubin = (ul & 0xff) >> 6, useg0 = ul & 63, ulen = ul >> 8;
       int si1 = si, ch1 = ch + 1;
-      if (ch1 == n_chunks) { ch1 = 0; ++si1; }
+      if (ch1 == c_hi) { ch1 = c_lo; ++si1; }
       int si2 = si1, ch2 = ch1 + 1;
-      if (ch2 == n_chunks) { ch2 = 0; ++si2; }
+      if (ch2 == c_hi) { ch2 = c_lo; ++si2; }
       const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
       // candidate embedding (:426), or its query for `ca`
       if (uctx) embed_finish_user<H>(c, oid, s.cvec[q & 1], e);

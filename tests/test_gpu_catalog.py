@@ -21,16 +21,17 @@ def test_catalog_kernel_variants_agree_at_beauty_width(variant, monkeypatch):
     from carca_replication_b200 import catalog, fused, synth
     from helpers import FP32_RTOL, rel_err
 
-    shape = dataclasses.replace(synth.BEAUTY, n_items=3001, n_attrs=200)
+    shape = dataclasses.replace(synth.BEAUTY, n_items=5001, n_attrs=200)
     model = synth.build_model(shape, "ca", seed=4).to("cuda").eval()
     model.embeds.set_attr_table(synth.make_attr_table(shape, seed=4).to("cuda"))
     b = {k: v.to("cuda") for k, v in synth.make_eval_batch(shape, 5, seed=4).items()}
     prof = (b["p_x"], None, b["p_c"])
     ctx = b["o_c"][:, 0].contiguous()
     monkeypatch.setattr(fused, "VARIANT", variant)
-    y = catalog.score_items(model, prof, ctx, 1000, 2500)
+    # 3500 candidates = 28 chunks of 128: the tensor-core kernel splits them into 2 slices per tile
+    y = catalog.score_items(model, prof, ctx, 1000, 4500)
     model.use_fused_eval = False
-    y_mod = catalog.score_items(model, prof, ctx, 1000, 2500, chunk=700)
+    y_mod = catalog.score_items(model, prof, ctx, 1000, 4500, chunk=700)
     assert rel_err(y.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL
 
 
