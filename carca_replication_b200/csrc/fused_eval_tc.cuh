@@ -85,8 +85,6 @@ struct TcSmem {
   float mct[8][64];                                  // folded context map, [context k][feature]
   float mcqt[8][64];                                 // the same through the decoder's WQ
   float mcw[8];                                      //   and through its ffn weight
-  float cvec[2][64];                                 // per-user context term of the candidates (double-buffered)
-  float cw[4];                                       //   and of the score residual ([2] used; keeps 16-byte alignment)
   alignas(16) float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
   alignas(16) float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
@@ -540,8 +538,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   tk.n = 0;
   const int n_slices = max(1, a.chunk_slices);
   const int n_tiles = ((a.n_bins[0] + 1) / 2) * n_slices;   // work items: every slice re-encodes its tile (cheap next
-  const int n_chunks = (a.T + 127) / 128;                    // to >= 16 candidate chunks per user) and scores its chunks
-  const int chunks_per_slice = (n_chunks + n_slices - 1) / n_slices;
+                                                            // to >= 16 candidate chunks per user) and scores its share
   const int u = c.row / 64, i = c.row % 64;   // bin (64-row half of the tile) and row within it
   float* const plast = s.k_hi;                // dot decoder: last-position vectors per segment (K is unused there)
   // tiles cost 62K cycles + 7K per user they hold: CTAs take the next tile from a global counter instead of
@@ -552,7 +549,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     __syncthreads();   // every thread is done with the previous tile (and has read s.next_tile)
     if (!first) tile = s.next_tile;
     if (tile >= n_tiles) break;
-    const int c_lo = (tile % n_slices) * chunks_per_slice, c_hi = min(n_chunks, c_lo + chunks_per_slice);
     const long long trow0 = (long long)(tile / n_slices) * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
@@ -790,81 +786,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         for (int q = 0; q < N2; ++q) plast[seg_idx * 64 + Own<H>::f0(h, c.half) + q] = v[h * N2 + q];
     }
 
-    // ---- decoder: one [128 candidates x 64 keys of the user's bin] problem per (segment, chunk).
-    // Software pipeline over iterations q: candidate ids of q+2 are loaded into a register, ids of q+1 sit in
-    // s.oid, and the table rows of q+1 are gathered into registers while the MMAs of q run.
-    // cross-attention: the candidate's query comes from the folded table TQ (= WQ e + bq, carca_eval_prepare),
-    // so an iteration is  Q -> TMEM, scores MMA, softmax, PV MMA, <O, wf> + <e, wf> + bf  (src/carca.py:338-347).
+    // ---- decoder.  The candidates of a bin's users form one stream of (segment, candidate) rows; an iteration
+    // takes the next 128 rows of it (T = 101 would otherwise leave 27 of 128 MMA rows idle) against the 64 keys
+    // of the bin, every row masked to its own user's key segment.  Software pipeline over iterations q:
+    // candidate ids of q+2 are loaded into a register, ids of q+1 sit in s.oid, and the table rows of q+1 are
+    // gathered into registers while the MMAs of q run.  cross-attention: the candidate's query comes from the
+    // folded table TQ (= WQ e + bq, carca_eval_prepare), so an iteration is  Q -> TMEM, scores MMA, softmax,
+    // PV MMA, <O, wf> + <e, wf> + bf  (src/carca.py:338-347).
     const bool ca = a.decoder == 1;
     const float* const tab = ca ? a.TQ : a.Tfold;
     const float(*const ctab)[64] = ca ? s.mcqt : s.mct;
-    auto cand_id = [&](int usr, int t) -> int {
-      return t < a.T ? (a.cat_lo > 0 ? a.cat_lo + t : ldg_now_i(a.o_x + (long long)usr * a.T + t)) : 0;
-    };
-    // one context row per user (expanded [B,T,C] view / catalog mode): its map is computed once per iteration
-    // by 65 threads instead of per row
+    // one context row per user (expanded [B,T,C] view / catalog mode): its map through the context table is
+    // computed once per segment into the (now idle) weight ring instead of per candidate row
     const bool uctx = a.oc_tgt == 0;
-    auto gather = [&](int id, int usr, int t, float(&e)[32], float(&cv)[8], float& twv) {
-      embed_load<H>(a, c, id, tab,
-                    uctx ? nullptr : a.o_c + (long long)usr * a.oc_user + (long long)min(t, a.T - 1) * a.oc_tgt, e, cv);
-      if (ca && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
-    };
-    auto user_ctx = [&](int usr, int slot) {
-      const float* cu = a.o_c + (long long)usr * a.oc_user;
-      if (c.tid < 96) {   // warps 0-2 (warp-uniform): 64 feature threads + one thread for the residual weight
-        float cu_[8];
+    float* const cvecs = s.w[0];              // [n_seg][64]
+    float* const cws = s.w[0] + 128 * 64;     // [n_seg]: the same through the decoder's ffn weight
+    const int nb0 = __popc(s.headbits[0]) + __popc(s.headbits[1]);
+    auto seg_base = [&](int bin) { return bin ? nb0 : 0; };            // segments are listed bin by bin
+    auto seg_cnt = [&](int bin) { return bin ? n_seg - nb0 : nb0; };
+    if (uctx) {
+      for (int idx = c.tid; idx < n_seg * 64; idx += TC_THREADS) {
+        const float* cu = a.o_c + (long long)s.uuser[idx >> 6] * a.oc_user;
+        float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cu_[k] = k < a.C ? __ldg(cu + k) : 0.f;   // all loads in flight together
-        if (c.tid < 64) {
-          float v = 0.f;
+        for (int k = 0; k < 8; ++k)
+          if (k < a.C) acc = fmaf(ctab[k][idx & 63], __ldg(cu + k), acc);
+        cvecs[idx] = acc;
+      }
+      if (ca) {
+        for (int sg = c.tid; sg < n_seg; sg += TC_THREADS) {
+          const float* cu = a.o_c + (long long)s.uuser[sg] * a.oc_user;
+          float acc = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v = fmaf(ctab[k][c.tid], cu_[k], v);
-          s.cvec[slot][c.tid] = v;
-        } else if (c.tid == 64 && ca) {
-          float v = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v = fmaf(s.mcw[k], cu_[k], v);
-          s.cw[slot] = v;
+          for (int k = 0; k < 8; ++k)
+            if (k < a.C) acc = fmaf(s.mcw[k], __ldg(cu + k), acc);
+          cws[sg] = acc;
         }
       }
+    }
+    // iterations [it_lo, it_hi) of each bin handled by this work item (all of them unless the tile is sliced)
+    const int n_it_a = (seg_cnt(0) * a.T + 127) / 128, n_it_b = (seg_cnt(1) * a.T + 127) / 128;
+    const int per_a = (n_it_a + n_slices - 1) / n_slices, per_b = (n_it_b + n_slices - 1) / n_slices;
+    const int lo_a = min(n_it_a, (tile % n_slices) * per_a), hi_a = min(n_it_a, lo_a + per_a);
+    const int lo_b = min(n_it_b, (tile % n_slices) * per_b), hi_b = min(n_it_b, lo_b + per_b);
+    const int n_iter = (hi_a - lo_a) + (hi_b - lo_b);
+    // iteration j of this work item -> (bin, iteration within the bin)
+    auto locate = [&](int j, int& bin, int& it) {
+      const int n0 = hi_a - lo_a;
+      bin = j < n0 ? 0 : 1;
+      it = j < n0 ? lo_a + j : lo_b + (j - n0);
     };
-    if (uctx) user_ctx(s.uuser[0], 0);
-    if (c.half == 1) s.oid[c.row] = cand_id(s.uuser[0], c_lo * 128 + c.row);
-    __syncthreads();   // s.oid, K/V/plast stores are visible
-    const int n_iter = n_seg * max(0, c_hi - c_lo);
+    // this thread's row of iteration (bin, it): segment index in the tile, candidate index, validity
+    auto row_of = [&](int bin, int it, int& sg, int& t) -> bool {
+      const int f = it * 128 + c.row;
+      if (f >= seg_cnt(bin) * a.T) {
+        sg = seg_base(bin);
+        t = 0;
+        return false;
+      }
+      const int qn = f / a.T;
+      sg = seg_base(bin) + qn;
+      t = f - qn * a.T;
+      return true;
+    };
+    auto cand_id = [&](bool valid, int sg, int t) -> int {
+      if (!valid) return 0;
+      return a.cat_lo > 0 ? a.cat_lo + t : ldg_now_i(a.o_x + (long long)s.uuser[sg] * a.T + t);
+    };
+    auto gather = [&](int id, int sg, int t, float(&e)[32], float(&cv)[8], float& twv) {
+      embed_load<H>(a, c, id, tab,
+                    uctx ? nullptr : a.o_c + (long long)s.uuser[sg] * a.oc_user + (long long)t * a.oc_tgt, e, cv);
+      if (ca && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
+    };
+    int bin0 = 0, it0 = 0, bin1 = 0, it1 = 0, bin2 = 0, it2 = 0;
+    int sg0 = 0, t0r = 0, sg1 = 0, t1r = 0;
+    bool v0 = false;
+    if (n_iter > 0) {
+      locate(0, bin0, it0);
+      v0 = row_of(bin0, it0, sg0, t0r);
+    }
+    if (c.half == 1) s.oid[c.row] = n_iter > 0 ? cand_id(v0, sg0, t0r) : 0;
+    __syncthreads();   // s.oid, K/V/plast/cvecs stores are visible
     int oid = s.oid[c.row];
     __syncthreads();   // s.oid is rewritten at the top of iteration 0
     float e[32], cv[8], twv = 0.f;
-    gather(oid, s.uuser[0], c_lo * 128 + c.row, e, cv, twv);
-    int si = 0, ch = c_lo, idn = 0;
-    if (c.half == 1 && n_iter > 1) {
-      const int s1 = c_hi - c_lo > 1 ? 0 : 1, c1 = c_hi - c_lo > 1 ? c_lo + 1 : c_lo;
-      idn = cand_id(s.uuser[s1], c1 * 128 + c.row);
+    gather(oid, sg0, t0r, e, cv, twv);
+    int idn = 0;
+    if (n_iter > 1) {
+      locate(1, bin1, it1);
+      const bool v1 = row_of(bin1, it1, sg1, t1r);
+      if (c.half == 1) idn = cand_id(v1, sg1, t1r);
     }
 #pragma unroll 1
     for (int q = 0; q < n_iter; ++q) {
-      const int t0 = ch * 128;
-      const int nq = min(128, a.T - t0);
-      const int usr = s.uuser[si], ul = s.ulist[si];
-      const int ubin = (ul & 0xff) >> 6, useg0 = ul & 63, ulen = ul >> 8;
-      int si1 = si, ch1 = ch + 1;
-      if (ch1 == c_hi) { ch1 = c_lo; ++si1; }
-      int si2 = si1, ch2 = ch1 + 1;
-      if (ch2 == c_hi) { ch2 = c_lo; ++si2; }
       const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
+      const int ubin = bin0;
+      const int usr = s.uuser[sg0], ul = s.ulist[sg0];
+      const int useg0 = ul & 63, ulen = ul >> 8;
       // candidate embedding (:426), or its query for `ca`
-      if (uctx) embed_finish_user<H>(c, oid, s.cvec[q & 1], e);
+      if (uctx) embed_finish_user<H>(c, oid, cvecs + sg0 * 64, e);
       else embed_finish<H>(a, c, oid, ctab, nullptr, e, cv);
       tick(tk, 14);
       float acc = 0.f;
       uint32_t cross_bits = 0;
       int W = 32, kw0 = 0;
       if (ca) {
-        // key window of this segment: the thread pair covers 2W consecutive keys starting at kw0 (multiple of
-        // 8) that contain [useg0, useg0 + ulen); softmax and PV touch only that window
-        const int wl = ((useg0 + ulen + 7) & ~7) - (useg0 & ~7);
+        // key window of the iteration: the thread pair covers 2W consecutive keys starting at kw0 (multiple of 8)
+        // that contain the segments of every user present in these 128 rows; softmax and PV touch only it
+        const int f_first = it0 * 128, f_last = min(f_first + 127, seg_cnt(ubin) * a.T - 1);
+        const int ul_a = s.ulist[seg_base(ubin) + f_first / a.T], ul_b = s.ulist[seg_base(ubin) + f_last / a.T];
+        const int w_lo = (ul_a & 63) & ~7, w_hi = (((ul_b & 63) + (ul_b >> 8)) + 7) & ~7;
+        const int wl = w_hi - w_lo;
         W = wl <= 16 ? 8 : (wl <= 32 ? 16 : 32);
-        kw0 = min(useg0 & ~7, 64 - 2 * W);
+        kw0 = min(w_lo, 64 - 2 * W);
         if (oid != 0) {
           const unsigned long long valid = ((unsigned long long)s.kbits[ubin][1] << 32) | s.kbits[ubin][0];
           const unsigned long long segm = (ulen >= 64 ? ~0ull : ((1ull << ulen) - 1ull)) << useg0;
@@ -873,7 +907,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           if (a.residual_ca && c.half == 0) {   // residual term <o, wf> (:343,:345) from the folded tables
             acc = twv;
             if (uctx) {
-              acc += s.cw[q & 1];
+              acc += cws[sg0];
             } else {
 #pragma unroll
               for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
@@ -885,15 +919,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
-          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], plast[si * 64 + Own<H>::f0(h, c.half) + qq], acc);
+          for (int qq = 0; qq < N2; ++qq) acc = fmaf(e[h * N2 + qq], plast[sg0 * 64 + Own<H>::f0(h, c.half) + qq], acc);
+      }
+      int sg2 = 0, t2r = 0;
+      bool v2 = false;
+      if (has2) {
+        locate(q + 2, bin2, it2);
+        v2 = row_of(bin2, it2, sg2, t2r);
       }
       if (c.half == 1) {   // s.oid <- ids of q+1 (every thread read the ids of q one sync ago); fetch ids of q+2
         s.oid[c.row] = has1 ? idn : 0;
-        if (has2) idn = cand_id(s.uuser[si2], ch2 * 128 + c.row);
+        if (has2) idn = cand_id(v2, sg2, t2r);
       }
       if (ca) publish();
       else __syncthreads();
-      if (!ca && uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);   // visible after this iteration's next CTA sync
+      int oid_next = 0;
       if (ca) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
@@ -910,12 +950,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             }
             c.ncommit++;
           }
-          // next iteration's context map and candidate rows: in flight while this chunk's attention runs (issued
-          // after the MMAs so that the issuing warp does not wait on them first)
-          if (hp == 0 && uctx && has1) user_ctx(s.uuser[si1], (q + 1) & 1);
+          // candidate rows of the next iteration: in flight while this iteration's attention runs (issued after
+          // the MMAs so that the issuing warp does not wait on them first)
           if (hp == 0 && has1) {
-            oid = s.oid[c.row];
-            gather(oid, s.uuser[si1], ch1 * 128 + c.row, e, cv, twv);
+            oid_next = s.oid[c.row];
+            gather(oid_next, sg1, t1r, e, cv, twv);
           }
           wait_mma(c);
           tick(tk, 20);
@@ -966,16 +1005,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       } else {
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
         if (has1) {
-          oid = s.oid[c.row];
-          gather(oid, s.uuser[si1], ch1 * 128 + c.row, e, cv, twv);
+          oid_next = s.oid[c.row];
+          gather(oid_next, sg1, t1r, e, cv, twv);
         }
         __syncthreads();   // s.oid is rewritten at the top of the next iteration
       }
-      if (c.half == 0 && c.row < nq)
-        a.y[(long long)usr * a.ldy + a.col0 + t0 + c.row] = 1.0f / (1.0f + expf(-acc));
+      if (c.half == 0 && v0) a.y[(long long)usr * a.ldy + a.col0 + t0r] = 1.0f / (1.0f + expf(-acc));
       tick(tk, 23);
-      si = si1;
-      ch = ch1;
+      // shift the pipeline: (q+1) becomes current, (q+2) becomes next
+      if (has1) v0 = row_of(bin1, it1, sg0, t0r);
+      bin0 = bin1; it0 = it1;
+      bin1 = bin2; it1 = it2;
+      sg1 = sg2; t1r = t2r;
+      oid = oid_next;
     }
     tk.out = nullptr;   // first tile only
   }
