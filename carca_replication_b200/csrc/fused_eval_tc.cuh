@@ -499,12 +499,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   const float sc = 1.4426950408889634f / sqrtf((float)DH);
   // MMAs are issued by one elected lane of warp 0; the branch on the warp index is warp-uniform so
   // descriptors stay in uniform registers (a divergent `tid == 0` branch costs a waterfall loop per MMA)
-  const bool issuer_warp = __shfl_sync(kFull, w, 0) == 0;
+  // Two issuers (warps 0 and 1): independent accumulators of a phase (the two heads of a pair, Q and K, ...)
+  // are issued concurrently — small MMAs are bound by the ~70-cycle issue path of one thread, not by the
+  // tensor pipe.  Both issuers commit in every phase, so every mbarrier phase takes two arrivals.
+  const int wu = __shfl_sync(kFull, w, 0);
+  const int iw = wu < 2 ? wu : -1;
 
   if (w == 0) umma::tmem_alloc(&s.tmem_slot, 512);
   if (c.tid == 0) {
-    umma::mbar_init(&s.bar[0], 1);
-    umma::mbar_init(&s.bar[1], 1);
+    umma::mbar_init(&s.bar[0], 2);
+    umma::mbar_init(&s.bar[1], 2);
   }
   for (int i = c.tid; i < 64 * 8; i += TC_THREADS) s.mct[i % 8][i / 8] = a.Mc[i];
   for (int i = c.tid; i < (4 * a.n_blocks + 2) * 64; i += TC_THREADS) {
@@ -602,17 +606,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 2);
       dump_regs<H>(a, c, dbg_row, 1 + 10 * b, ru, rp, v);
       // Q from LN1(x), K from raw x (:238-239), separate completion events
-      if (issuer_warp) {
+      if (iw >= 0) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
-          commit(c, 0);
-          issue_proj(tmem0, C_ACCK, C_XHI, C_XLO, s.w[1]);
-          commit(c, 1);
+          if (iw == 0) issue_proj(tmem0, C_ACCQ, C_QNHI, C_QNLO, s.w[0]);
+          else issue_proj(tmem0, C_ACCK, C_XHI, C_XLO, s.w[1]);
+          commit(c);
         }
-        c.ncommit += 2;
       }
-      wait_mma(c);                                              // Q done: slot 0 is free
+      c.ncommit++;
+      wait_mma(c);                                              // Q and K done: both weight slots are free
       weight_prefetch(c, 0, wb.wv);
+      weight_prefetch(c, 1, wb.w1);
       {   // tf32 remainder of Q (the A operand of the score products) -> QN_LO
         float q[32];
         ld_feat<H>(c, C_ACCQ, q);
@@ -621,19 +625,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         st_feat<H>(c, C_QNLO, q);
       }
       tick(tk, 3);
-      wait_mma(c);                                              // K done: slot 1 is free
-      weight_prefetch(c, 1, wb.w1);
       store_k_operand<H>(c, C_ACCK);
       weight_wait<1>();                                         // WV landed (W1 may still be in flight)
       publish();
       tick(tk, 4);
-      if (issuer_warp) {
+      if (iw >= 0) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);      // V (:240)
+          if (iw == 0) issue_proj(tmem0, C_ACCV, C_XHI, C_XLO, s.w[0]);      // V (:240)
           commit(c);
         }
-        c.ncommit++;
       }
+      c.ncommit++;
       wait_mma(c);
       tick(tk, 5);
       dump_tmem<H>(a, c, dbg_row, 2 + 10 * b, ru, rp, C_ACCQ);
@@ -650,19 +652,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       // ---- causal self-attention (:299), two heads per round; v accumulates qn + O (:302)
 #pragma unroll
       for (int hp = 0; hp < H; hp += 2) {
-        if (issuer_warp) {
+        if (iw >= 0) {   // one head per issuer
           if (umma::elect_one()) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int h = hp + e;
-              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u;
-              issue_3x<128, DH / 8>(tmem0 + (e ? C_ACCK : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
-                                    umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
-            }
+            const int e = iw, h = hp + e;
+            const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u;
+            issue_3x<128, DH / 8>(tmem0 + (e ? C_ACCK : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                                  umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
             commit(c);
           }
-          c.ncommit++;
         }
+        c.ncommit++;
         wait_mma(c);
         tick(tk, 20);
         {
@@ -671,20 +670,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
         publish();
         tick(tk, 21);
-        if (issuer_warp) {   // O_h = P_h V_h for both bins' V at once (each row keeps its own bin's columns)
+        if (iw >= 0) {   // O_h = P_h V_h for both bins' V at once (each row keeps its own bin's columns)
           if (umma::elect_one()) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int h = hp + e;
-              const uint32_t p = tmem0 + (e ? C_ACCK : C_XHI);
-              const uint32_t voff = (uint32_t)(h * 2 * DH) * 16u;
-              issue_3x<2 * DH, 8>(tmem0 + C_QNHI + e * 2 * DH, p, p + 64, umma::smem_u32(s.v_hi) + voff,
-                                  umma::smem_u32(s.v_lo) + voff, (uint32_t)TC_VLBO);
-            }
+            const int e = iw, h = hp + e;
+            const uint32_t p = tmem0 + (e ? C_ACCK : C_XHI);
+            const uint32_t voff = (uint32_t)(h * 2 * DH) * 16u;
+            issue_3x<2 * DH, 8>(tmem0 + C_QNHI + e * 2 * DH, p, p + 64, umma::smem_u32(s.v_hi) + voff,
+                                umma::smem_u32(s.v_lo) + voff, (uint32_t)TC_VLBO);
             commit(c);
           }
-          c.ncommit++;
         }
+        c.ncommit++;
         wait_mma(c);
         tick(tk, 22);
         {
@@ -713,13 +709,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<0>();
       publish();
       tick(tk, 7);
-      if (issuer_warp) {
+      if (iw >= 0) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);     // ffn_1 (:307)
+          if (iw == 0) issue_proj(tmem0, C_ACCQ, C_XHI, C_XLO, s.w[1]);     // ffn_1 (:307)
           commit(c);
         }
-        c.ncommit++;
       }
+      c.ncommit++;
       wait_mma(c);
       tick(tk, 8);
       {
@@ -731,13 +727,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
       publish();
       tick(tk, 9);
-      if (issuer_warp) {
+      if (iw >= 0) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);   // ffn_2 (:311)
+          if (iw == 0) issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);   // ffn_2 (:311)
           commit(c);
         }
-        c.ncommit++;
       }
+      c.ncommit++;
       wait_mma(c);
       tick(tk, 10);
       // next weights: the following block's WQ/WK, or the decoder's WK/WV
@@ -765,14 +761,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       weight_wait<0>();
       publish();
       tick(tk, 12);
-      if (issuer_warp) {
+      if (iw >= 0) {
         if (umma::elect_one()) {
-          issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
-          issue_proj(tmem0, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
+          if (iw == 0) issue_proj(tmem0, C_ACCK, C_QNHI, C_QNLO, s.w[0]);
+          else issue_proj(tmem0, C_ACCV, C_QNHI, C_QNLO, s.w[1]);
           commit(c);
         }
-        c.ncommit++;
       }
+      c.ncommit++;
     }
     if (a.decoder == 1) {
       wait_mma(c);
@@ -931,31 +927,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         s.oid[c.row] = has1 ? idn : 0;
         if (has2) idn = cand_id(v2, sg2, t2r);
       }
+      tick(tk, 30);
       if (ca) publish();
       else __syncthreads();
+      tick(tk, 31);
       int oid_next = 0;
       if (ca) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
-          if (issuer_warp) {
+          if (iw >= 0) {   // one head per issuer
             if (umma::elect_one()) {
-#pragma unroll
-              for (int ee = 0; ee < 2; ++ee) {
-                const int h = hp + ee;
-                const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)ubin * 64u * 16u;
-                issue_3x<64, DH / 8>(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
-                                     umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
-              }
+              const int ee = iw, h = hp + ee;
+              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)ubin * 64u * 16u;
+              issue_3x<64, DH / 8>(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
+                                   umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
               commit(c);
             }
-            c.ncommit++;
           }
+          c.ncommit++;
           // candidate rows of the next iteration: in flight while this iteration's attention runs (issued after
           // the MMAs so that the issuing warp does not wait on them first)
           if (hp == 0 && has1) {
             oid_next = s.oid[c.row];
             gather(oid_next, sg1, t1r, e, cv, twv);
           }
+          tick(tk, 32);
           wait_mma(c);
           tick(tk, 20);
           {
@@ -966,11 +962,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           }
           publish();
           tick(tk, 21);
-          if (issuer_warp) {
+          if (iw >= 0) {
             if (umma::elect_one()) {
-#pragma unroll
-              for (int ee = 0; ee < 2; ++ee) {
-                const int h = hp + ee;
+              {
+                const int ee = iw, h = hp + ee;
                 // keys kw0 .. kw0 + 2W of the bin: P columns from kw0, V key chunks from kw0 / 4
                 const uint32_t voff = (uint32_t)(h * 2 * DH + ubin * DH) * 16u + (uint32_t)(kw0 / 4) * (uint32_t)TC_VLBO;
                 const uint32_t d = tmem0 + C_QNHI + h * DH;
@@ -982,8 +977,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
               }
               commit(c);
             }
-            c.ncommit++;
           }
+          c.ncommit++;
           wait_mma(c);
           tick(tk, 22);
         }
