@@ -29,21 +29,41 @@ def _newest_source_mtime():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library if it is missing or older than a source.  Safe under `torchrun` (several ranks calling
+    it at once): one process builds under a file lock into temporary names and renames into place."""
+    import fcntl
+    import tempfile
+
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
-        objs.append(obj)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC",
-           "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
-    subprocess.run(cmd, check=True)
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+                return LIB                     # another rank built it while this one waited
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = tempfile.mkdtemp(prefix="carca_build_", dir=CSRC)
+            try:
+                objs = []
+                for src in SOURCES:
+                    obj = os.path.join(tmp, src.replace(".cu", ".o"))
+                    cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+                    if verbose:
+                        cmd.insert(1, "-Xptxas=-v")
+                        print(" ".join(cmd), flush=True)
+                    subprocess.run(cmd, check=True)
+                    objs.append(obj)
+                out = os.path.join(tmp, "libcarca_b200.so")
+                cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs, "-Xcompiler",
+                       "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+                subprocess.run(cmd, check=True)
+                os.replace(out, LIB)
+            finally:
+                import shutil
+
+                shutil.rmtree(tmp, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
