@@ -377,11 +377,60 @@ class CARCA(Model):
         # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin
         return fused.fits_packed(profile[0])
 
+    use_fused_train = True  # class default; set False on an instance to force the per-op training path
+
+    def _fused_train_applies(self, profile, targets) -> bool:
+        """Train mode, d == 64, L <= 64, stock blocks / decoder, 1-2 target tuples of L positions each: the
+        fused training core (csrc/fused_train.cuh) handles dropout -> blocks -> LayerNorm -> decoder."""
+        if not (self.training and self.use_fused_train) or not 1 <= len(targets) <= 2:
+            return False
+        L = profile[0].shape[1]
+        if self.norm.weight.shape[0] != 64 or L > 64 or profile[0].dim() != 2:
+            return False
+        blocks = list(self.encoder)
+        if len(blocks) > 8 or not all(type(b) is SelfAttentionBlock for b in blocks):
+            return False
+        heads = {b.attn.H for b in blocks}
+        resid = {bool(b.residual) for b in blocks}
+        drops = {float(b.dropout1.p) for b in blocks} | {float(b.attn.dropout.p) for b in blocks} | {float(self.dropout.p)}
+        dec = self.decoder
+        if type(dec) is CrossAttentionBlock:
+            heads.add(dec.attn.H)
+            drops.add(float(dec.attn.dropout.p))
+        elif type(dec) is not DotProduct:
+            return False
+        if len(heads) > 1 or len(resid) > 1 or len(drops) != 1 or (heads and next(iter(heads)) not in (1, 2, 4)):
+            return False
+        return all(t[0].dim() == 2 and t[0].shape[1] == L for t in targets)
+
+    def _forward_fused_train(self, profile, targets) -> Tensor:
+        p_x, p_a, p_c = profile
+        with ops.forward_seed():
+            p_mask = get_mask(p_x)
+            p_e = self.embeds.forward(p_x, p_a, p_c, p_mask, False)
+            o_es = [self.embeds.forward(o_x, o_a, o_c, get_mask(o_x), True) for (o_x, o_a, o_c) in targets]
+            blocks = list(self.encoder)
+            dec = self.decoder
+            is_ca = type(dec) is CrossAttentionBlock
+            H = blocks[0].attn.H if blocks else (dec.attn.H if is_ca else 1)
+            params = [t for b in blocks for t in b._params()] + [self.norm.weight, self.norm.bias]
+            if is_ca:
+                a = dec.attn
+                params += [a.WQ.weight, a.WQ.bias, a.WK.weight, a.WK.bias, a.WV.weight, a.WV.bias, dec.ffn.weight,
+                           dec.ffn.bias]
+            cfg = (H, len(blocks), 1 if is_ca else 0, bool(blocks[0].residual) if blocks else True,
+                   bool(dec.residual) if is_ca else True, float(self.dropout.p), ops.current_seed())
+            o_e1 = o_es[1] if len(o_es) > 1 else None
+            o_x1 = targets[1][0] if len(targets) > 1 else None
+            return ops.TrainCoreFn.apply(p_e, o_es[0], o_e1, p_x, targets[0][0], o_x1, cfg, *params)
+
     def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:
         if self._fused_eval_applies(profile, targets):
             from . import fused
             return fused.forward(self, profile, targets)
+        if self._fused_train_applies(profile, targets):
+            return self._forward_fused_train(profile, targets)
         with ops.forward_seed():
             p_e, p_mask = self.encode(profile)
             y_preds = []

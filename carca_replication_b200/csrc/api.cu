@@ -11,6 +11,7 @@
 #include "embed.cuh"
 #include "fused_eval.cuh"
 #include "fused_eval_tc.cuh"
+#include "fused_train.cuh"
 #include "gemm.cuh"
 #include "layernorm.cuh"
 #include "score.cuh"
@@ -598,6 +599,96 @@ int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* gr, c
   TRY(linear_dx(d_p, dK, w->wk, B * Lp, d, d, d, st, 1));
   TRY(linear_dx(d_p, dV, w->wv, B * Lp, d, d, d, st, 1));
   return 0;
+}
+
+// ------------------------------------------------------------------------------------ fused training core
+namespace {
+int train_args(TrainArgs& a, const carca_train_core* c) {
+  CARCA_REQUIRE(c != nullptr, "train_core: null descriptor");
+  if (c->L > TR || c->L < 1) return fail(-4, "train_core: L=%d outside [1, %d]", c->L, TR);
+  if (!(c->n_heads == 1 || c->n_heads == 2 || c->n_heads == 4))
+    return fail(-4, "train_core: n_heads=%d not in {1, 2, 4}", c->n_heads);
+  if (c->n_blocks < 0 || c->n_blocks > TMAXB) return fail(-4, "train_core: n_blocks=%d > %d", c->n_blocks, TMAXB);
+  if (c->n_tuples < 1 || c->n_tuples > TMAXT) return fail(-4, "train_core: %d target tuples (1 or 2)", c->n_tuples);
+  CARCA_REQUIRE(c->decoder_kind == 0 || c->decoder_kind == 1, "train_core: unknown decoder kind %d", c->decoder_kind);
+  CARCA_REQUIRE(c->p_drop >= 0.f && c->p_drop < 1.f, "train_core: p=%f outside [0,1)", c->p_drop);
+  CARCA_REQUIRE(c->rows && c->saved && c->p_x && c->p_e, "train_core: missing workspace or inputs");
+  memset(&a, 0, sizeof(a));
+  a.B = c->B; a.L = c->L; a.H = c->n_heads; a.n_blocks = c->n_blocks; a.n_tuples = c->n_tuples;
+  a.decoder = c->decoder_kind; a.residual_sa = c->residual_sa; a.residual_ca = c->residual_ca;
+  a.drop = drop_cfg(c->p_drop, c->seed, 0u);
+  a.p_x = c->p_x; a.p_e = c->p_e;
+  for (int t = 0; t < c->n_tuples; ++t) {
+    CARCA_REQUIRE(c->o_x[t] && c->o_e[t], "train_core: target tuple %d missing", t);
+    a.o_x[t] = c->o_x[t];
+    a.o_e[t] = c->o_e[t];
+  }
+  a.n_bins = c->rows;
+  a.row_src = c->rows + 4;
+  a.row_info = a.row_src + (long long)c->B * TR;
+  a.sv = c->saved;
+  a.sv_stride = (long long)c->B * TR * TD;
+  static_assert(sizeof(TrainBlockW) == sizeof(carca_block_params), "block parameter structs must match");
+  static_assert(sizeof(TrainCrossW) == sizeof(carca_cross_params), "decoder parameter structs must match");
+  for (int b = 0; b < c->n_blocks; ++b) memcpy(&a.blk[b], &c->blocks[b], sizeof(TrainBlockW));
+  a.fn_g = c->norm_g; a.fn_b = c->norm_b;
+  memcpy(&a.dec, &c->cross, sizeof(TrainCrossW));
+  return 0;
+}
+int train_grid(int B) { return B < 148 ? (B < 1 ? 1 : B) : 148; }
+}  // namespace
+
+int64_t carca_train_core_rows_ints(int B) { return 4 + 2 * (int64_t)B * TR; }
+int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples) {
+  return (int64_t)sv_count(n_blocks, n_tuples) * B * TR * TD;
+}
+
+int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void* stream) {
+  cudaStream_t st = S(stream);
+  TrainArgs a;
+  TRY(train_args(a, c));
+  if (a.B <= 0) return 0;
+  a.y = y;
+  a.ldy = ldy;
+  cudaMemsetAsync(a.n_bins, 0, 4 * sizeof(int), st);
+  cudaMemsetAsync(a.row_src, 0xFF, sizeof(int) * (size_t)a.B * TR, st);
+  {
+    auto k = train_pack_kernel;
+    CARCA_LAUNCH(k, dim3(ceil_div(a.B, 128)), dim3(128), 0, st, a);
+    TRY(check_launch("train_pack"));
+  }
+  auto k = fused_train_fwd_kernel;
+  const size_t smem = fused_train_smem();
+  TRY(allow_smem(k, smem));
+  CARCA_LAUNCH(k, dim3(train_grid(a.B)), dim3(TTHREADS), smem, st, a);
+  return check_launch("fused_train_fwd");
+}
+
+int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_block_grads* g_blocks, float* g_norm_g,
+                         float* g_norm_b, const carca_cross_grads* g_cross, const float* dy, int64_t ldy,
+                         const carca_train_core* c, void* stream) {
+  cudaStream_t st = S(stream);
+  TrainArgs a;
+  TRY(train_args(a, c));
+  if (a.B <= 0) return 0;
+  CARCA_REQUIRE(d_pe && d_oe0 && (c->n_tuples < 2 || d_oe1) && dy, "train_core_bwd: missing gradient buffers");
+  CARCA_REQUIRE(g_norm_g && g_norm_b && (c->n_blocks == 0 || g_blocks), "train_core_bwd: missing parameter gradients");
+  a.dy = dy;
+  a.ldy = ldy;
+  a.d_pe = d_pe;
+  a.d_oe[0] = d_oe0;
+  a.d_oe[1] = d_oe1;
+  for (int b = 0; b < c->n_blocks; ++b) memcpy(&a.gblk[b], &g_blocks[b], sizeof(TrainBlockG));
+  a.g_fn_g = g_norm_g; a.g_fn_b = g_norm_b;
+  if (c->decoder_kind == 1) {
+    CARCA_REQUIRE(g_cross != nullptr, "train_core_bwd: decoder gradients missing");
+    memcpy(&a.gdec, g_cross, sizeof(TrainCrossG));
+  }
+  auto k = fused_train_bwd_kernel;
+  const size_t smem = fused_train_smem();
+  TRY(allow_smem(k, smem));
+  CARCA_LAUNCH(k, dim3(train_grid(a.B)), dim3(TTHREADS), smem, st, a);
+  return check_launch("fused_train_bwd");
 }
 
 // ------------------------------------------------------------------------------------ loss / metrics

@@ -1,0 +1,1031 @@
+// Fused TRAINING core of CARCA for d = 64, L <= 64 (the Beauty configuration): everything between the
+// embeddings and the probabilities, forward and backward, in two kernels
+//   forward : dropout(p_e) -> n_blocks x SelfAttentionBlock -> final LayerNorm -> decoder -> y
+//   backward: dy -> d p_e, d o_e, every parameter gradient of the blocks / final norm / decoder
+// Reference path replaced: CARCA.forward in train mode, src/carca.py:416-431, with
+// SelfAttentionBlock :297-318, MultiHeadAttention :228-265, CrossAttentionBlock :338-349 (causal -1),
+// DotProduct :358-360, and autograd's backward of all of them (src/train.py:95).
+//
+// Why: at the reference batch size the per-op path is ~250 launches of microsecond kernels over
+// [B*L, 64] tensors that are mostly LEFT PADDING (src/data.py:112-113; Beauty: ~8 of 50 positions).
+// A padded position reaches no loss term: it is masked as a key (:246-251), its target rows carry a
+// zero loss mask (src/train.py:92), so its weight-gradient contribution is exactly zero.  The kernels
+// therefore run on ACTIVE positions only (profile id != 0 or a target id != 0), packed user after
+// user into 64-row bins (train_pack_kernel); a CTA owns a bin and keeps its activations in shared
+// memory as row-major [64][68] fp32 tiles.  Row r of a bin is the same (user, position) for the
+// profile and for every target tuple, so the decoder's causal rule "target i sees profile keys j < i"
+// is "row sees earlier rows of its own segment".
+//
+// All products are fp32 FFMA thread-tiled GEMMs on shared-memory operands (exactly the reference's
+// arithmetic type; no tf32 rounding in gradients):
+//   gemm_nt  C[r][n] = sum_k A[r][k] W[n][k]      projections (weights as stored, [out][in])
+//   gemm_nn  C[r][c] = sum_k A[r][k] B[k][c]      input gradients, P.V, dS.K
+//   gemm_tn  C[n][c] = sum_r A[r][n] X[r][c]      weight gradients (atomics into the grad tensors), dK, dV
+// The forward stores six [rows, 64] activations per block (+ K, V, s of the decoder) for the backward;
+// LayerNorm outputs, Q of the decoder and every dropout mask (Philox, same element indexing as the
+// per-op kernels, so both paths draw identical masks) are recomputed.
+#pragma once
+#include "common.cuh"
+
+namespace carca {
+
+constexpr int TR = 64;            // rows per bin
+constexpr int TD = 64;            // model width
+constexpr int TLD = 68;           // row stride of a tile in shared memory (floats)
+constexpr int TBUF = TR * TLD;    // floats per tile
+constexpr int TTHREADS = 256;
+constexpr int TWARPS = TTHREADS / 32;
+constexpr int TMAXB = 8;          // encoder blocks
+constexpr int TMAXT = 2;          // target tuples (positives | negatives, src/train.py:86-88)
+constexpr int TNBUF = 10;
+
+struct TrainBlockW { const float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2; };
+struct TrainBlockG { float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2; };
+struct TrainCrossW { const float *wq, *bq, *wk, *bk, *wv, *bv, *wf, *bf; };
+struct TrainCrossG { float *wq, *bq, *wk, *bk, *wv, *bv, *wf, *bf; };
+
+// row_info bits
+constexpr int TI_PVALID = 1 << 16;
+constexpr int TI_TVALID0 = 1 << 17;   // tuple t: TI_TVALID0 << t
+
+struct TrainArgs {
+  int B, L, H, n_blocks, n_tuples, decoder;   // decoder: 0 dot-product, 1 cross-attention
+  int residual_sa, residual_ca;
+  DropCfg drop;                               // p / seed / device seed word; the site is set per use
+  const int* p_x;                             // [B, L]
+  const int* o_x[TMAXT];                      // [B, L] each
+  const float* p_e;                           // [B, L, 64] embedded profile (masked, before dropout)
+  const float* o_e[TMAXT];                    // [B, L, 64] embedded targets (masked)
+  float* y;                                   // [B, ldy]; tuple t at columns t*L
+  long long ldy;
+  int* row_src;                               // [B*64] bin row -> u*L + i, or -1
+  int* row_info;                              // [B*64] seg start | seg last << 8 | validity bits
+  int* n_bins;                                // [1]
+  float* sv;                                  // saved activations: tensor k at sv + k*sv_stride, [B*64, 64]
+  long long sv_stride;
+  TrainBlockW blk[TMAXB];
+  const float *fn_g, *fn_b;
+  TrainCrossW dec;
+  // backward only
+  const float* dy;                            // [B, ldy]
+  float* d_pe;                                // [B, L, 64] zero-initialised by the caller
+  float* d_oe[TMAXT];
+  TrainBlockG gblk[TMAXB];
+  float *g_fn_g, *g_fn_b;
+  TrainCrossG gdec;
+};
+
+// saved-tensor slots
+__host__ __device__ __forceinline__ int sv_block(int b, int k) { return 6 * b + k; }     // k: 0 x, 1 Q, 2 K, 3 V, 4 s, 5 a1
+__host__ __device__ __forceinline__ int sv_final(int nb) { return 6 * nb; }              // last block's output
+__host__ __device__ __forceinline__ int sv_dec(int nb, int k) { return 6 * nb + 1 + k; } // 0 K, 1 V, 2 + t: s of tuple t
+__host__ __device__ __forceinline__ int sv_count(int nb, int nt) { return 6 * nb + 3 + nt; }
+
+struct TrainSmem {
+  float buf[TNBUF][TBUF];
+  float w[TBUF];                   // weight staging, [n][k] with row stride TLD
+  float red[TWARPS][2][TD];        // per-warp partial sums of vector gradients
+  float gsc[TR];                   // per-row scalars
+  int src[TR], info[TR], pos[TR], usr[TR];
+  int n, npad;
+};
+
+// -------------------------------------------------------------------------------------------------- packing
+// One CTA per 128 users: counts each user's active positions, packs users greedily into 64-row bins,
+// writes the row maps, and fills y of every INACTIVE position with the value the reference computes
+// there (sigmoid(ffn bias) for the cross-attention decoder: s = 0; 0.5 for the dot product).
+__global__ void __launch_bounds__(128) train_pack_kernel(const TrainArgs a) {
+  __shared__ int cnt[128], bin_of[128], start_of[128], base;
+  const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
+  const int L = a.L;
+  int n = 0;
+  if (usr < a.B) {
+    const float ydef = a.decoder == 1 ? 1.0f / (1.0f + expf(-a.dec.bf[0])) : 0.5f;
+    for (int j = 0; j < L; ++j) {
+      bool act = a.p_x[(long long)usr * L + j] != 0;
+      for (int q = 0; q < a.n_tuples; ++q) act = act || a.o_x[q][(long long)usr * L + j] != 0;
+      n += act ? 1 : 0;
+      if (!act)
+        for (int q = 0; q < a.n_tuples; ++q) a.y[(long long)usr * a.ldy + q * L + j] = ydef;
+    }
+  }
+  cnt[t] = n;
+  __syncthreads();
+  if (t == 0) {
+    int bin = 0, fill = 0;
+    const int users = min(128, a.B - (int)blockIdx.x * 128);
+    for (int q = 0; q < users; ++q) {
+      if (fill + cnt[q] > TR) {
+        ++bin;
+        fill = 0;
+      }
+      bin_of[q] = bin;
+      start_of[q] = fill;
+      fill += cnt[q];
+    }
+    base = atomicAdd(a.n_bins, bin + 1);
+  }
+  __syncthreads();
+  if (usr < a.B && n > 0) {
+    const long long o = (long long)(base + bin_of[t]) * TR;
+    int r = start_of[t];
+    const int seg = start_of[t] | ((start_of[t] + n - 1) << 8);
+    for (int j = 0; j < L; ++j) {
+      int flags = a.p_x[(long long)usr * L + j] != 0 ? TI_PVALID : 0;
+      for (int q = 0; q < a.n_tuples; ++q)
+        if (a.o_x[q][(long long)usr * L + j] != 0) flags |= TI_TVALID0 << q;
+      if (flags) {
+        a.row_src[o + r] = usr * L + j;
+        a.row_info[o + r] = seg | flags;
+        ++r;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- tiles
+// Thread (ty, tx) = (tid / 16, tid % 16).
+
+// C[r][n] = sum_k A[r][k] W[n][k], K % 4 == 0; thread owns rows 4ty..4ty+3 and the strided columns
+// tx, tx+16, tx+32, tx+48 (< NCOLS), so the 128-bit loads of W rows are bank-conflict free.
+// `need(j)` lets attention skip columns outside the rows' key range.
+template <int NCOLS, class Need, class Epi>
+__device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                        int K, int nrows, Need need, Epi epi) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  constexpr int NJ = NCOLS / 16;
+  if (ty * 4 < nrows) {
+    float acc[4][NJ];
+    bool on[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      on[j] = need(ty * 4, tx + 16 * j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][j] = 0.f;
+    }
+    const float* ap = A + (ty * 4) * lda;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+      float4 av[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(ap + i * lda + k);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (on[j]) {
+          const float4 b = *reinterpret_cast<const float4*>(W + (tx + 16 * j) * ldw + k);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][j] = fmaf(av[i].x, b.x, acc[i][j]);
+            acc[i][j] = fmaf(av[i].y, b.y, acc[i][j]);
+            acc[i][j] = fmaf(av[i].z, b.z, acc[i][j]);
+            acc[i][j] = fmaf(av[i].w, b.w, acc[i][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      if (on[j]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) epi(ty * 4 + i, tx + 16 * j, acc[i][j]);
+      }
+  }
+}
+
+struct NeedAll {
+  __device__ __forceinline__ bool operator()(int, int) const { return true; }
+};
+
+// C[r][c] = sum_{k in [klo, khi)} A[r][k] B[k][c] for c < NC (NC in {16, 32, 64}); thread owns RT = NC/16
+// rows and 4 contiguous columns.  range(r0, r1, klo, khi) gives the reduction range of rows r0..r1
+// (multiples of 4 are not required).
+template <int NC, class Range, class Epi>
+__device__ __forceinline__ void gemm_nn(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                        int nrows, Range range, Epi epi) {
+  constexpr int CG = NC / 4, RT = NC / 16;
+  const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
+  const int r0 = ty * RT;
+  if (r0 < nrows) {
+    int klo, khi;
+    range(r0, r0 + RT - 1, klo, khi);
+    float acc[RT][4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k = klo; k < khi; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(Bm + k * ldb + tx * 4);
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        const float av = A[(r0 + i) * lda + k];
+        acc[i][0] = fmaf(av, b.x, acc[i][0]);
+        acc[i][1] = fmaf(av, b.y, acc[i][1]);
+        acc[i][2] = fmaf(av, b.z, acc[i][2]);
+        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RT; ++i) epi(r0 + i, tx * 4, acc[i]);
+  }
+}
+
+// C[n][c] = sum_{r in [rlo, rhi)} A[r][n] X[r][c] for n < 64, c < NC; thread owns RT = NC/16 values of n and 4
+// contiguous columns.  range(n0, n1, rlo, rhi) gives the reduction range for output rows n0..n1.
+template <int NC, class Range, class Epi>
+__device__ __forceinline__ void gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ X, int ldx,
+                                        Range range, Epi epi) {
+  constexpr int CG = NC / 4, RT = NC / 16;
+  const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
+  const int n0 = ty * RT;
+  int rlo, rhi;
+  range(n0, n0 + RT - 1, rlo, rhi);
+  float acc[RT][4];
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int r = rlo; r < rhi; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + tx * 4);
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const float av = A[r * lda + n0 + i];
+      acc[i][0] = fmaf(av, x.x, acc[i][0]);
+      acc[i][1] = fmaf(av, x.y, acc[i][1]);
+      acc[i][2] = fmaf(av, x.z, acc[i][2]);
+      acc[i][3] = fmaf(av, x.w, acc[i][3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RT; ++i) epi(n0 + i, tx * 4, acc[i]);
+}
+
+// -------------------------------------------------------------------------------------------------- helpers
+// four keep-scales of the aligned flat elements 4q .. 4q+3 of a site's tensor (one Philox call)
+__device__ __forceinline__ void drop4(const DropCfg& c, unsigned long long q, float (&f)[4]) {
+  if (c.p <= 0.f) {
+    f[0] = f[1] = f[2] = f[3] = 1.0f;
+    return;
+  }
+  unsigned k0 = c.seed_lo, k1 = c.seed_hi;
+  if (c.seed_dev) {
+    const unsigned long long x = *c.seed_dev;
+    k0 ^= (unsigned)x;
+    k1 ^= (unsigned)(x >> 32);
+  }
+  const Philox4 r = philox4x32_10((unsigned)q, (unsigned)(q >> 32), c.site, 0u, k0, k1);
+  const unsigned wds[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float u = (float)(wds[i] >> 8) * 5.9604644775390625e-08f;
+    f[i] = u >= c.p ? c.scale : 0.0f;
+  }
+}
+
+__device__ __forceinline__ DropCfg at_site(DropCfg c, unsigned site) {
+  c.site = site;
+  return c;
+}
+
+// loads the 64 x 64 weight matrix Wg (row-major, as stored) into s.w with row stride TLD
+__device__ __forceinline__ void load_w(TrainSmem& s, const float* __restrict__ Wg) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = threadIdx.x + i * TTHREADS;   // float4 index, 16 per row
+    const int n = e >> 4, k4 = e & 15;
+    *reinterpret_cast<float4*>(s.w + n * TLD + k4 * 4) = *reinterpret_cast<const float4*>(Wg + n * TD + k4 * 4);
+  }
+}
+
+// tile <-> saved activation [bin*64 + r][64]
+__device__ __forceinline__ void save_tile(const TrainArgs& a, const TrainSmem& s, int slot, int bin, const float* tile) {
+  float* g = a.sv + slot * a.sv_stride + (long long)bin * TR * TD;
+  for (int e = threadIdx.x; e < s.n * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    *reinterpret_cast<float4*>(g + r * TD + c4 * 4) = *reinterpret_cast<const float4*>(tile + r * TLD + c4 * 4);
+  }
+}
+__device__ __forceinline__ void load_tile(const TrainArgs& a, const TrainSmem& s, int slot, int bin, float* tile) {
+  const float* g = a.sv + slot * a.sv_stride + (long long)bin * TR * TD;
+  for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < s.n) v = *reinterpret_cast<const float4*>(g + r * TD + c4 * 4);
+    *reinterpret_cast<float4*>(tile + r * TLD + c4 * 4) = v;
+  }
+}
+
+// rows of a [B, L, 64] tensor -> tile (zeros below the bin's fill), optional dropout of site `site`
+__device__ __forceinline__ void gather_rows(const TrainSmem& s, const float* __restrict__ src, float* tile,
+                                            const DropCfg* drop) {
+  for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < s.n) {
+      v = *reinterpret_cast<const float4*>(src + (long long)s.src[r] * TD + c4 * 4);
+      if (drop) {
+        float f[4];
+        drop4(*drop, (unsigned long long)s.src[r] * 16 + c4, f);
+        v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+      }
+    }
+    *reinterpret_cast<float4*>(tile + r * TLD + c4 * 4) = v;
+  }
+}
+// tile rows -> rows of a [B, L, 64] tensor (only the bin's rows), optional dropout factor (the backward of it)
+__device__ __forceinline__ void scatter_rows(const TrainSmem& s, float* __restrict__ dst, const float* tile,
+                                             const DropCfg* drop) {
+  for (int e = threadIdx.x; e < s.n * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    float4 v = *reinterpret_cast<const float4*>(tile + r * TLD + c4 * 4);
+    if (drop) {
+      float f[4];
+      drop4(*drop, (unsigned long long)s.src[r] * 16 + c4, f);
+      v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+    }
+    *reinterpret_cast<float4*>(dst + (long long)s.src[r] * TD + c4 * 4) = v;
+  }
+}
+
+// in-place elementwise pass over a tile: fn(r, c4, float4&) for r < rows
+template <class F>
+__device__ __forceinline__ void tile_pass(float* tile, int rows, F fn) {
+  for (int e = threadIdx.x; e < rows * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    float4 v = *reinterpret_cast<float4*>(tile + r * TLD + c4 * 4);
+    fn(r, c4, v);
+    *reinterpret_cast<float4*>(tile + r * TLD + c4 * 4) = v;
+  }
+}
+
+// LayerNorm of the bin's rows, warp per row (same arithmetic as layernorm_fwd_kernel)
+__device__ __forceinline__ void ln_rows(float* out, const float* in, int rows, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const float g0 = gamma[lane], g1 = gamma[lane + 32], b0 = beta[lane], b1 = beta[lane + 32];
+  for (int r = w; r < rows; r += TWARPS) {
+    const float x0 = in[r * TLD + lane], x1 = in[r * TLD + lane + 32];
+    const float mean = warp_sum(x0 + x1) / (float)TD;
+    const float c0 = x0 - mean, c1 = x1 - mean;
+    const float rstd = 1.0f / sqrtf(warp_sum(fmaf(c0, c0, c1 * c1)) / (float)TD + kLnEps);
+    out[r * TLD + lane] = c0 * rstd * g0 + b0;
+    out[r * TLD + lane + 32] = c1 * rstd * g1 + b1;
+  }
+}
+
+// LayerNorm backward over the bin's rows: dx (=|+=) ..., dgamma/dbeta accumulated with atomics.
+// dy and x are tiles; dx may alias dy.
+__device__ __forceinline__ void ln_bwd_rows(TrainSmem& s, float* dx, const float* dy, const float* x, int rows,
+                                            const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, bool accumulate) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const float g0 = gamma[lane], g1 = gamma[lane + 32];
+  float ag0 = 0.f, ag1 = 0.f, ab0 = 0.f, ab1 = 0.f;
+  for (int r = w; r < rows; r += TWARPS) {
+    const float x0 = x[r * TLD + lane], x1 = x[r * TLD + lane + 32];
+    const float mean = warp_sum(x0 + x1) / (float)TD;
+    const float c0 = x0 - mean, c1 = x1 - mean;
+    const float rstd = 1.0f / sqrtf(warp_sum(fmaf(c0, c0, c1 * c1)) / (float)TD + kLnEps);
+    const float h0 = c0 * rstd, h1 = c1 * rstd;
+    const float d0 = dy[r * TLD + lane], d1 = dy[r * TLD + lane + 32];
+    const float e0 = d0 * g0, e1 = d1 * g1;
+    const float m1 = warp_sum(e0 + e1) / (float)TD;
+    const float m2 = warp_sum(fmaf(e0, h0, e1 * h1)) / (float)TD;
+    ag0 = fmaf(d0, h0, ag0); ag1 = fmaf(d1, h1, ag1);
+    ab0 += d0; ab1 += d1;
+    const float v0 = rstd * (e0 - m1 - h0 * m2), v1 = rstd * (e1 - m1 - h1 * m2);
+    dx[r * TLD + lane] = accumulate ? dx[r * TLD + lane] + v0 : v0;
+    dx[r * TLD + lane + 32] = accumulate ? dx[r * TLD + lane + 32] + v1 : v1;
+  }
+  s.red[w][0][lane] = ag0; s.red[w][0][lane + 32] = ag1;
+  s.red[w][1][lane] = ab0; s.red[w][1][lane + 32] = ab1;
+  __syncthreads();
+  if (threadIdx.x < 2 * TD) {
+    const int which = threadIdx.x / TD, c = threadIdx.x % TD;
+    float acc = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < TWARPS; ++ww) acc += s.red[ww][which][c];
+    atomicAdd((which == 0 ? dgamma : dbeta) + c, acc);
+  }
+  __syncthreads();
+}
+
+// db[c] += sum_r tile[r][c]
+__device__ __forceinline__ void colsum_tile(TrainSmem& s, const float* tile, int rows, float* __restrict__ db) {
+  const int c = threadIdx.x % TD, part = threadIdx.x / TD;   // 4 row slices
+  float acc = 0.f;
+  for (int r = part; r < rows; r += TTHREADS / TD) acc += tile[r * TLD + c];
+  s.red[part][0][c] = acc;
+  __syncthreads();
+  if (threadIdx.x < TD) atomicAdd(db + c, s.red[0][0][c] + s.red[1][0][c] + s.red[2][0][c] + s.red[3][0][c]);
+  __syncthreads();
+}
+
+// dW[n][k] += sum_r dY[r][n] X[r][k]  (atomics into the gradient tensor), db[n] += colsum(dY)
+__device__ __forceinline__ void weight_grad(TrainSmem& s, const float* dY, const float* X, int rows,
+                                            float* __restrict__ dW, float* __restrict__ db) {
+  gemm_tn<TD>(dY, TLD, X, TLD,
+              [&](int, int, int& lo, int& hi) { lo = 0; hi = rows; },
+              [&](int n, int c, const float (&v)[4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(dW + n * TD + c + j, v[j]);
+              });
+  if (db) colsum_tile(s, dY, rows, db);
+}
+
+struct AttnCfg {
+  int H, dh;
+  float sqrt_dh;
+  bool cross;        // false: self (keys j <= i), true: decoder in training (keys j < i)
+  int qbit;          // info bit that validates a query row
+  int L;
+  DropCfg drop;
+};
+
+// rows' key range: keys of the segment up to the row itself
+__device__ __forceinline__ void key_range(const TrainSmem& s, int r0, int r1, int& lo, int& hi) {
+  lo = s.info[r0] & 0x7f;
+  hi = min(r1 + 1, s.n);
+  if (r0 >= s.n) { lo = 0; hi = 0; }
+}
+// keys' query range: from the key itself to the last row of its segment
+__device__ __forceinline__ void query_range(const TrainSmem& s, int j0, int j1, int& lo, int& hi) {
+  lo = j0;
+  hi = j1 < s.n ? ((s.info[j1] >> 8) & 0x7f) + 1 : s.n;
+  if (j0 >= s.n) { lo = 0; hi = 0; }
+}
+
+__device__ __forceinline__ bool attn_need(const TrainSmem& s, int r0, int j) {
+  // rows r0..r0+3: any of them may attend key j?
+  if (r0 >= s.n || j >= s.n) return false;
+  const int r1 = min(r0 + 3, s.n - 1);
+  return j <= r1 && j >= (s.info[r0] & 0x7f);
+}
+
+// softmax of row i of S (tile, logits before scaling) restricted to the allowed keys; returns p for the
+// lane's two keys (lane, lane + 32) and the keep-scales of the attention dropout
+__device__ __forceinline__ void softmax_row(const TrainSmem& s, const AttnCfg& c, const float* S, int i, int h, int lane,
+                                            float (&p)[2], float (&f)[2]) {
+  const int info = s.info[i];
+  const int seg0 = info & 0x7f;
+  const bool qv = (info & c.qbit) != 0;
+  const int jmax = c.cross ? i - 1 : i;
+  float sc[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j = lane + 32 * q;
+    const bool ok = qv && j >= seg0 && j <= jmax && (s.info[j] & TI_PVALID);
+    sc[q] = ok ? S[i * TLD + j] / c.sqrt_dh : -INFINITY;
+    mx = fmaxf(mx, sc[q]);
+  }
+  mx = warp_max(mx);
+  float e[2], sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    e[q] = sc[q] == -INFINITY ? 0.f : expf(sc[q] - mx);
+    sum += e[q];
+  }
+  sum = warp_sum(sum);
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j = lane + 32 * q;
+    p[q] = e[q] * inv;
+    f[q] = 1.0f;
+    if (p[q] != 0.f && c.drop.p > 0.f) {
+      const unsigned long long elem =
+          (((unsigned long long)s.usr[i] * c.H + h) * c.L + s.pos[i]) * c.L + s.pos[j];
+      f[q] = drop_factor(c.drop, elem);
+    }
+  }
+}
+
+// out[:, head columns] (=|+=) dropout(softmax(mask(Q K^T))) V for every head.  Sb: scratch tile.
+__device__ __forceinline__ void attention_fwd_tile(TrainSmem& s, const AttnCfg& c, float* out, const float* Q,
+                                                   const float* K, const float* V, float* Sb, bool accumulate) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  for (int h = 0; h < c.H; ++h) {
+    const int hc = h * c.dh;
+    gemm_nt<TR>(Q + hc, TLD, K + hc, TLD, c.dh, s.npad, [&](int r0, int j) { return attn_need(s, r0, j); },
+                [&](int r, int j, float v) { Sb[r * TLD + j] = v; });
+    __syncthreads();
+    for (int i = w; i < s.npad; i += TWARPS) {
+      float p[2], f[2];
+      softmax_row(s, c, Sb, i, h, lane, p, f);
+      Sb[i * TLD + lane] = p[0] * f[0];
+      Sb[i * TLD + lane + 32] = p[1] * f[1];
+    }
+    __syncthreads();
+    auto range = [&](int r0, int r1, int& lo, int& hi) { key_range(s, r0, r1, lo, hi); };
+    auto epi = [&](int r, int cc, const float (&v)[4]) {
+      float4* o = reinterpret_cast<float4*>(out + r * TLD + hc + cc);
+      float4 t = accumulate ? *o : make_float4(0.f, 0.f, 0.f, 0.f);
+      t.x += v[0]; t.y += v[1]; t.z += v[2]; t.w += v[3];
+      *o = t;
+    };
+    if (c.dh == 64) gemm_nn<64>(Sb, TLD, V + hc, TLD, s.npad, range, epi);
+    else if (c.dh == 32) gemm_nn<32>(Sb, TLD, V + hc, TLD, s.npad, range, epi);
+    else gemm_nn<16>(Sb, TLD, V + hc, TLD, s.npad, range, epi);
+    __syncthreads();
+  }
+}
+
+// Backward of attention_fwd_tile.  dQ is overwritten (head columns), dK / dV are accumulated when
+// `acc_kv`, else overwritten.  Sb, Db: two scratch tiles.
+__device__ __forceinline__ void attention_bwd_tile(TrainSmem& s, const AttnCfg& c, float* dQ, float* dK, float* dV,
+                                                   const float* dO, const float* Q, const float* K, const float* V,
+                                                   float* Sb, float* Db, bool acc_kv) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  for (int h = 0; h < c.H; ++h) {
+    const int hc = h * c.dh;
+    auto need = [&](int r0, int j) { return attn_need(s, r0, j); };
+    gemm_nt<TR>(Q + hc, TLD, K + hc, TLD, c.dh, s.npad, need, [&](int r, int j, float v) { Sb[r * TLD + j] = v; });
+    gemm_nt<TR>(dO + hc, TLD, V + hc, TLD, c.dh, s.npad, need, [&](int r, int j, float v) { Db[r * TLD + j] = v; });
+    __syncthreads();
+    for (int i = w; i < TR; i += TWARPS) {
+      float p[2] = {0.f, 0.f}, f[2] = {1.f, 1.f};
+      if (i < s.npad) softmax_row(s, c, Sb, i, h, lane, p, f);
+      float dp[2];
+      float D = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        dp[q] = p[q] != 0.f ? Db[i * TLD + lane + 32 * q] * f[q] : 0.f;
+        D = fmaf(p[q], dp[q], D);
+      }
+      D = warp_sum(D);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        Db[i * TLD + lane + 32 * q] = p[q] * (dp[q] - D) / c.sqrt_dh;   // d(Q K^T)
+        Sb[i * TLD + lane + 32 * q] = p[q] * f[q];                      // dropout(W)
+      }
+    }
+    __syncthreads();
+    auto krange = [&](int r0, int r1, int& lo, int& hi) { key_range(s, r0, r1, lo, hi); };
+    auto qrange = [&](int j0, int j1, int& lo, int& hi) { query_range(s, j0, j1, lo, hi); };
+    auto set_q = [&](int r, int cc, const float (&v)[4]) {
+      *reinterpret_cast<float4*>(dQ + r * TLD + hc + cc) = make_float4(v[0], v[1], v[2], v[3]);
+    };
+    auto put = [&](float* dst) {
+      return [=](int j, int cc, const float (&v)[4]) {
+        float4* o = reinterpret_cast<float4*>(dst + j * TLD + hc + cc);
+        float4 t = acc_kv ? *o : make_float4(0.f, 0.f, 0.f, 0.f);
+        t.x += v[0]; t.y += v[1]; t.z += v[2]; t.w += v[3];
+        *o = t;
+      };
+    };
+    if (c.dh == 64) {
+      gemm_nn<64>(Db, TLD, K + hc, TLD, TR, krange, set_q);
+      gemm_tn<64>(Db, TLD, Q + hc, TLD, qrange, put(dK));
+      gemm_tn<64>(Sb, TLD, dO + hc, TLD, qrange, put(dV));
+    } else if (c.dh == 32) {
+      gemm_nn<32>(Db, TLD, K + hc, TLD, TR, krange, set_q);
+      gemm_tn<32>(Db, TLD, Q + hc, TLD, qrange, put(dK));
+      gemm_tn<32>(Sb, TLD, dO + hc, TLD, qrange, put(dV));
+    } else {
+      gemm_nn<16>(Db, TLD, K + hc, TLD, TR, krange, set_q);
+      gemm_tn<16>(Db, TLD, Q + hc, TLD, qrange, put(dK));
+      gemm_tn<16>(Sb, TLD, dO + hc, TLD, qrange, put(dV));
+    }
+    __syncthreads();
+  }
+}
+
+// Y = X W^T + b into a tile (all 64 columns)
+__device__ __forceinline__ void project(TrainSmem& s, float* Y, const float* X, const float* __restrict__ Wg,
+                                        const float* __restrict__ bias) {
+  load_w(s, Wg);
+  __syncthreads();
+  gemm_nt<TD>(X, TLD, s.w, TLD, TD, s.npad, NeedAll(),
+              [&](int r, int n, float v) { Y[r * TLD + n] = v + bias[n]; });
+  __syncthreads();
+}
+
+// dX (=|+=) dY W into a tile
+__device__ __forceinline__ void project_bwd(TrainSmem& s, float* dX, const float* dY, const float* __restrict__ Wg,
+                                            bool accumulate) {
+  load_w(s, Wg);
+  __syncthreads();
+  gemm_nn<TD>(dY, TLD, s.w, TLD, s.npad,
+              [&](int, int, int& lo, int& hi) { lo = 0; hi = TD; },
+              [&](int r, int cc, const float (&v)[4]) {
+                float4* o = reinterpret_cast<float4*>(dX + r * TLD + cc);
+                float4 t = accumulate ? *o : make_float4(0.f, 0.f, 0.f, 0.f);
+                t.x += v[0]; t.y += v[1]; t.z += v[2]; t.w += v[3];
+                *o = t;
+              });
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_bin(const TrainArgs& a, TrainSmem& s, int bin) {
+  __syncthreads();
+  if (threadIdx.x < TR) {
+    const int r = threadIdx.x;
+    const int src = a.row_src[(long long)bin * TR + r];
+    s.src[r] = src;
+    s.info[r] = src >= 0 ? a.row_info[(long long)bin * TR + r] : 0;
+    s.pos[r] = src >= 0 ? src % a.L : 0;
+    s.usr[r] = src >= 0 ? src / a.L : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    while (n < TR && s.src[n] >= 0) ++n;
+    s.n = n;
+    s.npad = (n + 3) & ~3;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ AttnCfg self_cfg(const TrainArgs& a, int b) {
+  AttnCfg c;
+  c.H = a.H;
+  c.dh = TD / a.H;
+  c.sqrt_dh = sqrtf((float)c.dh);
+  c.cross = false;
+  c.qbit = TI_PVALID;
+  c.L = a.L;
+  c.drop = at_site(a.drop, 1u + 3u * (unsigned)b);
+  return c;
+}
+__device__ __forceinline__ AttnCfg cross_cfg(const TrainArgs& a, int t) {
+  AttnCfg c = self_cfg(a, 0);
+  c.cross = true;
+  c.qbit = TI_TVALID0 << t;
+  c.drop = at_site(a.drop, 1000u + (unsigned)t);
+  return c;
+}
+
+// y = sigmoid(<s_row, wf> + bf) for the bin's rows (warp per row); also usable to recompute y in the backward
+__device__ __forceinline__ float row_dot(const float* a, const float* __restrict__ b, int lane) {
+  return warp_sum(fmaf(a[lane], b[lane], a[lane + 32] * b[lane + 32]));
+}
+
+// -------------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const TrainArgs a) {
+  CARCA_DYN_SMEM(unsigned char, raw);
+  TrainSmem& s = *reinterpret_cast<TrainSmem*>(raw);
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  float* X = s.buf[0];
+  float* QN = s.buf[1];
+  float* Qb = s.buf[2];
+  float* Kb = s.buf[3];
+  float* Vb = s.buf[4];
+  float* Sb = s.buf[5];
+  for (int e = threadIdx.x; e < 6 * TBUF; e += TTHREADS) s.buf[0][e] = 0.f;
+  const int nbins = *a.n_bins;
+  for (int bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+    load_bin(a, s, bin);
+    const int n = s.n;
+    {  // x0 = dropout(p_e)   (src/carca.py:416, site 0)
+      const DropCfg d0 = at_site(a.drop, 0u);
+      gather_rows(s, a.p_e, X, a.drop.p > 0.f ? &d0 : nullptr);
+    }
+    __syncthreads();
+    for (int b = 0; b < a.n_blocks; ++b) {
+      const TrainBlockW& wb = a.blk[b];
+      save_tile(a, s, sv_block(b, 0), bin, X);
+      ln_rows(QN, X, n, wb.ln1_g, wb.ln1_b);                          // :298
+      __syncthreads();
+      project(s, Qb, QN, wb.wq, wb.bq);                               // :238 (query = LN1(x))
+      project(s, Kb, X, wb.wk, wb.bk);                                // :239 (key = raw x)
+      project(s, Vb, X, wb.wv, wb.bv);                                // :240
+      save_tile(a, s, sv_block(b, 1), bin, Qb);
+      save_tile(a, s, sv_block(b, 2), bin, Kb);
+      save_tile(a, s, sv_block(b, 3), bin, Vb);
+      // s = MHA(..., causal=0) (+ LN1(x)), in place over QN (:299-302)
+      attention_fwd_tile(s, self_cfg(a, b), QN, Qb, Kb, Vb, Sb, a.residual_sa != 0);
+      save_tile(a, s, sv_block(b, 4), bin, QN);
+      ln_rows(Qb, QN, n, wb.ln2_g, wb.ln2_b);                         // s2 (:304)
+      __syncthreads();
+      // a1 = dropout(LeakyReLU(ffn_1(s2)))  (:307-309, site 2 + 3b)
+      project(s, Kb, Qb, wb.w1, wb.b1);
+      {
+        const DropCfg d1 = at_site(a.drop, 2u + 3u * (unsigned)b);
+        tile_pass(Kb, n, [&](int r, int c4, float4& v) {
+          float f[4];
+          drop4(d1, (unsigned long long)s.src[r] * 16 + c4, f);
+          v.x = (v.x > 0.f ? v.x : kLeakySlope * v.x) * f[0];
+          v.y = (v.y > 0.f ? v.y : kLeakySlope * v.y) * f[1];
+          v.z = (v.z > 0.f ? v.z : kLeakySlope * v.z) * f[2];
+          v.w = (v.w > 0.f ? v.w : kLeakySlope * v.w) * f[3];
+        });
+      }
+      __syncthreads();
+      save_tile(a, s, sv_block(b, 5), bin, Kb);
+      // x' = dropout(ffn_2(a1)) (+ s2)  (:311-316, site 3 + 3b)
+      project(s, X, Kb, wb.w2, wb.b2);
+      {
+        const DropCfg d2 = at_site(a.drop, 3u + 3u * (unsigned)b);
+        const bool res = a.residual_sa != 0;
+        tile_pass(X, n, [&](int r, int c4, float4& v) {
+          float f[4];
+          drop4(d2, (unsigned long long)s.src[r] * 16 + c4, f);
+          const float4 q = *reinterpret_cast<const float4*>(Qb + r * TLD + c4 * 4);
+          v.x = v.x * f[0] + (res ? q.x : 0.f);
+          v.y = v.y * f[1] + (res ? q.y : 0.f);
+          v.z = v.z * f[2] + (res ? q.z : 0.f);
+          v.w = v.w * f[3] + (res ? q.w : 0.f);
+        });
+      }
+      __syncthreads();
+    }
+    save_tile(a, s, sv_final(a.n_blocks), bin, X);
+    float* PE = QN;
+    ln_rows(PE, X, n, a.fn_g, a.fn_b);                                // :421
+    __syncthreads();
+    if (a.decoder == 1) {
+      project(s, Kb, PE, a.dec.wk, a.dec.bk);
+      project(s, Vb, PE, a.dec.wv, a.dec.bv);
+      save_tile(a, s, sv_dec(a.n_blocks, 0), bin, Kb);
+      save_tile(a, s, sv_dec(a.n_blocks, 1), bin, Vb);
+    }
+    for (int t = 0; t < a.n_tuples; ++t) {
+      float* O = X;
+      gather_rows(s, a.o_e[t], O, nullptr);                           // :426 (embedded by the caller)
+      __syncthreads();
+      if (a.decoder == 1) {
+        project(s, Qb, O, a.dec.wq, a.dec.bq);
+        if (!a.residual_ca) {
+          for (int e = threadIdx.x; e < TBUF; e += TTHREADS) O[e] = 0.f;
+          __syncthreads();
+        }
+        attention_fwd_tile(s, cross_cfg(a, t), O, Qb, Kb, Vb, Sb, true);   // :339-343 (causal -1)
+        save_tile(a, s, sv_dec(a.n_blocks, 2 + t), bin, O);
+        const float bf = a.dec.bf[0];
+        for (int r = w; r < n; r += TWARPS) {                         // :345-347
+          const float z = row_dot(O + r * TLD, a.dec.wf, lane) + bf;
+          if (lane == 0)
+            a.y[(long long)s.usr[r] * a.ldy + t * a.L + s.pos[r]] = 1.0f / (1.0f + expf(-z));
+        }
+      } else {
+        for (int r = w; r < n; r += TWARPS) {                         // :360
+          const float z = row_dot(O + r * TLD, PE + r * TLD, lane);
+          if (lane == 0)
+            a.y[(long long)s.usr[r] * a.ldy + t * a.L + s.pos[r]] = 1.0f / (1.0f + expf(-z));
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- backward
+__global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const TrainArgs a) {
+  CARCA_DYN_SMEM(unsigned char, raw);
+  TrainSmem& s = *reinterpret_cast<TrainSmem*>(raw);
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  float* B0 = s.buf[0];
+  float* B1 = s.buf[1];
+  float* B2 = s.buf[2];
+  float* B3 = s.buf[3];
+  float* B4 = s.buf[4];
+  float* B5 = s.buf[5];
+  float* B6 = s.buf[6];
+  float* B7 = s.buf[7];
+  float* Sb = s.buf[8];
+  float* Db = s.buf[9];
+  for (int e = threadIdx.x; e < TNBUF * TBUF; e += TTHREADS) s.buf[0][e] = 0.f;
+  const int nbins = *a.n_bins;
+  const int nb = a.n_blocks;
+
+  // d(ffn bias) of the cross-attention decoder from INACTIVE positions (y = sigmoid(bf) there); zero in the
+  // reference loop (the loss mask kills dy), kept for exactness with any upstream gradient
+  if (a.decoder == 1) {
+    const float y0 = 1.0f / (1.0f + expf(-a.dec.bf[0]));
+    float acc = 0.f;
+    const long long total = (long long)a.B * a.L;
+    for (long long e = (long long)blockIdx.x * TTHREADS + threadIdx.x; e < total; e += (long long)gridDim.x * TTHREADS) {
+      bool act = a.p_x[e] != 0;
+      for (int q = 0; q < a.n_tuples; ++q) act = act || a.o_x[q][e] != 0;
+      if (!act) {
+        const long long u = e / a.L, i = e % a.L;
+        for (int q = 0; q < a.n_tuples; ++q) acc += a.dy[u * a.ldy + q * a.L + i];
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && acc != 0.f) atomicAdd(a.gdec.bf, acc * y0 * (1.0f - y0));
+  }
+
+  for (int bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+    load_bin(a, s, bin);
+    const int n = s.n;
+    float* DX = B0;   // gradient w.r.t. the output of the stage being processed
+
+    // ---------------- decoder
+    if (a.decoder == 1) {
+      float* Kd = B3;
+      float* Vd = B4;
+      float* dKd = B5;
+      float* dVd = B6;
+      load_tile(a, s, sv_dec(nb, 0), bin, Kd);
+      load_tile(a, s, sv_dec(nb, 1), bin, Vd);
+      for (int t = 0; t < a.n_tuples; ++t) {
+        float* St = B0;
+        float* DS = B1;
+        load_tile(a, s, sv_dec(nb, 2 + t), bin, St);
+        __syncthreads();
+        // g = dy * y (1 - y); d wf += g s; d bf += g; ds = g wf   (:345-347)
+        const float bf = a.dec.bf[0];
+        float awf0 = 0.f, awf1 = 0.f, abf = 0.f;
+        for (int r = w; r < TR; r += TWARPS) {
+          float g = 0.f;
+          if (r < n) {
+            const float z = row_dot(St + r * TLD, a.dec.wf, lane) + bf;
+            const float yv = 1.0f / (1.0f + expf(-z));
+            g = a.dy[(long long)s.usr[r] * a.ldy + t * a.L + s.pos[r]] * yv * (1.0f - yv);
+            awf0 = fmaf(g, St[r * TLD + lane], awf0);
+            awf1 = fmaf(g, St[r * TLD + lane + 32], awf1);
+            abf += g;
+          }
+          DS[r * TLD + lane] = g * a.dec.wf[lane];
+          DS[r * TLD + lane + 32] = g * a.dec.wf[lane + 32];
+        }
+        s.red[w][0][lane] = awf0; s.red[w][0][lane + 32] = awf1;
+        if (lane == 0) s.red[w][1][0] = abf;
+        __syncthreads();
+        if (threadIdx.x < TD) {
+          float acc = 0.f;
+          for (int ww = 0; ww < TWARPS; ++ww) acc += s.red[ww][0][threadIdx.x];
+          atomicAdd(a.gdec.wf + threadIdx.x, acc);
+        } else if (threadIdx.x == TD) {
+          float acc = 0.f;
+          for (int ww = 0; ww < TWARPS; ++ww) acc += s.red[ww][1][0];
+          atomicAdd(a.gdec.bf, acc);
+        }
+        __syncthreads();
+        // recompute Q of the targets
+        float* O = B0;
+        float* Qt = B2;
+        float* dQ = B7;
+        gather_rows(s, a.o_e[t], O, nullptr);
+        __syncthreads();
+        project(s, Qt, O, a.dec.wq, a.dec.bq);
+        attention_bwd_tile(s, cross_cfg(a, t), dQ, dKd, dVd, DS, Qt, Kd, Vd, Sb, Db, t > 0);
+        weight_grad(s, dQ, O, n, a.gdec.wq, a.gdec.bq);
+        __syncthreads();
+        // d o = dQ WQ (+ ds through the residual) -> d_oe rows
+        if (a.residual_ca) project_bwd(s, DS, dQ, a.dec.wq, true);
+        else project_bwd(s, DS, dQ, a.dec.wq, false);
+        scatter_rows(s, a.d_oe[t], DS, nullptr);
+        __syncthreads();
+      }
+      // keys / values: PE = LN_f(x_nb) recomputed
+      float* XF = B1;
+      float* PE = B2;
+      load_tile(a, s, sv_final(nb), bin, XF);
+      __syncthreads();
+      ln_rows(PE, XF, n, a.fn_g, a.fn_b);
+      __syncthreads();
+      weight_grad(s, dKd, PE, n, a.gdec.wk, a.gdec.bk);
+      weight_grad(s, dVd, PE, n, a.gdec.wv, a.gdec.bv);
+      float* DPE = B7;
+      project_bwd(s, DPE, dKd, a.dec.wk, false);
+      project_bwd(s, DPE, dVd, a.dec.wv, true);
+      // final LayerNorm backward -> DX
+      ln_bwd_rows(s, DX, DPE, XF, n, a.fn_g, a.g_fn_g, a.g_fn_b, false);
+    } else {
+      // dot product (:360): y = sigmoid(<pe_r, o_r>); d pe_r = sum_t g o_r; d o_r = g pe_r
+      float* XF = B1;
+      float* PE = B2;
+      float* DPE = B7;
+      load_tile(a, s, sv_final(nb), bin, XF);
+      __syncthreads();
+      ln_rows(PE, XF, n, a.fn_g, a.fn_b);
+      for (int e = threadIdx.x; e < TBUF; e += TTHREADS) DPE[e] = 0.f;
+      __syncthreads();
+      for (int t = 0; t < a.n_tuples; ++t) {
+        float* O = B3;
+        gather_rows(s, a.o_e[t], O, nullptr);
+        __syncthreads();
+        for (int r = w; r < n; r += TWARPS) {
+          const float z = row_dot(O + r * TLD, PE + r * TLD, lane);
+          const float yv = 1.0f / (1.0f + expf(-z));
+          const float g = a.dy[(long long)s.usr[r] * a.ldy + t * a.L + s.pos[r]] * yv * (1.0f - yv);
+          const float o0 = O[r * TLD + lane], o1 = O[r * TLD + lane + 32];
+          DPE[r * TLD + lane] = fmaf(g, o0, DPE[r * TLD + lane]);
+          DPE[r * TLD + lane + 32] = fmaf(g, o1, DPE[r * TLD + lane + 32]);
+          O[r * TLD + lane] = g * PE[r * TLD + lane];
+          O[r * TLD + lane + 32] = g * PE[r * TLD + lane + 32];
+        }
+        __syncthreads();
+        scatter_rows(s, a.d_oe[t], O, nullptr);
+        __syncthreads();
+      }
+      ln_bwd_rows(s, DX, DPE, XF, n, a.fn_g, a.g_fn_g, a.g_fn_b, false);
+    }
+
+    // ---------------- encoder blocks, last to first.  DX (B0) = d(block output)
+    for (int b = nb - 1; b >= 0; --b) {
+      const TrainBlockW& wb = a.blk[b];
+      const TrainBlockG& gb = a.gblk[b];
+      const bool res = a.residual_sa != 0;
+      // FFN (:305-316)
+      float* DF2 = B1;   // d ffn_2 output = dout * dropout2
+      {
+        const DropCfg d2 = at_site(a.drop, 3u + 3u * (unsigned)b);
+        for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {
+          const int r = e >> 4, c4 = e & 15;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < n) {
+            v = *reinterpret_cast<const float4*>(DX + r * TLD + c4 * 4);
+            float f[4];
+            drop4(d2, (unsigned long long)s.src[r] * 16 + c4, f);
+            v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+          }
+          *reinterpret_cast<float4*>(DF2 + r * TLD + c4 * 4) = v;
+        }
+      }
+      float* A1 = B2;
+      load_tile(a, s, sv_block(b, 5), bin, A1);
+      __syncthreads();
+      weight_grad(s, DF2, A1, n, gb.w2, gb.b2);
+      float* DF1 = B3;
+      project_bwd(s, DF1, DF2, wb.w2, false);                         // d a1
+      {
+        const DropCfg d1 = at_site(a.drop, 2u + 3u * (unsigned)b);
+        tile_pass(DF1, n, [&](int r, int c4, float4& v) {             // through dropout1 and LeakyReLU
+          float f[4];
+          drop4(d1, (unsigned long long)s.src[r] * 16 + c4, f);
+          const float4 q = *reinterpret_cast<const float4*>(A1 + r * TLD + c4 * 4);
+          v.x *= f[0] * (q.x > 0.f ? 1.0f : kLeakySlope);
+          v.y *= f[1] * (q.y > 0.f ? 1.0f : kLeakySlope);
+          v.z *= f[2] * (q.z > 0.f ? 1.0f : kLeakySlope);
+          v.w *= f[3] * (q.w > 0.f ? 1.0f : kLeakySlope);
+        });
+      }
+      __syncthreads();
+      // s2 = LN2(s) recomputed
+      float* Sx = B4;    // s (LN2 input)
+      float* S2 = B2;    // over A1 (no longer needed)
+      load_tile(a, s, sv_block(b, 4), bin, Sx);
+      __syncthreads();
+      ln_rows(S2, Sx, n, wb.ln2_g, wb.ln2_b);
+      __syncthreads();
+      weight_grad(s, DF1, S2, n, gb.w1, gb.b1);
+      float* DS2 = B1;   // over DF2
+      project_bwd(s, DS2, DF1, wb.w1, false);
+      if (res) {
+        tile_pass(DS2, n, [&](int r, int c4, float4& v) {
+          const float4 q = *reinterpret_cast<const float4*>(DX + r * TLD + c4 * 4);
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        });
+        __syncthreads();
+      }
+      // LN2 backward -> d s (B0)
+      float* DSx = B0;
+      ln_bwd_rows(s, DSx, DS2, Sx, n, wb.ln2_g, gb.ln2_g, gb.ln2_b, false);
+      // attention backward
+      float* Qb = B1;
+      float* Kb = B2;
+      float* Vb = B3;
+      float* dQ = B4;
+      float* dK = B5;
+      float* dV = B6;
+      load_tile(a, s, sv_block(b, 1), bin, Qb);
+      load_tile(a, s, sv_block(b, 2), bin, Kb);
+      load_tile(a, s, sv_block(b, 3), bin, Vb);
+      __syncthreads();
+      attention_bwd_tile(s, self_cfg(a, b), dQ, dK, dV, DSx, Qb, Kb, Vb, Sb, Db, false);
+      // x and qn = LN1(x) recomputed
+      float* Xb = B1;
+      float* QN = B2;
+      load_tile(a, s, sv_block(b, 0), bin, Xb);
+      __syncthreads();
+      ln_rows(QN, Xb, n, wb.ln1_g, wb.ln1_b);
+      __syncthreads();
+      weight_grad(s, dQ, QN, n, gb.wq, gb.bq);
+      weight_grad(s, dK, Xb, n, gb.wk, gb.bk);
+      weight_grad(s, dV, Xb, n, gb.wv, gb.bv);
+      // d qn = dQ WQ (+ d s through the residual)
+      float* DQN = B3;
+      project_bwd(s, DQN, dQ, wb.wq, false);
+      if (res) {
+        tile_pass(DQN, n, [&](int r, int c4, float4& v) {
+          const float4 q = *reinterpret_cast<const float4*>(DSx + r * TLD + c4 * 4);
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        });
+        __syncthreads();
+      }
+      // d x = dK WK + dV WV + LN1 backward(d qn)
+      float* DXn = B7;
+      project_bwd(s, DXn, dK, wb.wk, false);
+      project_bwd(s, DXn, dV, wb.wv, true);
+      ln_bwd_rows(s, DXn, DQN, Xb, n, wb.ln1_g, gb.ln1_g, gb.ln1_b, true);
+      for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {         // DX <- DXn
+        const int r = e >> 4, c4 = e & 15;
+        *reinterpret_cast<float4*>(DX + r * TLD + c4 * 4) = *reinterpret_cast<const float4*>(DXn + r * TLD + c4 * 4);
+      }
+      __syncthreads();
+    }
+    // d p_e = d x0 through the embedding dropout (site 0)
+    {
+      const DropCfg d0 = at_site(a.drop, 0u);
+      scatter_rows(s, a.d_pe, DX, a.drop.p > 0.f ? &d0 : nullptr);
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t fused_train_smem() { return sizeof(TrainSmem) + 16; }
+
+}  // namespace carca

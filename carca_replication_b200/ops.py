@@ -420,6 +420,75 @@ class CrossScoreFn(torch.autograd.Function):
         return (d_o, None, d_p, None, None, None, None, None, None, None, *grads)
 
 
+# ------------------------------------------------------------------------------- fused training core
+class TrainCoreFn(torch.autograd.Function):
+    """src/carca.py:416-431 in train mode (dropout, encoder blocks, final LayerNorm, decoder per target tuple)
+    -> carca_train_core_fwd / _bwd: one forward and one backward kernel over the ACTIVE positions only."""
+
+    @staticmethod
+    def forward(ctx, p_e, o_e0, o_e1, p_x, o_x0, o_x1, cfg, *params):
+        N.require_device(p_e, o_e0, o_e1, p_x, o_x0, o_x1, *params)
+        H, n_blocks, decoder_kind, residual_sa, residual_ca, p_drop, seed = cfg
+        n_tuples = 1 if o_e1 is None else 2
+        p_e, o_e0 = as_f32(p_e), as_f32(o_e0)
+        o_e1 = None if o_e1 is None else as_f32(o_e1)
+        p_x, o_x0 = as_ids(p_x), as_ids(o_x0)
+        o_x1 = None if o_x1 is None else as_ids(o_x1)
+        params = tuple(_c(t) for t in params)
+        B, L, d = p_e.shape
+        dev = p_e.device
+        nbp = len(N.BLOCK_PARAM_NAMES)
+        blocks = (N.BlockParams * max(n_blocks, 1))()
+        for b in range(n_blocks):
+            blocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, params[b * nbp:(b + 1) * nbp])
+        rest = params[n_blocks * nbp:]
+        c = N.TrainCore()
+        c.B, c.L, c.n_heads, c.n_blocks, c.n_tuples = B, L, int(H), int(n_blocks), n_tuples
+        c.decoder_kind, c.residual_sa, c.residual_ca = int(decoder_kind), int(bool(residual_sa)), int(bool(residual_ca))
+        c.p_drop, c.seed = float(p_drop), int(seed)
+        c.p_x, c.p_e = N.i32p(p_x), N.f32p(p_e)
+        c.o_x[0], c.o_e[0] = N.i32p(o_x0), N.f32p(o_e0)
+        if n_tuples == 2:
+            c.o_x[1], c.o_e[1] = N.i32p(o_x1), N.f32p(o_e1)
+        c.blocks = blocks
+        c.norm_g, c.norm_b = N.f32p(rest[0]), N.f32p(rest[1])
+        if decoder_kind == 1:
+            c.cross = _struct(N.CrossParams, N.CROSS_PARAM_NAMES, rest[2:2 + len(N.CROSS_PARAM_NAMES)])
+        L_ = N.lib()
+        rows = torch.empty(L_.carca_train_core_rows_ints(B), dtype=torch.int32, device=dev)
+        saved = torch.empty(L_.carca_train_core_saved_floats(B, int(n_blocks), n_tuples), dtype=torch.float32,
+                            device=dev)
+        c.rows, c.saved = rows.data_ptr(), saved.data_ptr()
+        y = torch.empty((B, n_tuples * L), dtype=torch.float32, device=dev)
+        N.call("carca_train_core_fwd", N.f32p(y), n_tuples * L, C.byref(c), N.stream())
+        ctx.save_for_backward(p_e, o_e0, o_e1, p_x, o_x0, o_x1, rows, saved, *params)
+        ctx.core, ctx.blocks, ctx.n_tuples, ctx.n_blocks, ctx.decoder_kind = c, blocks, n_tuples, int(n_blocks), int(decoder_kind)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        st = ctx.saved_tensors
+        p_e, o_e0, o_e1 = st[0], st[1], st[2]
+        params = st[8:]
+        c, n_blocks = ctx.core, ctx.n_blocks
+        nbp = len(N.BLOCK_PARAM_NAMES)
+        dy = as_f32(dy)
+        grads = tuple(torch.zeros_like(t) for t in params)
+        gblocks = (N.BlockParams * max(n_blocks, 1))()
+        for b in range(n_blocks):
+            gblocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, grads[b * nbp:(b + 1) * nbp])
+        rest = grads[n_blocks * nbp:]
+        gcross = None
+        if ctx.decoder_kind == 1:
+            gcross = C.byref(_struct(N.CrossParams, N.CROSS_PARAM_NAMES, rest[2:2 + len(N.CROSS_PARAM_NAMES)]))
+        d_pe = torch.zeros_like(p_e)
+        d_o0 = torch.zeros_like(o_e0)
+        d_o1 = None if o_e1 is None else torch.zeros_like(o_e1)
+        N.call("carca_train_core_bwd", N.f32p(d_pe), N.f32p(d_o0), N.f32p(d_o1), gblocks, N.f32p(rest[0]),
+               N.f32p(rest[1]), gcross, N.f32p(dy), dy.shape[1], C.byref(c), N.stream())
+        return (d_pe, d_o0, d_o1, None, None, None, None, *grads)
+
+
 # ------------------------------------------------------------------------------- loss / metrics
 class BCEFn(torch.autograd.Function):
     """BinaryCrossEntropy.forward (src/carca.py:441-444); `reduce_sums` lets data-parallel runs

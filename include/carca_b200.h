@@ -248,6 +248,47 @@ int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* grads
                           int Lp, int d, int H, int residual, int training, float p_drop, uint64_t seed,
                           uint32_t site, int64_t ldy, int col0, float* scratch4, void* stream);
 
+/* ------------------------------------------------------------------ fused training core */
+/* Everything between the embeddings and the probabilities of CARCA.forward in TRAIN mode
+ * (src/carca.py:416-431: post-embedding dropout, the SelfAttentionBlocks :297-318, the final LayerNorm :421,
+ * the decoder per target tuple :424-429 with causal -1, :339) as ONE forward and ONE backward kernel that
+ * run on the ACTIVE positions only (profile id != 0 or a target id != 0), packed into 64-row bins
+ * (csrc/fused_train.cuh).  Padded positions reach no loss term, so every result equals the per-op entry
+ * points' (carca_sa_block_*, carca_cross_score_*, carca_dot_score_*, carca_layernorm_*, carca_dropout) on the
+ * same inputs, dropout masks included (same Philox sites and element indices).
+ * Supported: d == 64, L <= 64, n_heads in {1, 2, 4}, n_blocks <= 8, 1 or 2 target tuples of L positions each;
+ * returns -4 otherwise so the caller can use the per-op entry points.                                    */
+typedef struct {
+  int B, L, n_heads, n_blocks, n_tuples;
+  int decoder_kind;                 /* 0 = DotProduct (position-wise, :360), 1 = CrossAttentionBlock */
+  int residual_sa, residual_ca;
+  float p_drop;
+  uint64_t seed;
+  const int32_t* p_x;               /* [B, L] */
+  const int32_t* o_x[2];            /* [B, L] per tuple (src/train.py:86-88) */
+  const float* p_e;                 /* [B, L, 64] AllEmbedding output of the profile (masked, before :416) */
+  const float* o_e[2];              /* [B, L, 64] AllEmbedding output of each target tuple */
+  const carca_block_params* blocks; /* HOST array of n_blocks entries */
+  const float *norm_g, *norm_b;
+  carca_cross_params cross;         /* decoder_kind == 1 */
+  int32_t* rows;                    /* workspace, carca_train_core_rows_ints(B) int32 */
+  float* saved;                     /* workspace, carca_train_core_saved_floats(...) floats: activations kept by
+                                       the forward for the backward */
+} carca_train_core;
+
+int64_t carca_train_core_rows_ints(int B);
+int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples);
+
+/* y [B, ldy]: tuple t's probabilities at columns t*L .. t*L + L - 1 (the cat of src/carca.py:431) */
+int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void* stream);
+
+/* Backward of carca_train_core_fwd for the upstream gradient dy [B, ldy] (call after the forward with the same
+ * `c`, whose workspaces still hold the forward's row maps and activations).  d_pe / d_oe[t] [B, L, 64] and
+ * every parameter gradient are ACCUMULATED (caller zero-initialises; g_blocks is a HOST array).            */
+int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_block_grads* g_blocks, float* g_norm_g,
+                         float* g_norm_b, const carca_cross_grads* g_cross, const float* dy, int64_t ldy,
+                         const carca_train_core* c, void* stream);
+
 /* ------------------------------------------------------------------ loss */
 /* sums[0] += sum(ell * mask), sums[1] += sum(mask); replaces src/carca.py:442-443 numerators.
  * y_true int32.  Under data parallelism `sums` is all-reduced before finalize.   */

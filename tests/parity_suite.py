@@ -235,3 +235,56 @@ def check_fused_vs_modular(device, shape_name="tiny", B=5, T=None, decoder="ca",
     assert rel_err(y_f.cpu().numpy(), y_m.cpu().numpy()) < FP32_RTOL
     assert topk_equal_up_to_ties(y_f.cpu().numpy(), y_m.cpu().numpy(), 10, tol=1e-6)
     return y_f
+
+
+def check_fused_train_vs_per_op(device, B=7, decoder="ca", p=0.3, heads=2, n_tuples=2, all_valid=False, odd_masks=False,
+                                shape_name="tiny", seed=5, gtol=2e-4):
+    """Fused training core (csrc/fused_train.cuh: active positions packed into 64-row bins, one forward and one
+    backward kernel) vs the per-op kernels on the same inputs, weights and Philox seed: probabilities, loss and
+    every parameter gradient.  odd_masks punches holes into the windows (padding inside a profile, targets at
+    padded profile positions and the reverse) — layouts the reference loader never builds but its model accepts."""
+    import dataclasses
+
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import synth
+
+    shape = dataclasses.replace(synth.SHAPES[shape_name], n_heads=heads)
+    L = shape.seq_len
+    b = synth.make_train_batch(shape, B, seed=seed, all_valid=all_valid)
+    if odd_masks:
+        g = torch.Generator().manual_seed(seed)
+        for key, frac in (("p_x", 0.15), ("o_x", 0.2)):
+            hole = torch.rand(b[key].shape, generator=g) < frac
+            b[key] = torch.where(hole, torch.zeros_like(b[key]), b[key])
+        b["o_x"][0, :L] = torch.randint(1, shape.n_items, (L,), generator=g, dtype=torch.int32)   # targets everywhere
+        b["p_x"][1] = 0                                                                          # empty profile
+    b = {k: v.to(device) for k, v in b.items()}
+    table = synth.make_attr_table(shape, seed=seed).to(device)
+    results = []
+    for fused in (True, False):
+        model = synth.build_model(shape, decoder, p=p, seed=seed).to(device).train()
+        model.embeds.set_attr_table(table)
+        model.use_fused_train = fused
+        tg = [(b["o_x"][:, :L], None, b["o_c"][:, :L]), (b["o_x"][:, L:], None, b["o_c"][:, L:])][:n_tuples]
+        ops.set_dropout_seed(1234 + seed)
+        try:
+            n0 = N.lib().carca_launch_count()
+            y = model.forward((b["p_x"], None, b["p_c"]), tg)
+            mask = cb.get_mask(b["o_x"][:, :n_tuples * L])
+            loss = cb.BinaryCrossEntropy().forward(y, b["y_true"][:, :n_tuples * L], mask)
+            loss.backward()
+            launches = N.lib().carca_launch_count() - n0
+        finally:
+            ops.set_dropout_seed(None)
+        results.append((y.detach().cpu().numpy(), loss.item(), {k: v.grad.cpu().numpy() for k, v in
+                                                                 model.named_parameters() if v.grad is not None},
+                        launches))
+    (y_f, loss_f, g_f, n_f), (y_m, loss_m, g_m, n_m) = results
+    assert n_f < n_m
+    assert y_f.shape == y_m.shape == (B, n_tuples * L)
+    assert rel_err(y_f, y_m) < FP32_RTOL
+    assert abs(loss_f - loss_m) < 1e-5 * max(1.0, abs(loss_m))
+    assert set(g_f) == set(g_m)
+    for k in g_m:
+        e = grad_err(g_f[k], g_m[k], grad_floor(k))
+        assert e < gtol, (k, e)

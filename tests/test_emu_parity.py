@@ -60,3 +60,11 @@ def test_module_variants_train(emu_backend, name, mode):
 
 def test_knn(emu_backend):
     S.check_knn(emu_backend)
+
+
+@pytest.mark.parametrize("kw", [dict(decoder="ca", p=0.3), dict(decoder="dot", p=0.3), dict(decoder="ca", p=0.0, heads=4),
+                                dict(decoder="ca", p=0.25, heads=1, odd_masks=True),
+                                dict(decoder="dot", p=0.25, odd_masks=True), dict(decoder="ca", p=0.5, n_tuples=1),
+                                dict(decoder="ca", p=0.3, B=9, all_valid=True)])
+def test_fused_train_vs_per_op_kernels(emu_backend, kw):
+    S.check_fused_train_vs_per_op(emu_backend, **kw)
