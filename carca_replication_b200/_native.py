@@ -66,7 +66,8 @@ class TrainCore(C.Structure):
     _fields_ = [("B", i32), ("L", i32), ("n_heads", i32), ("n_blocks", i32), ("n_tuples", i32), ("decoder_kind", i32),
                 ("residual_sa", i32), ("residual_ca", i32), ("p_drop", f32), ("seed", u64), ("p_x", vp),
                 ("o_x", vp * 2), ("p_e", vp), ("o_e", vp * 2), ("blocks", C.POINTER(BlockParams)), ("norm_g", vp),
-                ("norm_b", vp), ("cross", CrossParams), ("rows", vp), ("saved", vp)]
+                ("norm_b", vp), ("cross", CrossParams), ("rows", vp), ("saved", vp), ("embed", C.POINTER(EmbedParams)),
+                ("attrs", C.POINTER(AttrSource)), ("p_c", vp), ("o_c", vp * 2), ("fold", vp)]
 
 
 class Interactions(C.Structure):
@@ -115,7 +116,9 @@ SIGNATURES = {
     "carca_train_core_rows_ints": [i32],
     "carca_train_core_saved_floats": [i32, i32, i32],
     "carca_train_core_fwd": [vp, i64, P(TrainCore), vp],
-    "carca_train_core_bwd": [vp, vp, vp, P(BlockParams), vp, vp, P(CrossParams), vp, i64, P(TrainCore), vp],
+    "carca_train_core_fold_floats": [P(EmbedParams)],
+    "carca_train_core_bwd": [vp, vp, vp, P(BlockParams), vp, vp, P(CrossParams), P(EmbedGrads), vp, vp, i64,
+                             P(TrainCore), vp],
     "carca_bce_sums": [vp, vp, vp, vp, i64, f32, vp],
     "carca_bce_finalize": [vp, vp, vp],
     "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
@@ -149,6 +152,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.carca_eval_scratch_bytes.restype = C.c_int64
     lib.carca_train_core_rows_ints.restype = C.c_int64
     lib.carca_train_core_saved_floats.restype = C.c_int64
+    lib.carca_train_core_fold_floats.restype = C.c_int64
     return lib
 
 

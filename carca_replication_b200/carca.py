@@ -403,12 +403,22 @@ class CARCA(Model):
             return False
         return all(t[0].dim() == 2 and t[0].shape[1] == L for t in targets)
 
+    def _folded_embedding_table(self, profile, targets) -> Optional[ItemAttrTable]:
+        """The sparse item->attribute table when AllEmbedding can run inside the fused training kernels
+        (device-resident CSR attributes for every row set, built-in positional encodings), else None."""
+        emb = self.embeds
+        if type(emb) is not AllEmbedding or not hasattr(emb.enc, "table"):
+            return None
+        tables = [a if isinstance(a, ItemAttrTable) else (emb.attr_table if a is None else False)
+                  for a in [profile[1]] + [t[1] for t in targets]]
+        first = tables[0]
+        if not isinstance(first, ItemAttrTable) or not first.is_sparse or any(t is not first for t in tables):
+            return None
+        return first
+
     def _forward_fused_train(self, profile, targets) -> Tensor:
         p_x, p_a, p_c = profile
         with ops.forward_seed():
-            p_mask = get_mask(p_x)
-            p_e = self.embeds.forward(p_x, p_a, p_c, p_mask, False)
-            o_es = [self.embeds.forward(o_x, o_a, o_c, get_mask(o_x), True) for (o_x, o_a, o_c) in targets]
             blocks = list(self.encoder)
             dec = self.decoder
             is_ca = type(dec) is CrossAttentionBlock
@@ -420,9 +430,22 @@ class CARCA(Model):
                            dec.ffn.bias]
             cfg = (H, len(blocks), 1 if is_ca else 0, bool(blocks[0].residual) if blocks else True,
                    bool(dec.residual) if is_ca else True, float(self.dropout.p), ops.current_seed())
-            o_e1 = o_es[1] if len(o_es) > 1 else None
             o_x1 = targets[1][0] if len(targets) > 1 else None
-            return ops.TrainCoreFn.apply(p_e, o_es[0], o_e1, p_x, targets[0][0], o_x1, cfg, *params)
+            table = self._folded_embedding_table(profile, targets)
+            if table is not None:
+                # AllEmbedding runs inside the kernels too (folded tables): ids + context in, probabilities out
+                emb = self.embeds
+                pos = emb.enc.table(p_x.shape[1])
+                eparams = [emb.items_embed.weight, emb.feats_embed.weight, emb.feats_embed.bias,
+                           emb.joint_embed.weight, emb.joint_embed.bias] + ([pos] if pos is not None else [])
+                o_c1 = targets[1][2] if len(targets) > 1 else None
+                return ops.TrainCoreFn.apply(None, None, None, p_x, targets[0][0], o_x1,
+                                             (table, p_c, targets[0][2], o_c1, pos is not None), cfg, *eparams, *params)
+            p_mask = get_mask(p_x)
+            p_e = self.embeds.forward(p_x, p_a, p_c, p_mask, False)
+            o_es = [self.embeds.forward(o_x, o_a, o_c, get_mask(o_x), True) for (o_x, o_a, o_c) in targets]
+            o_e1 = o_es[1] if len(o_es) > 1 else None
+            return ops.TrainCoreFn.apply(p_e, o_es[0], o_e1, p_x, targets[0][0], o_x1, None, cfg, *params)
 
     def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:

@@ -612,14 +612,14 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
   if (c->n_tuples < 1 || c->n_tuples > TMAXT) return fail(-4, "train_core: %d target tuples (1 or 2)", c->n_tuples);
   CARCA_REQUIRE(c->decoder_kind == 0 || c->decoder_kind == 1, "train_core: unknown decoder kind %d", c->decoder_kind);
   CARCA_REQUIRE(c->p_drop >= 0.f && c->p_drop < 1.f, "train_core: p=%f outside [0,1)", c->p_drop);
-  CARCA_REQUIRE(c->rows && c->saved && c->p_x && c->p_e, "train_core: missing workspace or inputs");
+  CARCA_REQUIRE(c->rows && c->saved && c->p_x, "train_core: missing workspace or inputs");
   memset(&a, 0, sizeof(a));
   a.B = c->B; a.L = c->L; a.H = c->n_heads; a.n_blocks = c->n_blocks; a.n_tuples = c->n_tuples;
   a.decoder = c->decoder_kind; a.residual_sa = c->residual_sa; a.residual_ca = c->residual_ca;
   a.drop = drop_cfg(c->p_drop, c->seed, 0u);
   a.p_x = c->p_x; a.p_e = c->p_e;
   for (int t = 0; t < c->n_tuples; ++t) {
-    CARCA_REQUIRE(c->o_x[t] && c->o_e[t], "train_core: target tuple %d missing", t);
+    CARCA_REQUIRE(c->o_x[t] != nullptr, "train_core: target tuple %d missing", t);
     a.o_x[t] = c->o_x[t];
     a.o_e[t] = c->o_e[t];
   }
@@ -633,6 +633,27 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
   for (int b = 0; b < c->n_blocks; ++b) memcpy(&a.blk[b], &c->blocks[b], sizeof(TrainBlockW));
   a.fn_g = c->norm_g; a.fn_b = c->norm_b;
   memcpy(&a.dec, &c->cross, sizeof(TrainCrossW));
+  if (c->embed) {
+    const carca_embed_params* w = c->embed;
+    if (w->d != TD) return fail(-4, "train_core: d=%d, the fused kernels handle d=64", w->d);
+    if (w->n_ctx > 32) return fail(-4, "train_core: %d context features (at most 32)", w->n_ctx);
+    CARCA_REQUIRE(c->attrs && c->attrs->kind == CARCA_ATTR_CSR, "train_core: the folded embedding needs CSR attributes");
+    CARCA_REQUIRE(c->fold && c->p_c, "train_core: folded embedding without workspace / context");
+    if (w->pos) CARCA_REQUIRE(c->L <= w->pos_len, "train_core: sequence length %d > positional table %d", c->L, w->pos_len);
+    a.embed_mode = 1;
+    a.C = w->n_ctx; a.A = w->n_attrs; a.ldj = w->d + w->g;
+    a.sqrt_d = (float)std::sqrt((double)w->d);
+    a.E = w->items_embed; a.Wj = w->joint_w; a.fold = c->fold; a.pos_table = w->pos;
+    a.csr_rowptr = c->attrs->csr_rowptr; a.csr_cols = c->attrs->csr_cols; a.csr_vals = c->attrs->csr_vals;
+    a.p_c = c->p_c;
+    for (int t = 0; t < c->n_tuples; ++t) {
+      CARCA_REQUIRE(c->o_c[t] != nullptr, "train_core: context of target tuple %d missing", t);
+      a.o_c[t] = c->o_c[t];
+    }
+  } else {
+    CARCA_REQUIRE(c->p_e != nullptr, "train_core: p_e missing");
+    for (int t = 0; t < c->n_tuples; ++t) CARCA_REQUIRE(c->o_e[t] != nullptr, "train_core: o_e of tuple %d missing", t);
+  }
   return 0;
 }
 int train_grid(int B) { return B < 148 ? (B < 1 ? 1 : B) : 148; }
@@ -643,6 +664,10 @@ int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples) {
   return (int64_t)sv_count(n_blocks, n_tuples) * B * TR * TD;
 }
 
+int64_t carca_train_core_fold_floats(const carca_embed_params* w) {
+  return w ? ((int64_t)w->n_attrs + w->n_ctx + 1) * TD : 0;
+}
+
 int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void* stream) {
   cudaStream_t st = S(stream);
   TrainArgs a;
@@ -650,11 +675,22 @@ int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void*
   if (a.B <= 0) return 0;
   a.y = y;
   a.ldy = ldy;
+  if (a.embed_mode) {
+    // GT[a][c] = sum_g Wf[g][a] Wj[c][d + g]   ([A + C, 64]);  cst = Wj[:, d:] bf + bj
+    const carca_embed_params* w = c->embed;
+    const int AC = w->n_attrs + w->n_ctx;
+    GemmArgs g = gemm_defaults(w->feats_w, w->joint_w + w->d, c->fold, AC, TD, w->g);
+    g.transA = 1; g.lda = AC;
+    g.transB = 1; g.ldb = w->d + w->g;
+    g.ldc = TD;
+    TRY(launch_gemm(g, st));
+    TRY(linear(c->fold + (long long)AC * TD, w->feats_b, w->joint_w + w->d, w->joint_b, 1, TD, w->g, w->d + w->g, st));
+  }
   cudaMemsetAsync(a.n_bins, 0, 4 * sizeof(int), st);
   cudaMemsetAsync(a.row_src, 0xFF, sizeof(int) * (size_t)a.B * TR, st);
   {
     auto k = train_pack_kernel;
-    CARCA_LAUNCH(k, dim3(ceil_div(a.B, 128)), dim3(128), 0, st, a);
+    CARCA_LAUNCH(k, dim3(ceil_div(a.B, 128)), dim3(1024), 0, st, a);
     TRY(check_launch("train_pack"));
   }
   auto k = fused_train_fwd_kernel;
@@ -665,13 +701,23 @@ int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void*
 }
 
 int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_block_grads* g_blocks, float* g_norm_g,
-                         float* g_norm_b, const carca_cross_grads* g_cross, const float* dy, int64_t ldy,
-                         const carca_train_core* c, void* stream) {
+                         float* g_norm_b, const carca_cross_grads* g_cross, const carca_embed_grads* g_embed,
+                         float* d_fold, const float* dy, int64_t ldy, const carca_train_core* c, void* stream) {
   cudaStream_t st = S(stream);
   TrainArgs a;
   TRY(train_args(a, c));
   if (a.B <= 0) return 0;
-  CARCA_REQUIRE(d_pe && d_oe0 && (c->n_tuples < 2 || d_oe1) && dy, "train_core_bwd: missing gradient buffers");
+  CARCA_REQUIRE(dy != nullptr, "train_core_bwd: dy missing");
+  if (a.embed_mode) {
+    CARCA_REQUIRE(g_embed && d_fold && g_embed->items_embed && g_embed->feats_w && g_embed->feats_b &&
+                      g_embed->joint_w && g_embed->joint_b,
+                  "train_core_bwd: embedding gradients / workspace missing");
+    a.gE = g_embed->items_embed; a.gWj = g_embed->joint_w; a.dfold = d_fold;
+    a.gpos = a.pos_table ? g_embed->pos : nullptr;
+    cudaMemsetAsync(d_fold, 0, sizeof(float) * (size_t)carca_train_core_fold_floats(c->embed), st);
+  } else {
+    CARCA_REQUIRE(d_pe && d_oe0 && (c->n_tuples < 2 || d_oe1), "train_core_bwd: missing gradient buffers");
+  }
   CARCA_REQUIRE(g_norm_g && g_norm_b && (c->n_blocks == 0 || g_blocks), "train_core_bwd: missing parameter gradients");
   a.dy = dy;
   a.ldy = ldy;
@@ -688,7 +734,32 @@ int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_bl
   const size_t smem = fused_train_smem();
   TRY(allow_smem(k, smem));
   CARCA_LAUNCH(k, dim3(train_grid(a.B)), dim3(TTHREADS), smem, st, a);
-  return check_launch("fused_train_bwd");
+  TRY(check_launch("fused_train_bwd"));
+  if (a.embed_mode) {
+    // un-fold: dG = d_fold rows [A + C, 64] (transposed d(Wj_q Wf)), dcst = its last row
+    const carca_embed_params* w = c->embed;
+    const int AC = w->n_attrs + w->n_ctx, d = w->d, gd = w->g;
+    const float* dcst = d_fold + (long long)AC * TD;
+    {  // d Wf[g][a] = sum_c Wj[c][d + g] dG[a][c]
+      GemmArgs g = gemm_defaults(w->joint_w + d, d_fold, g_embed->feats_w, gd, AC, TD);
+      g.transA = 1; g.lda = d + gd;
+      g.transB = 1; g.ldb = TD;
+      g.ldc = AC;
+      TRY(launch_gemm(g, st));
+    }
+    {  // d Wj[c][d + g] += sum_a dG[a][c] Wf[g][a]
+      GemmArgs g = gemm_defaults(d_fold, w->feats_w, g_embed->joint_w + d, TD, gd, AC);
+      g.transA = 1; g.lda = TD;
+      g.transB = 1; g.ldb = AC;
+      g.ldc = d + gd;
+      g.accumulate = 1;
+      TRY(launch_gemm(g, st));
+    }
+    TRY(linear_dw(g_embed->joint_w + d, dcst, w->feats_b, 1, TD, gd, d + gd, gd, st));   // += dcst (x) bf
+    TRY(linear_dx(g_embed->feats_b, dcst, w->joint_w + d, 1, TD, gd, d + gd, st));       // d bf = Wj_q^T dcst
+    cudaMemcpyAsync(g_embed->joint_b, dcst, sizeof(float) * TD, cudaMemcpyDeviceToDevice, st);   // d bj = dcst
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------ loss / metrics

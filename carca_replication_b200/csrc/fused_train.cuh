@@ -33,7 +33,7 @@ constexpr int TR = 64;            // rows per bin
 constexpr int TD = 64;            // model width
 constexpr int TLD = 68;           // row stride of a tile in shared memory (floats)
 constexpr int TBUF = TR * TLD;    // floats per tile
-constexpr int TTHREADS = 256;
+constexpr int TTHREADS = 512;
 constexpr int TWARPS = TTHREADS / 32;
 constexpr int TMAXB = 8;          // encoder blocks
 constexpr int TMAXT = 2;          // target tuples (positives | negatives, src/train.py:86-88)
@@ -66,6 +66,19 @@ struct TrainArgs {
   TrainBlockW blk[TMAXB];
   const float *fn_g, *fn_b;
   TrainCrossW dec;
+  // folded in-kernel embedding (embed_mode == 1): e = mask * (Wj_z sqrt(d) E[x] + sum_attr val GT[attr] + sum_k c_k GT[A+k]
+  //                                                              + cst (+ pos)),  GT = (Wj_q Wf)^T, cst = Wj_q bf + bj
+  int embed_mode, C, A, ldj;                  // ldj = d + g, row stride of joint_embed.weight
+  float sqrt_d;
+  const float* E;                             // items_embed.weight [n_items, 64]
+  const float* Wj;                            // joint_embed.weight [64, ldj]; columns 0..63 multiply sqrt(d) E[x]
+  const float* fold;                          // [A + C + 1, 64]: GT rows, then cst
+  const float* pos_table;                     // optional [>= L, 64], profile rows only
+  const int *csr_rowptr, *csr_cols;
+  const float* csr_vals;
+  const float* p_c;                           // [B, L, C]
+  const float* o_c[TMAXT];
+  float *gE, *gWj, *dfold, *gpos;             // backward: d items_embed, d joint_embed.weight, d fold, d pos
   // backward only
   const float* dy;                            // [B, ldy]
   float* d_pe;                                // [B, L, 64] zero-initialised by the caller
@@ -87,6 +100,7 @@ struct TrainSmem {
   float red[TWARPS][2][TD];        // per-warp partial sums of vector gradients
   float gsc[TR];                   // per-row scalars
   int src[TR], info[TR], pos[TR], usr[TR];
+  int ids[1 + TMAXT][TR];          // embed_mode: item id of the row in the profile / each target tuple
   int n, npad;
 };
 
@@ -94,26 +108,33 @@ struct TrainSmem {
 // One CTA per 128 users: counts each user's active positions, packs users greedily into 64-row bins,
 // writes the row maps, and fills y of every INACTIVE position with the value the reference computes
 // there (sigmoid(ffn bias) for the cross-attention decoder: s = 0; 0.5 for the dot product).
-__global__ void __launch_bounds__(128) train_pack_kernel(const TrainArgs a) {
+__global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
+  __shared__ unsigned char flg[128][TR];   // per (user of this CTA, position): validity bits
   __shared__ int cnt[128], bin_of[128], start_of[128], base;
-  const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
+  const int t = threadIdx.x;
   const int L = a.L;
-  int n = 0;
-  if (usr < a.B) {
-    const float ydef = a.decoder == 1 ? 1.0f / (1.0f + expf(-a.dec.bf[0])) : 0.5f;
-    for (int j = 0; j < L; ++j) {
-      bool act = a.p_x[(long long)usr * L + j] != 0;
-      for (int q = 0; q < a.n_tuples; ++q) act = act || a.o_x[q][(long long)usr * L + j] != 0;
-      n += act ? 1 : 0;
-      if (!act)
-        for (int q = 0; q < a.n_tuples; ++q) a.y[(long long)usr * a.ldy + q * L + j] = ydef;
-    }
+  const int user0 = blockIdx.x * 128;
+  const int users = min(128, a.B - user0);
+  const float ydef = a.decoder == 1 ? 1.0f / (1.0f + expf(-a.dec.bf[0])) : 0.5f;
+  for (int e = t; e < users * L; e += blockDim.x) {          // coalesced sweep over the CTA's positions
+    const int u = e / L, j = e % L;
+    const long long g = (long long)(user0 + u) * L + j;
+    int f = a.p_x[g] != 0 ? 1 : 0;
+    for (int q = 0; q < a.n_tuples; ++q) f |= (a.o_x[q][g] != 0 ? 2 : 0) << q;
+    flg[u][j] = (unsigned char)f;
+    if (!f)
+      for (int q = 0; q < a.n_tuples; ++q) a.y[(long long)(user0 + u) * a.ldy + q * L + j] = ydef;
   }
-  cnt[t] = n;
+  __syncthreads();
+  if (t < 128) {
+    int n = 0;
+    if (t < users)
+      for (int j = 0; j < L; ++j) n += flg[t][j] != 0;
+    cnt[t] = n;
+  }
   __syncthreads();
   if (t == 0) {
     int bin = 0, fill = 0;
-    const int users = min(128, a.B - (int)blockIdx.x * 128);
     for (int q = 0; q < users; ++q) {
       if (fill + cnt[q] > TR) {
         ++bin;
@@ -126,17 +147,15 @@ __global__ void __launch_bounds__(128) train_pack_kernel(const TrainArgs a) {
     base = atomicAdd(a.n_bins, bin + 1);
   }
   __syncthreads();
-  if (usr < a.B && n > 0) {
+  if (t < users && cnt[t] > 0) {
     const long long o = (long long)(base + bin_of[t]) * TR;
     int r = start_of[t];
-    const int seg = start_of[t] | ((start_of[t] + n - 1) << 8);
+    const int seg = start_of[t] | ((start_of[t] + cnt[t] - 1) << 8);
     for (int j = 0; j < L; ++j) {
-      int flags = a.p_x[(long long)usr * L + j] != 0 ? TI_PVALID : 0;
-      for (int q = 0; q < a.n_tuples; ++q)
-        if (a.o_x[q][(long long)usr * L + j] != 0) flags |= TI_TVALID0 << q;
-      if (flags) {
-        a.row_src[o + r] = usr * L + j;
-        a.row_info[o + r] = seg | flags;
+      const int f = flg[t][j];
+      if (f) {
+        a.row_src[o + r] = (user0 + t) * L + j;
+        a.row_info[o + r] = seg | (f << 16);
         ++r;
       }
     }
@@ -146,7 +165,9 @@ __global__ void __launch_bounds__(128) train_pack_kernel(const TrainArgs a) {
 // -------------------------------------------------------------------------------------------------- tiles
 // Thread (ty, tx) = (tid / 16, tid % 16).
 
-// C[r][n] = sum_k A[r][k] W[n][k], K % 4 == 0; thread owns rows 4ty..4ty+3 and the strided columns
+constexpr int TNR = TR * 16 / TTHREADS;   // rows per thread in gemm_nt (2 with 512 threads)
+
+// C[r][n] = sum_k A[r][k] W[n][k], K % 4 == 0; thread owns rows TNR*ty .. TNR*ty + TNR - 1 and the strided columns
 // tx, tx+16, tx+32, tx+48 (< NCOLS), so the 128-bit loads of W rows are bank-conflict free.
 // `need(j)` lets attention skip columns outside the rows' key range.
 template <int NCOLS, class Need, class Epi>
@@ -154,27 +175,27 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, co
                                         int K, int nrows, Need need, Epi epi) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   constexpr int NJ = NCOLS / 16;
-  if (ty * 4 < nrows) {
-    float acc[4][NJ];
+  if (ty * TNR < nrows) {
+    float acc[TNR][NJ];
     bool on[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      on[j] = need(ty * 4, tx + 16 * j);
+      on[j] = need(ty * TNR, tx + 16 * j);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i][j] = 0.f;
+      for (int i = 0; i < TNR; ++i) acc[i][j] = 0.f;
     }
-    const float* ap = A + (ty * 4) * lda;
+    const float* ap = A + (ty * TNR) * lda;
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
-      float4 av[4];
+      float4 av[TNR];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(ap + i * lda + k);
+      for (int i = 0; i < TNR; ++i) av[i] = *reinterpret_cast<const float4*>(ap + i * lda + k);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (on[j]) {
           const float4 b = *reinterpret_cast<const float4*>(W + (tx + 16 * j) * ldw + k);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < TNR; ++i) {
             acc[i][j] = fmaf(av[i].x, b.x, acc[i][j]);
             acc[i][j] = fmaf(av[i].y, b.y, acc[i][j]);
             acc[i][j] = fmaf(av[i].z, b.z, acc[i][j]);
@@ -187,7 +208,7 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, co
     for (int j = 0; j < NJ; ++j)
       if (on[j]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) epi(ty * 4 + i, tx + 16 * j, acc[i][j]);
+        for (int i = 0; i < TNR; ++i) epi(ty * TNR + i, tx + 16 * j, acc[i][j]);
       }
   }
 }
@@ -196,16 +217,24 @@ struct NeedAll {
   __device__ __forceinline__ bool operator()(int, int) const { return true; }
 };
 
-// C[r][c] = sum_{k in [klo, khi)} A[r][k] B[k][c] for c < NC (NC in {16, 32, 64}); thread owns RT = NC/16
+// rows per thread of gemm_nn / gemm_tn for NC output columns (4 contiguous columns per thread)
+template <int NC>
+struct RowTile {
+  static constexpr int CG = NC / 4;
+  static constexpr int RG = TTHREADS / CG;
+  static constexpr int RT = RG >= TR ? 1 : TR / RG;
+};
+
+// C[r][c] = sum_{k in [klo, khi)} A[r][k] B[k][c] for c < NC (NC in {16, 32, 64}); thread owns RowTile<NC>::RT
 // rows and 4 contiguous columns.  range(r0, r1, klo, khi) gives the reduction range of rows r0..r1
 // (multiples of 4 are not required).
 template <int NC, class Range, class Epi>
 __device__ __forceinline__ void gemm_nn(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                         int nrows, Range range, Epi epi) {
-  constexpr int CG = NC / 4, RT = NC / 16;
+  constexpr int CG = RowTile<NC>::CG, RT = RowTile<NC>::RT;
   const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
   const int r0 = ty * RT;
-  if (r0 < nrows) {
+  if (r0 < nrows && r0 < TR) {
     int klo, khi;
     range(r0, r0 + RT - 1, klo, khi);
     float acc[RT][4];
@@ -229,14 +258,15 @@ __device__ __forceinline__ void gemm_nn(const float* __restrict__ A, int lda, co
   }
 }
 
-// C[n][c] = sum_{r in [rlo, rhi)} A[r][n] X[r][c] for n < 64, c < NC; thread owns RT = NC/16 values of n and 4
+// C[n][c] = sum_{r in [rlo, rhi)} A[r][n] X[r][c] for n < 64, c < NC; thread owns RowTile<NC>::RT values of n and 4
 // contiguous columns.  range(n0, n1, rlo, rhi) gives the reduction range for output rows n0..n1.
 template <int NC, class Range, class Epi>
 __device__ __forceinline__ void gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ X, int ldx,
                                         Range range, Epi epi) {
-  constexpr int CG = NC / 4, RT = NC / 16;
+  constexpr int CG = RowTile<NC>::CG, RT = RowTile<NC>::RT;
   const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
   const int n0 = ty * RT;
+  if (n0 >= TR) return;
   int rlo, rhi;
   range(n0, n0 + RT - 1, rlo, rhi);
   float acc[RT][4];
@@ -287,12 +317,12 @@ __device__ __forceinline__ DropCfg at_site(DropCfg c, unsigned site) {
 }
 
 // loads the 64 x 64 weight matrix Wg (row-major, as stored) into s.w with row stride TLD
-__device__ __forceinline__ void load_w(TrainSmem& s, const float* __restrict__ Wg) {
+__device__ __forceinline__ void load_w(TrainSmem& s, const float* __restrict__ Wg, int ldg = TD) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TR * 16 / TTHREADS; ++i) {
     const int e = threadIdx.x + i * TTHREADS;   // float4 index, 16 per row
     const int n = e >> 4, k4 = e & 15;
-    *reinterpret_cast<float4*>(s.w + n * TLD + k4 * 4) = *reinterpret_cast<const float4*>(Wg + n * TD + k4 * 4);
+    *reinterpret_cast<float4*>(s.w + n * TLD + k4 * 4) = *reinterpret_cast<const float4*>(Wg + (long long)n * ldg + k4 * 4);
   }
 }
 
@@ -411,23 +441,30 @@ __device__ __forceinline__ void ln_bwd_rows(TrainSmem& s, float* dx, const float
 
 // db[c] += sum_r tile[r][c]
 __device__ __forceinline__ void colsum_tile(TrainSmem& s, const float* tile, int rows, float* __restrict__ db) {
-  const int c = threadIdx.x % TD, part = threadIdx.x / TD;   // 4 row slices
+  constexpr int PARTS = TTHREADS / TD;                      // row slices
+  static_assert(PARTS <= TWARPS, "red[] holds one row of partials per slice");
+  const int c = threadIdx.x % TD, part = threadIdx.x / TD;
   float acc = 0.f;
-  for (int r = part; r < rows; r += TTHREADS / TD) acc += tile[r * TLD + c];
+  for (int r = part; r < rows; r += PARTS) acc += tile[r * TLD + c];
   s.red[part][0][c] = acc;
   __syncthreads();
-  if (threadIdx.x < TD) atomicAdd(db + c, s.red[0][0][c] + s.red[1][0][c] + s.red[2][0][c] + s.red[3][0][c]);
+  if (threadIdx.x < TD) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < PARTS; ++q) t += s.red[q][0][c];
+    atomicAdd(db + c, t);
+  }
   __syncthreads();
 }
 
 // dW[n][k] += sum_r dY[r][n] X[r][k]  (atomics into the gradient tensor), db[n] += colsum(dY)
 __device__ __forceinline__ void weight_grad(TrainSmem& s, const float* dY, const float* X, int rows,
-                                            float* __restrict__ dW, float* __restrict__ db) {
+                                            float* __restrict__ dW, float* __restrict__ db, int ldw = TD) {
   gemm_tn<TD>(dY, TLD, X, TLD,
               [&](int, int, int& lo, int& hi) { lo = 0; hi = rows; },
               [&](int n, int c, const float (&v)[4]) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(dW + n * TD + c + j, v[j]);
+                for (int j = 0; j < 4; ++j) atomicAdd(dW + (long long)n * ldw + c + j, v[j]);
               });
   if (db) colsum_tile(s, dY, rows, db);
 }
@@ -455,9 +492,9 @@ __device__ __forceinline__ void query_range(const TrainSmem& s, int j0, int j1, 
 }
 
 __device__ __forceinline__ bool attn_need(const TrainSmem& s, int r0, int j) {
-  // rows r0..r0+3: any of them may attend key j?
+  // rows r0 .. r0+TNR-1: any of them may attend key j?
   if (r0 >= s.n || j >= s.n) return false;
-  const int r1 = min(r0 + 3, s.n - 1);
+  const int r1 = min(r0 + TNR - 1, s.n - 1);
   return j <= r1 && j >= (s.info[r0] & 0x7f);
 }
 
@@ -625,6 +662,10 @@ __device__ __forceinline__ void load_bin(const TrainArgs& a, TrainSmem& s, int b
     s.info[r] = src >= 0 ? a.row_info[(long long)bin * TR + r] : 0;
     s.pos[r] = src >= 0 ? src % a.L : 0;
     s.usr[r] = src >= 0 ? src / a.L : 0;
+    if (a.embed_mode) {
+      s.ids[0][r] = src >= 0 ? a.p_x[src] : 0;
+      for (int t = 0; t < a.n_tuples; ++t) s.ids[1 + t][r] = src >= 0 ? a.o_x[t][src] : 0;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -660,6 +701,150 @@ __device__ __forceinline__ float row_dot(const float* a, const float* __restrict
   return warp_sum(fmaf(a[lane], b[lane], a[lane + 32] * b[lane + 32]));
 }
 
+// -------------------------------------------------------------------------------------------------- folded embedding
+// Z[r] = sqrt(d) E[id_r] (zero rows for padding ids and below the bin's fill)
+__device__ __forceinline__ void gather_items(const TrainArgs& a, const TrainSmem& s, const int* ids, float* Z) {
+  for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {
+    const int r = e >> 4, c4 = e & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int id = ids[r];
+    if (id != 0) {
+      v = *reinterpret_cast<const float4*>(a.E + (long long)id * TD + c4 * 4);
+      v.x *= a.sqrt_d; v.y *= a.sqrt_d; v.z *= a.sqrt_d; v.w *= a.sqrt_d;
+    }
+    *reinterpret_cast<float4*>(Z + r * TLD + c4 * 4) = v;
+  }
+}
+
+// AllEmbedding.forward (src/carca.py:85-95) of one row set through the folded tables.  Eo: output tile,
+// Z: scratch tile.  Rows with id 0 come out exactly 0 (the final `* mask`, :94).
+__device__ __forceinline__ void embed_rows(const TrainArgs& a, TrainSmem& s, const int* ids, const float* __restrict__ ctx,
+                                           bool add_pos, float* Eo, float* Z) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  gather_items(a, s, ids, Z);
+  load_w(s, a.Wj, a.ldj);
+  __syncthreads();
+  gemm_nt<TD>(Z, TLD, s.w, TLD, TD, s.npad, NeedAll(), [&](int r, int n, float v) { Eo[r * TLD + n] = v; });
+  __syncthreads();
+  const float* cst = a.fold + (long long)(a.A + a.C) * TD;
+  for (int r = w; r < s.npad; r += TWARPS) {
+    const int id = ids[r];
+    float v0 = 0.f, v1 = 0.f;
+    if (id != 0) {
+      v0 = Eo[r * TLD + lane] + cst[lane];
+      v1 = Eo[r * TLD + lane + 32] + cst[lane + 32];
+      // attribute rows of GT: the lanes fetch the row's column ids / values at once, then four table rows are in
+      // flight per step (a plain loop would serialise two dependent L2 round trips per attribute)
+      const int k0 = a.csr_rowptr[id], nnz = a.csr_rowptr[id + 1] - k0;
+      for (int kb = 0; kb < nnz; kb += 32) {
+        const int m = min(32, nnz - kb);
+        int col = 0;
+        float val = 0.f;
+        if (lane < m) {
+          col = a.csr_cols[k0 + kb + lane];
+          val = a.csr_vals[k0 + kb + lane];
+        }
+        for (int q = 0; q < m; q += 4) {
+          float g0[4], g1[4], vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cq = __shfl_sync(kFull, col, (q + u) & 31);
+            vv[u] = __shfl_sync(kFull, val, (q + u) & 31);
+            const float* g = a.fold + (long long)cq * TD;
+            g0[u] = g[lane];
+            g1[u] = g[lane + 32];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v0 = fmaf(vv[u], g0[u], v0);
+            v1 = fmaf(vv[u], g1[u], v1);
+          }
+        }
+      }
+      const float* cr = ctx + (long long)s.src[r] * a.C;
+      const float cmine = lane < a.C ? cr[lane] : 0.f;
+#pragma unroll 4
+      for (int k = 0; k < a.C; ++k) {
+        const float* g = a.fold + (long long)(a.A + k) * TD;
+        const float cv = __shfl_sync(kFull, cmine, k & 31);
+        v0 = fmaf(cv, g[lane], v0);
+        v1 = fmaf(cv, g[lane + 32], v1);
+      }
+      if (add_pos) {
+        v0 += a.pos_table[(long long)s.pos[r] * TD + lane];
+        v1 += a.pos_table[(long long)s.pos[r] * TD + lane + 32];
+      }
+    }
+    Eo[r * TLD + lane] = v0;
+    Eo[r * TLD + lane + 32] = v1;
+  }
+  __syncthreads();
+}
+
+// Backward of embed_rows for the row gradients DE (tile, modified in place): accumulates d fold (GT rows, context
+// rows, cst), d pos, d joint_embed.weight[:, :64] and d items_embed.  Z, T2: scratch tiles.
+__device__ __forceinline__ void embed_rows_bwd(const TrainArgs& a, TrainSmem& s, const int* ids,
+                                               const float* __restrict__ ctx, bool is_profile, float* DE, float* Z,
+                                               float* T2) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int n = s.n;
+  tile_pass(DE, TR, [&](int r, int, float4& v) {                     // the `* mask` of :94
+    if (r >= n || ids[r] == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+  });
+  gather_items(a, s, ids, Z);
+  __syncthreads();
+  colsum_tile(s, DE, n, a.dfold + (long long)(a.A + a.C) * TD);      // d cst
+  for (int e = threadIdx.x; e < a.C * TD; e += TTHREADS) {            // d (context rows of GT)
+    const int k = e / TD, c = e % TD;
+    float acc = 0.f;
+    for (int r = 0; r < n; ++r)
+      if (ids[r] != 0) acc = fmaf(ctx[(long long)s.src[r] * a.C + k], DE[r * TLD + c], acc);
+    atomicAdd(a.dfold + (long long)(a.A + k) * TD + c, acc);
+  }
+  for (int r = w; r < n; r += TWARPS) {                               // d (attribute rows of GT), d pos
+    const int id = ids[r];
+    if (id == 0) continue;
+    const float d0 = DE[r * TLD + lane], d1 = DE[r * TLD + lane + 32];
+    const int k0 = a.csr_rowptr[id], nnz = a.csr_rowptr[id + 1] - k0;
+    for (int kb = 0; kb < nnz; kb += 32) {
+      const int m = min(32, nnz - kb);
+      int col = 0;
+      float val = 0.f;
+      if (lane < m) {
+        col = a.csr_cols[k0 + kb + lane];
+        val = a.csr_vals[k0 + kb + lane];
+      }
+      for (int q = 0; q < m; ++q) {
+        const int cq = __shfl_sync(kFull, col, q);
+        const float vq = __shfl_sync(kFull, val, q);
+        float* g = a.dfold + (long long)cq * TD;
+        atomicAdd(g + lane, vq * d0);
+        atomicAdd(g + lane + 32, vq * d1);
+      }
+    }
+    if (is_profile && a.gpos) {
+      atomicAdd(a.gpos + (long long)s.pos[r] * TD + lane, d0);
+      atomicAdd(a.gpos + (long long)s.pos[r] * TD + lane + 32, d1);
+    }
+  }
+  weight_grad(s, DE, Z, n, a.gWj, nullptr, a.ldj);                    // d Wj[:, :64]
+  __syncthreads();
+  load_w(s, a.Wj, a.ldj);
+  __syncthreads();
+  gemm_nn<TD>(DE, TLD, s.w, TLD, s.npad,
+              [&](int, int, int& lo, int& hi) { lo = 0; hi = TD; },
+              [&](int r, int cc, const float (&v)[4]) {
+                *reinterpret_cast<float4*>(T2 + r * TLD + cc) = make_float4(v[0], v[1], v[2], v[3]);
+              });
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * TD; e += TTHREADS) {              // d items_embed (padding_idx row gets none)
+    const int r = e / TD, c = e % TD;
+    const int id = ids[r];
+    if (id != 0) atomicAdd(a.gE + (long long)id * TD + c, a.sqrt_d * T2[r * TLD + c]);
+  }
+  __syncthreads();
+}
+
 // -------------------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const TrainArgs a) {
   CARCA_DYN_SMEM(unsigned char, raw);
@@ -676,9 +861,20 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
   for (int bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
     load_bin(a, s, bin);
     const int n = s.n;
-    {  // x0 = dropout(p_e)   (src/carca.py:416, site 0)
+    {  // x0 = dropout(p_e)   (src/carca.py:415-416, site 0)
       const DropCfg d0 = at_site(a.drop, 0u);
-      gather_rows(s, a.p_e, X, a.drop.p > 0.f ? &d0 : nullptr);
+      if (a.embed_mode) {
+        embed_rows(a, s, s.ids[0], a.p_c, a.pos_table != nullptr, X, QN);
+        if (a.drop.p > 0.f) {
+          tile_pass(X, n, [&](int r, int c4, float4& v) {
+            float f[4];
+            drop4(d0, (unsigned long long)s.src[r] * 16 + c4, f);
+            v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+          });
+        }
+      } else {
+        gather_rows(s, a.p_e, X, a.drop.p > 0.f ? &d0 : nullptr);
+      }
     }
     __syncthreads();
     for (int b = 0; b < a.n_blocks; ++b) {
@@ -741,7 +937,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
     }
     for (int t = 0; t < a.n_tuples; ++t) {
       float* O = X;
-      gather_rows(s, a.o_e[t], O, nullptr);                           // :426 (embedded by the caller)
+      if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, Qb);   // :426
+      else gather_rows(s, a.o_e[t], O, nullptr);                      // (embedded by the caller)
       __syncthreads();
       if (a.decoder == 1) {
         project(s, Qb, O, a.dec.wq, a.dec.bq);
@@ -857,7 +1054,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
         float* O = B0;
         float* Qt = B2;
         float* dQ = B7;
-        gather_rows(s, a.o_e[t], O, nullptr);
+        if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, dQ);
+        else gather_rows(s, a.o_e[t], O, nullptr);
         __syncthreads();
         project(s, Qt, O, a.dec.wq, a.dec.bq);
         attention_bwd_tile(s, cross_cfg(a, t), dQ, dKd, dVd, DS, Qt, Kd, Vd, Sb, Db, t > 0);
@@ -866,7 +1064,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
         // d o = dQ WQ (+ ds through the residual) -> d_oe rows
         if (a.residual_ca) project_bwd(s, DS, dQ, a.dec.wq, true);
         else project_bwd(s, DS, dQ, a.dec.wq, false);
-        scatter_rows(s, a.d_oe[t], DS, nullptr);
+        if (a.embed_mode) embed_rows_bwd(a, s, s.ids[1 + t], a.o_c[t], false, DS, B0, B2);
+        else scatter_rows(s, a.d_oe[t], DS, nullptr);
         __syncthreads();
       }
       // keys / values: PE = LN_f(x_nb) recomputed
@@ -895,7 +1094,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       __syncthreads();
       for (int t = 0; t < a.n_tuples; ++t) {
         float* O = B3;
-        gather_rows(s, a.o_e[t], O, nullptr);
+        if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, B4);
+        else gather_rows(s, a.o_e[t], O, nullptr);
         __syncthreads();
         for (int r = w; r < n; r += TWARPS) {
           const float z = row_dot(O + r * TLD, PE + r * TLD, lane);
@@ -908,7 +1108,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
           O[r * TLD + lane + 32] = g * PE[r * TLD + lane + 32];
         }
         __syncthreads();
-        scatter_rows(s, a.d_oe[t], O, nullptr);
+        if (a.embed_mode) embed_rows_bwd(a, s, s.ids[1 + t], a.o_c[t], false, O, B4, B5);
+        else scatter_rows(s, a.d_oe[t], O, nullptr);
         __syncthreads();
       }
       ln_bwd_rows(s, DX, DPE, XF, n, a.fn_g, a.g_fn_g, a.g_fn_b, false);
@@ -1020,7 +1221,19 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
     // d p_e = d x0 through the embedding dropout (site 0)
     {
       const DropCfg d0 = at_site(a.drop, 0u);
-      scatter_rows(s, a.d_pe, DX, a.drop.p > 0.f ? &d0 : nullptr);
+      if (a.embed_mode) {
+        if (a.drop.p > 0.f) {
+          tile_pass(DX, n, [&](int r, int c4, float4& v) {
+            float f[4];
+            drop4(d0, (unsigned long long)s.src[r] * 16 + c4, f);
+            v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+          });
+          __syncthreads();
+        }
+        embed_rows_bwd(a, s, s.ids[0], a.p_c, true, DX, B1, B2);
+      } else {
+        scatter_rows(s, a.d_pe, DX, a.drop.p > 0.f ? &d0 : nullptr);
+      }
     }
     __syncthreads();
   }

@@ -421,72 +421,142 @@ class CrossScoreFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------- fused training core
+class _FlatZeros:
+    """Carves zero-initialised gradient tensors out of ONE zero-filled buffer (one fill launch instead of one
+    per parameter)."""
+
+    def __init__(self, shapes, device):
+        sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh in shapes]      # 16-byte aligned pieces
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.views, off = [], 0
+        for sh, n in zip(shapes, sizes):
+            self.views.append(self.flat[off:off + int(torch.Size(sh).numel())].view(sh))
+            off += n
+
+
 class TrainCoreFn(torch.autograd.Function):
-    """src/carca.py:416-431 in train mode (dropout, encoder blocks, final LayerNorm, decoder per target tuple)
-    -> carca_train_core_fwd / _bwd: one forward and one backward kernel over the ACTIVE positions only."""
+    """src/carca.py:415-431 in train mode (dropout, encoder blocks, final LayerNorm, decoder per target tuple, and
+    optionally AllEmbedding itself through folded tables) -> carca_train_core_fwd / _bwd: one forward and one
+    backward kernel over the ACTIVE positions only.
+
+    emb is None: p_e / o_e* are the embedded rows (any Embedding module) and params = block params, norm, decoder.
+    emb = (table, p_c, o_c0, o_c1, has_pos): p_e / o_e* are None, the kernels embed the rows themselves and params
+    starts with AllEmbedding's E, Wf, bf, Wj, bj (, pos)."""
 
     @staticmethod
-    def forward(ctx, p_e, o_e0, o_e1, p_x, o_x0, o_x1, cfg, *params):
+    def forward(ctx, p_e, o_e0, o_e1, p_x, o_x0, o_x1, emb, cfg, *params):
         N.require_device(p_e, o_e0, o_e1, p_x, o_x0, o_x1, *params)
         H, n_blocks, decoder_kind, residual_sa, residual_ca, p_drop, seed = cfg
-        n_tuples = 1 if o_e1 is None else 2
-        p_e, o_e0 = as_f32(p_e), as_f32(o_e0)
-        o_e1 = None if o_e1 is None else as_f32(o_e1)
+        n_tuples = 1 if o_x1 is None else 2
         p_x, o_x0 = as_ids(p_x), as_ids(o_x0)
         o_x1 = None if o_x1 is None else as_ids(o_x1)
         params = tuple(_c(t) for t in params)
-        B, L, d = p_e.shape
-        dev = p_e.device
+        B, L = p_x.shape
+        dev = params[0].device
+        L_ = N.lib()
+        c = N.TrainCore()
+        keep = []
+        n_emb = 0
+        if emb is not None:
+            table, p_c, o_c0, o_c1, has_pos = emb
+            N.require_device(p_c, o_c0, o_c1)
+            n_emb = 6 if has_pos else 5
+            E, Wf, bf, Wj, bj = params[:5]
+            pos = params[5] if has_pos else None
+            Cn = p_c.shape[-1]
+            prm = _embed_params(E, Wf, None, bf, Wj, bj, pos, Wf.shape[1] - Cn, Cn)
+            src = _attr_source(table, None)
+            p_c, o_c0 = as_f32(p_c), as_f32(o_c0)
+            o_c1 = None if o_c1 is None else as_f32(o_c1)
+            fold = torch.empty(L_.carca_train_core_fold_floats(C.byref(prm)), dtype=torch.float32, device=dev)
+            c.embed, c.attrs = C.pointer(prm), C.pointer(src)
+            c.p_c, c.fold = N.f32p(p_c), fold.data_ptr()
+            c.o_c[0] = N.f32p(o_c0)
+            if n_tuples == 2:
+                c.o_c[1] = N.f32p(o_c1)
+            keep += [prm, src, table]
+            tensors = (p_c, o_c0, o_c1, fold)
+        else:
+            p_e, o_e0 = as_f32(p_e), as_f32(o_e0)
+            o_e1 = None if o_e1 is None else as_f32(o_e1)
+            c.p_e = N.f32p(p_e)
+            c.o_e[0] = N.f32p(o_e0)
+            if n_tuples == 2:
+                c.o_e[1] = N.f32p(o_e1)
+            tensors = (p_e, o_e0, o_e1, None)
+        core = params[n_emb:]
         nbp = len(N.BLOCK_PARAM_NAMES)
         blocks = (N.BlockParams * max(n_blocks, 1))()
         for b in range(n_blocks):
-            blocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, params[b * nbp:(b + 1) * nbp])
-        rest = params[n_blocks * nbp:]
-        c = N.TrainCore()
+            blocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, core[b * nbp:(b + 1) * nbp])
+        rest = core[n_blocks * nbp:]
         c.B, c.L, c.n_heads, c.n_blocks, c.n_tuples = B, L, int(H), int(n_blocks), n_tuples
         c.decoder_kind, c.residual_sa, c.residual_ca = int(decoder_kind), int(bool(residual_sa)), int(bool(residual_ca))
         c.p_drop, c.seed = float(p_drop), int(seed)
-        c.p_x, c.p_e = N.i32p(p_x), N.f32p(p_e)
-        c.o_x[0], c.o_e[0] = N.i32p(o_x0), N.f32p(o_e0)
+        c.p_x = N.i32p(p_x)
+        c.o_x[0] = N.i32p(o_x0)
         if n_tuples == 2:
-            c.o_x[1], c.o_e[1] = N.i32p(o_x1), N.f32p(o_e1)
+            c.o_x[1] = N.i32p(o_x1)
         c.blocks = blocks
         c.norm_g, c.norm_b = N.f32p(rest[0]), N.f32p(rest[1])
         if decoder_kind == 1:
             c.cross = _struct(N.CrossParams, N.CROSS_PARAM_NAMES, rest[2:2 + len(N.CROSS_PARAM_NAMES)])
-        L_ = N.lib()
         rows = torch.empty(L_.carca_train_core_rows_ints(B), dtype=torch.int32, device=dev)
         saved = torch.empty(L_.carca_train_core_saved_floats(B, int(n_blocks), n_tuples), dtype=torch.float32,
                             device=dev)
         c.rows, c.saved = rows.data_ptr(), saved.data_ptr()
         y = torch.empty((B, n_tuples * L), dtype=torch.float32, device=dev)
         N.call("carca_train_core_fwd", N.f32p(y), n_tuples * L, C.byref(c), N.stream())
-        ctx.save_for_backward(p_e, o_e0, o_e1, p_x, o_x0, o_x1, rows, saved, *params)
-        ctx.core, ctx.blocks, ctx.n_tuples, ctx.n_blocks, ctx.decoder_kind = c, blocks, n_tuples, int(n_blocks), int(decoder_kind)
+        ctx.save_for_backward(p_x, o_x0, o_x1, rows, saved, *tensors, *params)
+        ctx.core, ctx.keep = c, (blocks, keep)
+        ctx.cfg = (n_tuples, int(n_blocks), int(decoder_kind), n_emb, emb is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         st = ctx.saved_tensors
-        p_e, o_e0, o_e1 = st[0], st[1], st[2]
-        params = st[8:]
-        c, n_blocks = ctx.core, ctx.n_blocks
+        t0, t1, t2 = st[5], st[6], st[7]          # p_e, o_e0, o_e1  or  p_c, o_c0, o_c1
+        params = st[9:]
+        c = ctx.core
+        n_tuples, n_blocks, decoder_kind, n_emb, embed_mode = ctx.cfg
         nbp = len(N.BLOCK_PARAM_NAMES)
         dy = as_f32(dy)
-        grads = tuple(torch.zeros_like(t) for t in params)
+        dev = dy.device
+        # gradients that are accumulated with atomics come out of one zero-filled buffer; the others are written whole
+        core = params[n_emb:]
+        shapes = [t.shape for t in core]
+        if embed_mode:
+            E, Wf, bf, Wj, bj = params[:5]
+            shapes += [E.shape, Wj.shape] + ([params[5].shape] if n_emb == 6 else [])
+            shapes.append((int(N.lib().carca_train_core_fold_floats(c.embed)),))
+        else:
+            shapes += [t0.shape, t1.shape] + ([t2.shape] if t2 is not None else [])
+        z = _FlatZeros(shapes, dev)
+        grads = z.views[:len(core)]
+        extra = z.views[len(core):]
         gblocks = (N.BlockParams * max(n_blocks, 1))()
         for b in range(n_blocks):
             gblocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, grads[b * nbp:(b + 1) * nbp])
         rest = grads[n_blocks * nbp:]
         gcross = None
-        if ctx.decoder_kind == 1:
+        if decoder_kind == 1:
             gcross = C.byref(_struct(N.CrossParams, N.CROSS_PARAM_NAMES, rest[2:2 + len(N.CROSS_PARAM_NAMES)]))
-        d_pe = torch.zeros_like(p_e)
-        d_o0 = torch.zeros_like(o_e0)
-        d_o1 = None if o_e1 is None else torch.zeros_like(o_e1)
+        if embed_mode:
+            gE, gWj = extra[0], extra[1]
+            gpos = extra[2] if n_emb == 6 else None
+            d_fold = extra[-1]
+            gWf, gbf, gbj = torch.empty_like(Wf), torch.empty_like(bf), torch.empty_like(bj)
+            gemb = _struct(N.EmbedGrads, ("items_embed", "feats_w", "feats_b", "joint_w", "joint_b", "pos"),
+                           (gE, gWf, gbf, gWj, gbj, gpos))
+            N.call("carca_train_core_bwd", None, None, None, gblocks, N.f32p(rest[0]), N.f32p(rest[1]), gcross,
+                   C.byref(gemb), N.f32p(d_fold), N.f32p(dy), dy.shape[1], C.byref(c), N.stream())
+            emb_grads = (gE, gWf, gbf, gWj, gbj) + ((gpos,) if n_emb == 6 else ())
+            return (None,) * 8 + emb_grads + tuple(grads)
+        d_pe, d_o0 = extra[0], extra[1]
+        d_o1 = extra[2] if t2 is not None else None
         N.call("carca_train_core_bwd", N.f32p(d_pe), N.f32p(d_o0), N.f32p(d_o1), gblocks, N.f32p(rest[0]),
-               N.f32p(rest[1]), gcross, N.f32p(dy), dy.shape[1], C.byref(c), N.stream())
-        return (d_pe, d_o0, d_o1, None, None, None, None, *grads)
+               N.f32p(rest[1]), gcross, None, None, N.f32p(dy), dy.shape[1], C.byref(c), N.stream())
+        return (d_pe, d_o0, d_o1, None, None, None, None, None, *grads)
 
 
 # ------------------------------------------------------------------------------- loss / metrics

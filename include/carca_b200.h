@@ -274,20 +274,35 @@ typedef struct {
   int32_t* rows;                    /* workspace, carca_train_core_rows_ints(B) int32 */
   float* saved;                     /* workspace, carca_train_core_saved_floats(...) floats: activations kept by
                                        the forward for the backward */
+  /* Optional in-kernel AllEmbedding (src/carca.py:85-95) — embed != NULL: p_e / o_e are not read; the kernels
+   * embed every row set themselves from ids + context through tables folded once per call,
+   *   GT = (Wj[:, d:] Wf)^T [A + C, 64],  cst = Wj[:, d:] bf + bj,
+   *   e = mask * (Wj[:, :d] sqrt(d) E[x] + sum_attr val GT[attr] + sum_k c_k GT[A + k] + cst (+ pos)),
+   * an exact re-association of the two bias-only linears (as in carca_eval_prepare); their gradients are
+   * un-folded by three GEMMs after the backward kernel.  attrs must be CARCA_ATTR_CSR.                      */
+  const carca_embed_params* embed;
+  const carca_attr_source* attrs;
+  const float* p_c;                 /* [B, L, C] */
+  const float* o_c[2];              /* [B, L, C] per tuple */
+  float* fold;                      /* workspace, carca_train_core_fold_floats(embed) floats */
 } carca_train_core;
 
 int64_t carca_train_core_rows_ints(int B);
 int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples);
+int64_t carca_train_core_fold_floats(const carca_embed_params* embed);
 
 /* y [B, ldy]: tuple t's probabilities at columns t*L .. t*L + L - 1 (the cat of src/carca.py:431) */
 int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void* stream);
 
 /* Backward of carca_train_core_fwd for the upstream gradient dy [B, ldy] (call after the forward with the same
- * `c`, whose workspaces still hold the forward's row maps and activations).  d_pe / d_oe[t] [B, L, 64] and
- * every parameter gradient are ACCUMULATED (caller zero-initialises; g_blocks is a HOST array).            */
+ * `c`, whose workspaces still hold the forward's row maps, activations and folded tables).  Parameter gradients
+ * are ACCUMULATED (caller zero-initialises; g_blocks is a HOST array); d_pe / d_oe[t] [B, L, 64] are written at
+ * the active positions only (caller zero-initialises) and unused when c->embed != NULL.  With c->embed:
+ * g_embed receives the AllEmbedding gradients (items_embed, joint_w and pos accumulated — zero-initialise;
+ * feats_w, feats_b, joint_b overwritten) and d_fold is a workspace of carca_train_core_fold_floats floats.  */
 int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_block_grads* g_blocks, float* g_norm_g,
-                         float* g_norm_b, const carca_cross_grads* g_cross, const float* dy, int64_t ldy,
-                         const carca_train_core* c, void* stream);
+                         float* g_norm_b, const carca_cross_grads* g_cross, const carca_embed_grads* g_embed,
+                         float* d_fold, const float* dy, int64_t ldy, const carca_train_core* c, void* stream);
 
 /* ------------------------------------------------------------------ loss */
 /* sums[0] += sum(ell * mask), sums[1] += sum(mask); replaces src/carca.py:442-443 numerators.
