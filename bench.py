@@ -564,19 +564,25 @@ def time_device_pipeline(model, shape, args, dev):
 
 def time_train(shape, args, dev, table):
     """fwd + BCE + bwd + Adam seqs/s (src/train.py:84-97), dropout 0.5, at the reference batch size: the whole
-    step body replayed as one CUDA graph (carca_replication_b200/graph.py) and, for comparison, eagerly;
-    plus the eager step at a large batch (GPU-bound regime)."""
+    step body replayed as one CUDA graph (carca_replication_b200/graph.py).  Default path: the fused training
+    kernels (csrc/fused_train.cuh, embeddings folded in) + FusedAdam; for comparison the same step with the stock
+    torch.optim.Adam, eagerly, on the per-op kernels, and at a large batch (throughput regime)."""
     import carca_replication_b200 as cb
+    from carca_replication_b200 import _native as N
     from carca_replication_b200 import synth
     from carca_replication_b200.graph import GraphedTrainStep
 
     L = shape.seq_len
     loss_fn = cb.BinaryCrossEntropy()
 
-    def setup(Bt, capturable):
+    def setup(Bt, optimizer="fused", fused_kernels=True):
         model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
         model.embeds.set_attr_table(table)
-        optim = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), capturable=capturable)
+        model.use_fused_train = fused_kernels
+        if optimizer == "fused":
+            optim = cb.FusedAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
+        else:
+            optim = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), capturable=optimizer == "capturable")
         batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + i).items()} for i in range(4)]
         return model, optim, batches
 
@@ -588,35 +594,58 @@ def time_train(shape, args, dev, table):
         loss = loss_fn.forward(y, b["y_true"], cb.get_mask(o_x))
         loss.backward()
         optim.step()
-        return loss
+        return loss.detach()
 
     def clock(fn, n):
         for i in range(3):
             fn(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        n0 = N.lib().carca_launch_count()
         e0.record()
         for i in range(n):
             loss = fn(i)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n, float(loss.item())
+        return e0.elapsed_time(e1) / n, float(loss.item()), (N.lib().carca_launch_count() - n0) / n
+
+    def graphed(Bt, n, **kw):
+        model, optim, batches = setup(Bt, **kw)
+        step = GraphedTrainStep(model, optim, batches[0])
+        ms, loss, _ = clock(lambda i: step(batches[i % 4]), n)
+        return ms, loss
 
     n = max(args.steps, 5)
-    Bt = args.train_batch
-    model, optim, batches = setup(Bt, True)
-    step = GraphedTrainStep(model, optim, batches[0])
-    ms_g, loss_g = clock(lambda i: step(batches[i % 4]), 4 * n)
-    model, optim, batches = setup(Bt, False)
-    ms_e, loss_e = clock(lambda i: eager_step(model, optim, batches[i % 4]), n)
-    Bl = 4096
-    model, optim, batches = setup(Bl, False)
-    ms_l, _ = clock(lambda i: eager_step(model, optim, batches[i % 4]), n)
+    Bt, Bl = args.train_batch, 4096
+    ms_g, loss_g = graphed(Bt, 4 * n)
+    ms_s, _ = graphed(Bt, 4 * n, optimizer="capturable")
+    ms_p, _ = graphed(Bt, 2 * n, optimizer="capturable", fused_kernels=False)
+    ms_l, _ = graphed(Bl, 2 * n)
+    ms_lp, _ = graphed(Bl, n, optimizer="capturable", fused_kernels=False)
+    model, optim, batches = setup(Bt, optimizer="stock")
+    ms_e, loss_e, launches = clock(lambda i: eager_step(model, optim, batches[i % 4]), n)
+    # algorithmic work of one train step per sequence: 3x the forward FLOPs (fwd + 2x in bwd) with
+    # 2L targets; all L positions counted as the reference executes them
+    d, g, nb, C = shape.d, shape.g, shape.n_blocks, shape.n_ctx
+    T = 2 * L
+    fwd = 2 * (L + T) * (g + d) * d + nb * (10 * L * d * d + 4 * L * L * d)
+    fwd += (2 * T * d * d + 4 * L * d * d + 4 * T * L * d + 2 * T * d) if args.decoder == "ca" else 2 * T * d
+    flops = 3.0 * fwd
     return {"value": Bt / (ms_g * 1e-3), "unit": "seqs/s", "batch_per_gpu": Bt, "ms_per_step": ms_g,
-            "mode": "whole step (zero_grad, fwd, BCE, bwd, Adam) replayed as one CUDA graph", "final_loss": loss_g,
-            "optimizer": "torch.optim.Adam (stock, capturable)", "dropout": 0.5,
-            "eager": {"value": Bt / (ms_e * 1e-3), "ms_per_step": ms_e, "final_loss": loss_e},
-            "eager_large_batch": {"value": Bl / (ms_l * 1e-3), "batch_per_gpu": Bl, "ms_per_step": ms_l}}
+            "mode": "whole step (zero_grad, fwd, BCE, bwd, Adam) replayed as one CUDA graph; fused training kernels "
+                    "(active positions only, embeddings folded in) + FusedAdam", "final_loss": loss_g,
+            "optimizer": "carca_replication_b200.FusedAdam (one launch; torch.optim.Adam update rule)", "dropout": 0.5,
+            "algorithmic_tflops": flops * Bt / (ms_g * 1e-3) / 1e12,
+            "flops_per_seq": flops,
+            "stock_adam": {"value": Bt / (ms_s * 1e-3), "ms_per_step": ms_s,
+                           "what": "same graph with torch.optim.Adam(capturable=True)"},
+            "per_op_kernels": {"value": Bt / (ms_p * 1e-3), "ms_per_step": ms_p,
+                               "what": "same graph on the per-op kernels (use_fused_train=False), stock Adam"},
+            "eager": {"value": Bt / (ms_e * 1e-3), "ms_per_step": ms_e, "final_loss": loss_e,
+                      "launches_of_ours_per_step": launches, "what": "no graph, stock Adam"},
+            "large_batch": {"value": Bl / (ms_l * 1e-3), "batch_per_gpu": Bl, "ms_per_step": ms_l,
+                            "algorithmic_tflops": flops * Bl / (ms_l * 1e-3) / 1e12,
+                            "per_op_kernels": {"value": Bl / (ms_lp * 1e-3), "ms_per_step": ms_lp}}}
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ from .carca import (  # noqa: F401
     SelfAttentionBlock, WeightedDotProduct,
 )
 from .knn import KNN  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 from .train import compute_HR, compute_NDCG, evaluate  # noqa: F401
 from .utils import get_mask, to  # noqa: F401
 
@@ -20,5 +21,5 @@ __all__ = [
     "CARCA", "AllEmbedding", "AttrCtxEmbedding", "AttrEmbedding", "IdEmbedding", "MLPIdEmbedding",
     "WeightedDotProduct", "KNN", "BinaryCrossEntropy", "CrossAttentionBlock", "DotProduct", "IdentityEncoding",
     "LearnableEncoding", "MultiHeadAttention", "PositionalEncoding", "SelfAttentionBlock", "ItemAttrTable",
-    "compute_HR", "compute_NDCG", "evaluate", "get_mask", "to",
+    "compute_HR", "compute_NDCG", "evaluate", "get_mask", "to", "FusedAdam",
 ]

@@ -70,6 +70,10 @@ class TrainCore(C.Structure):
                 ("attrs", C.POINTER(AttrSource)), ("p_c", vp), ("o_c", vp * 2), ("fold", vp)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("step", vp), ("numel", i64)]
+
+
 class Interactions(C.Structure):
     _fields_ = [("rowptr", vp), ("items", vp), ("ctx", vp), ("n_users", i32), ("n_ctx", i32)]
 
@@ -123,6 +127,7 @@ SIGNATURES = {
     "carca_bce_finalize": [vp, vp, vp],
     "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
     "carca_rank_metrics": [vp, vp, vp, vp, i32, i32, i64, i64, i32, vp],
+    "carca_adam_step": [P(AdamTensor), i32, f32, f32, f32, f32, f32, vp],
     "carca_build_eval_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, i32, i32, u64, vp],
     "carca_build_train_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, u64, vp],
     "carca_eval_plan_floats": [P(ModelParams)],

@@ -14,6 +14,7 @@
 #include "fused_train.cuh"
 #include "gemm.cuh"
 #include "layernorm.cuh"
+#include "optim.cuh"
 #include "score.cuh"
 #include "variants.cuh"
 
@@ -617,6 +618,7 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
   a.B = c->B; a.L = c->L; a.H = c->n_heads; a.n_blocks = c->n_blocks; a.n_tuples = c->n_tuples;
   a.decoder = c->decoder_kind; a.residual_sa = c->residual_sa; a.residual_ca = c->residual_ca;
   a.drop = drop_cfg(c->p_drop, c->seed, 0u);
+  a.n_sms = 148;
   a.p_x = c->p_x; a.p_e = c->p_e;
   for (int t = 0; t < c->n_tuples; ++t) {
     CARCA_REQUIRE(c->o_x[t] != nullptr, "train_core: target tuple %d missing", t);
@@ -684,7 +686,10 @@ int carca_train_core_fwd(float* y, int64_t ldy, const carca_train_core* c, void*
     g.transB = 1; g.ldb = w->d + w->g;
     g.ldc = TD;
     TRY(launch_gemm(g, st));
-    TRY(linear(c->fold + (long long)AC * TD, w->feats_b, w->joint_w + w->d, w->joint_b, 1, TD, w->g, w->d + w->g, st));
+    auto kc = fold_cst_kernel;
+    CARCA_LAUNCH(kc, dim3(8), dim3(256), 0, st, c->fold + (long long)AC * TD, w->joint_w, w->feats_b, w->joint_b, w->d,
+                 w->g);
+    TRY(check_launch("fold_cst"));
   }
   cudaMemsetAsync(a.n_bins, 0, 4 * sizeof(int), st);
   cudaMemsetAsync(a.row_src, 0xFF, sizeof(int) * (size_t)a.B * TR, st);
@@ -755,9 +760,10 @@ int carca_train_core_bwd(float* d_pe, float* d_oe0, float* d_oe1, const carca_bl
       g.accumulate = 1;
       TRY(launch_gemm(g, st));
     }
-    TRY(linear_dw(g_embed->joint_w + d, dcst, w->feats_b, 1, TD, gd, d + gd, gd, st));   // += dcst (x) bf
-    TRY(linear_dx(g_embed->feats_b, dcst, w->joint_w + d, 1, TD, gd, d + gd, st));       // d bf = Wj_q^T dcst
-    cudaMemcpyAsync(g_embed->joint_b, dcst, sizeof(float) * TD, cudaMemcpyDeviceToDevice, st);   // d bj = dcst
+    auto ku = unfold_cst_kernel;   // d Wj[:, d:] += dcst (x) bf;  d bf = Wj[:, d:]^T dcst;  d bj = dcst
+    CARCA_LAUNCH(ku, dim3(d), dim3(256), 0, st, g_embed->joint_w, g_embed->feats_b, g_embed->joint_b, dcst, w->joint_w,
+                 w->feats_b, d, gd);
+    TRY(check_launch("unfold_cst"));
   }
   return 0;
 }
@@ -795,6 +801,40 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
   CARCA_LAUNCH(kern, dim3(grid), dim3(256), 0, S(stream), acc, first_rank, y_pred, y_true, B, T, (long long)ldy,
                (long long)ldt, k);
   return check_launch("rank_metrics");
+}
+
+// ------------------------------------------------------------------------------------ optimizer
+int carca_adam_step(const carca_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, void* stream) {
+  cudaStream_t st = S(stream);
+  CARCA_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || tensors), "adam_step: missing arguments");
+  for (int first = 0; first < n_tensors; first += kAdamMaxTensors) {
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_tensors = min(kAdamMaxTensors, n_tensors - first);
+    int chunks = 0;
+    for (int i = 0; i < a.n_tensors; ++i) {
+      const carca_adam_tensor& t = tensors[first + i];
+      CARCA_REQUIRE(t.param && t.grad && t.exp_avg && t.exp_avg_sq && t.step && t.numel >= 0,
+                    "adam_step: tensor %d incomplete", first + i);
+      a.p[i] = t.param; a.g[i] = t.grad; a.m[i] = t.exp_avg; a.v[i] = t.exp_avg_sq; a.step[i] = t.step;
+      a.n[i] = t.numel;
+      a.chunk0[i] = chunks;
+      chunks += (int)ceil_div_ll(t.numel, kAdamChunk);
+    }
+    a.chunk0[a.n_tensors] = chunks;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    {
+      auto k = adam_tick_kernel;
+      CARCA_LAUNCH(k, dim3(1), dim3(kAdamMaxTensors), 0, st, a);
+      TRY(check_launch("adam_tick"));
+    }
+    if (chunks == 0) continue;
+    auto k = adam_step_kernel;
+    CARCA_LAUNCH(k, dim3(chunks), dim3(256), 0, st, a);
+    TRY(check_launch("adam_step"));
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------ batch construction

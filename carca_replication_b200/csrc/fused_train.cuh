@@ -50,6 +50,7 @@ constexpr int TI_TVALID0 = 1 << 17;   // tuple t: TI_TVALID0 << t
 
 struct TrainArgs {
   int B, L, H, n_blocks, n_tuples, decoder;   // decoder: 0 dot-product, 1 cross-attention
+  int n_sms;                                  // CTAs the bins should spread over (packing heuristic)
   int residual_sa, residual_ca;
   DropCfg drop;                               // p / seed / device seed word; the site is set per use
   const int* p_x;                             // [B, L]
@@ -134,9 +135,16 @@ __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
   }
   __syncthreads();
   if (t == 0) {
+    // bin capacity: 64 rows when there is enough work for every SM, fewer (>= 16) for small batches so the rows
+    // spread over more CTAs and each CTA's dependent chain of phases gets shorter; a user always fits (L <= 64)
+    int total = 0;
+    for (int q = 0; q < users; ++q) total += cnt[q];
+    const long long est = (long long)total * a.B / users;            // rows of the whole batch, extrapolated
+    int cap = (int)((est / a.n_sms + 7) / 8 * 8);
+    cap = cap < 16 ? 16 : (cap > TR ? TR : cap);
     int bin = 0, fill = 0;
     for (int q = 0; q < users; ++q) {
-      if (fill + cnt[q] > TR) {
+      if (fill > 0 && fill + cnt[q] > cap) {
         ++bin;
         fill = 0;
       }
@@ -1236,6 +1244,40 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       }
     }
     __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- fold helpers
+// cst[c] = sum_g Wj[c][d + g] bf[g] + bj[c]: the constant row of the folded embedding tables (one warp per output)
+__global__ void __launch_bounds__(256) fold_cst_kernel(float* __restrict__ cst, const float* __restrict__ Wj,
+                                                       const float* __restrict__ bf, const float* __restrict__ bj,
+                                                       int d, int g) {
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  for (int c = blockIdx.x * (blockDim.x / kWarp) + w; c < d; c += gridDim.x * (blockDim.x / kWarp)) {
+    const float* row = Wj + (long long)c * (d + g) + d;
+    float acc = 0.f;
+    for (int k = lane; k < g; k += kWarp) acc = fmaf(row[k], bf[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) cst[c] = acc + bj[c];
+  }
+}
+
+// Un-folds d cst: d bj = dcst; d bf[g] = sum_c dcst[c] Wj[c][d + g]; d Wj[c][d + g] += dcst[c] bf[g].
+// Grid: d blocks (one per c); block 0 also writes d bf and d bj.
+__global__ void __launch_bounds__(256) unfold_cst_kernel(float* __restrict__ gWj, float* __restrict__ gbf,
+                                                         float* __restrict__ gbj, const float* __restrict__ dcst,
+                                                         const float* __restrict__ Wj, const float* __restrict__ bf,
+                                                         int d, int g) {
+  const int c = blockIdx.x;
+  const float dc = dcst[c];
+  for (int k = threadIdx.x; k < g; k += blockDim.x) atomicAdd(gWj + (long long)c * (d + g) + d + k, dc * bf[k]);
+  if (c == 0) {
+    for (int k = threadIdx.x; k < g; k += blockDim.x) {
+      float acc = 0.f;
+      for (int cc = 0; cc < d; ++cc) acc = fmaf(dcst[cc], Wj[(long long)cc * (d + g) + d + k], acc);
+      gbf[k] = acc;
+    }
+    for (int k = threadIdx.x; k < d; k += blockDim.x) gbj[k] = dcst[k];
   }
 }
 

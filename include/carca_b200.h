@@ -314,6 +314,24 @@ int carca_bce_finalize(float* loss, const float* sums, void* stream);
 int carca_bce_bwd(float* dy, const float* grad_out, const float* sums, const float* y_pred,
                   const int32_t* y_true, const float* mask, int64_t n, float eps, void* stream);
 
+/* ------------------------------------------------------------------ optimizer */
+/* One Adam step over a list of parameter tensors in one launch (plus a one-thread counter tick):
+ * torch.optim.Adam as scripts/training.py:174 builds it and src/train.py:96 steps it (weight_decay is added to
+ * the gradient; no amsgrad):  g += wd p;  m += (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;
+ * p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  `tensors` is a HOST array (device pointers
+ * inside); `step` is the tensor's own device float counter t (torch keeps one per parameter), incremented by
+ * this call before the update, which makes the call CUDA-graph capturable.                                 */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* step;
+  int64_t numel;
+} carca_adam_tensor;
+int carca_adam_step(const carca_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, void* stream);
+
 /* ------------------------------------------------------------------ ranking metrics */
 /* acc[0] += hits@k, acc[1] += sum 1/log2(rank+2) over labelled candidates with rank < k,
  * acc[2] += B (fp64 device accumulators); replaces compute_HR / compute_NDCG,

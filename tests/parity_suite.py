@@ -288,3 +288,27 @@ def check_fused_train_vs_per_op(device, B=7, decoder="ca", p=0.3, heads=2, n_tup
     for k in g_m:
         e = grad_err(g_f[k], g_m[k], grad_floor(k))
         assert e < gtol, (k, e)
+
+
+def check_fused_adam(device, weight_decay=0.0, steps=5):
+    """FusedAdam (one launch, csrc/optim.cuh) vs torch.optim.Adam with the constructor arguments of
+    scripts/training.py:174 on tensors of awkward sizes (unaligned tails, > one 4096-element chunk)."""
+    g = torch.Generator().manual_seed(3)
+    shapes = [(5, 7), (4096,), (4097,), (3,), (64, 64, 1), (130, 64), (1,)]
+    ref = [torch.randn(s, generator=g).requires_grad_(True) for s in shapes]
+    ours = [t.detach().clone().to(device).requires_grad_(True) for t in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=weight_decay, betas=(0.9, 0.98))
+    o_ours = cb.FusedAdam(ours, lr=1e-3, weight_decay=weight_decay, betas=(0.9, 0.98))
+    for step in range(steps):
+        for a, b in zip(ref, ours):
+            gr = torch.randn(a.shape, generator=g) * (0.1 + step)
+            a.grad = gr.clone()
+            b.grad = None if (step == 1 and a.numel() == 3) else gr.to(device)    # a parameter without grad is skipped
+            if b.grad is None:
+                a.grad = None
+        o_ref.step()
+        o_ours.step()
+    for a, b in zip(ref, ours):
+        np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().numpy(), rtol=2e-5, atol=1e-7)
+    sd = o_ours.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}

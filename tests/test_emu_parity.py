@@ -68,3 +68,8 @@ def test_knn(emu_backend):
                                 dict(decoder="ca", p=0.3, B=9, all_valid=True)])
 def test_fused_train_vs_per_op_kernels(emu_backend, kw):
     S.check_fused_train_vs_per_op(emu_backend, **kw)
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_vs_torch(emu_backend, wd):
+    S.check_fused_adam(emu_backend, weight_decay=wd)

@@ -39,3 +39,8 @@ def test_train_forward_falls_back_to_per_op_kernels_outside_the_fused_range():
     x = torch.zeros(2, 12, dtype=torch.int32)
     assert tiny._fused_train_applies((x, None, None), [(x, None, None), (x, None, None)])
     assert not tiny._fused_train_applies((x, None, None), [(x[:, :5], None, None)])
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_vs_torch(wd):
+    S.check_fused_adam(DEV, weight_decay=wd)
