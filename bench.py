@@ -373,6 +373,8 @@ def run_ours(args):
     out["all_valid_profiles"] = {"value": users_per_step / (ms_full / 1e3), "unit": "users/s", "ms_per_step": ms_full,
                                  "what": "same step with all 50 profile positions valid (no padding to skip)"}
 
+    if world > 1 and not args.no_train:
+        out["train"] = time_train_dp(shape, args, dev, table, rank, world)
     if world == 1 and rank == 0:
         if not args.no_train:
             out["train"] = time_train(shape, args, dev, table)
@@ -646,6 +648,73 @@ def time_train(shape, args, dev, table):
             "large_batch": {"value": Bl / (ms_l * 1e-3), "batch_per_gpu": Bl, "ms_per_step": ms_l,
                             "algorithmic_tflops": flops * Bl / (ms_l * 1e-3) / 1e12,
                             "per_op_kernels": {"value": Bl / (ms_lp * 1e-3), "ms_per_step": ms_lp}}}
+
+
+def time_train_dp(shape, args, dev, table, rank, world):
+    """Data-parallel train step: every rank runs the fused step on its own `--train-batch` users
+    (weak scaling), the flat gradient buffer is all-reduced in place over NCCL (one collective per step, plus the
+    two BCE partial sums), FusedAdam steps the replicated weights.  Timed on the device, max over ranks; as one
+    CUDA graph per rank when NCCL capture works, eagerly otherwise."""
+    import torch.distributed as dist
+
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
+    from carca_replication_b200.parallel import UserDataParallel
+
+    L, Bt = shape.seq_len, args.train_batch
+    model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
+    model.embeds.set_attr_table(table)
+    dp = UserDataParallel(model)
+    optim = cb.FusedAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + 10 * rank + i).items()}
+               for i in range(4)]
+
+    def eager_step(b):
+        o_x, o_c = b["o_x"], b["o_c"]
+        optim.zero_grad()
+        y = model.forward(profile=(b["p_x"], None, b["p_c"]),
+                          targets=[(o_x[:, :L], None, o_c[:, :L]), (o_x[:, L:], None, o_c[:, L:])])
+        loss = dp.loss_fn.forward(y, b["y_true"], cb.get_mask(o_x))
+        loss.backward()
+        optim.step()
+        return loss.detach()
+
+    def clock(fn, n):
+        for i in range(3):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            loss = fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(loss.item())
+
+    n = max(args.steps, 5)
+    ms_e, loss_e = clock(lambda i: eager_step(batches[i % 4]), n)
+    out = {"unit": "seqs/s", "batch_per_gpu": Bt, "global_batch": Bt * world, "scaling": "weak",
+           "collective": "one in-place NCCL all-reduce of the flat gradient buffer per step + 2 floats of BCE sums",
+           "eager": {"value": world * Bt / (ms_e * 1e-3), "ms_per_step": ms_e, "final_loss": loss_e}}
+    ok = torch.ones(1, device=dev)
+    try:
+        step = GraphedTrainStep(model, optim, batches[0], loss_fn=dp.loss_fn)
+        ms_g, loss_g = clock(lambda i: step(batches[i % 4]), 4 * n)
+    except Exception as ex:  # noqa: BLE001 -- NCCL capture is best effort; the eager number stands
+        ok.zero_()
+        out["graph_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() > 0:
+        out.update({"value": world * Bt / (ms_g * 1e-3), "ms_per_step": ms_g, "final_loss": loss_g,
+                    "mode": "whole data-parallel step (incl. the NCCL all-reduce) replayed as one CUDA graph per rank"})
+    else:
+        out.update({"value": out["eager"]["value"], "ms_per_step": ms_e, "mode": "eager"})
+    return out
 
 
 if __name__ == "__main__":

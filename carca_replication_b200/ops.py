@@ -522,18 +522,18 @@ class TrainCoreFn(torch.autograd.Function):
         nbp = len(N.BLOCK_PARAM_NAMES)
         dy = as_f32(dy)
         dev = dy.device
-        # gradients that are accumulated with atomics come out of one zero-filled buffer; the others are written whole
+        # every gradient comes out of ONE zero-filled buffer (one fill launch; atomics accumulate into it), the
+        # parameter gradients first and contiguous so data parallelism can all-reduce the buffer in place
         core = params[n_emb:]
-        shapes = [t.shape for t in core]
+        shapes = [t.shape for t in params[:n_emb]] + [t.shape for t in core]
         if embed_mode:
-            E, Wf, bf, Wj, bj = params[:5]
-            shapes += [E.shape, Wj.shape] + ([params[5].shape] if n_emb == 6 else [])
             shapes.append((int(N.lib().carca_train_core_fold_floats(c.embed)),))
         else:
             shapes += [t0.shape, t1.shape] + ([t2.shape] if t2 is not None else [])
         z = _FlatZeros(shapes, dev)
-        grads = z.views[:len(core)]
-        extra = z.views[len(core):]
+        egrads = z.views[:n_emb]
+        grads = z.views[n_emb:n_emb + len(core)]
+        extra = z.views[n_emb + len(core):]
         gblocks = (N.BlockParams * max(n_blocks, 1))()
         for b in range(n_blocks):
             gblocks[b] = _struct(N.BlockParams, N.BLOCK_PARAM_NAMES, grads[b * nbp:(b + 1) * nbp])
@@ -542,16 +542,14 @@ class TrainCoreFn(torch.autograd.Function):
         if decoder_kind == 1:
             gcross = C.byref(_struct(N.CrossParams, N.CROSS_PARAM_NAMES, rest[2:2 + len(N.CROSS_PARAM_NAMES)]))
         if embed_mode:
-            gE, gWj = extra[0], extra[1]
-            gpos = extra[2] if n_emb == 6 else None
-            d_fold = extra[-1]
-            gWf, gbf, gbj = torch.empty_like(Wf), torch.empty_like(bf), torch.empty_like(bj)
+            gE, gWf, gbf, gWj, gbj = egrads[:5]
+            gpos = egrads[5] if n_emb == 6 else None
+            d_fold = extra[0]
             gemb = _struct(N.EmbedGrads, ("items_embed", "feats_w", "feats_b", "joint_w", "joint_b", "pos"),
                            (gE, gWf, gbf, gWj, gbj, gpos))
             N.call("carca_train_core_bwd", None, None, None, gblocks, N.f32p(rest[0]), N.f32p(rest[1]), gcross,
                    C.byref(gemb), N.f32p(d_fold), N.f32p(dy), dy.shape[1], C.byref(c), N.stream())
-            emb_grads = (gE, gWf, gbf, gWj, gbj) + ((gpos,) if n_emb == 6 else ())
-            return (None,) * 8 + emb_grads + tuple(grads)
+            return (None,) * 8 + tuple(egrads) + tuple(grads)
         d_pe, d_o0 = extra[0], extra[1]
         d_o1 = extra[2] if t2 is not None else None
         N.call("carca_train_core_bwd", N.f32p(d_pe), N.f32p(d_o0), N.f32p(d_o1), gblocks, N.f32p(rest[0]),

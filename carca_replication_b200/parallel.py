@@ -71,6 +71,12 @@ class UserDataParallel:
         if self.world == 1:
             return
         dev = self.params[0].device
+        flat = self._shared_grad_buffer()
+        if flat is not None:
+            # the fused training step (ops.TrainCoreFn) produces every gradient inside one flat buffer:
+            # all-reduce it in place — no bucket copies
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return
         if self._bucket is None or self._bucket.device != dev:
             self._bucket = torch.empty(sum(self._sizes), dtype=torch.float32, device=dev)
         views = self._bucket.split(self._sizes)
@@ -85,6 +91,21 @@ class UserDataParallel:
                 p.grad = v.reshape(p.shape).clone()
             else:
                 p.grad.copy_(v.reshape(p.shape))
+
+    def _shared_grad_buffer(self) -> Optional[Tensor]:
+        """The flat tensor spanning all gradients when they are views of one storage (else None)."""
+        grads = [p.grad for p in self.params]
+        if any(g is None or not g.is_contiguous() or g.dtype != torch.float32 for g in grads):
+            return None
+        storage = grads[0].untyped_storage()
+        base = storage.data_ptr()
+        if any(g.untyped_storage().data_ptr() != base for g in grads[1:]):
+            return None
+        lo = min(g.storage_offset() for g in grads)
+        hi = max(g.storage_offset() + g.numel() for g in grads)
+        if hi - lo > 2 * sum(self._sizes):                  # mostly foreign data: not worth reducing
+            return None
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(storage, lo, (hi - lo,))
 
     def _allreduce_sum(self, t: Tensor) -> None:
         if self.world > 1:
