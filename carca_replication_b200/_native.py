@@ -117,6 +117,7 @@ SIGNATURES = {
                               f32, u64, u32, i64, i32, vp],
     "carca_cross_score_bwd": [vp, vp, P(CrossParams), vp, vp, P(CrossSaved), vp, vp, vp, vp, P(CrossParams), i32,
                               i32, i32, i32, i32, i32, i32, f32, u64, u32, i64, i32, vp, vp],
+    "carca_train_core_set_ticks": [vp, i32],
     "carca_train_core_rows_ints": [i32],
     "carca_train_core_saved_floats": [i32, i32, i32],
     "carca_train_core_fwd": [vp, i64, P(TrainCore), vp],
@@ -155,6 +156,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.carca_set_seed_source.restype = None
     lib.carca_eval_plan_floats.restype = C.c_int64
     lib.carca_eval_scratch_bytes.restype = C.c_int64
+    lib.carca_train_core_set_ticks.restype = None
     lib.carca_train_core_rows_ints.restype = C.c_int64
     lib.carca_train_core_saved_floats.restype = C.c_int64
     lib.carca_train_core_fold_floats.restype = C.c_int64

@@ -407,7 +407,7 @@ class CARCA(Model):
         """The sparse item->attribute table when AllEmbedding can run inside the fused training kernels
         (device-resident CSR attributes for every row set, built-in positional encodings), else None."""
         emb = self.embeds
-        if type(emb) is not AllEmbedding or not hasattr(emb.enc, "table"):
+        if type(emb) is not AllEmbedding or not hasattr(emb.enc, "table") or profile[2].shape[-1] > 8:
             return None
         tables = [a if isinstance(a, ItemAttrTable) else (emb.attr_table if a is None else False)
                   for a in [profile[1]] + [t[1] for t in targets]]

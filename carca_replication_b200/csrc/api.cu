@@ -604,6 +604,8 @@ int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* gr, c
 
 // ------------------------------------------------------------------------------------ fused training core
 namespace {
+long long* g_train_ticks = nullptr;
+int g_train_ticks_cap = 0;
 int train_args(TrainArgs& a, const carca_train_core* c) {
   CARCA_REQUIRE(c != nullptr, "train_core: null descriptor");
   if (c->L > TR || c->L < 1) return fail(-4, "train_core: L=%d outside [1, %d]", c->L, TR);
@@ -619,6 +621,8 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
   a.decoder = c->decoder_kind; a.residual_sa = c->residual_sa; a.residual_ca = c->residual_ca;
   a.drop = drop_cfg(c->p_drop, c->seed, 0u);
   a.n_sms = 148;
+  a.ticks = g_train_ticks;
+  a.ticks_cap = g_train_ticks_cap;
   a.p_x = c->p_x; a.p_e = c->p_e;
   for (int t = 0; t < c->n_tuples; ++t) {
     CARCA_REQUIRE(c->o_x[t] != nullptr, "train_core: target tuple %d missing", t);
@@ -638,7 +642,7 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
   if (c->embed) {
     const carca_embed_params* w = c->embed;
     if (w->d != TD) return fail(-4, "train_core: d=%d, the fused kernels handle d=64", w->d);
-    if (w->n_ctx > 32) return fail(-4, "train_core: %d context features (at most 32)", w->n_ctx);
+    if (w->n_ctx > TMAXC) return fail(-4, "train_core: %d context features (at most %d)", w->n_ctx, TMAXC);
     CARCA_REQUIRE(c->attrs && c->attrs->kind == CARCA_ATTR_CSR, "train_core: the folded embedding needs CSR attributes");
     CARCA_REQUIRE(c->fold && c->p_c, "train_core: folded embedding without workspace / context");
     if (w->pos) CARCA_REQUIRE(c->L <= w->pos_len, "train_core: sequence length %d > positional table %d", c->L, w->pos_len);
@@ -660,6 +664,11 @@ int train_args(TrainArgs& a, const carca_train_core* c) {
 }
 int train_grid(int B) { return B < 148 ? (B < 1 ? 1 : B) : 148; }
 }  // namespace
+
+void carca_train_core_set_ticks(int64_t* device_buf, int capacity) {
+  g_train_ticks = reinterpret_cast<long long*>(device_buf);
+  g_train_ticks_cap = device_buf ? capacity : 0;
+}
 
 int64_t carca_train_core_rows_ints(int B) { return 4 + 2 * (int64_t)B * TR; }
 int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples) {

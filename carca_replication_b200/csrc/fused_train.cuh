@@ -38,6 +38,7 @@ constexpr int TWARPS = TTHREADS / 32;
 constexpr int TMAXB = 8;          // encoder blocks
 constexpr int TMAXT = 2;          // target tuples (positives | negatives, src/train.py:86-88)
 constexpr int TNBUF = 10;
+constexpr int TMAXC = 8;          // context features the in-kernel embedding handles
 
 struct TrainBlockW { const float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2; };
 struct TrainBlockG { float *ln1_g, *ln1_b, *wq, *bq, *wk, *bk, *wv, *bv, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2; };
@@ -80,6 +81,8 @@ struct TrainArgs {
   const float* p_c;                           // [B, L, C]
   const float* o_c[TMAXT];
   float *gE, *gWj, *dfold, *gpos;             // backward: d items_embed, d joint_embed.weight, d fold, d pos
+  long long* ticks;                           // optional (development): (label, clock64) pairs of CTA 0, thread 0
+  int ticks_cap;
   // backward only
   const float* dy;                            // [B, ldy]
   float* d_pe;                                // [B, L, 64] zero-initialised by the caller
@@ -93,7 +96,7 @@ struct TrainArgs {
 __host__ __device__ __forceinline__ int sv_block(int b, int k) { return 6 * b + k; }     // k: 0 x, 1 Q, 2 K, 3 V, 4 s, 5 a1
 __host__ __device__ __forceinline__ int sv_final(int nb) { return 6 * nb; }              // last block's output
 __host__ __device__ __forceinline__ int sv_dec(int nb, int k) { return 6 * nb + 1 + k; } // 0 K, 1 V, 2 + t: s of tuple t
-__host__ __device__ __forceinline__ int sv_count(int nb, int nt) { return 6 * nb + 3 + nt; }
+__host__ __device__ __forceinline__ int sv_count(int nb, int nt) { return 6 * nb + 3 + 2 * nt; }   // + nt + t: embedded targets
 
 struct TrainSmem {
   float buf[TNBUF][TBUF];
@@ -102,8 +105,31 @@ struct TrainSmem {
   float gsc[TR];                   // per-row scalars
   int src[TR], info[TR], pos[TR], usr[TR];
   int ids[1 + TMAXT][TR];          // embed_mode: item id of the row in the profile / each target tuple
+  float gtc[TMAXC + 1][TD];        // embed_mode: context rows of the folded table, then cst (loaded once per CTA)
+  float ctxv[TR][TMAXC];           // embed_mode: context values of the row set being embedded
   int n, npad;
 };
+
+struct TrainTicks {
+  long long* out;
+  int n, cap;
+};
+__device__ __forceinline__ TrainTicks ticks_begin(const TrainArgs& a) {
+  TrainTicks t;
+  t.out = (a.ticks && blockIdx.x == 0 && threadIdx.x == 0) ? a.ticks : nullptr;
+  t.n = 0;
+  t.cap = a.ticks_cap;
+  return t;
+}
+__device__ __forceinline__ void tick(TrainTicks& t, int label) {
+#ifndef CARCA_EMU
+  if (t.out && t.n < t.cap) {
+    t.out[2 * t.n] = label;
+    t.out[2 * t.n + 1] = clock64();
+    ++t.n;
+  }
+#endif
+}
 
 // -------------------------------------------------------------------------------------------------- packing
 // One CTA per 128 users: counts each user's active positions, packs users greedily into 64-row bins,
@@ -173,26 +199,43 @@ __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
 // -------------------------------------------------------------------------------------------------- tiles
 // Thread (ty, tx) = (tid / 16, tid % 16).
 
-constexpr int TNR = TR * 16 / TTHREADS;   // rows per thread in gemm_nt (2 with 512 threads)
+// Thread mapping of the tile products (512 threads = 16 warps): warp w owns the 8 rows [8 (w >> 1), +8) and the 32
+// columns [32 (w & 1), +32) of a 64 x 64 output; lane = (ty, tx) = (lane >> 3, lane & 7) owns rows 2 ty, 2 ty + 1 of
+// the warp's rows.  A warp thus reads 8 operand rows and 32 operand columns per step: every shared-memory request
+// is one conflict-free wavefront and the products are FFMA-bound, not shared-memory-bound.
+static_assert(TTHREADS == 512 && TR == 64 && TD == 64, "tile mapping below assumes 16 warps over a 64 x 64 tile");
+constexpr int TNR = 2;   // rows per thread
 
-// C[r][n] = sum_k A[r][k] W[n][k], K % 4 == 0; thread owns rows TNR*ty .. TNR*ty + TNR - 1 and the strided columns
-// tx, tx+16, tx+32, tx+48 (< NCOLS), so the 128-bit loads of W rows are bank-conflict free.
-// `need(j)` lets attention skip columns outside the rows' key range.
+struct TileMap {
+  int r0, c0, tx;
+  __device__ __forceinline__ TileMap() {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    tx = lane & 7;
+    r0 = 8 * (w >> 1) + 2 * (lane >> 3);
+    c0 = 32 * (w & 1);
+  }
+};
+
+// C[r][n] = sum_k A[r][k] W[n][k], K % 4 == 0; thread owns rows r0, r0 + 1 and the strided columns c0 + tx + 8 j
+// (j < 4), so the 128-bit loads of W rows are bank-conflict free.  `need(r0, col)` lets attention skip columns
+// outside the rows' key range.
 template <int NCOLS, class Need, class Epi>
 __device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                         int K, int nrows, Need need, Epi epi) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  constexpr int NJ = NCOLS / 16;
-  if (ty * TNR < nrows) {
+  static_assert(NCOLS == 64, "gemm_nt covers 64 output columns");
+  const TileMap m;
+  constexpr int NJ = 4;
+  if (m.r0 < nrows) {
     float acc[TNR][NJ];
     bool on[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      on[j] = need(ty * TNR, tx + 16 * j);
+      on[j] = need(m.r0, m.c0 + m.tx + 8 * j);
 #pragma unroll
       for (int i = 0; i < TNR; ++i) acc[i][j] = 0.f;
     }
-    const float* ap = A + (ty * TNR) * lda;
+    const float* ap = A + m.r0 * lda;
+    const float* wp = W + (m.c0 + m.tx) * ldw;
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
       float4 av[TNR];
@@ -201,7 +244,7 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, co
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         if (on[j]) {
-          const float4 b = *reinterpret_cast<const float4*>(W + (tx + 16 * j) * ldw + k);
+          const float4 b = *reinterpret_cast<const float4*>(wp + 8 * j * ldw + k);
 #pragma unroll
           for (int i = 0; i < TNR; ++i) {
             acc[i][j] = fmaf(av[i].x, b.x, acc[i][j]);
@@ -216,7 +259,7 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ A, int lda, co
     for (int j = 0; j < NJ; ++j)
       if (on[j]) {
 #pragma unroll
-        for (int i = 0; i < TNR; ++i) epi(ty * TNR + i, tx + 16 * j, acc[i][j]);
+        for (int i = 0; i < TNR; ++i) epi(m.r0 + i, m.c0 + m.tx + 8 * j, acc[i][j]);
       }
   }
 }
@@ -225,76 +268,116 @@ struct NeedAll {
   __device__ __forceinline__ bool operator()(int, int) const { return true; }
 };
 
-// rows per thread of gemm_nn / gemm_tn for NC output columns (4 contiguous columns per thread)
+// Output rows / columns of a thread for products with NC output columns (4 contiguous columns per thread):
+//   NC = 64: the TileMap above, 2 rows;   NC = 32: warp w owns rows 4w .. 4w+3, 1 row per thread;
+//   NC = 16: warps 0..7 own rows 8w .. 8w+7, 1 row per thread.
 template <int NC>
-struct RowTile {
-  static constexpr int CG = NC / 4;
-  static constexpr int RG = TTHREADS / CG;
-  static constexpr int RT = RG >= TR ? 1 : TR / RG;
+struct OutMap {
+  static constexpr int RT = NC == 64 ? 2 : 1;
+  int r0, c0;
+  bool active;
+  __device__ __forceinline__ OutMap() {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (NC == 64) {
+      r0 = 8 * (w >> 1) + 2 * (lane >> 3);
+      c0 = 32 * (w & 1) + 4 * (lane & 7);
+      active = true;
+    } else if (NC == 32) {
+      r0 = 4 * w + (lane >> 3);
+      c0 = 4 * (lane & 7);
+      active = true;
+    } else {
+      r0 = 8 * w + (lane >> 2);
+      c0 = 4 * (lane & 3);
+      active = w < 8;
+    }
+  }
 };
 
-// C[r][c] = sum_{k in [klo, khi)} A[r][k] B[k][c] for c < NC (NC in {16, 32, 64}); thread owns RowTile<NC>::RT
-// rows and 4 contiguous columns.  range(r0, r1, klo, khi) gives the reduction range of rows r0..r1
-// (multiples of 4 are not required).
+// C[r][c] = sum_{k in [klo, khi)} A[r][k] B[k][c] for c < NC (NC in {16, 32, 64}).  range(r0, r1, klo, khi) gives the
+// reduction range of rows r0..r1; it is widened to multiples of 4 (A is read 128 bits at a time), so A must hold
+// zeros and B finite values just outside it.
 template <int NC, class Range, class Epi>
 __device__ __forceinline__ void gemm_nn(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                         int nrows, Range range, Epi epi) {
-  constexpr int CG = RowTile<NC>::CG, RT = RowTile<NC>::RT;
-  const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
-  const int r0 = ty * RT;
-  if (r0 < nrows && r0 < TR) {
+  const OutMap<NC> m;
+  constexpr int RT = OutMap<NC>::RT;
+  if (m.active && m.r0 < nrows) {
     int klo, khi;
-    range(r0, r0 + RT - 1, klo, khi);
+    range(m.r0, m.r0 + RT - 1, klo, khi);
+    klo &= ~3;
+    khi = min((khi + 3) & ~3, TR);
     float acc[RT][4];
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k = klo; k < khi; ++k) {
-      const float4 b = *reinterpret_cast<const float4*>(Bm + k * ldb + tx * 4);
+    const float* ap = A + m.r0 * lda;
+    const float* bp = Bm + m.c0;
+#pragma unroll 2
+    for (int k = klo; k < khi; k += 4) {
+      float4 av[RT];
+#pragma unroll
+      for (int i = 0; i < RT; ++i) av[i] = *reinterpret_cast<const float4*>(ap + i * lda + k);
+      const float4 b0 = *reinterpret_cast<const float4*>(bp + (k + 0) * ldb);
+      const float4 b1 = *reinterpret_cast<const float4*>(bp + (k + 1) * ldb);
+      const float4 b2 = *reinterpret_cast<const float4*>(bp + (k + 2) * ldb);
+      const float4 b3 = *reinterpret_cast<const float4*>(bp + (k + 3) * ldb);
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
-        const float av = A[(r0 + i) * lda + k];
-        acc[i][0] = fmaf(av, b.x, acc[i][0]);
-        acc[i][1] = fmaf(av, b.y, acc[i][1]);
-        acc[i][2] = fmaf(av, b.z, acc[i][2]);
-        acc[i][3] = fmaf(av, b.w, acc[i][3]);
+        acc[i][0] = fmaf(av[i].x, b0.x, acc[i][0]); acc[i][1] = fmaf(av[i].x, b0.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i].x, b0.z, acc[i][2]); acc[i][3] = fmaf(av[i].x, b0.w, acc[i][3]);
+        acc[i][0] = fmaf(av[i].y, b1.x, acc[i][0]); acc[i][1] = fmaf(av[i].y, b1.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i].y, b1.z, acc[i][2]); acc[i][3] = fmaf(av[i].y, b1.w, acc[i][3]);
+        acc[i][0] = fmaf(av[i].z, b2.x, acc[i][0]); acc[i][1] = fmaf(av[i].z, b2.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i].z, b2.z, acc[i][2]); acc[i][3] = fmaf(av[i].z, b2.w, acc[i][3]);
+        acc[i][0] = fmaf(av[i].w, b3.x, acc[i][0]); acc[i][1] = fmaf(av[i].w, b3.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i].w, b3.z, acc[i][2]); acc[i][3] = fmaf(av[i].w, b3.w, acc[i][3]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < RT; ++i) epi(r0 + i, tx * 4, acc[i]);
+    for (int i = 0; i < RT; ++i) epi(m.r0 + i, m.c0, acc[i]);
   }
 }
 
-// C[n][c] = sum_{r in [rlo, rhi)} A[r][n] X[r][c] for n < 64, c < NC; thread owns RowTile<NC>::RT values of n and 4
-// contiguous columns.  range(n0, n1, rlo, rhi) gives the reduction range for output rows n0..n1.
+// C[n][c] = sum_{r in [rlo, rhi)} A[r][n] X[r][c] for n < 64, c < NC.  range(n0, n1, rlo, rhi) gives the reduction
+// range for output rows n0..n1.
 template <int NC, class Range, class Epi>
 __device__ __forceinline__ void gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ X, int ldx,
                                         Range range, Epi epi) {
-  constexpr int CG = RowTile<NC>::CG, RT = RowTile<NC>::RT;
-  const int tx = threadIdx.x % CG, ty = threadIdx.x / CG;
-  const int n0 = ty * RT;
-  if (n0 >= TR) return;
+  const OutMap<NC> m;
+  constexpr int RT = OutMap<NC>::RT;
+  if (!m.active) return;
   int rlo, rhi;
-  range(n0, n0 + RT - 1, rlo, rhi);
+  range(m.r0, m.r0 + RT - 1, rlo, rhi);
   float acc[RT][4];
 #pragma unroll
   for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float* ap = A + m.r0;
+  const float* xp = X + m.c0;
+#pragma unroll 4
   for (int r = rlo; r < rhi; ++r) {
-    const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + tx * 4);
+    const float4 x = *reinterpret_cast<const float4*>(xp + r * ldx);
+    float av[RT];
+    if (RT == 2) {
+      const float2 t = *reinterpret_cast<const float2*>(ap + r * lda);
+      av[0] = t.x;
+      av[RT - 1] = t.y;
+    } else {
+      av[0] = ap[r * lda];
+    }
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
-      const float av = A[r * lda + n0 + i];
-      acc[i][0] = fmaf(av, x.x, acc[i][0]);
-      acc[i][1] = fmaf(av, x.y, acc[i][1]);
-      acc[i][2] = fmaf(av, x.z, acc[i][2]);
-      acc[i][3] = fmaf(av, x.w, acc[i][3]);
+      acc[i][0] = fmaf(av[i], x.x, acc[i][0]);
+      acc[i][1] = fmaf(av[i], x.y, acc[i][1]);
+      acc[i][2] = fmaf(av[i], x.z, acc[i][2]);
+      acc[i][3] = fmaf(av[i], x.w, acc[i][3]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < RT; ++i) epi(n0 + i, tx * 4, acc[i]);
+  for (int i = 0; i < RT; ++i) epi(m.r0 + i, m.c0, acc[i]);
 }
 
 // -------------------------------------------------------------------------------------------------- helpers
@@ -395,18 +478,55 @@ __device__ __forceinline__ void tile_pass(float* tile, int rows, F fn) {
   }
 }
 
-// LayerNorm of the bin's rows, warp per row (same arithmetic as layernorm_fwd_kernel)
+// Row passes give every warp TRW = 4 consecutive rows and run them TOGETHER (independent shuffle / exp / Philox
+// chains interleave), instead of one row after the other: with 16 warps per SM these passes are latency-bound.
+constexpr int TRW = TR / TWARPS;
+
+template <int NR>
+__device__ __forceinline__ void warp_sum_n(float (&v)[NR]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < NR; ++q) v[q] += __shfl_xor_sync(kFull, v[q], o);
+}
+template <int NR>
+__device__ __forceinline__ void warp_max_n(float (&v)[NR]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < NR; ++q) v[q] = fmaxf(v[q], __shfl_xor_sync(kFull, v[q], o));
+}
+
+// LayerNorm of the bin's rows (same arithmetic as layernorm_fwd_kernel)
 __device__ __forceinline__ void ln_rows(float* out, const float* in, int rows, const float* __restrict__ gamma,
                                         const float* __restrict__ beta) {
   const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r0 = w * TRW;
+  if (r0 >= rows) return;
   const float g0 = gamma[lane], g1 = gamma[lane + 32], b0 = beta[lane], b1 = beta[lane + 32];
-  for (int r = w; r < rows; r += TWARPS) {
-    const float x0 = in[r * TLD + lane], x1 = in[r * TLD + lane + 32];
-    const float mean = warp_sum(x0 + x1) / (float)TD;
-    const float c0 = x0 - mean, c1 = x1 - mean;
-    const float rstd = 1.0f / sqrtf(warp_sum(fmaf(c0, c0, c1 * c1)) / (float)TD + kLnEps);
-    out[r * TLD + lane] = c0 * rstd * g0 + b0;
-    out[r * TLD + lane + 32] = c1 * rstd * g1 + b1;
+  float x0[TRW], x1[TRW], t[TRW];
+#pragma unroll
+  for (int q = 0; q < TRW; ++q) {
+    x0[q] = in[(r0 + q) * TLD + lane];
+    x1[q] = in[(r0 + q) * TLD + lane + 32];
+    t[q] = x0[q] + x1[q];
+  }
+  warp_sum_n(t);
+#pragma unroll
+  for (int q = 0; q < TRW; ++q) {
+    const float mean = t[q] / (float)TD;
+    x0[q] -= mean;
+    x1[q] -= mean;
+    t[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
+  }
+  warp_sum_n(t);
+#pragma unroll
+  for (int q = 0; q < TRW; ++q) {
+    const float rstd = 1.0f / sqrtf(t[q] / (float)TD + kLnEps);
+    if (r0 + q < rows) {
+      out[(r0 + q) * TLD + lane] = x0[q] * rstd * g0 + b0;
+      out[(r0 + q) * TLD + lane + 32] = x1[q] * rstd * g1 + b1;
+    }
   }
 }
 
@@ -416,23 +536,51 @@ __device__ __forceinline__ void ln_bwd_rows(TrainSmem& s, float* dx, const float
                                             const float* __restrict__ gamma, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, bool accumulate) {
   const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int r0 = w * TRW;
   const float g0 = gamma[lane], g1 = gamma[lane + 32];
   float ag0 = 0.f, ag1 = 0.f, ab0 = 0.f, ab1 = 0.f;
-  for (int r = w; r < rows; r += TWARPS) {
-    const float x0 = x[r * TLD + lane], x1 = x[r * TLD + lane + 32];
-    const float mean = warp_sum(x0 + x1) / (float)TD;
-    const float c0 = x0 - mean, c1 = x1 - mean;
-    const float rstd = 1.0f / sqrtf(warp_sum(fmaf(c0, c0, c1 * c1)) / (float)TD + kLnEps);
-    const float h0 = c0 * rstd, h1 = c1 * rstd;
-    const float d0 = dy[r * TLD + lane], d1 = dy[r * TLD + lane + 32];
-    const float e0 = d0 * g0, e1 = d1 * g1;
-    const float m1 = warp_sum(e0 + e1) / (float)TD;
-    const float m2 = warp_sum(fmaf(e0, h0, e1 * h1)) / (float)TD;
-    ag0 = fmaf(d0, h0, ag0); ag1 = fmaf(d1, h1, ag1);
-    ab0 += d0; ab1 += d1;
-    const float v0 = rstd * (e0 - m1 - h0 * m2), v1 = rstd * (e1 - m1 - h1 * m2);
-    dx[r * TLD + lane] = accumulate ? dx[r * TLD + lane] + v0 : v0;
-    dx[r * TLD + lane + 32] = accumulate ? dx[r * TLD + lane + 32] + v1 : v1;
+  if (r0 < rows) {
+    float h0[TRW], h1[TRW], d0[TRW], d1[TRW], t[TRW], u[TRW], rstd[TRW];
+#pragma unroll
+    for (int q = 0; q < TRW; ++q) {
+      const bool live = r0 + q < rows;
+      h0[q] = live ? x[(r0 + q) * TLD + lane] : 0.f;
+      h1[q] = live ? x[(r0 + q) * TLD + lane + 32] : 0.f;
+      d0[q] = live ? dy[(r0 + q) * TLD + lane] : 0.f;
+      d1[q] = live ? dy[(r0 + q) * TLD + lane + 32] : 0.f;
+      t[q] = h0[q] + h1[q];
+    }
+    warp_sum_n(t);
+#pragma unroll
+    for (int q = 0; q < TRW; ++q) {
+      const float mean = t[q] / (float)TD;
+      h0[q] -= mean;
+      h1[q] -= mean;
+      t[q] = fmaf(h0[q], h0[q], h1[q] * h1[q]);
+    }
+    warp_sum_n(t);
+#pragma unroll
+    for (int q = 0; q < TRW; ++q) {
+      rstd[q] = 1.0f / sqrtf(t[q] / (float)TD + kLnEps);
+      h0[q] *= rstd[q];
+      h1[q] *= rstd[q];
+      t[q] = d0[q] * g0 + d1[q] * g1;
+      u[q] = fmaf(d0[q] * g0, h0[q], d1[q] * g1 * h1[q]);
+      ag0 = fmaf(d0[q], h0[q], ag0); ag1 = fmaf(d1[q], h1[q], ag1);
+      ab0 += d0[q]; ab1 += d1[q];
+    }
+    warp_sum_n(t);
+    warp_sum_n(u);
+#pragma unroll
+    for (int q = 0; q < TRW; ++q) {
+      if (r0 + q < rows) {
+        const float m1 = t[q] / (float)TD, m2 = u[q] / (float)TD;
+        const float v0 = rstd[q] * (d0[q] * g0 - m1 - h0[q] * m2), v1 = rstd[q] * (d1[q] * g1 - m1 - h1[q] * m2);
+        float* o = dx + (r0 + q) * TLD;
+        o[lane] = accumulate ? o[lane] + v0 : v0;
+        o[lane + 32] = accumulate ? o[lane + 32] + v1 : v1;
+      }
+    }
   }
   s.red[w][0][lane] = ag0; s.red[w][0][lane + 32] = ag1;
   s.red[w][1][lane] = ab0; s.red[w][1][lane + 32] = ab1;
@@ -506,41 +654,48 @@ __device__ __forceinline__ bool attn_need(const TrainSmem& s, int r0, int j) {
   return j <= r1 && j >= (s.info[r0] & 0x7f);
 }
 
-// softmax of row i of S (tile, logits before scaling) restricted to the allowed keys; returns p for the
-// lane's two keys (lane, lane + 32) and the keep-scales of the attention dropout
-__device__ __forceinline__ void softmax_row(const TrainSmem& s, const AttnCfg& c, const float* S, int i, int h, int lane,
-                                            float (&p)[2], float (&f)[2]) {
-  const int info = s.info[i];
-  const int seg0 = info & 0x7f;
-  const bool qv = (info & c.qbit) != 0;
-  const int jmax = c.cross ? i - 1 : i;
-  float sc[2];
-  float mx = -INFINITY;
+// softmax of rows i0 .. i0+TRW-1 of S (tile, logits before scaling) restricted to the allowed keys; returns p for
+// the lane's two keys (lane, lane + 32) of every row and the keep-scales of the attention dropout
+__device__ __forceinline__ void softmax_rows(const TrainSmem& s, const AttnCfg& c, const float* S, int i0, int h, int lane,
+                                             float (&p)[TRW][2], float (&f)[TRW][2]) {
+  float sc[TRW][2], mx[TRW], sum[TRW];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int j = lane + 32 * q;
-    const bool ok = qv && j >= seg0 && j <= jmax && (s.info[j] & TI_PVALID);
-    sc[q] = ok ? S[i * TLD + j] / c.sqrt_dh : -INFINITY;
-    mx = fmaxf(mx, sc[q]);
+  for (int r = 0; r < TRW; ++r) {
+    const int i = i0 + r;
+    const int info = s.info[i];
+    const int seg0 = info & 0x7f;
+    const bool qv = (info & c.qbit) != 0;
+    const int jmax = c.cross ? i - 1 : i;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int j = lane + 32 * q;
+      const bool ok = qv && j >= seg0 && j <= jmax && (s.info[j] & TI_PVALID);
+      sc[r][q] = ok ? S[i * TLD + j] / c.sqrt_dh : -INFINITY;
+    }
+    mx[r] = fmaxf(sc[r][0], sc[r][1]);
   }
-  mx = warp_max(mx);
-  float e[2], sum = 0.f;
+  warp_max_n(mx);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    e[q] = sc[q] == -INFINITY ? 0.f : expf(sc[q] - mx);
-    sum += e[q];
+  for (int r = 0; r < TRW; ++r) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) p[r][q] = sc[r][q] == -INFINITY ? 0.f : expf(sc[r][q] - mx[r]);
+    sum[r] = p[r][0] + p[r][1];
   }
-  sum = warp_sum(sum);
-  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  warp_sum_n(sum);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int j = lane + 32 * q;
-    p[q] = e[q] * inv;
-    f[q] = 1.0f;
-    if (p[q] != 0.f && c.drop.p > 0.f) {
-      const unsigned long long elem =
-          (((unsigned long long)s.usr[i] * c.H + h) * c.L + s.pos[i]) * c.L + s.pos[j];
-      f[q] = drop_factor(c.drop, elem);
+  for (int r = 0; r < TRW; ++r) {
+    const int i = i0 + r;
+    const float inv = sum[r] > 0.f ? 1.0f / sum[r] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int j = lane + 32 * q;
+      p[r][q] *= inv;
+      f[r][q] = 1.0f;
+      if (c.drop.p > 0.f) {
+        const unsigned long long elem =
+            (((unsigned long long)s.usr[i] * c.H + h) * c.L + s.pos[i]) * c.L + s.pos[j];
+        f[r][q] = drop_factor(c.drop, elem);
+      }
     }
   }
 }
@@ -554,11 +709,14 @@ __device__ __forceinline__ void attention_fwd_tile(TrainSmem& s, const AttnCfg& 
     gemm_nt<TR>(Q + hc, TLD, K + hc, TLD, c.dh, s.npad, [&](int r0, int j) { return attn_need(s, r0, j); },
                 [&](int r, int j, float v) { Sb[r * TLD + j] = v; });
     __syncthreads();
-    for (int i = w; i < s.npad; i += TWARPS) {
-      float p[2], f[2];
-      softmax_row(s, c, Sb, i, h, lane, p, f);
-      Sb[i * TLD + lane] = p[0] * f[0];
-      Sb[i * TLD + lane + 32] = p[1] * f[1];
+    if (w * TRW < s.npad) {
+      float p[TRW][2], f[TRW][2];
+      softmax_rows(s, c, Sb, w * TRW, h, lane, p, f);
+#pragma unroll
+      for (int r = 0; r < TRW; ++r) {
+        Sb[(w * TRW + r) * TLD + lane] = p[r][0] * f[r][0];
+        Sb[(w * TRW + r) * TLD + lane + 32] = p[r][1] * f[r][1];
+      }
     }
     __syncthreads();
     auto range = [&](int r0, int r1, int& lo, int& hi) { key_range(s, r0, r1, lo, hi); };
@@ -587,21 +745,28 @@ __device__ __forceinline__ void attention_bwd_tile(TrainSmem& s, const AttnCfg& 
     gemm_nt<TR>(Q + hc, TLD, K + hc, TLD, c.dh, s.npad, need, [&](int r, int j, float v) { Sb[r * TLD + j] = v; });
     gemm_nt<TR>(dO + hc, TLD, V + hc, TLD, c.dh, s.npad, need, [&](int r, int j, float v) { Db[r * TLD + j] = v; });
     __syncthreads();
-    for (int i = w; i < TR; i += TWARPS) {
-      float p[2] = {0.f, 0.f}, f[2] = {1.f, 1.f};
-      if (i < s.npad) softmax_row(s, c, Sb, i, h, lane, p, f);
-      float dp[2];
-      float D = 0.f;
+    {
+      float p[TRW][2], f[TRW][2], dp[TRW][2], D[TRW];
+      softmax_rows(s, c, Sb, w * TRW, h, lane, p, f);      // rows beyond the bin's fill come out as zeros
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        dp[q] = p[q] != 0.f ? Db[i * TLD + lane + 32 * q] * f[q] : 0.f;
-        D = fmaf(p[q], dp[q], D);
+      for (int r = 0; r < TRW; ++r) {
+        const int i = w * TRW + r;
+        D[r] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          dp[r][q] = p[r][q] != 0.f ? Db[i * TLD + lane + 32 * q] * f[r][q] : 0.f;
+          D[r] = fmaf(p[r][q], dp[r][q], D[r]);
+        }
       }
-      D = warp_sum(D);
+      warp_sum_n(D);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        Db[i * TLD + lane + 32 * q] = p[q] * (dp[q] - D) / c.sqrt_dh;   // d(Q K^T)
-        Sb[i * TLD + lane + 32 * q] = p[q] * f[q];                      // dropout(W)
+      for (int r = 0; r < TRW; ++r) {
+        const int i = w * TRW + r;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          Db[i * TLD + lane + 32 * q] = p[r][q] * (dp[r][q] - D[r]) / c.sqrt_dh;   // d(Q K^T)
+          Sb[i * TLD + lane + 32 * q] = p[r][q] * f[r][q];                          // dropout(W)
+        }
       }
     }
     __syncthreads();
@@ -724,67 +889,98 @@ __device__ __forceinline__ void gather_items(const TrainArgs& a, const TrainSmem
   }
 }
 
+// context rows of the folded table and cst -> shared memory (once per CTA)
+__device__ __forceinline__ void load_fold_consts(const TrainArgs& a, TrainSmem& s) {
+  for (int e = threadIdx.x; e < (TMAXC + 1) * TD; e += TTHREADS) {
+    const int k = e / TD, c = e % TD;
+    float v = 0.f;
+    if (k < a.C) v = a.fold[(long long)(a.A + k) * TD + c];
+    else if (k == TMAXC) v = a.fold[(long long)(a.A + a.C) * TD + c];
+    s.gtc[k][c] = v;
+  }
+}
+
+// context values of the bin's rows -> shared memory (zeros for padding ids / unused slots)
+__device__ __forceinline__ void stage_ctx(const TrainArgs& a, TrainSmem& s, const int* ids, const float* __restrict__ ctx) {
+  for (int e = threadIdx.x; e < TR * TMAXC; e += TTHREADS) {
+    const int r = e / TMAXC, k = e % TMAXC;
+    float v = 0.f;
+    if (r < s.n && k < a.C && ids[r] != 0) v = ctx[(long long)s.src[r] * a.C + k];
+    s.ctxv[r][k] = v;
+  }
+}
+
 // AllEmbedding.forward (src/carca.py:85-95) of one row set through the folded tables.  Eo: output tile,
 // Z: scratch tile.  Rows with id 0 come out exactly 0 (the final `* mask`, :94).
+// The attribute gather runs one row per HALF-warp (16 lanes x 128 bits = one 64-float table row per load), the
+// row's column ids fetched by the lanes at once and four table rows in flight per step; the loop bounds are
+// made warp-uniform so both halves stay converged.
 __device__ __forceinline__ void embed_rows(const TrainArgs& a, TrainSmem& s, const int* ids, const float* __restrict__ ctx,
                                            bool add_pos, float* Eo, float* Z) {
   const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int half = lane >> 4, hl = lane & 15;
   gather_items(a, s, ids, Z);
   load_w(s, a.Wj, a.ldj);
+  stage_ctx(a, s, ids, ctx);
   __syncthreads();
   gemm_nt<TD>(Z, TLD, s.w, TLD, TD, s.npad, NeedAll(), [&](int r, int n, float v) { Eo[r * TLD + n] = v; });
   __syncthreads();
-  const float* cst = a.fold + (long long)(a.A + a.C) * TD;
-  for (int r = w; r < s.npad; r += TWARPS) {
+  for (int r0 = 2 * w; r0 < s.npad; r0 += 2 * TWARPS) {
+    const int r = r0 + half;
     const int id = ids[r];
-    float v0 = 0.f, v1 = 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k0 = 0, nnz = 0;
     if (id != 0) {
-      v0 = Eo[r * TLD + lane] + cst[lane];
-      v1 = Eo[r * TLD + lane + 32] + cst[lane + 32];
-      // attribute rows of GT: the lanes fetch the row's column ids / values at once, then four table rows are in
-      // flight per step (a plain loop would serialise two dependent L2 round trips per attribute)
-      const int k0 = a.csr_rowptr[id], nnz = a.csr_rowptr[id + 1] - k0;
-      for (int kb = 0; kb < nnz; kb += 32) {
-        const int m = min(32, nnz - kb);
-        int col = 0;
-        float val = 0.f;
-        if (lane < m) {
-          col = a.csr_cols[k0 + kb + lane];
-          val = a.csr_vals[k0 + kb + lane];
-        }
-        for (int q = 0; q < m; q += 4) {
-          float g0[4], g1[4], vv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int cq = __shfl_sync(kFull, col, (q + u) & 31);
-            vv[u] = __shfl_sync(kFull, val, (q + u) & 31);
-            const float* g = a.fold + (long long)cq * TD;
-            g0[u] = g[lane];
-            g1[u] = g[lane + 32];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            v0 = fmaf(vv[u], g0[u], v0);
-            v1 = fmaf(vv[u], g1[u], v1);
-          }
-        }
+      k0 = a.csr_rowptr[id];
+      nnz = a.csr_rowptr[id + 1] - k0;
+      v = *reinterpret_cast<const float4*>(Eo + r * TLD + hl * 4);
+      const float4 c4 = *reinterpret_cast<const float4*>(&s.gtc[TMAXC][hl * 4]);
+      v.x += c4.x; v.y += c4.y; v.z += c4.z; v.w += c4.w;
+    }
+    const int nmax = max(nnz, __shfl_xor_sync(kFull, nnz, 16));
+    for (int kb = 0; kb < nmax; kb += 16) {
+      int col = 0;
+      float val = 0.f;
+      if (kb + hl < nnz) {
+        col = a.csr_cols[k0 + kb + hl];
+        val = a.csr_vals[k0 + kb + hl];
       }
-      const float* cr = ctx + (long long)s.src[r] * a.C;
-      const float cmine = lane < a.C ? cr[lane] : 0.f;
-#pragma unroll 4
-      for (int k = 0; k < a.C; ++k) {
-        const float* g = a.fold + (long long)(a.A + k) * TD;
-        const float cv = __shfl_sync(kFull, cmine, k & 31);
-        v0 = fmaf(cv, g[lane], v0);
-        v1 = fmaf(cv, g[lane + 32], v1);
-      }
-      if (add_pos) {
-        v0 += a.pos_table[(long long)s.pos[r] * TD + lane];
-        v1 += a.pos_table[(long long)s.pos[r] * TD + lane + 32];
+      const int mm = min(16, nmax - kb);
+      for (int q = 0; q < mm; q += 4) {
+        float4 g[4];
+        float vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int from = (lane & 16) | ((q + u) & 15);
+          const int cq = __shfl_sync(kFull, col, from);
+          vv[u] = __shfl_sync(kFull, val, from);
+          g[u] = *reinterpret_cast<const float4*>(a.fold + (long long)cq * TD + hl * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v.x = fmaf(vv[u], g[u].x, v.x);
+          v.y = fmaf(vv[u], g[u].y, v.y);
+          v.z = fmaf(vv[u], g[u].z, v.z);
+          v.w = fmaf(vv[u], g[u].w, v.w);
+        }
       }
     }
-    Eo[r * TLD + lane] = v0;
-    Eo[r * TLD + lane + 32] = v1;
+    if (id != 0) {
+#pragma unroll
+      for (int k = 0; k < TMAXC; ++k) {
+        const float cv = s.ctxv[r][k];
+        const float4 g = *reinterpret_cast<const float4*>(&s.gtc[k][hl * 4]);
+        v.x = fmaf(cv, g.x, v.x);
+        v.y = fmaf(cv, g.y, v.y);
+        v.z = fmaf(cv, g.z, v.z);
+        v.w = fmaf(cv, g.w, v.w);
+      }
+      if (add_pos) {
+        const float4 pv = *reinterpret_cast<const float4*>(a.pos_table + (long long)s.pos[r] * TD + hl * 4);
+        v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+      }
+    }
+    *reinterpret_cast<float4*>(Eo + r * TLD + hl * 4) = v;
   }
   __syncthreads();
 }
@@ -795,44 +991,58 @@ __device__ __forceinline__ void embed_rows_bwd(const TrainArgs& a, TrainSmem& s,
                                                const float* __restrict__ ctx, bool is_profile, float* DE, float* Z,
                                                float* T2) {
   const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int half = lane >> 4, hl = lane & 15;
   const int n = s.n;
   tile_pass(DE, TR, [&](int r, int, float4& v) {                     // the `* mask` of :94
     if (r >= n || ids[r] == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
   });
   gather_items(a, s, ids, Z);
+  stage_ctx(a, s, ids, ctx);
   __syncthreads();
   colsum_tile(s, DE, n, a.dfold + (long long)(a.A + a.C) * TD);      // d cst
   for (int e = threadIdx.x; e < a.C * TD; e += TTHREADS) {            // d (context rows of GT)
     const int k = e / TD, c = e % TD;
     float acc = 0.f;
-    for (int r = 0; r < n; ++r)
-      if (ids[r] != 0) acc = fmaf(ctx[(long long)s.src[r] * a.C + k], DE[r * TLD + c], acc);
+    for (int r = 0; r < n; ++r) acc = fmaf(s.ctxv[r][k], DE[r * TLD + c], acc);
     atomicAdd(a.dfold + (long long)(a.A + k) * TD + c, acc);
   }
-  for (int r = w; r < n; r += TWARPS) {                               // d (attribute rows of GT), d pos
+  for (int r0 = 2 * w; r0 < s.npad; r0 += 2 * TWARPS) {              // d (attribute rows of GT), d pos
+    const int r = r0 + half;
     const int id = ids[r];
-    if (id == 0) continue;
-    const float d0 = DE[r * TLD + lane], d1 = DE[r * TLD + lane + 32];
-    const int k0 = a.csr_rowptr[id], nnz = a.csr_rowptr[id + 1] - k0;
-    for (int kb = 0; kb < nnz; kb += 32) {
-      const int m = min(32, nnz - kb);
+    // lane hl of the half-warp owns features hl, hl+16, hl+32, hl+48: each RED instruction of the half-warp then
+    // covers 16 consecutive floats (two sectors) instead of 16 sectors
+    float dv[4] = {0.f, 0.f, 0.f, 0.f};
+    int k0 = 0, nnz = 0;
+    if (id != 0) {
+      k0 = a.csr_rowptr[id];
+      nnz = a.csr_rowptr[id + 1] - k0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dv[j] = DE[r * TLD + hl + 16 * j];
+    }
+    const int nmax = max(nnz, __shfl_xor_sync(kFull, nnz, 16));
+    for (int kb = 0; kb < nmax; kb += 16) {
       int col = 0;
       float val = 0.f;
-      if (lane < m) {
-        col = a.csr_cols[k0 + kb + lane];
-        val = a.csr_vals[k0 + kb + lane];
+      if (kb + hl < nnz) {
+        col = a.csr_cols[k0 + kb + hl];
+        val = a.csr_vals[k0 + kb + hl];
       }
-      for (int q = 0; q < m; ++q) {
-        const int cq = __shfl_sync(kFull, col, q);
-        const float vq = __shfl_sync(kFull, val, q);
-        float* g = a.dfold + (long long)cq * TD;
-        atomicAdd(g + lane, vq * d0);
-        atomicAdd(g + lane + 32, vq * d1);
+      const int mm = min(16, nmax - kb);
+      for (int q = 0; q < mm; ++q) {
+        const int from = (lane & 16) | q;
+        const int cq = __shfl_sync(kFull, col, from);
+        const float vq = __shfl_sync(kFull, val, from);
+        if (kb + q < nnz) {
+          float* g = a.dfold + (long long)cq * TD + hl;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) atomicAdd(g + 16 * j, vq * dv[j]);
+        }
       }
     }
-    if (is_profile && a.gpos) {
-      atomicAdd(a.gpos + (long long)s.pos[r] * TD + lane, d0);
-      atomicAdd(a.gpos + (long long)s.pos[r] * TD + lane + 32, d1);
+    if (id != 0 && is_profile && a.gpos) {
+      float* g = a.gpos + (long long)s.pos[r] * TD + hl;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(g + 16 * j, dv[j]);
     }
   }
   weight_grad(s, DE, Z, n, a.gWj, nullptr, a.ldj);                    // d Wj[:, :64]
@@ -865,10 +1075,14 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
   float* Vb = s.buf[4];
   float* Sb = s.buf[5];
   for (int e = threadIdx.x; e < 6 * TBUF; e += TTHREADS) s.buf[0][e] = 0.f;
+  if (a.embed_mode) load_fold_consts(a, s);
   const int nbins = *a.n_bins;
+  TrainTicks tk = ticks_begin(a);
   for (int bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+    tick(tk, 0);
     load_bin(a, s, bin);
     const int n = s.n;
+    tick(tk, 1);
     {  // x0 = dropout(p_e)   (src/carca.py:415-416, site 0)
       const DropCfg d0 = at_site(a.drop, 0u);
       if (a.embed_mode) {
@@ -885,22 +1099,28 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
       }
     }
     __syncthreads();
+    tick(tk, 2);
     for (int b = 0; b < a.n_blocks; ++b) {
       const TrainBlockW& wb = a.blk[b];
       save_tile(a, s, sv_block(b, 0), bin, X);
       ln_rows(QN, X, n, wb.ln1_g, wb.ln1_b);                          // :298
       __syncthreads();
+      tick(tk, 3);
       project(s, Qb, QN, wb.wq, wb.bq);                               // :238 (query = LN1(x))
       project(s, Kb, X, wb.wk, wb.bk);                                // :239 (key = raw x)
       project(s, Vb, X, wb.wv, wb.bv);                                // :240
+      tick(tk, 4);
       save_tile(a, s, sv_block(b, 1), bin, Qb);
       save_tile(a, s, sv_block(b, 2), bin, Kb);
       save_tile(a, s, sv_block(b, 3), bin, Vb);
+      tick(tk, 5);
       // s = MHA(..., causal=0) (+ LN1(x)), in place over QN (:299-302)
       attention_fwd_tile(s, self_cfg(a, b), QN, Qb, Kb, Vb, Sb, a.residual_sa != 0);
+      tick(tk, 6);
       save_tile(a, s, sv_block(b, 4), bin, QN);
       ln_rows(Qb, QN, n, wb.ln2_g, wb.ln2_b);                         // s2 (:304)
       __syncthreads();
+      tick(tk, 7);
       // a1 = dropout(LeakyReLU(ffn_1(s2)))  (:307-309, site 2 + 3b)
       project(s, Kb, Qb, wb.w1, wb.b1);
       {
@@ -932,29 +1152,39 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
         });
       }
       __syncthreads();
+      tick(tk, 8);
     }
     save_tile(a, s, sv_final(a.n_blocks), bin, X);
     float* PE = QN;
     ln_rows(PE, X, n, a.fn_g, a.fn_b);                                // :421
     __syncthreads();
+    tick(tk, 9);
     if (a.decoder == 1) {
       project(s, Kb, PE, a.dec.wk, a.dec.bk);
       project(s, Vb, PE, a.dec.wv, a.dec.bv);
       save_tile(a, s, sv_dec(a.n_blocks, 0), bin, Kb);
       save_tile(a, s, sv_dec(a.n_blocks, 1), bin, Vb);
     }
+    tick(tk, 10);
     for (int t = 0; t < a.n_tuples; ++t) {
       float* O = X;
-      if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, Qb);   // :426
-      else gather_rows(s, a.o_e[t], O, nullptr);                      // (embedded by the caller)
+      if (a.embed_mode) {
+        embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, Qb);       // :426
+        save_tile(a, s, sv_dec(a.n_blocks, 2 + a.n_tuples + t), bin, O);
+      } else {
+        gather_rows(s, a.o_e[t], O, nullptr);                         // (embedded by the caller)
+      }
       __syncthreads();
+      tick(tk, 11);
       if (a.decoder == 1) {
         project(s, Qb, O, a.dec.wq, a.dec.bq);
         if (!a.residual_ca) {
           for (int e = threadIdx.x; e < TBUF; e += TTHREADS) O[e] = 0.f;
           __syncthreads();
         }
+        tick(tk, 12);
         attention_fwd_tile(s, cross_cfg(a, t), O, Qb, Kb, Vb, Sb, true);   // :339-343 (causal -1)
+        tick(tk, 13);
         save_tile(a, s, sv_dec(a.n_blocks, 2 + t), bin, O);
         const float bf = a.dec.bf[0];
         for (int r = w; r < n; r += TWARPS) {                         // :345-347
@@ -970,6 +1200,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_fwd_kernel(const Trai
         }
       }
       __syncthreads();
+      tick(tk, 14);
     }
   }
 }
@@ -990,6 +1221,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
   float* Sb = s.buf[8];
   float* Db = s.buf[9];
   for (int e = threadIdx.x; e < TNBUF * TBUF; e += TTHREADS) s.buf[0][e] = 0.f;
+  if (a.embed_mode) load_fold_consts(a, s);
   const int nbins = *a.n_bins;
   const int nb = a.n_blocks;
 
@@ -1011,7 +1243,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
     if (lane == 0 && acc != 0.f) atomicAdd(a.gdec.bf, acc * y0 * (1.0f - y0));
   }
 
+  TrainTicks tk = ticks_begin(a);
   for (int bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+    tick(tk, 100);
     load_bin(a, s, bin);
     const int n = s.n;
     float* DX = B0;   // gradient w.r.t. the output of the stage being processed
@@ -1027,6 +1261,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       for (int t = 0; t < a.n_tuples; ++t) {
         float* St = B0;
         float* DS = B1;
+        tick(tk, 101);
         load_tile(a, s, sv_dec(nb, 2 + t), bin, St);
         __syncthreads();
         // g = dy * y (1 - y); d wf += g s; d bf += g; ds = g wf   (:345-347)
@@ -1062,19 +1297,26 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
         float* O = B0;
         float* Qt = B2;
         float* dQ = B7;
-        if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, dQ);
+        tick(tk, 102);
+        if (a.embed_mode) load_tile(a, s, sv_dec(nb, 2 + a.n_tuples + t), bin, O);   // embedded in the forward
         else gather_rows(s, a.o_e[t], O, nullptr);
         __syncthreads();
+        tick(tk, 103);
         project(s, Qt, O, a.dec.wq, a.dec.bq);
+        tick(tk, 104);
         attention_bwd_tile(s, cross_cfg(a, t), dQ, dKd, dVd, DS, Qt, Kd, Vd, Sb, Db, t > 0);
+        tick(tk, 105);
         weight_grad(s, dQ, O, n, a.gdec.wq, a.gdec.bq);
         __syncthreads();
+        tick(tk, 106);
         // d o = dQ WQ (+ ds through the residual) -> d_oe rows
         if (a.residual_ca) project_bwd(s, DS, dQ, a.dec.wq, true);
         else project_bwd(s, DS, dQ, a.dec.wq, false);
+        tick(tk, 107);
         if (a.embed_mode) embed_rows_bwd(a, s, s.ids[1 + t], a.o_c[t], false, DS, B0, B2);
         else scatter_rows(s, a.d_oe[t], DS, nullptr);
         __syncthreads();
+        tick(tk, 108);
       }
       // keys / values: PE = LN_f(x_nb) recomputed
       float* XF = B1;
@@ -1090,6 +1332,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       project_bwd(s, DPE, dVd, a.dec.wv, true);
       // final LayerNorm backward -> DX
       ln_bwd_rows(s, DX, DPE, XF, n, a.fn_g, a.g_fn_g, a.g_fn_b, false);
+      tick(tk, 109);
     } else {
       // dot product (:360): y = sigmoid(<pe_r, o_r>); d pe_r = sum_t g o_r; d o_r = g pe_r
       float* XF = B1;
@@ -1102,7 +1345,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       __syncthreads();
       for (int t = 0; t < a.n_tuples; ++t) {
         float* O = B3;
-        if (a.embed_mode) embed_rows(a, s, s.ids[1 + t], a.o_c[t], false, O, B4);
+        if (a.embed_mode) load_tile(a, s, sv_dec(nb, 2 + a.n_tuples + t), bin, O);
         else gather_rows(s, a.o_e[t], O, nullptr);
         __syncthreads();
         for (int r = w; r < n; r += TWARPS) {
@@ -1128,6 +1371,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       const TrainBlockW& wb = a.blk[b];
       const TrainBlockG& gb = a.gblk[b];
       const bool res = a.residual_sa != 0;
+      tick(tk, 110);
       // FFN (:305-316)
       float* DF2 = B1;   // d ffn_2 output = dout * dropout2
       {
@@ -1180,9 +1424,11 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
         });
         __syncthreads();
       }
+      tick(tk, 111);
       // LN2 backward -> d s (B0)
       float* DSx = B0;
       ln_bwd_rows(s, DSx, DS2, Sx, n, wb.ln2_g, gb.ln2_g, gb.ln2_b, false);
+      tick(tk, 112);
       // attention backward
       float* Qb = B1;
       float* Kb = B2;
@@ -1194,7 +1440,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       load_tile(a, s, sv_block(b, 2), bin, Kb);
       load_tile(a, s, sv_block(b, 3), bin, Vb);
       __syncthreads();
+      tick(tk, 113);
       attention_bwd_tile(s, self_cfg(a, b), dQ, dK, dV, DSx, Qb, Kb, Vb, Sb, Db, false);
+      tick(tk, 114);
       // x and qn = LN1(x) recomputed
       float* Xb = B1;
       float* QN = B2;
@@ -1205,6 +1453,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       weight_grad(s, dQ, QN, n, gb.wq, gb.bq);
       weight_grad(s, dK, Xb, n, gb.wk, gb.bk);
       weight_grad(s, dV, Xb, n, gb.wv, gb.bv);
+      tick(tk, 115);
       // d qn = dQ WQ (+ d s through the residual)
       float* DQN = B3;
       project_bwd(s, DQN, dQ, wb.wq, false);
@@ -1220,6 +1469,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
       project_bwd(s, DXn, dK, wb.wk, false);
       project_bwd(s, DXn, dV, wb.wv, true);
       ln_bwd_rows(s, DXn, DQN, Xb, n, wb.ln1_g, gb.ln1_g, gb.ln1_b, true);
+      tick(tk, 116);
       for (int e = threadIdx.x; e < TR * 16; e += TTHREADS) {         // DX <- DXn
         const int r = e >> 4, c4 = e & 15;
         *reinterpret_cast<float4*>(DX + r * TLD + c4 * 4) = *reinterpret_cast<const float4*>(DXn + r * TLD + c4 * 4);
@@ -1238,12 +1488,14 @@ __global__ void __launch_bounds__(TTHREADS, 1) fused_train_bwd_kernel(const Trai
           });
           __syncthreads();
         }
+        tick(tk, 117);
         embed_rows_bwd(a, s, s.ids[0], a.p_c, true, DX, B1, B2);
       } else {
         scatter_rows(s, a.d_pe, DX, a.drop.p > 0.f ? &d0 : nullptr);
       }
     }
     __syncthreads();
+    tick(tk, 118);
   }
 }
 

@@ -287,6 +287,10 @@ typedef struct {
   float* fold;                      /* workspace, carca_train_core_fold_floats(embed) floats */
 } carca_train_core;
 
+/* Development aid (tools/train_phase_times.py): while set, thread 0 of CTA 0 of the fused training kernels writes
+ * (label, clock64) pairs at its phase boundaries into device_buf [capacity, 2].  NULL switches it off.        */
+void carca_train_core_set_ticks(int64_t* device_buf, int capacity);
+
 int64_t carca_train_core_rows_ints(int B);
 int64_t carca_train_core_saved_floats(int B, int n_blocks, int n_tuples);
 int64_t carca_train_core_fold_floats(const carca_embed_params* embed);
