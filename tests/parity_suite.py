@@ -312,3 +312,53 @@ def check_fused_adam(device, weight_decay=0.0, steps=5):
         np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().numpy(), rtol=2e-5, atol=1e-7)
     sd = o_ours.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def check_fused_train_edges(device):
+    """Boundary shapes of the fused training core against the per-op kernels: L = 64 with every position valid (a
+    user fills a bin), L = 1, B = 1, a batch whose rows are all padding, 8 context features (the in-kernel
+    embedding's limit) and 9 (embedding on the per-op kernels, core still fused)."""
+    import dataclasses
+
+    from carca_replication_b200 import synth
+
+    base = synth.SHAPES["tiny"]
+    cases = [dict(shape=dataclasses.replace(base, seq_len=64), B=3, all_valid=True, decoder="ca"),
+             dict(shape=dataclasses.replace(base, seq_len=64), B=5, all_valid=False, decoder="dot"),
+             dict(shape=dataclasses.replace(base, seq_len=1), B=4, all_valid=True, decoder="ca"),
+             dict(shape=base, B=1, all_valid=False, decoder="ca"),
+             dict(shape=base, B=4, all_valid=False, decoder="ca", empty=True),
+             dict(shape=dataclasses.replace(base, n_ctx=8), B=4, all_valid=False, decoder="ca"),
+             dict(shape=dataclasses.replace(base, n_ctx=9), B=4, all_valid=False, decoder="dot"),
+             dict(shape=dataclasses.replace(base, n_blocks=1, n_heads=4), B=6, all_valid=False, decoder="ca")]
+    for case in cases:
+        shape, B = case["shape"], case["B"]
+        L = shape.seq_len
+        b = synth.make_train_batch(shape, B, seed=9, all_valid=case["all_valid"])
+        if case.get("empty"):
+            b["p_x"].zero_()
+            b["o_x"].zero_()
+        b = {k: v.to(device) for k, v in b.items()}
+        table = synth.make_attr_table(shape, seed=9).to(device)
+        out = []
+        for fused in (True, False):
+            model = synth.build_model(shape, case["decoder"], p=0.2, seed=9).to(device).train()
+            model.embeds.set_attr_table(table)
+            model.use_fused_train = fused
+            tg = [(b["o_x"][:, :L], None, b["o_c"][:, :L]), (b["o_x"][:, L:], None, b["o_c"][:, L:])]
+            assert model._fused_train_applies((b["p_x"], None, b["p_c"]), tg) == fused
+            ops.set_dropout_seed(77)
+            try:
+                y = model.forward((b["p_x"], None, b["p_c"]), tg)
+                (y * torch.linspace(0.5, 1.5, y.numel(), device=y.device).view_as(y)).sum().backward()
+            finally:
+                ops.set_dropout_seed(None)
+            out.append((y.detach().cpu().numpy(), {k: v.grad.cpu().numpy() for k, v in model.named_parameters()
+                                                   if v.grad is not None}))
+        (y_f, g_f), (y_m, g_m) = out
+        assert rel_err(y_f, y_m) < FP32_RTOL, case
+        assert set(g_f) == set(g_m)
+        for k in g_m:
+            e = grad_err(g_f[k], g_m[k], grad_floor(k))
+            # d/d WK.bias is mathematically zero: both sides hold summation noise of this un-normalised loss
+            assert e < (5e-3 if k.endswith("WK.bias") else 3e-4), (case, k, e)

@@ -73,3 +73,7 @@ def test_fused_train_vs_per_op_kernels(emu_backend, kw):
 @pytest.mark.parametrize("wd", [0.0, 0.01])
 def test_fused_adam_vs_torch(emu_backend, wd):
     S.check_fused_adam(emu_backend, weight_decay=wd)
+
+
+def test_fused_train_edge_shapes(emu_backend):
+    S.check_fused_train_edges(emu_backend)

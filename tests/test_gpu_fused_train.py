@@ -44,3 +44,7 @@ def test_train_forward_falls_back_to_per_op_kernels_outside_the_fused_range():
 @pytest.mark.parametrize("wd", [0.0, 0.01])
 def test_fused_adam_vs_torch(wd):
     S.check_fused_adam(DEV, weight_decay=wd)
+
+
+def test_fused_train_edge_shapes():
+    S.check_fused_train_edges(DEV)
