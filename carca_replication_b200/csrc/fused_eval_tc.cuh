@@ -88,6 +88,7 @@ struct TcSmem {
   alignas(16) float ln[TC_LNROWS][64];                           // per block: ln1 g, b, ln2 g, b; then final g, b
   alignas(16) float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
+  float uval[4][128];                                // decoder: <V_h[key], wf_h> per (head, key row of the tile)
   int oid[128];
   int ulist[128];                                    // segments of the tile: first row | length << 8
   int uuser[128];                                    //   and their users
@@ -479,6 +480,52 @@ __device__ __forceinline__ void softmax_pair(TcCtx& c, uint32_t bits, float sc, 
   tmem_st_w<W>(p1lo, lo);
 }
 
+// Cross-attention of the decoder never needs the attention output itself, only its product with the scorer's
+// weight (src/carca.py:343-345: y = ffn(attn + o), ffn = Linear(d, 1)):  <sum_j p_j V_h[j], wf_h> =
+// sum_j p_j <V_h[j], wf_h> = sum_j p_j u_h[j].  So the decoder keeps one scalar u_h[j] per (head, key) and the
+// softmax below returns this thread's share of  sum_h sum_j p_hj u_hj  directly — no P operand, no P.V MMA, no
+// read-back of O.  Same masking / scaling rules as softmax_pair.  u0 / u1: the W keys of this thread, heads of the pair.
+template <int W>
+__device__ __forceinline__ float softmax_pair_dot(TcCtx& c, uint32_t bits, float sc, uint32_t s0, uint32_t s1,
+                                                  const float* __restrict__ u0, const float* __restrict__ u1) {
+  float v0[W], v1[W];
+  tmem_ld_w<W>(s0, v0);
+  tmem_ld_w<W>(s1, v1);
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < W; ++t) {
+    const bool ok = (bits >> t) & 1u;
+    v0[t] = ok ? v0[t] * sc : -INFINITY;
+    v1[t] = ok ? v1[t] * sc : -INFINITY;
+    m0 = fmaxf(m0, v0[t]);
+    m1 = fmaxf(m1, v1[t]);
+  }
+  float2 o = pair_exchange(c, make_float2(m0, m1));
+  m0 = fmaxf(m0, o.x);
+  m1 = fmaxf(m1, o.y);
+  m0 = (m0 == -INFINITY) ? 0.f : m0;
+  m1 = (m1 == -INFINITY) ? 0.f : m1;
+  float z0 = 0.f, z1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < W; t += 4) {
+    const float4 a0 = *reinterpret_cast<const float4*>(u0 + t);
+    const float4 a1 = *reinterpret_cast<const float4*>(u1 + t);
+    const float ua[4] = {a0.x, a0.y, a0.z, a0.w}, ub[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float e0 = ex2_approx(v0[t + q] - m0), e1 = ex2_approx(v1[t + q] - m1);
+      z0 += e0;
+      z1 += e1;
+      d0 = fmaf(e0, ua[q], d0);
+      d1 = fmaf(e1, ub[q], d1);
+    }
+  }
+  o = pair_exchange(c, make_float2(z0, z1));
+  z0 += o.x;
+  z1 += o.y;
+  return (z0 > 0.f ? d0 / z0 : 0.f) + (z1 > 0.f ? d1 / z1 : 0.f);
+}
+
 template <int H>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
   constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
@@ -773,7 +820,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     if (a.decoder == 1) {
       wait_mma(c);
       store_k_operand<H>(c, C_ACCK);
-      store_v_operand<H>(c, C_ACCV);
+      {   // u_h[row] = <V_h[row], wf_h> (see softmax_pair_dot): the decoder needs nothing else of V
+        float vv[32];
+        ld_feat<H>(c, C_ACCV, vv);
+        float part[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          part[h] = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < N2; ++qq) part[h] = fmaf(vv[h * N2 + qq], s.dwf[Own<H>::f0(h, c.half) + qq], part[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < H; h += 2) {
+          const float2 o = pair_exchange(c, make_float2(part[h], part[h + 1]));
+          if (c.half == 0) {
+            s.uval[h][c.row] = part[h] + o.x;
+            s.uval[h + 1][c.row] = part[h + 1] + o.y;
+          }
+        }
+      }
       tick(tk, 13);
     } else if (src >= 0 && rp == L - 1) {   // dot decoder: only the last profile position is used (:362)
 #pragma unroll
@@ -956,44 +1021,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           tick(tk, 20);
           {
             const uint32_t t = c.tmem + kw0 + W * c.half;
-            if (W == 8) softmax_pair<8>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
-            else if (W == 16) softmax_pair<16>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
-            else softmax_pair<32>(c, cross_bits, sc, t + C_XHI, t + C_XLO, t + C_XHI, t + C_ACCK, t + C_XLO, t + C_ACCV);
+            const float* u0 = &s.uval[hp][ubin * 64 + kw0 + W * c.half];
+            const float* u1 = &s.uval[hp + 1][ubin * 64 + kw0 + W * c.half];
+            if (W == 8) acc += softmax_pair_dot<8>(c, cross_bits, sc, t + C_XHI, t + C_XLO, u0, u1);
+            else if (W == 16) acc += softmax_pair_dot<16>(c, cross_bits, sc, t + C_XHI, t + C_XLO, u0, u1);
+            else acc += softmax_pair_dot<32>(c, cross_bits, sc, t + C_XHI, t + C_XLO, u0, u1);
           }
-          publish();
           tick(tk, 21);
-          if (iw >= 0) {
-            if (umma::elect_one()) {
-              {
-                const int ee = iw, h = hp + ee;
-                // keys kw0 .. kw0 + 2W of the bin: P columns from kw0, V key chunks from kw0 / 4
-                const uint32_t voff = (uint32_t)(h * 2 * DH + ubin * DH) * 16u + (uint32_t)(kw0 / 4) * (uint32_t)TC_VLBO;
-                const uint32_t d = tmem0 + C_QNHI + h * DH;
-                const uint32_t phi = tmem0 + (ee ? C_XLO : C_XHI) + kw0, plo = tmem0 + (ee ? C_ACCV : C_ACCK) + kw0;
-                const uint32_t vh = umma::smem_u32(s.v_hi) + voff, vl = umma::smem_u32(s.v_lo) + voff;
-                if (W == 8) issue_3x<DH, 2>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
-                else if (W == 16) issue_3x<DH, 4>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
-                else issue_3x<DH, 8>(d, phi, plo, vh, vl, (uint32_t)TC_VLBO);
-              }
-              commit(c);
-            }
+          if (hp + 2 < H) {   // the next head pair's score MMAs overwrite the TMEM columns just read
+            umma::fence_before_sync();
+            __syncthreads();
+            umma::fence_after_sync();
           }
-          c.ncommit++;
-          wait_mma(c);
-          tick(tk, 22);
-        }
-        {   // s = attention (+ o) (:340-343); y = sigmoid(<s, wf> + bf) (:345-347)
-          float o[32];
-          ld_feat<H>(c, C_QNHI, o);
-#pragma unroll
-          for (int h = 0; h < H; ++h)
-#pragma unroll
-            for (int qq = 0; qq < N2 / 4; ++qq) {
-              const float4 wv = *reinterpret_cast<const float4*>(&s.dwf[Own<H>::f0(h, c.half) + 4 * qq]);
-              const float* oo = &o[h * N2 + 4 * qq];
-              acc = fmaf(oo[0], wv.x, acc); acc = fmaf(oo[1], wv.y, acc);
-              acc = fmaf(oo[2], wv.z, acc); acc = fmaf(oo[3], wv.w, acc);
-            }
         }
         acc += pair_exchange(c, make_float2(acc, 0.f)).x;
         acc += __ldg(a.dbf);
