@@ -485,10 +485,10 @@ def roofline(op_ms, shape, B, decoder, pk):
     dom = max(op_ms, key=op_ms.get)
     r = table[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum of one fused_eval_tc launch over 8192 Beauty-shaped users
-    # (ncu --set full, profiles/r01/ncu_fused_tc_v8_raw.csv): 26.92 MB = 3286 B/user.  Algorithmic HBM bytes with
+    # (ncu --set full, profiles/r01/ncu_fused_tc_v10_raw.csv): 27.06 MB = 3304 B/user.  Algorithmic HBM bytes with
     # one context row per user: ids + context in, scores out = 2.2 KB/user; the item tables and weights are
     # L2 hits (90 % sector hit rate), the scores were still in L2 when the kernel ended.
-    traffic = 3286.0 * B if (dom == "fused_forward" and shape.name == "beauty") else None
+    traffic = 3304.0 * B if (dom == "fused_forward" and shape.name == "beauty") else None
     roof = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
             "frac": r["frac"], "traffic": traffic, "peak_source": pk["source"],
             "share_of_step": op_ms[dom] / sum(op_ms.values())}

@@ -1003,9 +1003,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
           if (iw >= 0) {   // one head per issuer
             if (umma::elect_one()) {
               const int ee = iw, h = hp + ee;
-              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)ubin * 64u * 16u;
-              issue_3x<64, DH / 8>(tmem0 + (ee ? C_XLO : C_XHI), tmem0 + C_ACCQ + h * DH, tmem0 + C_QNLO + h * DH,
-                                   umma::smem_u32(s.k_hi) + koff, umma::smem_u32(s.k_lo) + koff, 2048u);
+              // only the 2W keys of the iteration's window (softmax reads nothing else): N = 2W instead of 64
+              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)(ubin * 64 + kw0) * 16u;
+              const uint32_t dcol = tmem0 + (ee ? C_XLO : C_XHI) + kw0;
+              const uint32_t qh = tmem0 + C_ACCQ + h * DH, ql = tmem0 + C_QNLO + h * DH;
+              const uint32_t kh = umma::smem_u32(s.k_hi) + koff, kl = umma::smem_u32(s.k_lo) + koff;
+              if (W == 8) issue_3x<16, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
+              else if (W == 16) issue_3x<32, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
+              else issue_3x<64, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
               commit(c);
             }
           }
