@@ -380,12 +380,13 @@ class CARCA(Model):
     use_fused_train = True  # class default; set False on an instance to force the per-op training path
 
     def _fused_train_applies(self, profile, targets) -> bool:
-        """Train mode, d == 64, L <= 64, stock blocks / decoder, 1-2 target tuples of L positions each: the
+        """Train mode, d == 64, L <= 256 with at most 64 active positions per user (always true for L <= 64),
+        stock blocks / decoder, 1-2 target tuples of L positions each: the
         fused training core (csrc/fused_train.cuh) handles dropout -> blocks -> LayerNorm -> decoder."""
         if not (self.training and self.use_fused_train) or not 1 <= len(targets) <= 2:
             return False
         L = profile[0].shape[1]
-        if self.norm.weight.shape[0] != 64 or L > 64 or profile[0].dim() != 2:
+        if self.norm.weight.shape[0] != 64 or L > 256 or profile[0].dim() != 2:
             return False
         blocks = list(self.encoder)
         if len(blocks) > 8 or not all(type(b) is SelfAttentionBlock for b in blocks):
@@ -401,7 +402,27 @@ class CARCA(Model):
             return False
         if len(heads) > 1 or len(resid) > 1 or len(drops) != 1 or (heads and next(iter(heads)) not in (1, 2, 4)):
             return False
-        return all(t[0].dim() == 2 and t[0].shape[1] == L for t in targets)
+        if not all(t[0].dim() == 2 and t[0].shape[1] == L for t in targets):
+            return False
+        if L > 64:
+            # a user's ACTIVE positions must fit one 64-row bin: one device reduction + host read per step
+            # (not possible while a CUDA graph is being captured)
+            if self._fits_override is not None:        # GraphedTrainStep checked the batch before replaying
+                return self._fits_override
+            if profile[0].is_cuda and torch.cuda.is_current_stream_capturing():
+                return False
+            return self.max_active_positions(profile[0], [t[0] for t in targets]) <= 64
+        return True
+
+    _fits_override: Optional[bool] = None
+
+    @staticmethod
+    def max_active_positions(p_x: Tensor, o_xs: List[Tensor]) -> int:
+        """Largest number of positions of one user whose profile id or any target id is non-zero (host read)."""
+        active = p_x != 0
+        for o_x in o_xs:
+            active = active | (o_x != 0)
+        return int(active.sum(dim=1).max().item()) if active.numel() else 0
 
     def _folded_embedding_table(self, profile, targets) -> Optional[ItemAttrTable]:
         """The sparse item->attribute table when AllEmbedding can run inside the fused training kernels

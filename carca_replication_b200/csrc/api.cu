@@ -608,7 +608,7 @@ long long* g_train_ticks = nullptr;
 int g_train_ticks_cap = 0;
 int train_args(TrainArgs& a, const carca_train_core* c) {
   CARCA_REQUIRE(c != nullptr, "train_core: null descriptor");
-  if (c->L > TR || c->L < 1) return fail(-4, "train_core: L=%d outside [1, %d]", c->L, TR);
+  if (c->L > TMAXL || c->L < 1) return fail(-4, "train_core: L=%d outside [1, %d]", c->L, TMAXL);
   if (!(c->n_heads == 1 || c->n_heads == 2 || c->n_heads == 4))
     return fail(-4, "train_core: n_heads=%d not in {1, 2, 4}", c->n_heads);
   if (c->n_blocks < 0 || c->n_blocks > TMAXB) return fail(-4, "train_core: n_blocks=%d > %d", c->n_blocks, TMAXB);

@@ -135,9 +135,11 @@ __device__ __forceinline__ void tick(TrainTicks& t, int label) {
 // One CTA per 128 users: counts each user's active positions, packs users greedily into 64-row bins,
 // writes the row maps, and fills y of every INACTIVE position with the value the reference computes
 // there (sigmoid(ffn bias) for the cross-attention decoder: s = 0; 0.5 for the dot product).
+constexpr int TMAXL = 256;        // longest window the packing pass handles (a user's ACTIVE positions must fit a bin)
+
 __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
-  __shared__ unsigned char flg[128][TR];   // per (user of this CTA, position): validity bits
-  __shared__ int cnt[128], bin_of[128], start_of[128], base;
+  __shared__ unsigned char flg[128][TMAXL];   // per (user of this CTA, position): validity bits
+  __shared__ int cnt[128], skip_of[128], bin_of[128], start_of[128], base;
   const int t = threadIdx.x;
   const int L = a.L;
   const int user0 = blockIdx.x * 128;
@@ -157,12 +159,19 @@ __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
     int n = 0;
     if (t < users)
       for (int j = 0; j < L; ++j) n += flg[t][j] != 0;
+    // a bin holds 64 rows: a user with more active positions (possible only when L > 64) keeps the LAST 64 and
+    // is flagged in n_bins[1] — the host routes such batches to the per-op kernels before calling (carca.py)
+    skip_of[t] = n > TR ? n - TR : 0;
+    if (n > TR) {
+      n = TR;
+      atomicAdd(a.n_bins + 1, 1);
+    }
     cnt[t] = n;
   }
   __syncthreads();
   if (t == 0) {
     // bin capacity: 64 rows when there is enough work for every SM, fewer (>= 16) for small batches so the rows
-    // spread over more CTAs and each CTA's dependent chain of phases gets shorter; a user always fits (L <= 64)
+    // spread over more CTAs and each CTA's dependent chain of phases gets shorter; a user always fits (<= 64 rows)
     int total = 0;
     for (int q = 0; q < users; ++q) total += cnt[q];
     const long long est = (long long)total * a.B / users;            // rows of the whole batch, extrapolated
@@ -184,10 +193,16 @@ __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
   if (t < users && cnt[t] > 0) {
     const long long o = (long long)(base + bin_of[t]) * TR;
     int r = start_of[t];
+    int skip = skip_of[t];
     const int seg = start_of[t] | ((start_of[t] + cnt[t] - 1) << 8);
     for (int j = 0; j < L; ++j) {
       const int f = flg[t][j];
       if (f) {
+        if (skip > 0) {
+          --skip;
+          for (int q = 0; q < a.n_tuples; ++q) a.y[(long long)(user0 + t) * a.ldy + q * L + j] = ydef;   // (flagged)
+          continue;
+        }
         a.row_src[o + r] = (user0 + t) * L + j;
         a.row_info[o + r] = seg | (f << 16);
         ++r;
@@ -195,9 +210,6 @@ __global__ void __launch_bounds__(1024) train_pack_kernel(const TrainArgs a) {
     }
   }
 }
-
-// -------------------------------------------------------------------------------------------------- tiles
-// Thread (ty, tx) = (tid / 16, tid % 16).
 
 // Thread mapping of the tile products (512 threads = 16 warps): warp w owns the 8 rows [8 (w >> 1), +8) and the 32
 // columns [32 (w & 1), +32) of a 64 x 64 output; lane = (ty, tx) = (lane >> 3, lane & 7) owns rows 2 ty, 2 ty + 1 of

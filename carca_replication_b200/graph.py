@@ -38,6 +38,11 @@ class GraphedTrainStep:
         self.static = {k: batch[k].clone() for k in self.KEYS}
         self.seed = torch.zeros(1, dtype=torch.int64, device=dev)      # device seed word, bumped per replay
         self.graph = torch.cuda.CUDAGraph()
+        # windows longer than 64: the fused training kernels need every user's active positions to fit a 64-row bin,
+        # which cannot be checked inside a capture — check the example batch here and every batch before its replay
+        self.long_windows = batch["p_x"].shape[1] > 64 and hasattr(model, "max_active_positions")
+        if self.long_windows:
+            model._fits_override = self._fits(batch)
         N.lib().carca_set_seed_source(self.seed.data_ptr())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -49,6 +54,13 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         N.lib().carca_set_seed_source(None)
+        self.graph_is_fused = bool(getattr(model, "_fits_override", None))
+        if self.long_windows:
+            model._fits_override = None
+
+    def _fits(self, batch: Dict[str, Tensor]) -> bool:
+        L = batch["p_x"].shape[1]
+        return self.model.max_active_positions(batch["p_x"], [batch["o_x"][:, :L], batch["o_x"][:, L:]]) <= 64
 
     def _body(self) -> Tensor:
         b = self.static
@@ -65,5 +77,12 @@ class GraphedTrainStep:
     def __call__(self, batch: Dict[str, Tensor]) -> Tensor:
         for k in self.KEYS:
             self.static[k].copy_(batch[k], non_blocking=True)
+        if self.long_windows and self.graph_is_fused and not self._fits(batch):
+            # a user with more than 64 active positions: this step runs eagerly on the per-op kernels
+            N.lib().carca_set_seed_source(self.seed.data_ptr())
+            try:
+                return self._body()
+            finally:
+                N.lib().carca_set_seed_source(None)
         self.graph.replay()
         return self.loss

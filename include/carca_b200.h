@@ -256,8 +256,10 @@ int carca_cross_score_bwd(float* d_o, float* d_p, const carca_cross_grads* grads
  * (csrc/fused_train.cuh).  Padded positions reach no loss term, so every result equals the per-op entry
  * points' (carca_sa_block_*, carca_cross_score_*, carca_dot_score_*, carca_layernorm_*, carca_dropout) on the
  * same inputs, dropout masks included (same Philox sites and element indices).
- * Supported: d == 64, L <= 64, n_heads in {1, 2, 4}, n_blocks <= 8, 1 or 2 target tuples of L positions each;
- * returns -4 otherwise so the caller can use the per-op entry points.                                    */
+ * Supported: d == 64, L <= 256 with at most 64 ACTIVE positions per user (always true for L <= 64; otherwise the
+ * caller checks before calling — rows[1] counts the users that did not fit, whose rows are then truncated),
+ * n_heads in {1, 2, 4}, n_blocks <= 8, 1 or 2 target tuples of L positions each; returns -4 otherwise so the
+ * caller can use the per-op entry points.                                                                */
 typedef struct {
   int B, L, n_heads, n_blocks, n_tuples;
   int decoder_kind;                 /* 0 = DotProduct (position-wise, :360), 1 = CrossAttentionBlock */

@@ -330,11 +330,23 @@ def check_fused_train_edges(device):
              dict(shape=base, B=4, all_valid=False, decoder="ca", empty=True),
              dict(shape=dataclasses.replace(base, n_ctx=8), B=4, all_valid=False, decoder="ca"),
              dict(shape=dataclasses.replace(base, n_ctx=9), B=4, all_valid=False, decoder="dot"),
-             dict(shape=dataclasses.replace(base, n_blocks=1, n_heads=4), B=6, all_valid=False, decoder="ca")]
+             dict(shape=dataclasses.replace(base, n_blocks=1, n_heads=4), B=6, all_valid=False, decoder="ca"),
+             # L > 64: fused as long as every user's active positions fit one 64-row bin
+             dict(shape=dataclasses.replace(base, seq_len=100), B=6, all_valid=False, decoder="ca", max_valid=64),
+             dict(shape=dataclasses.replace(base, seq_len=200), B=5, all_valid=False, decoder="dot", max_valid=40),
+             dict(shape=dataclasses.replace(base, seq_len=100), B=4, all_valid=True, decoder="ca", expect_fused=False)]
     for case in cases:
         shape, B = case["shape"], case["B"]
         L = shape.seq_len
         b = synth.make_train_batch(shape, B, seed=9, all_valid=case["all_valid"])
+        if case.get("max_valid"):                      # left-pad further: at most max_valid positions per window
+            cut = L - case["max_valid"]
+            b["p_x"][:, :cut] = 0
+            b["o_x"][:, :cut] = 0
+            b["o_x"][:, L:L + cut] = 0
+            b["p_x"][0, cut:] = 7                      # one user uses the whole budget
+            b["o_x"][0, cut:L] = 9
+            b["o_x"][0, L + cut:] = 11
         if case.get("empty"):
             b["p_x"].zero_()
             b["o_x"].zero_()
@@ -346,7 +358,7 @@ def check_fused_train_edges(device):
             model.embeds.set_attr_table(table)
             model.use_fused_train = fused
             tg = [(b["o_x"][:, :L], None, b["o_c"][:, :L]), (b["o_x"][:, L:], None, b["o_c"][:, L:])]
-            assert model._fused_train_applies((b["p_x"], None, b["p_c"]), tg) == fused
+            assert model._fused_train_applies((b["p_x"], None, b["p_c"]), tg) == (fused and case.get("expect_fused", True))
             ops.set_dropout_seed(77)
             try:
                 y = model.forward((b["p_x"], None, b["p_c"]), tg)

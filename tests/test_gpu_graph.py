@@ -62,3 +62,65 @@ def test_graphed_step_draws_new_dropout_masks_every_replay():
     step = GraphedTrainStep(m, opt, b)
     losses = {round(step(b).item(), 7) for _ in range(6)}
     assert len(losses) >= 5          # same data, same weights: only the masks differ
+
+
+def test_graphed_step_with_long_windows_and_fused_adam():
+    """maxlen 100: the fused kernels run inside the graph while every user's active positions fit a 64-row bin; a
+    batch with a longer user takes the eager per-op step.  Both must track the plain eager loop (FusedAdam on both)."""
+    import dataclasses
+
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
+
+    dev = "cuda"
+    shape = dataclasses.replace(synth.TINY, seq_len=100)
+    L = shape.seq_len
+    table = synth.make_attr_table(shape, seed=3).to(dev)
+    batches = []
+    for i in range(4):
+        b = synth.make_train_batch(shape, 16, seed=80 + i)
+        cut = L - 40
+        if i != 2:                                  # batch 2 keeps its long users (> 64 active positions)
+            b["p_x"][:, :cut] = 0
+            b["o_x"][:, :cut] = 0
+            b["o_x"][:, L:L + cut] = 0
+        else:
+            b["p_x"][0, :] = 5
+            b["o_x"][0, :] = 6
+        batches.append({k: v.to(dev) for k, v in b.items()})
+
+    def fresh():
+        m = synth.build_model(shape, "ca", p=0.0, seed=3).to(dev).train()
+        m.embeds.set_attr_table(table)
+        return m, cb.FusedAdam(m.parameters(), lr=1e-3, betas=(0.9, 0.98))
+
+    m1, o1 = fresh()
+    sd0 = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    step = GraphedTrainStep(m1, o1, batches[0], warmup=2)
+    assert step.long_windows and step.graph_is_fused
+    m1.load_state_dict(sd0)
+    for st in o1.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    m2, o2 = fresh()
+    m2.load_state_dict(sd0)
+    loss_fn = cb.BinaryCrossEntropy()
+    for i, b in enumerate(batches):
+        n0 = N.lib().carca_launch_count()
+        l1 = step(b).clone()
+        eager_fallback = N.lib().carca_launch_count() - n0 > 50      # a replay launches nothing through the C ABI
+        assert eager_fallback == (i == 2)
+        o2.zero_grad()
+        y = m2.forward((b["p_x"], None, b["p_c"]), [(b["o_x"][:, :L], None, b["o_c"][:, :L]),
+                                                    (b["o_x"][:, L:], None, b["o_c"][:, L:])])
+        l2 = loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+        l2.backward()
+        o2.step()
+        assert abs(l1.item() - l2.item()) < 1e-5 * max(1.0, abs(l2.item()))
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if k.endswith("WK.bias"):
+            continue
+        assert torch.allclose(p1, p2, rtol=1e-3, atol=2e-5), k

@@ -8,7 +8,8 @@ from carca_replication_b200.graph import GraphedTrainStep
 decoder = sys.argv[1] if len(sys.argv) > 1 else "ca"
 batches = [int(x) for x in sys.argv[2:]] or [256, 1024, 4096]
 dev = torch.device("cuda")
-shape = synth.BEAUTY
+import dataclasses, os
+shape = dataclasses.replace(synth.BEAUTY, seq_len=int(os.environ.get("CARCA_L", synth.BEAUTY.seq_len)))   # maxlen sweep
 table = synth.make_attr_table(shape).to(dev)
 L = shape.seq_len
 for Bt in batches:
@@ -36,7 +37,7 @@ for Bt in batches:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         launches = (N.lib().carca_launch_count() - n0) // 10
-        line = f"B={Bt} fused={fused}: eager {ms:.3f} ms/step ({Bt / ms * 1e3:.0f} seqs/s, {launches} launches of ours, loss {loss.item():.4f})"
+        line = f"L={L} B={Bt} fused={fused} (applies={model._fused_train_applies((b['p_x'], None, b['p_c']), [(b['o_x'][:, :L], None, b['o_c'][:, :L]), (b['o_x'][:, L:], None, b['o_c'][:, L:])])}): eager {ms:.3f} ms/step ({Bt / ms * 1e3:.0f} seqs/s, {launches} launches of ours, loss {loss.item():.4f})"
         del loss          # the autograd graph it keeps alive would break the capture below
         try:
             step = GraphedTrainStep(model, optim, b, loss_fn)
