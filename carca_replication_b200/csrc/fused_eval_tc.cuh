@@ -182,6 +182,14 @@ __device__ __forceinline__ float2 pair_exchange(TcCtx& c, float2 mine) {
   return o;
 }
 
+// named barriers of the pipelined decoder loop: most warps only arrive, the iteration's two issuing warps wait
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---- MMA issue helpers (one thread) ---------------------------------------------------------
 // D[d .. d+N) (=) A(tmem, 8*ksteps cols at a_hi / a_lo) x B(smem hi / lo)^T, 3xTF32
 template <int N, int KSTEPS>
@@ -579,10 +587,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   umma::fence_after_sync();
   const uint32_t tmem0 = s.tmem_slot;                 // lane 0 (MMA operand / accumulator addresses)
   c.tmem = tmem0 + ((uint32_t)(32 * (w % 4)) << 16);  // this warp's lane quarter
-  if (c.half == 0) {   // constant [1,0,0,0,0,0,0,0] column block: the A operand of every bias step
-    float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    umma::tmem_st8(c.tmem + C_ONES, ones);
-  }
 
   TcTicks tk;
   tk.out = (a.dbg && a.dbg_stage == -1 && blockIdx.x == 0 && c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;
@@ -600,6 +604,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     __syncthreads();   // every thread is done with the previous tile (and has read s.next_tile)
     if (!first) tile = s.next_tile;
     if (tile >= n_tiles) break;
+    if (c.half == 0) {   // constant [1,0,0,0,0,0,0,0] column block: the A operand of every bias step (per tile: the
+      float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // pipelined decoder reuses these columns for scores)
+      umma::tmem_st8(c.tmem + C_ONES, ones);
+    }
     const long long trow0 = (long long)(tile / n_slices) * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
@@ -938,8 +946,128 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       const bool v1 = row_of(bin1, it1, sg1, t1r);
       if (c.half == 1) idn = cand_id(v1, sg1, t1r);
     }
+    // ---- cross-attention with two heads: SOFTWARE-PIPELINED loop.  Iteration q writes its query operand, hands it
+    // to the iteration's two issuing warps (a 256-count named barrier on which every other warp only ARRIVES),
+    // starts the gather of q+1 and then does softmax + score of iteration q-1, whose score MMAs were issued one
+    // iteration ago: MMA issue (~1.1 K cycles of one thread) and execution overlap the row work instead of sitting
+    // between two CTA-wide barriers.  Query operands and scores are double-buffered in TMEM (free since the
+    // attention output is folded into uval):  buffer 0: Q hi/lo at ACC_Q / QN_LO, scores at X_HI / X_LO;
+    // buffer 1: Q hi/lo at ACC_K / ACC_V, scores at QN_HI / ONES.  The issuer role rotates over the four warp pairs.
+    const bool pipelined = ca && H == 2;
+    if (pipelined) {
+      float p_acc = 0.f;
+      uint32_t p_bits = 0;
+      int p_W = 32, p_kw0 = 0, p_ubin = 0, p_usr = 0, p_t0r = 0;
+      bool p_v0 = false;
 #pragma unroll 1
-    for (int q = 0; q < n_iter; ++q) {
+      for (int q = 0; q <= n_iter; ++q) {
+        const bool cur = q < n_iter;   // q == n_iter only drains iteration n_iter - 1
+        const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
+        const int ubin = bin0;
+        float acc = 0.f;
+        uint32_t cross_bits = 0;
+        int W = 32, kw0 = 0, usr = 0, oid_next = 0, sg2 = 0, t2r = 0;
+        if (cur) {
+          usr = s.uuser[sg0];
+          const int ul = s.ulist[sg0];
+          const int useg0 = ul & 63, ulen = ul >> 8;
+          if (uctx) embed_finish_user<H>(c, oid, cvecs + sg0 * 64, e);
+          else embed_finish<H>(a, c, oid, ctab, nullptr, e, cv);
+          tick(tk, 14);
+          const int f_first = it0 * 128, f_last = min(f_first + 127, seg_cnt(ubin) * a.T - 1);
+          const int ul_a = s.ulist[seg_base(ubin) + f_first / a.T], ul_b = s.ulist[seg_base(ubin) + f_last / a.T];
+          const int w_lo = (ul_a & 63) & ~7, w_hi = (((ul_b & 63) + (ul_b >> 8)) + 7) & ~7;
+          const int wl = w_hi - w_lo;
+          W = wl <= 16 ? 8 : (wl <= 32 ? 16 : 32);
+          kw0 = min(w_lo, 64 - 2 * W);
+          if (oid != 0) {
+            const unsigned long long valid = ((unsigned long long)s.kbits[ubin][1] << 32) | s.kbits[ubin][0];
+            const unsigned long long segm = (ulen >= 64 ? ~0ull : ((1ull << ulen) - 1ull)) << useg0;
+            cross_bits = (uint32_t)((valid & segm) >> (kw0 + c.half * W));
+            if (W < 32) cross_bits &= (1u << W) - 1u;
+            if (a.residual_ca && c.half == 0) {   // residual term <o, wf> (:343,:345) from the folded tables
+              acc = twv;
+              if (uctx) {
+                acc += cws[sg0];
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
+              }
+            }
+          }
+          const int qb = q & 1;
+          st_operand<H>(c, qb ? C_ACCK : C_ACCQ, qb ? C_ACCV : C_QNLO, e);
+          bool v2 = false;
+          if (has2) {
+            locate(q + 2, bin2, it2);
+            v2 = row_of(bin2, it2, sg2, t2r);
+          }
+          if (c.half == 1) {   // s.oid <- ids of q+1; fetch ids of q+2
+            s.oid[c.row] = has1 ? idn : 0;
+            if (has2) idn = cand_id(v2, sg2, t2r);
+          }
+          tick(tk, 30);
+          umma::tmem_st_wait();
+          umma::fence_before_sync();
+          const int iwq = ((wu & 3) == (q & 3)) ? (wu >> 2) : -1;   // this iteration's issuers: one warp pair, one head each
+          if (iwq >= 0) {
+            named_bar_sync(5 + qb, TC_THREADS);
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+              const int h = iwq;
+              const uint32_t koff = (uint32_t)(h * DH / 4) * 2048u + (uint32_t)(ubin * 64 + kw0) * 16u;
+              const uint32_t dcol = tmem0 + (qb ? (h ? C_ONES : C_QNHI) : (h ? C_XLO : C_XHI)) + kw0;
+              const uint32_t qh = tmem0 + (qb ? C_ACCK : C_ACCQ) + h * DH, ql = tmem0 + (qb ? C_ACCV : C_QNLO) + h * DH;
+              const uint32_t kh = umma::smem_u32(s.k_hi) + koff, kl = umma::smem_u32(s.k_lo) + koff;
+              if (W == 8) issue_3x<16, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
+              else if (W == 16) issue_3x<32, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
+              else issue_3x<64, DH / 8>(dcol, qh, ql, kh, kl, 2048u);
+              commit(c);
+            }
+          } else {
+            named_bar_arrive(5 + qb, TC_THREADS);
+          }
+          c.ncommit++;
+          tick(tk, 33);
+          // s.oid was written by the row's half-1 thread above: pair barrier, then both halves read it
+          named_bar_sync(c.pair_bar, 64);
+          if (has1) {
+            oid_next = s.oid[c.row];
+            gather(oid_next, sg1, t1r, e, cv, twv);
+          }
+          if (q == 0) named_bar_sync(c.pair_bar, 64);   // (later iterations: the pair exchanges below order the next write)
+          tick(tk, 32);
+        }
+        if (q > 0) {   // softmax + score of iteration q-1
+          wait_mma(c);
+          tick(tk, 20);
+          const int pb = (q - 1) & 1;
+          const uint32_t t = c.tmem + p_kw0 + p_W * c.half;
+          const uint32_t s0 = t + (pb ? C_QNHI : C_XHI), s1 = t + (pb ? C_ONES : C_XLO);
+          const float* u0 = &s.uval[0][p_ubin * 64 + p_kw0 + p_W * c.half];
+          const float* u1 = &s.uval[1][p_ubin * 64 + p_kw0 + p_W * c.half];
+          if (p_W == 8) p_acc += softmax_pair_dot<8>(c, p_bits, sc, s0, s1, u0, u1);
+          else if (p_W == 16) p_acc += softmax_pair_dot<16>(c, p_bits, sc, s0, s1, u0, u1);
+          else p_acc += softmax_pair_dot<32>(c, p_bits, sc, s0, s1, u0, u1);
+          tick(tk, 21);
+          p_acc += pair_exchange(c, make_float2(p_acc, 0.f)).x;
+          p_acc += __ldg(a.dbf);
+          if (c.half == 0 && p_v0) a.y[(long long)p_usr * a.ldy + a.col0 + p_t0r] = 1.0f / (1.0f + expf(-p_acc));
+          tick(tk, 23);
+        }
+        p_acc = acc; p_bits = cross_bits; p_W = W; p_kw0 = kw0; p_ubin = ubin; p_usr = usr; p_t0r = t0r;
+        p_v0 = cur && v0;
+        if (cur) {   // shift the pipeline: (q+1) becomes current, (q+2) becomes next
+          if (has1) v0 = row_of(bin1, it1, sg0, t0r);
+          bin0 = bin1; it0 = it1;
+          bin1 = bin2; it1 = it2;
+          sg1 = sg2; t1r = t2r;
+          oid = oid_next;
+        }
+      }
+    }
+#pragma unroll 1
+    for (int q = 0; q < (pipelined ? 0 : n_iter); ++q) {
       const bool has1 = q + 1 < n_iter, has2 = q + 2 < n_iter;
       const int ubin = bin0;
       const int usr = s.uuser[sg0], ul = s.ulist[sg0];
@@ -1015,6 +1143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             }
           }
           c.ncommit++;
+          tick(tk, 33);
           // candidate rows of the next iteration: in flight while this iteration's attention runs (issued after
           // the MMAs so that the issuing warp does not wait on them first)
           if (hp == 0 && has1) {

@@ -4,7 +4,7 @@ import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from carca_replication_b200 import fused, synth
 LABELS = {0: "tile start", 1: "ids + profile embed", 2: "x store + LN1 + publish", 3: "Q MMA wait + Q lo",
-          4: "K MMA wait + K store + publish", 5: "V MMA", 6: "V store + publish", 30: "  window, bits, Q -> TMEM (st_operand)", 31: "  publish (st wait + fences + CTA sync)", 32: "  scores MMA issue + next-row gather issue", 20: "  scores MMA wait",
+          4: "K MMA wait + K store + publish", 5: "V MMA", 6: "V store + publish", 30: "  window, bits, Q -> TMEM (st_operand)", 31: "  publish (st wait + fences + CTA sync)", 32: "  next-row gather issue", 33: "  scores MMA issue (elected lane of warps 0/1)", 20: "  scores MMA wait",
           21: "  softmax pair + publish", 22: "  PV MMA (head pair)", 7: "O read + LN2 + publish", 8: "ffn_1 MMA",
           9: "LeakyReLU + publish", 10: "ffn_2 MMA", 11: "block out", 12: "final LN + publish",
           13: "dec K,V proj + store", 14: "loop top + candidate finish", 15: "(unused)", 23: "score + sigmoid + store"}
