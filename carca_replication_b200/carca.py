@@ -21,6 +21,13 @@ from .attrs import ItemAttrTable
 from .utils import get_mask
 
 
+def _invalidate_plans() -> None:
+    """.to() / .cuda() / .float() replace parameter tensors: cached inference plans (fused.py) must be rebuilt."""
+    from . import fused
+
+    fused.invalidate_plans()
+
+
 def _xavier(layer: nn.Module, zero_bias: bool = True) -> nn.Module:
     nn.init.xavier_uniform_(layer.weight)
     if zero_bias and getattr(layer, "bias", None) is not None:
@@ -102,6 +109,7 @@ class AllEmbedding(Embedding):
         return self._attr_table[0] if self._attr_table else None
 
     def _apply(self, fn, *args, **kwargs):
+        _invalidate_plans()
         for t in self._attr_table:                        # follow .to(device) / .cuda()
             t._apply(fn, *args, **kwargs)
         return super()._apply(fn, *args, **kwargs)
@@ -270,6 +278,10 @@ class SelfAttentionBlock(Encoder):
         self.dropout2 = nn.Dropout(p=p)
         self._block_index = 0                            # set by CARCA: selects the dropout sites
 
+    def _apply(self, fn, *args, **kwargs):
+        _invalidate_plans()
+        return super()._apply(fn, *args, **kwargs)
+
     def _params(self) -> Tuple[Tensor, ...]:
         a = self.attn
         return (self.norm1.weight, self.norm1.bias, a.WQ.weight, a.WQ.bias, a.WK.weight, a.WK.bias, a.WV.weight,
@@ -343,6 +355,10 @@ class CARCA(Model):
         for i, blk in enumerate(enc):
             if isinstance(blk, SelfAttentionBlock):
                 blk._block_index = i
+
+    def _apply(self, fn, *args, **kwargs):
+        _invalidate_plans()
+        return super()._apply(fn, *args, **kwargs)
 
     def encode(self, profile) -> Tuple[Tensor, Tensor]:
         p_x, p_a, p_c = profile

@@ -104,17 +104,37 @@ def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int
     return m, keep
 
 
-def _version_key(model, table: ItemAttrTable) -> Tuple:
-    return (id(table),) + tuple((p.data_ptr(), p._version) for p in model.parameters()) + \
-        tuple((b.data_ptr(), b._version) for b in model.buffers())
+# Bumped whenever one of this package's modules is moved / cast (`Module._apply`, i.e. .to() / .cuda() / .float()):
+# those REPLACE parameter tensors, which the cached tensor lists below would not notice.  In-place updates
+# (optimizer steps, load_state_dict) are caught through the tensors' version counters.
+_struct_epoch = [0]
 
 
-def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
-    """Inference plan for the model's current weights (cached until a parameter changes)."""
-    key = _version_key(model, table)
-    hit = _plans.get(model)
-    if hit is not None and hit[0] == key:
-        return hit[1], hit[2]
+def invalidate_plans() -> None:
+    _struct_epoch[0] += 1
+
+
+class _Entry:
+    __slots__ = ("epoch", "tensors", "key", "plan", "status", "m", "keep", "n_ctx")
+
+
+def _tensors_of(model) -> list:
+    return list(model.parameters()) + list(model.buffers())
+
+
+def _version_key(tensors, table: ItemAttrTable) -> Tuple:
+    return (id(table),) + tuple(t._version for t in tensors)
+
+
+def eval_plan(model, table: ItemAttrTable, n_ctx: int):
+    """Inference plan for the model's current weights (cached until a parameter changes) and the argument block of
+    the forward calls (device pointers of every parameter; rebuilt together with the plan)."""
+    ent = _plans.get(model)
+    if ent is not None and ent.epoch == _struct_epoch[0] and ent.n_ctx == n_ctx:
+        if ent.key == _version_key(ent.tensors, table):
+            return ent
+    tensors = _tensors_of(model)
+    key = _version_key(tensors, table)
     emb = model.embeds
     dev = emb.items_embed.weight.device
     Wf = _c(emb.feats_embed.weight)
@@ -129,10 +149,13 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int) -> Tensor:
     scratch = torch.empty((emb.items_embed.weight.shape[0], g), dtype=torch.float32, device=dev)
     src = _attr_source(table, None)
     N.call("carca_eval_prepare", N.f32p(plan), N.f32p(scratch), C.byref(m), C.byref(src), N.stream())
-    del keep
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    _plans[model] = (key, plan, status)
-    return plan, status
+    ent = _Entry()
+    ent.epoch, ent.tensors, ent.key, ent.n_ctx = _struct_epoch[0], tensors, key, n_ctx
+    ent.plan = plan
+    ent.status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ent.m, ent.keep = _model_params(model, table, None, n_ctx)     # the forward calls' argument block
+    _plans[model] = ent
+    return ent
 
 
 _scratch_cache: dict = {}
@@ -155,7 +178,7 @@ def _scratch(B: int, device) -> Tensor:
 def mma_timed_out(model) -> bool:
     """True if a tensor-core completion wait ever timed out for this model's plan (device sync)."""
     hit = _plans.get(model)
-    return bool(hit is not None and (int(hit[2].item()) & 1) != 0)
+    return bool(hit is not None and (int(hit.status.item()) & 1) != 0)
 
 
 def forward(model, profile, targets: Sequence, variant: Optional[int] = None, dbg: Optional[Tensor] = None,
@@ -180,14 +203,13 @@ def forward(model, profile, targets: Sequence, variant: Optional[int] = None, db
         o_x = torch.cat([as_ids(t[0]) for t in targets], dim=1)
         o_c = torch.cat([as_f32(t[2]) for t in targets], dim=1)
     T = o_x.shape[1]
-    plan, status = eval_plan(model, table, n_ctx)
-    m, keep = _model_params(model, table, None, n_ctx)
+    ent = eval_plan(model, table, n_ctx)
+    plan, status, m = ent.plan, ent.status, ent.m
     y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
     v = (VARIANT if variant is None else int(variant)) | (0x100 if per_user_ctx else 0)
     N.call("carca_eval_forward_opts", N.f32p(y), T, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
            N.i32p(o_x), N.f32p(o_c), B, L, T, v, N.i32p(status),
            None if dbg is None else N.f32p(dbg), int(dbg_stage), _scratch(B, p_x.device).data_ptr(), N.stream())
-    del keep
     return y
 
 
@@ -201,11 +223,10 @@ def forward_catalog(model, profile, ctx_user: Tensor, item_lo: int, n_cand: int,
     p_x, p_c, ctx_user = as_ids(p_x), as_f32(p_c), as_f32(ctx_user)
     B, L = p_x.shape
     n_ctx = p_c.shape[-1]
-    plan, status = eval_plan(model, table, n_ctx)
-    m, keep = _model_params(model, table, None, n_ctx)
+    ent = eval_plan(model, table, n_ctx)
+    plan, status, m = ent.plan, ent.status, ent.m
     y = torch.empty((B, n_cand), dtype=torch.float32, device=p_x.device)
     N.call("carca_eval_forward_catalog", N.f32p(y), n_cand, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
            N.f32p(ctx_user), int(item_lo), int(n_cand), B, L, VARIANT if variant is None else int(variant),
            N.i32p(status), _scratch(B, p_x.device).data_ptr(), N.stream())
-    del keep
     return y
