@@ -534,8 +534,118 @@ __device__ __forceinline__ float softmax_pair_dot(TcCtx& c, uint32_t bits, float
   return (z0 > 0.f ? d0 / z0 : 0.f) + (z1 > 0.f ? d1 / z1 : 0.f);
 }
 
-template <int H>
+
+// ---- cross-attention decoder, two heads, one thread per (user, candidate) row, fp32 FFMA ---------------------
+// A candidate attends only to the keys of its OWN user (mean ~8 of 50 for Beauty-shaped profiles), so an M = 128
+// score MMA over the bin's key window computes mostly masked products and pays a TMEM round trip, two barriers and
+// an MMA completion per 128 rows.  Here a thread owns a row: its query (the folded table row TQ[id] + the context
+// map, src/carca.py:238 with :85-95 folded) sits in 64 registers, the keys K_h[j] of its user are read from the
+// K operand in shared memory (k_hi holds the full fp32 value; lanes of one user read the same address: broadcast),
+// softmax runs online over key pairs, and the attention output is folded into u_h[j] = <V_h[j], wf_h> (see
+// softmax_pair_dot).  No TMEM, no barrier, no exchange between threads; exact fp32 products.
+struct DecRow {
+  int id, sg, t;
+  bool valid;
+};
+// query features of head h (32 of the 64 columns of TQ[id]); with h == 0 also the row's context and <T[id], wf>
+__device__ __forceinline__ void dec_gather(const TcArgs& a, const TcSmem& s, const DecRow& r, int h, bool uctx,
+                                           float (&e)[32], float (&cv)[8], float& twv) {
+  if (r.id == 0) return;
+  if (h == 0) {
+    if (!uctx) {
+      const float* ctx = a.o_c + (long long)s.uuser[r.sg] * a.oc_user + (long long)r.t * a.oc_tgt;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? ldg_now(ctx + k) : 0.f;
+    }
+    twv = ldg_now(a.tw + r.id);
+  }
+  const float* t = a.TQ + (long long)r.id * 64 + 32 * h;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 x = ldg_now4(t + 4 * i);
+    e[4 * i] = x.x; e[4 * i + 1] = x.y; e[4 * i + 2] = x.z; e[4 * i + 3] = x.w;
+  }
+}
+// residual term <o, wf> of the row (src/carca.py:343,:345) from the folded tables
+__device__ __forceinline__ float dec_residual(const TcArgs& a, const TcSmem& s, const DecRow& r, bool uctx,
+                                              const float* __restrict__ cws, const float (&cv)[8], float twv) {
+  if (r.id == 0 || !a.residual_ca) return 0.f;
+  float acc = twv;
+  if (uctx) {
+    acc += cws[r.sg];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(s.mcw[k], cv[k], acc);
+  }
+  return acc;
+}
+// head h of one row:  sum_j softmax_j(<q_h, K_h[j]> / sqrt(dh)) u_h[j]  over the keys of the row's user (:340)
+__device__ __forceinline__ float dec_head(const TcArgs& a, const TcSmem& s, const DecRow& r, int h, bool uctx,
+                                          const float* __restrict__ cvecs, float (&e)[32], const float (&cv)[8],
+                                          float sc) {
+  if (r.id == 0) return 0.f;   // padded candidate: query mask 0 -> attention row exactly 0 (:256)
+  const int ul = s.ulist[r.sg];
+  const int row0 = ul & 0xff, ulen = ul >> 8;
+  if (uctx) {
+    const float4* cp = reinterpret_cast<const float4*>(cvecs + r.sg * 64 + 32 * h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 m = cp[i];
+      e[4 * i] += m.x; e[4 * i + 1] += m.y; e[4 * i + 2] += m.z; e[4 * i + 3] += m.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < a.C) {
+        const float4* mp = reinterpret_cast<const float4*>(&s.mcqt[k][32 * h]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 m = mp[i];
+          e[4 * i] = fmaf(m.x, cv[k], e[4 * i]);
+          e[4 * i + 1] = fmaf(m.y, cv[k], e[4 * i + 1]);
+          e[4 * i + 2] = fmaf(m.z, cv[k], e[4 * i + 2]);
+          e[4 * i + 3] = fmaf(m.w, cv[k], e[4 * i + 3]);
+        }
+      }
+  }
+  // valid keys of the user's segment (a segment may hold position L-1 as a padding row)
+  const uint32_t* kb = &s.kbits[row0 >> 6][0];
+  unsigned long long m = (((unsigned long long)kb[1] << 32) | kb[0]) >> (row0 & 63);
+  if (ulen < 64) m &= (1ull << ulen) - 1ull;
+  const float4* const kh = reinterpret_cast<const float4*>(s.k_hi) + row0 + h * 8 * 128;
+  const float* const uh = s.uval[h] + row0;
+  float mx = -INFINITY, z = 0.f, d = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < ulen; j += 2) {
+    const int j1 = min(j + 1, ulen - 1);
+    float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+      const float4 k0 = kh[kc * 128 + j], k1 = kh[kc * 128 + j1];
+      const float* q = &e[4 * kc];
+      s0a = fmaf(q[0], k0.x, s0a); s0b = fmaf(q[1], k0.y, s0b);
+      s0a = fmaf(q[2], k0.z, s0a); s0b = fmaf(q[3], k0.w, s0b);
+      s1a = fmaf(q[0], k1.x, s1a); s1b = fmaf(q[1], k1.y, s1b);
+      s1a = fmaf(q[2], k1.z, s1a); s1b = fmaf(q[3], k1.w, s1b);
+    }
+    const bool ok0 = (m >> j) & 1ull, ok1 = (j + 1 < ulen) && ((m >> (j + 1)) & 1ull);
+    const float x0 = ok0 ? (s0a + s0b) * sc : -INFINITY, x1 = ok1 ? (s1a + s1b) * sc : -INFINITY;
+    const float mn = fmaxf(mx, fmaxf(x0, x1));
+    const float mref = (mn == -INFINITY) ? 0.f : mn;
+    const float corr = ex2_approx(mx - mref), p0 = ex2_approx(x0 - mref), p1 = ex2_approx(x1 - mref);
+    z = fmaf(z, corr, p0 + p1);
+    d = fmaf(d, corr, fmaf(p0, uh[j], p1 * uh[j1]));
+    mx = mn;
+  }
+  return z > 0.f ? d / z : 0.f;
+}
+
+// ROW_DEC: the two-head cross-attention decoder runs as the per-row fp32 loop above (default for H == 2); otherwise
+// (and for the dot decoder / four heads) the tcgen05 decoder loops below.  A template parameter, so that each kernel
+// is register-allocated for the one decoder it contains.
+template <int H, bool ROW_DEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
+  static_assert(!ROW_DEC || H == 2, "the per-row decoder is written for two heads");
   constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
   CARCA_DYN_SMEM(unsigned char, raw);
   TcSmem& s = *reinterpret_cast<TcSmem*>(raw);
@@ -893,6 +1003,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
       }
     }
+    if (ROW_DEC && ca) {   // per-row fp32 decoder (dec_head above); rows of iteration it+1 are
+      __syncthreads();                  // gathered while iteration it computes, ids are fetched two iterations ahead
+      tick(tk, 40);
+      const int total = n_seg * a.T;    // (segment, candidate) rows of the tile
+      const int n_it = (total + TC_THREADS - 1) / TC_THREADS;
+      const int per = (n_it + n_slices - 1) / n_slices;
+      const int it_lo = min(n_it, (tile % n_slices) * per), it_hi = min(n_it, it_lo + per);
+      const float bfv = __ldg(a.dbf);
+      auto row_at = [&](int it) {
+        DecRow r;
+        const int f = it * TC_THREADS + c.tid;
+        r.valid = it < it_hi && f < total;
+        r.sg = r.valid ? f / a.T : 0;
+        r.t = r.valid ? f - r.sg * a.T : 0;
+        r.id = 0;
+        if (r.valid) r.id = a.cat_lo > 0 ? a.cat_lo + r.t : ldg_now_i(a.o_x + (long long)s.uuser[r.sg] * a.T + r.t);
+        return r;
+      };
+      // the query halves (one per head) are prefetched in two stages: head 0 of the next row while this row's head 0
+      // runs, head 1 of the next row while its head 1 (and the next row's head 0) run — 96 live query registers
+      DecRow cur = row_at(it_lo), nxt = row_at(it_lo + 1);
+      float qa[32], qb[32], qc[32], cvc[8], cvn[8], twc = 0.f, twn = 0.f;
+      auto step = [&](int it, float(&c0)[32], float(&c1)[32], float(&n0)[32]) {
+        const DecRow nn = row_at(it + 2);
+        dec_gather(a, s, nxt, 0, uctx, n0, cvn, twn);
+        tick(tk, 41);
+        float acc = dec_residual(a, s, cur, uctx, cws, cvc, twc) + bfv;
+        acc += dec_head(a, s, cur, 0, uctx, cvecs, c0, cvc, sc);
+        dec_gather(a, s, nxt, 1, uctx, c0, cvn, twn);   // c0 is free now: it receives head 1 of the next row
+        acc += dec_head(a, s, cur, 1, uctx, cvecs, c1, cvc, sc);
+        if (cur.valid) a.y[(long long)s.uuser[cur.sg] * a.ldy + a.col0 + cur.t] = 1.0f / (1.0f + expf(-acc));
+        tick(tk, 42);
+        cur = nxt;
+        nxt = nn;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cvc[k] = cvn[k];
+        twc = twn;
+      };
+      // buffer rotation over three 32-float arrays: (head 0, head 1, next head 0) = (A, B, C) -> (C, A, B) -> (B, C, A)
+      dec_gather(a, s, cur, 0, uctx, qa, cvc, twc);
+      dec_gather(a, s, cur, 1, uctx, qb, cvc, twc);
+#pragma unroll 1
+      for (int it = it_lo; it < it_hi; it += 3) {
+        step(it, qa, qb, qc);
+        if (it + 1 < it_hi) step(it + 1, qc, qa, qb);
+        if (it + 2 < it_hi) step(it + 2, qb, qc, qa);
+      }
+      tk.out = nullptr;   // first tile only
+      continue;
+    }
+    const bool ca_mma = ROW_DEC ? false : ca;   // (ROW_DEC: only the dot decoder gets here)
     // iterations [it_lo, it_hi) of each bin handled by this work item (all of them unless the tile is sliced)
     const int n_it_a = (seg_cnt(0) * a.T + 127) / 128, n_it_b = (seg_cnt(1) * a.T + 127) / 128;
     const int per_a = (n_it_a + n_slices - 1) / n_slices, per_b = (n_it_b + n_slices - 1) / n_slices;
@@ -925,7 +1086,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     auto gather = [&](int id, int sg, int t, float(&e)[32], float(&cv)[8], float& twv) {
       embed_load<H>(a, c, id, tab,
                     uctx ? nullptr : a.o_c + (long long)s.uuser[sg] * a.oc_user + (long long)t * a.oc_tgt, e, cv);
-      if (ca && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
+      if (ca_mma && id != 0 && c.half == 0) twv = ldg_now(a.tw + id);
     };
     int bin0 = 0, it0 = 0, bin1 = 0, it1 = 0, bin2 = 0, it2 = 0;
     int sg0 = 0, t0r = 0, sg1 = 0, t1r = 0;
@@ -953,7 +1114,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     // between two CTA-wide barriers.  Query operands and scores are double-buffered in TMEM (free since the
     // attention output is folded into uval):  buffer 0: Q hi/lo at ACC_Q / QN_LO, scores at X_HI / X_LO;
     // buffer 1: Q hi/lo at ACC_K / ACC_V, scores at QN_HI / ONES.  The issuer role rotates over the four warp pairs.
-    const bool pipelined = ca && H == 2;
+    const bool pipelined = ca_mma && H == 2;
     if (pipelined) {
       float p_acc = 0.f;
       uint32_t p_bits = 0;
@@ -1079,7 +1240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       float acc = 0.f;
       uint32_t cross_bits = 0;
       int W = 32, kw0 = 0;
-      if (ca) {
+      if (ca_mma) {
         // key window of the iteration: the thread pair covers 2W consecutive keys starting at kw0 (multiple of 8)
         // that contain the segments of every user present in these 128 rows; softmax and PV touch only it
         const int f_first = it0 * 128, f_last = min(f_first + 127, seg_cnt(ubin) * a.T - 1);
@@ -1121,11 +1282,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         if (has2) idn = cand_id(v2, sg2, t2r);
       }
       tick(tk, 30);
-      if (ca) publish();
+      if (ca_mma) publish();
       else __syncthreads();
       tick(tk, 31);
       int oid_next = 0;
-      if (ca) {
+      if (ca_mma) {
 #pragma unroll
         for (int hp = 0; hp < H; hp += 2) {
           if (iw >= 0) {   // one head per issuer

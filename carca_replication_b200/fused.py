@@ -22,7 +22,9 @@ from .ops import _attr_source, _c, _embed_params, _struct, as_f32, as_ids
 _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 # kernel variant: 0 = best available (tensor-core kernel when the shape allows), 1 = fp32 FFMA
-# kernel, 2 = tcgen05 tensor-core kernel.  CARCA_FUSED_VARIANT overrides (benchmark comparisons).
+# kernel, 2 = tcgen05 tensor-core kernel (two-head cross-attention decoder as a per-row fp32 loop),
+# 3 = the same kernel with the decoder on tcgen05 score MMAs (the earlier default).
+# CARCA_FUSED_VARIANT overrides (benchmark comparisons).
 VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "0"))
 
 MAX_L, MAX_L_TC, MAX_CTX, MAX_BLOCKS, WIDTH = 52, 256, 8, 8, 64

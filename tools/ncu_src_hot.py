@@ -11,7 +11,8 @@ for r in rows:
         cur = r[1].split('/')[-1]
         continue
     if len(r) > 7 and r[0].isdigit():
-        samples = int(r[4] or 0); inst = int(r[7] or 0)
+        num = lambda x: int(x) if x.strip().lstrip('-').isdigit() else 0
+        samples = num(r[4]); inst = num(r[7])
         key = (cur, int(r[0]), r[1].strip()[:110])
         a = agg.setdefault(key, [0, 0]); a[0] += samples; a[1] += inst
         tot += samples
