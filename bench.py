@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-catalog", action="store_true")
     ap.add_argument("--catalog-users", type=int, default=1024)
     ap.add_argument("--rotate", type=int, default=8, help="distinct input batches cycled through")
+    ap.add_argument("--e2e-eager", action="store_true",
+                    help="e2e leg: issue the step's calls eagerly instead of replaying GraphedEvalStep")
     ap.add_argument("--no-graph", action="store_true",
                     help="time eager steps instead of CUDA-graph replays of them (device-resident leg)")
     return ap.parse_args()
@@ -323,19 +325,32 @@ def run_ours(args):
             for k, v in views(arena).items():
                 v.copy_(hb[k])
             host_arenas.append(arena)
-        dev_arenas = [torch.empty(h2d_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        NS = 3                                               # input slots: copies run up to two steps ahead
+        dev_arenas = [torch.empty(h2d_bytes, dtype=torch.uint8, device=dev) for _ in range(NS)]
+        for j, a_ in enumerate(dev_arenas):                  # valid ids in every slot before anything runs on it
+            a_.copy_(host_arenas[j % args.rotate])
         slots = [views(a_) for a_ in dev_arenas]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        ready = [torch.cuda.Event() for _ in range(NS)]
+        freed = [torch.cuda.Event() for _ in range(NS)]
         # the step's result (hits, ndcg sum, users, loss sum) is read back every step; the host waits for the
         # read of step i after it has queued step i+1, so the device never idles on the round trip
-        stats = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(2)]
-        stats_host = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
-        landed = [torch.cuda.Event(), torch.cuda.Event()]
+        stats_host = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(NS)]
+        landed = [torch.cuda.Event() for _ in range(NS)]
         results = []
+        # the public API for this loop is GraphedEvalStep (carca_replication_b200/graph.py): evaluate()'s per-batch
+        # body (CARCA.forward + BinaryCrossEntropy + rank metrics + the D2H copy of the accumulators) captured once
+        # per input slot and replayed; --e2e-eager issues the same calls eagerly (~0.2 ms of host time per step)
+        ev_steps = None
+        stats_dev = torch.zeros(4, dtype=torch.float64, device=dev)
+        if not args.e2e_eager:
+            from carca_replication_b200.graph import GraphedEvalStep
+
+            ev_steps = [GraphedEvalStep(model, dict(sl, o_c=sl["o_c"].expand(-1, T_, -1)), k=10, stats=stats_dev,
+                                        result=stats_host[j], static_inputs=True) for j, sl in enumerate(slots)]
+        stats = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(NS)]
 
         def upload(i):
-            slot = i % 2
+            slot = i % NS
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[slot])          # the step that last used this slot is done
                 dev_arenas[slot].copy_(host_arenas[i % args.rotate], non_blocking=True)
@@ -345,26 +360,32 @@ def run_ours(args):
             cur = torch.cuda.current_stream()
             for e in freed:
                 e.record(cur)
-            upload(0)
+            for j in range(min(NS - 1, n)):
+                upload(j)
             for i in range(n):
-                if i + 1 < n:
-                    upload(i + 1)
-                cur.wait_event(ready[i % 2])
-                sl = slots[i % 2]
-                step(dict(sl, o_c=sl["o_c"].expand(-1, T_, -1)))
-                freed[i % 2].record(cur)
-                st = stats[i % 2]
-                st[:3].copy_(acc)
-                st[3] = loss_sum
-                stats_host[i % 2].copy_(st, non_blocking=True)
-                landed[i % 2].record(cur)
+                if i + NS - 1 < n:
+                    upload(i + NS - 1)
+                cur.wait_event(ready[i % NS])
+                if ev_steps is not None:
+                    ev_steps[i % NS].replay()                # ends with the D2H copy of the accumulators
+                    freed[i % NS].record(cur)
+                else:
+                    sl = slots[i % NS]
+                    step(dict(sl, o_c=sl["o_c"].expand(-1, T_, -1)))
+                    freed[i % NS].record(cur)
+                    st = stats[i % NS]
+                    st[:3].copy_(acc)
+                    st[3] = loss_sum
+                    stats_host[i % NS].copy_(st, non_blocking=True)
+                landed[i % NS].record(cur)
                 if i > 0:                                    # the caller consumes step i-1's metrics
-                    landed[(i - 1) % 2].synchronize()
-                    results.append(float(stats_host[(i - 1) % 2][0]))
-            landed[(n - 1) % 2].synchronize()
-            results.append(float(stats_host[(n - 1) % 2][0]))
+                    landed[(i - 1) % NS].synchronize()
+                    results.append(float(stats_host[(i - 1) % NS][0]))
+            landed[(n - 1) % NS].synchronize()
+            results.append(float(stats_host[(n - 1) % NS][0]))
 
-        e2e_run(W)
+        e2e_run(max(W, args.rotate))                 # every pinned host arena has crossed PCIe once (the first
+                                                     # copy out of a pinned buffer runs at ~1/5 of the link rate)
         ms_e2e = timed(lambda _i: e2e_run(K), 1)
         clocks.__exit__(None, None, None)
 
@@ -391,9 +412,10 @@ def run_ours(args):
                                                     "(CARCA.forward + loss + metrics on one rotated batch)"
                                                     if graphs is not None else "eager steps")),
         "e2e": {"value": e2e, "unit": "users/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,
-                "ms_per_step": ms_e2e / K, "api": "CARCA.forward + BinaryCrossEntropy + rank metrics; per step one "
-                                                  "H2D copy of a pinned arena (ids, context, labels; issued one step "
-                                                  "ahead on a second stream) and one D2H read of the accumulators "
+                "ms_per_step": ms_e2e / K, "launch": "eager calls" if args.e2e_eager else "GraphedEvalStep (one CUDA "
+                "graph replay per step)", "api": "CARCA.forward + BinaryCrossEntropy + rank metrics; per step one "
+                                                  "H2D copy of a pinned arena (ids, context, labels; issued up to two "
+                                                  "steps ahead on a second stream) and one D2H read of the accumulators "
                                                   "(consumed by the host one step behind)"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
         "ops_per_op_path": per_op_table,

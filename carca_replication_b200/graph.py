@@ -1,4 +1,4 @@
-"""Whole-train-step CUDA graph (B200: launch-bound inner loops belong in graphs).
+"""Whole-train-step and whole-eval-step CUDA graphs (B200: launch-bound inner loops belong in graphs).
 
 The reference's step body (src/train.py:90-96: zero_grad, forward, BCE, backward, Adam) is ~170
 kernel launches of this library plus the optimizer's; at the reference batch size (256) the Python /
@@ -86,3 +86,70 @@ class GraphedTrainStep:
                 N.lib().carca_set_seed_source(None)
         self.graph.replay()
         return self.loss
+
+
+class GraphedEvalStep:
+    """The per-batch body of `evaluate` (src/train.py:44-50: forward, BCE loss, HR@k / NDCG@k accumulation)
+    captured once as a CUDA graph and replayed per batch — the eager body is ~8 launches whose Python / ctypes
+    dispatch (~0.2 ms) is as long as the kernels run for a Beauty-sized batch.
+
+        stats = torch.zeros(4, dtype=torch.float64, device=dev)   # hits@k, sum 1/log2(rank+2), users, sum of batch losses
+        step = GraphedEvalStep(model, first_batch, k=10, stats=stats)
+        for batch in loader: step(batch)                          # copies the batch into the static buffers, replays
+        hr, ndcg, loss = stats[0] / stats[2], stats[1] / stats[2], stats[3] / n_batches     # one read at the end
+
+    `batch`: dict of p_x, p_c, o_x, o_c, y_true on the device.  With `static_inputs=True` the tensors of `batch` ARE
+    the graph's input buffers (e.g. views into a device arena that the caller refills with one H2D copy per step) and
+    `replay()` runs the step on whatever they hold.  `result`: optional pinned host fp64[4]; the graph then ends with
+    an asynchronous device-to-host copy of `stats` into it (read it after synchronising on an event recorded behind
+    the replay).  Several steps (one per input slot) may share one `stats` tensor.
+    """
+    KEYS = ("p_x", "p_c", "o_x", "o_c", "y_true")
+
+    def __init__(self, model, batch: Dict[str, Tensor], k: int = 10, stats: Optional[Tensor] = None,
+                 result: Optional[Tensor] = None, static_inputs: bool = False,
+                 loss_fn: Optional[BinaryCrossEntropy] = None, warmup: int = 2):
+        from . import ops
+
+        if model.training:
+            raise ValueError("GraphedEvalStep captures the eval-mode forward: call model.eval() first")
+        dev = batch["p_x"].device
+        self.model, self.k = model, int(k)
+        self.loss_fn = loss_fn or BinaryCrossEntropy()
+        self.static = {key: (batch[key] if static_inputs else batch[key].clone()) for key in self.KEYS}
+        self.stats = stats if stats is not None else torch.zeros(4, dtype=torch.float64, device=dev)
+        if self.stats.dtype != torch.float64 or self.stats.numel() != 4 or not self.stats.is_contiguous():
+            raise ValueError("stats must be a contiguous float64[4] device tensor")
+        if result is not None and not (result.is_pinned() and result.dtype == torch.float64 and result.numel() == 4):
+            raise ValueError("result must be a pinned float64[4] host tensor")
+        self.result = result
+        self._rank = ops.rank_metrics_
+        keep = self.stats.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                  # builds the inference plan and every cached buffer
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._body()
+        self.stats.copy_(keep)                       # warm-up runs do not count
+
+    def _body(self) -> None:
+        b = self.static
+        y = self.model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
+        loss = self.loss_fn.forward(y, b["y_true"], get_mask(b["o_x"]))
+        self.stats[3:4].add_(loss)
+        self._rank(self.stats[:3], y, b["y_true"], self.k)
+        if self.result is not None:
+            self.result.copy_(self.stats, non_blocking=True)
+
+    def replay(self) -> None:
+        self.graph.replay()
+
+    def __call__(self, batch: Dict[str, Tensor]) -> None:
+        for key in self.KEYS:
+            if batch[key] is not self.static[key]:
+                self.static[key].copy_(batch[key], non_blocking=True)
+        self.graph.replay()

@@ -124,3 +124,57 @@ def test_graphed_step_with_long_windows_and_fused_adam():
         if k.endswith("WK.bias"):
             continue
         assert torch.allclose(p1, p2, rtol=1e-3, atol=2e-5), k
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_graphed_eval_step_matches_eager_evaluate_body(decoder):
+    """GraphedEvalStep (forward + BCE + HR@10 / NDCG@10 accumulation as one CUDA graph) against the same calls
+    issued eagerly, over several batches; also the static-input form with an expanded per-user context view and a
+    pinned host result."""
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import ops, synth
+    from carca_replication_b200.graph import GraphedEvalStep
+
+    dev = "cuda"
+    shape = synth.TINY
+    model = synth.build_model(shape, decoder, seed=4).to(dev).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=4).to(dev))
+    batches = [{k: v.to(dev) for k, v in synth.make_eval_batch(shape, 48, seed=70 + i).items()} for i in range(4)]
+    loss_fn = cb.BinaryCrossEntropy()
+    ref = torch.zeros(4, dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for b in batches:
+            y = model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])])
+            ref[3] += loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+            ops.rank_metrics_(ref[:3], y, b["y_true"], 10)
+    step = GraphedEvalStep(model, batches[0], k=10)
+    assert float(step.stats.abs().sum()) == 0.0          # warm-up and capture runs are not counted
+    for b in batches:
+        step(b)
+    assert torch.allclose(step.stats, ref, rtol=1e-6, atol=1e-9)
+    assert float(ref[2]) == 4 * 48
+
+    # static inputs (the caller refills the buffers), one context row per user as an expanded view, host result
+    T = batches[0]["o_x"].shape[1]
+    bufs = {k: v.clone() for k, v in batches[0].items()}
+    bufs["o_c"] = bufs["o_c"][:, :1, :].contiguous()
+    host = torch.zeros(4, dtype=torch.float64).pin_memory()
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    step2 = GraphedEvalStep(model, dict(bufs, o_c=bufs["o_c"].expand(-1, T, -1)), k=10, stats=stats, result=host,
+                            static_inputs=True)
+    ref2 = torch.zeros(4, dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for b in batches:
+            for k in ("p_x", "p_c", "o_x", "y_true"):
+                bufs[k].copy_(b[k])
+            bufs["o_c"].copy_(b["o_c"][:, :1, :])
+            step2.replay()
+            oc = b["o_c"][:, :1, :].expand(-1, T, -1)
+            y = model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, oc)])
+            ref2[3] += loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
+            ops.rank_metrics_(ref2[:3], y, b["y_true"], 10)
+    torch.cuda.synchronize()
+    assert torch.allclose(stats, ref2, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(host, ref2.cpu(), rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        GraphedEvalStep(model.train(), batches[0])
