@@ -1007,7 +1007,7 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
 static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
                            int T, int32_t* status, float* dbg, int dbg_stage, int cat_lo, int ctx_per_user, void* scratch,
-                           void* stream, int dec_mma) {
+                           void* stream, int dec) {
   const PlanLayout pl = plan_layout(m);
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -1056,16 +1056,20 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.chunk_slices = max(1, ceil_div(ceil_div(T, 128), 16));   // <= 16 candidate chunks per work item
   const size_t smem = sizeof(TcSmem);
   const long long n_tiles = (long long)ceil_div(B, 2) * a.chunk_slices;   // upper bound on the work items
-  if (m->n_heads == 2 && !dec_mma) {
-    auto k = fused_eval_tc_kernel<2, true>;
+  if (m->n_heads == 2 && dec == 2) {
+    auto k = fused_eval_tc_kernel<2, 2>;
+    TRY(allow_smem(k, smem));
+    CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
+  } else if (m->n_heads == 2 && dec == 1) {
+    auto k = fused_eval_tc_kernel<2, 1>;
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   } else if (m->n_heads == 2) {
-    auto k = fused_eval_tc_kernel<2, false>;
+    auto k = fused_eval_tc_kernel<2, 0>;
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   } else {
-    auto k = fused_eval_tc_kernel<4, false>;
+    auto k = fused_eval_tc_kernel<4, 0>;
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   }
@@ -1085,7 +1089,7 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
 #else
   const bool tc_ok = false;
 #endif
-  if ((variant == 2 || variant == 3) && !tc_ok)
+  if (variant >= 2 && variant <= 5 && !tc_ok)
     return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=256, H in {2,4}, status and scratch");
   if (variant == 1 && !ffma_ok) return fail(-4, "eval_forward: FFMA kernel needs d=64, L<=52, dh%%4==0");
   if (!ffma_ok && !tc_ok)
@@ -1095,9 +1099,14 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
                                   m->embed.pos_len);
   if (B <= 0 || T <= 0) return 0;
 #ifndef CARCA_EMU
-  if (variant == 2 || variant == 3 || (variant == 0 && tc_ok))
+  if ((variant >= 2 && variant <= 5) || (variant == 0 && tc_ok)) {
+    // two-head cross-attention decoder inside the kernel: 3 -> tcgen05 score MMAs, 4 -> fp32 loop with one row per
+    // thread, 5 -> fp32 loop over candidate pairs; otherwise pairs for the long candidate lists of catalog mode
+    // (7.0 vs 5.7 G scores/s) and one row per thread for sampled candidates (22.6 vs 20.9 M users/s)
+    const int dec = variant == 3 ? 0 : variant == 4 ? 1 : variant == 5 ? 2 : (cat_lo > 0 ? 2 : 1);
     return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, cat_lo,
-                           ctx_per_user, scratch, stream, variant == 3);
+                           ctx_per_user, scratch, stream, dec);
+  }
 #endif
   const PlanLayout pl = plan_layout(m);
   FusedArgs a;

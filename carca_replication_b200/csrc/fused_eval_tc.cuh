@@ -89,6 +89,8 @@ struct TcSmem {
   alignas(16) float dwf[64];
   float2 xch[2][2][128];                             // pair exchange: [slot][half][row]
   float uval[4][128];                                // decoder: <V_h[key], wf_h> per (head, key row of the tile)
+  float kc[2][128];                                  // pair decoder: <K_h[key], context map of the key's user>, or -inf
+                                                     //   for a key row that is padding (two heads)
   int oid[128];
   int ulist[128];                                    // segments of the tile: first row | length << 8
   int uuser[128];                                    //   and their users
@@ -640,12 +642,103 @@ __device__ __forceinline__ float dec_head(const TcArgs& a, const TcSmem& s, cons
   return z > 0.f ? d / z : 0.f;
 }
 
-// ROW_DEC: the two-head cross-attention decoder runs as the per-row fp32 loop above (default for H == 2); otherwise
-// (and for the dot decoder / four heads) the tcgen05 decoder loops below.  A template parameter, so that each kernel
-// is register-allocated for the one decoder it contains.
-template <int H, bool ROW_DEC>
+
+// ---- the same decoder over PAIRS of candidates of one user -------------------------------------------------------
+// The per-row loop above is bound by shared-memory operand delivery, not by FFMA issue: every FFMA takes one K value
+// through an LDS.128, and a 128-bit shared load costs 4 wavefronts per warp even when all lanes read the same address
+// (ncu: 4.0 wavefronts per LDS of dec_head).  Here a thread owns candidates 2p and 2p+1 of a user, so every K value it
+// loads feeds two FFMAs.  With one context row per user the context part of the query is the same for all of the
+// user's candidates and is folded into kc_h[j] = <K_h[j], context map> once per tile (kc = -inf marks a padding key):
+// the query is the folded table row itself.
+struct DecPair {
+  int id0, id1, sg, t0;   // candidates t0 and t0 + 1 of segment sg; t0 < 0: no such pair; id1 = 0 if t0 + 1 == T
+};
+// head h of both rows: e[0..32) = row 0, e[32..64) = row 1
+__device__ __forceinline__ void pair_gather(const TcArgs& a, const DecPair& r, int h, float (&e)[64]) {
+  const int ids[2] = {r.id0, r.id1};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (ids[k] == 0) continue;
+    const float* t = a.TQ + (long long)ids[k] * 64 + 32 * h;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x = ldg_now4(t + 4 * i);
+      float* o = &e[32 * k + 4 * i];
+      o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    }
+  }
+}
+// per-candidate context (not one row per user): q += McQ ctx for head h of row k of the pair
+__device__ __forceinline__ void pair_ctx_add(const TcArgs& a, const TcSmem& s, int h, int k, const float (&cv)[16],
+                                             float (&e)[64]) {
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk)
+    if (kk < a.C) {
+      const float4* mp = reinterpret_cast<const float4*>(&s.mcqt[kk][32 * h]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 m = mp[i];
+        float* o = &e[32 * k + 4 * i];
+        o[0] = fmaf(m.x, cv[8 * k + kk], o[0]); o[1] = fmaf(m.y, cv[8 * k + kk], o[1]);
+        o[2] = fmaf(m.z, cv[8 * k + kk], o[2]); o[3] = fmaf(m.w, cv[8 * k + kk], o[3]);
+      }
+    }
+}
+// head h: att[k] = sum_j softmax_j((<q_k, K_h[j]> + kc_h[j]) / sqrt(dh)) u_h[j] for both rows (src/carca.py:340)
+__device__ __forceinline__ void pair_head(const TcSmem& s, const DecPair& r, int h, const float (&e)[64], float sc,
+                                          float& att0, float& att1) {
+  const int ul = s.ulist[r.sg];
+  const int row0 = ul & 0xff, ulen = ul >> 8;
+  const float4* const kh = reinterpret_cast<const float4*>(s.k_hi) + row0 + h * 8 * 128;
+  const float* const uh = s.uval[h] + row0;
+  const float* const ch = s.kc[h] + row0;
+  float mxa = -INFINITY, za = 0.f, da = 0.f, mxb = -INFINITY, zb = 0.f, db = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < ulen; j += 2) {
+    const int j1 = min(j + 1, ulen - 1);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;   // a: row 0, b: row 1; 0 / 1: key j / j1
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+      const float4 k0 = kh[kc * 128 + j], k1 = kh[kc * 128 + j1];
+      const float* qa = &e[4 * kc];
+      const float* qb = &e[32 + 4 * kc];
+      a0 = fmaf(qa[0], k0.x, a0); a1 = fmaf(qa[0], k1.x, a1); b0 = fmaf(qb[0], k0.x, b0); b1 = fmaf(qb[0], k1.x, b1);
+      a0 = fmaf(qa[1], k0.y, a0); a1 = fmaf(qa[1], k1.y, a1); b0 = fmaf(qb[1], k0.y, b0); b1 = fmaf(qb[1], k1.y, b1);
+      a0 = fmaf(qa[2], k0.z, a0); a1 = fmaf(qa[2], k1.z, a1); b0 = fmaf(qb[2], k0.z, b0); b1 = fmaf(qb[2], k1.z, b1);
+      a0 = fmaf(qa[3], k0.w, a0); a1 = fmaf(qa[3], k1.w, a1); b0 = fmaf(qb[3], k0.w, b0); b1 = fmaf(qb[3], k1.w, b1);
+    }
+    const float c0 = ch[j], c1 = (j + 1 < ulen) ? ch[j1] : -INFINITY;
+    const float u0 = uh[j], u1 = uh[j1];
+    {
+      const float x0 = (a0 + c0) * sc, x1 = (a1 + c1) * sc;
+      const float mn = fmaxf(mxa, fmaxf(x0, x1));
+      const float mref = (mn == -INFINITY) ? 0.f : mn;
+      const float corr = ex2_approx(mxa - mref), p0 = ex2_approx(x0 - mref), p1 = ex2_approx(x1 - mref);
+      za = fmaf(za, corr, p0 + p1);
+      da = fmaf(da, corr, fmaf(p0, u0, p1 * u1));
+      mxa = mn;
+    }
+    {
+      const float x0 = (b0 + c0) * sc, x1 = (b1 + c1) * sc;
+      const float mn = fmaxf(mxb, fmaxf(x0, x1));
+      const float mref = (mn == -INFINITY) ? 0.f : mn;
+      const float corr = ex2_approx(mxb - mref), p0 = ex2_approx(x0 - mref), p1 = ex2_approx(x1 - mref);
+      zb = fmaf(zb, corr, p0 + p1);
+      db = fmaf(db, corr, fmaf(p0, u0, p1 * u1));
+      mxb = mn;
+    }
+  }
+  att0 = za > 0.f ? da / za : 0.f;
+  att1 = zb > 0.f ? db / zb : 0.f;
+}
+
+// DEC selects the two-head cross-attention decoder: 2 = fp32 loop over candidate PAIRS (default for H == 2), 1 = fp32
+// loop with one row per thread, 0 = the tcgen05 decoder loops below (also used by the dot decoder and by four heads).
+// A template parameter, so that each kernel is register-allocated for the one decoder it contains.
+template <int H, int DEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
-  static_assert(!ROW_DEC || H == 2, "the per-row decoder is written for two heads");
+  static_assert(DEC == 0 || H == 2, "the row / pair decoders are written for two heads");
+  constexpr bool ROW_DEC = DEC != 0;
   constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
   CARCA_DYN_SMEM(unsigned char, raw);
   TcSmem& s = *reinterpret_cast<TcSmem*>(raw);
@@ -1003,7 +1096,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
       }
     }
-    if (ROW_DEC && ca) {   // per-row fp32 decoder (dec_head above); rows of iteration it+1 are
+    if (DEC == 2 && ca) {   // fp32 decoder over candidate pairs (pair_head above)
+      __syncthreads();      // cvecs / K / uval of the tile are visible
+      {   // kc_h[key row] = <K_h[row], context map of the row's user> (thread (row, half): head = half); -inf: padding key
+        float kcv = (src >= 0 && my_pid != 0) ? 0.f : -INFINITY;
+        if (uctx && kcv == 0.f) {
+          const float4* kp = reinterpret_cast<const float4*>(s.k_hi) + c.half * 8 * 128 + c.row;
+          const float4* cp = reinterpret_cast<const float4*>(cvecs + seg_idx * 64 + 32 * c.half);
+          float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+          for (int kc = 0; kc < 8; ++kc) {
+            const float4 k = kp[kc * 128], m = cp[kc];
+            p0 = fmaf(k.x, m.x, p0); p1 = fmaf(k.y, m.y, p1);
+            p0 = fmaf(k.z, m.z, p0); p1 = fmaf(k.w, m.w, p1);
+          }
+          kcv = p0 + p1;
+        }
+        s.kc[c.half][c.row] = kcv;
+      }
+      __syncthreads();
+      tick(tk, 40);
+      const int P = (a.T + 1) / 2;      // candidate pairs per user
+      const int total = n_seg * P;      // (segment, pair) work items of the tile
+      const int n_it = (total + TC_THREADS - 1) / TC_THREADS;
+      const int per = (n_it + n_slices - 1) / n_slices;
+      const int it_lo = min(n_it, (tile % n_slices) * per), it_hi = min(n_it, it_lo + per);
+      const float bfv = __ldg(a.dbf);
+      auto pair_at = [&](int it) {
+        DecPair r;
+        const int f = it * TC_THREADS + c.tid;
+        r.id0 = r.id1 = 0;
+        r.sg = 0;
+        r.t0 = -1;
+        if (it < it_hi && f < total) {
+          r.sg = f / P;
+          r.t0 = 2 * (f - r.sg * P);
+          const bool two = r.t0 + 1 < a.T;
+          if (a.cat_lo > 0) {
+            r.id0 = a.cat_lo + r.t0;
+            r.id1 = two ? r.id0 + 1 : 0;
+          } else {
+            const int* px = a.o_x + (long long)s.uuser[r.sg] * a.T + r.t0;
+            r.id0 = ldg_now_i(px);
+            r.id1 = two ? ldg_now_i(px + 1) : 0;
+          }
+        }
+        return r;
+      };
+      // Two 64-register query buffers: A = head 0 of both rows, B = head 1.  Head 0 of the NEXT pair is gathered into A
+      // as soon as this pair's head 0 is done (covered by its head 1), head 1 into B after head 1 (covered by the next
+      // pair's head 0).
+      DecPair cur = pair_at(it_lo), nxt = pair_at(it_lo + 1);
+      float qA[64], qB[64];
+      pair_gather(a, cur, 0, qA);
+      pair_gather(a, cur, 1, qB);
+#pragma unroll 1
+      for (int it = it_lo; it < it_hi; ++it) {
+        const DecPair nn = pair_at(it + 2);
+        float res0 = bfv, res1 = bfv, cv[16];
+        if (cur.t0 >= 0) {
+          if (uctx) {
+            if (a.residual_ca) {
+              const float cw = cws[cur.sg];
+              if (cur.id0 != 0) res0 += ldg_now(a.tw + cur.id0) + cw;
+              if (cur.id1 != 0) res1 += ldg_now(a.tw + cur.id1) + cw;
+            }
+          } else {   // per-candidate context: read here (not prefetched) and folded into the queries
+            const float* ctx = a.o_c + (long long)s.uuser[cur.sg] * a.oc_user + (long long)cur.t0 * a.oc_tgt;
+            float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              cv[k] = (k < a.C && cur.id0 != 0) ? __ldg(ctx + k) : 0.f;
+              cv[8 + k] = (k < a.C && cur.id1 != 0) ? __ldg(ctx + a.oc_tgt + k) : 0.f;
+              r0 = fmaf(s.mcw[k], cv[k], r0);
+              r1 = fmaf(s.mcw[k], cv[8 + k], r1);
+            }
+            if (a.residual_ca) {
+              if (cur.id0 != 0) res0 += ldg_now(a.tw + cur.id0) + r0;
+              if (cur.id1 != 0) res1 += ldg_now(a.tw + cur.id1) + r1;
+            }
+            if (cur.id0 != 0) pair_ctx_add(a, s, 0, 0, cv, qA);
+            if (cur.id1 != 0) pair_ctx_add(a, s, 0, 1, cv, qA);
+          }
+        }
+        tick(tk, 41);
+        float h0a = 0.f, h0b = 0.f, h1a = 0.f, h1b = 0.f;
+        if (cur.id0 != 0 || cur.id1 != 0) pair_head(s, cur, 0, qA, sc, h0a, h0b);
+        pair_gather(a, nxt, 0, qA);
+        if (cur.id0 != 0 || cur.id1 != 0) {
+          if (!uctx) {
+            if (cur.id0 != 0) pair_ctx_add(a, s, 1, 0, cv, qB);
+            if (cur.id1 != 0) pair_ctx_add(a, s, 1, 1, cv, qB);
+          }
+          pair_head(s, cur, 1, qB, sc, h1a, h1b);
+        }
+        pair_gather(a, nxt, 1, qB);
+        if (cur.t0 >= 0) {   // a padded candidate scores sigmoid(bf): query mask 0 -> attention row 0, o = 0 (:94, :256)
+          float* yp = a.y + (long long)s.uuser[cur.sg] * a.ldy + a.col0 + cur.t0;
+          yp[0] = 1.0f / (1.0f + expf(-(res0 + (cur.id0 != 0 ? h0a + h1a : 0.f))));
+          if (cur.t0 + 1 < a.T) yp[1] = 1.0f / (1.0f + expf(-(res1 + (cur.id1 != 0 ? h0b + h1b : 0.f))));
+        }
+        tick(tk, 42);
+        cur = nxt;
+        nxt = nn;
+      }
+      tk.out = nullptr;   // first tile only
+      continue;
+    }
+    if (DEC == 1 && ca) {   // per-row fp32 decoder (dec_head above); rows of iteration it+1 are
       __syncthreads();                  // gathered while iteration it computes, ids are fetched two iterations ahead
       tick(tk, 40);
       const int total = n_seg * a.T;    // (segment, candidate) rows of the tile

@@ -22,8 +22,9 @@ from .ops import _attr_source, _c, _embed_params, _struct, as_f32, as_ids
 _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 # kernel variant: 0 = best available (tensor-core kernel when the shape allows), 1 = fp32 FFMA
-# kernel, 2 = tcgen05 tensor-core kernel (two-head cross-attention decoder as a per-row fp32 loop),
-# 3 = the same kernel with the decoder on tcgen05 score MMAs (the earlier default).
+# kernel, 2 = tcgen05 tensor-core kernel (two-head cross-attention decoder as an fp32 loop: one candidate row per
+# thread, or a pair of rows per thread in catalog mode), 3 = the same kernel with that decoder on tcgen05 score MMAs
+# over 128-row tiles, 4 / 5 = the row / pair loop forced.
 # CARCA_FUSED_VARIANT overrides (benchmark comparisons).
 VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "0"))
 

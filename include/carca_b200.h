@@ -413,9 +413,10 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
 /* Same call with the kernel variant chosen explicitly: 0 = best available, 1 = fp32 FFMA kernel
  * (L <= 52), 2 = tcgen05 tensor-core kernel (n_heads in {2,4}; L <= 256 with at most 64 non-padding
  * positions per user — always true for L <= 64; activations in TMEM, 3xTF32 fp32-grade MMAs; with
- * two heads the cross-attention decoder runs one thread per (user, candidate) row in fp32 against
- * the user's own keys), 3 = variant 2 with that decoder on tcgen05 score MMAs over 128-row tiles.
- * status (device int32[1], required for variants 2 / 3): bit 0 is set if an MMA completion wait timed
+ * two heads the cross-attention decoder runs in fp32 against the user's own keys, one thread per
+ * candidate row, or per pair of rows in catalog mode), 3 = variant 2 with that decoder on tcgen05
+ * score MMAs over 128-row tiles, 4 / 5 = the row / pair loop forced.
+ * status (device int32[1], required for variants 2 - 5): bit 0 is set if an MMA completion wait timed
  * out, bit 1 if some user had more than 64 non-padding positions (that user's scores are then
  * computed from its last 64 positions only: route such batches to the per-op entry points).  dbg (optional device [128,64]) receives the intermediate
  * activation `dbg_stage` of the first tile (10*block + {1: LN1, 2: Q, 3: K, 4: V, 5: attention +

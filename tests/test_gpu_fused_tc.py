@@ -48,16 +48,19 @@ def test_tc_kernel_vs_per_op_and_ffma_kernels(H, decoder, B, T, L, all_valid):
     assert topk_equal_up_to_ties(y_tc.cpu().numpy(), y_mod.cpu().numpy(), 10, tol=1e-6)
     if y_ff is not None:
         assert rel_err(y_tc.cpu().numpy(), y_ff.cpu().numpy()) < FP32_RTOL
-    with torch.no_grad():   # variant 3: the same kernel with the cross-attention decoder on the score MMAs
-        y_mma = fused.forward(model, prof, tgt, variant=3)
-        # one context row per user handed over as an expanded view (the other context path of both decoders)
-        o_cu = b["o_c"][:, :1, :].contiguous().expand(-1, T, -1)
+    # every decoder of the kernel (variant 2 picks one by mode): 3 = tcgen05 score MMAs, 4 = fp32 loop with one row
+    # per thread, 5 = fp32 loop over candidate pairs; and the second context path (one context row per user as an
+    # expanded view)
+    o_cu = b["o_c"][:, :1, :].contiguous().expand(-1, T, -1)
+    with torch.no_grad():
         y_u2 = fused.forward(model, prof, [(b["o_x"], None, o_cu)], variant=2)
-        y_u3 = fused.forward(model, prof, [(b["o_x"], None, o_cu)], variant=3)
+        for v in (3, 4, 5):
+            y_v = fused.forward(model, prof, tgt, variant=v)
+            y_uv = fused.forward(model, prof, [(b["o_x"], None, o_cu)], variant=v)
+            assert rel_err(y_v.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL, v
+            assert rel_err(y_u2.cpu().numpy(), y_uv.cpu().numpy()) < FP32_RTOL, v
+            assert topk_equal_up_to_ties(y_u2.cpu().numpy(), y_uv.cpu().numpy(), 10, tol=1e-6), v
     assert not fused.mma_timed_out(model)
-    assert rel_err(y_mma.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL
-    assert rel_err(y_u2.cpu().numpy(), y_u3.cpu().numpy()) < FP32_RTOL
-    assert topk_equal_up_to_ties(y_u2.cpu().numpy(), y_u3.cpu().numpy(), 10, tol=1e-6)
 
 
 def test_tc_kernel_is_the_default_and_two_launches():

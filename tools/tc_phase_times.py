@@ -8,8 +8,8 @@ LABELS = {0: "tile start", 1: "ids + profile embed", 2: "x store + LN1 + publish
           21: "  softmax pair + publish", 22: "  PV MMA (head pair)", 7: "O read + LN2 + publish", 8: "ffn_1 MMA",
           9: "LeakyReLU + publish", 10: "ffn_2 MMA", 11: "block out", 12: "final LN + publish",
           13: "dec K,V proj + store", 14: "loop top + candidate finish", 15: "(unused)", 23: "score + sigmoid + store",
-          40: "decoder tables visible (CTA sync)", 41: "  row decoder: ids of it+2, gather issue of it+1",
-          42: "  row decoder: both heads + sigmoid + store"}
+          40: "decoder tables visible (CTA sync)", 41: "  row / pair decoder: ids of it+2, gather issue of it+1",
+          42: "  row / pair decoder: both heads + sigmoid + store"}
 decoder = sys.argv[1] if len(sys.argv) > 1 else "ca"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 VAR = int(sys.argv[3]) if len(sys.argv) > 3 else 2
