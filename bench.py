@@ -9,6 +9,7 @@ One step = one evaluate() batch body (src/train.py:42-51) over `--batch` users p
   value : users/s with the step's inputs already resident in HBM (device-timed, CUDA events)
   e2e   : same metric through the public API from pinned HOST buffers: per step the ids/context
           H2D copies, forward, metrics and the D2H read of the accumulators are inside the timed region
+          (the step is replayed through carca_replication_b200.graph.GraphedEvalStep; --e2e-eager: eager calls)
   roofline / ops : per C-ABI op device time measured live with CUDA events, against MEASURED_PEAKS.json
   cpu_baseline : the oracle port of the reference timed on this box's host cores (bounded sample)
   train : fwd + BCE + bwd + Adam step seqs/s at the reference's batch size (256 per GPU)
