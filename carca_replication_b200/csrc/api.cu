@@ -1003,6 +1003,8 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
   return 0;
 }
 
+// row_src | row_seg | n_bins (packing pass), then — split decoder — Kg [rows, 64] | Ug [rows, 4] | useg [B] | cwsg [B]
+static int64_t eval_scratch_pack_bytes(int B) { return ((int64_t)sizeof(int) * (2ll * (B + 1) * 64 + 4) + 255) / 256 * 256; }
 #ifndef CARCA_EMU
 static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
@@ -1055,8 +1057,32 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
   a.chunk_slices = max(1, ceil_div(ceil_div(T, 128), 16));   // <= 16 candidate chunks per work item
   const size_t smem = sizeof(TcSmem);
+  // split decoder: two heads, cross-attention, one context row per user, packed rows addressable in 24 bits
+  if (dec == 3 && !(m->n_heads == 2 && m->decoder_kind == 1 && ctx_per_user && rows < (1ll << 24))) dec = cat_lo > 0 ? 2 : 1;
+  if (dec == 3) {
+    float* f = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + eval_scratch_pack_bytes(B));
+    a.Kg = f;
+    a.Ug = f + rows * 64;
+    a.useg = reinterpret_cast<int*>(f + rows * 68);
+    a.cwsg = f + rows * 68 + B;
+    a.chunk_slices = 1;   // the tile is only encoded here
+  }
   const long long n_tiles = (long long)ceil_div(B, 2) * a.chunk_slices;   // upper bound on the work items
-  if (m->n_heads == 2 && dec == 2) {
+  if (m->n_heads == 2 && dec == 3) {
+    auto k = fused_eval_tc_kernel<2, 3>;
+    TRY(allow_smem(k, smem));
+    CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
+    TRY(check_launch("fused_eval_tc (encoder)"));
+    DecPairsArgs d;
+    d.Kg = a.Kg; d.Ug = a.Ug; d.cwsg = a.cwsg; d.TQ = a.TQ; d.tw = a.tw; d.dbf = a.dbf;
+    d.useg = a.useg; d.o_x = o_x;
+    d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.cat_lo = cat_lo; d.residual_ca = m->residual_ca;
+    d.sc = 1.4426950408889634f / sqrtf(32.0f);
+    const long long items = (long long)B * ((T + 1) / 2);
+    auto dk = decode_pairs_kernel;
+    CARCA_LAUNCH(dk, dim3((unsigned)min((items + 255) / 256, 148ll * 64)), dim3(256), 0, S(stream), d);
+    return check_launch("decode_pairs");
+  } else if (m->n_heads == 2 && dec == 2) {
     auto k = fused_eval_tc_kernel<2, 2>;
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
@@ -1089,7 +1115,7 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
 #else
   const bool tc_ok = false;
 #endif
-  if (variant >= 2 && variant <= 5 && !tc_ok)
+  if (variant >= 2 && variant <= 6 && !tc_ok)
     return fail(-4, "eval_forward: tensor-core kernel needs d=64, L<=256, H in {2,4}, status and scratch");
   if (variant == 1 && !ffma_ok) return fail(-4, "eval_forward: FFMA kernel needs d=64, L<=52, dh%%4==0");
   if (!ffma_ok && !tc_ok)
@@ -1099,11 +1125,12 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
                                   m->embed.pos_len);
   if (B <= 0 || T <= 0) return 0;
 #ifndef CARCA_EMU
-  if ((variant >= 2 && variant <= 5) || (variant == 0 && tc_ok)) {
-    // two-head cross-attention decoder inside the kernel: 3 -> tcgen05 score MMAs, 4 -> fp32 loop with one row per
-    // thread, 5 -> fp32 loop over candidate pairs; otherwise pairs for the long candidate lists of catalog mode
-    // (7.0 vs 5.7 G scores/s) and one row per thread for sampled candidates (22.6 vs 20.9 M users/s)
-    const int dec = variant == 3 ? 0 : variant == 4 ? 1 : variant == 5 ? 2 : (cat_lo > 0 ? 2 : 1);
+  if ((variant >= 2 && variant <= 6) || (variant == 0 && tc_ok)) {
+    // two-head cross-attention decoder: 3 -> tcgen05 score MMAs inside the kernel, 4 -> fp32 loop with one row per
+    // thread, 5 -> fp32 loop over candidate pairs, 6 -> separate decoder kernel over all (user, pair) items; otherwise
+    // the separate kernel for the long candidate lists of catalog mode (8.4 G scores/s; pairs 7.0, rows 5.7) and one
+    // row per thread for sampled candidates (22.5 M users/s; separate kernel 21.9, pairs 20.9, tcgen05 19.8)
+    const int dec = variant == 3 ? 0 : variant == 4 ? 1 : variant == 5 ? 2 : variant == 6 ? 3 : (cat_lo > 0 ? 3 : 1);
     return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, cat_lo,
                            ctx_per_user, scratch, stream, dec);
   }
@@ -1146,7 +1173,10 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
   return check_launch("fused_eval");
 }
 
-int64_t carca_eval_scratch_bytes(int B) { return (int64_t)sizeof(int) * (2ll * (B + 1) * 64 + 4); }
+int64_t carca_eval_scratch_bytes(int B) {
+  const int64_t rows = ((int64_t)B + 1) * 64;
+  return eval_scratch_pack_bytes(B) + 4 * (rows * 64 + rows * 4 + 2ll * B);
+}
 
 int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                             const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,

@@ -74,6 +74,12 @@ struct TcArgs {
   int* n_bins;                                       // [0] bins written by the packing pass, [1] tile scheduler counter
   int chunk_slices;                                  // work item = (tile, one of this many slices of the candidate chunks):
                                                      //   long candidate lists (full catalog) are spread over CTAs
+  // DEC == 3 (split decoder): the kernel stops after the encoder and exports, per packed row, the decoder's key
+  // K[row][64] and (u_0, u_1, kc_0, kc_1), and per user its segment (first packed row | length << 24) and <ctx map, wf>
+  float* Kg;
+  float* Ug;
+  int* useg;
+  float* cwsg;
 };
 
 struct TcSmem {
@@ -732,8 +738,9 @@ __device__ __forceinline__ void pair_head(const TcSmem& s, const DecPair& r, int
   att1 = zb > 0.f ? db / zb : 0.f;
 }
 
-// DEC selects the two-head cross-attention decoder: 2 = fp32 loop over candidate PAIRS (default for H == 2), 1 = fp32
-// loop with one row per thread, 0 = the tcgen05 decoder loops below (also used by the dot decoder and by four heads).
+// DEC selects the two-head cross-attention decoder: 3 = none (keys exported for decode_pairs_kernel below), 2 = fp32
+// loop over candidate PAIRS, 1 = fp32 loop with one row per thread, 0 = the tcgen05 decoder loops below (also used by
+// the dot decoder and by four heads).
 // A template parameter, so that each kernel is register-allocated for the one decoder it contains.
 template <int H, int DEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
@@ -1096,7 +1103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         }
       }
     }
-    if (DEC == 2 && ca) {   // fp32 decoder over candidate pairs (pair_head above)
+    if (DEC >= 2 && ca) {   // fp32 decoder over candidate pairs (pair_head above), or export for the split decoder
       __syncthreads();      // cvecs / K / uval of the tile are visible
       {   // kc_h[key row] = <K_h[row], context map of the row's user> (thread (row, half): head = half); -inf: padding key
         float kcv = (src >= 0 && my_pid != 0) ? 0.f : -INFINITY;
@@ -1116,6 +1123,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       }
       __syncthreads();
       tick(tk, 40);
+      if (DEC == 3) {   // export keys and per-key / per-user terms; decode_pairs_kernel scores the candidates
+        const long long grow = trow0 + c.row;
+        float4* kg = reinterpret_cast<float4*>(a.Kg + grow * 64 + c.half * 32);
+        const float4* kp = reinterpret_cast<const float4*>(s.k_hi) + c.half * 8 * 128 + c.row;
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) kg[kc] = kp[kc * 128];
+        if (c.half == 0) {
+          reinterpret_cast<float4*>(a.Ug)[grow] = make_float4(s.uval[0][c.row], s.uval[1][c.row], s.kc[0][c.row], s.kc[1][c.row]);
+          if (head) {
+            a.useg[ru] = (int)grow | (seglen << 24);
+            a.cwsg[ru] = cws[seg_idx];
+          }
+        }
+        tk.out = nullptr;
+        continue;
+      }
       const int P = (a.T + 1) / 2;      // candidate pairs per user
       const int total = n_seg * P;      // (segment, pair) work items of the tile
       const int n_it = (total + TC_THREADS - 1) / TC_THREADS;
@@ -1553,6 +1576,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   umma::fence_before_sync();
   __syncthreads();
   if (w == 0) umma::tmem_free(tmem0, 512);
+}
+
+
+// ---- split decoder (DEC == 3): the candidates of ALL users as one grid of (user, candidate pair) work items -------
+// The in-kernel row / pair loops run on the encoder kernel's 8 warps per SM (255 registers, one CTA per SM).  This
+// kernel has no TMEM, no shared memory and half the registers (16 warps per SM); keys come from the rows the encoder
+// kernel exported (one 128-byte line per (key, head), read through L1 — lanes of one user read the same line),
+// everything else is pair_head's arithmetic.  One context row per user only (the context is folded into kc).
+// Measured: the default for catalog mode (8.4 vs 7.0 G scores/s: consecutive item ids, so the table rows of a warp
+// are contiguous); for 101 sampled candidates it is no faster than the in-kernel row loop (21.9 vs 22.5 M users/s:
+// one item per thread leaves the id -> table-row -> first-FFMA latency chain exposed, ncu: 72 % long-scoreboard
+// stalls, and prefetching it costs the registers the higher occupancy was bought with).
+struct DecPairsArgs {
+  const float *Kg, *Ug, *cwsg, *TQ, *tw, *dbf;
+  const int *useg, *o_x;
+  float* y;
+  long long ldy;
+  int col0, B, T, cat_lo, residual_ca;
+  float sc;
+};
+__global__ void __launch_bounds__(256, 2) decode_pairs_kernel(const DecPairsArgs a) {
+  const int P = (a.T + 1) / 2;
+  const long long total = (long long)a.B * P;
+  const float bfv = __ldg(a.dbf);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(p / P);
+    const int t0 = 2 * (int)(p - (long long)u * P);
+    const bool two = t0 + 1 < a.T;
+    int id0, id1;
+    if (a.cat_lo > 0) {
+      id0 = a.cat_lo + t0;
+      id1 = two ? id0 + 1 : 0;
+    } else {
+      const int* px = a.o_x + (long long)u * a.T + t0;
+      id0 = __ldg(px);
+      id1 = two ? __ldg(px + 1) : 0;
+    }
+    const int seg = __ldg(a.useg + u);
+    const int row0 = seg & 0xffffff, ulen = seg >> 24;
+    float res0 = bfv, res1 = bfv, att0 = 0.f, att1 = 0.f;
+    if (a.residual_ca) {
+      const float cw = __ldg(a.cwsg + u);
+      if (id0 != 0) res0 += __ldg(a.tw + id0) + cw;
+      if (id1 != 0) res1 += __ldg(a.tw + id1) + cw;
+    }
+    if (id0 != 0 || id1 != 0) {
+      const float4* const ug = reinterpret_cast<const float4*>(a.Ug) + row0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float e[64];   // query features of head h: row 0, row 1 (zeros for a padded candidate)
+        const int ids[2] = {id0, id1};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float4* t = reinterpret_cast<const float4*>(a.TQ + (long long)ids[k] * 64 + 32 * h);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = ids[k] != 0 ? __ldg(t + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* o = &e[32 * k + 4 * i];
+            o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+          }
+        }
+        const float4* const kh = reinterpret_cast<const float4*>(a.Kg + (long long)row0 * 64 + 32 * h);
+        float mxa = -INFINITY, za = 0.f, da = 0.f, mxb = -INFINITY, zb = 0.f, db = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < ulen; j += 2) {
+          const int j1 = min(j + 1, ulen - 1);
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;   // a: row 0, b: row 1; 0 / 1: key j / j1
+#pragma unroll
+          for (int kc = 0; kc < 8; ++kc) {
+            const float4 k0 = __ldg(kh + j * 16 + kc), k1 = __ldg(kh + j1 * 16 + kc);
+            const float* qa = &e[4 * kc];
+            const float* qb = &e[32 + 4 * kc];
+            a0 = fmaf(qa[0], k0.x, a0); a1 = fmaf(qa[0], k1.x, a1); b0 = fmaf(qb[0], k0.x, b0); b1 = fmaf(qb[0], k1.x, b1);
+            a0 = fmaf(qa[1], k0.y, a0); a1 = fmaf(qa[1], k1.y, a1); b0 = fmaf(qb[1], k0.y, b0); b1 = fmaf(qb[1], k1.y, b1);
+            a0 = fmaf(qa[2], k0.z, a0); a1 = fmaf(qa[2], k1.z, a1); b0 = fmaf(qb[2], k0.z, b0); b1 = fmaf(qb[2], k1.z, b1);
+            a0 = fmaf(qa[3], k0.w, a0); a1 = fmaf(qa[3], k1.w, a1); b0 = fmaf(qb[3], k0.w, b0); b1 = fmaf(qb[3], k1.w, b1);
+          }
+          const float4 g0 = __ldg(ug + j), g1 = __ldg(ug + j1);
+          const float u0 = h ? g0.y : g0.x, u1 = h ? g1.y : g1.x;
+          const float c0 = h ? g0.w : g0.z, c1 = (j + 1 < ulen) ? (h ? g1.w : g1.z) : -INFINITY;
+          {
+            const float x0 = (a0 + c0) * a.sc, x1 = (a1 + c1) * a.sc;
+            const float mn = fmaxf(mxa, fmaxf(x0, x1));
+            const float mref = (mn == -INFINITY) ? 0.f : mn;
+            const float corr = ex2_approx(mxa - mref), p0 = ex2_approx(x0 - mref), p1 = ex2_approx(x1 - mref);
+            za = fmaf(za, corr, p0 + p1);
+            da = fmaf(da, corr, fmaf(p0, u0, p1 * u1));
+            mxa = mn;
+          }
+          {
+            const float x0 = (b0 + c0) * a.sc, x1 = (b1 + c1) * a.sc;
+            const float mn = fmaxf(mxb, fmaxf(x0, x1));
+            const float mref = (mn == -INFINITY) ? 0.f : mn;
+            const float corr = ex2_approx(mxb - mref), p0 = ex2_approx(x0 - mref), p1 = ex2_approx(x1 - mref);
+            zb = fmaf(zb, corr, p0 + p1);
+            db = fmaf(db, corr, fmaf(p0, u0, p1 * u1));
+            mxb = mn;
+          }
+        }
+        if (id0 != 0 && za > 0.f) att0 += da / za;
+        if (id1 != 0 && zb > 0.f) att1 += db / zb;
+      }
+    }
+    // a padded candidate scores sigmoid(bf): query mask 0 -> attention row 0, o = 0 (src/carca.py:94, :256)
+    float* yp = a.y + (long long)u * a.ldy + a.col0 + t0;
+    yp[0] = 1.0f / (1.0f + expf(-(res0 + att0)));
+    if (two) yp[1] = 1.0f / (1.0f + expf(-(res1 + att1)));
+  }
 }
 
 // Packs the valid profile positions of every user into 64-row bins (two bins = one 128-row tile of

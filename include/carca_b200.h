@@ -413,10 +413,12 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
 /* Same call with the kernel variant chosen explicitly: 0 = best available, 1 = fp32 FFMA kernel
  * (L <= 52), 2 = tcgen05 tensor-core kernel (n_heads in {2,4}; L <= 256 with at most 64 non-padding
  * positions per user — always true for L <= 64; activations in TMEM, 3xTF32 fp32-grade MMAs; with
- * two heads the cross-attention decoder runs in fp32 against the user's own keys, one thread per
- * candidate row, or per pair of rows in catalog mode), 3 = variant 2 with that decoder on tcgen05
- * score MMAs over 128-row tiles, 4 / 5 = the row / pair loop forced.
- * status (device int32[1], required for variants 2 - 5): bit 0 is set if an MMA completion wait timed
+ * two heads the cross-attention decoder runs in fp32 against the user's own keys: one thread per
+ * candidate row inside the kernel, or — catalog mode — a second kernel over all (user, candidate
+ * pair) items reading the keys the first one exported to the scratch buffer), 3 = variant 2 with
+ * that decoder on tcgen05 score MMAs over 128-row tiles, 4 / 5 = the in-kernel row / pair loop
+ * forced, 6 = the separate decoder kernel forced (one context row per user; otherwise as 2).
+ * status (device int32[1], required for variants 2 - 6): bit 0 is set if an MMA completion wait timed
  * out, bit 1 if some user had more than 64 non-padding positions (that user's scores are then
  * computed from its last 64 positions only: route such batches to the per-op entry points).  dbg (optional device [128,64]) receives the intermediate
  * activation `dbg_stage` of the first tile (10*block + {1: LN1, 2: Q, 3: K, 4: V, 5: attention +
@@ -428,7 +430,8 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
                             int T, int variant, int32_t* status, float* dbg, int dbg_stage, void* scratch,
                             void* stream);
 
-/* Bytes of device scratch the tensor-core kernel needs for a batch of B users (variant 0 / 2): it
+/* Bytes of device scratch the tensor-core kernel needs for a batch of B users (variants 0, 2 - 6;
+ * packing tables, plus per packed row the exported decoder keys of the split decoder): it
  * first packs the VALID profile positions of every user into 64-row bins — Beauty-shaped profiles
  * are mostly left padding (src/data.py:112-113) and padded rows influence nothing the decoder reads
  * (src/carca.py:246-251) — so the encoder runs on valid rows only.                              */

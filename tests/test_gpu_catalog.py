@@ -14,7 +14,7 @@ def test_catalog_scores_and_ranks_vs_oracle(decoder, fused_on):
     S.check_catalog("cuda", "tiny", decoder, B=9, fused_on=fused_on)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_catalog_kernel_variants_agree_at_beauty_width(variant, monkeypatch):
     import dataclasses
 

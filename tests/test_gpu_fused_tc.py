@@ -49,12 +49,12 @@ def test_tc_kernel_vs_per_op_and_ffma_kernels(H, decoder, B, T, L, all_valid):
     if y_ff is not None:
         assert rel_err(y_tc.cpu().numpy(), y_ff.cpu().numpy()) < FP32_RTOL
     # every decoder of the kernel (variant 2 picks one by mode): 3 = tcgen05 score MMAs, 4 = fp32 loop with one row
-    # per thread, 5 = fp32 loop over candidate pairs; and the second context path (one context row per user as an
+    # per thread, 5 = fp32 loop over candidate pairs, 6 = split decoder kernel; and the second context path (one context row per user as an
     # expanded view)
     o_cu = b["o_c"][:, :1, :].contiguous().expand(-1, T, -1)
     with torch.no_grad():
         y_u2 = fused.forward(model, prof, [(b["o_x"], None, o_cu)], variant=2)
-        for v in (3, 4, 5):
+        for v in (3, 4, 5, 6):
             y_v = fused.forward(model, prof, tgt, variant=v)
             y_uv = fused.forward(model, prof, [(b["o_x"], None, o_cu)], variant=v)
             assert rel_err(y_v.cpu().numpy(), y_mod.cpu().numpy()) < FP32_RTOL, v
