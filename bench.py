@@ -558,22 +558,23 @@ def roofline(op_ms, shape, B, decoder, pk):
     dom = max(op_ms, key=op_ms.get)
     r = table[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum of one fused_eval_tc launch over 8192 Beauty-shaped users
-    # (ncu --set full, profiles/r01/ncu_fused_tc_v10_raw.csv): 27.06 MB = 3304 B/user.  Algorithmic HBM bytes with
+    # (ncu --set full, profiles/r01/ncu_fused_tc_v12_raw.csv): 27.24 MB read + 0.08 MB written = 3334 B/user.  Algorithmic HBM bytes with
     # one context row per user: ids + context in, scores out = 2.2 KB/user; the item tables and weights are
     # L2 hits (90 % sector hit rate), the scores were still in L2 when the kernel ended.
-    traffic = 3304.0 * B if (dom == "fused_forward" and shape.name == "beauty") else None
+    traffic = 3334.0 * B if (dom == "fused_forward" and shape.name == "beauty") else None
     roof = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
             "frac": r["frac"], "traffic": traffic, "peak_source": pk["source"],
             "share_of_step": op_ms[dom] / sum(op_ms.values())}
     if "frac_of_fp32_ffma_peak" in r:
         from carca_replication_b200 import fused
         if dom == "fused_forward" and fused.VARIANT != 1:
-            roof["note"] = ("tcgen05 kind::tf32 kernel, fp32-grade via the 3xTF32 split (3 MMAs per fp32 product). "
-                            "achieved = algorithmic FLOPs (all 50 profile positions per user, as the reference "
-                            "executes them) / measured time; the kernel runs the encoder on valid positions only "
-                            "(all_valid_profiles is the no-padding case). peak is the measured dense bf16 cuBLAS "
-                            "rate; the kernel is bound by the row operations between small dependent MMAs, not "
-                            "by tensor or HBM throughput (profiles/r01/README.md)")
+            roof["note"] = ("encoder on tcgen05 kind::tf32 (fp32-grade via the 3xTF32 split, 3 MMAs per fp32 product), "
+                            "cross-attention decoder as an fp32 loop per candidate row. achieved = algorithmic FLOPs "
+                            "(all 50 profile positions per user, as the reference executes them) / measured time; the "
+                            "kernel runs the encoder on valid positions only (all_valid_profiles is the no-padding "
+                            "case). peak is the measured dense bf16 cuBLAS rate; the encoder is bound by the row "
+                            "operations between small dependent MMAs, the decoder by shared-memory operand delivery, "
+                            "neither by tensor or HBM throughput (profiles/r01/README.md)")
         else:
             roof["note"] = ("fp32 CUDA-core (FFMA) kernel measured against the bf16 tensor peak; against the "
                             f"{FP32_FFMA_PEAK_TFLOPS:.1f} TFLOP/s fp32 FFMA peak the fraction is "

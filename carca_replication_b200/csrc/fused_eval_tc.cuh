@@ -119,9 +119,9 @@ struct TcCtx {
   int* status;
 };
 
-struct TcTicks { long long* out; int n; };
+struct TcTicks { long long* out; int n; bool tiles_only; };   // tiles_only (dbg_stage <= -2): tile starts of every tile of the CTA
 __device__ __forceinline__ void tick(TcTicks& t, int label) {
-  if (t.out && t.n < 2000) {
+  if (t.out && t.n < 2000 && (!t.tiles_only || label == 0)) {
     t.out[2 * t.n] = label;
     t.out[2 * t.n + 1] = clock64();
     ++t.n;
@@ -799,8 +799,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   c.tmem = tmem0 + ((uint32_t)(32 * (w % 4)) << 16);  // this warp's lane quarter
 
   TcTicks tk;
-  tk.out = (a.dbg && a.dbg_stage == -1 && blockIdx.x == 0 && c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;
+  tk.out = (a.dbg && (a.dbg_stage == -1 || a.dbg_stage <= -2) && blockIdx.x == (a.dbg_stage <= -2 ? -2 - a.dbg_stage : 0) &&
+            c.tid == 0) ? reinterpret_cast<long long*>(a.dbg) : nullptr;   // dbg_stage -2 - k: tile starts of CTA k
   tk.n = 0;
+  tk.tiles_only = a.dbg_stage <= -2;
   const int n_slices = max(1, a.chunk_slices);
   const int n_tiles = ((a.n_bins[0] + 1) / 2) * n_slices;   // work items: every slice re-encodes its tile (cheap next
                                                             // to >= 16 candidate chunks per user) and scores its share
@@ -1136,7 +1138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
             a.cwsg[ru] = cws[seg_idx];
           }
         }
-        tk.out = nullptr;
+        if (!tk.tiles_only) tk.out = nullptr;
         continue;
       }
       const int P = (a.T + 1) / 2;      // candidate pairs per user
@@ -1223,7 +1225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         cur = nxt;
         nxt = nn;
       }
-      tk.out = nullptr;   // first tile only
+      if (!tk.tiles_only) tk.out = nullptr;   // first tile only
       continue;
     }
     if (DEC == 1 && ca) {   // per-row fp32 decoder (dec_head above); rows of iteration it+1 are
@@ -1273,7 +1275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
         if (it + 1 < it_hi) step(it + 1, qc, qa, qb);
         if (it + 2 < it_hi) step(it + 2, qb, qc, qa);
       }
-      tk.out = nullptr;   // first tile only
+      if (!tk.tiles_only) tk.out = nullptr;   // first tile only
       continue;
     }
     const bool ca_mma = ROW_DEC ? false : ca;   // (ROW_DEC: only the dot decoder gets here)
@@ -1571,8 +1573,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       sg1 = sg2; t1r = t2r;
       oid = oid_next;
     }
-    tk.out = nullptr;   // first tile only
+    if (!tk.tiles_only) tk.out = nullptr;   // first tile only
   }
+  tick(tk, 0);   // (tiles_only: end of the CTA's last tile)
   umma::fence_before_sync();
   __syncthreads();
   if (w == 0) umma::tmem_free(tmem0, 512);

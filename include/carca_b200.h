@@ -422,7 +422,8 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
  * out, bit 1 if some user had more than 64 non-padding positions (that user's scores are then
  * computed from its last 64 positions only: route such batches to the per-op entry points).  dbg (optional device [128,64]) receives the intermediate
  * activation `dbg_stage` of the first tile (10*block + {1: LN1, 2: Q, 3: K, 4: V, 5: attention +
- * residual, 9: block output}, 100: final LayerNorm) for stage-by-stage validation.
+ * residual, 9: block output}, 100: final LayerNorm) for stage-by-stage validation; dbg_stage -1: phase
+ * clock ticks of CTA 0's first tile, -2 - k: start clocks of every tile CTA k processed (tools/tc_*.py).
  * variant | 0x100: o_c is [B, C], one context row per user shared by all of the user's candidates
  * (what src/data.py:185 builds; lets the host pass the base of an expanded [B,T,C] view).      */
 int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
