@@ -128,6 +128,7 @@ SIGNATURES = {
     "carca_bce_finalize": [vp, vp, vp],
     "carca_bce_bwd": [vp, vp, vp, vp, vp, vp, i64, f32, vp],
     "carca_rank_metrics": [vp, vp, vp, vp, i32, i32, i64, i64, i32, vp],
+    "carca_eval_metrics": [vp, vp, vp, vp, vp, i32, i32, i64, i64, i64, i32, f32, vp],
     "carca_adam_step": [P(AdamTensor), i32, f32, f32, f32, f32, f32, vp],
     "carca_build_eval_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, i32, i32, u64, vp],
     "carca_build_train_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, u64, vp],

@@ -812,6 +812,16 @@ int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, co
   return check_launch("rank_metrics");
 }
 
+int carca_eval_metrics(double* stats, double* work, const float* y_pred, const int32_t* y_true, const int32_t* o_x, int B,
+                       int T, int64_t ldy, int64_t ldt, int64_t ldx, int k, float eps, void* stream) {
+  if (B <= 0 || T <= 0) return 0;
+  const int grid = min(148 * 4, ceil_div(B, 8));
+  auto kern = eval_metrics_kernel;
+  CARCA_LAUNCH(kern, dim3(grid), dim3(256), 0, S(stream), stats, work, y_pred, y_true, o_x, B, T, (long long)ldy,
+               (long long)ldt, (long long)ldx, k, eps);
+  return check_launch("eval_metrics");
+}
+
 // ------------------------------------------------------------------------------------ optimizer
 int carca_adam_step(const carca_adam_tensor* tensors, int n_tensors, float lr, float beta1, float beta2, float eps,
                     float weight_decay, void* stream) {

@@ -229,4 +229,75 @@ __global__ void __launch_bounds__(256) catalog_rank_count_kernel(int* __restrict
   if (lane == 0 && c) atomicAdd(count + b, c);
 }
 
+// evaluate()'s per-batch reductions in ONE launch (src/train.py:44-50): masked BCE of the batch
+// (src/carca.py:441-444 with mask = get_mask(o_x), src/utils.py:6-7) and HR@k / NDCG@k (src/train.py:15-32, torch's
+// stable tie order) — y is read once, five small launches (mask, BCE sums, finalize, rank metrics, accumulator add)
+// become one.  One warp per row.  stats += [hits, sum 1/log2(rank+2), B, sum(l mask) / sum(mask)];  work (3 doubles,
+// zero before the first launch) holds the two BCE partial sums and a block counter; the last block to finish forms
+// the batch loss and clears it again, so replays (CUDA graphs) need no memset.
+__global__ void __launch_bounds__(256) eval_metrics_kernel(double* __restrict__ stats, double* __restrict__ work,
+                                                           const float* __restrict__ y, const int* __restrict__ yt,
+                                                           const int* __restrict__ ox, int B, int T, long long ldy,
+                                                           long long ldt, long long ldx, int k, float eps) {
+  __shared__ double part[4][8];
+  const int w = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int warps = blockDim.x / kWarp;
+  double hits = 0.0, ndcg = 0.0;
+  float ls = 0.f, ms = 0.f;
+  for (int b = blockIdx.x * warps + w; b < B; b += gridDim.x * warps) {
+    const float* yr = y + (long long)b * ldy;
+    const int* tr = yt + (long long)b * ldt;
+    const int* xr = ox + (long long)b * ldx;
+    for (int j0 = 0; j0 < T; j0 += kWarp) {
+      const int jj = j0 + lane;
+      const int lab = jj < T ? tr[jj] : 0;
+      if (jj < T && xr[jj] != 0) {
+        const float tv = (float)lab, yv = yr[jj];
+        ls += -(tv * logf(yv + eps) + (1.0f - tv) * logf(1.0f - yv + eps));
+        ms += 1.0f;
+      }
+      unsigned pos = __ballot_sync(kFull, lab != 0);
+      while (pos) {
+        const int l = __ffs((int)pos) - 1;
+        pos &= pos - 1;
+        const int j = j0 + l;
+        const float sj = yr[j];
+        const int labj = __shfl_sync(kFull, lab, l);
+        int cnt = 0;
+        for (int i = lane; i < T; i += kWarp) {
+          const float si = yr[i];
+          cnt += (si > sj) || (si == sj && i < j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+        if (cnt < k) {
+          hits += (double)labj;
+          ndcg += (double)(1.0f / log2f((float)(cnt + 2)));
+        }
+      }
+    }
+  }
+  ls = warp_sum(ls);
+  ms = warp_sum(ms);
+  if (lane == 0) { part[0][w] = hits; part[1][w] = ndcg; part[2][w] = (double)ls; part[3][w] = (double)ms; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double h = 0.0, n = 0.0, a = 0.0, m = 0.0;
+    for (int i = 0; i < warps; ++i) { h += part[0][i]; n += part[1][i]; a += part[2][i]; m += part[3][i]; }
+    atomicAdd(stats + 0, h);
+    atomicAdd(stats + 1, n);
+    atomicAdd(work + 0, a);
+    atomicAdd(work + 1, m);
+    __threadfence();
+    const double done = atomicAdd(work + 2, 1.0) + 1.0;
+    if (done == (double)gridDim.x) {   // last block: every partial sum above is visible (fence + atomics at L2)
+      __threadfence();
+      const double num = atomicAdd(work + 0, 0.0), den = atomicAdd(work + 1, 0.0);
+      atomicAdd(stats + 2, (double)B);
+      atomicAdd(stats + 3, (double)((float)num / (float)den));
+      work[0] = 0.0; work[1] = 0.0; work[2] = 0.0;
+    }
+  }
+}
+
 }  // namespace carca

@@ -123,7 +123,7 @@ class GraphedEvalStep:
         if result is not None and not (result.is_pinned() and result.dtype == torch.float64 and result.numel() == 4):
             raise ValueError("result must be a pinned float64[4] host tensor")
         self.result = result
-        self._rank = ops.rank_metrics_
+        self._metrics = ops.eval_metrics_
         keep = self.stats.clone()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -139,9 +139,13 @@ class GraphedEvalStep:
     def _body(self) -> None:
         b = self.static
         y = self.model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
-        loss = self.loss_fn.forward(y, b["y_true"], get_mask(b["o_x"]))
-        self.stats[3:4].add_(loss)
-        self._rank(self.stats[:3], y, b["y_true"], self.k)
+        if type(self.loss_fn) is BinaryCrossEntropy:       # loss + HR@k + NDCG@k in one launch
+            self._metrics(self.stats, y, b["y_true"], b["o_x"], self.k)
+        else:
+            from . import ops
+
+            self.stats[3:4].add_(self.loss_fn.forward(y, b["y_true"], get_mask(b["o_x"])))
+            ops.rank_metrics_(self.stats[:3], y, b["y_true"], self.k)
         if self.result is not None:
             self.result.copy_(self.stats, non_blocking=True)
 

@@ -603,6 +603,33 @@ def rank_metrics_(acc: Tensor, y_pred: Tensor, y_true: Tensor, k: int, first_ran
            y_pred.data_ptr(), y_true.data_ptr(), B, T, y_pred.stride(0), y_true.stride(0), int(k), N.stream())
 
 
+_eval_work: dict = {}
+
+
+def eval_metrics_(stats: Tensor, y_pred: Tensor, y_true: Tensor, o_x: Tensor, k: int, eps: float = 1e-8) -> None:
+    """stats (fp64[4], device) += [hits@k, sum 1/log2(rank+2), rows, masked BCE of the batch]: the per-batch
+    reductions of evaluate() (src/train.py:44-50) in one launch; mask = get_mask(o_x) (src/utils.py:6-7)."""
+    N.require_device(stats, y_pred, y_true, o_x)
+    if stats.dtype != torch.float64 or stats.numel() != 4 or not stats.is_contiguous():
+        raise ValueError("stats must be a contiguous float64[4] device tensor")
+    y_pred = y_pred if y_pred.dtype == torch.float32 else y_pred.float()
+    y_true = y_true if y_true.dtype == torch.int32 else y_true.to(torch.int32)
+    o_x = as_ids(o_x)
+    if y_pred.stride(-1) != 1:
+        y_pred = y_pred.contiguous()
+    if y_true.stride(-1) != 1:
+        y_true = y_true.contiguous()
+    if o_x.stride(-1) != 1:
+        o_x = o_x.contiguous()
+    B, T = y_pred.shape
+    key = str(stats.device)
+    work = _eval_work.get(key)
+    if work is None:      # scratch of the kernel (it leaves it zero again); one per device, calls on a stream are ordered
+        work = _eval_work[key] = torch.zeros(3, dtype=torch.float64, device=stats.device)
+    N.call("carca_eval_metrics", stats.data_ptr(), work.data_ptr(), y_pred.data_ptr(), y_true.data_ptr(), o_x.data_ptr(),
+           B, T, y_pred.stride(0), y_true.stride(0), o_x.stride(0), int(k), float(eps), N.stream())
+
+
 # ------------------------------------------------------------------------------- module variants (SURVEY §8f N3)
 class FeatsFn(torch.autograd.Function):
     """q = Wf [a | c] + bf (src/carca.py:113, :138): dense `a` tensor or the device-resident ItemAttrTable."""

@@ -47,19 +47,16 @@ def evaluate(model: Model, loader: DataLoader, device: str, k: int,
     [hits, ndcg, users, loss_sum, n_batches] before the single device->host read.
     """
     model = model.eval().to(device)
-    loss_fn = BinaryCrossEntropy()
-    acc = _metric_acc(device)
-    loss_sum = torch.zeros((), dtype=torch.float32, device=device)
+    acc = torch.zeros(4, dtype=torch.float64, device=device)     # hits, ndcg, users, sum of batch losses
     n_batches = 0
     with torch.no_grad():
         for batch in loader:
             p_x, p_a, p_c, o_x, o_a, o_c, y_true = to(*batch, device=device)
             y_pred = model.forward(profile=(p_x, p_a, p_c), targets=[(o_x, o_a, o_c)])
-            loss_sum += loss_fn.forward(y_pred, y_true, get_mask(o_x))
-            ops.rank_metrics_(acc, y_pred, y_true, k)
+            # BinaryCrossEntropy over get_mask(o_x) + compute_HR + compute_NDCG of the batch in one launch
+            ops.eval_metrics_(acc, y_pred, y_true, o_x, k)
             n_batches += 1
-    stats = torch.cat([acc, loss_sum.double().reshape(1),
-                       torch.tensor([float(n_batches)], dtype=torch.float64, device=device)])
+    stats = torch.cat([acc, torch.tensor([float(n_batches)], dtype=torch.float64, device=device)])
     if reduce_fn is not None:
         reduce_fn(stats)
     hits, ndcg, total, lsum, nb = stats.tolist()          # the one device->host sync

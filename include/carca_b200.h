@@ -346,6 +346,14 @@ int carca_adam_step(const carca_adam_tensor* tensors, int n_tensors, float lr, f
 int carca_rank_metrics(double* acc, int32_t* first_rank, const float* y_pred, const int32_t* y_true, int B,
                        int T, int64_t ldy, int64_t ldt, int k, void* stream);
 
+/* The per-batch reductions of evaluate() (src/train.py:44-50) in one launch: stats[0] += hits@k, stats[1] += sum
+ * 1/log2(rank+2) (as carca_rank_metrics), stats[2] += B, stats[3] += the batch's masked BCE
+ * sum(l * mask) / sum(mask) with mask = (o_x != 0) (src/carca.py:441-444, src/utils.py:6-7, eps on probabilities).
+ * stats: fp64[4] device accumulators; work: fp64[3] device scratch, zero before the first call (the kernel leaves it
+ * zero again, so the call can be replayed inside a CUDA graph).                                              */
+int carca_eval_metrics(double* stats, double* work, const float* y_pred, const int32_t* y_true, const int32_t* o_x, int B,
+                       int T, int64_t ldy, int64_t ldt, int64_t ldx, int k, float eps, void* stream);
+
 /* ------------------------------------------------------------------ batch construction */
 /* The users' interaction log on the device, CSR over users: items of user u (chronological) are
  * items[rowptr[u] .. rowptr[u+1]) and ctx[j, :] is the context of interaction j — what

@@ -185,6 +185,19 @@ def check_metrics(device):
     loss.backward()
     assert abs(loss.item() - float(z["loss"])) < 1e-5
     np.testing.assert_allclose(yv.grad.cpu().numpy(), z["dy"], rtol=1e-4, atol=1e-8)
+    # the same three reductions in one launch (carca_eval_metrics: the per-batch body of evaluate()); called twice,
+    # the kernel has to leave its scratch clean for the next call
+    from carca_replication_b200 import ops
+    o_x = (m != 0).to(torch.int32)
+    stats = torch.zeros(4, dtype=torch.float64, device=device)
+    for _ in range(2):
+        ops.eval_metrics_(stats, y, yt, o_x, k)
+    st = stats.cpu().numpy()
+    assert st[0] == 2 * float(z["HR"]) and st[2] == 2 * y.shape[0]
+    assert abs(st[1] - 2 * float(z["NDCG"])) < 2e-4 and abs(st[3] - 2 * float(z["loss"])) < 2e-5
+    stats.zero_()
+    ops.eval_metrics_(stats, y_ties, yt, o_x, k)
+    assert float(stats[0]) == float(z["HR_stable"]) and abs(float(stats[1]) - float(z["NDCG_stable"])) < 1e-4
 
 
 def check_knn(device):

@@ -151,7 +151,7 @@ def test_graphed_eval_step_matches_eager_evaluate_body(decoder):
     assert float(step.stats.abs().sum()) == 0.0          # warm-up and capture runs are not counted
     for b in batches:
         step(b)
-    assert torch.allclose(step.stats, ref, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(step.stats, ref, rtol=1e-5, atol=1e-9)     # (loss: one-launch reduction vs three kernels)
     assert float(ref[2]) == 4 * 48
 
     # static inputs (the caller refills the buffers), one context row per user as an expanded view, host result
@@ -174,7 +174,7 @@ def test_graphed_eval_step_matches_eager_evaluate_body(decoder):
             ref2[3] += loss_fn.forward(y, b["y_true"], cb.get_mask(b["o_x"]))
             ops.rank_metrics_(ref2[:3], y, b["y_true"], 10)
     torch.cuda.synchronize()
-    assert torch.allclose(stats, ref2, rtol=1e-6, atol=1e-9)
-    assert torch.allclose(host, ref2.cpu(), rtol=1e-6, atol=1e-9)
+    assert torch.allclose(stats, ref2, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(host, ref2.cpu(), rtol=1e-5, atol=1e-9)
     with pytest.raises(ValueError):
         GraphedEvalStep(model.train(), batches[0])
