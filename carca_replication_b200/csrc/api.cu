@@ -1067,6 +1067,12 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
   a.chunk_slices = max(1, ceil_div(ceil_div(T, 128), 16));   // <= 16 candidate chunks per work item
   const size_t smem = sizeof(TcSmem);
+  // dec < 0: chosen here by mode and, for two-head cross-attention, on the device by profile density (TcArgs::auto_dec)
+  const bool autosel = dec < 0;
+  if (autosel) dec = cat_lo > 0 ? 3 : 1;
+  a.auto_dec = (autosel && m->n_heads == 2 && m->decoder_kind == 1) ? 1 : 0;
+  TcArgs a_dense = a;          // the tcgen05-decoder launch of the same call
+  a_dense.auto_dec = 2;
   // split decoder: two heads, cross-attention, one context row per user, packed rows addressable in 24 bits
   if (dec == 3 && !(m->n_heads == 2 && m->decoder_kind == 1 && ctx_per_user && rows < (1ll << 24))) dec = cat_lo > 0 ? 2 : 1;
   if (dec == 3) {
@@ -1088,10 +1094,11 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
     d.useg = a.useg; d.o_x = o_x;
     d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.cat_lo = cat_lo; d.residual_ca = m->residual_ca;
     d.sc = 1.4426950408889634f / sqrtf(32.0f);
+    d.n_bins = n_bins; d.auto_dec = a.auto_dec;
     const long long items = (long long)B * ((T + 1) / 2);
     auto dk = decode_pairs_kernel;
     CARCA_LAUNCH(dk, dim3((unsigned)min((items + 255) / 256, 148ll * 64)), dim3(256), 0, S(stream), d);
-    return check_launch("decode_pairs");
+    TRY(check_launch("decode_pairs"));
   } else if (m->n_heads == 2 && dec == 2) {
     auto k = fused_eval_tc_kernel<2, 2>;
     TRY(allow_smem(k, smem));
@@ -1109,7 +1116,15 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles, 148ll)), dim3(TC_THREADS), smem, S(stream), a);
   }
-  return check_launch("fused_eval_tc");
+  TRY(check_launch("fused_eval_tc"));
+  if (a.auto_dec) {   // dense profiles: the same forward with the tcgen05 decoder (returns at once otherwise)
+    const long long n_tiles_d = (long long)ceil_div(B, 2) * a_dense.chunk_slices;
+    auto k = fused_eval_tc_kernel<2, 0>;
+    TRY(allow_smem(k, smem));
+    CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles_d, 148ll)), dim3(TC_THREADS), smem, S(stream), a_dense);
+    TRY(check_launch("fused_eval_tc (dense)"));
+  }
+  return 0;
 }
 #endif
 
@@ -1138,9 +1153,10 @@ static int eval_forward_any(float* y, int64_t ldy, int col0, const float* plan, 
   if ((variant >= 2 && variant <= 6) || (variant == 0 && tc_ok)) {
     // two-head cross-attention decoder: 3 -> tcgen05 score MMAs inside the kernel, 4 -> fp32 loop with one row per
     // thread, 5 -> fp32 loop over candidate pairs, 6 -> separate decoder kernel over all (user, pair) items; otherwise
-    // the separate kernel for the long candidate lists of catalog mode (8.4 G scores/s; pairs 7.0, rows 5.7) and one
-    // row per thread for sampled candidates (22.5 M users/s; separate kernel 21.9, pairs 20.9, tcgen05 19.8)
-    const int dec = variant == 3 ? 0 : variant == 4 ? 1 : variant == 5 ? 2 : variant == 6 ? 3 : (cat_lo > 0 ? 3 : 1);
+    // (-1) the separate kernel for the long candidate lists of catalog mode (8.4 G scores/s; pairs 7.0, rows 5.7) and
+    // one row per thread for sampled candidates (22.5 M users/s; separate kernel 21.9, pairs 20.9, tcgen05 19.8) — or,
+    // decided on the device, the tcgen05 decoder when the batch's profiles are dense
+    const int dec = variant == 3 ? 0 : variant == 4 ? 1 : variant == 5 ? 2 : variant == 6 ? 3 : -1;
     return eval_forward_tc(y, ldy, col0, plan, m, p_x, p_c, o_x, o_c, B, L, T, status, dbg, dbg_stage, cat_lo,
                            ctx_per_user, scratch, stream, dec);
   }

@@ -80,7 +80,19 @@ struct TcArgs {
   float* Ug;
   int* useg;
   float* cwsg;
+  // decoder picked on the DEVICE by profile density (the host cannot know it without a sync): the entry point launches
+  // the fp32-decoder kernel with auto_dec = 1 and the tcgen05-decoder kernel with auto_dec = 2; a kernel whose decoder
+  // is not the one for this batch returns at once.  Dense = more than kDenseRows packed rows per user on average:
+  // the fp32 loops cost ~ the user's valid positions per candidate, the tcgen05 loop is flat (all-valid profiles of
+  // 50 positions: 5.9 vs 5.0 M users/s; Beauty-shaped, ~7 positions: 19.8 vs 22.6 M).
+  int auto_dec;
 };
+constexpr int kDenseRows = 24;
+__device__ __forceinline__ bool tc_auto_skip(int auto_dec, const int* n_bins, int B) {
+  if (!auto_dec) return false;
+  const bool dense = (long long)n_bins[0] * 64 > (long long)B * kDenseRows;
+  return (auto_dec == 2) != dense;
+}
 
 struct TcSmem {
   float w[2][2 * TC_WFLOATS];                        // weight ring: [slot][hi | lo]
@@ -746,6 +758,7 @@ template <int H, int DEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcArgs a) {
   static_assert(DEC == 0 || H == 2, "the row / pair decoders are written for two heads");
   constexpr bool ROW_DEC = DEC != 0;
+  if (tc_auto_skip(a.auto_dec, a.n_bins, a.B)) return;
   constexpr int DH = Own<H>::DH, N2 = Own<H>::N2;
   CARCA_DYN_SMEM(unsigned char, raw);
   TcSmem& s = *reinterpret_cast<TcSmem*>(raw);
@@ -1598,8 +1611,11 @@ struct DecPairsArgs {
   long long ldy;
   int col0, B, T, cat_lo, residual_ca;
   float sc;
+  const int* n_bins;
+  int auto_dec;
 };
 __global__ void __launch_bounds__(256, 2) decode_pairs_kernel(const DecPairsArgs a) {
+  if (tc_auto_skip(a.auto_dec, a.n_bins, a.B)) return;
   const int P = (a.T + 1) / 2;
   const long long total = (long long)a.B * P;
   const float bfv = __ldg(a.dbf);

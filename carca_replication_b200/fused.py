@@ -25,7 +25,8 @@ _plans: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 # kernel, 2 = tcgen05 tensor-core kernel (two-head cross-attention decoder as an fp32 loop: one candidate row per
 # thread inside the kernel, or — catalog mode — a separate decoder kernel over all (user, candidate pair) items),
 # 3 = the same kernel with that decoder on tcgen05 score MMAs over 128-row tiles, 4 / 5 = the in-kernel row / pair
-# loop forced, 6 = the separate decoder kernel forced (needs one context row per user; otherwise as 2).
+# loop forced, 6 = the separate decoder kernel forced (needs one context row per user; otherwise as 2).  Variants 0 / 2
+# switch to the tcgen05 decoder on the device when the batch's profiles are dense (> 24 valid positions per user).
 # CARCA_FUSED_VARIANT overrides (benchmark comparisons).
 VARIANT = int(__import__("os").environ.get("CARCA_FUSED_VARIANT", "0"))
 

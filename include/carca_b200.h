@@ -425,7 +425,11 @@ int carca_eval_forward(float* y, int64_t ldy, int col0, const float* plan, const
  * candidate row inside the kernel, or — catalog mode — a second kernel over all (user, candidate
  * pair) items reading the keys the first one exported to the scratch buffer), 3 = variant 2 with
  * that decoder on tcgen05 score MMAs over 128-row tiles, 4 / 5 = the in-kernel row / pair loop
- * forced, 6 = the separate decoder kernel forced (one context row per user; otherwise as 2).
+ * forced, 6 = the separate decoder kernel forced (one context row per user; otherwise as 2).  With
+ * variants 0 / 2 and two-head cross-attention the call also launches the tcgen05-decoder kernel, and
+ * the two decide ON THE DEVICE which of them runs: the tcgen05 decoder when the batch averages more
+ * than 24 non-padding positions per user (the packing pass knows; the host would need a sync), the
+ * fp32 decoder otherwise; the other launch returns at once.
  * status (device int32[1], required for variants 2 - 6): bit 0 is set if an MMA completion wait timed
  * out, bit 1 if some user had more than 64 non-padding positions (that user's scores are then
  * computed from its last 64 positions only: route such batches to the per-op entry points).  dbg (optional device [128,64]) receives the intermediate

@@ -74,13 +74,13 @@ def check_eval(name, device, mode="dense"):
         from carca_replication_b200 import fused
 
         if fused.supported(model, cfg["L"], cfg["C"]):
-            # second call: plan cached -> the whole forward is one kernel launch (+ the row-packing pre-pass
-            # of the tensor-core kernel)
+            # second call: plan cached -> the whole forward is one kernel launch (+ the row-packing pre-pass of
+            # the tensor-core kernel, + the launch of its other decoder variant, which returns at once)
             n0 = N.lib().carca_launch_count()
             with torch.no_grad():
                 y_again = model.forward(profile=(p_x.to(device), pa, p_c.to(device)),
                                         targets=[(o_x.to(device), oa, o_c.to(device))])
-            assert N.lib().carca_launch_count() - n0 <= 2
+            assert N.lib().carca_launch_count() - n0 <= 3
             assert torch.equal(y, y_again)
             model.use_fused_eval = False                  # per-op kernels on the same inputs
             with torch.no_grad():

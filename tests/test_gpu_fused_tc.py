@@ -63,7 +63,7 @@ def test_tc_kernel_vs_per_op_and_ffma_kernels(H, decoder, B, T, L, all_valid):
     assert not fused.mma_timed_out(model)
 
 
-def test_tc_kernel_is_the_default_and_two_launches():
+def test_tc_kernel_is_the_default_and_three_launches():
     from carca_replication_b200 import _native as N
     from carca_replication_b200 import fused, synth
 
@@ -77,7 +77,8 @@ def test_tc_kernel_is_the_default_and_two_launches():
         y0 = model.forward(prof, tgt)
         n0 = N.lib().carca_launch_count()
         y1 = model.forward(prof, tgt)
-        assert N.lib().carca_launch_count() - n0 == 2      # row packing + the fused forward
+        assert N.lib().carca_launch_count() - n0 == 3      # row packing + the fused forward (fp32-decoder kernel and
+                                                           # tcgen05-decoder kernel: the one not for this batch returns at once)
         y2 = fused.forward(model, prof, tgt, variant=2)
     assert torch.equal(y0, y1) and torch.equal(y1, y2)       # variant 0 picks the tensor-core kernel
 
@@ -105,7 +106,7 @@ def test_long_windows_use_the_packed_kernel_when_profiles_fit_a_bin(decoder, L):
         model.forward(prof, tgt)                               # builds the plan
         n0 = N.lib().carca_launch_count()
         y = model.forward(prof, tgt)
-        assert N.lib().carca_launch_count() - n0 == 2          # row packing + one fused launch
+        assert N.lib().carca_launch_count() - n0 == (3 if decoder == "ca" else 2)   # row packing + fused launch(es)
         model.use_fused_eval = False
         y_mod = model.forward(prof, tgt)
         model.use_fused_eval = True
