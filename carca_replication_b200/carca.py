@@ -390,8 +390,15 @@ class CARCA(Model):
         if not (_native.is_device_tensor(profile[0]) and fused.supported(self, profile[0].shape[1],
                                                                          profile[2].shape[-1])):
             return False
-        # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin
+        # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin (one device
+        # reduction + host read; GraphedEvalStep checks the batch itself before it replays a captured step)
+        if self._fits_eval_override is not None:
+            return self._fits_eval_override
+        if profile[0].shape[1] > fused.BIN_ROWS and profile[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            return False
         return fused.fits_packed(profile[0])
+
+    _fits_eval_override: Optional[bool] = None
 
     use_fused_train = True  # class default; set False on an instance to force the per-op training path
 

@@ -125,15 +125,27 @@ class GraphedEvalStep:
         self.result = result
         self._metrics = ops.eval_metrics_
         keep = self.stats.clone()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):                  # builds the inference plan and every cached buffer
+        # windows longer than 64: the fused kernel needs every user's valid positions to fit a 64-row bin, which takes
+        # a host read and so cannot be checked inside a capture — check the example batch here and every batch before
+        # its replay (a batch that does not fit runs eagerly on the per-op kernels)
+        from . import fused
+
+        self.long_windows = batch["p_x"].shape[1] > fused.BIN_ROWS
+        if self.long_windows:
+            model._fits_eval_override = fused.fits_packed(self.static["p_x"])
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(warmup):                  # builds the inference plan and every cached buffer
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
                 self._body()
-        torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self._body()
+            self.graph_is_fused = bool(model._fits_eval_override) if self.long_windows else True
+        finally:
+            model._fits_eval_override = None
         self.stats.copy_(keep)                       # warm-up runs do not count
 
     def _body(self) -> None:
@@ -150,10 +162,17 @@ class GraphedEvalStep:
             self.result.copy_(self.stats, non_blocking=True)
 
     def replay(self) -> None:
+        """Runs the step on the current contents of the static input buffers."""
+        from . import fused
+
+        if self.long_windows and self.graph_is_fused and not fused.fits_packed(self.static["p_x"]):
+            with torch.no_grad():                    # a user with more than 64 valid positions: per-op kernels, eagerly
+                self._body()
+            return
         self.graph.replay()
 
     def __call__(self, batch: Dict[str, Tensor]) -> None:
         for key in self.KEYS:
             if batch[key] is not self.static[key]:
                 self.static[key].copy_(batch[key], non_blocking=True)
-        self.graph.replay()
+        self.replay()

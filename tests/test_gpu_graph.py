@@ -178,3 +178,32 @@ def test_graphed_eval_step_matches_eager_evaluate_body(decoder):
     assert torch.allclose(host, ref2.cpu(), rtol=1e-5, atol=1e-9)
     with pytest.raises(ValueError):
         GraphedEvalStep(model.train(), batches[0])
+
+
+def test_graphed_eval_step_long_windows_checks_every_batch():
+    """maxlen 100: the captured step runs the packed tensor-core kernel; a batch with a user of more than 64 valid
+    positions is detected before the replay and runs eagerly on the per-op kernels, with the same accumulators."""
+    import dataclasses
+
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import ops, synth
+    from carca_replication_b200.graph import GraphedEvalStep
+
+    dev = "cuda"
+    shape = dataclasses.replace(synth.BEAUTY, seq_len=100, n_items=4000, n_attrs=300)
+    model = synth.build_model(shape, "ca", seed=6).to(dev).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=6).to(dev))
+    b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, 40, seed=6).items()}
+    keep = (b["p_x"] != 0).sum(1) <= 60
+    short = {k: v[keep][:24].contiguous() for k, v in b.items()}
+    full = {k: v[:24].to(dev) for k, v in synth.make_eval_batch(shape, 24, seed=7, all_valid=True).items()}
+    step = GraphedEvalStep(model, short, k=10)
+    assert step.long_windows and step.graph_is_fused
+    ref = torch.zeros(4, dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for batch in (short, full, short):
+            step(batch)
+            y = model.forward((batch["p_x"], None, batch["p_c"]), [(batch["o_x"], None, batch["o_c"])])
+            ops.eval_metrics_(ref, y, batch["y_true"], batch["o_x"], 10)
+    assert torch.allclose(step.stats, ref, rtol=1e-5, atol=1e-9)
+    assert float(ref[2]) == 72
