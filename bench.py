@@ -205,6 +205,10 @@ def run_ours(args):
     B_.build()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    from carca_replication_b200.parallel import bind_host_to_gpu_numa_node
+    # N > 1: each rank stays on its GPU's NUMA node, before any pinned host buffer is allocated (N = 1 keeps every
+    # core: the cpu_baseline leg of the same process times the reference path on all of them)
+    numa = bind_host_to_gpu_numa_node(local) if world > 1 else {"gpu": local, "bound": False}
     shape = synth.SHAPES[args.shape]
     B, K, W = args.batch, args.steps, args.warmup
     model = synth.build_model(shape, args.decoder, p=0.5)
@@ -420,7 +424,7 @@ def run_ours(args):
                                                   "(consumed by the host one step behind)"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
         "ops_per_op_path": per_op_table,
-        "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1],
+        "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1], "host_numa": numa,
     }
 
     # worst case for the row packing: every profile position valid (one user per 64-row bin)

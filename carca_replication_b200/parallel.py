@@ -136,3 +136,34 @@ class UserDataParallel:
 
         it = loader if sharded else self.shard_loader(loader)
         return evaluate(self.module, it, device, k, reduce_fn=self._allreduce_sum)
+
+
+def bind_host_to_gpu_numa_node(device_index: int) -> dict:
+    """One process per GPU: keep this process (and the pinned host buffers it allocates afterwards, first-touch) on the
+    NUMA node the GPU's PCIe root hangs off, so that its per-step host->device copies do not cross the socket
+    interconnect.  Reads the node from sysfs; a machine that does not expose one (numa_node = -1, e.g. a VM) is left
+    alone.  Returns what was found / done."""
+    import os
+
+    info = {"gpu": int(device_index), "numa_node": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"], info["cpus"] = True, len(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError) as ex:
+        info["error"] = f"{type(ex).__name__}: {ex}"[:120]
+    return info
