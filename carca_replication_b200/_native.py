@@ -95,6 +95,7 @@ SIGNATURES = {
     "carca_gather_rows_fwd": [vp, vp, vp, f32, i32, i32, vp],
     "carca_gather_rows_bwd": [vp, vp, vp, f32, i32, i32, vp],
     "carca_pos_mask_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+    "carca_embed_folded_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "carca_pos_mask_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
     "carca_wdot_score_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i64, i32, vp],
     "carca_wdot_score_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i64, i32, vp],

@@ -114,6 +114,53 @@ class AllEmbedding(Embedding):
             t._apply(fn, *args, **kwargs)
         return super()._apply(fn, *args, **kwargs)
 
+    # ---- inference through a folded item table (per-op path; the fused kernels keep their own plan) -------------
+    use_folded_eval = True   # class default; set False on an instance to always run the unfolded op
+    _FOLD_CHUNK = 16384      # item ids per call when the table is built
+
+    def _folded(self, table: ItemAttrTable):
+        """(T [n_items, d], McT [C, d]) for the current weights: T[i] = joint(sqrt(d) E[i], feats(attrs[i], 0)) is this
+        module's own unfolded op applied to every item id with a zero context, McT = (Wj[:, d:] Wf[:, A:])^T.  Exact
+        re-association of src/carca.py:86-89 (no nonlinearity between the two linears); rebuilt when a parameter
+        or the attribute table changes."""
+        ps = (self.items_embed.weight, self.feats_embed.weight, self.feats_embed.bias, self.joint_embed.weight,
+              self.joint_embed.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (id(table),)
+        hit = getattr(self, "_fold_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        E, Wf, bf, Wj, bj = ps
+        n_items, d = E.shape
+        Cn = Wf.shape[1] - table.n_attrs
+        dev = E.device
+        T = torch.empty((n_items, d), dtype=torch.float32, device=dev)
+        for lo in range(0, n_items, self._FOLD_CHUNK):
+            n = min(self._FOLD_CHUNK, n_items - lo)
+            ids = torch.arange(lo, lo + n, dtype=torch.int32, device=dev).reshape(1, n)
+            T[lo:lo + n] = ops.EmbedFn.apply(ids, torch.zeros((1, n, Cn), dtype=torch.float32, device=dev),
+                                             torch.ones((1, n), dtype=torch.float32, device=dev), None, E, Wf, bf, Wj, bj,
+                                             None, table, True)[0]
+        A = table.n_attrs
+        McT = ops.LinearFn.apply(Wf[:, A:].t().contiguous(), Wj[:, d:].contiguous(),
+                                 torch.zeros(d, dtype=torch.float32, device=dev)) if Cn > 0 else \
+            torch.zeros((0, d), dtype=torch.float32, device=dev)
+        self._fold_cache = (key, T, McT.contiguous())
+        return T, self._fold_cache[2]
+
+    def _forward_folded(self, x: Tensor, c: Tensor, mask: Tensor, pos: Optional[Tensor], table: ItemAttrTable) -> Tensor:
+        from . import _native as N_
+        from .ops import as_f32, as_ids
+
+        T, McT = self._folded(table)
+        x, c, mask = as_ids(x), as_f32(c), as_f32(mask)
+        n_rows, n_cols = x.shape
+        d = T.shape[1]
+        out = torch.empty((n_rows, n_cols, d), dtype=torch.float32, device=T.device)
+        posc = None if pos is None else pos.contiguous()
+        N_.call("carca_embed_folded_fwd", N_.f32p(out), N_.f32p(T), N_.f32p(McT), N_.i32p(x), N_.f32p(c),
+                None if posc is None else N_.f32p(posc), N_.f32p(mask), n_rows, n_cols, d, int(c.shape[-1]), N_.stream())
+        return out
+
     def forward(self, x: Tensor, a: Union[Tensor, ItemAttrTable, None], c: Tensor, mask: Tensor,
                 target: bool) -> Tensor:
         table = a if isinstance(a, ItemAttrTable) else (self.attr_table if a is None else None)
@@ -125,6 +172,12 @@ class AllEmbedding(Embedding):
             else:
                 foreign_enc = True                        # a user-supplied Encoding plug-in
         kernel_mask = torch.ones_like(mask) if foreign_enc else mask
+        if (self.use_folded_eval and not self.training and not torch.is_grad_enabled() and table is not None
+                and dense is None and self.d % 4 == 0 and x.dim() == 2):
+            e = self._forward_folded(x, c, kernel_mask, pos, table)
+            if foreign_enc:
+                e = self.enc.forward(e) * mask.unsqueeze(2)
+            return e
         e = ops.EmbedFn.apply(x, c, kernel_mask, dense, self.items_embed.weight, self.feats_embed.weight,
                               self.feats_embed.bias, self.joint_embed.weight, self.joint_embed.bias, pos, table,
                               bool(target))

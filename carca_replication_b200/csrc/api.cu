@@ -362,6 +362,17 @@ int carca_pos_mask_fwd(float* out, const float* in, const float* pos, const floa
   return check_launch("pos_mask");
 }
 
+int carca_embed_folded_fwd(float* out, const float* T, const float* McT, const int32_t* x, const float* c,
+                           const float* pos, const float* mask, int n_rows, int n_cols, int d, int n_ctx, void* stream) {
+  CARCA_REQUIRE(d % 4 == 0, "embed_folded_fwd: d = %d must be a multiple of 4", d);
+  const long long total4 = (long long)n_rows * n_cols * (d / 4);
+  if (total4 <= 0) return 0;
+  auto k = embed_folded_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(total4, 256)), dim3(256), 0, S(stream), out, T, McT, x, c, pos, mask, total4,
+               d, n_ctx, n_cols);
+  return check_launch("embed_folded");
+}
+
 int carca_pos_mask_bwd(float* d_in, float* d_pos, const float* d_out, const float* mask, int n_rows, int n_cols,
                        int d, void* stream) {
   const long long P = (long long)n_rows * n_cols;

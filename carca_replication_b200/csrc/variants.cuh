@@ -42,6 +42,41 @@ __global__ void __launch_bounds__(256) pos_mask_kernel(float* __restrict__ out, 
   out[i] = v * mask[p];
 }
 
+// AllEmbedding.forward (src/carca.py:85-95) in inference through a folded item table: the two linears have no
+// nonlinearity between them, so  e = Wj [sqrt(d) E[x] | Wf [a | c] + bf] + bj = T[x] + Mc c  with
+// T[i] = Wj [sqrt(d) E[i] | Wf_a attrs[i] + bf] + bj  (one row per item, built once per weight version by running
+// the unfolded op over all item ids with a zero context) and Mc = Wj[:, d:] Wf[:, A:]  ([d, C], passed transposed).
+//   out[p, :] = mask[p] * (T[x[p], :] + sum_k c[p, k] McT[k, :] + pos[p % n_cols, :])
+// One thread per 4 features; HBM-bound gather (d * 4 bytes per position instead of a K = A + C and a K = g + d product).
+__global__ void __launch_bounds__(256) embed_folded_kernel(float* __restrict__ out, const float* __restrict__ T,
+                                                           const float* __restrict__ McT, const int* __restrict__ x,
+                                                           const float* __restrict__ c, const float* __restrict__ pos,
+                                                           const float* __restrict__ mask, long long total4, int d,
+                                                           int n_ctx, int n_cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int d4 = d / 4;
+  const long long p = i / d4;
+  const int f = (int)(i % d4) * 4;
+  const float m = mask[p];
+  const int id = x[p];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m != 0.f && id != 0) {
+    v = *reinterpret_cast<const float4*>(T + (long long)id * d + f);
+    for (int k = 0; k < n_ctx; ++k) {
+      const float ck = c[p * n_ctx + k];
+      const float4 w = *reinterpret_cast<const float4*>(McT + (long long)k * d + f);
+      v.x = fmaf(ck, w.x, v.x); v.y = fmaf(ck, w.y, v.y); v.z = fmaf(ck, w.z, v.z); v.w = fmaf(ck, w.w, v.w);
+    }
+    if (pos) {
+      const float4 q = *reinterpret_cast<const float4*>(pos + (p % n_cols) * d + f);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+  }
+  *reinterpret_cast<float4*>(out + p * d + f) = v;
+}
+
 __device__ __forceinline__ float geometric_sum(float gamma, int n_terms) {   // sum_{j<n} gamma^j as the reference's W row
   float s = 0.f;
   for (int j = 0; j < n_terms; ++j) s += powf(gamma, (float)j);

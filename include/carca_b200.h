@@ -124,6 +124,14 @@ int carca_gather_rows_bwd(float* d_table, const float* d_out, const int32_t* ids
 /* out = (in + pos[position]) * mask — positional encoding of non-target rows (pos may be NULL) and the final mask
  * of every embedding (e.g. src/carca.py:116-120).  in/out [n_rows, n_cols, d], mask [n_rows, n_cols].
  * Backward: d_in = d_out * mask; d_pos [n_cols, d] += column sums (d_pos may be NULL).                 */
+/* AllEmbedding.forward (src/carca.py:85-95) in inference through a folded item table:
+ * out[p,:] = mask[p] * (T[x[p],:] + sum_k c[p,k] McT[k,:] + pos[p % n_cols,:]) with T [n_items, d] =
+ * the unfolded op applied to every item id with a zero context and McT [C, d] = (Wj[:, d:] Wf[:, A:])^T — exact
+ * re-association of the two bias-only linears (:86-89).  x [n_rows, n_cols] ids (0 = padding -> zero row), c
+ * [n_rows, n_cols, C], pos [n_cols, d] or NULL, mask [n_rows, n_cols].  d % 4 == 0.                        */
+int carca_embed_folded_fwd(float* out, const float* T, const float* McT, const int32_t* x, const float* c,
+                           const float* pos, const float* mask, int n_rows, int n_cols, int d, int n_ctx, void* stream);
+
 int carca_pos_mask_fwd(float* out, const float* in, const float* pos, const float* mask, int n_rows, int n_cols, int d,
                        void* stream);
 int carca_pos_mask_bwd(float* d_in, float* d_pos, const float* d_out, const float* mask, int n_rows, int n_cols, int d,
