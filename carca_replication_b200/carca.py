@@ -147,6 +147,12 @@ class AllEmbedding(Embedding):
         self._fold_cache = (key, T, McT.contiguous())
         return T, self._fold_cache[2]
 
+    def __getstate__(self):
+        state = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        state = dict(state)
+        state.pop("_fold_cache", None)               # derived from the weights: never pickled with the module
+        return state
+
     def _forward_folded(self, x: Tensor, c: Tensor, mask: Tensor, pos: Optional[Tensor], table: ItemAttrTable) -> Tensor:
         from . import _native as N_
         from .ops import as_f32, as_ids
