@@ -198,6 +198,21 @@ def check_metrics(device):
     stats.zero_()
     ops.eval_metrics_(stats, y_ties, yt, o_x, k)
     assert float(stats[0]) == float(z["HR_stable"]) and abs(float(stats[1]) - float(z["NDCG_stable"])) < 1e-4
+    # edge shapes: one row, one candidate; several labelled candidates in a row; strided views; int64 ids
+    for Bn, Tn in ((1, 1), (3, 40), (37, 101)):
+        g = torch.Generator().manual_seed(100 * Bn + Tn)
+        yy = torch.rand((Bn, Tn + 3), generator=g).to(device)[:, 1:Tn + 1]            # non-contiguous rows
+        tt = (torch.rand((Bn, Tn), generator=g) < 0.2).to(torch.int32).to(device)
+        tt[:, 0] = 1
+        xx = (torch.rand((Bn, Tn), generator=g) < 0.8).to(torch.int64).to(device) * 7
+        xx[:, 0] = 5
+        st2 = torch.zeros(4, dtype=torch.float64, device=device)
+        ops.eval_metrics_(st2, yy, tt, xx, 10)
+        acc = torch.zeros(3, dtype=torch.float64, device=device)
+        ops.rank_metrics_(acc, yy, tt, 10)
+        loss = cb.BinaryCrossEntropy().forward(yy.contiguous(), tt, cb.get_mask(xx))
+        assert torch.allclose(st2[:3], acc, rtol=0, atol=1e-9), (Bn, Tn)
+        assert abs(float(st2[3]) - float(loss)) < 1e-5 * max(1.0, abs(float(loss))), (Bn, Tn)
 
 
 def check_knn(device):

@@ -43,3 +43,13 @@ def test_no_cpu_fallback(monkeypatch):
     monkeypatch.setattr(N, "_LIB", None)
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         N.lib()
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bind_host_to_gpu_numa_node never raises and never narrows the affinity when it cannot find the GPU's node."""
+    from carca_replication_b200.parallel import bind_host_to_gpu_numa_node
+
+    before = os.sched_getaffinity(0)
+    info = bind_host_to_gpu_numa_node(0)
+    assert info["gpu"] == 0 and info["bound"] is False
+    assert os.sched_getaffinity(0) == before
