@@ -1025,7 +1025,9 @@ int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* 
 }
 
 // row_src | row_seg | n_bins (packing pass), then — split decoder — Kg [rows, 64] | Ug [rows, 4] | useg [B] | cwsg [B]
-static int64_t eval_scratch_pack_bytes(int B) { return ((int64_t)sizeof(int) * (2ll * (B + 1) * 64 + 4) + 255) / 256 * 256; }
+static int64_t eval_scratch_pack_bytes(int B) {   // row_src | row_seg | n_bins [4] | bin_users [B + 1] | order [B / 2 + 2]
+  return ((int64_t)sizeof(int) * (2ll * (B + 1) * 64 + 4 + (B + 1) + (B / 2 + 2)) + 255) / 256 * 256;
+}
 #ifndef CARCA_EMU
 static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, const carca_model_params* m,
                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
@@ -1072,8 +1074,18 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   cudaMemsetAsync(n_bins, 0, 2 * sizeof(int), S(stream));   // [0] bin count, [1] tile scheduler counter
   {
     auto pk = pack_rows_kernel;
-    CARCA_LAUNCH(pk, dim3(ceil_div(B, 128)), dim3(128), 0, S(stream), row_src, row_seg, n_bins, status, p_x, B, L);
+    int* bin_users = n_bins + 4;
+    int* order = bin_users + (B + 1);
+    CARCA_LAUNCH(pk, dim3(ceil_div(B, 128)), dim3(128), 0, S(stream), row_src, row_seg, n_bins, status, p_x, B, L,
+                 bin_users);
     TRY(check_launch("pack_rows"));
+    a.order = nullptr;
+    if (B > 2 * 148) {   // more tiles than CTAs can be: hand out the longest tiles first
+      auto ok = tile_order_kernel;
+      CARCA_LAUNCH(ok, dim3(1), dim3(256), 0, S(stream), order, bin_users, n_bins);
+      TRY(check_launch("tile_order"));
+      a.order = order;
+    }
   }
   a.row_src = row_src; a.row_seg = row_seg; a.n_bins = n_bins;
   a.chunk_slices = max(1, ceil_div(ceil_div(T, 128), 16));   // <= 16 candidate chunks per work item

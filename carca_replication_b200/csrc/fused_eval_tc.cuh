@@ -72,6 +72,8 @@ struct TcArgs {
                                                      //   one row per user, e.g. an expanded view or catalog mode: C, 0)
   const int *row_src, *row_seg;                      // packed profile rows (pack_rows_kernel)
   int* n_bins;                                       // [0] bins written by the packing pass, [1] tile scheduler counter
+  const int* order;                                  // tiles in descending order of their user count (tile_order_kernel):
+                                                     //   the scheduler hands out the longest tiles first
   int chunk_slices;                                  // work item = (tile, one of this many slices of the candidate chunks):
                                                      //   long candidate lists (full catalog) are spread over CTAs
   // DEC == 3 (split decoder): the kernel stops after the encoder and exports, per packed row, the decoder's key
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // pipelined decoder reuses these columns for scores)
       umma::tmem_st8(c.tmem + C_ONES, ones);
     }
-    const long long trow0 = (long long)(tile / n_slices) * 128;
+    const long long trow0 = (long long)(a.order ? a.order[tile / n_slices] : tile / n_slices) * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
     const int src = a.row_src[trow0 + c.row];
@@ -1716,8 +1718,9 @@ __global__ void __launch_bounds__(256, 2) decode_pairs_kernel(const DecPairsArgs
 // One 128-thread block packs 128 consecutive users (next-fit) and claims its bins with one atomicAdd.
 __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
                                                         int* __restrict__ n_bins, int* __restrict__ status,
-                                                        const int* __restrict__ p_x, int B, int L) {
-  __shared__ int cnt[128], bin_of[128], start_of[128], base;
+                                                        const int* __restrict__ p_x, int B, int L,
+                                                        int* __restrict__ bin_users) {
+  __shared__ int cnt[128], bin_of[128], start_of[128], users_of[128], base, nbins;
   const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
   int n = 0;
   if (usr < B) {
@@ -1733,20 +1736,26 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
   cnt[t] = n;
   __syncthreads();
   if (t == 0) {
-    int bin = 0, fill = 0;
+    int bin = 0, fill = 0, in_bin = 0;
     const int users = min(128, B - blockIdx.x * 128);
     for (int q = 0; q < users; ++q) {
       if (fill + cnt[q] > 64) {
+        users_of[bin] = in_bin;
         ++bin;
         fill = 0;
+        in_bin = 0;
       }
       bin_of[q] = bin;
       start_of[q] = fill;
       fill += cnt[q];
+      ++in_bin;
     }
+    users_of[bin] = in_bin;
+    nbins = bin + 1;
     base = atomicAdd(n_bins, bin + 1);
   }
   __syncthreads();
+  if (bin_users && t < nbins) bin_users[base + t] = users_of[t];   // users per bin: the tile's decoder work
   if (usr < B) {
     const int* x = p_x + (long long)usr * L;
     const long long o = (long long)(base + bin_of[t]) * 64;
@@ -1765,6 +1774,33 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
     }
   }
 }
+
+// Tiles in descending order of their user count (= decoder work; the encoder part of a tile is constant): CTAs take
+// work items from a global counter, so with the longest tiles first the last, partly filled wave consists of the
+// cheapest ones (502 tiles on 148 CTAs run as 4 waves: profiles/r01/tc_tile_times.log).  Counting sort, one CTA.
+__global__ void __launch_bounds__(256) tile_order_kernel(int* __restrict__ order, const int* __restrict__ bin_users,
+                                                         const int* __restrict__ n_bins) {
+  __shared__ int hist[130], cursor[130];
+  const int nb = n_bins[0], n_tiles = (nb + 1) / 2;
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  auto bucket = [&](int t) {   // 128 - users, users <= 128 (a bin holds at most 64 users)
+    const int u = bin_users[2 * t] + (2 * t + 1 < nb ? bin_users[2 * t + 1] : 0);
+    return 128 - min(u, 128);
+  };
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) atomicAdd(&hist[bucket(t)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < 129; ++i) {
+      cursor[i] = acc;
+      acc += hist[i];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) order[atomicAdd(&cursor[bucket(t)], 1)] = t;
+}
+
 
 // Packs W [64 out, 64 in] (+ bias [64]) into the K-major B operand of umma.cuh with the bias as
 // K step 8: dst = [hi: 18 chunks x 64 rows x 4 | lo: same].
