@@ -1070,7 +1070,6 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   int* row_src = reinterpret_cast<int*>(scratch);
   int* row_seg = row_src + rows;
   int* n_bins = row_seg + rows;
-  cudaMemsetAsync(row_src, 0xff, sizeof(int) * (size_t)rows, S(stream));
   cudaMemsetAsync(n_bins, 0, 2 * sizeof(int), S(stream));   // [0] bin count, [1] tile scheduler counter
   {
     auto pk = pack_rows_kernel;

@@ -838,7 +838,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     const long long trow0 = (long long)(a.order ? a.order[tile / n_slices] : tile / n_slices) * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
-    const int src = a.row_src[trow0 + c.row];
+    // (a tile is two bins: with an odd bin count the last tile's second bin does not exist)
+    const int src = (trow0 + c.row) / 64 < a.n_bins[0] ? a.row_src[trow0 + c.row] : -1;
     const int seg = src >= 0 ? a.row_seg[trow0 + c.row] : 0;
     const int ru = src >> 8, rp = src & 255;
     const int seg0 = seg & 0xff, seglen = (seg >> 8) & 0xff;
@@ -1715,12 +1716,13 @@ __global__ void __launch_bounds__(256, 2) decode_pairs_kernel(const DecPairsArgs
 // and in sequence order inside one bin (causal mask = row order); position L-1 is always included
 // (the dot decoder reads it even when it is padding, src/carca.py:362).
 //   row_src[bin*64 + r] = user*256 + position (or -1), row_seg = segment start | length << 8.
-// One 128-thread block packs 128 consecutive users (next-fit) and claims its bins with one atomicAdd.
+// One 128-thread block packs 128 consecutive users (next-fit) and claims its bins with one atomicAdd; it writes
+// every row of its bins (-1 for the unused ones), so the scratch needs no clearing between calls.
 __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
                                                         int* __restrict__ n_bins, int* __restrict__ status,
                                                         const int* __restrict__ p_x, int B, int L,
                                                         int* __restrict__ bin_users) {
-  __shared__ int cnt[128], bin_of[128], start_of[128], users_of[128], base, nbins;
+  __shared__ int cnt[128], bin_of[128], start_of[128], users_of[128], fill_of[128], base, nbins;
   const int t = threadIdx.x, usr = blockIdx.x * 128 + t;
   int n = 0;
   if (usr < B) {
@@ -1741,6 +1743,7 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
     for (int q = 0; q < users; ++q) {
       if (fill + cnt[q] > 64) {
         users_of[bin] = in_bin;
+        fill_of[bin] = fill;
         ++bin;
         fill = 0;
         in_bin = 0;
@@ -1751,6 +1754,7 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
       ++in_bin;
     }
     users_of[bin] = in_bin;
+    fill_of[bin] = fill;
     nbins = bin + 1;
     base = atomicAdd(n_bins, bin + 1);
   }
@@ -1772,6 +1776,11 @@ __global__ void __launch_bounds__(128) pack_rows_kernel(int* __restrict__ row_sr
         ++r;
       }
     }
+  }
+  // unused rows of the block's bins (the fused kernel treats the bin past the last one as empty itself)
+  for (int i = t; i < nbins * 64; i += 128) {
+    const int b = i / 64, r = i % 64;
+    if (r >= fill_of[b]) row_src[(long long)(base + b) * 64 + r] = -1;
   }
 }
 
