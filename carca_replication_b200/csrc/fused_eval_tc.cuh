@@ -819,7 +819,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   tk.n = 0;
   tk.tiles_only = a.dbg_stage <= -2;
   const int n_slices = max(1, a.chunk_slices);
-  const int n_tiles = ((a.n_bins[0] + 1) / 2) * n_slices;   // work items: every slice re-encodes its tile (cheap next
+  // Tail slicing: with the tiles in longest-first order the last, partly filled wave (n_tiles mod gridDim tiles) holds
+  // the cheapest tiles while the other CTAs idle; those tiles become S work items each (every item re-encodes the tile,
+  // which only costs idle CTAs their time, and scores 1/S of its candidates), S as large as keeps them in one wave.
+  const int n_tiles_real = (a.n_bins[0] + 1) / 2;
+  int tail = 0, tail_s = 1;
+  if (n_slices == 1 && DEC != 3 && a.order != nullptr && n_tiles_real > (int)gridDim.x) {
+    tail = n_tiles_real % (int)gridDim.x;
+    tail_s = tail > 0 ? min(4, (int)gridDim.x / tail) : 1;
+    if (tail_s < 2) { tail = 0; tail_s = 1; }
+  }
+  const int n_full = n_tiles_real - tail;
+  const int n_tiles = n_slices > 1 ? n_tiles_real * n_slices : n_full + tail * tail_s;
+                                                            // work items: every slice re-encodes its tile (cheap next
                                                             // to >= 16 candidate chunks per user) and scores its share
   const int u = c.row / 64, i = c.row % 64;   // bin (64-row half of the tile) and row within it
   float* const plast = s.k_hi;                // dot decoder: last-position vectors per segment (K is unused there)
@@ -835,7 +847,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // pipelined decoder reuses these columns for scores)
       umma::tmem_st8(c.tmem + C_ONES, ones);
     }
-    const long long trow0 = (long long)(a.order ? a.order[tile / n_slices] : tile / n_slices) * 128;
+    int tile_idx, slice, ns;   // the item's tile, its slice of the tile's candidates, slices of that tile
+    if (n_slices > 1) {
+      tile_idx = tile / n_slices; slice = tile % n_slices; ns = n_slices;
+    } else if (tile < n_full) {
+      tile_idx = tile; slice = 0; ns = 1;
+    } else {
+      tile_idx = n_full + (tile - n_full) / tail_s; slice = (tile - n_full) % tail_s; ns = tail_s;
+    }
+    if (a.order) tile_idx = a.order[tile_idx];
+    const long long trow0 = (long long)tile_idx * 128;
     tick(tk, 0);
     // ---- packed rows (csrc/fused_eval_tc.cuh: pack_rows_kernel): row -> (user, position), segment of the user
     // (a tile is two bins: with an odd bin count the last tile's second bin does not exist)
@@ -1160,8 +1181,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       const int P = (a.T + 1) / 2;      // candidate pairs per user
       const int total = n_seg * P;      // (segment, pair) work items of the tile
       const int n_it = (total + TC_THREADS - 1) / TC_THREADS;
-      const int per = (n_it + n_slices - 1) / n_slices;
-      const int it_lo = min(n_it, (tile % n_slices) * per), it_hi = min(n_it, it_lo + per);
+      const int per = (n_it + ns - 1) / ns;
+      const int it_lo = min(n_it, slice * per), it_hi = min(n_it, it_lo + per);
       const float bfv = __ldg(a.dbf);
       auto pair_at = [&](int it) {
         DecPair r;
@@ -1249,8 +1270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
       tick(tk, 40);
       const int total = n_seg * a.T;    // (segment, candidate) rows of the tile
       const int n_it = (total + TC_THREADS - 1) / TC_THREADS;
-      const int per = (n_it + n_slices - 1) / n_slices;
-      const int it_lo = min(n_it, (tile % n_slices) * per), it_hi = min(n_it, it_lo + per);
+      const int per = (n_it + ns - 1) / ns;
+      const int it_lo = min(n_it, slice * per), it_hi = min(n_it, it_lo + per);
       const float bfv = __ldg(a.dbf);
       auto row_at = [&](int it) {
         DecRow r;
@@ -1297,9 +1318,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
     const bool ca_mma = ROW_DEC ? false : ca;   // (ROW_DEC: only the dot decoder gets here)
     // iterations [it_lo, it_hi) of each bin handled by this work item (all of them unless the tile is sliced)
     const int n_it_a = (seg_cnt(0) * a.T + 127) / 128, n_it_b = (seg_cnt(1) * a.T + 127) / 128;
-    const int per_a = (n_it_a + n_slices - 1) / n_slices, per_b = (n_it_b + n_slices - 1) / n_slices;
-    const int lo_a = min(n_it_a, (tile % n_slices) * per_a), hi_a = min(n_it_a, lo_a + per_a);
-    const int lo_b = min(n_it_b, (tile % n_slices) * per_b), hi_b = min(n_it_b, lo_b + per_b);
+    const int per_a = (n_it_a + ns - 1) / ns, per_b = (n_it_b + ns - 1) / ns;
+    const int lo_a = min(n_it_a, slice * per_a), hi_a = min(n_it_a, lo_a + per_a);
+    const int lo_b = min(n_it_b, slice * per_b), hi_b = min(n_it_b, lo_b + per_b);
     const int n_iter = (hi_a - lo_a) + (hi_b - lo_b);
     // iteration j of this work item -> (bin, iteration within the bin)
     auto locate = [&](int j, int& bin, int& it) {
