@@ -1105,7 +1105,8 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
     a.cwsg = f + rows * 68 + B;
     a.chunk_slices = 1;   // the tile is only encoded here
   }
-  const long long n_tiles = (long long)ceil_div(B, 2) * a.chunk_slices;   // upper bound on the work items
+  // upper bound on the work items (a small batch's tiles are split into up to 4 items each: tail slicing in the kernel)
+  const long long n_tiles = (long long)ceil_div(B, 2) * max(a.chunk_slices, 4);
   if (m->n_heads == 2 && dec == 3) {
     auto k = fused_eval_tc_kernel<2, 3>;
     TRY(allow_smem(k, smem));
@@ -1140,7 +1141,7 @@ static int eval_forward_tc(float* y, int64_t ldy, int col0, const float* plan, c
   }
   TRY(check_launch("fused_eval_tc"));
   if (a.auto_dec) {   // dense profiles: the same forward with the tcgen05 decoder (returns at once otherwise)
-    const long long n_tiles_d = (long long)ceil_div(B, 2) * a_dense.chunk_slices;
+    const long long n_tiles_d = (long long)ceil_div(B, 2) * max(a_dense.chunk_slices, 4);
     auto k = fused_eval_tc_kernel<2, 0>;
     TRY(allow_smem(k, smem));
     CARCA_LAUNCH(k, dim3((unsigned)min(n_tiles_d, 148ll)), dim3(TC_THREADS), smem, S(stream), a_dense);

@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fused_eval_tc_kernel(const TcAr
   // which only costs idle CTAs their time, and scores 1/S of its candidates), S as large as keeps them in one wave.
   const int n_tiles_real = (a.n_bins[0] + 1) / 2;
   int tail = 0, tail_s = 1;
-  if (n_slices == 1 && DEC != 3 && a.order != nullptr && n_tiles_real > (int)gridDim.x) {
+  if (n_slices == 1 && DEC != 3 && n_tiles_real > 0) {   // (fewer tiles than CTAs: every tile is a tail tile)
     tail = n_tiles_real % (int)gridDim.x;
     tail_s = tail > 0 ? min(4, (int)gridDim.x / tail) : 1;
     if (tail_s < 2) { tail = 0; tail_s = 1; }
