@@ -240,14 +240,21 @@ def run_ours(args):
         return y
 
     def timed(fn, n):
+        import gc
+
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(world)
         torch.cuda.synchronize()
-        e0.record()
-        for i in range(n):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()                  # no collector pause inside the timed region (the e2e loop is host-paced)
+        try:
+            e0.record()
+            for i in range(n):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         barrier(world)
         ms = e0.elapsed_time(e1)
         if world > 1:
