@@ -14,7 +14,7 @@ from .carca import (  # noqa: F401
 )
 from .knn import KNN  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .train import compute_HR, compute_NDCG, evaluate  # noqa: F401
+from .train import compute_HR, compute_NDCG, evaluate, load_checkpoint, save_checkpoint  # noqa: F401
 from .utils import get_mask, to  # noqa: F401
 
 __all__ = [

@@ -87,6 +87,7 @@ SIGNATURES = {
     "carca_set_seed_source": [vp],
     "carca_transpose": [vp, vp, i32, i32, i32, vp],
     "carca_padding_mask": [vp, vp, i64, vp],
+    "carca_padding_mask_f32": [vp, vp, i64, vp],
     "carca_embed_fwd": [vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32, vp],
     "carca_embed_bwd": [P(EmbedGrads), vp, vp, P(EmbedParams), P(AttrSource), vp, vp, vp, i32, i32, i32,
                         vp, vp, vp, vp],

@@ -110,9 +110,15 @@ class AllEmbedding(Embedding):
 
     def _apply(self, fn, *args, **kwargs):
         _invalidate_plans()
+        self.__dict__.pop("_fold_cache", None)
         for t in self._attr_table:                        # follow .to(device) / .cuda()
             t._apply(fn, *args, **kwargs)
         return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        if mode:
+            self.__dict__.pop("_fold_cache", None)        # weights are about to change: drop the derived table
+        return super().train(mode)
 
     # ---- inference through a folded item table (per-op path; the fused kernels keep their own plan) -------------
     use_folded_eval = True   # class default; set False on an instance to always run the unfolded op
@@ -125,7 +131,9 @@ class AllEmbedding(Embedding):
         or the attribute table changes."""
         ps = (self.items_embed.weight, self.feats_embed.weight, self.feats_embed.bias, self.joint_embed.weight,
               self.joint_embed.bias)
-        key = tuple((p.data_ptr(), p._version) for p in ps) + (id(table),)
+        from . import fused
+
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (id(table), fused.weights_epoch())
         hit = getattr(self, "_fold_cache", None)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]

@@ -222,6 +222,13 @@ int carca_padding_mask(float* mask, const int32_t* ids, int64_t n, void* stream)
   return check_launch("padding_mask");
 }
 
+int carca_padding_mask_f32(float* mask, const float* x, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  auto k = padding_mask_f32_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, S(stream), mask, x, (long long)n);
+  return check_launch("padding_mask_f32");
+}
+
 int carca_dropout(float* y, const float* x, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
   CARCA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f outside [0,1)", p);
   return scale_rows(y, x, nullptr, drop_cfg(p, seed, site), n, 1, S(stream));

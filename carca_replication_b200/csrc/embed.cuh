@@ -152,5 +152,10 @@ __global__ void __launch_bounds__(256) padding_mask_kernel(float* __restrict__ m
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) mask[i] = ids[i] != 0 ? 1.0f : 0.0f;
 }
+__global__ void __launch_bounds__(256) padding_mask_f32_kernel(float* __restrict__ mask, const float* __restrict__ x,
+                                                               long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mask[i] = x[i] == 0.0f ? 0.0f : 1.0f;
+}
 
 }  // namespace carca

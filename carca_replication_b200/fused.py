@@ -119,6 +119,20 @@ def invalidate_plans() -> None:
     _struct_epoch[0] += 1
 
 
+# Weights epoch: bumped by everything that writes parameters through RAW POINTERS, which tensor version counters do
+# not see — FusedAdam.step() (csrc/optim.cuh) and every GraphedTrainStep replay.  Part of every cache key derived
+# from the weights (inference plans here, AllEmbedding's folded table in carca.py).
+_weights_epoch = [0]
+
+
+def bump_weights_epoch() -> None:
+    _weights_epoch[0] += 1
+
+
+def weights_epoch() -> int:
+    return _weights_epoch[0]
+
+
 class _Entry:
     __slots__ = ("epoch", "tensors", "key", "plan", "status", "m", "keep", "n_ctx")
 
@@ -128,16 +142,26 @@ def _tensors_of(model) -> list:
 
 
 def _version_key(tensors, table: ItemAttrTable) -> Tuple:
-    return (id(table),) + tuple(t._version for t in tensors)
+    return (id(table), _weights_epoch[0]) + tuple(t._version for t in tensors)
+
+
+def plan_is_current(model) -> bool:
+    """True when the cached inference plan of `model` was built from its current weights."""
+    ent = _plans.get(model)
+    return (ent is not None and ent.epoch == _struct_epoch[0]
+            and ent.key[1:] == (_weights_epoch[0],) + tuple(t._version for t in ent.tensors))
 
 
 def eval_plan(model, table: ItemAttrTable, n_ctx: int):
     """Inference plan for the model's current weights (cached until a parameter changes) and the argument block of
     the forward calls (device pointers of every parameter; rebuilt together with the plan)."""
     ent = _plans.get(model)
-    if ent is not None and ent.epoch == _struct_epoch[0] and ent.n_ctx == n_ctx:
-        if ent.key == _version_key(ent.tensors, table):
-            return ent
+    same_struct = ent is not None and ent.epoch == _struct_epoch[0] and ent.n_ctx == n_ctx
+    if same_struct and ent.key == _version_key(ent.tensors, table):
+        return ent
+    # same parameter tensors, new values: the plan is rebuilt INTO THE SAME BUFFER, so that CUDA graphs which captured
+    # its address (GraphedEvalStep) score with the new weights after a refresh
+    reuse = ent.plan if same_struct and ent.key[0] == id(table) else None
     tensors = _tensors_of(model)
     key = _version_key(tensors, table)
     emb = model.embeds
@@ -150,14 +174,16 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int):
         N.call("carca_transpose", N.f32p(WfT), N.f32p(Wf), g, AC, 0, N.stream())
     m, keep = _model_params(model, table, WfT, n_ctx)
     n_floats = N.lib().carca_eval_plan_floats(C.byref(m))
-    plan = torch.empty(n_floats, dtype=torch.float32, device=dev)
+    plan = reuse if reuse is not None and reuse.numel() == n_floats and reuse.device == dev else \
+        torch.empty(n_floats, dtype=torch.float32, device=dev)
     scratch = torch.empty((emb.items_embed.weight.shape[0], g), dtype=torch.float32, device=dev)
     src = _attr_source(table, None)
     N.call("carca_eval_prepare", N.f32p(plan), N.f32p(scratch), C.byref(m), C.byref(src), N.stream())
     ent = _Entry()
     ent.epoch, ent.tensors, ent.key, ent.n_ctx = _struct_epoch[0], tensors, key, n_ctx
     ent.plan = plan
-    ent.status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ent.status = _plans[model].status if reuse is not None and plan is reuse else \
+        torch.zeros(1, dtype=torch.int32, device=dev)
     ent.m, ent.keep = _model_params(model, table, None, n_ctx)     # the forward calls' argument block
     _plans[model] = ent
     return ent
@@ -178,6 +204,15 @@ def _scratch(B: int, device) -> Tensor:
         buf = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
         _scratch_cache[key] = buf
     return buf
+
+
+def status_word(model, device) -> Tensor:
+    """float64[1] device tensor: the status word of the model's inference plan (bit 0: a tcgen05 completion wait
+    timed out), 0 when the model has no plan.  No host sync — evaluate() appends it to its accumulators."""
+    hit = _plans.get(model)
+    if hit is None:
+        return torch.zeros(1, dtype=torch.float64, device=device)
+    return hit.status.to(torch.float64)
 
 
 def mma_timed_out(model) -> bool:

@@ -75,8 +75,11 @@ class GraphedTrainStep:
         return loss.detach()
 
     def __call__(self, batch: Dict[str, Tensor]) -> Tensor:
+        from . import fused
+
         for k in self.KEYS:
             self.static[k].copy_(batch[k], non_blocking=True)
+        fused.bump_weights_epoch()      # the replayed Adam launch writes parameters through raw pointers
         if self.long_windows and self.graph_is_fused and not self._fits(batch):
             # a user with more than 64 active positions: this step runs eagerly on the per-op kernels
             N.lib().carca_set_seed_source(self.seed.data_ptr())
@@ -144,6 +147,7 @@ class GraphedEvalStep:
             with torch.no_grad(), torch.cuda.graph(self.graph):
                 self._body()
             self.graph_is_fused = bool(model._fits_eval_override) if self.long_windows else True
+            self.uses_plan = fused._plans.get(model) is not None       # the capture reads the fused inference plan
         finally:
             model._fits_eval_override = None
         self.stats.copy_(keep)                       # warm-up runs do not count
@@ -161,10 +165,29 @@ class GraphedEvalStep:
         if self.result is not None:
             self.result.copy_(self.stats, non_blocking=True)
 
+    def refresh(self) -> None:
+        """Rebuilds the inference plan (folded tables, packed weights) the captured kernels read, in place, from the
+        model's current weights.  `replay()` calls it automatically when the weights changed since the last build
+        (optimizer steps, FusedAdam / GraphedTrainStep included, load_state_dict); moving the model to another device
+        or dtype invalidates the capture itself and raises."""
+        from . import fused
+
+        if not self.uses_plan:
+            return
+        before = fused._plans.get(self.model)
+        buf = None if before is None else before.plan.data_ptr()
+        emb = self.model.embeds
+        ent = fused.eval_plan(self.model, emb.attr_table, self.static["p_c"].shape[-1])
+        if buf is not None and ent.plan.data_ptr() != buf:
+            raise RuntimeError("GraphedEvalStep: the model's parameters were replaced (moved / cast) after capture; "
+                               "build a new GraphedEvalStep")
+
     def replay(self) -> None:
         """Runs the step on the current contents of the static input buffers."""
         from . import fused
 
+        if self.uses_plan and not fused.plan_is_current(self.model):
+            self.refresh()
         if self.long_windows and self.graph_is_fused and not fused.fits_packed(self.static["p_x"]):
             with torch.no_grad():                    # a user with more than 64 valid positions: per-op kernels, eagerly
                 self._body()

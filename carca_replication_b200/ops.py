@@ -25,6 +25,7 @@ class _SeedState(threading.local):
         self.counter = 0
         self.forced: Optional[int] = None     # tests pin the Philox seed to compare with the oracle
         self.active: Optional[int] = None     # seed of the CARCA.forward currently running
+        self.salt = 0                         # data-parallel rank: independent dropout masks per rank
 
 
 _seeds = _SeedState()
@@ -35,11 +36,18 @@ def set_dropout_seed(seed: Optional[int]) -> None:
     _seeds.forced = None if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
 
 
+def set_seed_salt(salt: int) -> None:
+    """Mixed into every fresh seed: UserDataParallel passes its rank, so that ranks (which all start from the same
+    torch.initial_seed() and counter) do not draw identical dropout masks for the same row / site indices."""
+    _seeds.salt = int(salt)
+
+
 def fresh_seed() -> int:
     if _seeds.forced is not None:
         return _seeds.forced
     _seeds.counter += 1
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seeds.counter * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seeds.counter * 0xD1B54A32D192ED03
+            + _seeds.salt * 0xA24BAED4963EE407) & 0xFFFFFFFFFFFFFFFF
 
 
 class forward_seed:
@@ -74,8 +82,13 @@ def as_f32(t: Tensor) -> Tensor:
 
 
 def padding_mask(ids: Tensor) -> Tensor:
-    """get_mask (src/utils.py:6-7) on device."""
+    """get_mask (src/utils.py:6-7) on device: integer ids, or any floating input (compared as float32)."""
     N.require_device(ids)
+    if ids.dtype.is_floating_point:
+        x = as_f32(ids)
+        m = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        N.call("carca_padding_mask_f32", N.f32p(m), N.f32p(x), x.numel(), N.stream())
+        return m
     x = as_ids(ids)
     m = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     N.call("carca_padding_mask", N.f32p(m), N.i32p(x), x.numel(), N.stream())

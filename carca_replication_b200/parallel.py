@@ -53,6 +53,9 @@ class UserDataParallel:
         self._queued = False
         self.loss_fn = BinaryCrossEntropy()
         self.loss_fn.reduce_sums = self._allreduce_sum
+        from . import ops
+
+        ops.set_seed_salt(self.rank)          # independent dropout masks per rank
         if broadcast:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)
@@ -120,6 +123,10 @@ class UserDataParallel:
                 out.append(None)
                 continue
             n = t.shape[0]
+            if n < self.world:
+                # an empty slice would put B = 0 into the kernels of one rank while the others wait in the
+                # gradient all-reduce: refuse instead (use drop_last / a batch size >= the number of ranks)
+                raise ValueError(f"UserDataParallel.shard: a batch of {n} users cannot be split over {self.world} ranks")
             lo, hi = (n * self.rank) // self.world, (n * (self.rank + 1)) // self.world
             out.append(t[lo:hi])
         return tuple(out)

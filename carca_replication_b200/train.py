@@ -56,12 +56,64 @@ def evaluate(model: Model, loader: DataLoader, device: str, k: int,
             # BinaryCrossEntropy over get_mask(o_x) + compute_HR + compute_NDCG of the batch in one launch
             ops.eval_metrics_(acc, y_pred, y_true, o_x, k)
             n_batches += 1
-    stats = torch.cat([acc, torch.tensor([float(n_batches)], dtype=torch.float64, device=device)])
+    from . import fused
+
+    # the tensor-core kernels flag a timed-out MMA completion wait in a device status word: it travels with the
+    # accumulators in the single device->host read, and wrong metrics are never returned silently
+    status = fused.status_word(model, device)
+    stats = torch.cat([acc, torch.tensor([float(n_batches)], dtype=torch.float64, device=device), status])
     if reduce_fn is not None:
         reduce_fn(stats)
-    hits, ndcg, total, lsum, nb = stats.tolist()          # the one device->host sync
+    hits, ndcg, total, lsum, nb, bad = stats.tolist()     # the one device->host sync
+    if bad != 0.0:
+        raise RuntimeError("carca_b200: a tensor-core completion wait timed out during evaluate(); the scores of this "
+                           "run are not valid (status word %d)" % int(bad))
     total = max(total, 1.0)
     return hits / total, ndcg / total, lsum / max(nb, 1.0)
+
+
+CHECKPOINT_FORMAT = "carca_b200.state_dict.v1"
+
+
+def save_checkpoint(model: Model, path: str, epoch: int, HR: float, NDCG: float) -> None:
+    """Best-model checkpoint (src/train.py:118-124), same file name convention, but the file holds the
+    `state_dict` (the reference's own keys and shapes, so it loads into the reference's classes too) plus the epoch
+    and metrics — tensors and plain Python values only, readable with `torch.load(..., weights_only=True)`.  The
+    reference pickles the whole module, which torch >= 2.6 refuses to load by default."""
+    torch.save({"format": CHECKPOINT_FORMAT, "epoch": int(epoch), "HR": float(HR), "NDCG": float(NDCG),
+                "state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, path)
+
+
+def load_checkpoint(model: Model, path: str, trust_pickle: bool = False) -> Model:
+    """Loads a checkpoint written by `save_checkpoint` into `model` (strict keys) with the weights-only unpickler.
+    A whole-module pickle as the reference writes it (src/train.py:124) is only read with `trust_pickle=True`
+    (arbitrary code execution on load is the caller's decision), and its weights are copied into `model`."""
+    try:
+        blob = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        if not trust_pickle:
+            raise
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(blob, torch.nn.Module):
+        sd = blob.state_dict()
+    elif isinstance(blob, dict) and "state_dict" in blob:
+        sd = blob["state_dict"]
+    else:
+        sd = blob
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+def _broadcast_from_main(model: Model) -> None:
+    """Data-parallel runs: every rank leaves train() with rank 0's (best-checkpoint) weights."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+        from . import fused
+
+        fused.bump_weights_epoch()
 
 
 def train(
@@ -79,14 +131,17 @@ def train(
     scheduler: Union[_LRScheduler, None] = None,
     loss_fn: Optional[BinaryCrossEntropy] = None,
     is_main: bool = True,
+    reduce_fn=None,
 ) -> Model:
     """Epoch loop, CSV log, save-best checkpoint and early stop as src/train.py:56-152.
 
     Differences, all outside the hot path: the per-step loss is accumulated on the device (one
-    read per epoch instead of `loss.item()` per step, :97); the best checkpoint is re-read with
-    `weights_only=False` (torch >= 2.6 rejects the reference's bare `torch.load`, :142);
-    `loss_fn` / `is_main` let the data-parallel wrapper inject its loss and keep file output on
-    rank 0.
+    read per epoch instead of `loss.item()` per step, :97); the best checkpoint is a `state_dict` file
+    (`save_checkpoint`, same `{epoch:03d}_{HR:.4f}_{NDCG:.4f}.pth` name) reloaded with the weights-only unpickler
+    (torch >= 2.6 rejects the reference's bare `torch.load` of a pickled module, :142);
+    `loss_fn` / `is_main` / `reduce_fn` let the data-parallel wrapper inject its loss, keep file output on
+    rank 0 and all-reduce the validation accumulators, so that every rank sees the same NDCG and takes the same
+    checkpoint / early-stop branch; at the end rank 0's best weights are broadcast to all ranks.
     """
     if is_main:
         os.makedirs(datadir, exist_ok=True)
@@ -120,14 +175,14 @@ def train(
             logfile.write(f"{now};{epoch};train;{train_loss};;\n")
         if scheduler is not None:
             scheduler.step()
-        HR, NDCG, loss = evaluate(model, val_loader, device, top_k)
+        HR, NDCG, loss = evaluate(model, val_loader, device, top_k, reduce_fn=reduce_fn)
         model = model.train().to(device)
         if NDCG > best:
             best, no_improve = NDCG, 0
             if is_main:
                 for f in [f for f in os.listdir(datadir) if f.endswith(".pth")]:
                     os.remove(os.path.join(datadir, f))
-                torch.save(model, os.path.join(datadir, f"{epoch:03d}_{HR:.4f}_{NDCG:.4f}.pth"))
+                save_checkpoint(model, os.path.join(datadir, f"{epoch:03d}_{HR:.4f}_{NDCG:.4f}.pth"), epoch, HR, NDCG)
         else:
             no_improve += 1
         if verbose in [1, 2] and is_main:
@@ -143,7 +198,9 @@ def train(
     if is_main:
         saved = [os.path.join(datadir, f) for f in os.listdir(datadir) if f.endswith(".pth")]
         if saved:
-            model = torch.load(saved[0], weights_only=False)
+            model = load_checkpoint(model, saved[0]).to(device)
+    _broadcast_from_main(model)
+    if is_main:
         if test_loader is not None:
             HR, NDCG, loss = evaluate(model, test_loader, device, top_k)
             now = datetime.now().strftime("%H:%M:%S")
@@ -151,3 +208,15 @@ def train(
             logfile.write(f"{now};{epoch};test;{loss};{HR};{NDCG}\n")
         logfile.close()
     return model
+
+
+def _broadcast_from_main(model: Model) -> None:
+    """Data-parallel runs: every rank leaves train() with rank 0's (best-checkpoint) weights."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+        from . import fused
+
+        fused.bump_weights_epoch()

@@ -7,14 +7,10 @@ from . import ops
 
 
 def get_mask(input: torch.Tensor) -> torch.Tensor:
-    """fp32 padding mask: 0.0 where the id is 0, else 1.0 (src/utils.py:6-7).
-
-    Integer ids on a CUDA device go through the carca_padding_mask kernel; anything else
-    (float inputs, the loss mask computed on host tensors in user code) keeps torch semantics.
-    """
-    if input.is_cuda and input.dtype in (torch.int32, torch.int64):
-        return ops.padding_mask(input)
-    return torch.where(input == 0.0, 0.0, 1.0)
+    """fp32 padding mask: 0.0 where the input is 0, else 1.0 (src/utils.py:6-7), computed by the
+    carca_padding_mask / carca_padding_mask_f32 kernels.  Device tensors only: like every op of this
+    package there is no CPU path (a host tensor raises RuntimeError)."""
+    return ops.padding_mask(input)
 
 
 def to(*tensors: torch.Tensor, device: str) -> Tuple[torch.Tensor, ...]:

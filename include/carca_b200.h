@@ -85,6 +85,8 @@ int carca_transpose(float* dst, const float* src, int rows, int cols, int accumu
 
 /* mask[i] = ids[i] != 0           replaces get_mask, src/utils.py:6-7 */
 int carca_padding_mask(float* mask, const int32_t* ids, int64_t n, void* stream);
+/* the same for a float32 input (the reference's get_mask is dtype-agnostic: where(x == 0, 0, 1); -0.0 counts as 0) */
+int carca_padding_mask_f32(float* mask, const float* x, int64_t n, void* stream);
 
 /* e[p,:] = mask[p] * ( Wj [ sqrt(d) E[x_p] | Wf [a_p | c_p] + bf ] + bj (+ pos[p % n_cols]) )
  * replaces AllEmbedding.forward, src/carca.py:85-95.

@@ -12,8 +12,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Contract rows first: fixture / oracle parity of the whole path, then the fused kernels, then the wider rows.
+# (`-x` stops at the first failure: whatever runs before it is what the driver's GPU gate has seen.)
+_ORDER = ["test_abi", "test_oracle_golden", "test_gpu_parity", "test_gpu_fused_tc", "test_gpu_long_windows",
+          "test_gpu_bf16", "test_gpu_men", "test_gpu_fused_train", "test_gpu_graph", "test_gpu_catalog",
+          "test_gpu_data", "test_gpu_gemm_tc", "test_gpu_umma"]
+
+
+def _rank(item):
+    name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+    return _ORDER.index(name) if name in _ORDER else len(_ORDER)
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
+
+    items.sort(key=_rank)                     # stable: order inside a file is kept
 
     if torch.cuda.is_available():
         return

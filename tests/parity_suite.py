@@ -402,3 +402,123 @@ def check_fused_train_edges(device):
             e = grad_err(g_f[k], g_m[k], grad_floor(k))
             # d/d WK.bias is mathematically zero: both sides hold summation noise of this un-normalised loss
             assert e < (5e-3 if k.endswith("WK.bias") else 3e-4), (case, k, e)
+
+
+def _tuple_batches(shape, n_batches, B, seed, device):
+    """Eval batches as the 7-tuples a DataLoader over CARCADataset yields (p_a = o_a = None: device attr table)."""
+    from carca_replication_b200 import synth
+
+    out = []
+    for i in range(n_batches):
+        b = synth.make_eval_batch(shape, B, seed=seed + i)
+        out.append(b)
+    return out
+
+
+def check_evaluate_vs_oracle(device, decoder="ca"):
+    """evaluate() (src/train.py:35-53 signature; device accumulators, one host read) against the oracle's
+    per-batch body on the same batches: HR@10 and NDCG@10 equal to 3 decimals, mean batch loss to 1e-4."""
+    from carca_replication_b200 import synth
+    from oracle import carca_oracle as O
+
+    shape = synth.TINY
+    model = synth.build_model(shape, decoder, p=0.5, seed=21)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    table = synth.make_attr_table(shape, seed=21)
+    cfg = O.OracleConfig(d=shape.d, n_heads=shape.n_heads, n_blocks=shape.n_blocks, decoder=decoder)
+    batches = _tuple_batches(shape, 3, 11, 40, device)
+    hits = ndcg = loss = 0.0
+    users = 0
+    for b in batches:
+        h, n, l, u = O.eval_batch(sd, cfg, (b["p_x"], table.gather_dense(b["p_x"]), b["p_c"], b["o_x"],
+                                            table.gather_dense(b["o_x"]), b["o_c"], b["y_true"]))
+        hits, ndcg, loss, users = hits + h, ndcg + n, loss + l, users + u
+    model = model.to(device)
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=21).to(device))
+    loader = [(b["p_x"], None, b["p_c"], b["o_x"], None, b["o_c"], b["y_true"]) for b in batches]
+    hr, nd, ls = cb.evaluate(model, loader, device, 10)
+    assert round(hr, 3) == round(hits / users, 3)
+    assert round(nd, 3) == round(ndcg / users, 3)
+    assert abs(ls - loss / len(batches)) < 1e-4 * max(1.0, abs(loss))
+
+
+def check_weights_epoch(device, d=64):
+    """Caches derived from the weights (fused inference plan, AllEmbedding's folded item table) follow parameter
+    updates that tensor version counters cannot see: FusedAdam writes through raw pointers.  After k optimizer steps
+    the fused path, the folded per-op path and the unfolded per-op path must agree on the NEW weights."""
+    import dataclasses
+
+    from carca_replication_b200 import synth
+
+    shape = dataclasses.replace(synth.TINY, d=d)
+    model = synth.build_model(shape, "ca", p=0.0, seed=3).to(device)
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=3).to(device))
+    b = {k: v.to(device) for k, v in synth.make_eval_batch(shape, 6, seed=3).items()}
+    bt = {k: v.to(device) for k, v in synth.make_train_batch(shape, 6, seed=4).items()}
+    L = shape.seq_len
+    opt = cb.FusedAdam(model.parameters(), lr=5e-2, betas=(0.9, 0.98))
+
+    def scores(fused_on, folded_on):
+        model.eval()
+        model.use_fused_eval, model.embeds.use_folded_eval = fused_on, folded_on
+        with torch.no_grad():
+            return model.forward((b["p_x"], None, b["p_c"]), [(b["o_x"], None, b["o_c"])]).cpu().numpy()
+
+    before = scores(True, True)          # builds the plan / the folded table from the initial weights
+    scores(False, True)
+    versions = [p._version for p in model.parameters()]
+    for _ in range(3):
+        model.train()
+        opt.zero_grad()
+        y = model.forward((bt["p_x"], None, bt["p_c"]),
+                          [(bt["o_x"][:, :L], None, bt["o_c"][:, :L]), (bt["o_x"][:, L:], None, bt["o_c"][:, L:])])
+        cb.BinaryCrossEntropy().forward(y, bt["y_true"], cb.get_mask(bt["o_x"])).backward()
+        opt.step()
+    assert versions == [p._version for p in model.parameters()]      # the premise: versions did not move
+    ref = scores(False, False)           # per-op kernels, unfolded embedding: reads the parameters directly
+    assert rel_err(before, ref) > 1e-3   # the weights did move
+    assert rel_err(scores(False, True), ref) < FP32_RTOL
+    assert rel_err(scores(True, True), ref) < FP32_RTOL
+    model.use_fused_eval, model.embeds.use_folded_eval = True, True
+
+
+def check_train_loop_checkpoint(device, tmpdir):
+    """train() (src/train.py:56-152 signature) end to end on a tiny synthetic set: CSV log format, best-NDCG
+    checkpoint written as a state_dict file that the weights-only unpickler reads and that loads strictly into a
+    fresh model (and into the reference's own key layout), returned model == checkpoint."""
+    import os
+
+    from carca_replication_b200 import synth
+    from carca_replication_b200.train import CHECKPOINT_FORMAT, load_checkpoint, train
+
+    shape = synth.TINY
+    model = synth.build_model(shape, "dot", p=0.2, seed=8).to(device)
+    table = synth.make_attr_table(shape, seed=8).to(device)
+    model.embeds.set_attr_table(table)
+    tr = [synth.make_train_batch(shape, 8, seed=60 + i) for i in range(3)]
+    ev = [synth.make_eval_batch(shape, 8, seed=70 + i) for i in range(2)]
+    as_tuple = lambda b: (b["p_x"], None, b["p_c"], b["o_x"], None, b["o_c"], b["y_true"])   # noqa: E731
+    opt = cb.FusedAdam(model.parameters(), lr=1e-2, betas=(0.9, 0.98))
+    datadir = os.path.join(str(tmpdir), "run")
+    cwd = os.getcwd()
+    os.chdir(str(tmpdir))
+    try:
+        out = train(model, [as_tuple(b) for b in tr], [as_tuple(b) for b in ev], [as_tuple(b) for b in ev], device, opt,
+                    epochs=3, top_k=10, verbose=1, early_stop=5, datadir="run")
+    finally:
+        os.chdir(cwd)
+    files = sorted(os.listdir(datadir))
+    pth = [f for f in files if f.endswith(".pth")]
+    assert len(pth) == 1 and len(pth[0].split("_")) == 3                       # {epoch:03d}_{HR:.4f}_{NDCG:.4f}.pth
+    blob = torch.load(os.path.join(datadir, pth[0]), weights_only=True)        # no pickled code in the file
+    assert blob["format"] == CHECKPOINT_FORMAT and int(pth[0][:3]) == blob["epoch"]
+    assert set(blob["state_dict"]) == set(model.state_dict())
+    fresh = synth.build_model(shape, "dot", p=0.2, seed=99).to(device)
+    fresh.embeds.set_attr_table(table)
+    load_checkpoint(fresh, os.path.join(datadir, pth[0]))
+    for (k, a), (_, c) in zip(out.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a.cpu(), c.cpu()), k
+    csv = [f for f in files if f.endswith(".csv")]
+    assert len(csv) == 1
+    rows = [r.split(";") for r in open(os.path.join(datadir, csv[0])).read().strip().split("\n")]
+    assert all(len(r) == 6 for r in rows) and {r[2] for r in rows} == {"train", "val", "test"}   # time;epoch;split;loss;HR;NDCG

@@ -77,3 +77,17 @@ def test_fused_adam_vs_torch(emu_backend, wd):
 
 def test_fused_train_edge_shapes(emu_backend):
     S.check_fused_train_edges(emu_backend)
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_evaluate_vs_oracle(emu_backend, decoder):
+    S.check_evaluate_vs_oracle(emu_backend, decoder)
+
+
+@pytest.mark.parametrize("d", [64, 32])
+def test_weight_derived_caches_follow_fused_adam(emu_backend, d):
+    S.check_weights_epoch(emu_backend, d=d)
+
+
+def test_train_loop_writes_state_dict_checkpoint(emu_backend, tmp_path):
+    S.check_train_loop_checkpoint(emu_backend, tmp_path)

@@ -18,8 +18,10 @@ def test_device_loader_drops_into_evaluate():
     S.check_loader_in_evaluate("cuda")
 
 
-def test_loader_throughput_smoke():
-    """Beauty-sized log: one 8192-user eval batch is built in well under a millisecond-scale budget."""
+def test_loader_covers_every_user_of_a_beauty_sized_log():
+    """Beauty-sized log through DeviceLoader in 8192-user eval batches: every user appears exactly once, windows are
+    left-padded and end in a valid item.  (Throughput is reported by bench.py's `device_pipeline` section — there is
+    no wall-clock threshold in the parity gate.)"""
     import numpy as np
     import torch
 
@@ -33,16 +35,12 @@ def test_loader_throughput_smoke():
     ctx = rng.random((int(rowptr[-1]), C), dtype=np.float32)
     log = DeviceInteractions(torch.from_numpy(rowptr), torch.from_numpy(items), torch.from_numpy(ctx)).to("cuda")
     loader = DeviceLoader(log, n_items, 50, 100, "test", batch_size=8192)
-    it = iter(loader)
-    next(it)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
     n = 0
-    for b in it:
-        n += b[0].shape[0]
-    e1.record()
-    torch.cuda.synchronize()
-    users_per_s = n / (e0.elapsed_time(e1) * 1e-3)
-    print(f"device loader: {users_per_s:.0f} users/s")
-    assert users_per_s > 1e6          # the reference loader builds ~500 users/s on the host
+    for b in loader:
+        p_x, o_x = b[0], b[3]
+        n += p_x.shape[0]
+        assert bool((p_x[:, -1] != 0).all())                       # left padding: the window ends in a real item
+        assert bool((o_x != 0).all()) and o_x.shape[1] == 101        # 1 positive + 100 sampled negatives
+        pad = (p_x == 0)
+        assert bool((pad[:, 1:] <= pad[:, :-1]).all())               # padding only on the left
+    assert n == U

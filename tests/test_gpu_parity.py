@@ -48,6 +48,20 @@ def test_pickle_roundtrip_and_b1_shape():
     S.check_pickle_and_shapes(DEV)
 
 
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_evaluate_vs_oracle(decoder):
+    S.check_evaluate_vs_oracle(DEV, decoder)
+
+
+@pytest.mark.parametrize("d", [64, 32])
+def test_weight_derived_caches_follow_fused_adam(d):
+    S.check_weights_epoch(DEV, d=d)
+
+
+def test_train_loop_writes_state_dict_checkpoint(tmp_path):
+    S.check_train_loop_checkpoint(DEV, tmp_path)
+
+
 def test_library_loaded_is_the_in_tree_cuda_build():
     from carca_replication_b200 import _native as N
 
