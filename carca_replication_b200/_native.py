@@ -141,6 +141,10 @@ SIGNATURES = {
                                 vp],
     "carca_eval_scratch_bytes": [i32],
     "carca_eval_forward_catalog": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+    "carca_rows_plan_bytes": [P(ModelParams)],
+    "carca_rows_prepare": [vp, vp, vp, P(ModelParams), vp],
+    "carca_rows_scratch_bytes": [P(ModelParams), i32, i32],
+    "carca_rows_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
@@ -159,6 +163,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.carca_set_seed_source.restype = None
     lib.carca_eval_plan_floats.restype = C.c_int64
     lib.carca_eval_scratch_bytes.restype = C.c_int64
+    lib.carca_rows_plan_bytes.restype = C.c_int64
+    lib.carca_rows_scratch_bytes.restype = C.c_int64
     lib.carca_train_core_set_ticks.restype = None
     lib.carca_train_core_rows_ints.restype = C.c_int64
     lib.carca_train_core_saved_floats.restype = C.c_int64

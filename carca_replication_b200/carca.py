@@ -454,8 +454,15 @@ class CARCA(Model):
             return False
         from . import fused
         from . import _native
-        if not (_native.is_device_tensor(profile[0]) and fused.supported(self, profile[0].shape[1],
-                                                                         profile[2].shape[-1])):
+        if not _native.is_device_tensor(profile[0]):
+            return False
+        if self.eval_dtype == "bf16":
+            # bf16 packed-rows pipeline: no per-user row limit, nothing to check on the host
+            if not fused.rows_supported(self, profile[0].shape[1], profile[2].shape[-1]):
+                raise RuntimeError("CARCA.eval_dtype == 'bf16' needs AllEmbedding with a device attribute table, stock "
+                                   "blocks / decoder, d in {64, 256}, head width 32 or 64, C <= 8, L <= 256")
+            return True
+        if not fused.supported(self, profile[0].shape[1], profile[2].shape[-1]):
             return False
         # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin (one device
         # reduction + host read; GraphedEvalStep checks the batch itself before it replays a captured step)
@@ -466,6 +473,17 @@ class CARCA(Model):
         return fused.fits_packed(profile[0])
 
     _fits_eval_override: Optional[bool] = None
+
+    # Arithmetic of the fused inference path: "fp32" (3xTF32 tensor-core kernel, scores within 1e-4 of the reference)
+    # or "bf16" (BASELINE configs[1]: bf16 operands and tables, fp32 accumulation / softmax / LayerNorm, within 1e-2)
+    eval_dtype = "fp32"
+
+    def set_eval_dtype(self, dtype) -> "CARCA":
+        name = {torch.float32: "fp32", torch.bfloat16: "bf16", "fp32": "fp32", "f32": "fp32", "bf16": "bf16"}.get(dtype)
+        if name is None:
+            raise ValueError(f"eval_dtype must be fp32 or bf16, got {dtype!r}")
+        self.eval_dtype = name
+        return self
 
     use_fused_train = True  # class default; set False on an instance to force the per-op training path
 
@@ -562,6 +580,8 @@ class CARCA(Model):
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:
         if self._fused_eval_applies(profile, targets):
             from . import fused
+            if self.eval_dtype == "bf16":
+                return fused.forward_rows(self, profile, targets)
             return fused.forward(self, profile, targets)
         if self._fused_train_applies(profile, targets):
             return self._forward_fused_train(profile, targets)

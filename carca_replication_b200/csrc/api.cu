@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "layernorm.cuh"
 #include "optim.cuh"
+#include "plan_layout.cuh"
 #include "score.cuh"
 #include "variants.cuh"
 
@@ -913,31 +914,6 @@ int carca_build_train_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c, 
 }
 
 // ------------------------------------------------------------------------------------ fused inference
-namespace {
-struct PlanLayout {
-  long long tfold, mc, blocks, cross, tc_blocks, tc_cross, tq, tw, mcq, mcw, total;
-};
-constexpr long long kTcPacked = 2 * 18 * 64 * 4;   // floats of one packed tensor-core weight (hi | lo)
-PlanLayout plan_layout(const carca_model_params* m) {
-  PlanLayout p;
-  const long long d = m->embed.d, n = m->embed.n_items;
-  p.tfold = 0;
-  p.mc = p.tfold + n * d;
-  p.blocks = p.mc + d * 8;
-  p.cross = p.blocks + (long long)m->n_blocks * 5 * d * d;
-  p.tc_blocks = p.cross + (m->decoder_kind == 1 ? 3 * d * d : 0);
-  const bool tc = d == 64;   // packed operands of the tcgen05 kernel (fused_eval_tc.cuh)
-  const bool tcx = tc && m->decoder_kind == 1;
-  p.tc_cross = p.tc_blocks + (tc ? (long long)m->n_blocks * 5 * kTcPacked : 0);
-  p.tq = p.tc_cross + (tcx ? 3 * kTcPacked : 0);
-  p.tw = p.tq + (tcx ? n * 64 : 0);
-  p.mcq = p.tw + (tcx ? (n + 3) / 4 * 4 : 0);
-  p.mcw = p.mcq + (tcx ? 64 * 8 : 0);
-  p.total = p.mcw + (tcx ? 8 : 0);
-  return p;
-}
-}  // namespace
-
 int64_t carca_eval_plan_floats(const carca_model_params* m) { return plan_layout(m).total; }
 
 int carca_eval_prepare(float* plan, float* scratch_q, const carca_model_params* m, const carca_attr_source* at,

@@ -1,0 +1,769 @@
+// bf16 inference pipeline over PACKED ROWS (d = 64 or 256): CARCA.forward in eval mode, src/carca.py:411-431 with
+// :85-95 (embedding, folded), :228-265 (attention), :297-318 (encoder block), :338-365 (decoders).
+//
+// The fp32 path (fused_eval_tc.cuh) keeps a 128-row tile on one SM through the whole model; that dependent chain is
+// latency-bound and needs every user to fit a 64-row bin.  This path is the opposite trade: the batch's VALID profile
+// positions (plus position L-1, which the dot decoder reads) are packed, user after user, into one flat row array
+// [R, d] and every stage of the model is one kernel over all R rows:
+//
+//   rows_pack        ids -> row list (user, position), segment start per row, (start, length) per user
+//   rows_embed_ln    e = T[id] + Mc c (+ pos)           -> x (bf16 operand tiles), LN1(x) (fp32 rows + bf16 tiles)
+//   per block:
+//     rows_gemm x3   Q = LN1(x) Wq^T, K = x Wk^T, V = x Wv^T        (one grouped launch, tcgen05 kind::f16)
+//     rows_attn      causal attention inside the row's segment + residual + LN2   (fp32 softmax / LN)
+//     rows_gemm      F1 = LeakyReLU(s2 W1^T + b1)
+//     rows_gemm      x' = F1 W2^T + b2 + s2, then the NEXT LayerNorm (LN1 of block b+1 or the final norm) in the epilogue
+//   decoder:  K / V projections of the encoded profile (grouped rows_gemm, epilogues fold V into u = <V_h, wf_h> and
+//             K into its context terms), then one kernel over (user, candidate) rows.
+//
+// rows_gemm is a warp-specialised tcgen05 GEMM: [R, d] x [d, d] with the WEIGHT MATRIX RESIDENT in shared memory for
+// the whole kernel (128 KB at d = 256), A tiles streamed by the TMA engine (cp.async.bulk, 16 KB per 64-wide K chunk:
+// activations are stored in HBM in the operand layout [tile][k/8][128 rows][8], so a chunk is one contiguous copy),
+// fp32 accumulators double-buffered in TMEM (2 x d columns) so the epilogue of tile i (bias, activation, residual,
+// LayerNorm, bf16 conversion: one thread per row, whole row visible in TMEM) overlaps the MMAs of tile i+1; two
+// epilogue warpgroups alternate tiles.  Roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..9 = epilogue.
+// No segment or tile constraint: a user may have any number of valid positions (L <= 256).
+#pragma once
+#include "common.cuh"
+#ifndef CARCA_EMU
+#include <cuda_bf16.h>
+
+#include "tmem_io.cuh"
+#include "umma.cuh"
+
+namespace carca {
+namespace rows {
+
+typedef __nv_bfloat16 bf16;
+constexpr int TILE = 128;
+
+// ---------------------------------------------------------------------------------------------- small helpers
+__device__ __forceinline__ void unpack8(const uint4& p, float (&v)[8]) {
+  const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+// element offset of (row r, k-group kg) in the operand-tiled layout [tile][D/8][128][8]
+template <int D>
+__device__ __forceinline__ long long tile_off(long long r, int kg) {
+  return ((r >> 7) * (D / 8) + kg) * (128 * 8) + (r & 127) * 8;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---------------------------------------------------------------------------------------------- packing
+// row_src[r] = pos | user << 8 | (id == 0) << 31;  row_seg[r] = first row of the user's segment;
+// useg[u] = (first row, rows).  Segments are placed with one atomicAdd per user (order is irrelevant: users are
+// independent and every row-wise stage is position-independent inside a tile).
+__global__ void __launch_bounds__(256) rows_pack_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
+                                                        int2* __restrict__ useg, int* __restrict__ n_rows,
+                                                        const int* __restrict__ p_x, int B, int L) {
+  const int u = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (u >= B) return;
+  const int* px = p_x + (long long)u * L;
+  int n = 0;
+  for (int p0 = 0; p0 < L; p0 += 32) {
+    const int p = p0 + lane;
+    const bool keep = p < L && (px[p] != 0 || p == L - 1);
+    n += __popc(__ballot_sync(kFull, keep));
+  }
+  int base = 0;
+  if (lane == 0) {
+    base = atomicAdd(n_rows, n);
+    useg[u] = make_int2(base, n);
+  }
+  base = __shfl_sync(kFull, base, 0);
+  int k = 0;
+  for (int p0 = 0; p0 < L; p0 += 32) {
+    const int p = p0 + lane;
+    const int id = p < L ? px[p] : 0;
+    const bool keep = p < L && (id != 0 || p == L - 1);
+    const uint32_t m = __ballot_sync(kFull, keep);
+    if (keep) {
+      const int r = base + k + __popc(m & ((1u << lane) - 1u));
+      row_src[r] = p | (u << 8) | (id == 0 ? (int)0x80000000u : 0);
+      row_seg[r] = base;
+    }
+    k += __popc(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- embedding + LN1
+struct EmbedArgs {
+  const bf16* Tb;           // folded item table [n_items, D] (T[i] = Wj [sqrt(d) E[i] | Wf_a attrs[i] + bf] + bj)
+  const float* Mc;          // folded context map [D][8]
+  const float* pos;         // optional positional table [L, D]
+  const int* p_x;
+  const float* p_c;
+  const int *row_src, *n_rows;
+  const float *ln_g, *ln_b;
+  bf16 *XA, *QA;            // operand tiles: x and LN(x)
+  float* QN;                // LN(x) rows, fp32 (residual)
+  int L, C;
+};
+// one group of D/8 lanes per row, 8 consecutive features per lane
+template <int D>
+__global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
+  constexpr int G = D / 8, RPW = 32 / G;
+  __shared__ float mct[8][D];
+  for (int i = threadIdx.x; i < 8 * D; i += blockDim.x) mct[i % 8][i / 8] = a.Mc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+  const int R = *a.n_rows;
+  for (long long r0 = (long long)warp * RPW; r0 < R; r0 += (long long)n_warps * RPW) {
+    const long long r = r0 + sub;
+    const bool live = r < R;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    if (live) {
+      const int src = a.row_src[r];
+      const int pos = src & 255, u = (src >> 8) & 0x7fffff;
+      if (src >= 0) {
+        const int id = a.p_x[(long long)u * a.L + pos];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.Tb + (long long)id * D) + l), x);
+        const float* c = a.p_c + ((long long)u * a.L + pos) * a.C;
+        for (int k = 0; k < a.C; ++k) {
+          const float cv = __ldg(c + k);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = fmaf(mct[k][8 * l + e], cv, x[e]);
+        }
+        if (a.pos) {
+          const float4* pp = reinterpret_cast<const float4*>(a.pos + (long long)pos * D + 8 * l);
+          const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+          x[0] += p0.x; x[1] += p0.y; x[2] += p0.z; x[3] += p0.w;
+          x[4] += p1.x; x[5] += p1.y; x[6] += p1.z; x[7] += p1.w;
+        }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += x[e];
+    const float mean = group_sum<G>(s) * (1.0f / D);
+    float m2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m2 = fmaf(x[e] - mean, x[e] - mean, m2);
+    const float rstd = rsqrtf(group_sum<G>(m2) * (1.0f / D) + kLnEps);
+    if (live) {
+      float q[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * l)), g1 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * l) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * l)), b1 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * l) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[e] = (x[e] - mean) * rstd * gg[e] + bb[e];
+      *reinterpret_cast<uint4*>(a.XA + tile_off<D>(r, l)) = pack8(x);
+      *reinterpret_cast<uint4*>(a.QA + tile_off<D>(r, l)) = pack8(q);
+      float4* qo = reinterpret_cast<float4*>(a.QN + r * D + 8 * l);
+      qo[0] = make_float4(q[0], q[1], q[2], q[3]);
+      qo[1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- attention + LN2
+struct AttnRowsArgs {
+  const bf16 *Q, *K, *V;    // rows [R, D]
+  const float* QN;          // LN1(x) rows (residual, src/carca.py:302)
+  const int *row_src, *row_seg, *n_rows;
+  const float *ln_g, *ln_b;
+  float* S2;                // LN2 rows, fp32 (residual of the FFN, :316)
+  bf16* S2A;                // LN2 operand tiles
+  int residual;
+};
+// causal self-attention of one packed row over the rows of its own segment (src/carca.py:299 with :246-256: keys of
+// the same user at positions <= the query's; a padding query row gives exactly 0), + LN1 residual, LayerNorm 2.
+// One group of D/8 lanes per row; a lane owns 8 consecutive features, i.e. a slice of one head.
+template <int D, int H>
+__global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a) {
+  constexpr int G = D / 8, RPW = 32 / G, DH = D / H, LPH = DH / 8;   // lanes per head
+  static_assert(DH % 8 == 0 && LPH >= 1 && LPH <= 8, "head width");
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+  const int R = *a.n_rows;
+  const float sc = 1.4426950408889634f * rsqrtf((float)DH);
+  for (long long r0 = (long long)warp * RPW; r0 < R; r0 += (long long)n_warps * RPW) {
+    const long long r = r0 + sub;
+    const bool live = r < R;
+    const int src = live ? a.row_src[r] : (int)0x80000000u;
+    const int s0 = live ? a.row_seg[r] : 0;
+    // every lane of the warp runs the same number of iterations (shuffles inside): the longest of its rows
+    int n_keys = (live && src >= 0) ? (int)(r - s0) + 1 : 0;
+    int n_max = n_keys;
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) n_max = max(n_max, __shfl_xor_sync(kFull, n_max, o));
+    float q[8], acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { q[e] = 0.f; acc[e] = 0.f; }
+    if (n_keys > 0) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.Q + r * D) + l), q);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[e] *= sc;
+    }
+    float m = -INFINITY, z = 0.f;
+    for (int j = 0; j < n_max; ++j) {
+      const bool on = j < n_keys;
+      const long long kr = on ? (long long)s0 + j : 0;
+      float kv[8], vv[8];
+      unpack8(on ? __ldg(reinterpret_cast<const uint4*>(a.K + kr * D) + l) : make_uint4(0, 0, 0, 0), kv);
+      unpack8(on ? __ldg(reinterpret_cast<const uint4*>(a.V + kr * D) + l) : make_uint4(0, 0, 0, 0), vv);
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q[e], kv[e], s);
+#pragma unroll
+      for (int o = LPH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+      if (on) {
+        const float mn = fmaxf(m, s);
+        const float corr = ex2f(m - mn), p = ex2f(s - mn);
+        z = fmaf(z, corr, p);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(acc[e], corr, p * vv[e]);
+        m = mn;
+      }
+    }
+    float v[8];
+    {
+      const float inv = z > 0.f ? 1.0f / z : 0.f;
+      float qn[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live && a.residual) {
+        const float4* qp = reinterpret_cast<const float4*>(a.QN + r * D + 8 * l);
+        const float4 q0 = qp[0], q1 = qp[1];
+        qn[0] = q0.x; qn[1] = q0.y; qn[2] = q0.z; qn[3] = q0.w; qn[4] = q1.x; qn[5] = q1.y; qn[6] = q1.z; qn[7] = q1.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(acc[e], inv, qn[e]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[e];
+    const float mean = group_sum<G>(s) * (1.0f / D);
+    float m2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m2 = fmaf(v[e] - mean, v[e] - mean, m2);
+    const float rstd = rsqrtf(group_sum<G>(m2) * (1.0f / D) + kLnEps);
+    if (live) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * l)), g1 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * l) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * l)), b1 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * l) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
+      float4* so = reinterpret_cast<float4*>(a.S2 + r * D + 8 * l);
+      so[0] = make_float4(o[0], o[1], o[2], o[3]);
+      so[1] = make_float4(o[4], o[5], o[6], o[7]);
+      *reinterpret_cast<uint4*>(a.S2A + tile_off<D>(r, l)) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+enum { EPI_ROWS = 0, EPI_LRELU_TILE = 1, EPI_LN = 2, EPI_VDOT = 3, EPI_KDEC = 4 };
+
+struct GemmJob {
+  const bf16* A;            // operand tiles [n_tiles][D/8][128][8]
+  const bf16* W;            // packed weight [D/8][D (out features)][8]
+  const float* bias;        // [D]
+  int epi;
+  bf16* out_rows;           // EPI_ROWS / EPI_KDEC: bf16 rows [R, D]
+  bf16* out_tile;           // EPI_LRELU_TILE: activation tiles; EPI_LN: tiles of the pre-norm value x' (may be null)
+  const float* resid;       // EPI_LN: fp32 rows added before the norm (null: no residual)
+  const float *ln_g, *ln_b; // EPI_LN
+  float* out_f32;           // EPI_LN: LN rows fp32
+  bf16* out_tile2;          // EPI_LN: LN tiles
+  const float* wf;          // EPI_VDOT: scorer weight [D]
+  float* U;                 // EPI_VDOT: u[r][h] = <V_h[r], wf_h>
+  const float* McQ;         // EPI_KDEC: context map of the query side [D][8]
+  float* KM;                // EPI_KDEC: km[r][h][k] = <K_h[r], McQ_h[:, k]>
+};
+struct GemmArgs {
+  GemmJob job[3];
+  int n_jobs;
+  const int* n_rows;
+  int H;
+  int* status;
+};
+
+template <int D>
+struct GemmCfg {
+  static constexpr int KG = D / 8;
+  static constexpr int CHUNK_KG = 8;                         // 64 k per A stage
+  static constexpr int CHUNKS = KG / CHUNK_KG;
+  static constexpr int STAGE_BYTES = CHUNK_KG * TILE * 16;   // 16 KB
+  static constexpr int STAGES = D == 256 ? 5 : 4;
+  static constexpr int W_BYTES = KG * D * 16;
+  static constexpr int PARAM_FLOATS = 12 * D;                // bias | ln_g | ln_b | wf | McQ^T [8][D]
+  static constexpr int TMEM_COLS = 2 * D;
+  static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)STAGES * STAGE_BYTES + PARAM_FLOATS * 4 + 256;
+};
+constexpr int GEMM_THREADS = 320;   // producer warp, MMA warp, 8 epilogue warps
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+// TMA engine, non-tensor form: one contiguous global -> shared copy that completes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   umma::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) {   // bf16 x bf16 -> f32, both K-major, M = 128
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+      : "memory");
+}
+__device__ __forceinline__ bool wait_or_flag(uint64_t* bar, uint32_t parity, int* status) {
+  if (umma::mbar_wait(bar, parity, 20000000)) return true;
+  atomicOr(status, 2);
+  return false;
+}
+
+template <int D>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmArgs a) {
+  using Cfg = GemmCfg<D>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* w_smem = smem_raw;
+  unsigned char* a_smem = smem_raw + Cfg::W_BYTES;
+  float* prm = reinterpret_cast<float*>(a_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(prm + Cfg::PARAM_FLOATS);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* acc_full = empty + Cfg::STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* w_full = acc_empty + 2;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jid = blockIdx.x % a.n_jobs, slot = blockIdx.x / a.n_jobs, n_slots = gridDim.x / a.n_jobs;
+  const GemmJob& J = a.job[jid];
+  const int R = *a.n_rows;
+  const int n_tiles = (R + TILE - 1) / TILE;
+  if (slot >= n_slots) return;                 // (gridDim.x not a multiple of n_jobs)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { umma::mbar_init(&acc_full[s], 1); umma::mbar_init(&acc_empty[s], 4); }
+    umma::mbar_init(w_full, 1);
+  }
+  if (warp == 1) umma::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  // epilogue parameters -> shared memory
+  for (int i = threadIdx.x; i < D; i += GEMM_THREADS) {
+    prm[i] = J.bias ? J.bias[i] : 0.f;
+    prm[D + i] = J.ln_g ? J.ln_g[i] : 1.f;
+    prm[2 * D + i] = J.ln_b ? J.ln_b[i] : 0.f;
+    prm[3 * D + i] = J.wf ? J.wf[i] : 0.f;
+  }
+  if (J.epi == EPI_KDEC)
+    for (int i = threadIdx.x; i < 8 * D; i += GEMM_THREADS) prm[4 * D + (i % 8) * D + i / 8] = J.McQ[i];
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem0 = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: the weight matrix once, then the A chunks of this CTA's tiles through the stage ring
+    if (lane == 0 && slot < n_tiles) {
+      mbar_expect_tx(w_full, Cfg::W_BYTES);
+      for (int off = 0; off < Cfg::W_BYTES; off += 16384)
+        bulk_g2s(w_smem + off, reinterpret_cast<const unsigned char*>(J.W) + off, min(16384, Cfg::W_BYTES - off), w_full);
+      uint32_t it = 0;
+      for (int tile = slot; tile < n_tiles; tile += n_slots) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(J.A) + (size_t)tile * (TILE * D * 2);
+        for (int c = 0; c < Cfg::CHUNKS; ++c, ++it) {
+          const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1u;
+          if (!wait_or_flag(&empty[s], ph ^ 1u, a.status)) break;
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          bulk_g2s(a_smem + s * Cfg::STAGE_BYTES, src + (size_t)c * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane)
+    if (slot < n_tiles) {
+      constexpr uint32_t idesc = idesc_bf16(D);
+      constexpr uint32_t a_lbo = TILE * 16, b_lbo = D * 16;
+      const uint32_t w_addr = umma::smem_u32(w_smem), a_addr0 = umma::smem_u32(a_smem);
+      bool ok = wait_or_flag(w_full, 0, a.status);
+      uint32_t it = 0, t = 0;
+      for (int tile = slot; tile < n_tiles && ok; tile += n_slots, ++t) {
+        const uint32_t as = t & 1u, aph = (t >> 1) & 1u;
+        ok = wait_or_flag(&acc_empty[as], aph ^ 1u, a.status);       // epilogue drained this accumulator
+        umma::fence_after_sync();
+        const uint32_t d_tmem = tmem0 + as * D;
+        for (int c = 0; c < Cfg::CHUNKS && ok; ++c, ++it) {
+          const uint32_t s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1u;
+          ok = wait_or_flag(&full[s], ph, a.status);
+          umma::fence_after_sync();
+          if (umma::elect_one()) {
+            const uint32_t a_addr = a_addr0 + s * Cfg::STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = umma::smem_desc(a_addr + ks * 2 * a_lbo, a_lbo, 128);
+              const uint64_t db = umma::smem_desc(w_addr + (c * 8 + ks * 2) * b_lbo, b_lbo, 128);
+              mma_bf16_ss(d_tmem, da, db, idesc, !(c == 0 && ks == 0));
+            }
+            umma::commit(&empty[s]);                                 // stage free when these MMAs have read it
+            if (c == Cfg::CHUNKS - 1) umma::commit(&acc_full[as]);   // accumulator complete
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: group g = (warp - 2) / 4 takes the tiles whose accumulator stage is g
+    const int g = (warp - 2) >> 2, quarter = warp & 3;
+    const int row_in_tile = 32 * quarter + lane;
+    const uint32_t lane_base = tmem0 + ((uint32_t)(32 * quarter) << 16) + g * D;
+    const int H = a.H, DH = D / H;
+    uint32_t t = 0;
+    bool ok = true;
+    for (int tile = slot; tile < n_tiles && ok; tile += n_slots, ++t) {
+      if ((int)(t & 1u) != g) continue;
+      const uint32_t aph = (t >> 1) & 1u;
+      ok = wait_or_flag(&acc_full[g], aph, a.status);
+      umma::fence_after_sync();
+      const long long r = (long long)tile * TILE + row_in_tile;
+      const bool live = r < R;
+      if (J.epi == EPI_ROWS || J.epi == EPI_LRELU_TILE) {
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            v[e] += prm[32 * c + e];
+            if (J.epi == EPI_LRELU_TILE) v[e] = v[e] > 0.f ? v[e] : kLeakySlope * v[e];
+          }
+          if (J.epi == EPI_ROWS) {
+            if (live) {
+              uint4* o = reinterpret_cast<uint4*>(J.out_rows + r * D + 32 * c);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[q] = pack8(&v[8 * q]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(J.out_tile + tile_off<D>(r, 4 * c + q)) = pack8(&v[8 * q]);
+          }
+        }
+      } else if (J.epi == EPI_LN) {
+        // pass 1: x' = acc + bias (+ residual) back into TMEM, row sum
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+          if (J.resid && live) {
+            const float4* rp = reinterpret_cast<const float4*>(J.resid + r * D + 32 * c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 x = rp[q];
+              v[4 * q] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            v[e] += prm[32 * c + e];
+            sum += v[e];
+          }
+          umma::tmem_st_x32(lane_base + 32 * c, v, 0);
+          if (J.out_tile) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(J.out_tile + tile_off<D>(r, 4 * c + q)) = pack8(&v[8 * q]);
+          }
+        }
+        umma::tmem_st_wait();
+        const float mean = sum * (1.0f / D);
+        float m2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m2 = fmaf(v[e] - mean, v[e] - mean, m2);
+        }
+        const float rstd = rsqrtf(m2 * (1.0f / D) + kLnEps);
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = (v[e] - mean) * rstd * prm[D + 32 * c + e] + prm[2 * D + 32 * c + e];
+          if (live) {
+            float4* o = reinterpret_cast<float4*>(J.out_f32 + r * D + 32 * c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(J.out_tile2 + tile_off<D>(r, 4 * c + q)) = pack8(&v[8 * q]);
+        }
+      } else if (J.epi == EPI_VDOT) {
+        float u = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) u = fmaf(v[e] + prm[32 * c + e], prm[3 * D + 32 * c + e], u);
+          if ((32 * (c + 1)) % DH == 0) {
+            if (live) J.U[r * H + (32 * c) / DH] = u;
+            u = 0.f;
+          }
+        }
+      } else {   // EPI_KDEC
+        float km[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) km[k] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          float v[32];
+          umma::tmem_ld_1x32(lane_base + 32 * c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] += prm[32 * c + e];
+          if (live) {
+            uint4* o = reinterpret_cast<uint4*>(J.out_rows + r * D + 32 * c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = pack8(&v[8 * q]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float* mk = prm + 4 * D + k * D + 32 * c;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) km[k] = fmaf(v[e], mk[e], km[k]);
+          }
+          if ((32 * (c + 1)) % DH == 0) {
+            if (live) {
+              float4* o = reinterpret_cast<float4*>(J.KM + (r * H + (32 * c) / DH) * 8);
+              o[0] = make_float4(km[0], km[1], km[2], km[3]);
+              o[1] = make_float4(km[4], km[5], km[6], km[7]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) km[k] = 0.f;
+          }
+        }
+      }
+      // accumulator stage g is free again
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[g]);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_free(tmem0, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------- decoders
+struct DecodeArgs {
+  // cross-attention (src/carca.py:338-347): keys of the encoded profile and the folded candidate tables
+  const bf16* Kd;           // decoder keys, rows [R, D]
+  const float* U;           // u[r][h] = <V_h[r], wf_h>
+  const float* KM;          // km[r][h][k]
+  const bf16* TQb;          // WQ T[i] + bq  [n_items, D]
+  const float* tw;          // <T[i], wf>    [n_items]
+  const float* mcw;         // wf Mc         [8]
+  const float* dbf;         // scorer bias   [1]
+  // dot product (:358-365)
+  const float* PE;          // encoded profile rows fp32 [R, D]
+  const bf16* Tb;
+  const float* Mc;          // [D][8]
+  const int2* useg;
+  const int* row_src;
+  const int* o_x;
+  const float* o_c;
+  long long oc_user, oc_tgt;
+  float* y;
+  long long ldy;
+  int col0, B, T, C, L, cat_lo, residual_ca;
+};
+constexpr int DEC_KEYS = 48;   // keys staged per pass (48 KB of static shared memory at d = 256, 8 heads)
+
+// one CTA per (user, slice of 128 candidates); thread = candidate; the user's keys are staged in shared memory and
+// read by all threads at the same address (broadcast)
+template <int D, int H>
+__global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a) {
+  constexpr int DH = D / H;
+  __shared__ __align__(16) bf16 ks[DEC_KEYS][D];
+  __shared__ float us[DEC_KEYS][H];
+  __shared__ __align__(16) float kms[DEC_KEYS][H][8];
+  __shared__ float kvalid[DEC_KEYS];
+  const float sc = 1.4426950408889634f * rsqrtf((float)DH);
+  const int n_slices = (a.T + 127) / 128;
+  const float bfv = __ldg(a.dbf);
+  for (long long item = blockIdx.x; item < (long long)a.B * n_slices; item += gridDim.x) {
+    const int u = (int)(item / n_slices), t = (int)(item % n_slices) * 128 + threadIdx.x;
+    const int2 sg = a.useg[u];
+    const bool has = t < a.T;
+    const int id = !has ? 0 : (a.cat_lo > 0 ? a.cat_lo + t : __ldg(a.o_x + (long long)u * a.T + t));
+    float cv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cv[k] = 0.f;
+    if (has && id != 0) {
+      const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
+      for (int k = 0; k < a.C; ++k) cv[k] = __ldg(c + k);
+    }
+    float m[H], z[H], d[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; z[h] = 0.f; d[h] = 0.f; }
+    for (int k0 = 0; k0 < sg.y; k0 += DEC_KEYS) {
+      const int nk = min(DEC_KEYS, sg.y - k0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nk * (D / 8); i += 128) {
+        const int j = i / (D / 8), kg = i % (D / 8);
+        reinterpret_cast<uint4*>(&ks[j][0])[kg] = __ldg(reinterpret_cast<const uint4*>(a.Kd + (long long)(sg.x + k0 + j) * D) + kg);
+      }
+      for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
+      for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
+      for (int i = threadIdx.x; i < nk; i += 128) kvalid[i] = a.row_src[sg.x + k0 + i] >= 0 ? 1.f : 0.f;
+      __syncthreads();
+      if (has && id != 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float q[DH];
+          const uint4* qp = reinterpret_cast<const uint4*>(a.TQb + (long long)id * D + h * DH);
+#pragma unroll
+          for (int i = 0; i < DH / 8; ++i) {
+            float t8[8];
+            unpack8(__ldg(qp + i), t8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[8 * i + e] = t8[e];
+          }
+          for (int j = 0; j < nk; ++j) {
+            if (kvalid[j] == 0.f) continue;                   // padding key (position L-1 of a short window)
+            const uint4* kp = reinterpret_cast<const uint4*>(&ks[j][h * DH]);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < DH / 8; ++i) {
+              float k8[8];
+              unpack8(kp[i], k8);
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                s0 = fmaf(q[8 * i + e], k8[e], s0);
+                s1 = fmaf(q[8 * i + e + 1], k8[e + 1], s1);
+              }
+            }
+            float s = s0 + s1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(cv[k], kms[j][h][k], s);
+            s *= sc;
+            const float mn = fmaxf(m[h], s);
+            const float corr = ex2f(m[h] - mn), p = ex2f(s - mn);
+            z[h] = fmaf(z[h], corr, p);
+            d[h] = fmaf(d[h], corr, p * us[j][h]);
+            m[h] = mn;
+          }
+        }
+      }
+    }
+    if (has) {
+      float acc = bfv;
+      if (id != 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc += z[h] > 0.f ? d[h] / z[h] : 0.f;
+        if (a.residual_ca) {
+          acc += __ldg(a.tw + id);
+          for (int k = 0; k < a.C; ++k) acc = fmaf(__ldg(a.mcw + k), cv[k], acc);
+        }
+      }
+      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + __expf(-acc));
+    }
+  }
+}
+
+// dot decoder (src/carca.py:362): y = sigmoid(<p[L-1], e_t>), e_t = T[id] + Mc c_t (0 for a padding candidate)
+template <int D>
+__global__ void __launch_bounds__(128) rows_decode_dot_kernel(const DecodeArgs a) {
+  __shared__ __align__(16) float pl[D];
+  __shared__ float pmc[8];
+  const int n_slices = (a.T + 127) / 128;
+  for (long long item = blockIdx.x; item < (long long)a.B * n_slices; item += gridDim.x) {
+    const int u = (int)(item / n_slices), t = (int)(item % n_slices) * 128 + threadIdx.x;
+    const int2 sg = a.useg[u];
+    const long long last = (long long)sg.x + sg.y - 1;     // position L-1 is always the segment's last row
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += 128) pl[i] = a.PE[last * D + i];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float s = 0.f;
+      if (threadIdx.x < a.C)
+        for (int i = 0; i < D; ++i) s = fmaf(pl[i], a.Mc[i * 8 + threadIdx.x], s);
+      pmc[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (t < a.T) {
+      const int id = a.cat_lo > 0 ? a.cat_lo + t : __ldg(a.o_x + (long long)u * a.T + t);
+      float acc = 0.f;
+      if (id != 0) {
+        const uint4* tp = reinterpret_cast<const uint4*>(a.Tb + (long long)id * D);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < D / 8; ++i) {
+          float e8[8];
+          unpack8(__ldg(tp + i), e8);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            s0 = fmaf(pl[8 * i + e], e8[e], s0);
+            s1 = fmaf(pl[8 * i + e + 1], e8[e + 1], s1);
+          }
+        }
+        acc = s0 + s1;
+        const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
+        for (int k = 0; k < a.C; ++k) acc = fmaf(pmc[k], __ldg(c + k), acc);
+      }
+      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + __expf(-acc));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- plan preparation
+// fp32 [n, D] -> bf16
+__global__ void __launch_bounds__(256) to_bf16_kernel(bf16* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+// W [N = D out][K = D in] fp32 (nn.Linear / Conv1d k=1 layout) -> B operand [K/8][N][8] bf16
+__global__ void __launch_bounds__(256) pack_weight_bf16_kernel(bf16* __restrict__ dst, const float* __restrict__ W, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * D) return;
+  const int n = i / D, k = i % D;
+  dst[((long long)(k / 8) * D + n) * 8 + (k % 8)] = __float2bfloat16(W[i]);
+}
+
+}  // namespace rows
+}  // namespace carca
+#endif  // CARCA_EMU

@@ -134,7 +134,7 @@ def weights_epoch() -> int:
 
 
 class _Entry:
-    __slots__ = ("epoch", "tensors", "key", "plan", "status", "m", "keep", "n_ctx")
+    __slots__ = ("epoch", "tensors", "key", "plan", "status", "m", "keep", "n_ctx", "rows", "rows_spare")
 
 
 def _tensors_of(model) -> list:
@@ -179,11 +179,13 @@ def eval_plan(model, table: ItemAttrTable, n_ctx: int):
     scratch = torch.empty((emb.items_embed.weight.shape[0], g), dtype=torch.float32, device=dev)
     src = _attr_source(table, None)
     N.call("carca_eval_prepare", N.f32p(plan), N.f32p(scratch), C.byref(m), C.byref(src), N.stream())
+    old = _plans.get(model)
     ent = _Entry()
+    ent.rows = None                                  # bf16 plan (rows_plan), built on first use
+    ent.rows_spare = None if (old is None or reuse is None) else (old.rows if old.rows is not None else old.rows_spare)
     ent.epoch, ent.tensors, ent.key, ent.n_ctx = _struct_epoch[0], tensors, key, n_ctx
     ent.plan = plan
-    ent.status = _plans[model].status if reuse is not None and plan is reuse else \
-        torch.zeros(1, dtype=torch.int32, device=dev)
+    ent.status = old.status if reuse is not None and plan is reuse else torch.zeros(1, dtype=torch.int32, device=dev)
     ent.m, ent.keep = _model_params(model, table, None, n_ctx)     # the forward calls' argument block
     _plans[model] = ent
     return ent
@@ -269,4 +271,96 @@ def forward_catalog(model, profile, ctx_user: Tensor, item_lo: int, n_cand: int,
     N.call("carca_eval_forward_catalog", N.f32p(y), n_cand, 0, N.f32p(plan), C.byref(m), N.i32p(p_x), N.f32p(p_c),
            N.f32p(ctx_user), int(item_lo), int(n_cand), B, L, VARIANT if variant is None else int(variant),
            N.i32p(status), _scratch(B, p_x.device).data_ptr(), N.stream())
+    return y
+
+
+# ------------------------------------------------------------------------------- bf16 packed-rows pipeline
+ROWS_WIDTHS, ROWS_HEAD_WIDTHS, ROWS_MAX_L = (64, 256), (32, 64), 256
+
+
+def rows_supported(model, seq_len: int, n_ctx: int) -> bool:
+    """Shape range of the bf16 pipeline (csrc/rows_bf16.cuh): d in {64, 256}, head width 32 or 64, L <= 256 with any
+    number of valid positions per user, stock blocks, cross-attention or dot-product decoder."""
+    from . import carca as M
+
+    emb, dec = model.embeds, model.decoder
+    if not isinstance(emb, M.AllEmbedding) or not hasattr(emb.enc, "table"):
+        return False
+    blocks = list(model.encoder)
+    if not blocks or len(blocks) > MAX_BLOCKS or not all(isinstance(b, M.SelfAttentionBlock) for b in blocks):
+        return False
+    H = blocks[0].attn.H
+    if any(b.attn.H != H or bool(b.residual) != bool(blocks[0].residual) for b in blocks):
+        return False
+    if isinstance(dec, M.CrossAttentionBlock):
+        if dec.attn.H != H:
+            return False
+    elif not isinstance(dec, M.DotProduct):
+        return False
+    d = emb.d
+    return (d in ROWS_WIDTHS and d % H == 0 and d // H in ROWS_HEAD_WIDTHS and n_ctx <= MAX_CTX
+            and seq_len <= ROWS_MAX_L and N.is_device_tensor(emb.items_embed.weight))
+
+
+def rows_plan(model, table: ItemAttrTable, n_ctx: int):
+    """(entry, bf16 plan buffer) for the model's current weights: the fp32 plan's folded tables converted / folded
+    further for the bf16 pipeline (carca_rows_prepare).  Rebuilt with the fp32 plan, into the same buffer."""
+    ent = eval_plan(model, table, n_ctx)
+    if ent.rows is None:
+        nbytes = int(N.lib().carca_rows_plan_bytes(C.byref(ent.m)))
+        dev = ent.plan.device
+        buf = ent.rows_spare
+        if buf is None or buf.numel() != nbytes or buf.device != dev:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        emb = model.embeds
+        tmp = torch.empty((emb.items_embed.weight.shape[0], emb.d), dtype=torch.float32, device=dev)
+        N.call("carca_rows_prepare", buf.data_ptr(), N.f32p(tmp), N.f32p(ent.plan), C.byref(ent.m), N.stream())
+        ent.rows, ent.rows_spare = buf, None
+    return ent
+
+
+_rows_scratch_cache: dict = {}
+
+
+def _rows_scratch(ent, B: int, L: int, device) -> Tensor:
+    key = (str(device), int(B), int(L), int(ent.m.embed.d), int(ent.m.n_heads))
+    buf = _rows_scratch_cache.get(key)
+    if buf is None:
+        if len(_rows_scratch_cache) > 6:
+            _rows_scratch_cache.clear()
+        nbytes = int(N.lib().carca_rows_scratch_bytes(C.byref(ent.m), int(B), int(L)))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _rows_scratch_cache[key] = buf
+    return buf
+
+
+def forward_rows(model, profile, targets: Sequence, cat_lo: int = 0, n_cand: int = 0,
+                 ctx_user: Optional[Tensor] = None) -> Tensor:
+    """CARCA.forward in eval mode (src/carca.py:411-431) through the bf16 packed-rows pipeline -> [B, sum(T)].
+    With cat_lo > 0: catalog mode, scores of items [cat_lo, cat_lo + n_cand) with one context row per user."""
+    p_x, p_a, p_c = profile
+    table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
+    N.require_device(p_x, p_c)
+    p_x, p_c = as_ids(p_x), as_f32(p_c)
+    B, L = p_x.shape
+    n_ctx = p_c.shape[-1]
+    per_user_ctx = False
+    if cat_lo > 0:
+        o_x, o_c, per_user_ctx, T = None, as_f32(ctx_user), True, int(n_cand)
+    elif len(targets) == 1:
+        o_x, o_c = as_ids(targets[0][0]), targets[0][2]
+        if o_c.dim() == 3 and o_c.stride(2) == 1 and (o_c.shape[1] == 1 or o_c.stride(1) == 0):
+            o_c, per_user_ctx = as_f32(o_c[:, 0, :]), True      # expanded view of one context row per user
+        else:
+            o_c = as_f32(o_c)
+        T = o_x.shape[1]
+    else:
+        o_x = torch.cat([as_ids(t[0]) for t in targets], dim=1)
+        o_c = torch.cat([as_f32(t[2]) for t in targets], dim=1)
+        T = o_x.shape[1]
+    ent = rows_plan(model, table, n_ctx)
+    y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
+    N.call("carca_rows_eval_forward", N.f32p(y), T, 0, ent.rows.data_ptr(), C.byref(ent.m), N.i32p(p_x), N.f32p(p_c),
+           None if o_x is None else N.i32p(o_x), N.f32p(o_c), B, L, T, int(per_user_ctx), int(cat_lo),
+           N.i32p(ent.status), _rows_scratch(ent, B, L, p_x.device).data_ptr(), N.stream())
     return y

@@ -460,6 +460,30 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
  * (src/carca.py:246-251) — so the encoder runs on valid rows only.                              */
 int64_t carca_eval_scratch_bytes(int B);
 
+/* ------------------------------------------------------------------ bf16 inference over packed rows */
+/* CARCA.forward in eval mode (src/carca.py:411-431) in bf16 with fp32 accumulation, fp32 softmax and fp32 LayerNorm
+ * (BASELINE configs[1] "bf16/fp32", configs[2] Men-shaped d = 256): a pipeline of kernels over the batch's PACKED
+ * valid profile rows — tcgen05 kind::f16 GEMMs with the weight matrix resident in shared memory, A tiles streamed by
+ * cp.async.bulk, double-buffered TMEM accumulators and fused bias / LeakyReLU / residual / LayerNorm epilogues
+ * (csrc/rows_bf16.cuh).  Supported: d in {64, 256}, head width 32 or 64, C <= 8, 1..8 blocks, L <= 256 with ANY number
+ * of valid positions per user, both decoders.  Tolerance contract: scores within 1e-2 of the fp32 reference.
+ *
+ * carca_rows_plan_bytes / carca_rows_prepare: bf16 plan derived from the fp32 plan of carca_eval_prepare (folded item
+ * table T and context map Mc) and the model parameters: bf16 T, packed bf16 projection weights and, for the
+ * cross-attention decoder, the folded candidate tables TQ = WQ T + bq (bf16), tw = <T, wf>, McQ = WQ Mc, mcw = wf Mc.
+ * tmp: [n_items, d] floats of scratch.  Call again whenever the weights change.                                    */
+int64_t carca_rows_plan_bytes(const carca_model_params* m);
+int carca_rows_prepare(void* plan, float* tmp, const float* plan_f32, const carca_model_params* m, void* stream);
+/* Bytes of device scratch for a batch of B users with windows of L positions (worst case: every position valid). */
+int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L);
+/* y[b, col0 + t] = CARCA.forward(profile, [targets]) in eval mode.  p_x [B,L], p_c [B,L,C], o_x [B,T],
+ * o_c [B,T,C] (ctx_per_user != 0: [B,C], one context row per user as src/data.py:185 builds).  cat_lo > 0: catalog
+ * mode, candidate t is item cat_lo + t and o_x is not read.  status (device int32[1]): bit 1 is set if an mbarrier
+ * wait of the GEMM pipeline timed out (results invalid).                                                            */
+int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const carca_model_params* m,
+                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
+                            int T, int ctx_per_user, int cat_lo, int32_t* status, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ full-catalog scoring */
 /* Scores every item of the contiguous id range [item_lo, item_lo + n_cand) (an item-table shard)
  * for every user: y[b, col0 + j] = CARCA.forward(profile_b, [(item_lo + j, ., ctx_user_b)]) in eval
