@@ -142,9 +142,10 @@ SIGNATURES = {
     "carca_eval_scratch_bytes": [i32],
     "carca_eval_forward_catalog": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
     "carca_rows_plan_bytes": [P(ModelParams)],
-    "carca_rows_prepare": [vp, vp, vp, P(ModelParams), vp],
+    "carca_rows_prepare": [vp, vp, P(ModelParams), vp],
     "carca_rows_scratch_bytes": [P(ModelParams), i32, i32],
-    "carca_rows_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+    "carca_rows_eval_forward": [vp, i64, i32, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp,
+                                vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
@@ -204,6 +205,11 @@ def require_device(*tensors: Optional[torch.Tensor]) -> None:
 
 def is_device_tensor(t: torch.Tensor) -> bool:
     return t.is_cuda
+
+
+def is_emulated() -> bool:
+    """True only under the development emulator fixture of the CPU tests (which has no tcgen05 pipeline)."""
+    return False
 
 
 def stream() -> int:

@@ -440,37 +440,46 @@ class CARCA(Model):
 
     use_fused_eval = True   # class default; set False on an instance to force the per-op path
 
-    def _fused_eval_applies(self, profile, targets) -> bool:
-        """Inference (eval mode, no autograd), device-resident attributes, shape in the fused range."""
+    def _fused_eval_mode(self, profile, targets) -> Optional[str]:
+        """Which whole-model inference path serves this call (eval mode, no autograd, device-resident attributes):
+        "tc"   — the one-kernel fp32 tensor-core forward (d = 64, windows of at most one 64-row bin: L <= 64),
+        "rows_fp32" — the packed-rows pipeline with 3xTF32 GEMMs (fp32 contract; any number of valid positions per
+                 user, L <= 256, d in {32, 64, 128, 256}): longer windows and the widths the fused kernel does not cover,
+        "rows_bf16" — the same pipeline in bf16 (eval_dtype == "bf16"),
+        None   — the per-op kernels.  Nothing is decided by reading the device: no host sync on this path."""
         if self.training or torch.is_grad_enabled() or not self.use_fused_eval or not targets:
-            return False
+            return None
         emb = self.embeds
         if not isinstance(emb, AllEmbedding):
-            return False
+            return None
         for a in [profile[1]] + [t[1] for t in targets]:
             if isinstance(a, Tensor) or (a is None and emb.attr_table is None):
-                return False
+                return None
         if any(isinstance(t[1], ItemAttrTable) and t[1] is not (profile[1] or emb.attr_table) for t in targets):
-            return False
+            return None
         from . import fused
         from . import _native
         if not _native.is_device_tensor(profile[0]):
-            return False
+            return None
+        L, n_ctx = profile[0].shape[1], profile[2].shape[-1]
         if self.eval_dtype == "bf16":
-            # bf16 packed-rows pipeline: no per-user row limit, nothing to check on the host
-            if not fused.rows_supported(self, profile[0].shape[1], profile[2].shape[-1]):
+            if not fused.rows_supported(self, L, n_ctx, "bf16"):
                 raise RuntimeError("CARCA.eval_dtype == 'bf16' needs AllEmbedding with a device attribute table, stock "
                                    "blocks / decoder, d in {64, 256}, head width 32 or 64, C <= 8, L <= 256")
-            return True
-        if not fused.supported(self, profile[0].shape[1], profile[2].shape[-1]):
-            return False
-        # sequences longer than one 64-row bin: only when every user's valid positions fit in a bin (one device
-        # reduction + host read; GraphedEvalStep checks the batch itself before it replays a captured step)
-        if self._fits_eval_override is not None:
-            return self._fits_eval_override
-        if profile[0].shape[1] > fused.BIN_ROWS and profile[0].is_cuda and torch.cuda.is_current_stream_capturing():
-            return False
-        return fused.fits_packed(profile[0])
+            return "rows_bf16"
+        if self.force_eval_path is not None:            # tests / benchmarks: "tc", "rows_fp32"
+            return self.force_eval_path
+        if L <= fused.BIN_ROWS and fused.supported(self, L, n_ctx):
+            return "tc"
+        if self.use_rows_eval and fused.rows_supported(self, L, n_ctx, "fp32") and not _native.is_emulated():
+            return "rows_fp32"
+        return None
+
+    def _fused_eval_applies(self, profile, targets) -> bool:
+        return self._fused_eval_mode(profile, targets) is not None
+
+    force_eval_path: Optional[str] = None
+    use_rows_eval = True    # class default; set False on an instance to keep shapes outside the fused kernel per-op
 
     _fits_eval_override: Optional[bool] = None
 
@@ -578,11 +587,12 @@ class CARCA(Model):
 
     def forward(self, profile: Tuple[Tensor, Tensor, Tensor],
                 targets: List[Tuple[Tensor, Tensor, Tensor]]) -> Tensor:
-        if self._fused_eval_applies(profile, targets):
+        mode = self._fused_eval_mode(profile, targets)
+        if mode is not None:
             from . import fused
-            if self.eval_dtype == "bf16":
-                return fused.forward_rows(self, profile, targets)
-            return fused.forward(self, profile, targets)
+            if mode == "tc":
+                return fused.forward(self, profile, targets)
+            return fused.forward_rows(self, profile, targets, precision=mode[5:])
         if self._fused_train_applies(profile, targets):
             return self._forward_fused_train(profile, targets)
         with ops.forward_seed():

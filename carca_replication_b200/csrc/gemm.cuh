@@ -34,6 +34,8 @@ struct GemmArgs {
   int r_mod;
   const float* row_mask;  // [M] or null; multiplies the final value
   int k_per_split;        // split-K chunk (multiple of BK); gridDim.z chunks
+  const int* m_dev;       // optional device word: only the first min(M, *m_dev) rows exist (row counts known on the
+                          //   device only, e.g. the packed rows of a batch); the grid is sized for M, tiles past it exit
 };
 
 template <int BM, int BN, int TM, int TN>
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM;
+  const int gM = g.m_dev ? min(g.M, *g.m_dev) : g.M;
+  if (m0 >= gM) return;
   const int n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
       if (g.transA) { k = e / BM; m = e % BM; } else { m = e / BK; k = e % BK; }
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < g.M && gk < k_end) {
+      if (gm < gM && gk < k_end) {
         if (g.transA) {
           v = g.A[(long long)gk * g.lda + gm];
         } else {
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int gm = m0 + ty * TM + i;
-    if (gm >= g.M) continue;
+    if (gm >= gM) continue;
     const float rm = g.row_mask ? g.row_mask[gm] : 1.0f;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {

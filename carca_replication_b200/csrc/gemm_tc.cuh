@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
   GemmTcSmem<BN>& s = *reinterpret_cast<GemmTcSmem<BN>*>(raw);
   const int tid = threadIdx.x, w = tid / 32, lane = tid % 32;
   const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * BN;
+  const int gM = g.m_dev ? min(g.M, *g.m_dev) : g.M;
+  if (m0 >= gM) return;   // (whole CTA, before any barrier / TMEM allocation)
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
   const int nk = k_end > k_begin ? (k_end - k_begin + GT_BK - 1) / GT_BK : 0;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
   const bool a_k = !g.transA, b_k = g.transB != 0;
   float4 ra[GT_BM / 32], rb[BN / 32];
   if (nk > 0) {
-    fetch_tile<GT_BM>(ra, g.A, g.lda, a_k, a_k ? g.a_rows : nullptr, m0, g.M, k_begin, k_end, vec_a);
+    fetch_tile<GT_BM>(ra, g.A, g.lda, a_k, a_k ? g.a_rows : nullptr, m0, gM, k_begin, k_end, vec_a);
     fetch_tile<BN>(rb, g.B, g.ldb, b_k, b_k ? nullptr : g.b_rows, n0, g.N, k_begin, k_end, vec_b);
   }
   bool ok = true;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
     umma::fence_after_sync();
     if (kt + 1 < nk) {   // next step's global loads fly while this step's MMAs run
       const int k0 = k_begin + (kt + 1) * GT_BK;
-      fetch_tile<GT_BM>(ra, g.A, g.lda, a_k, a_k ? g.a_rows : nullptr, m0, g.M, k0, k_end, vec_a);
+      fetch_tile<GT_BM>(ra, g.A, g.lda, a_k, a_k ? g.a_rows : nullptr, m0, gM, k0, k_end, vec_a);
       fetch_tile<BN>(rb, g.B, g.ldb, b_k, b_k ? nullptr : g.b_rows, n0, g.N, k0, k_end, vec_b);
     }
     if (issuer_warp) {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
     for (int r0 = w * RPW; r0 < GT_BM; r0 += 8 * RPW) {
       const int r = r0 + lane / Q, jq = lane % Q;
       const int gm = m0 + r, gn = n0 + pass * BNC + 4 * jq;
-      if (gm >= g.M || gn >= g.N) continue;
+      if (gm >= gM || gn >= g.N) continue;
       const float4 t = ct[r * Q + (jq ^ (r % 32 % Q))];
       float x[4] = {t.x, t.y, t.z, t.w};
       float* dst = g.C + (long long)gm * g.ldc + gn;

@@ -21,12 +21,12 @@ using namespace carca;
 // the tcgen05 pipeline has no CPU emulation: the development emulator (tools/emu) only covers the plain-CUDA kernels
 extern "C" {
 int64_t carca_rows_plan_bytes(const carca_model_params*) { return 0; }
-int carca_rows_prepare(void*, float*, const float*, const carca_model_params*, void*) {
+int carca_rows_prepare(void*, const float*, const carca_model_params*, void*) {
   return fail(-5, "rows pipeline: not available under the CPU emulator");
 }
 int64_t carca_rows_scratch_bytes(const carca_model_params*, int, int) { return 0; }
-int carca_rows_eval_forward(float*, int64_t, int, const void*, const carca_model_params*, const int32_t*, const float*,
-                            const int32_t*, const float*, int, int, int, int, int, int32_t*, void*, void*) {
+int carca_rows_eval_forward(float*, int64_t, int, const void*, const float*, const carca_model_params*, const int32_t*,
+                            const float*, const int32_t*, const float*, int, int, int, int, int, int, int32_t*, void*, void*) {
   return fail(-5, "rows pipeline: not available under the CPU emulator");
 }
 }
@@ -39,27 +39,26 @@ inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
 // byte offsets of the bf16 plan
 struct RowsPlan {
-  long long tb, mc, w, dw, tqb, tw, mcq, mcw, total;
+  long long mc, w, dw, tq, tw, mcq, mcw, total;
 };
 RowsPlan rows_plan(const carca_model_params* m) {
   RowsPlan p;
   const long long d = m->embed.d, n = m->embed.n_items;
   const bool ca = m->decoder_kind == 1;
-  p.tb = 0;
-  p.mc = align256(p.tb + n * d * 2);
+  p.mc = 0;
   p.w = align256(p.mc + d * 8 * 4);
   p.dw = align256(p.w + (long long)m->n_blocks * 5 * d * d * 2);
-  p.tqb = align256(p.dw + (ca ? 2 * d * d * 2 : 0));
-  p.tw = align256(p.tqb + (ca ? n * d * 2 : 0));
+  p.tq = align256(p.dw + (ca ? 2 * d * d * 2 : 0));
+  p.tw = align256(p.tq + (ca ? n * d * 4 : 0));
   p.mcq = align256(p.tw + (ca ? n * 4 : 0));
   p.mcw = align256(p.mcq + (ca ? d * 8 * 4 : 0));
   p.total = align256(p.mcw + (ca ? 8 * 4 : 0));
   return p;
 }
 
-// byte offsets of the per-call scratch
+// byte offsets of the per-call scratch: seven [Rp, d] fp32-sized slots shared by both flavours
 struct RowsScratch {
-  long long counters, row_src, row_seg, useg, XA, QA, S2A, F1A, QN, S2, Qb, Kb, Vb, U, KM, total, Rp;
+  long long counters, row_src, row_seg, useg, slot[7], U, KM, total, Rp;
 };
 RowsScratch rows_scratch(const carca_model_params* m, int B, int L) {
   RowsScratch s;
@@ -70,25 +69,28 @@ RowsScratch rows_scratch(const carca_model_params* m, int B, int L) {
   s.row_src = 256;
   s.row_seg = align256(s.row_src + Rp * 4);
   s.useg = align256(s.row_seg + Rp * 4);
-  s.XA = align256(s.useg + (long long)B * 8);
-  s.QA = align256(s.XA + Rp * d * 2);
-  s.S2A = align256(s.QA + Rp * d * 2);
-  s.F1A = align256(s.S2A + Rp * d * 2);
-  s.QN = align256(s.F1A + Rp * d * 2);
-  s.S2 = align256(s.QN + Rp * d * 4);
-  s.Qb = align256(s.S2 + Rp * d * 4);
-  s.Kb = align256(s.Qb + Rp * d * 2);
-  s.Vb = align256(s.Kb + Rp * d * 2);
-  s.U = align256(s.Vb + Rp * d * 2);
+  long long off = align256(s.useg + (long long)B * 8);
+  for (int i = 0; i < 7; ++i) {
+    s.slot[i] = off;
+    off = align256(off + Rp * d * 4);
+  }
+  s.U = off;
   s.KM = align256(s.U + Rp * H * 4);
   s.total = align256(s.KM + Rp * H * 8 * 4);
   return s;
 }
 
+// bf16 flavour: tcgen05 kind::f16 GEMMs with the weight matrix resident in shared memory
 bool rows_shape_ok(const carca_model_params* m) {
   const int d = m->embed.d, H = m->n_heads;
-  return (d == 64 || d == 256) && (H == 1 || H == 2 || H == 4 || H == 8) && (d / H == 32 || d / H == 64) && m->embed.n_ctx <= 8 &&
+  return (d == 64 || d == 256) && H >= 1 && d % H == 0 && (d / H == 32 || d / H == 64) && m->embed.n_ctx <= 8 &&
          m->n_blocks >= 1 && m->n_blocks <= 8;
+}
+// fp32 flavour: the general 3xTF32 tcgen05 GEMM (gemm_tc.cuh) over the packed rows
+bool rows_shape_ok_f32(const carca_model_params* m) {
+  const int d = m->embed.d, H = m->n_heads;
+  return (d == 32 || d == 64 || d == 128 || d == 256) && H >= 1 && d % H == 0 &&
+         (d / H == 16 || d / H == 32 || d / H == 64) && m->embed.n_ctx <= 8 && m->n_blocks >= 1 && m->n_blocks <= 8;
 }
 
 template <int D>
@@ -108,7 +110,7 @@ int launch_gemm_rows(const rows::GemmArgs& g, cudaStream_t st) {
 }
 
 template <int D, int H>
-int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const carca_model_params* m,
+int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
               const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
               int ctx_per_user, int cat_lo, int32_t* status, unsigned char* scr, cudaStream_t st) {
   const RowsPlan pl = rows_plan(m);
@@ -118,18 +120,18 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
   int* row_seg = reinterpret_cast<int*>(scr + sc.row_seg);
   int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
-  bf16* XA = reinterpret_cast<bf16*>(scr + sc.XA);
-  bf16* QA = reinterpret_cast<bf16*>(scr + sc.QA);
-  bf16* S2A = reinterpret_cast<bf16*>(scr + sc.S2A);
-  bf16* F1A = reinterpret_cast<bf16*>(scr + sc.F1A);
-  float* QN = reinterpret_cast<float*>(scr + sc.QN);
-  float* S2 = reinterpret_cast<float*>(scr + sc.S2);
-  bf16* Qb = reinterpret_cast<bf16*>(scr + sc.Qb);
-  bf16* Kb = reinterpret_cast<bf16*>(scr + sc.Kb);
-  bf16* Vb = reinterpret_cast<bf16*>(scr + sc.Vb);
+  const long long half = sc.Rp * D * 2;
+  bf16* XA = reinterpret_cast<bf16*>(scr + sc.slot[0]);
+  bf16* QA = reinterpret_cast<bf16*>(scr + sc.slot[0] + half);
+  bf16* S2A = reinterpret_cast<bf16*>(scr + sc.slot[1]);
+  bf16* F1A = reinterpret_cast<bf16*>(scr + sc.slot[1] + half);
+  float* QN = reinterpret_cast<float*>(scr + sc.slot[2]);
+  float* S2 = reinterpret_cast<float*>(scr + sc.slot[3]);
+  bf16* Qb = reinterpret_cast<bf16*>(scr + sc.slot[4]);
+  bf16* Kb = reinterpret_cast<bf16*>(scr + sc.slot[4] + half);
+  bf16* Vb = reinterpret_cast<bf16*>(scr + sc.slot[5]);
   float* U = reinterpret_cast<float*>(scr + sc.U);
   float* KM = reinterpret_cast<float*>(scr + sc.KM);
-  const bf16* Tb = reinterpret_cast<const bf16*>(plan + pl.tb);
   const float* Mc = reinterpret_cast<const float*>(plan + pl.mc);
   const bf16* W = reinterpret_cast<const bf16*>(plan + pl.w);
   const long long wsz = (long long)D * D;
@@ -143,10 +145,10 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   const int row_grid = 148 * 4;
   {
     rows::EmbedArgs e;
-    e.Tb = Tb; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows;
+    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows;
     e.ln_g = m->blocks[0].ln1_g; e.ln_b = m->blocks[0].ln1_b;
     e.XA = XA; e.QA = QA; e.QN = QN; e.L = L; e.C = C;
-    auto k = rows::rows_embed_ln_kernel<D>;
+    auto k = rows::rows_embed_ln_kernel<D, false>;
     CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, e);
     TRY(check_launch("rows_embed_ln"));
   }
@@ -166,7 +168,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       rows::AttnRowsArgs t;
       t.Q = Qb; t.K = Kb; t.V = Vb; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
       t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.S2A = S2A; t.residual = m->residual_sa;
-      auto k = rows::rows_attn_ln_kernel<D, H>;
+      auto k = rows::rows_attn_ln_kernel<D, H, false>;
       CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
       TRY(check_launch("rows_attn_ln"));
     }
@@ -208,20 +210,127 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     memset(&g, 0, sizeof(g));
     g.n_jobs = 2; g.n_rows = n_rows; g.H = H; g.status = status;
     g.job[0].A = QA; g.job[0].W = dw;       g.job[0].bias = m->cross.bk; g.job[0].epi = rows::EPI_KDEC;
-    g.job[0].out_rows = Kb; g.job[0].McQ = reinterpret_cast<const float*>(plan + pl.mcq); g.job[0].KM = KM;
+    g.job[0].out_f32 = S2; g.job[0].McQ = reinterpret_cast<const float*>(plan + pl.mcq); g.job[0].KM = KM;
     g.job[1].A = QA; g.job[1].W = dw + wsz; g.job[1].bias = m->cross.bv; g.job[1].epi = rows::EPI_VDOT;
     g.job[1].wf = m->cross.wf; g.job[1].U = U;
     TRY(launch_gemm_rows<D>(g, st));
-    d.Kd = Kb; d.U = U; d.KM = KM;
-    d.TQb = reinterpret_cast<const bf16*>(plan + pl.tqb);
+    d.Kd = S2; d.U = U; d.KM = KM;      // (the S2 buffer is free after the last block: it holds the fp32 keys)
+    (void)Kb;
+    d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
     d.tw = reinterpret_cast<const float*>(plan + pl.tw);
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
     d.dbf = m->cross.bf;
-    auto k = rows::rows_decode_ca_kernel<D, H>;
+    auto k = rows::rows_decode_ca_kernel<D, H, false>;
     CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
     TRY(check_launch("rows_decode_ca"));
   } else {
-    d.PE = QN; d.Tb = Tb; d.Mc = Mc;
+    d.PE = QN; d.Tf = Tf; d.Mc = Mc;
+    auto k = rows::rows_decode_dot_kernel<D>;
+    CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
+    TRY(check_launch("rows_decode_dot"));
+  }
+  return 0;
+}
+
+// fp32 flavour of the same pipeline: fp32 rows everywhere, every projection through the general 3xTF32 tcgen05 GEMM
+// (gemm_tc.cuh) with the row count read on the device (GemmArgs::m_dev), LayerNorms as row kernels.  No per-user row
+// limit: this is the fp32 path for windows longer than one 64-row bin and for widths the fused kernels do not cover.
+int gemm_rows_f32(float* C, const float* A, const float* W, const float* bias, int Mcap, int d, const int* n_rows, int act,
+                  const float* R, cudaStream_t st) {
+  GemmArgs g = gemm_defaults(A, W, C, Mcap, d, d);
+  g.bias = bias;
+  g.act = act;
+  g.R = R;
+  g.ldr = d;
+  g.m_dev = n_rows;
+  return launch_gemm(g, st);
+}
+
+template <int D, int H>
+int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
+                  const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
+                  int ctx_per_user, int cat_lo, unsigned char* scr, cudaStream_t st) {
+  const RowsPlan pl = rows_plan(m);
+  const RowsScratch sc = rows_scratch(m, B, L);
+  const int C = m->embed.n_ctx;
+  int* n_rows = reinterpret_cast<int*>(scr + sc.counters);
+  int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
+  int* row_seg = reinterpret_cast<int*>(scr + sc.row_seg);
+  int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
+  float* Xf = reinterpret_cast<float*>(scr + sc.slot[0]);
+  float* QN = reinterpret_cast<float*>(scr + sc.slot[1]);
+  float* S2 = reinterpret_cast<float*>(scr + sc.slot[2]);
+  float* Qf = reinterpret_cast<float*>(scr + sc.slot[3]);
+  float* Kf = reinterpret_cast<float*>(scr + sc.slot[4]);
+  float* Vf = reinterpret_cast<float*>(scr + sc.slot[5]);
+  float* F1 = reinterpret_cast<float*>(scr + sc.slot[6]);
+  const float* Mc = reinterpret_cast<const float*>(plan + pl.mc);
+  const int Mcap = (int)min((long long)B * L, (long long)INT32_MAX);
+
+  cudaMemsetAsync(n_rows, 0, 256, st);
+  {
+    auto k = rows::rows_pack_kernel;
+    CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L);
+    TRY(check_launch("rows_pack"));
+  }
+  const int row_grid = 148 * 4;
+  {
+    rows::EmbedArgs e;
+    memset(&e, 0, sizeof(e));
+    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows;
+    e.ln_g = m->blocks[0].ln1_g; e.ln_b = m->blocks[0].ln1_b;
+    e.Xf = Xf; e.QN = QN; e.L = L; e.C = C;
+    auto k = rows::rows_embed_ln_kernel<D, true>;
+    CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, e);
+    TRY(check_launch("rows_embed_ln"));
+  }
+  for (int b = 0; b < m->n_blocks; ++b) {
+    const carca_block_params& bp = m->blocks[b];
+    TRY(gemm_rows_f32(Qf, QN, bp.wq, bp.bq, Mcap, D, n_rows, 0, nullptr, st));   // Q from LN1(x), K / V from x (:238-240)
+    TRY(gemm_rows_f32(Kf, Xf, bp.wk, bp.bk, Mcap, D, n_rows, 0, nullptr, st));
+    TRY(gemm_rows_f32(Vf, Xf, bp.wv, bp.bv, Mcap, D, n_rows, 0, nullptr, st));
+    {
+      rows::AttnRowsArgs t;
+      memset(&t, 0, sizeof(t));
+      t.Q = Qf; t.K = Kf; t.V = Vf; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
+      t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.residual = m->residual_sa;
+      auto k = rows::rows_attn_ln_kernel<D, H, true>;
+      CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
+      TRY(check_launch("rows_attn_ln"));
+    }
+    TRY(gemm_rows_f32(F1, S2, bp.w1, bp.b1, Mcap, D, n_rows, 1, nullptr, st));                              // :307-308
+    TRY(gemm_rows_f32(Xf, F1, bp.w2, bp.b2, Mcap, D, n_rows, 0, m->residual_sa ? S2 : nullptr, st));       // :311, :316
+    {
+      const bool last = b + 1 == m->n_blocks;
+      auto k = rows::rows_ln_kernel<D>;
+      CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, QN, (const float*)Xf, last ? m->norm_g : m->blocks[b + 1].ln1_g,
+                   last ? m->norm_b : m->blocks[b + 1].ln1_b, (const int*)n_rows);
+      TRY(check_launch("rows_ln"));
+    }
+  }
+  rows::DecodeArgs d;
+  memset(&d, 0, sizeof(d));
+  d.useg = useg; d.row_src = row_src; d.o_x = o_x; d.o_c = o_c;
+  d.oc_user = ctx_per_user ? C : (long long)T * C;
+  d.oc_tgt = ctx_per_user ? 0 : C;
+  d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.C = C; d.L = L; d.cat_lo = cat_lo;
+  d.residual_ca = m->residual_ca;
+  const long long items = (long long)B * ceil_div(T, 128);
+  const int dgrid = (int)min(items, 148ll * 16);
+  if (m->decoder_kind == 1) {
+    TRY(gemm_rows_f32(Kf, QN, m->cross.wk, m->cross.bk, Mcap, D, n_rows, 0, nullptr, st));
+    TRY(gemm_rows_f32(Vf, QN, m->cross.wv, m->cross.bv, Mcap, D, n_rows, 0, nullptr, st));
+    d.Kd = Kf; d.Vd = Vf; d.wf = m->cross.wf;
+    d.McQ = reinterpret_cast<const float*>(plan + pl.mcq);
+    d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
+    d.tw = reinterpret_cast<const float*>(plan + pl.tw);
+    d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
+    d.dbf = m->cross.bf;
+    auto k = rows::rows_decode_ca_kernel<D, H, true>;
+    CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
+    TRY(check_launch("rows_decode_ca"));
+  } else {
+    d.PE = QN; d.Tf = Tf; d.Mc = Mc;
     auto k = rows::rows_decode_dot_kernel<D>;
     CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
     TRY(check_launch("rows_decode_dot"));
@@ -235,10 +344,11 @@ extern "C" {
 
 int64_t carca_rows_plan_bytes(const carca_model_params* m) { return rows_plan(m).total; }
 
-int carca_rows_prepare(void* plan_v, float* tmp, const float* plan_f32, const carca_model_params* m, void* stream) {
+int carca_rows_prepare(void* plan_v, const float* plan_f32, const carca_model_params* m, void* stream) {
   cudaStream_t st = S(stream);
-  CARCA_REQUIRE(rows_shape_ok(m), "rows_prepare: needs d in {64, 256}, head width 32 or 64, C <= 8, 1..8 blocks "
-                                  "(got d=%d H=%d C=%d blocks=%d)", m->embed.d, m->n_heads, m->embed.n_ctx, m->n_blocks);
+  CARCA_REQUIRE(rows_shape_ok_f32(m), "rows_prepare: needs d in {32, 64, 128, 256}, head width 16 / 32 / 64, C <= 8, "
+                                      "1..8 blocks (got d=%d H=%d C=%d blocks=%d)", m->embed.d, m->n_heads, m->embed.n_ctx,
+                m->n_blocks);
   unsigned char* plan = reinterpret_cast<unsigned char*>(plan_v);
   const RowsPlan pl = rows_plan(m);
   const PlanLayout fl = plan_layout(m);
@@ -246,10 +356,6 @@ int carca_rows_prepare(void* plan_v, float* tmp, const float* plan_f32, const ca
   const long long n = m->embed.n_items;
   const float* T = plan_f32 + fl.tfold;
   const float* Mc = plan_f32 + fl.mc;
-  auto cvt = rows::to_bf16_kernel;
-  CARCA_LAUNCH(cvt, dim3((unsigned)ceil_div_ll(n * d, 1024)), dim3(256), 0, st, reinterpret_cast<bf16*>(plan + pl.tb), T,
-               n * d);
-  TRY(check_launch("to_bf16(T)"));
   cudaMemcpyAsync(plan + pl.mc, Mc, sizeof(float) * d * 8, cudaMemcpyDeviceToDevice, st);
   auto pk = rows::pack_weight_bf16_kernel;
   for (int b = 0; b < m->n_blocks; ++b) {
@@ -271,12 +377,9 @@ int carca_rows_prepare(void* plan_v, float* tmp, const float* plan_f32, const ca
     // candidate-side folds (exact re-associations of linear maps): TQ[i] = WQ T[i] + bq, tw[i] = <T[i], wf>,
     // McQ = WQ Mc, mcw = wf Mc   (src/carca.py:238 with :85-95 folded, :343-345)
     {
-      GemmArgs g = gemm_defaults(T, m->cross.wq, tmp, (int)n, d, d);
+      GemmArgs g = gemm_defaults(T, m->cross.wq, reinterpret_cast<float*>(plan + pl.tq), (int)n, d, d);
       g.bias = m->cross.bq;
       TRY(launch_gemm(g, st));
-      CARCA_LAUNCH(cvt, dim3((unsigned)ceil_div_ll(n * d, 1024)), dim3(256), 0, st,
-                   reinterpret_cast<bf16*>(plan + pl.tqb), tmp, n * d);
-      TRY(check_launch("to_bf16(TQ)"));
     }
     {
       GemmArgs g = gemm_defaults(T, m->cross.wf, reinterpret_cast<float*>(plan + pl.tw), (int)n, 1, d);
@@ -296,12 +399,19 @@ int carca_rows_prepare(void* plan_v, float* tmp, const float* plan_f32, const ca
 
 int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L) { return rows_scratch(m, B, L).total; }
 
-int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const carca_model_params* m,
-                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                            int T, int ctx_per_user, int cat_lo, int32_t* status, void* scratch, void* stream) {
-  CARCA_REQUIRE(rows_shape_ok(m), "rows_eval_forward: needs d in {64, 256}, head width 32 or 64, C <= 8, 1..8 "
-                                  "blocks (got d=%d H=%d C=%d blocks=%d)", m->embed.d, m->n_heads, m->embed.n_ctx,
-                m->n_blocks);
+int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const float* plan_f32,
+                            const carca_model_params* m, const int32_t* p_x, const float* p_c, const int32_t* o_x,
+                            const float* o_c, int B, int L, int T, int ctx_per_user, int cat_lo, int precision,
+                            int32_t* status, void* scratch, void* stream) {
+  CARCA_REQUIRE(precision == 0 || precision == 1, "rows_eval_forward: precision %d (0 = bf16, 1 = fp32)", precision);
+  if (precision == 0)
+    CARCA_REQUIRE(rows_shape_ok(m), "rows_eval_forward(bf16): needs d in {64, 256}, head width 32 or 64, C <= 8, 1..8 "
+                                    "blocks (got d=%d H=%d C=%d blocks=%d)", m->embed.d, m->n_heads, m->embed.n_ctx,
+                  m->n_blocks);
+  else
+    CARCA_REQUIRE(rows_shape_ok_f32(m), "rows_eval_forward(fp32): needs d in {32, 64, 128, 256}, head width 16 / 32 / 64, "
+                                        "C <= 8, 1..8 blocks (got d=%d H=%d C=%d blocks=%d)", m->embed.d, m->n_heads,
+                  m->embed.n_ctx, m->n_blocks);
   CARCA_REQUIRE(L >= 1 && L <= 256, "rows_eval_forward: L=%d outside 1..256", L);
   CARCA_REQUIRE(status != nullptr && scratch != nullptr, "rows_eval_forward: status and scratch are required");
   CARCA_REQUIRE((long long)B < (1ll << 23), "rows_eval_forward: at most 2^23 users per call");
@@ -312,11 +422,21 @@ int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, c
   unsigned char* scr = reinterpret_cast<unsigned char*>(scratch);
   cudaStream_t st = S(stream);
   const int d = m->embed.d, H = m->n_heads;
-#define ROWS_CASE(DD, HH)                                                                                          \
-  if (d == DD && H == HH)                                                                                          \
-    return forward_t<DD, HH>(y, ldy, col0, pl, m, p_x, p_c, o_x, o_c, B, L, T, ctx_per_user, cat_lo, status, scr, st);
-  ROWS_CASE(64, 1) ROWS_CASE(64, 2) ROWS_CASE(256, 4) ROWS_CASE(256, 8)
+  const float* Tf = plan_f32 + plan_layout(m).tfold;
+  if (precision == 0) {
+#define ROWS_CASE(DD, HH)                                                                                            \
+  if (d == DD && H == HH)                                                                                            \
+    return forward_t<DD, HH>(y, ldy, col0, pl, Tf, m, p_x, p_c, o_x, o_c, B, L, T, ctx_per_user, cat_lo, status, scr, st);
+    ROWS_CASE(64, 1) ROWS_CASE(64, 2) ROWS_CASE(256, 4) ROWS_CASE(256, 8)
 #undef ROWS_CASE
+  } else {
+#define ROWS_CASE(DD, HH)                                                                                            \
+  if (d == DD && H == HH)                                                                                            \
+    return forward_f32_t<DD, HH>(y, ldy, col0, pl, Tf, m, p_x, p_c, o_x, o_c, B, L, T, ctx_per_user, cat_lo, scr, st);
+    ROWS_CASE(32, 1) ROWS_CASE(32, 2) ROWS_CASE(64, 1) ROWS_CASE(64, 2) ROWS_CASE(64, 4) ROWS_CASE(128, 2)
+    ROWS_CASE(128, 4) ROWS_CASE(128, 8) ROWS_CASE(256, 4) ROWS_CASE(256, 8)
+#undef ROWS_CASE
+  }
   return fail(-4, "rows_eval_forward: unsupported (d, heads) = (%d, %d)", d, H);
 }
 

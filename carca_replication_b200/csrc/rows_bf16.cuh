@@ -109,19 +109,20 @@ __global__ void __launch_bounds__(256) rows_pack_kernel(int* __restrict__ row_sr
 
 // ---------------------------------------------------------------------------------------------- embedding + LN1
 struct EmbedArgs {
-  const bf16* Tb;           // folded item table [n_items, D] (T[i] = Wj [sqrt(d) E[i] | Wf_a attrs[i] + bf] + bj)
+  const float* T;           // folded item table [n_items, D] (T[i] = Wj [sqrt(d) E[i] | Wf_a attrs[i] + bf] + bj), fp32
   const float* Mc;          // folded context map [D][8]
   const float* pos;         // optional positional table [L, D]
   const int* p_x;
   const float* p_c;
   const int *row_src, *n_rows;
   const float *ln_g, *ln_b;
-  bf16 *XA, *QA;            // operand tiles: x and LN(x)
+  bf16 *XA, *QA;            // operand tiles: x and LN(x)                 (bf16 flavour)
+  float* Xf;                // x rows, fp32                                 (fp32 flavour)
   float* QN;                // LN(x) rows, fp32 (residual)
   int L, C;
 };
 // one group of D/8 lanes per row, 8 consecutive features per lane
-template <int D>
+template <int D, bool F32>
 __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
   constexpr int G = D / 8, RPW = 32 / G;
   __shared__ float mct[8][D];
@@ -141,7 +142,11 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
       const int pos = src & 255, u = (src >> 8) & 0x7fffff;
       if (src >= 0) {
         const int id = a.p_x[(long long)u * a.L + pos];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.Tb + (long long)id * D) + l), x);
+        {
+          const float4* tp = reinterpret_cast<const float4*>(a.T + (long long)id * D + 8 * l);
+          const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+          x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+        }
         const float* c = a.p_c + ((long long)u * a.L + pos) * a.C;
         for (int k = 0; k < a.C; ++k) {
           const float cv = __ldg(c + k);
@@ -172,8 +177,14 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) q[e] = (x[e] - mean) * rstd * gg[e] + bb[e];
-      *reinterpret_cast<uint4*>(a.XA + tile_off<D>(r, l)) = pack8(x);
-      *reinterpret_cast<uint4*>(a.QA + tile_off<D>(r, l)) = pack8(q);
+      if (F32) {
+        float4* xo = reinterpret_cast<float4*>(a.Xf + r * D + 8 * l);
+        xo[0] = make_float4(x[0], x[1], x[2], x[3]);
+        xo[1] = make_float4(x[4], x[5], x[6], x[7]);
+      } else {
+        *reinterpret_cast<uint4*>(a.XA + tile_off<D>(r, l)) = pack8(x);
+        *reinterpret_cast<uint4*>(a.QA + tile_off<D>(r, l)) = pack8(q);
+      }
       float4* qo = reinterpret_cast<float4*>(a.QN + r * D + 8 * l);
       qo[0] = make_float4(q[0], q[1], q[2], q[3]);
       qo[1] = make_float4(q[4], q[5], q[6], q[7]);
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
 
 // ---------------------------------------------------------------------------------------------- attention + LN2
 struct AttnRowsArgs {
-  const bf16 *Q, *K, *V;    // rows [R, D]
+  const void *Q, *K, *V;    // rows [R, D]: bf16 (bf16 flavour) or fp32
   const float* QN;          // LN1(x) rows (residual, src/carca.py:302)
   const int *row_src, *row_seg, *n_rows;
   const float *ln_g, *ln_b;
@@ -194,7 +205,22 @@ struct AttnRowsArgs {
 // causal self-attention of one packed row over the rows of its own segment (src/carca.py:299 with :246-256: keys of
 // the same user at positions <= the query's; a padding query row gives exactly 0), + LN1 residual, LayerNorm 2.
 // One group of D/8 lanes per row; a lane owns 8 consecutive features, i.e. a slice of one head.
-template <int D, int H>
+template <bool F32>
+__device__ __forceinline__ void load_row8(const void* base, long long row, int D, int l, bool on, float (&v)[8]) {
+  if (!on) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    return;
+  }
+  if (F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row * D + 8 * l);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + row * D) + l), v);
+  }
+}
+template <int D, int H, bool F32>
 __global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a) {
   constexpr int G = D / 8, RPW = 32 / G, DH = D / H, LPH = DH / 8;   // lanes per head
   static_assert(DH % 8 == 0 && LPH >= 1 && LPH <= 8, "head width");
@@ -216,7 +242,7 @@ __global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a)
 #pragma unroll
     for (int e = 0; e < 8; ++e) { q[e] = 0.f; acc[e] = 0.f; }
     if (n_keys > 0) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(a.Q + r * D) + l), q);
+      load_row8<F32>(a.Q, r, D, l, true, q);
 #pragma unroll
       for (int e = 0; e < 8; ++e) q[e] *= sc;
     }
@@ -225,8 +251,8 @@ __global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a)
       const bool on = j < n_keys;
       const long long kr = on ? (long long)s0 + j : 0;
       float kv[8], vv[8];
-      unpack8(on ? __ldg(reinterpret_cast<const uint4*>(a.K + kr * D) + l) : make_uint4(0, 0, 0, 0), kv);
-      unpack8(on ? __ldg(reinterpret_cast<const uint4*>(a.V + kr * D) + l) : make_uint4(0, 0, 0, 0), vv);
+      load_row8<F32>(a.K, kr, D, l, on, kv);
+      load_row8<F32>(a.V, kr, D, l, on, vv);
       float s = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) s = fmaf(q[e], kv[e], s);
@@ -272,7 +298,42 @@ __global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a)
       float4* so = reinterpret_cast<float4*>(a.S2 + r * D + 8 * l);
       so[0] = make_float4(o[0], o[1], o[2], o[3]);
       so[1] = make_float4(o[4], o[5], o[6], o[7]);
-      *reinterpret_cast<uint4*>(a.S2A + tile_off<D>(r, l)) = pack8(o);
+      if (!F32) *reinterpret_cast<uint4*>(a.S2A + tile_off<D>(r, l)) = pack8(o);
+    }
+  }
+}
+
+// y[r] = LayerNorm(x[r]) over fp32 rows (fp32 flavour: LN1 of the next block / the final norm, src/carca.py:298,421)
+template <int D>
+__global__ void __launch_bounds__(256) rows_ln_kernel(float* __restrict__ Y, const float* __restrict__ X,
+                                                      const float* __restrict__ g, const float* __restrict__ b,
+                                                      const int* __restrict__ n_rows) {
+  constexpr int G = D / 8, RPW = 32 / G;
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+  const int R = *n_rows;
+  for (long long r0 = (long long)warp * RPW; r0 < R; r0 += (long long)n_warps * RPW) {
+    const long long r = r0 + sub;
+    const bool live = r < R;
+    float v[8];
+    load_row8<true>(X, r, D, l, live, v);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[e];
+    const float mean = group_sum<G>(s) * (1.0f / D);
+    float m2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m2 = fmaf(v[e] - mean, v[e] - mean, m2);
+    const float rstd = rsqrtf(group_sum<G>(m2) * (1.0f / D) + kLnEps);
+    if (live) {
+      float gg[8], bb[8], o[8];
+      load_row8<true>(g, 0, D, l, true, gg);
+      load_row8<true>(b, 0, D, l, true, bb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
+      float4* yo = reinterpret_cast<float4*>(Y + r * D + 8 * l);
+      yo[0] = make_float4(o[0], o[1], o[2], o[3]);
+      yo[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
 }
@@ -285,11 +346,11 @@ struct GemmJob {
   const bf16* W;            // packed weight [D/8][D (out features)][8]
   const float* bias;        // [D]
   int epi;
-  bf16* out_rows;           // EPI_ROWS / EPI_KDEC: bf16 rows [R, D]
+  bf16* out_rows;           // EPI_ROWS: bf16 rows [R, D]
   bf16* out_tile;           // EPI_LRELU_TILE: activation tiles; EPI_LN: tiles of the pre-norm value x' (may be null)
   const float* resid;       // EPI_LN: fp32 rows added before the norm (null: no residual)
   const float *ln_g, *ln_b; // EPI_LN
-  float* out_f32;           // EPI_LN: LN rows fp32
+  float* out_f32;           // EPI_LN: LN rows fp32; EPI_KDEC: key rows fp32 [R, D]
   bf16* out_tile2;          // EPI_LN: LN tiles
   const float* wf;          // EPI_VDOT: scorer weight [D]
   float* U;                 // EPI_VDOT: u[r][h] = <V_h[r], wf_h>
@@ -551,9 +612,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmAr
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] += prm[32 * c + e];
           if (live) {
-            uint4* o = reinterpret_cast<uint4*>(J.out_rows + r * D + 32 * c);
+            float4* o = reinterpret_cast<float4*>(J.out_f32 + r * D + 32 * c);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = pack8(&v[8 * q]);
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -586,16 +647,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmAr
 // ---------------------------------------------------------------------------------------------- decoders
 struct DecodeArgs {
   // cross-attention (src/carca.py:338-347): keys of the encoded profile and the folded candidate tables
-  const bf16* Kd;           // decoder keys, rows [R, D]
-  const float* U;           // u[r][h] = <V_h[r], wf_h>
+  const float* Kd;          // decoder keys, rows [R, D] fp32
+  const float* U;           // u[r][h] = <V_h[r], wf_h>            (bf16 flavour: from the GEMM epilogue)
   const float* KM;          // km[r][h][k]
-  const bf16* TQb;          // WQ T[i] + bq  [n_items, D]
+  const float* Vd;          // decoder values, rows [R, D] fp32  (fp32 flavour: u / km are folded here)
+  const float *wf, *McQ;    //   scorer weight [D], query-side context map [D][8]
+  const float* TQ;          // WQ T[i] + bq  [n_items, D] fp32
   const float* tw;          // <T[i], wf>    [n_items]
   const float* mcw;         // wf Mc         [8]
   const float* dbf;         // scorer bias   [1]
   // dot product (:358-365)
   const float* PE;          // encoded profile rows fp32 [R, D]
-  const bf16* Tb;
+  const float* Tf;          // folded item table fp32
   const float* Mc;          // [D][8]
   const int2* useg;
   const int* row_src;
@@ -606,14 +669,15 @@ struct DecodeArgs {
   long long ldy;
   int col0, B, T, C, L, cat_lo, residual_ca;
 };
-constexpr int DEC_KEYS = 48;   // keys staged per pass (48 KB of static shared memory at d = 256, 8 heads)
+// keys staged per pass: the decoder (the stage whose rounding lands directly on the logit) runs in fp32 on fp32 tables
+template <int D> struct DecCfg { static constexpr int KEYS = D >= 128 ? 32 : 64; };
 
 // one CTA per (user, slice of 128 candidates); thread = candidate; the user's keys are staged in shared memory and
 // read by all threads at the same address (broadcast)
-template <int D, int H>
+template <int D, int H, bool F32>
 __global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a) {
-  constexpr int DH = D / H;
-  __shared__ __align__(16) bf16 ks[DEC_KEYS][D];
+  constexpr int DH = D / H, DEC_KEYS = DecCfg<D>::KEYS;
+  __shared__ __align__(16) float ks[DEC_KEYS][D];
   __shared__ float us[DEC_KEYS][H];
   __shared__ __align__(16) float kms[DEC_KEYS][H][8];
   __shared__ float kvalid[DEC_KEYS];
@@ -638,39 +702,52 @@ __global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a)
     for (int k0 = 0; k0 < sg.y; k0 += DEC_KEYS) {
       const int nk = min(DEC_KEYS, sg.y - k0);
       __syncthreads();
-      for (int i = threadIdx.x; i < nk * (D / 8); i += 128) {
-        const int j = i / (D / 8), kg = i % (D / 8);
-        reinterpret_cast<uint4*>(&ks[j][0])[kg] = __ldg(reinterpret_cast<const uint4*>(a.Kd + (long long)(sg.x + k0 + j) * D) + kg);
+      for (int i = threadIdx.x; i < nk * (D / 4); i += 128)
+        reinterpret_cast<float4*>(&ks[0][0])[i] = __ldg(reinterpret_cast<const float4*>(a.Kd + (long long)(sg.x + k0) * D) + i);
+      if (!F32) {
+        for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
+        for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
       }
-      for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
-      for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
       for (int i = threadIdx.x; i < nk; i += 128) kvalid[i] = a.row_src[sg.x + k0 + i] >= 0 ? 1.f : 0.f;
       __syncthreads();
+      if (F32) {   // u[j][h] = <V_h[j], wf_h>,  km[j][h][k] = <K_h[j], McQ_h[:, k]>  (see DecodeArgs)
+        for (int i = threadIdx.x; i < nk * H; i += 128) {
+          const int j = i / H, h = i % H;
+          const float* vp = a.Vd + (long long)(sg.x + k0 + j) * D + h * DH;
+          float u = 0.f, km[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int n = 0; n < DH; ++n) {
+            u = fmaf(__ldg(vp + n), __ldg(a.wf + h * DH + n), u);
+            const float kv = ks[j][h * DH + n];
+            const float4* mq = reinterpret_cast<const float4*>(a.McQ + (long long)(h * DH + n) * 8);
+            const float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);
+            km[0] = fmaf(kv, m0.x, km[0]); km[1] = fmaf(kv, m0.y, km[1]); km[2] = fmaf(kv, m0.z, km[2]); km[3] = fmaf(kv, m0.w, km[3]);
+            km[4] = fmaf(kv, m1.x, km[4]); km[5] = fmaf(kv, m1.y, km[5]); km[6] = fmaf(kv, m1.z, km[6]); km[7] = fmaf(kv, m1.w, km[7]);
+          }
+          us[j][h] = u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) kms[j][h][k] = km[k];
+        }
+        __syncthreads();
+      }
       if (has && id != 0) {
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           float q[DH];
-          const uint4* qp = reinterpret_cast<const uint4*>(a.TQb + (long long)id * D + h * DH);
+          const float4* qp = reinterpret_cast<const float4*>(a.TQ + (long long)id * D + h * DH);
 #pragma unroll
-          for (int i = 0; i < DH / 8; ++i) {
-            float t8[8];
-            unpack8(__ldg(qp + i), t8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) q[8 * i + e] = t8[e];
+          for (int i = 0; i < DH / 4; ++i) {
+            const float4 t4 = __ldg(qp + i);
+            q[4 * i] = t4.x; q[4 * i + 1] = t4.y; q[4 * i + 2] = t4.z; q[4 * i + 3] = t4.w;
           }
           for (int j = 0; j < nk; ++j) {
             if (kvalid[j] == 0.f) continue;                   // padding key (position L-1 of a short window)
-            const uint4* kp = reinterpret_cast<const uint4*>(&ks[j][h * DH]);
+            const float4* kp = reinterpret_cast<const float4*>(&ks[j][h * DH]);
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < DH / 8; ++i) {
-              float k8[8];
-              unpack8(kp[i], k8);
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) {
-                s0 = fmaf(q[8 * i + e], k8[e], s0);
-                s1 = fmaf(q[8 * i + e + 1], k8[e + 1], s1);
-              }
+            for (int i = 0; i < DH / 4; ++i) {
+              const float4 k4 = kp[i];
+              s0 = fmaf(q[4 * i], k4.x, s0); s1 = fmaf(q[4 * i + 1], k4.y, s1);
+              s0 = fmaf(q[4 * i + 2], k4.z, s0); s1 = fmaf(q[4 * i + 3], k4.w, s1);
             }
             float s = s0 + s1;
 #pragma unroll
@@ -695,7 +772,7 @@ __global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a)
           for (int k = 0; k < a.C; ++k) acc = fmaf(__ldg(a.mcw + k), cv[k], acc);
         }
       }
-      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + __expf(-acc));
+      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + expf(-acc));
     }
   }
 }
@@ -724,23 +801,19 @@ __global__ void __launch_bounds__(128) rows_decode_dot_kernel(const DecodeArgs a
       const int id = a.cat_lo > 0 ? a.cat_lo + t : __ldg(a.o_x + (long long)u * a.T + t);
       float acc = 0.f;
       if (id != 0) {
-        const uint4* tp = reinterpret_cast<const uint4*>(a.Tb + (long long)id * D);
+        const float4* tp = reinterpret_cast<const float4*>(a.Tf + (long long)id * D);
         float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < D / 8; ++i) {
-          float e8[8];
-          unpack8(__ldg(tp + i), e8);
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            s0 = fmaf(pl[8 * i + e], e8[e], s0);
-            s1 = fmaf(pl[8 * i + e + 1], e8[e + 1], s1);
-          }
+#pragma unroll 8
+        for (int i = 0; i < D / 4; ++i) {
+          const float4 e4 = __ldg(tp + i);
+          s0 = fmaf(pl[4 * i], e4.x, s0); s1 = fmaf(pl[4 * i + 1], e4.y, s1);
+          s0 = fmaf(pl[4 * i + 2], e4.z, s0); s1 = fmaf(pl[4 * i + 3], e4.w, s1);
         }
         acc = s0 + s1;
         const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
         for (int k = 0; k < a.C; ++k) acc = fmaf(pmc[k], __ldg(c + k), acc);
       }
-      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + __expf(-acc));
+      a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + expf(-acc));
     }
   }
 }

@@ -275,12 +275,14 @@ def forward_catalog(model, profile, ctx_user: Tensor, item_lo: int, n_cand: int,
 
 
 # ------------------------------------------------------------------------------- bf16 packed-rows pipeline
-ROWS_WIDTHS, ROWS_HEAD_WIDTHS, ROWS_MAX_L = (64, 256), (32, 64), 256
+ROWS_MAX_L = 256
+ROWS_SHAPES = {"bf16": ((64, 256), (32, 64)), "fp32": ((32, 64, 128, 256), (16, 32, 64))}   # widths, head widths
 
 
-def rows_supported(model, seq_len: int, n_ctx: int) -> bool:
-    """Shape range of the bf16 pipeline (csrc/rows_bf16.cuh): d in {64, 256}, head width 32 or 64, L <= 256 with any
-    number of valid positions per user, stock blocks, cross-attention or dot-product decoder."""
+def rows_supported(model, seq_len: int, n_ctx: int, precision: str = "bf16") -> bool:
+    """Shape range of the packed-rows pipeline (csrc/rows_bf16.cuh): L <= 256 with any number of valid positions per
+    user, stock blocks, cross-attention or dot-product decoder; bf16 flavour d in {64, 256} with head width 32 / 64,
+    fp32 flavour d in {32, 64, 128, 256} with head width 16 / 32 / 64."""
     from . import carca as M
 
     emb, dec = model.embeds, model.decoder
@@ -298,7 +300,10 @@ def rows_supported(model, seq_len: int, n_ctx: int) -> bool:
     elif not isinstance(dec, M.DotProduct):
         return False
     d = emb.d
-    return (d in ROWS_WIDTHS and d % H == 0 and d // H in ROWS_HEAD_WIDTHS and n_ctx <= MAX_CTX
+    widths, head_widths = ROWS_SHAPES[precision]
+    if (d, H) == (256, 16):
+        return False
+    return (d in widths and d % H == 0 and d // H in head_widths and n_ctx <= MAX_CTX
             and seq_len <= ROWS_MAX_L and N.is_device_tensor(emb.items_embed.weight))
 
 
@@ -312,9 +317,7 @@ def rows_plan(model, table: ItemAttrTable, n_ctx: int):
         buf = ent.rows_spare
         if buf is None or buf.numel() != nbytes or buf.device != dev:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        emb = model.embeds
-        tmp = torch.empty((emb.items_embed.weight.shape[0], emb.d), dtype=torch.float32, device=dev)
-        N.call("carca_rows_prepare", buf.data_ptr(), N.f32p(tmp), N.f32p(ent.plan), C.byref(ent.m), N.stream())
+        N.call("carca_rows_prepare", buf.data_ptr(), N.f32p(ent.plan), C.byref(ent.m), N.stream())
         ent.rows, ent.rows_spare = buf, None
     return ent
 
@@ -334,10 +337,11 @@ def _rows_scratch(ent, B: int, L: int, device) -> Tensor:
     return buf
 
 
-def forward_rows(model, profile, targets: Sequence, cat_lo: int = 0, n_cand: int = 0,
+def forward_rows(model, profile, targets: Sequence, precision: str = "bf16", cat_lo: int = 0, n_cand: int = 0,
                  ctx_user: Optional[Tensor] = None) -> Tensor:
-    """CARCA.forward in eval mode (src/carca.py:411-431) through the bf16 packed-rows pipeline -> [B, sum(T)].
-    With cat_lo > 0: catalog mode, scores of items [cat_lo, cat_lo + n_cand) with one context row per user."""
+    """CARCA.forward in eval mode (src/carca.py:411-431) through the packed-rows pipeline -> [B, sum(T)]; precision
+    "bf16" or "fp32".  With cat_lo > 0: catalog mode, scores of items [cat_lo, cat_lo + n_cand) with one context row
+    per user."""
     p_x, p_a, p_c = profile
     table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
     N.require_device(p_x, p_c)
@@ -360,7 +364,9 @@ def forward_rows(model, profile, targets: Sequence, cat_lo: int = 0, n_cand: int
         T = o_x.shape[1]
     ent = rows_plan(model, table, n_ctx)
     y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
-    N.call("carca_rows_eval_forward", N.f32p(y), T, 0, ent.rows.data_ptr(), C.byref(ent.m), N.i32p(p_x), N.f32p(p_c),
+    N.call("carca_rows_eval_forward", N.f32p(y), T, 0, ent.rows.data_ptr(), N.f32p(ent.plan), C.byref(ent.m), N.i32p(p_x),
+           N.f32p(p_c),
            None if o_x is None else N.i32p(o_x), N.f32p(o_c), B, L, T, int(per_user_ctx), int(cat_lo),
-           N.i32p(ent.status), _rows_scratch(ent, B, L, p_x.device).data_ptr(), N.stream())
+           {"bf16": 0, "fp32": 1}[precision], N.i32p(ent.status), _rows_scratch(ent, B, L, p_x.device).data_ptr(),
+           N.stream())
     return y

@@ -128,14 +128,11 @@ class GraphedEvalStep:
         self.result = result
         self._metrics = ops.eval_metrics_
         keep = self.stats.clone()
-        # windows longer than 64: the fused kernel needs every user's valid positions to fit a 64-row bin, which takes
-        # a host read and so cannot be checked inside a capture — check the example batch here and every batch before
-        # its replay (a batch that does not fit runs eagerly on the per-op kernels)
+        # (windows longer than one 64-row bin run on the packed-rows pipeline, which has no per-user row limit and
+        # needs no host-side check: nothing to decide per batch)
         from . import fused
 
-        self.long_windows = batch["p_x"].shape[1] > fused.BIN_ROWS
-        if self.long_windows:
-            model._fits_eval_override = fused.fits_packed(self.static["p_x"])
+        self.long_windows = False
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -146,10 +143,10 @@ class GraphedEvalStep:
             self.graph = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(self.graph):
                 self._body()
-            self.graph_is_fused = bool(model._fits_eval_override) if self.long_windows else True
+            self.graph_is_fused = True
             self.uses_plan = fused._plans.get(model) is not None       # the capture reads the fused inference plan
         finally:
-            model._fits_eval_override = None
+            pass
         self.stats.copy_(keep)                       # warm-up runs do not count
 
     def _body(self) -> None:
@@ -175,10 +172,14 @@ class GraphedEvalStep:
         if not self.uses_plan:
             return
         before = fused._plans.get(self.model)
-        buf = None if before is None else before.plan.data_ptr()
+        bufs = None if before is None else (before.plan.data_ptr(), None if before.rows is None else before.rows.data_ptr())
         emb = self.model.embeds
-        ent = fused.eval_plan(self.model, emb.attr_table, self.static["p_c"].shape[-1])
-        if buf is not None and ent.plan.data_ptr() != buf:
+        n_ctx = self.static["p_c"].shape[-1]
+        ent = fused.eval_plan(self.model, emb.attr_table, n_ctx)
+        if bufs is not None and bufs[1] is not None:
+            ent = fused.rows_plan(self.model, emb.attr_table, n_ctx)
+        if bufs is not None and (ent.plan.data_ptr() != bufs[0] or
+                                 (bufs[1] is not None and ent.rows.data_ptr() != bufs[1])):
             raise RuntimeError("GraphedEvalStep: the model's parameters were replaced (moved / cast) after capture; "
                                "build a new GraphedEvalStep")
 
@@ -188,10 +189,6 @@ class GraphedEvalStep:
 
         if self.uses_plan and not fused.plan_is_current(self.model):
             self.refresh()
-        if self.long_windows and self.graph_is_fused and not fused.fits_packed(self.static["p_x"]):
-            with torch.no_grad():                    # a user with more than 64 valid positions: per-op kernels, eagerly
-                self._body()
-            return
         self.graph.replay()
 
     def __call__(self, batch: Dict[str, Tensor]) -> None:

@@ -460,29 +460,34 @@ int carca_eval_forward_opts(float* y, int64_t ldy, int col0, const float* plan, 
  * (src/carca.py:246-251) — so the encoder runs on valid rows only.                              */
 int64_t carca_eval_scratch_bytes(int B);
 
-/* ------------------------------------------------------------------ bf16 inference over packed rows */
-/* CARCA.forward in eval mode (src/carca.py:411-431) in bf16 with fp32 accumulation, fp32 softmax and fp32 LayerNorm
- * (BASELINE configs[1] "bf16/fp32", configs[2] Men-shaped d = 256): a pipeline of kernels over the batch's PACKED
- * valid profile rows — tcgen05 kind::f16 GEMMs with the weight matrix resident in shared memory, A tiles streamed by
- * cp.async.bulk, double-buffered TMEM accumulators and fused bias / LeakyReLU / residual / LayerNorm epilogues
- * (csrc/rows_bf16.cuh).  Supported: d in {64, 256}, head width 32 or 64, C <= 8, 1..8 blocks, L <= 256 with ANY number
- * of valid positions per user, both decoders.  Tolerance contract: scores within 1e-2 of the fp32 reference.
+/* ------------------------------------------------------------------ inference over packed rows */
+/* CARCA.forward in eval mode (src/carca.py:411-431) as a pipeline of kernels over the batch's PACKED valid profile
+ * rows (csrc/rows_bf16.cuh): the valid positions of every user (plus position L-1) form one flat row array, every
+ * stage of the model is one kernel over all rows, and a user may have ANY number of valid positions (L <= 256) —
+ * there is no bin or tile limit and nothing is decided on the host.  Both decoders.  Two arithmetic flavours:
+ *   precision 0 (bf16; BASELINE configs[1] "bf16/fp32", configs[2] Men-shaped d = 256): tcgen05 kind::f16 GEMMs with
+ *     the weight matrix resident in shared memory, A tiles streamed by cp.async.bulk, double-buffered TMEM
+ *     accumulators and fused bias / LeakyReLU / residual / LayerNorm epilogues; fp32 accumulation, softmax, LayerNorm,
+ *     embedding gather and decoder.  d in {64, 256}, head width 32 or 64.  Scores within 1e-2 of the fp32 reference.
+ *   precision 1 (fp32): every projection through the 3xTF32 tcgen05 GEMM of the training path with the row count
+ *     read on the device; d in {32, 64, 128, 256}, head width 16 / 32 / 64.  Scores within 1e-4 (the fp32 contract).
  *
- * carca_rows_plan_bytes / carca_rows_prepare: bf16 plan derived from the fp32 plan of carca_eval_prepare (folded item
- * table T and context map Mc) and the model parameters: bf16 T, packed bf16 projection weights and, for the
- * cross-attention decoder, the folded candidate tables TQ = WQ T + bq (bf16), tw = <T, wf>, McQ = WQ Mc, mcw = wf Mc.
- * tmp: [n_items, d] floats of scratch.  Call again whenever the weights change.                                    */
+ * carca_rows_plan_bytes / carca_rows_prepare: plan derived from the fp32 plan of carca_eval_prepare (folded item
+ * table T and context map Mc) and the model parameters: packed bf16 projection weights and, for the cross-attention
+ * decoder, the folded candidate tables TQ = WQ T + bq, tw = <T, wf>, McQ = WQ Mc, mcw = wf Mc (fp32).  Call again
+ * whenever the weights change; the forward call takes both plans.                                                   */
 int64_t carca_rows_plan_bytes(const carca_model_params* m);
-int carca_rows_prepare(void* plan, float* tmp, const float* plan_f32, const carca_model_params* m, void* stream);
+int carca_rows_prepare(void* plan, const float* plan_f32, const carca_model_params* m, void* stream);
 /* Bytes of device scratch for a batch of B users with windows of L positions (worst case: every position valid). */
 int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L);
 /* y[b, col0 + t] = CARCA.forward(profile, [targets]) in eval mode.  p_x [B,L], p_c [B,L,C], o_x [B,T],
  * o_c [B,T,C] (ctx_per_user != 0: [B,C], one context row per user as src/data.py:185 builds).  cat_lo > 0: catalog
  * mode, candidate t is item cat_lo + t and o_x is not read.  status (device int32[1]): bit 1 is set if an mbarrier
- * wait of the GEMM pipeline timed out (results invalid).                                                            */
-int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const carca_model_params* m,
-                            const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L,
-                            int T, int ctx_per_user, int cat_lo, int32_t* status, void* scratch, void* stream);
+ * wait of the bf16 GEMM pipeline timed out (results invalid).                                                        */
+int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const float* plan_f32,
+                            const carca_model_params* m, const int32_t* p_x, const float* p_c, const int32_t* o_x,
+                            const float* o_c, int B, int L, int T, int ctx_per_user, int cat_lo, int precision,
+                            int32_t* status, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------ full-catalog scoring */
 /* Scores every item of the contiguous id range [item_lo, item_lo + n_cand) (an item-table shard)

@@ -55,4 +55,5 @@ def emu_backend(monkeypatch):
     monkeypatch.setattr(N, "require_device", lambda *t: None)
     monkeypatch.setattr(N, "stream", lambda: 0)
     monkeypatch.setattr(N, "is_device_tensor", lambda t: True)
+    monkeypatch.setattr(N, "is_emulated", lambda: True)
     return "cpu"

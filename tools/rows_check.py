@@ -44,12 +44,17 @@ def run(name):
     model = model.cuda().eval()
     model.embeds.set_attr_table(synth.make_attr_table(shape, seed=5).cuda())
     d = {k: v.cuda() for k, v in b.items()}
-    model.set_eval_dtype("bf16")
-    with torch.no_grad():
-        y = model.forward((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])])
-    torch.cuda.synchronize()
-    st = int(fused._plans[model].status.item())
-    y = y.cpu().numpy()
+    for dt in ("bf16", "fp32"):
+        model.set_eval_dtype(dt)
+        model.force_eval_path = "rows_fp32" if dt == "fp32" else None
+        with torch.no_grad():
+            y = model.forward((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])])
+        torch.cuda.synchronize()
+        st = int(fused._plans[model].status.item())
+        report(name + ":" + dt, y.cpu().numpy(), y_ref, st)
+
+
+def report(name, y, y_ref, st):
     abs_err = np.abs(y - y_ref).max()
     rel = (np.abs(y - y_ref) / np.maximum(np.abs(y_ref), 1e-12)).max()
     logit = lambda p: np.log(np.clip(p, 1e-30, 1) / np.clip(1 - p, 1e-30, 1))  # noqa: E731
@@ -57,7 +62,7 @@ def run(name):
     le = le[np.isfinite(le)]
     top = np.mean([len(set(np.argsort(-a)[:10]) & set(np.argsort(-r)[:10])) / 10 for a, r in zip(y, y_ref)])
     hr = np.mean((y_ref[:, 1:] > y_ref[:, :1]).sum(1) < 10), np.mean((y[:, 1:] > y[:, :1]).sum(1) < 10)
-    print(f"{name:20s} status {st} nan {int(np.isnan(y).sum())} max|dp| {abs_err:.2e} max rel {rel:.2e} "
+    print(f"{name:24s} status {st} nan {int(np.isnan(y).sum())} max|dp| {abs_err:.2e} max rel {rel:.2e} "
           f"logit err max {le.max():.3e} mean {le.mean():.3e} (|logit| max {np.abs(logit(y_ref.astype(np.float64))).max():.1f}) "
           f"top10 overlap {top:.3f} HR ref/ours {hr[0]:.3f}/{hr[1]:.3f}", flush=True)
 
