@@ -65,6 +65,8 @@ static int launch_tc(const GemmArgs& g, int tn, int tm, int splits, int vec_a, i
     if (e != cudaSuccess) return fail(-3, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
+  // rows known on the device only (m_dev): at most ~8 CTAs per SM, each loops over its row tiles
+  if (g.m_dev) tm = min(tm, max(1, 148 * 8 / max(1, tn * splits)));
   CARCA_LAUNCH(k, dim3(tn, tm, splits), dim3(GT_THREADS), smem, stream, g, vec_a, vec_b, vec_c);
   return check_launch("gemm_tc");
 }

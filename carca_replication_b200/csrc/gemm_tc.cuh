@@ -104,14 +104,14 @@ __device__ __forceinline__ void stash_tile(float* __restrict__ hi, float* __rest
 }
 
 template <int BN>
-__global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, int vec_a, int vec_b, int vec_c) {
+__global__ void __launch_bounds__(GT_THREADS, (BN > 128 ? 2 : 3)) gemm_tc_kernel(const GemmArgs g, int vec_a, int vec_b, int vec_c) {
   constexpr int BNC = BN > 128 ? 128 : BN;   // columns of one epilogue pass
   CARCA_DYN_SMEM(unsigned char, raw);
   GemmTcSmem<BN>& s = *reinterpret_cast<GemmTcSmem<BN>*>(raw);
   const int tid = threadIdx.x, w = tid / 32, lane = tid % 32;
-  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.x * BN;
   const int gM = g.m_dev ? min(g.M, *g.m_dev) : g.M;
-  if (m0 >= gM) return;   // (whole CTA, before any barrier / TMEM allocation)
+  if ((int)blockIdx.y * GT_BM >= gM) return;   // (whole CTA, before any barrier / TMEM allocation)
   const int k_begin = blockIdx.z * g.k_per_split;
   const int k_end = min(g.K, k_begin + g.k_per_split);
   const int nk = k_end > k_begin ? (k_end - k_begin + GT_BK - 1) / GT_BK : 0;
@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = s.tmem_slot;
+  uint32_t n_commit = 0;   // commits so far on s.bar (running over the row tiles of this CTA)
+  bool ok = true;
+
+  // row tiles blockIdx.y, + gridDim.y, ...: the grid's y extent may be capped below the tile count (rows known on
+  // the device only: a worst-case grid would launch thousands of CTAs that exit at once)
+#pragma unroll 1
+  for (int m0 = blockIdx.y * GT_BM; m0 < gM; m0 += gridDim.y * GT_BM) {
+  __syncthreads();   // the previous tile's epilogue no longer reads the shared C tile (same bytes as the operands)
 
   const bool a_k = !g.transA, b_k = g.transB != 0;
   float4 ra[GT_BM / 32], rb[BN / 32];
@@ -130,10 +138,9 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
     fetch_tile<GT_BM>(ra, g.A, g.lda, a_k, a_k ? g.a_rows : nullptr, m0, gM, k_begin, k_end, vec_a);
     fetch_tile<BN>(rb, g.B, g.ldb, b_k, b_k ? nullptr : g.b_rows, n0, g.N, k_begin, k_end, vec_b);
   }
-  bool ok = true;
 #pragma unroll 1
   for (int kt = 0; kt < nk; ++kt) {
-    if (kt >= 1) ok = umma::mbar_wait(&s.bar, (uint32_t)((kt - 1) & 1)) && ok;   // MMAs of step kt-1 read the buffers
+    if (kt >= 1) ok = umma::mbar_wait(&s.bar, (n_commit - 1) & 1u) && ok;   // MMAs of step kt-1 read the buffers
     umma::fence_after_sync();
     stash_tile<GT_BM>(s.a[0], s.a[1], ra, a_k);
     stash_tile<BN>(s.b[0], s.b[1], rb, b_k);
@@ -162,9 +169,10 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
         umma::commit(&s.bar);
       }
     }
+    ++n_commit;
   }
   if (nk > 0) {
-    ok = umma::mbar_wait(&s.bar, (uint32_t)((nk - 1) & 1)) && ok;
+    ok = umma::mbar_wait(&s.bar, (n_commit - 1) & 1u) && ok;
     umma::fence_after_sync();
   }
 
@@ -246,6 +254,8 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const GemmArgs g, i
       }
     }
   }
+  umma::fence_before_sync();   // this tile's TMEM reads are ordered before the next tile's MMAs
+  }   // row tiles
   umma::fence_before_sync();
   __syncthreads();
   if (w == 0) umma::tmem_free(tmem0, BN);

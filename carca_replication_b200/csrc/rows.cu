@@ -202,7 +202,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   d.oc_tgt = ctx_per_user ? 0 : C;
   d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.C = C; d.L = L; d.cat_lo = cat_lo;
   d.residual_ca = m->residual_ca;
-  const long long items = (long long)B * ceil_div(T, 128);
+  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
     const bf16* dw = reinterpret_cast<const bf16*>(plan + pl.dw);
@@ -315,7 +315,7 @@ int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, co
   d.oc_tgt = ctx_per_user ? 0 : C;
   d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.C = C; d.L = L; d.cat_lo = cat_lo;
   d.residual_ca = m->residual_ca;
-  const long long items = (long long)B * ceil_div(T, 128);
+  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
     TRY(gemm_rows_f32(Kf, QN, m->cross.wk, m->cross.bk, Mcap, D, n_rows, 0, nullptr, st));

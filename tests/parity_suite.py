@@ -579,12 +579,13 @@ def assert_fp32_parity(y, y_ref, d, B, k=10):
 
 
 def bf16_errors(y, y_ref):
-    """(max |dp|, max |dlogit| over unsaturated candidates / max(1, max |logit_ref|), top-10 overlap)."""
+    """(max |dp|, max |dlogit| over unsaturated candidates / max(1, max |logit_ref| of the batch), top-10 overlap)."""
     yn = np.asarray(y, dtype=np.float64)
-    live = (y_ref > 1e-6) & (y_ref < 1 - 1e-6)
+    live = (y_ref > 1e-6) & (y_ref < 1 - 1e-6)           # candidates whose fp32 probability still resolves the logit
     lr = _logit(y_ref)
     dl = np.abs(_logit(yn) - lr)[live]
-    scale = max(1.0, float(np.abs(lr[live]).max())) if live.any() else 1.0
+    finite = (y_ref > 0) & (y_ref < 1)                   # the batch's logit scale: every logit fp32 can represent
+    scale = max(1.0, float(np.abs(lr[finite]).max())) if finite.any() else 1.0
     top = np.mean([len(set(np.argsort(-a, kind="stable")[:10]) & set(np.argsort(-r, kind="stable")[:10])) / 10.0
                    for a, r in zip(yn, y_ref)])
     return float(np.abs(yn - y_ref).max()), float(dl.max() / scale) if dl.size else 0.0, float(top)

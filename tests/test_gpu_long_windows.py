@@ -29,7 +29,8 @@ def test_long_windows_with_users_beyond_one_bin_vs_oracle(decoder, L):
     assert int((batch["p_x"] != 0).sum(1).max()) == L            # a user with every position valid
     model, y_ref = S.oracle_scores(shape, decoder, batch, seed=31)
     model, y, d = S.run_eval_path(model, shape, batch, DEV, seed=31, no_sync=True)
-    assert model._fused_eval_mode((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])]) == "rows_fp32"
+    with torch.no_grad():
+        assert model._fused_eval_mode((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])]) == "rows_fp32"
     S.assert_fp32_parity(y, y_ref, d, B)
 
 

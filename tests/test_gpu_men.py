@@ -26,7 +26,8 @@ def test_men_shape_fp32_rows_vs_oracle(all_valid):
     batch = synth.make_eval_batch(shape, B, seed=5, all_valid=all_valid)
     model, y_ref = S.oracle_scores(shape, "ca", batch, seed=5)
     model, y, d = S.run_eval_path(model, shape, batch, DEV, seed=5, no_sync=True)
-    assert model._fused_eval_mode((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])]) == "rows_fp32"
+    with torch.no_grad():
+        assert model._fused_eval_mode((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])]) == "rows_fp32"
     S.assert_fp32_parity(y, y_ref, d, B)
 
 
