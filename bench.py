@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-catalog", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bf16 / sweep / Men sections")
+    ap.add_argument("--men-batch", type=int, default=2048)
     ap.add_argument("--catalog-users", type=int, default=1024)
     ap.add_argument("--rotate", type=int, default=8, help="distinct input batches cycled through")
     ap.add_argument("--e2e-eager", action="store_true",
@@ -144,21 +146,86 @@ def oracle_config(shape, decoder):
     return OracleConfig(d=shape.d, n_heads=shape.n_heads, n_blocks=shape.n_blocks, decoder=decoder, p_drop=0.0)
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_model(shape, decoder, sd, device="cpu"):
+    """The UNMODIFIED reference (baseline/_ref, staged by __graft_entry__.build()) built as scripts/training.py:165-172
+    does and loaded with our weights (identical state_dict layout), or None when the copy is absent."""
+    if not os.path.isdir(os.path.join(REF_DIR, "src")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import torch.nn as nn
+    from src import carca as R  # noqa: E402  (the reference package)
+
+    emb = R.AllEmbedding(shape.n_items, shape.d, shape.g, shape.n_ctx, shape.n_attrs, R.IdentityEncoding())
+    enc = nn.ModuleList([R.SelfAttentionBlock(shape.d, shape.n_heads, 0.5, True) for _ in range(shape.n_blocks)])
+    dec = R.CrossAttentionBlock(shape.d, shape.n_heads, 0.5, True) if decoder == "ca" else R.DotProduct()
+    model = R.CARCA(d=shape.d, p=0.5, emb=emb, enc=enc, dec=dec)
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval()
+
+
+def reference_eval_body(model, batch):
+    """evaluate()'s per-batch body exactly as src/train.py:42-50 runs it (forward, BCE, two sorts, three .item())."""
+    from src.carca import BinaryCrossEntropy
+    from src.train import compute_HR, compute_NDCG
+    from src.utils import get_mask
+
+    p_x, p_a, p_c, o_x, o_a, o_c, y_true = batch
+    with torch.no_grad():
+        y = model.forward(profile=(p_x, p_a, p_c), targets=[(o_x, o_a, o_c)])
+        loss = BinaryCrossEntropy().forward(y, y_true, get_mask(o_x)).item()
+        return compute_HR(y, y_true, 10), compute_NDCG(y, y_true, 10), loss
+
+
 def time_cpu_eval(shape, decoder, sd, table, B, steps, warmup):
-    """users/s of the reference's evaluate() body on the host cores (oracle port, all threads)."""
+    """users/s of the reference's evaluate() body on the host cores, all threads: the real reference when
+    baseline/_ref is staged (kind "reference"), else the oracle port (kind "port")."""
     from carca_replication_b200 import synth
     from oracle import carca_oracle as O
 
     torch.set_num_threads(os.cpu_count())
-    cfg = oracle_config(shape, decoder)
     batches = [dense_batch(table, synth.make_eval_batch(shape, B, seed=100 + i)) for i in range(2)]
+    ref = reference_model(shape, decoder, sd)
+    if ref is not None:
+        body, kind = (lambda b: reference_eval_body(ref, b)), "reference"
+    else:
+        cfg = oracle_config(shape, decoder)
+        body, kind = (lambda b: O.eval_batch(sd, cfg, b)), "port"
     for i in range(warmup):
-        O.eval_batch(sd, cfg, batches[i % 2])
+        body(batches[i % 2])
     t0 = time.perf_counter()
     for i in range(steps):
-        O.eval_batch(sd, cfg, batches[i % 2])
+        body(batches[i % 2])
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps
+    return B * steps / dt, dt / steps, kind
+
+
+def time_reference_cuda(shape, decoder, sd, table, B, steps, dev):
+    """Secondary baseline: the same reference code, PyTorch eager on this B200, dense attributes
+    resident on the device (what `model.forward` consumes), CUDA-event timed."""
+    from carca_replication_b200 import synth
+
+    ref = reference_model(shape, decoder, sd, device=dev)
+    if ref is None:
+        return {"unavailable": "baseline/_ref not staged"}
+    batches = [tuple(t.to(dev) for t in dense_batch(table, synth.make_eval_batch(shape, B, seed=100 + i)))
+               for i in range(2)]
+    for i in range(3):
+        reference_eval_body(ref, batches[i % 2])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        reference_eval_body(ref, batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "users/s", "batch": B, "ms_per_batch": ms,
+            "what": "unmodified reference (baseline/_ref) on device='cuda', PyTorch eager, fp32, dense [B,N,A] attributes "
+                    "already on the device; evaluate() body incl. its three .item() syncs"}
 
 
 def run_reference(args):
@@ -172,18 +239,27 @@ def run_reference(args):
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     table = synth.make_attr_table(shape)
     B = args.cpu_batch
-    ups, sec = time_cpu_eval(shape, args.decoder, sd, table, B, args.steps, max(1, min(args.warmup, 2)))
+    ups, sec, kind = time_cpu_eval(shape, args.decoder, sd, table, B, args.steps, max(1, min(args.warmup, 2)))
     cores = os.cpu_count()
     sample = f"{args.steps} batches of {B} users (dense [B,N,A] attributes pre-materialised, loader excluded)"
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "eval_users_per_sec", "value": ups, "unit": "users/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, shape, B),
-        "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ups, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }
+    # the same body at the largest batch whose dense attribute tensors (3.9 MB per Beauty user) fit comfortably
+    if not args.no_cpu_baseline and shape.name == "beauty":
+        try:
+            big = 1024
+            ups2, sec2, _ = time_cpu_eval(shape, args.decoder, sd, table, big, max(1, args.steps // 4), 1)
+            out["large_batch"] = {"value": ups2, "unit": "users/s", "batch": big, "ms_per_step": sec2 * 1e3}
+        except (RuntimeError, MemoryError) as ex:
+            out["large_batch"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    print(json.dumps(out), flush=True)
 
 
 def workload_config(args, shape, batch):
@@ -410,6 +486,23 @@ def run_ours(args):
     pk = peaks()
     roof, ops_table = roofline(op_ms, shape, B, args.decoder, pk)
     _, per_op_table = roofline(op_ms_per_op_path, shape, B, args.decoder, pk)
+    if roof["kernel"] == "fused_forward":
+        # the SAME CUDA-event timing as `value`: kernel time = ms_per_step x the kernel's share of the step (the share
+        # from per-op events around the two launches of a step, cross-checked by the committed ncu launch list)
+        t_kernel_ms = (ms_dev / K) * roof["share_of_step"]
+        fl = fwd_flops_per_user(shape, args.decoder)
+        roof["achieved"] = fl * B / (t_kernel_ms * 1e-3) / 1e12
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["kernel_ms"] = t_kernel_ms
+        roof["timing"] = "ms_per_step of the timed region x share_of_step"
+        cap_path = os.path.join(ROOT, "profiles", "r02", "roofline_capture.json")
+        if os.path.exists(cap_path):
+            cap = json.load(open(cap_path))
+            roof["traffic"] = cap["dram_bytes_per_user"] * B
+            roof["traffic_source"] = cap["source"]
+            roof["tensor_pipe_active_pct"] = cap.get("tensor_pipe_active_pct")
+        else:
+            roof["traffic_source"] = "profiles/r01/ncu_fused_tc_v17_raw.csv (3334 B/user)"
 
     out = {
         "metric": "eval_users_per_sec", "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -459,19 +552,35 @@ def run_ours(args):
 
     if world > 1 and not args.no_train:
         optional("train", lambda: time_train_dp(shape, args, dev, table, rank, world))
+    if world > 1 and not args.no_catalog:
+        optional("catalog", lambda: time_catalog_sharded(model, shape, args, dev, rank, world))
+    if world > 1 and not args.no_extra:
+        optional("men", lambda: time_men(args, dev, pk, rank=rank, world=world))
     if world == 1 and rank == 0:
         if not args.no_train:
             optional("train", lambda: time_train(shape, args, dev, table))
         if not args.no_catalog:
             optional("catalog", lambda: time_catalog(model, shape, args, dev))
             optional("device_pipeline", lambda: time_device_pipeline(model, shape, args, dev))
+        if not args.no_extra:
+            optional("bf16", lambda: time_bf16(model, shape, args, dev, devb, step, pk))
+            optional("sweep", lambda: time_sweep(shape, args, dev, table))
+            optional("men", lambda: time_men(args, dev, pk))
         if not args.no_cpu_baseline:
             cb_B = args.cpu_batch
-            ups, sec = time_cpu_eval(shape, args.decoder, sd_cpu, table_cpu, cb_B, 3, 1)
-            out["cpu_baseline"] = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+            ups, sec, kind = time_cpu_eval(shape, args.decoder, sd_cpu, table_cpu, cb_B, 3, 1)
+            out["cpu_baseline"] = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": kind,
                                    "sample": f"3 batches of {cb_B} users after 1 warm-up, dense attributes "
                                              "pre-materialised (reference API), loader excluded",
-                                   "ms_per_batch": sec * 1e3}
+                                   "ms_per_batch": sec * 1e3,
+                                   "same_batch_as_ours": {"batch": cb_B, "ours_users_per_s": None}}
+            # the same (reference-sized) batch through our path, so that the ratio at EQUAL batch is on the line too
+            small = [{k: v.to(dev) for k, v in synth.make_eval_batch(shape, cb_B, seed=900 + i).items()} for i in range(4)]
+            for b in small:
+                b["o_c"] = b["o_c"][:, :1, :].contiguous().expand(-1, b["o_x"].shape[1], -1)
+            with torch.no_grad():
+                out["cpu_baseline"]["same_batch_as_ours"]["ours_users_per_s"] = graphed_rate(step, small, cb_B, 50)
+            optional("reference_cuda", lambda: time_reference_cuda(shape, args.decoder, sd_cpu, table_cpu, cb_B, 5, dev))
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -592,6 +701,209 @@ def roofline(op_ms, shape, B, decoder, pk):
                             f"{FP32_FFMA_PEAK_TFLOPS:.1f} TFLOP/s fp32 FFMA peak the fraction is "
                             f"{r['frac_of_fp32_ffma_peak']:.3f}")
     return roof, table
+
+
+def graphed_rate(step, batches, B, n, world=1, dev=None):
+    """users/s of `step(batch)` replayed as CUDA graphs over the rotated `batches` (CUDA events; max over ranks)."""
+    graphs = []
+    for b in batches:
+        step(b)
+    torch.cuda.synchronize()
+    for b in batches:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step(b)
+        graphs.append(g)
+    for g in graphs:
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(n):
+        graphs[i % len(graphs)].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = e0.elapsed_time(e1) / n
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return world * B / (ms * 1e-3)
+
+
+def fwd_flops_per_user(shape, decoder, rows=None):
+    """Algorithmic forward FLOPs per user: all L positions unless `rows` (valid rows per user) is given."""
+    L, T, d, C, nb = shape.seq_len, shape.n_targets, shape.d, shape.n_ctx, shape.n_blocks
+    n = L if rows is None else rows
+    enc = nb * (10 * n * d * d + 4 * n * n * d)
+    dec = (2 * T * d * d + 4 * n * d * d + 4 * T * n * d + 2 * T * d) if decoder == "ca" else 2 * T * d
+    return enc + dec + 2 * (n + T) * C * d
+
+
+def eval_step_fn(model, acc4):
+    from carca_replication_b200 import ops
+
+    def step(b):
+        y = model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
+        ops.eval_metrics_(acc4, y, b["y_true"], b["o_x"], 10)
+        return y
+    return step
+
+
+def device_batches(shape, B, dev, n=4, seed=0, all_valid=False):
+    from carca_replication_b200 import synth
+
+    out = []
+    for i in range(n):
+        b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, B, seed=seed + i, all_valid=all_valid).items()}
+        b["o_c"] = b["o_c"][:, :1, :].contiguous().expand(-1, b["o_x"].shape[1], -1)
+        out.append(b)
+    return out
+
+
+def time_bf16(model, shape, args, dev, devb, step, pk):
+    """BASELINE configs[1] "bf16/fp32": the same eval step with CARCA.eval_dtype = "bf16" (packed-rows pipeline:
+    tcgen05 kind::f16 GEMMs, fp32 accumulation / softmax / LayerNorm / embedding / decoder), and its deviation from the
+    fp32 path on the same batch."""
+    B = args.batch
+    with torch.no_grad():
+        y32 = step(devb[0]).clone()
+        model.set_eval_dtype("bf16")
+        try:
+            y16 = step(devb[0]).clone()
+            rate = graphed_rate(step, devb[:4], B, max(args.steps, 10))
+            full = device_batches(shape, B, dev, n=2, seed=5000, all_valid=True)
+            rate_full = graphed_rate(step, full, B, max(3, args.steps // 2))
+        finally:
+            model.set_eval_dtype("fp32")
+    dp = float((y16 - y32).abs().max().item())
+    hr32 = float(((y32[:, 1:] > y32[:, :1]).sum(1) < 10).double().mean().item())
+    hr16 = float(((y16[:, 1:] > y16[:, :1]).sum(1) < 10).double().mean().item())
+    fl = fwd_flops_per_user(shape, args.decoder)
+    return {"value": rate, "unit": "users/s", "dtype": "bf16 operands, fp32 accumulate / softmax / LayerNorm / decoder",
+            "path": "packed-rows pipeline (csrc/rows_bf16.cuh), whole step as one CUDA graph",
+            "max_abs_prob_diff_vs_fp32_path": dp, "hr10_fp32": hr32, "hr10_bf16": hr16,
+            "algorithmic_tflops": fl * rate / 1e12, "frac_of_bf16_peak": fl * rate / 1e12 / pk["bf16_tflops_sustained"],
+            "all_valid_profiles": {"value": rate_full, "unit": "users/s",
+                                   "algorithmic_tflops": fl * rate_full / 1e12,
+                                   "frac_of_bf16_peak": fl * rate_full / 1e12 / pk["bf16_tflops_sustained"]}}
+
+
+def time_sweep(shape, args, dev, table):
+    """BASELINE configs[4]: maxlen 50 / 100 / 200 x batch 128 .. 8192 on this GPU, UNFILTERED synthetic users (the
+    length law produces users with more than 64 valid positions at L >= 100: nothing is dropped or re-routed on the
+    host), fp32 and bf16, plus every position valid at maxlen 100."""
+    import dataclasses
+
+    from carca_replication_b200 import synth
+
+    out = {"unit": "users/s", "rows": []}
+    n = max(args.steps, 10)
+    for L in (50, 100, 200):
+        shp = dataclasses.replace(shape, seq_len=L)
+        model = synth.build_model(shp, args.decoder, p=0.5).to(dev).eval()
+        model.embeds.set_attr_table(table)
+        acc4 = torch.zeros(4, dtype=torch.float64, device=dev)
+        step = eval_step_fn(model, acc4)
+        for B in (128, 1024, 8192):
+            bs = device_batches(shp, B, dev, n=4, seed=300 + L)
+            longest = int(max((b["p_x"] != 0).sum(1).max().item() for b in bs))
+            row = {"maxlen": L, "batch": B, "longest_profile": longest}
+            with torch.no_grad():
+                for dt in ("fp32", "bf16"):
+                    model.set_eval_dtype(dt)
+                    row[dt] = graphed_rate(step, bs, B, n)
+                    if dt == "fp32":
+                        row["fp32_path"] = model._fused_eval_mode((bs[0]["p_x"], None, bs[0]["p_c"]),
+                                                                  [(bs[0]["o_x"], None, bs[0]["o_c"])])
+                model.set_eval_dtype("fp32")
+            out["rows"].append(row)
+        if L == 100:
+            bs = device_batches(shp, 2048, dev, n=2, seed=77, all_valid=True)
+            with torch.no_grad():
+                row = {"maxlen": L, "batch": 2048, "all_valid": True}
+                for dt in ("fp32", "bf16"):
+                    model.set_eval_dtype(dt)
+                    row[dt] = graphed_rate(step, bs, 2048, max(3, n // 3))
+                model.set_eval_dtype("fp32")
+            out["rows"].append(row)
+    return out
+
+
+def time_men(args, dev, pk, rank=0, world=1):
+    """BASELINE configs[2]: Men-shaped CARCA (d = 256, 4 heads, 512-d dense attributes, 110,637 items), eval step
+    (forward + loss + HR@10 / NDCG@10), users sharded over the ranks (weak scaling, no data-path collective):
+    fp32 (packed rows, 3xTF32 GEMMs) and bf16 (tcgen05 kind::f16 pipeline), Beauty-like sparse profiles and every
+    position valid."""
+    from carca_replication_b200 import synth
+
+    shape = synth.MEN
+    B = args.men_batch
+    model = synth.build_model(shape, args.decoder, p=0.5).to(dev).eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape).to(dev))
+    acc4 = torch.zeros(4, dtype=torch.float64, device=dev)
+    step = eval_step_fn(model, acc4)
+    n = max(args.steps, 10)
+    out = {"unit": "users/s", "batch_per_gpu": B, "n_gpus": world, "scaling": "weak",
+           "workload": f"men-shaped eval: d={shape.d}, H={shape.n_heads}, A={shape.n_attrs} dense, {shape.n_items} items, "
+                       f"maxlen {shape.seq_len}, 1+{shape.n_targets - 1} candidates, decoder={args.decoder}"}
+    sparse = device_batches(shape, B, dev, n=4, seed=1000 * rank + 11)
+    full = device_batches(shape, B, dev, n=2, seed=1000 * rank + 22, all_valid=True)
+    rows_sparse = float(sum(((b["p_x"] != 0).sum() + (b["p_x"][:, -1] == 0).sum()).item() for b in sparse)) / len(sparse) / B
+    with torch.no_grad():
+        for dt in ("fp32", "bf16"):
+            model.set_eval_dtype(dt)
+            r_s = graphed_rate(step, sparse, B, n, world, dev)
+            r_f = graphed_rate(step, full, B, max(3, n // 3), world, dev)
+            fl_exec_s = fwd_flops_per_user(shape, args.decoder, rows=rows_sparse)
+            fl_all = fwd_flops_per_user(shape, args.decoder)
+            peak = pk["bf16_tflops_sustained"]
+            out[dt] = {"value": r_s, "all_valid_profiles": r_f,
+                       "algorithmic_tflops": fl_all * r_s / 1e12, "executed_tflops": fl_exec_s * r_s / 1e12,
+                       "all_valid_tflops": fl_all * r_f / 1e12, "all_valid_frac_of_bf16_peak": fl_all * r_f / 1e12 / peak / world}
+        model.set_eval_dtype("fp32")
+    out["value"] = out["bf16"]["value"]
+    out["valid_rows_per_user"] = rows_sparse
+    out["per_kernel_evidence"] = "profiles/r02/README.md (ncu: tensor-pipe utilisation of rows_gemm_kernel<256> per epilogue)"
+    return out
+
+
+def time_catalog_sharded(model, shape, args, dev, rank, world):
+    """BASELINE configs[3] at N GPUs: the item table sharded over the ranks in contiguous id ranges; every rank scores
+    ALL `--catalog-users` users against its shard, one all-reduce of the per-user rank counts (catalog.py)."""
+    import torch.distributed as dist
+
+    from carca_replication_b200 import catalog, synth
+
+    Bc = args.catalog_users
+    b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, Bc, seed=4242).items()}       # same users on every rank
+    prof = (b["p_x"], None, b["p_c"])
+    pos, ctx = b["o_x"][:, 0].contiguous(), b["o_c"][:, 0].contiguous()
+    ranks = catalog.catalog_ranks(model, prof, pos, ctx)
+    ref = catalog.catalog_ranks(model, prof, pos, ctx, shard=(1, shape.n_items), reduce=False)   # whole table, this rank
+    same = bool(torch.equal(ranks, ref))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    n = 3
+    for _ in range(n):
+        ranks = catalog.catalog_ranks(model, prof, pos, ctx)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": Bc / (ms * 1e-3), "unit": "users/s", "users": Bc, "items": shape.n_items - 1, "ms": ms, "n_gpus": world,
+            "scores_per_s": Bc * (shape.n_items - 1) / (ms * 1e-3), "sharded_equals_unsharded": same,
+            "scaling": "strong (the item table is split; every rank encodes all users)",
+            "collective": "one all-reduce of [users] int32 rank counts"}
+
 
 
 def time_catalog(model, shape, args, dev):

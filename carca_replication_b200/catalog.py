@@ -53,8 +53,12 @@ def score_items(model, profile, ctx_user: Tensor, item_lo: int, item_hi: int, ch
     model.eval()
     try:
         with torch.no_grad():
-            if model._fused_eval_applies((p_x, p_a, p_c), [(p_x, p_a, p_c)]):
+            mode = model._fused_eval_mode((p_x, p_a, p_c), [(p_x, p_a, p_c)])
+            if mode == "tc":
                 return fused.forward_catalog(model, profile, ctx_user, item_lo, n)
+            if mode is not None:        # packed-rows pipeline (long windows, d = 256, bf16): same catalog mode
+                return fused.forward_rows(model, profile, [], precision=mode[5:], cat_lo=item_lo, n_cand=n,
+                                          ctx_user=ctx_user)
             out = torch.empty((B, n), dtype=torch.float32, device=p_x.device)
             for lo in range(item_lo, item_hi, chunk):
                 hi = min(item_hi, lo + chunk)
@@ -67,9 +71,10 @@ def score_items(model, profile, ctx_user: Tensor, item_lo: int, item_hi: int, ch
 
 
 def catalog_ranks(model, profile, pos_item: Tensor, pos_ctx: Tensor, group=None,
-                  shard: Optional[Tuple[int, int]] = None, user_chunk: int = 2048) -> Tensor:
+                  shard: Optional[Tuple[int, int]] = None, user_chunk: int = 2048, reduce: bool = True) -> Tensor:
     """Rank (0 = best) of each user's positive item among ALL items, int32 [B] on every rank.
-    With torch.distributed initialised the item table is sharded over the group's ranks."""
+    With torch.distributed initialised the item table is sharded over the group's ranks (`shard` overrides this
+    rank's id range; `reduce=False` returns the local counts without the all-reduce)."""
     N.require_device(pos_item, pos_ctx)
     emb = model.embeds
     n_items = emb.items_embed.weight.shape[0]
@@ -97,7 +102,7 @@ def catalog_ranks(model, profile, pos_item: Tensor, pos_ctx: Tensor, group=None,
                        N.i32p(pos), int(lo), u1 - u0, hi - lo, N.stream())
     finally:
         model.train(was_training)
-    if world > 1:
+    if world > 1 and reduce:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)      # the one exchange of the path
     return counts
 
