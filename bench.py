@@ -391,34 +391,26 @@ def run_ours(args):
         # second stream before step i's kernels (the double buffering a pinned DataLoader with
         # non_blocking copies gives), and the caller reads the metrics back every step.
         copy_stream = torch.cuda.Stream(device=dev)
-        # every candidate of a user carries the positive's context (src/data.py:185): the host keeps one row per
-        # user and hands CARCA.forward an expanded [B,T,C] view of it, so the copies never cross PCIe
+        # What crosses PCIe per step is the PACKED batch (device_data.PackedEvalLayout): per-user offsets, candidate ids,
+        # one context row per user (every candidate carries the positive's context, src/data.py:185) and the (id,
+        # context) records of the VALID profile positions only — the windows are left-padded (src/data.py:112-113) and
+        # ~86 % padding at Beauty shape; y_true is the constant [1, 0, ..] row (src/data.py:189-190) and is not sent.
+        # The dense p_x / p_c the model takes are rebuilt by one kernel inside the step's graph.
+        from carca_replication_b200.device_data import PackedEvalLayout, pack_eval_batch, unpack_eval_batch
+
         T_ = devb[0]["o_x"].shape[1]
-        for hb in host:
-            hb["o_c"] = hb["o_c"][:, :1, :].contiguous()
-        # one pinned arena per host batch (what a collate_fn writing into a pinned buffer produces): a step's
-        # inputs cross PCIe as ONE copy; the tensors handed to the model are views into the device arena
-        layout, off = {}, 0
-        for k in names:
-            t = host[0][k]
-            layout[k] = (off, t.numel() * t.element_size(), t.dtype, tuple(t.shape))
-            off = (off + layout[k][1] + 255) // 256 * 256
-        h2d_bytes = off
-
-        def views(arena):
-            return {k: arena[o:o + nb].view(dt).view(shp) for k, (o, nb, dt, shp) in layout.items()}
-
-        host_arenas = []
-        for hb in host:
-            arena = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
-            for k, v in views(arena).items():
-                v.copy_(hb[k])
+        layout = PackedEvalLayout(B, shape.seq_len, T_, shape.n_ctx)
+        host_arenas, used = [], []
+        for hb in host:                  # the collate step: one pinned arena per host batch
+            arena = torch.empty(layout.capacity, dtype=torch.uint8).pin_memory()
+            used.append(pack_eval_batch(layout, arena, hb["p_x"], hb["p_c"], hb["o_x"], hb["o_c"]))
             host_arenas.append(arena)
+        h2d_bytes = int(sum(used) / len(used))
         NS = 3                                               # input slots: copies run up to two steps ahead
-        dev_arenas = [torch.empty(h2d_bytes, dtype=torch.uint8, device=dev) for _ in range(NS)]
-        for j, a_ in enumerate(dev_arenas):                  # valid ids in every slot before anything runs on it
-            a_.copy_(host_arenas[j % args.rotate])
-        slots = [views(a_) for a_ in dev_arenas]
+        dev_arenas = [torch.empty(layout.capacity, dtype=torch.uint8, device=dev) for _ in range(NS)]
+        for j, a_ in enumerate(dev_arenas):                  # valid contents in every slot before anything runs on it
+            a_[:used[j % args.rotate]].copy_(host_arenas[j % args.rotate][:used[j % args.rotate]])
+        slots = [unpack_eval_batch(layout, a_) for a_ in dev_arenas]
         ready = [torch.cuda.Event() for _ in range(NS)]
         freed = [torch.cuda.Event() for _ in range(NS)]
         # the step's result (hits, ndcg sum, users, loss sum) is read back every step; the host waits for the
@@ -427,22 +419,24 @@ def run_ours(args):
         landed = [torch.cuda.Event() for _ in range(NS)]
         results = []
         # the public API for this loop is GraphedEvalStep (carca_replication_b200/graph.py): evaluate()'s per-batch
-        # body (CARCA.forward + BinaryCrossEntropy + rank metrics + the D2H copy of the accumulators) captured once
-        # per input slot and replayed; --e2e-eager issues the same calls eagerly (~0.2 ms of host time per step)
+        # body (window unpack + CARCA.forward + BinaryCrossEntropy + rank metrics + the D2H copy of the accumulators)
+        # captured once per input slot and replayed; --e2e-eager issues the same calls eagerly
         ev_steps = None
         stats_dev = torch.zeros(4, dtype=torch.float64, device=dev)
         if not args.e2e_eager:
             from carca_replication_b200.graph import GraphedEvalStep
 
-            ev_steps = [GraphedEvalStep(model, dict(sl, o_c=sl["o_c"].expand(-1, T_, -1)), k=10, stats=stats_dev,
-                                        result=stats_host[j], static_inputs=True) for j, sl in enumerate(slots)]
+            ev_steps = [GraphedEvalStep(model, slots[j], k=10, stats=stats_dev, result=stats_host[j], static_inputs=True,
+                                        prologue=(lambda j=j: unpack_eval_batch(layout, dev_arenas[j], slots[j])))
+                        for j in range(NS)]
         stats = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(NS)]
 
         def upload(i):
             slot = i % NS
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[slot])          # the step that last used this slot is done
-                dev_arenas[slot].copy_(host_arenas[i % args.rotate], non_blocking=True)
+                n_ = used[i % args.rotate]
+                dev_arenas[slot][:n_].copy_(host_arenas[i % args.rotate][:n_], non_blocking=True)
                 ready[slot].record(copy_stream)
 
         def e2e_run(n):
@@ -459,8 +453,8 @@ def run_ours(args):
                     ev_steps[i % NS].replay()                # ends with the D2H copy of the accumulators
                     freed[i % NS].record(cur)
                 else:
-                    sl = slots[i % NS]
-                    step(dict(sl, o_c=sl["o_c"].expand(-1, T_, -1)))
+                    sl = unpack_eval_batch(layout, dev_arenas[i % NS], slots[i % NS])
+                    step(sl)
                     freed[i % NS].record(cur)
                     st = stats[i % NS]
                     st.copy_(acc4)
@@ -517,11 +511,14 @@ def run_ours(args):
                                                     "(CARCA.forward + loss + metrics on one rotated batch)"
                                                     if graphs is not None else "eager steps")),
         "e2e": {"value": e2e, "unit": "users/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,
+                "h2d_bytes_per_step_dense_tensors": layout.dense_bytes(),
                 "ms_per_step": ms_e2e / K, "launch": "eager calls" if args.e2e_eager else "GraphedEvalStep (one CUDA "
-                "graph replay per step)", "api": "CARCA.forward + BinaryCrossEntropy + rank metrics; per step one "
-                                                  "H2D copy of a pinned arena (ids, context, labels; issued up to two "
-                                                  "steps ahead on a second stream) and one D2H read of the accumulators "
-                                                  "(consumed by the host one step behind)"},
+                "graph replay per step)", "api": "device_data.unpack_eval_batch + CARCA.forward + BinaryCrossEntropy + "
+                                                  "rank metrics; per step one H2D copy of a pinned PACKED arena (per-user "
+                                                  "offsets, candidate ids, one context row per user, (id, context) of "
+                                                  "the valid profile positions; issued up to two steps ahead on a second "
+                                                  "stream) and one D2H read of the accumulators (consumed by the host one "
+                                                  "step behind)"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
         "ops_per_op_path": per_op_table,
         "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1], "host_numa": numa,

@@ -134,6 +134,7 @@ SIGNATURES = {
     "carca_adam_step": [P(AdamTensor), i32, f32, f32, f32, f32, f32, vp],
     "carca_build_eval_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, i32, i32, u64, vp],
     "carca_build_train_batch": [vp, vp, vp, vp, vp, P(Interactions), vp, i32, i32, i32, i32, u64, vp],
+    "carca_unpack_windows": [vp, vp, vp, vp, i32, i32, i32, vp],
     "carca_eval_plan_floats": [P(ModelParams)],
     "carca_eval_prepare": [vp, vp, P(ModelParams), P(AttrSource), vp],
     "carca_eval_forward": [vp, i64, i32, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, vp],

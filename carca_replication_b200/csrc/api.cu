@@ -913,6 +913,15 @@ int carca_build_train_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c, 
   return check_launch("build_train_batch");
 }
 
+int carca_unpack_windows(int32_t* p_x, float* p_c, const int32_t* offs, const float* rows, int B, int L, int C,
+                         void* stream) {
+  if (B <= 0 || L <= 0) return 0;
+  CARCA_REQUIRE(C >= 0 && C <= 64, "unpack_windows: C=%d outside 0..64", C);
+  auto k = unpack_windows_kernel;
+  CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll((long long)B * L, 256)), dim3(256), 0, S(stream), p_x, p_c, offs, rows, B, L, C);
+  return check_launch("unpack_windows");
+}
+
 // ------------------------------------------------------------------------------------ fused inference
 int64_t carca_eval_plan_floats(const carca_model_params* m) { return plan_layout(m).total; }
 

@@ -140,4 +140,27 @@ __global__ void __launch_bounds__(128) build_train_batch_kernel(int* __restrict_
   }
 }
 
+// Left-padded windows rebuilt on the device from their packed form (host -> device transfer diet): offs [B + 1] is
+// the exclusive scan of the users' valid lengths, rows [R, 1 + C] holds per valid position the item id (as int bits)
+// followed by its C context values, oldest first.  p_x [B, L] / p_c [B, L, C] get the window layout of
+// src/data.py:53-74,112-113 (padding on the left, zeros).
+__global__ void __launch_bounds__(256) unpack_windows_kernel(int* __restrict__ p_x, float* __restrict__ p_c,
+                                                             const int* __restrict__ offs, const float* __restrict__ rows,
+                                                             int B, int L, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * L) return;
+  const int u = (int)(i / L), pos = (int)(i % L);
+  const int o0 = offs[u], n = min(offs[u + 1] - o0, L);
+  const int j = pos - (L - n);
+  float* c = p_c + i * C;
+  if (j < 0) {
+    p_x[i] = 0;
+    for (int k = 0; k < C; ++k) c[k] = 0.f;
+    return;
+  }
+  const float* r = rows + (long long)(o0 + j) * (1 + C);
+  p_x[i] = __float_as_int(r[0]);
+  for (int k = 0; k < C; ++k) c[k] = r[1 + k];
+}
+
 }  // namespace carca

@@ -138,3 +138,73 @@ class DeviceLoader:
             else:
                 yield self.log.eval_batch(u, self.n_items, self.L, self.T, self.mode, self.test, seed)
         self.epoch += 1
+
+
+# ------------------------------------------------------------------------------- packed host -> device batches
+class PackedEvalLayout:
+    """Byte layout of one packed evaluate() batch inside a pinned host arena / its device mirror:
+
+        [ offs int32 [B + 1] | o_x int32 [B, T] | o_c_user fp32 [B, C] | rows fp32 [R, 1 + C] ]
+
+    `rows` comes last, so a batch occupies a PREFIX of the arena and one copy of `used_bytes(R)` bytes moves it.  What
+    is not sent: the padding of p_x / p_c (Beauty-shaped windows are ~86 % padding), the [B, T, C] copies of the
+    positive's context (src/data.py:185) and y_true, which is the constant row [1, 0, ..., 0] (src/data.py:189-190)."""
+
+    def __init__(self, B: int, L: int, T: int, C: int):
+        self.B, self.L, self.T, self.C = int(B), int(L), int(T), int(C)
+        al = lambda x: (x + 255) // 256 * 256                       # noqa: E731
+        self.o_offs = 0
+        self.o_ox = al(4 * (self.B + 1))
+        self.o_oc = al(self.o_ox + 4 * self.B * self.T)
+        self.o_rows = al(self.o_oc + 4 * self.B * self.C)
+        self.capacity = self.o_rows + 4 * self.B * self.L * (1 + self.C)
+
+    def used_bytes(self, n_rows: int) -> int:
+        return self.o_rows + 4 * int(n_rows) * (1 + self.C)
+
+    def dense_bytes(self) -> int:
+        """What the same batch takes as the reference loader's dense tensors (p_x, p_c, o_x, o_c, y_true)."""
+        return 4 * self.B * (self.L * (1 + self.C) + self.T * (2 + self.C))
+
+
+def pack_eval_batch(layout: PackedEvalLayout, arena: Tensor, p_x: Tensor, p_c: Tensor, o_x: Tensor, o_c: Tensor) -> int:
+    """Host side (a collate_fn's job): writes the batch into `arena` (uint8, ideally pinned) in PackedEvalLayout and
+    returns the bytes to copy.  p_x / p_c must be left-padded windows (what pad_profile builds, src/data.py:53-74);
+    o_c is [B, T, C] with the positive's context in every row, or [B, C]."""
+    B, L, T, Cn = layout.B, layout.L, layout.T, layout.C
+    valid = p_x != 0
+    lens = valid.sum(1)
+    if not bool((valid == (torch.arange(L).unsqueeze(0) >= (L - lens).unsqueeze(1))).all()):
+        raise ValueError("pack_eval_batch: windows must be left-padded (no padding between valid positions)")
+    offs = torch.zeros(B + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    R = int(offs[-1])
+    arena[layout.o_offs:layout.o_offs + 4 * (B + 1)].view(torch.int32).copy_(offs)
+    arena[layout.o_ox:layout.o_ox + 4 * B * T].view(torch.int32).view(B, T).copy_(o_x)
+    ocu = o_c[:, 0, :] if o_c.dim() == 3 else o_c
+    arena[layout.o_oc:layout.o_oc + 4 * B * Cn].view(torch.float32).view(B, Cn).copy_(ocu)
+    rows = arena[layout.o_rows:layout.o_rows + 4 * R * (1 + Cn)].view(torch.float32).view(R, 1 + Cn)
+    rows[:, 0].copy_(p_x[valid].to(torch.int32).view(torch.float32))
+    rows[:, 1:].copy_(p_c[valid])
+    return layout.used_bytes(R)
+
+
+def unpack_eval_batch(layout: PackedEvalLayout, dev_arena: Tensor, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    """Device side: the evaluate() batch as the tensors CARCA.forward / the metrics take (p_x, p_c rebuilt by one
+    kernel; o_x a view of the arena; o_c and y_true expanded views — nothing else is materialised).  `out` (from a
+    previous call) reuses the p_x / p_c buffers, so the call can sit inside a CUDA graph."""
+    B, L, T, Cn = layout.B, layout.L, layout.T, layout.C
+    N.require_device(dev_arena)
+    dev = dev_arena.device
+    offs = dev_arena[layout.o_offs:layout.o_offs + 4 * (B + 1)].view(torch.int32)
+    o_x = dev_arena[layout.o_ox:layout.o_ox + 4 * B * T].view(torch.int32).view(B, T)
+    o_cu = dev_arena[layout.o_oc:layout.o_oc + 4 * B * Cn].view(torch.float32).view(B, Cn)
+    rows = dev_arena[layout.o_rows:layout.capacity].view(torch.float32)
+    if out is None:
+        label = torch.zeros((1, T), dtype=torch.int32, device=dev)
+        label[0, 0] = 1
+        out = {"p_x": torch.empty((B, L), dtype=torch.int32, device=dev),
+               "p_c": torch.empty((B, L, Cn), dtype=torch.float32, device=dev),
+               "o_x": o_x, "o_c": o_cu.unsqueeze(1).expand(B, T, Cn), "y_true": label.expand(B, T)}
+    N.call("carca_unpack_windows", N.i32p(out["p_x"]), N.f32p(out["p_c"]), N.i32p(offs), N.f32p(rows), B, L, Cn, N.stream())
+    return out

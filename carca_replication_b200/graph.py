@@ -111,7 +111,7 @@ class GraphedEvalStep:
 
     def __init__(self, model, batch: Dict[str, Tensor], k: int = 10, stats: Optional[Tensor] = None,
                  result: Optional[Tensor] = None, static_inputs: bool = False,
-                 loss_fn: Optional[BinaryCrossEntropy] = None, warmup: int = 2):
+                 loss_fn: Optional[BinaryCrossEntropy] = None, warmup: int = 2, prologue=None):
         from . import ops
 
         if model.training:
@@ -126,6 +126,8 @@ class GraphedEvalStep:
         if result is not None and not (result.is_pinned() and result.dtype == torch.float64 and result.numel() == 4):
             raise ValueError("result must be a pinned float64[4] host tensor")
         self.result = result
+        self.prologue = prologue          # optional callable run at the start of every step, inside the graph (e.g.
+                                          # device_data.unpack_eval_batch rebuilding the windows from a packed arena)
         self._metrics = ops.eval_metrics_
         keep = self.stats.clone()
         # (windows longer than one 64-row bin run on the packed-rows pipeline, which has no per-user row limit and
@@ -151,6 +153,8 @@ class GraphedEvalStep:
 
     def _body(self) -> None:
         b = self.static
+        if self.prologue is not None:
+            self.prologue()
         y = self.model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
         if type(self.loss_fn) is BinaryCrossEntropy:       # loss + HR@k + NDCG@k in one launch
             self._metrics(self.stats, y, b["y_true"], b["o_x"], self.k)

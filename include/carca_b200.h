@@ -394,6 +394,14 @@ int carca_build_train_batch(int32_t* p_x, float* p_c, int32_t* o_x, float* o_c, 
                             const carca_interactions* log, const int32_t* users, int B, int L, int n_items, int test,
                             uint64_t seed, void* stream);
 
+/* Host -> device transfer diet for eval / train batches: the loader's windows are LEFT-padded (src/data.py:53-74,
+ * :112-113), so a batch of windows is fully described by the users' valid lengths and the valid positions' (id,
+ * context) records; Beauty-shaped windows are ~86 % padding.  offs [B + 1] = exclusive scan of the lengths,
+ * rows [R, 1 + C] = per valid position the id (int32 bits in a float slot) then its C context values, oldest first.
+ * Writes p_x [B, L] and p_c [B, L, C] exactly as the dense tensors the reference loader would have sent.            */
+int carca_unpack_windows(int32_t* p_x, float* p_c, const int32_t* offs, const float* rows, int B, int L, int C,
+                         void* stream);
+
 /* ------------------------------------------------------------------ whole-model inference */
 /* Every parameter of a CARCA model (src/carca.py:401-409) in its state_dict layout.
  * `blocks` is a HOST array of n_blocks entries; decoder_kind 0 = DotProduct, 1 = CrossAttentionBlock. */

@@ -111,3 +111,35 @@ def check_loader_in_evaluate(device):
     tl = DeviceLoader(log, n_items, L, T, "train", batch_size=4, shuffle=True, seed=5)
     n = sum(b[0].shape[0] for b in tl)
     assert n == tl.users.numel() == 10
+
+
+def check_packed_eval_batch(device):
+    """Host -> device transfer diet: pack_eval_batch / unpack_eval_batch reproduce the dense tensors of the batch
+    (left-padded windows, candidates, one context row per user, the constant label row) bit for bit."""
+    import torch
+
+    from carca_replication_b200 import synth
+    from carca_replication_b200.device_data import PackedEvalLayout, pack_eval_batch, unpack_eval_batch
+
+    shape = synth.TINY
+    b = synth.make_eval_batch(shape, 9, seed=12)
+    b["p_x"][3] = 0                                   # an empty window
+    b["p_c"][3] = 0.0
+    lay = PackedEvalLayout(9, shape.seq_len, shape.n_targets, shape.n_ctx)
+    arena = torch.zeros(lay.capacity, dtype=torch.uint8)
+    used = pack_eval_batch(lay, arena, b["p_x"], b["p_c"], b["o_x"], b["o_c"])
+    assert used <= lay.capacity and used < lay.dense_bytes()
+    dev_arena = torch.zeros(lay.capacity, dtype=torch.uint8, device=device)
+    dev_arena[:used].copy_(arena[:used])
+    out = unpack_eval_batch(lay, dev_arena)
+    for k in ("p_x", "p_c", "o_x", "o_c", "y_true"):
+        assert torch.equal(out[k].cpu(), b[k]), k
+    again = unpack_eval_batch(lay, dev_arena, out)     # reuses the buffers (what a captured graph replays)
+    assert again["p_x"].data_ptr() == out["p_x"].data_ptr()
+    holes = b["p_x"].clone()
+    holes[0, -2] = 0
+    try:
+        pack_eval_batch(lay, arena, holes, b["p_c"], b["o_x"], b["o_c"])
+        raise AssertionError("padding inside a window must be rejected")
+    except ValueError:
+        pass

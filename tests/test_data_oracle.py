@@ -36,3 +36,7 @@ def test_device_batches_match_reference_fixtures_emulated(emu_backend):
 
 def test_device_loader_drops_into_evaluate_emulated(emu_backend):
     S.check_loader_in_evaluate(emu_backend)
+
+
+def test_packed_eval_batch_roundtrip(emu_backend):
+    S.check_packed_eval_batch(emu_backend)

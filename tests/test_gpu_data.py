@@ -14,6 +14,10 @@ def test_sampled_negatives_are_uniform_over_free_items():
     S.check_negatives_are_uniform("cuda")
 
 
+def test_packed_eval_batch_roundtrip():
+    S.check_packed_eval_batch("cuda")
+
+
 def test_device_loader_drops_into_evaluate():
     S.check_loader_in_evaluate("cuda")
 

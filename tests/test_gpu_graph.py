@@ -180,9 +180,9 @@ def test_graphed_eval_step_matches_eager_evaluate_body(decoder):
         GraphedEvalStep(model.train(), batches[0])
 
 
-def test_graphed_eval_step_long_windows_checks_every_batch():
-    """maxlen 100: the captured step runs the packed tensor-core kernel; a batch with a user of more than 64 valid
-    positions is detected before the replay and runs eagerly on the per-op kernels, with the same accumulators."""
+def test_graphed_eval_step_long_windows_replays_every_batch():
+    """maxlen 100: the captured step runs the packed-rows pipeline, which has no per-user row limit — a batch whose
+    users have every position valid replays through the SAME graph (nothing is checked or re-routed on the host)."""
     import dataclasses
 
     import carca_replication_b200 as cb
@@ -198,7 +198,7 @@ def test_graphed_eval_step_long_windows_checks_every_batch():
     short = {k: v[keep][:24].contiguous() for k, v in b.items()}
     full = {k: v[:24].to(dev) for k, v in synth.make_eval_batch(shape, 24, seed=7, all_valid=True).items()}
     step = GraphedEvalStep(model, short, k=10)
-    assert step.long_windows and step.graph_is_fused
+    assert step.graph_is_fused and not step.long_windows
     ref = torch.zeros(4, dtype=torch.float64, device=dev)
     with torch.no_grad():
         for batch in (short, full, short):
