@@ -923,9 +923,22 @@ def time_catalog(model, shape, args, dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     r = ranks.double()
+    # the same ranks through the score-matrix path (scores written to HBM, then counted): the round-1 formulation
+    ref = catalog.catalog_ranks(model, prof, pos, ctx, use_tc=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        ref = catalog.catalog_ranks(model, prof, pos, ctx, use_tc=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_ref = e0.elapsed_time(e1) / n
     return {"value": Bc / (ms * 1e-3), "unit": "users/s", "users": Bc, "items": shape.n_items - 1, "ms": ms,
             "scores_per_s": Bc * (shape.n_items - 1) / (ms * 1e-3), "hr10": float((r < 10).double().mean().item()),
-            "mean_rank": float(r.mean().item())}
+            "mean_rank": float(r.mean().item()),
+            "path": "packed-rows fp32 encoder + tcgen05 catalog kernel (scores, softmax, sigmoid and rank comparison in "
+                    "the GEMM epilogue; no [users, items] score matrix)",
+            "score_matrix_path": {"scores_per_s": Bc * (shape.n_items - 1) / (ms_ref * 1e-3), "ms": ms_ref,
+                                  "ranks_equal": float((ranks == ref).double().mean().item())}}
 
 
 def time_device_pipeline(model, shape, args, dev):

@@ -147,6 +147,8 @@ SIGNATURES = {
     "carca_rows_scratch_bytes": [P(ModelParams), i32, i32],
     "carca_rows_eval_forward": [vp, i64, i32, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp,
                                 vp, vp],
+    "carca_rows_catalog_scratch_bytes": [P(ModelParams), i32, i32],
+    "carca_rows_catalog_counts": [vp, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
@@ -167,6 +169,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.carca_eval_scratch_bytes.restype = C.c_int64
     lib.carca_rows_plan_bytes.restype = C.c_int64
     lib.carca_rows_scratch_bytes.restype = C.c_int64
+    lib.carca_rows_catalog_scratch_bytes.restype = C.c_int64
     lib.carca_train_core_set_ticks.restype = None
     lib.carca_train_core_rows_ints.restype = C.c_int64
     lib.carca_train_core_saved_floats.restype = C.c_int64

@@ -71,10 +71,12 @@ def score_items(model, profile, ctx_user: Tensor, item_lo: int, item_hi: int, ch
 
 
 def catalog_ranks(model, profile, pos_item: Tensor, pos_ctx: Tensor, group=None,
-                  shard: Optional[Tuple[int, int]] = None, user_chunk: int = 2048, reduce: bool = True) -> Tensor:
+                  shard: Optional[Tuple[int, int]] = None, user_chunk: int = 2048, reduce: bool = True,
+                  use_tc: bool = True) -> Tensor:
     """Rank (0 = best) of each user's positive item among ALL items, int32 [B] on every rank.
     With torch.distributed initialised the item table is sharded over the group's ranks (`shard` overrides this
-    rank's id range; `reduce=False` returns the local counts without the all-reduce)."""
+    rank's id range; `reduce=False` returns the local counts without the all-reduce; `use_tc=False` keeps the
+    score-matrix path where the tensor-core catalog kernel would apply)."""
     N.require_device(pos_item, pos_ctx)
     emb = model.embeds
     n_items = emb.items_embed.weight.shape[0]
@@ -90,7 +92,18 @@ def catalog_ranks(model, profile, pos_item: Tensor, pos_ctx: Tensor, group=None,
     model.eval()
     try:
         with torch.no_grad():
-            for u0 in range(0, B, user_chunk):      # bounds the [users, shard] score matrix
+            from . import fused
+
+            if use_tc and model.use_fused_eval and N.is_device_tensor(p_x) and not isinstance(p_a, Tensor) and \
+                    (p_a is not None or emb.attr_table is not None) and hasattr(emb, "joint_embed") and \
+                    fused.catalog_tc_supported(model, p_x.shape[1], p_c.shape[-1]):
+                # tensor-core path: no [users, shard] score matrix at all
+                for u0 in range(0, B, 4096):
+                    u1 = min(B, u0 + 4096)
+                    fused.catalog_counts(model, (p_x[u0:u1], p_a, p_c[u0:u1]), pos_item[u0:u1], pos_ctx[u0:u1], lo, hi,
+                                         counts[u0:u1])
+                user_chunk = 0
+            for u0 in (range(0, B, user_chunk) if user_chunk else ()):      # bounds the [users, shard] score matrix
                 u1 = min(B, u0 + user_chunk)
                 prof = (p_x[u0:u1], p_a, p_c[u0:u1])
                 ctx = pos_ctx[u0:u1].contiguous()

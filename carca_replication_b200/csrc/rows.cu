@@ -3,11 +3,13 @@
 #include "../../include/carca_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm.cuh"
 #include "plan_layout.cuh"
 #include "rows_bf16.cuh"
+#include "catalog_tc.cuh"
 
 using namespace carca;
 
@@ -25,6 +27,11 @@ int carca_rows_prepare(void*, const float*, const carca_model_params*, void*) {
   return fail(-5, "rows pipeline: not available under the CPU emulator");
 }
 int64_t carca_rows_scratch_bytes(const carca_model_params*, int, int) { return 0; }
+int64_t carca_rows_catalog_scratch_bytes(const carca_model_params*, int, int) { return 0; }
+int carca_rows_catalog_counts(int32_t*, const void*, const float*, const carca_model_params*, const int32_t*, const float*,
+                              const float*, const int32_t*, int, int, int, int, int32_t*, void*, void*) {
+  return fail(-5, "rows pipeline: not available under the CPU emulator");
+}
 int carca_rows_eval_forward(float*, int64_t, int, const void*, const float*, const carca_model_params*, const int32_t*,
                             const float*, const int32_t*, const float*, int, int, int, int, int, int, int32_t*, void*, void*) {
   return fail(-5, "rows pipeline: not available under the CPU emulator");
@@ -246,10 +253,10 @@ int gemm_rows_f32(float* C, const float* A, const float* W, const float* bias, i
   return launch_gemm(g, st);
 }
 
+// encoder half: ids -> final LayerNorm rows (QN) and, for the cross-attention decoder, its key / value rows (Kf, Vf)
 template <int D, int H>
-int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
-                  const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
-                  int ctx_per_user, int cat_lo, unsigned char* scr, cudaStream_t st) {
+int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_params* m, const int32_t* p_x,
+                 const float* p_c, int B, int L, unsigned char* scr, cudaStream_t st) {
   const RowsPlan pl = rows_plan(m);
   const RowsScratch sc = rows_scratch(m, B, L);
   const int C = m->embed.n_ctx;
@@ -308,6 +315,28 @@ int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, co
       TRY(check_launch("rows_ln"));
     }
   }
+  if (m->decoder_kind == 1) {
+    TRY(gemm_rows_f32(Kf, QN, m->cross.wk, m->cross.bk, Mcap, D, n_rows, 0, nullptr, st));
+    TRY(gemm_rows_f32(Vf, QN, m->cross.wv, m->cross.bv, Mcap, D, n_rows, 0, nullptr, st));
+  }
+  (void)useg; (void)Qf;
+  return 0;
+}
+
+// decoder half over the (user, candidate) rows
+template <int D, int H>
+int decode_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
+                 const int32_t* o_x, const float* o_c, int B, int L, int T, int ctx_per_user, int cat_lo, unsigned char* scr,
+                 cudaStream_t st) {
+  const RowsPlan pl = rows_plan(m);
+  const RowsScratch sc = rows_scratch(m, B, L);
+  const int C = m->embed.n_ctx;
+  int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
+  int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
+  float* QN = reinterpret_cast<float*>(scr + sc.slot[1]);
+  float* Kf = reinterpret_cast<float*>(scr + sc.slot[4]);
+  float* Vf = reinterpret_cast<float*>(scr + sc.slot[5]);
+  const float* Mc = reinterpret_cast<const float*>(plan + pl.mc);
   rows::DecodeArgs d;
   memset(&d, 0, sizeof(d));
   d.useg = useg; d.row_src = row_src; d.o_x = o_x; d.o_c = o_c;
@@ -318,8 +347,6 @@ int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, co
   const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
-    TRY(gemm_rows_f32(Kf, QN, m->cross.wk, m->cross.bk, Mcap, D, n_rows, 0, nullptr, st));
-    TRY(gemm_rows_f32(Vf, QN, m->cross.wv, m->cross.bv, Mcap, D, n_rows, 0, nullptr, st));
     d.Kd = Kf; d.Vd = Vf; d.wf = m->cross.wf;
     d.McQ = reinterpret_cast<const float*>(plan + pl.mcq);
     d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
@@ -336,6 +363,108 @@ int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, co
     TRY(check_launch("rows_decode_dot"));
   }
   return 0;
+}
+
+template <int D, int H>
+int forward_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
+                  const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
+                  int ctx_per_user, int cat_lo, unsigned char* scr, cudaStream_t st) {
+  TRY((encode_f32_t<D, H>(plan, Tf, m, p_x, p_c, B, L, scr, st)));
+  return decode_f32_t<D, H>(y, ldy, col0, plan, Tf, m, o_x, o_c, B, L, T, ctx_per_user, cat_lo, scr, st);
+}
+
+// ---- full-catalog rank counts on the tensor cores (catalog_tc.cuh), d = 64
+struct CatScratch {
+  long long ucol, cw, ypos, meta, bt, total;
+  long long gmax;
+};
+CatScratch cat_scratch(const carca_model_params* m, int B, int L) {
+  CatScratch c;
+  const long long base = rows_scratch(m, B, L).total;
+  c.gmax = m->decoder_kind == 1 ? 2ll * B * L / cat::CT + B / 64 + 2 : (B + cat::CT - 1) / cat::CT;
+  c.ucol = base;
+  c.cw = align256(c.ucol + 4ll * B);
+  c.ypos = align256(c.cw + 4ll * B);
+  c.meta = align256(c.ypos + 4ll * B);
+  c.bt = align256(c.meta + c.gmax * cat::META_WORDS * 4ll);
+  c.total = align256(c.bt + c.gmax * cat::GROUP_FLOATS * 4ll);
+  return c;
+}
+
+template <int H>
+int catalog_counts_t(int32_t* counts, const unsigned char* plan, const float* Tf, const carca_model_params* m,
+                     const int32_t* p_x, const float* p_c, const float* ctx_user, const int32_t* pos_item, int item_lo,
+                     int n_shard, int B, int L, int32_t* status, unsigned char* scr, cudaStream_t st) {
+  constexpr int D = 64;
+  const RowsPlan pl = rows_plan(m);
+  const RowsScratch sc = rows_scratch(m, B, L);
+  const CatScratch cs = cat_scratch(m, B, L);
+  const int C = m->embed.n_ctx;
+  const bool ca = m->decoder_kind == 1;
+  TRY((encode_f32_t<D, H>(plan, Tf, m, p_x, p_c, B, L, scr, st)));
+  int* counters = reinterpret_cast<int*>(scr + sc.counters);     // [0] rows, [1] column groups
+  float* y_pos = reinterpret_cast<float*>(scr + cs.ypos);
+  // the positive's own probability, by the same decoder arithmetic as the per-candidate path
+  TRY((decode_f32_t<D, H>(y_pos, 1, 0, plan, Tf, m, pos_item, ctx_user, B, L, 1, 1, 0, scr, st)));
+  int* ucol = reinterpret_cast<int*>(scr + cs.ucol);
+  float* meta = reinterpret_cast<float*>(scr + cs.meta);
+  float* Bt = reinterpret_cast<float*>(scr + cs.bt);
+  cat::FillArgs f;
+  memset(&f, 0, sizeof(f));
+  f.Bt = Bt; f.meta = meta; f.ucol = ucol; f.useg = reinterpret_cast<const int2*>(scr + sc.useg);
+  f.row_src = reinterpret_cast<const int*>(scr + sc.row_src); f.n_rows = counters;
+  f.Kd = reinterpret_cast<const float*>(scr + sc.slot[4]); f.Vd = reinterpret_cast<const float*>(scr + sc.slot[5]);
+  f.wf = m->cross.wf; f.McQ = reinterpret_cast<const float*>(plan + pl.mcq); f.ctx_user = ctx_user;
+  f.PE = reinterpret_cast<const float*>(scr + sc.slot[1]); f.Mc = reinterpret_cast<const float*>(plan + pl.mc);
+  f.mcw = reinterpret_cast<const float*>(plan + pl.mcw); f.y_pos = y_pos; f.pos_item = pos_item;
+  f.B = B; f.C = C; f.sc = 1.4426950408889634f / sqrtf((float)(D / H));
+  {
+    auto k = cat::cat_clear_meta_kernel;
+    const long long n = cs.gmax * cat::CT;
+    CARCA_LAUNCH(k, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, st, meta, n);
+    TRY(check_launch("cat_clear_meta"));
+  }
+  if (ca) {
+    auto ka = cat::cat_assign_kernel;
+    CARCA_LAUNCH(ka, dim3(ceil_div(B, 64)), dim3(32), 0, st, ucol, counters + 1, f.useg, B);
+    TRY(check_launch("cat_assign"));
+    auto kf = cat::cat_fill_ca_kernel;
+    const long long rows_cap = (long long)B * L;
+    CARCA_LAUNCH(kf, dim3((unsigned)ceil_div_ll(rows_cap * 32, 256)), dim3(256), 0, st, f);
+    TRY(check_launch("cat_fill_ca"));
+  } else {
+    f.n_groups_out = counters + 1;
+    auto kf = cat::cat_fill_dot_kernel;
+    CARCA_LAUNCH(kf, dim3((unsigned)ceil_div_ll((long long)B * 32, 256)), dim3(256), 0, st, f);
+    TRY(check_launch("cat_fill_dot"));
+  }
+  cat::CatArgs a;
+  memset(&a, 0, sizeof(a));
+  a.TA = ca ? reinterpret_cast<const float*>(plan + pl.tq) : Tf;
+  a.tw = reinterpret_cast<const float*>(plan + pl.tw);
+  a.Bt = Bt; a.meta = meta; a.n_groups = counters + 1;
+  a.counts = counts;
+  a.dbf = m->cross.bf;
+  a.item_lo = item_lo; a.n_items = n_shard; a.residual_ca = m->residual_ca; a.decoder = m->decoder_kind;
+  a.status = status;
+  const int n_tiles = ceil_div(n_shard, cat::CT);
+  a.parts = max(1, min(16, ceil_div(148 * 6, n_tiles)));
+  if (const char* e = getenv("CARCA_CAT_PARTS")) a.parts = max(1, atoi(e));
+  const size_t smem = sizeof(cat::CatSmem);
+  if (getenv("CARCA_CAT_SKIP")) return 0;
+  if (const char* e = getenv("CARCA_CAT_DBG")) a.dbg = reinterpret_cast<volatile int*>(strtoull(e, nullptr, 10));
+  if (ca) {
+    auto k = cat::catalog_tc_kernel<1>;
+    static bool set1 = false;
+    if (!set1) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set1 = true; }
+    CARCA_LAUNCH(k, dim3(n_tiles * a.parts), dim3(cat::CAT_THREADS), smem, st, a);
+  } else {
+    auto k = cat::catalog_tc_kernel<0>;
+    static bool set0 = false;
+    if (!set0) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set0 = true; }
+    CARCA_LAUNCH(k, dim3(n_tiles * a.parts), dim3(cat::CAT_THREADS), smem, st, a);
+  }
+  return check_launch("catalog_tc");
 }
 
 }  // namespace
@@ -398,6 +527,29 @@ int carca_rows_prepare(void* plan_v, const float* plan_f32, const carca_model_pa
 }
 
 int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L) { return rows_scratch(m, B, L).total; }
+
+int64_t carca_rows_catalog_scratch_bytes(const carca_model_params* m, int B, int L) { return cat_scratch(m, B, L).total; }
+
+int carca_rows_catalog_counts(int32_t* counts, const void* plan, const float* plan_f32, const carca_model_params* m,
+                              const int32_t* p_x, const float* p_c, const float* ctx_user, const int32_t* pos_item,
+                              int item_lo, int n_shard, int B, int L, int32_t* status, void* scratch, void* stream) {
+  const int d = m->embed.d, H = m->n_heads;
+  CARCA_REQUIRE(d == 64 && rows_shape_ok_f32(m) && L >= 1 && L <= cat::CT,
+                "rows_catalog_counts: needs d = 64, L <= 128, C <= 8 (got d=%d L=%d C=%d)", d, L, m->embed.n_ctx);
+  CARCA_REQUIRE(m->decoder_kind == 0 || H == 2, "rows_catalog_counts: the cross-attention decoder needs 2 heads (got %d)", H);
+  CARCA_REQUIRE(status != nullptr && scratch != nullptr, "rows_catalog_counts: status and scratch are required");
+  if (m->embed.pos) CARCA_REQUIRE(L <= m->embed.pos_len, "rows_catalog_counts: sequence length %d > positional table %d", L,
+                                  m->embed.pos_len);
+  if (B <= 0 || n_shard <= 0) return 0;
+  const unsigned char* pl = reinterpret_cast<const unsigned char*>(plan);
+  unsigned char* scr = reinterpret_cast<unsigned char*>(scratch);
+  const float* Tf = plan_f32 + plan_layout(m).tfold;
+  cudaStream_t st = S(stream);
+  if (H == 1) return catalog_counts_t<1>(counts, pl, Tf, m, p_x, p_c, ctx_user, pos_item, item_lo, n_shard, B, L, status, scr, st);
+  if (H == 2) return catalog_counts_t<2>(counts, pl, Tf, m, p_x, p_c, ctx_user, pos_item, item_lo, n_shard, B, L, status, scr, st);
+  if (H == 4) return catalog_counts_t<4>(counts, pl, Tf, m, p_x, p_c, ctx_user, pos_item, item_lo, n_shard, B, L, status, scr, st);
+  return fail(-4, "rows_catalog_counts: unsupported head count %d", H);
+}
 
 int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, const float* plan_f32,
                             const carca_model_params* m, const int32_t* p_x, const float* p_c, const int32_t* o_x,

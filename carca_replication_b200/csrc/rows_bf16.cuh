@@ -432,9 +432,18 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
       : "memory");
 }
-__device__ __forceinline__ bool wait_or_flag(uint64_t* bar, uint32_t parity, int* status) {
-  if (umma::mbar_wait(bar, parity, 20000000)) return true;
-  atomicOr(status, 2);
+// wait bounded in TIME (a failed mbarrier.try_wait may itself suspend for a while, so a spin COUNT bounds nothing):
+// on a timeout (~0.25 s) the caller's bit is set in the status word and the role stops — never a hang
+__device__ __forceinline__ bool wait_or_flag(uint64_t* bar, uint32_t parity, int* status, int bit = 2) {
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (umma::mbar_try(bar, parity)) return true;
+    if (clock64() - t0 > 500000000ll) break;
+  }
+  atomicOr(status, bit);
   return false;
 }
 

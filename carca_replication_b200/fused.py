@@ -370,3 +370,40 @@ def forward_rows(model, profile, targets: Sequence, precision: str = "bf16", cat
            {"bf16": 0, "fp32": 1}[precision], N.i32p(ent.status), _rows_scratch(ent, B, L, p_x.device).data_ptr(),
            N.stream())
     return y
+
+
+def catalog_tc_supported(model, seq_len: int, n_ctx: int) -> bool:
+    """Tensor-core full-catalog kernel (csrc/catalog_tc.cuh): d = 64, L <= 128, fp32, dot decoder or two-head
+    cross-attention."""
+    from . import carca as M
+
+    if not rows_supported(model, seq_len, n_ctx, "fp32") or model.embeds.d != 64 or seq_len > 128:
+        return False
+    if model.eval_dtype != "fp32" or N.is_emulated():
+        return False
+    dec = model.decoder
+    return isinstance(dec, M.DotProduct) or dec.attn.H == 2
+
+
+_cat_scratch_cache: dict = {}
+
+
+def catalog_counts(model, profile, pos_item: Tensor, pos_ctx: Tensor, item_lo: int, item_hi: int, counts: Tensor) -> None:
+    """counts[b] += items of [item_lo, item_hi) ranked before user b's positive (carca_rows_catalog_counts): encoder on
+    the packed-rows fp32 pipeline, scores + softmax + sigmoid + comparison in one tcgen05 kernel, no score matrix."""
+    p_x, p_a, p_c = profile
+    table = p_a if isinstance(p_a, ItemAttrTable) else model.embeds.attr_table
+    N.require_device(p_x, p_c, pos_item, pos_ctx, counts)
+    p_x, p_c, pos_item, pos_ctx = as_ids(p_x), as_f32(p_c), as_ids(pos_item), as_f32(pos_ctx)
+    B, L = p_x.shape
+    ent = rows_plan(model, table, p_c.shape[-1])
+    key = (str(p_x.device), B, L)
+    buf = _cat_scratch_cache.get(key)
+    if buf is None:
+        if len(_cat_scratch_cache) > 4:
+            _cat_scratch_cache.clear()
+        nbytes = int(N.lib().carca_rows_catalog_scratch_bytes(C.byref(ent.m), B, L))
+        buf = _cat_scratch_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=p_x.device)
+    N.call("carca_rows_catalog_counts", N.i32p(counts), ent.rows.data_ptr(), N.f32p(ent.plan), C.byref(ent.m), N.i32p(p_x),
+           N.f32p(p_c), N.f32p(pos_ctx), N.i32p(pos_item), int(item_lo), int(item_hi - item_lo), B, L, N.i32p(ent.status),
+           buf.data_ptr(), N.stream())

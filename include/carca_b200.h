@@ -497,6 +497,17 @@ int carca_rows_eval_forward(float* y, int64_t ldy, int col0, const void* plan, c
                             const float* o_c, int B, int L, int T, int ctx_per_user, int cat_lo, int precision,
                             int32_t* status, void* scratch, void* stream);
 
+/* Full-catalog rank counts on the tensor cores (csrc/catalog_tc.cuh; d = 64, L <= 128, dot decoder or two-head
+ * cross-attention): counts[b] += number of items of the shard [item_lo, item_lo + n_shard) that a stable descending
+ * sort of the user's scores places before the positive pos_item[b] (same rule as carca_catalog_rank_count), computed
+ * as a 3xTF32 tcgen05 GEMM between the folded item table and the users' packed key / profile vectors with the softmax,
+ * sigmoid and comparison in its epilogue — the [B, n_shard] score matrix is never written.  ctx_user [B, C] is the
+ * context every candidate of the user carries (src/data.py:185).  counts must be zeroed by the caller.              */
+int64_t carca_rows_catalog_scratch_bytes(const carca_model_params* m, int B, int L);
+int carca_rows_catalog_counts(int32_t* counts, const void* plan, const float* plan_f32, const carca_model_params* m,
+                              const int32_t* p_x, const float* p_c, const float* ctx_user, const int32_t* pos_item,
+                              int item_lo, int n_shard, int B, int L, int32_t* status, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ full-catalog scoring */
 /* Scores every item of the contiguous id range [item_lo, item_lo + n_cand) (an item-table shard)
  * for every user: y[b, col0 + j] = CARCA.forward(profile_b, [(item_lo + j, ., ctx_user_b)]) in eval

@@ -52,3 +52,38 @@ def test_expanded_candidate_context_is_read_per_user():
 
     # same scores; the per-user context term is summed in a different order (cvec first), hence not bit-equal
     assert rel_err(y_exp.cpu().numpy(), y_dense.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+@pytest.mark.parametrize("L", [50, 100])
+def test_tensor_core_catalog_counts_equal_the_score_matrix_path(decoder, L):
+    """carca_rows_catalog_counts (tcgen05 scores + softmax + comparison, no score matrix) against the score-matrix path
+    (scores written, then carca_catalog_rank_count) on an item shard that is not tile-aligned, users with empty and
+    full windows included; ranks may differ only where another item ties the positive within fp32 noise."""
+    import dataclasses
+
+    import numpy as np
+
+    from carca_replication_b200 import catalog, synth
+
+    shape = dataclasses.replace(synth.BEAUTY, n_items=7001, n_attrs=200, seq_len=L)
+    model = synth.build_model(shape, decoder, seed=4).to("cuda").eval()
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=4).to("cuda"))
+    b = synth.make_eval_batch(shape, 300, seed=4)
+    full = synth.make_eval_batch(shape, 300, seed=5, all_valid=True)
+    b["p_x"][:3], b["p_c"][:3] = full["p_x"][:3], full["p_c"][:3]     # every position valid
+    b["p_x"][3], b["p_c"][3] = 0, 0.0                                   # an empty window
+    b = {k: v.to("cuda") for k, v in b.items()}
+    prof = (b["p_x"], None, b["p_c"])
+    pos, ctx = b["o_x"][:, 0].contiguous(), b["o_c"][:, 0].contiguous()
+    for shard in ((1, 7001), (1234, 5000)):
+        tc = catalog.catalog_ranks(model, prof, pos, ctx, shard=shard, reduce=False)
+        ref = catalog.catalog_ranks(model, prof, pos, ctx, shard=shard, reduce=False, use_tc=False)
+        y = catalog.score_items(model, prof, ctx, shard[0], shard[1]).cpu().numpy()
+        with torch.no_grad():
+            y_pos = model.forward(prof, [(pos.unsqueeze(1), None, ctx.unsqueeze(1))])[:, 0].cpu().numpy()
+        got, want = tc.cpu().numpy(), ref.cpu().numpy()
+        for bi in np.nonzero(got != want)[0]:
+            near = int(np.sum(np.abs(y[bi] - y_pos[bi]) <= 4e-6 * abs(y_pos[bi])))
+            assert abs(int(got[bi]) - int(want[bi])) <= near, (shard, bi, got[bi], want[bi], near)
+        assert (got != want).mean() < 0.05
