@@ -73,10 +73,17 @@ __global__ void __launch_bounds__(32) cat_assign_kernel(int* __restrict__ ucol, 
   for (int u = u0; u < u1; ++u) ucol[u] += base * CT;
 }
 
-// user plane of every group <- -1 (unused column)
+constexpr float kMasked = -1.0e30f;   // context term of a masked / unused column: its softmax weight underflows to 0
+// every column starts as unused: user -1, masked in both heads, zero value fold
 __global__ void __launch_bounds__(256) cat_clear_meta_kernel(float* __restrict__ meta, long long n_cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_cols) meta[(i / CT) * META_WORDS + MP_USER * CT + (i % CT)] = __int_as_float(-1);
+  if (i >= n_cols) return;
+  float* mp = meta + (i / CT) * META_WORDS + (i % CT);
+  mp[MP_USER * CT] = __int_as_float(-1);
+  mp[MP_KC0 * CT] = kMasked;
+  mp[MP_KC1 * CT] = kMasked;
+  mp[MP_U0 * CT] = 0.f;
+  mp[MP_U1 * CT] = 0.f;
 }
 
 struct FillArgs {
@@ -147,8 +154,8 @@ __global__ void __launch_bounds__(256) cat_fill_ca_kernel(const FillArgs a) {
     const bool pad = src < 0;                    // position L-1 of a short window: a padding key (masked)
     const bool last = j == min(sg.y, CT) - 1;
     mp[MP_USER * CT] = __int_as_float(u | (last ? (1 << 30) : 0));
-    mp[MP_KC0 * CT] = pad ? -INFINITY : kc * a.sc;
-    mp[MP_KC1 * CT] = pad ? -INFINITY : kc1 * a.sc;
+    mp[MP_KC0 * CT] = pad ? kMasked : kc * a.sc;
+    mp[MP_KC1 * CT] = pad ? kMasked : kc1 * a.sc;
     mp[MP_U0 * CT] = uu;
     mp[MP_U1 * CT] = u1;
     if (last) {
@@ -310,41 +317,46 @@ __global__ void __launch_bounds__(CAT_THREADS, 1) catalog_tc_kernel(const CatArg
       umma::fence_after_sync();
       const uint32_t tb = tmem0 + ((uint32_t)(32 * quarter) << 16) + st * 256;
       const float4* mt = reinterpret_cast<const float4*>(s.meta[st]);
-      float m0 = -INFINITY, z0 = 0.f, d0 = 0.f, m1 = -INFINITY, z1 = 0.f, d1 = 0.f;
+      // running softmax state of the open user, per head.  Masked / unused columns carry kc = -1e30: their weight
+      // underflows to exactly 0 as soon as a real key has been seen, and a user with no real key at all keeps
+      // m <= -1e29, which the finalisation turns into the all-masked attention row 0 (src/carca.py:256) — so the
+      // per-column math needs no branch; the only (warp-uniform) branch is the user's last column.
+      float m0 = kMasked, z0 = 0.f, d0 = 0.f, m1 = kMasked, z1 = 0.f, d1 = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < CT; c0 += 32) {
-        float v0[32], v1[32];
-        umma::tmem_ld_1x32(tb + c0, v0);
-        if (DEC == 1) umma::tmem_ld_1x32(tb + CT + c0, v1);
+      for (int c0 = 0; c0 < CT; c0 += 16) {
+        float v0[16], v1[16];
+        umma::tmem_ld_1x16(tb + c0, v0);
+        if (DEC == 1) umma::tmem_ld_1x16(tb + CT + c0, v1);
 #pragma unroll
-        for (int e4 = 0; e4 < 32; e4 += 4) {
-          // metadata of 4 columns (the same for every thread: broadcast reads)
-          const int q4 = (c0 + e4) / 4;
+        for (int e4 = 0; e4 < 16; e4 += 4) {
+          const int q4 = (c0 + e4) / 4;                    // metadata of 4 columns: broadcast reads
           const float4 fu = mt[MP_USER * (CT / 4) + q4], fk0 = mt[MP_KC0 * (CT / 4) + q4];
-          const float4 fk1 = mt[MP_KC1 * (CT / 4) + q4], fa0 = mt[MP_U0 * (CT / 4) + q4], fa1 = mt[MP_U1 * (CT / 4) + q4];
           const float uu[4] = {fu.x, fu.y, fu.z, fu.w}, k0[4] = {fk0.x, fk0.y, fk0.z, fk0.w};
-          const float k1[4] = {fk1.x, fk1.y, fk1.z, fk1.w}, a0[4] = {fa0.x, fa0.y, fa0.z, fa0.w};
-          const float a1[4] = {fa1.x, fa1.y, fa1.z, fa1.w};
+          float k1[4], a0[4], a1[4];
+          if (DEC == 1) {
+            const float4 fk1 = mt[MP_KC1 * (CT / 4) + q4], fa0 = mt[MP_U0 * (CT / 4) + q4], fa1 = mt[MP_U1 * (CT / 4) + q4];
+            k1[0] = fk1.x; k1[1] = fk1.y; k1[2] = fk1.z; k1[3] = fk1.w;
+            a0[0] = fa0.x; a0[1] = fa0.y; a0[2] = fa0.z; a0[3] = fa0.w;
+            a1[0] = fa1.x; a1[1] = fa1.y; a1[2] = fa1.z; a1[3] = fa1.w;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int e = e4 + q;
             const int uw = __float_as_int(uu[q]);
-            if (uw < 0) continue;                            // unused column (warp-uniform: metadata is per column)
             float logit;
             if (DEC == 1) {
-              if (k0[q] > -INFINITY) {                       // a padding key is masked (src/carca.py:246-251)
-                const float s0 = v0[e] + k0[q], s1 = v1[e] + k1[q];
-                const float n0 = fmaxf(m0, s0), n1 = fmaxf(m1, s1);
-                const float c0f = rows::ex2f(m0 - n0), p0 = rows::ex2f(s0 - n0);
-                const float c1f = rows::ex2f(m1 - n1), p1 = rows::ex2f(s1 - n1);
-                z0 = fmaf(z0, c0f, p0); d0 = fmaf(d0, c0f, p0 * a0[q]); m0 = n0;
-                z1 = fmaf(z1, c1f, p1); d1 = fmaf(d1, c1f, p1 * a1[q]); m1 = n1;
-              }
-              if (!(uw & (1 << 30))) continue;
-              logit = (z0 > 0.f ? d0 / z0 : 0.f) + (z1 > 0.f ? d1 / z1 : 0.f) + bfv;
+              const float s0 = v0[e] + k0[q], s1 = v1[e] + k1[q];
+              const float n0 = fmaxf(m0, s0), n1 = fmaxf(m1, s1);
+              const float c0f = rows::ex2f(m0 - n0), p0 = rows::ex2f(s0 - n0);
+              const float c1f = rows::ex2f(m1 - n1), p1 = rows::ex2f(s1 - n1);
+              z0 = fmaf(z0, c0f, p0); d0 = fmaf(d0, c0f, p0 * a0[q]); m0 = n0;
+              z1 = fmaf(z1, c1f, p1); d1 = fmaf(d1, c1f, p1 * a1[q]); m1 = n1;
+              if (uw < (1 << 30)) continue;                  // not a user's last column (unused columns: uw = -1)
+              logit = (m0 > -1.0e29f ? d0 / z0 : 0.f) + (m1 > -1.0e29f ? d1 / z1 : 0.f) + bfv;
               if (a.residual_ca) logit += twv + s.meta[st][MP_CW * CT + c0 + e];
-              m0 = m1 = -INFINITY; z0 = z1 = d0 = d1 = 0.f;
+              m0 = m1 = kMasked; z0 = z1 = d0 = d1 = 0.f;
             } else {
+              if (uw < 0) continue;
               logit = v0[e] + k0[q];
             }
             const float y = 1.0f / (1.0f + expf(-logit));
