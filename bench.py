@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-catalog", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the bf16 / sweep / Men sections")
-    ap.add_argument("--men-batch", type=int, default=2048)
+    ap.add_argument("--men-batch", type=int, default=8192)
     ap.add_argument("--catalog-users", type=int, default=1024)
     ap.add_argument("--rotate", type=int, default=8, help="distinct input batches cycled through")
     ap.add_argument("--e2e-eager", action="store_true",
