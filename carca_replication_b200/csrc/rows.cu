@@ -46,7 +46,7 @@ inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
 // byte offsets of the bf16 plan
 struct RowsPlan {
-  long long mc, w, dw, tq, tw, mcq, mcw, total;
+  long long mc, w, dw, tq, tw, mcq, mcw, tqb, total;
 };
 RowsPlan rows_plan(const carca_model_params* m) {
   RowsPlan p;
@@ -59,7 +59,8 @@ RowsPlan rows_plan(const carca_model_params* m) {
   p.tw = align256(p.tq + (ca ? n * d * 4 : 0));
   p.mcq = align256(p.tw + (ca ? n * 4 : 0));
   p.mcw = align256(p.mcq + (ca ? d * 8 * 4 : 0));
-  p.total = align256(p.mcw + (ca ? 8 * 4 : 0));
+  p.tqb = align256(p.mcw + (ca ? 8 * 4 : 0));
+  p.total = align256(p.tqb + (ca ? n * d * 2 : 0));
   return p;
 }
 
@@ -221,8 +222,33 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     g.job[1].A = QA; g.job[1].W = dw + wsz; g.job[1].bias = m->cross.bv; g.job[1].epi = rows::EPI_VDOT;
     g.job[1].wf = m->cross.wf; g.job[1].U = U;
     TRY(launch_gemm_rows<D>(g, st));
-    d.Kd = S2; d.U = U; d.KM = KM;      // (the S2 buffer is free after the last block: it holds the fp32 keys)
     (void)Kb;
+    if (H <= 4 && !getenv("CARCA_ROWS_FFMA_DECODE")) {   // tensor-core decoder (rows_decode_tc_kernel)
+      rows::DecTcArgs t;
+      memset(&t, 0, sizeof(t));
+      t.TQb = reinterpret_cast<const bf16*>(plan + pl.tqb);
+      t.Kd = S2; t.U = U; t.KM = KM;
+      t.tw = reinterpret_cast<const float*>(plan + pl.tw);
+      t.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
+      t.dbf = m->cross.bf;
+      t.useg = useg; t.row_src = row_src; t.o_x = o_x; t.o_c = o_c;
+      t.oc_user = d.oc_user; t.oc_tgt = d.oc_tgt;
+      t.y = y; t.ldy = ldy; t.col0 = col0; t.B = B; t.T = T; t.C = C; t.cat_lo = cat_lo; t.residual_ca = m->residual_ca;
+      t.status = status;
+      auto k = rows::rows_decode_tc_kernel<D, (H <= 4 ? H : 1)>;
+      const size_t smem = sizeof(rows::DecTcSmem<D, (H <= 4 ? H : 1)>);
+      static bool set = false;
+      if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(-3, "rows_decode_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        set = true;
+      }
+      const long long work = (long long)B * ceil_div(T, 128);
+      const int per_sm = D == 256 ? 1 : 2;
+      CARCA_LAUNCH(k, dim3((unsigned)min(work, 148ll * per_sm)), dim3(rows::DT_THREADS), smem, st, t);
+      return check_launch("rows_decode_tc");
+    }
+    d.Kd = S2; d.U = U; d.KM = KM;      // (the S2 buffer is free after the last block: it holds the fp32 keys)
     d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
     d.tw = reinterpret_cast<const float*>(plan + pl.tw);
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
@@ -509,6 +535,10 @@ int carca_rows_prepare(void* plan_v, const float* plan_f32, const carca_model_pa
       GemmArgs g = gemm_defaults(T, m->cross.wq, reinterpret_cast<float*>(plan + pl.tq), (int)n, d, d);
       g.bias = m->cross.bq;
       TRY(launch_gemm(g, st));
+      auto cvt = rows::to_bf16_kernel;
+      CARCA_LAUNCH(cvt, dim3((unsigned)ceil_div_ll(n * d, 1024)), dim3(256), 0, st, reinterpret_cast<bf16*>(plan + pl.tqb),
+                   reinterpret_cast<const float*>(plan + pl.tq), n * d);
+      TRY(check_launch("to_bf16(TQ)"));
     }
     {
       GemmArgs g = gemm_defaults(T, m->cross.wf, reinterpret_cast<float*>(plan + pl.tw), (int)n, 1, d);

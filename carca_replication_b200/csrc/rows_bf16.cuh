@@ -881,3 +881,277 @@ __global__ void __launch_bounds__(256) pack_weight_bf16_kernel(bf16* __restrict_
 }  // namespace rows
 }  // namespace carca
 #endif  // CARCA_EMU
+
+// ---------------------------------------------------------------------------------------------- tcgen05 decoder
+#ifndef CARCA_EMU
+namespace carca {
+namespace rows {
+
+// Cross-attention decoder of the bf16 flavour on the tensor cores (src/carca.py:338-347).  Work item = (user, tile of
+// 128 candidates).  Four producer warps (thread = candidate row) GATHER the candidates' folded query rows TQ[id] (bf16
+// table) straight into the K-major operand layout with 16-byte cp.async copies and stage the user's keys (fp32 rows ->
+// bf16 operand) and their per-key terms; one elected lane issues per head h  S_h[128 x 64] = TQ_h K_h^T
+// (tcgen05.mma kind::f16, M = 128, N = 64, K = d / H) into one of two TMEM stages; four epilogue warps (thread =
+// candidate) run the softmax over the user's keys, fold the attention output through u_h[j] = <V_h[j], wf_h> and write
+// sigmoid(att + <o, wf> + bf).  Users with more than 64 keys take several key chunks (online softmax across chunks).
+// Two stages: the gather of item i+1 runs under the MMAs / epilogue of item i.
+constexpr int DT_KEYS = 64;
+constexpr int DT_THREADS = 288;   // warps 0..3 epilogue, 4 MMA, 5..8 producers
+
+template <int D, int H>
+struct DecTcSmem {
+  static constexpr int NST = 2;                    // stages (96 KB each at d = 256; two CTAs per SM at d = 64)
+  static constexpr int A_BYTES = (D / 8) * 128 * 16;
+  static constexpr int K_BYTES = (D / 8) * DT_KEYS * 16;
+  unsigned char a[NST][A_BYTES];
+  unsigned char k[NST][K_BYTES];
+  float kc[NST][H][DT_KEYS];        // context term of the key per head (one context row per user), -1e30: masked
+  float uu[NST][H][DT_KEYS];        // u_h[j] = <V_h[j], wf_h>
+  alignas(16) float km[NST][DT_KEYS][H][8];   // per-candidate context: km[j][h][k] = <K_h[j], McQ_h[:, k]>
+  // per candidate row, written by its producer thread: item id, residual term <o, wf> = tw[id] + <mcw, c>, context
+  int rid[NST][128];
+  float rres[NST][128];
+  alignas(16) float rcv[NST][128][8];
+  uint64_t full[NST], empty[NST], acc_full[NST], acc_empty[NST];
+  uint32_t tmem_slot;
+};
+
+struct DecTcArgs {
+  const bf16* TQb;          // WQ T[i] + bq, bf16 [n_items, D]
+  const float* Kd;          // decoder keys, fp32 rows [R, D]
+  const float* U;           // [R, H]
+  const float* KM;          // [R, H, 8]
+  const float* tw;
+  const float* mcw;
+  const float* dbf;
+  const int2* useg;
+  const int* row_src;
+  const int* o_x;
+  const float* o_c;
+  long long oc_user, oc_tgt;
+  float* y;
+  long long ldy;
+  int col0, B, T, C, cat_lo, residual_ca;
+  int* status;
+};
+
+template <int D, int H>
+// (d = 64: two CTAs per SM; 9 warps are allocated as 12, so the register budget is that of a 384-thread block)
+__global__ void __launch_bounds__((D >= 256 ? DT_THREADS : 384), (D >= 256 ? 1 : 2)) rows_decode_tc_kernel(const DecTcArgs a) {
+  using SM = DecTcSmem<D, H>;
+  constexpr int DH = D / H, KG = D / 8, NST = SM::NST;
+  constexpr float kMask = -1.0e30f;
+  extern __shared__ __align__(128) unsigned char dec_raw[];
+  SM& s = *reinterpret_cast<SM*>(dec_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.T + 127) / 128;
+  const bool uctx = a.oc_tgt == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) {
+      umma::mbar_init(&s.full[i], 128);       // every producer thread arrives when its copies have landed
+      umma::mbar_init(&s.empty[i], 1);        // tcgen05.commit: the MMAs have read the stage
+      umma::mbar_init(&s.acc_full[i], 1);
+      umma::mbar_init(&s.acc_empty[i], 4);    // one arrival per epilogue warp
+    }
+  }
+  if (warp == 4) umma::tmem_alloc(&s.tmem_slot, NST * H * DT_KEYS);
+  // key columns past a user's last key are masked by their -1e30 term, but what the MMA reads there must be finite
+  for (int i = threadIdx.x; i < NST * SM::K_BYTES / 16; i += DT_THREADS) reinterpret_cast<uint4*>(s.k[0])[i] = make_uint4(0, 0, 0, 0);
+  umma::fence_smem_to_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem0 = s.tmem_slot;
+  const float sc = 1.4426950408889634f * rsqrtf((float)DH);
+
+  // the sequence of (user, candidate tile, key chunk) steps of this CTA: identical in every role
+  // step `it`: user u, tile, key chunk k0 .. k0 + nk
+  auto for_each_step = [&](auto&& body) {
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < (long long)a.B * n_tiles; item += gridDim.x) {
+      const int u = (int)(item / n_tiles), t0 = (int)(item % n_tiles) * 128;
+      const int2 sg = a.useg[u];
+      for (int k0 = 0; k0 < max(sg.y, 1); k0 += DT_KEYS, ++it)
+        if (!body(it, u, t0, sg, k0, min(DT_KEYS, sg.y - k0), k0 + DT_KEYS >= sg.y)) return;
+    }
+  };
+
+  if (warp >= 5) {
+    // ===== producers: thread r gathers candidate row r of the tile and helps staging the keys
+    const int r = threadIdx.x - 160;
+    for_each_step([&](uint32_t it, int u, int t0, int2 sg, int k0, int nk, bool last) {
+      const int st = it % NST, ph = (it / NST) & 1;
+      if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
+      if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
+      const int t = t0 + r;
+      const int id = t < a.T ? (a.cat_lo > 0 ? a.cat_lo + t : __ldg(a.o_x + (long long)u * a.T + t)) : 0;
+      {   // what the epilogue needs of this row, so that it reads no global memory
+        float cv[8], res = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cv[k] = 0.f;
+        if (id != 0) {
+          const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
+          for (int k = 0; k < a.C; ++k) cv[k] = __ldg(c + k);
+          if (a.residual_ca) {
+            res = __ldg(a.tw + id);
+            for (int k = 0; k < a.C; ++k) res = fmaf(__ldg(a.mcw + k), cv[k], res);
+          }
+        }
+        s.rid[st][r] = t < a.T ? id : -1;
+        s.rres[st][r] = res;
+        if (!uctx) {
+          reinterpret_cast<float4*>(s.rcv[st][r])[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          reinterpret_cast<float4*>(s.rcv[st][r])[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+        }
+      }
+      if (id != 0) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.TQb + (long long)id * D);
+        const uint32_t dst = umma::smem_u32(s.a[st]) + r * 16;
+#pragma unroll 8
+        for (int kg = 0; kg < KG; ++kg)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kg * 2048), "l"(src + kg * 16) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // keys of the chunk: fp32 rows -> bf16 operand [k/8][64 keys][8]; key j = r / 2, half of the k-groups each
+      {
+        const int j = r >> 1, hf = r & 1;
+        uint4* kd = reinterpret_cast<uint4*>(s.k[st]);
+        if (j < nk) {
+          const float* kr = a.Kd + (long long)(sg.x + k0 + j) * D;
+#pragma unroll 4
+          for (int kg = hf * (KG / 2); kg < (hf + 1) * (KG / 2); ++kg) {
+            float v[8];
+            ldg256(kr + 8 * kg, v);
+            kd[kg * DT_KEYS + j] = pack8(v);
+          }
+        }
+      }
+      // per-key terms
+      for (int i = r; i < DT_KEYS * H; i += 128) {
+        const int j = i / H, h = i % H;
+        float kcv = kMask, uv = 0.f;
+        if (j < nk && a.row_src[sg.x + k0 + j] >= 0) {
+          const long long row = (long long)sg.x + k0 + j;
+          uv = a.U[row * H + h];
+          const float4* kmp = reinterpret_cast<const float4*>(a.KM + (row * H + h) * 8);
+          const float4 m0 = __ldg(kmp), m1 = __ldg(kmp + 1);
+          if (uctx) {
+            const float* cu = a.o_c + (long long)u * a.oc_user;
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            kcv = 0.f;
+            for (int k = 0; k < a.C; ++k) kcv = fmaf(mm[k], __ldg(cu + k), kcv);
+          } else {
+            kcv = 0.f;
+            reinterpret_cast<float4*>(&s.km[st][j][h][0])[0] = m0;
+            reinterpret_cast<float4*>(&s.km[st][j][h][0])[1] = m1;
+          }
+        }
+        s.kc[st][h][j] = kcv;
+        s.uu[st][h][j] = uv;
+      }
+      // this thread's copies and stores are complete and visible to the tensor core's (async-proxy) reads
+      // (with two stages a lagged arrival would serialise the steps; at d = 64 two CTAs per SM hide this wait)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      umma::fence_smem_to_async();
+      mbar_arrive(&s.full[st]);
+      return true;
+    });
+  } else if (warp == 4) {
+    // ===== MMA issuer
+    constexpr uint32_t idesc = idesc_bf16(DT_KEYS);
+    for_each_step([&](uint32_t it, int, int, int2, int, int, bool) {
+      const int st = it % NST, ph = (it / NST) & 1;
+      if (!wait_or_flag(&s.full[st], ph, a.status, 16)) return false;
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        const uint32_t ab = umma::smem_u32(s.a[st]), kb = umma::smem_u32(s.k[st]);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const uint32_t d = tmem0 + st * (H * DT_KEYS) + h * DT_KEYS;
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks) {
+            const int kg = h * (DH / 8) + 2 * ks;
+            mma_bf16_ss(d, umma::smem_desc(ab + kg * 2048, 2048, 128), umma::smem_desc(kb + kg * (DT_KEYS * 16), DT_KEYS * 16, 128),
+                        idesc, ks != 0);
+          }
+        }
+        umma::commit(&s.empty[st]);
+        umma::commit(&s.acc_full[st]);
+      }
+      __syncwarp();
+      return true;
+    });
+  } else {
+    // ===== epilogue: thread = candidate row
+    const int r = 32 * warp + lane;
+    const float bfv = __ldg(a.dbf);
+    float m[H], z[H], dd[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = kMask; z[h] = 0.f; dd[h] = 0.f; }
+    for_each_step([&](uint32_t it, int u, int t0, int2, int, int nk, bool last) {
+      const int st = it % NST, ph = (it / NST) & 1;
+      if (!wait_or_flag(&s.acc_full[st], ph, a.status, 32)) return false;
+      umma::fence_after_sync();
+      const int t = t0 + r;
+      const int rid = s.rid[st][r];
+      const bool has = rid >= 0;
+      const int id = has ? rid : 0;
+      float cv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cv[k] = 0.f;
+      if (!uctx) {
+        const float4 c0 = reinterpret_cast<const float4*>(s.rcv[st][r])[0], c1 = reinterpret_cast<const float4*>(s.rcv[st][r])[1];
+        cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+      }
+      const float res = s.rres[st][r];
+      const uint32_t tb = tmem0 + ((uint32_t)(32 * warp) << 16) + st * (H * DT_KEYS);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < nk; c0 += 8) {
+          float v[8];
+          umma::tmem_ld_1x8(tb + h * DT_KEYS + c0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float sv = v[e] + s.kc[st][h][c0 + e];          // masked / missing keys carry -1e30
+            if (!uctx) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) sv = fmaf(cv[k], s.km[st][c0 + e][h][k], sv);
+            }
+            sv *= sc;
+            const float mn = fmaxf(m[h], sv);
+            const float corr = ex2f(m[h] - mn), p = ex2f(sv - mn);
+            z[h] = fmaf(z[h], corr, p);
+            dd[h] = fmaf(dd[h], corr, p * s.uu[st][h][c0 + e]);
+            m[h] = mn;
+          }
+        }
+      }
+      if (last) {
+        if (has) {
+          float acc = bfv;
+          if (id != 0) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) acc += m[h] > -1.0e29f * 1.4426950408889634f ? dd[h] / z[h] : 0.f;
+            acc += res;
+          }
+          a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + expf(-acc));
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) { m[h] = kMask; z[h] = 0.f; dd[h] = 0.f; }
+      }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_empty[st]);
+      return true;
+    });
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) umma::tmem_free(tmem0, NST * H * DT_KEYS);
+}
+
+}  // namespace rows
+}  // namespace carca
+#endif
