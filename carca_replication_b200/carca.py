@@ -481,8 +481,6 @@ class CARCA(Model):
     force_eval_path: Optional[str] = None
     use_rows_eval = True    # class default; set False on an instance to keep shapes outside the fused kernel per-op
 
-    _fits_eval_override: Optional[bool] = None
-
     # Arithmetic of the fused inference path: "fp32" (3xTF32 tensor-core kernel, scores within 1e-4 of the reference)
     # or "bf16" (BASELINE configs[1]: bf16 operands and tables, fp32 accumulation / softmax / LayerNorm, within 1e-2)
     eval_dtype = "fp32"

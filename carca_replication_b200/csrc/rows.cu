@@ -475,9 +475,8 @@ int catalog_counts_t(int32_t* counts, const unsigned char* plan, const float* Tf
   a.status = status;
   const int n_tiles = ceil_div(n_shard, cat::CT);
   a.parts = max(1, min(16, ceil_div(148 * 6, n_tiles)));
-  if (const char* e = getenv("CARCA_CAT_PARTS")) a.parts = max(1, atoi(e));
+  if (const char* e = getenv("CARCA_CAT_PARTS")) a.parts = max(1, atoi(e));   // (development: work split per item tile)
   const size_t smem = sizeof(cat::CatSmem);
-  if (getenv("CARCA_CAT_SKIP")) return 0;
   if (const char* e = getenv("CARCA_CAT_DBG")) a.dbg = reinterpret_cast<volatile int*>(strtoull(e, nullptr, 10));
   if (ca) {
     auto k = cat::catalog_tc_kernel<1>;

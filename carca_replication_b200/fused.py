@@ -1,10 +1,12 @@
 """Whole-model inference path: carca_eval_prepare + carca_eval_forward (one fused kernel).
 
 Used by CARCA.forward when the model is in eval mode under torch.no_grad(), every sub-module is one
-of this package's classes, attributes come from a device-resident ItemAttrTable and the shape is in
-the fused kernel's range (d = 64, L <= 52, C <= 8, <= 8 blocks).  Anything else keeps the per-op
-entry points.  The "plan" (folded item table + transposed projection weights) is rebuilt only when
-a parameter changes (tracked through tensor versions), e.g. once per evaluate() during training.
+of this package's classes and attributes come from a device-resident ItemAttrTable: the one-kernel
+tensor-core forward (`forward`: d = 64, L <= 64), the packed-rows pipeline (`forward_rows`: any window up
+to 256 positions, d in {32, 64, 128, 256}, fp32 or bf16) and the tensor-core full-catalog kernel
+(`catalog_counts`).  Anything else keeps the per-op entry points.  The "plan" (folded item table + packed
+projection weights) is rebuilt only when a parameter changes (tensor versions + `weights_epoch`, which
+raw-pointer optimizers bump), e.g. once per evaluate() during training.
 """
 from __future__ import annotations
 
@@ -57,17 +59,6 @@ def supported(model, seq_len: int, n_ctx: int) -> bool:
     ffma = seq_len <= MAX_L and (d // H) % 4 == 0
     tc = seq_len <= MAX_L_TC and H in (2, 4) and N.is_device_tensor(emb.items_embed.weight)
     return ffma or tc
-
-
-def fits_packed(p_x: Tensor) -> bool:
-    """Tensor-core kernel precondition for L > 64: every user has at most 64 rows after packing
-    (its non-padding positions plus position L-1).  One small reduction + device->host read; never
-    needed for L <= 64."""
-    L = p_x.shape[1]
-    if L <= BIN_ROWS:
-        return True
-    rows = (p_x != 0).sum(dim=1) + (p_x[:, -1] == 0).to(torch.int64)
-    return int(rows.max().item()) <= BIN_ROWS if rows.numel() else True
 
 
 def _model_params(model, table: ItemAttrTable, WfT: Optional[Tensor], n_ctx: int):

@@ -135,20 +135,17 @@ class GraphedEvalStep:
         from . import fused
 
         self.long_windows = False
-        try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), torch.no_grad():
-                for _ in range(warmup):                  # builds the inference plan and every cached buffer
-                    self._body()
-            torch.cuda.current_stream().wait_stream(side)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(self.graph):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                  # builds the inference plan and every cached buffer
                 self._body()
-            self.graph_is_fused = True
-            self.uses_plan = fused._plans.get(model) is not None       # the capture reads the fused inference plan
-        finally:
-            pass
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._body()
+        self.graph_is_fused = True
+        self.uses_plan = fused._plans.get(model) is not None       # the capture reads the fused inference plan
         self.stats.copy_(keep)                       # warm-up runs do not count
 
     def _body(self) -> None:
