@@ -71,3 +71,37 @@ def test_bf16_follows_weight_updates_and_reports_status():
     hr, ndcg, loss = cb.evaluate(model, loader, DEV, 10)
     assert 0.0 <= hr <= 1.0 and np.isfinite(loss)
     assert not fused.mma_timed_out(model)
+
+
+@pytest.mark.parametrize("name", ["beauty_ca", "beauty_dot", "learnable_ca", "sinus_dot", "single_user_ca"])
+def test_reference_fixtures_in_bf16(name):
+    """Golden fixtures of the real reference (learnable / sinusoidal positions, B = 1, both decoders) through the bf16
+    pipeline: scores within the bf16 contract of the reference's fp32 output."""
+    import carca_replication_b200 as cb
+    from helpers import load_case
+
+    cfg, sd, z = load_case(name)
+    model = S.build_model(cfg, sd, DEV).eval().set_eval_dtype("bf16")
+    model.embeds.set_attr_table(cb.ItemAttrTable.from_dense(z["attr_table"], sparse=True).to(DEV))
+    p_x, _, p_c, o_x, _, o_c, y_true = [t.to(DEV) for t in S.batch_of(z, "eval")]
+    with torch.no_grad():
+        assert model._fused_eval_mode((p_x, None, p_c), [(o_x, None, o_c)]) == "rows_bf16"
+        y = model.forward((p_x, None, p_c), [(o_x, None, o_c)])
+    dp, dl, top = S.bf16_errors(y.cpu().numpy(), z["eval/y_pred"])
+    assert dl < S.BF16_TOL and top >= 0.9
+    if cfg["decoder"] == "ca":
+        assert dp < S.BF16_TOL
+
+
+def test_bf16_needs_a_supported_shape():
+    """eval_dtype == "bf16" on a shape the pipeline does not cover fails loudly instead of silently running fp32."""
+    from helpers import load_case
+
+    cfg, sd, z = load_case("men_dot_d128")
+    import carca_replication_b200 as cb
+
+    model = S.build_model(cfg, sd, DEV).eval().set_eval_dtype("bf16")
+    model.embeds.set_attr_table(cb.ItemAttrTable.from_dense(z["attr_table"], sparse=False).to(DEV))
+    p_x, _, p_c, o_x, _, o_c, _ = [t.to(DEV) for t in S.batch_of(z, "eval")]
+    with torch.no_grad(), pytest.raises(RuntimeError, match="bf16"):
+        model.forward((p_x, None, p_c), [(o_x, None, o_c)])
