@@ -92,7 +92,8 @@ struct FillArgs {
   const int* ucol;
   const int2* useg;
   const int *row_src, *n_rows;
-  const float *Kd, *Vd;       // ca: decoder keys / values, fp32 rows [R, 64]
+  const float *Kd, *Vd;       // ca: decoder keys / values, fp32 rows (row stride ld)
+  int ld;
   const float *wf, *McQ;      // ca
   const float* ctx_user;      // [B, C]
   const float* PE;            // dot: encoded profile rows
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(256) cat_fill_ca_kernel(const FillArgs a) {
   // lane l < 16: float4 l of the key row -> head l / 8, chunk l % 8
   float4 kq = make_float4(0.f, 0.f, 0.f, 0.f), vq = kq;
   if (lane < 16) {
-    kq = __ldg(reinterpret_cast<const float4*>(a.Kd + r * 64) + lane);
-    vq = __ldg(reinterpret_cast<const float4*>(a.Vd + r * 64) + lane);
+    kq = __ldg(reinterpret_cast<const float4*>(a.Kd + r * a.ld) + lane);
+    vq = __ldg(reinterpret_cast<const float4*>(a.Vd + r * a.ld) + lane);
   }
   // context term of the key and the value fold, per head (lanes 0..7 head 0, 8..15 head 1)
   float kc = 0.f, uu = 0.f;

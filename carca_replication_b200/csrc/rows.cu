@@ -46,7 +46,7 @@ inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
 // byte offsets of the bf16 plan
 struct RowsPlan {
-  long long mc, w, dw, tq, tw, mcq, mcw, tqb, total;
+  long long mc, w, dw, tq, tw, mcq, mcw, tqb, wkv, bkv, total;   // wkv: fp32 [Wk; Wv] per block (+ decoder), bkv biases
 };
 RowsPlan rows_plan(const carca_model_params* m) {
   RowsPlan p;
@@ -60,7 +60,9 @@ RowsPlan rows_plan(const carca_model_params* m) {
   p.mcq = align256(p.tw + (ca ? n * 4 : 0));
   p.mcw = align256(p.mcq + (ca ? d * 8 * 4 : 0));
   p.tqb = align256(p.mcw + (ca ? 8 * 4 : 0));
-  p.total = align256(p.tqb + (ca ? n * d * 2 : 0));
+  p.wkv = align256(p.tqb + (ca ? n * d * 2 : 0));
+  p.bkv = align256(p.wkv + (long long)(m->n_blocks + 1) * 2 * d * d * 4);
+  p.total = align256(p.bkv + (long long)(m->n_blocks + 1) * 2 * d * 4);
   return p;
 }
 
@@ -174,7 +176,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     }
     {
       rows::AttnRowsArgs t;
-      t.Q = Qb; t.K = Kb; t.V = Vb; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
+      t.Q = Qb; t.K = Kb; t.V = Vb; t.ldkv = D; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
       t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.S2A = S2A; t.residual = m->residual_sa;
       auto k = rows::rows_attn_ln_kernel<D, H, false>;
       CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
@@ -248,7 +250,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       CARCA_LAUNCH(k, dim3((unsigned)min(work, 148ll * per_sm)), dim3(rows::DT_THREADS), smem, st, t);
       return check_launch("rows_decode_tc");
     }
-    d.Kd = S2; d.U = U; d.KM = KM;      // (the S2 buffer is free after the last block: it holds the fp32 keys)
+    d.Kd = S2; d.ldk = D; d.U = U; d.KM = KM;   // (the S2 buffer is free after the last block: it holds the fp32 keys)
     d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
     d.tw = reinterpret_cast<const float*>(plan + pl.tw);
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
@@ -269,8 +271,8 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
 // (gemm_tc.cuh) with the row count read on the device (GemmArgs::m_dev), LayerNorms as row kernels.  No per-user row
 // limit: this is the fp32 path for windows longer than one 64-row bin and for widths the fused kernels do not cover.
 int gemm_rows_f32(float* C, const float* A, const float* W, const float* bias, int Mcap, int d, const int* n_rows, int act,
-                  const float* R, cudaStream_t st) {
-  GemmArgs g = gemm_defaults(A, W, C, Mcap, d, d);
+                  const float* R, cudaStream_t st, int n_out = 0) {
+  GemmArgs g = gemm_defaults(A, W, C, Mcap, n_out ? n_out : d, d);
   g.bias = bias;
   g.act = act;
   g.R = R;
@@ -298,6 +300,8 @@ int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_p
   float* Vf = reinterpret_cast<float*>(scr + sc.slot[5]);
   float* F1 = reinterpret_cast<float*>(scr + sc.slot[6]);
   const float* Mc = reinterpret_cast<const float*>(plan + pl.mc);
+  const float* wkv = reinterpret_cast<const float*>(plan + pl.wkv);
+  const float* bkv = reinterpret_cast<const float*>(plan + pl.bkv);
   const int Mcap = (int)min((long long)B * L, (long long)INT32_MAX);
 
   cudaMemsetAsync(n_rows, 0, 256, st);
@@ -320,12 +324,13 @@ int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_p
   for (int b = 0; b < m->n_blocks; ++b) {
     const carca_block_params& bp = m->blocks[b];
     TRY(gemm_rows_f32(Qf, QN, bp.wq, bp.bq, Mcap, D, n_rows, 0, nullptr, st));   // Q from LN1(x), K / V from x (:238-240)
-    TRY(gemm_rows_f32(Kf, Xf, bp.wk, bp.bk, Mcap, D, n_rows, 0, nullptr, st));
-    TRY(gemm_rows_f32(Vf, Xf, bp.wv, bp.bv, Mcap, D, n_rows, 0, nullptr, st));
+    TRY(gemm_rows_f32(Kf, Xf, wkv + (long long)b * 2 * D * D, bkv + (long long)b * 2 * D, Mcap, D, n_rows, 0, nullptr, st,
+                      2 * D));                                                     // [K | V] rows of 2 D floats
     {
       rows::AttnRowsArgs t;
       memset(&t, 0, sizeof(t));
-      t.Q = Qf; t.K = Kf; t.V = Vf; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
+      t.Q = Qf; t.K = Kf; t.V = Kf + D; t.ldkv = 2 * D; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg;
+      t.n_rows = n_rows;
       t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.residual = m->residual_sa;
       auto k = rows::rows_attn_ln_kernel<D, H, true>;
       CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
@@ -341,11 +346,16 @@ int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_p
       TRY(check_launch("rows_ln"));
     }
   }
-  if (m->decoder_kind == 1) {
-    TRY(gemm_rows_f32(Kf, QN, m->cross.wk, m->cross.bk, Mcap, D, n_rows, 0, nullptr, st));
-    TRY(gemm_rows_f32(Vf, QN, m->cross.wv, m->cross.bv, Mcap, D, n_rows, 0, nullptr, st));
+  if (m->decoder_kind == 1) {   // decoder keys | values (:239-240 with the encoded profile) and their folds
+    TRY(gemm_rows_f32(Kf, QN, wkv + (long long)m->n_blocks * 2 * D * D, bkv + (long long)m->n_blocks * 2 * D, Mcap, D, n_rows,
+                      0, nullptr, st, 2 * D));
+    auto k = rows::rows_fold_kv_kernel<D, H>;
+    CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, reinterpret_cast<float*>(scr + sc.U), reinterpret_cast<float*>(scr + sc.KM),
+                 (const float*)Kf, (const float*)(Kf + D), 2 * D, m->cross.wf, reinterpret_cast<const float*>(plan + pl.mcq),
+                 (const int*)n_rows);
+    TRY(check_launch("rows_fold_kv"));
   }
-  (void)useg; (void)Qf;
+  (void)useg; (void)Qf; (void)Vf;
   return 0;
 }
 
@@ -360,8 +370,7 @@ int decode_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, con
   int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
   int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
   float* QN = reinterpret_cast<float*>(scr + sc.slot[1]);
-  float* Kf = reinterpret_cast<float*>(scr + sc.slot[4]);
-  float* Vf = reinterpret_cast<float*>(scr + sc.slot[5]);
+  float* Kf = reinterpret_cast<float*>(scr + sc.slot[4]);       // [K | V] rows of 2 d floats (slots 4 and 5)
   const float* Mc = reinterpret_cast<const float*>(plan + pl.mc);
   rows::DecodeArgs d;
   memset(&d, 0, sizeof(d));
@@ -373,8 +382,8 @@ int decode_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, con
   const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
-    d.Kd = Kf; d.Vd = Vf; d.wf = m->cross.wf;
-    d.McQ = reinterpret_cast<const float*>(plan + pl.mcq);
+    d.Kd = Kf; d.ldk = 2 * D;
+    d.U = reinterpret_cast<const float*>(scr + sc.U); d.KM = reinterpret_cast<const float*>(scr + sc.KM);
     d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
     d.tw = reinterpret_cast<const float*>(plan + pl.tw);
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
@@ -439,7 +448,7 @@ int catalog_counts_t(int32_t* counts, const unsigned char* plan, const float* Tf
   memset(&f, 0, sizeof(f));
   f.Bt = Bt; f.meta = meta; f.ucol = ucol; f.useg = reinterpret_cast<const int2*>(scr + sc.useg);
   f.row_src = reinterpret_cast<const int*>(scr + sc.row_src); f.n_rows = counters;
-  f.Kd = reinterpret_cast<const float*>(scr + sc.slot[4]); f.Vd = reinterpret_cast<const float*>(scr + sc.slot[5]);
+  f.Kd = reinterpret_cast<const float*>(scr + sc.slot[4]); f.Vd = f.Kd + D; f.ld = 2 * D;   // [K | V] rows of the fused GEMM
   f.wf = m->cross.wf; f.McQ = reinterpret_cast<const float*>(plan + pl.mcq); f.ctx_user = ctx_user;
   f.PE = reinterpret_cast<const float*>(scr + sc.slot[1]); f.Mc = reinterpret_cast<const float*>(plan + pl.mc);
   f.mcw = reinterpret_cast<const float*>(plan + pl.mcw); f.y_pos = y_pos; f.pos_item = pos_item;
@@ -520,6 +529,20 @@ int carca_rows_prepare(void* plan_v, const float* plan_f32, const carca_model_pa
                    reinterpret_cast<bf16*>(plan + pl.w) + ((long long)b * 5 + i) * d * d, ws[i], d);
       TRY(check_launch("pack_weight_bf16"));
     }
+  }
+  // fp32 flavour: K and V share their A operand (src/carca.py:239-240), so [Wk; Wv] runs as ONE [R, d] x [d, 2d] GEMM
+  for (int b = 0; b <= m->n_blocks; ++b) {
+    if (b == m->n_blocks && m->decoder_kind != 1) break;
+    const float* wk = b < m->n_blocks ? m->blocks[b].wk : m->cross.wk;
+    const float* wv = b < m->n_blocks ? m->blocks[b].wv : m->cross.wv;
+    const float* bk = b < m->n_blocks ? m->blocks[b].bk : m->cross.bk;
+    const float* bv = b < m->n_blocks ? m->blocks[b].bv : m->cross.bv;
+    float* w2 = reinterpret_cast<float*>(plan + pl.wkv) + (long long)b * 2 * d * d;
+    float* b2 = reinterpret_cast<float*>(plan + pl.bkv) + (long long)b * 2 * d;
+    cudaMemcpyAsync(w2, wk, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(w2 + (long long)d * d, wv, sizeof(float) * d * d, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(b2, bk, sizeof(float) * d, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(b2 + d, bv, sizeof(float) * d, cudaMemcpyDeviceToDevice, st);
   }
   if (m->decoder_kind == 1) {
     const float* ws[2] = {m->cross.wk, m->cross.wv};

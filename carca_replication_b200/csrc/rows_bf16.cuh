@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
 // ---------------------------------------------------------------------------------------------- attention + LN2
 struct AttnRowsArgs {
   const void *Q, *K, *V;    // rows [R, D]: bf16 (bf16 flavour) or fp32
+  int ldkv;                 // row stride of K and V in elements (fp32 flavour: K | V come from one fused GEMM, 2 D)
   const float* QN;          // LN1(x) rows (residual, src/carca.py:302)
   const int *row_src, *row_seg, *n_rows;
   const float *ln_g, *ln_b;
@@ -214,16 +215,16 @@ struct AttnRowsArgs {
 // the same user at positions <= the query's; a padding query row gives exactly 0), + LN1 residual, LayerNorm 2.
 // One group of D/8 lanes per row; a lane owns 8 consecutive features, i.e. a slice of one head.
 template <bool F32>
-__device__ __forceinline__ void load_row8(const void* base, long long row, int D, int l, bool on, float (&v)[8]) {
+__device__ __forceinline__ void load_row8(const void* base, long long row, int ld, int l, bool on, float (&v)[8]) {
   if (!on) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
     return;
   }
   if (F32) {
-    ldg256(reinterpret_cast<const float*>(base) + row * D + 8 * l, v);
+    ldg256(reinterpret_cast<const float*>(base) + row * ld + 8 * l, v);
   } else {
-    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + row * D) + l), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + row * ld) + l), v);
   }
 }
 template <int D, int H, bool F32>
@@ -260,9 +261,9 @@ __global__ void __launch_bounds__(256) rows_attn_ln_kernel(const AttnRowsArgs a)
     for (int j0 = 0; j0 < n_max; j0 += KC) {
       float kv[KC][8], vv[KC][8], sj[KC];
 #pragma unroll
-      for (int i = 0; i < KC; ++i) load_row8<F32>(a.K, (long long)s0 + j0 + i, D, l, j0 + i < n_keys, kv[i]);
+      for (int i = 0; i < KC; ++i) load_row8<F32>(a.K, (long long)s0 + j0 + i, a.ldkv, l, j0 + i < n_keys, kv[i]);
 #pragma unroll
-      for (int i = 0; i < KC; ++i) load_row8<F32>(a.V, (long long)s0 + j0 + i, D, l, j0 + i < n_keys, vv[i]);
+      for (int i = 0; i < KC; ++i) load_row8<F32>(a.V, (long long)s0 + j0 + i, a.ldkv, l, j0 + i < n_keys, vv[i]);
 #pragma unroll
       for (int i = 0; i < KC; ++i) {
         float t = 0.f;
@@ -362,6 +363,53 @@ __global__ void __launch_bounds__(256) rows_ln_kernel(float* __restrict__ Y, con
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
       stg256(Y + r * D + 8 * l, o);
+    }
+  }
+}
+
+// fp32 flavour: per packed row the decoder's value fold u[r][h] = <V_h[r], wf_h> and the context terms of its key
+// km[r][h][k] = <K_h[r], McQ_h[:, k]> (the bf16 flavour gets both from its GEMM epilogues).  One group of D/8 lanes per row.
+template <int D, int H>
+__global__ void __launch_bounds__(256) rows_fold_kv_kernel(float* __restrict__ U, float* __restrict__ KM,
+                                                           const float* __restrict__ Kd, const float* __restrict__ Vd, int ld,
+                                                           const float* __restrict__ wf, const float* __restrict__ McQ,
+                                                           const int* __restrict__ n_rows) {
+  constexpr int G = D / 8, RPW = 32 / G, DH = D / H, LPH = DH / 8;
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+  const int R = *n_rows;
+  float w8[8], mq[8][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    w8[e] = __ldg(wf + 8 * l + e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mq[e][k] = __ldg(McQ + (8 * l + e) * 8 + k);
+  }
+  for (long long r0 = (long long)warp * RPW; r0 < R; r0 += (long long)n_warps * RPW) {
+    const long long r = r0 + sub;
+    const bool live = r < R;
+    float kv[8], vv[8];
+    load_row8<true>(Kd, r, ld, l, live, kv);
+    load_row8<true>(Vd, r, ld, l, live, vv);
+    float u = 0.f, km[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      u = fmaf(vv[e], w8[e], u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) km[k] = fmaf(kv[e], mq[e][k], km[k]);
+    }
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) {
+      u += __shfl_xor_sync(kFull, u, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) km[k] += __shfl_xor_sync(kFull, km[k], o);
+    }
+    if (live && l % LPH == 0) {
+      const int h = l / LPH;
+      U[r * H + h] = u;
+      float4* o = reinterpret_cast<float4*>(KM + (r * H + h) * 8);
+      o[0] = make_float4(km[0], km[1], km[2], km[3]);
+      o[1] = make_float4(km[4], km[5], km[6], km[7]);
     }
   }
 }
@@ -684,11 +732,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmAr
 // ---------------------------------------------------------------------------------------------- decoders
 struct DecodeArgs {
   // cross-attention (src/carca.py:338-347): keys of the encoded profile and the folded candidate tables
-  const float* Kd;          // decoder keys, rows [R, D] fp32
+  const float* Kd;          // decoder keys, fp32 rows (row stride ldk)
+  int ldk;
   const float* U;           // u[r][h] = <V_h[r], wf_h>            (bf16 flavour: from the GEMM epilogue)
   const float* KM;          // km[r][h][k]
-  const float* Vd;          // decoder values, rows [R, D] fp32  (fp32 flavour: u / km are folded here)
-  const float *wf, *McQ;    //   scorer weight [D], query-side context map [D][8]
   const float* TQ;          // WQ T[i] + bq  [n_items, D] fp32
   const float* tw;          // <T[i], wf>    [n_items]
   const float* mcw;         // wf Mc         [8]
@@ -752,32 +799,12 @@ __global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a)
       const int nk = min(DEC_KEYS, sg.y - k0);
       __syncthreads();
       for (int i = threadIdx.x; i < nk * (D / 4); i += 128)
-        reinterpret_cast<float4*>(&ks[0][0])[i] = __ldg(reinterpret_cast<const float4*>(a.Kd + (long long)(sg.x + k0) * D) + i);
-      if (!F32) {
-        for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
-        for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
-      }
+        reinterpret_cast<float4*>(&ks[0][0])[i] =
+            __ldg(reinterpret_cast<const float4*>(a.Kd + (long long)(sg.x + k0 + i / (D / 4)) * a.ldk) + i % (D / 4));
+      for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
+      for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
       for (int i = threadIdx.x; i < nk; i += 128) kvalid[i] = a.row_src[sg.x + k0 + i] >= 0 ? 1.f : 0.f;
       __syncthreads();
-      if (F32) {   // u[j][h] = <V_h[j], wf_h>,  km[j][h][k] = <K_h[j], McQ_h[:, k]>  (see DecodeArgs)
-        for (int i = threadIdx.x; i < nk * H; i += 128) {
-          const int j = i / H, hh = i % H;
-          const float* vp = a.Vd + (long long)(sg.x + k0 + j) * D + hh * DH;
-          float uu = 0.f, km[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int n = 0; n < DH; ++n) {
-            uu = fmaf(__ldg(vp + n), __ldg(a.wf + hh * DH + n), uu);
-            const float kv = ks[j][hh * DH + n];
-            const float4* mq = reinterpret_cast<const float4*>(a.McQ + (long long)(hh * DH + n) * 8);
-            const float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);
-            km[0] = fmaf(kv, m0.x, km[0]); km[1] = fmaf(kv, m0.y, km[1]); km[2] = fmaf(kv, m0.z, km[2]); km[3] = fmaf(kv, m0.w, km[3]);
-            km[4] = fmaf(kv, m1.x, km[4]); km[5] = fmaf(kv, m1.y, km[5]); km[6] = fmaf(kv, m1.z, km[6]); km[7] = fmaf(kv, m1.w, km[7]);
-          }
-          us[j][hh] = uu;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) kms[j][hh][k] = km[k];
-        }
-        __syncthreads();
-      }
       if (id != 0) {
         for (int j = 0; j < nk; ++j) {
           if (kvalid[j] == 0.f) continue;                   // padding key (position L-1 of a short window)
