@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "plan_layout.cuh"
 #include "rows_bf16.cuh"
+#include "rows_attn_tc.cuh"
 #include "catalog_tc.cuh"
 
 using namespace carca;
@@ -119,6 +120,30 @@ int launch_gemm_rows(const rows::GemmArgs& g, cudaStream_t st) {
   return check_launch("rows_gemm");
 }
 
+// tensor-core attention (rows_attn_tc.cuh): the key window of a 128-row tile is at most 127 + L rows
+inline int attn_tc_window(int L) { return (127 + L + 15) / 16 * 16; }
+
+template <int D, int H>
+int launch_attn_tc(rows::AttnTcArgs& t, int L, cudaStream_t st) {
+  using Cfg = rows::AttnTcCfg<D, H>;
+  t.win_max = attn_tc_window(L);
+  t.s_cols = (D == 64 && t.win_max <= 192) ? 192 : 256;
+  t.tmem_cols = t.s_cols + D <= 256 ? 256 : 512;
+  if (const char* e = getenv("CARCA_ATTN_VSWAP")) t.vswap = atoi(e);   // (development)
+  const size_t smem = Cfg::smem_bytes(t.win_max);
+  if (smem > 227 * 1024) return fail(-2, "rows_attn_tc: %zu bytes of shared memory (d=%d, L=%d)", smem, D, L);
+  auto k = rows::rows_attn_tc_kernel<D, H>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(-3, "rows_attn_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  const int per_sm = (t.tmem_cols == 256 && 2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
+  CARCA_LAUNCH(k, dim3(148 * per_sm), dim3(rows::AT_THREADS), smem, st, t);
+  return check_launch("rows_attn_tc");
+}
+
 template <int D, int H>
 int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
               const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
@@ -162,10 +187,26 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, e);
     TRY(check_launch("rows_embed_ln"));
   }
+  const bool attn_tc = attn_tc_window(L) <= 256 && !getenv("CARCA_ROWS_ATTN_FFMA");
   for (int b = 0; b < m->n_blocks; ++b) {
     const carca_block_params& bp = m->blocks[b];
     const bf16* wb = W + (long long)b * 5 * wsz;
-    {
+    if (attn_tc) {
+      // Q / K / V written as the attention's tensor-core operands, then the tcgen05 attention (rows_attn_tc.cuh)
+      rows::GemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.n_jobs = 3; g.n_rows = n_rows; g.H = H; g.status = status;
+      g.job[0].A = QA; g.job[0].W = wb;           g.job[0].bias = bp.bq; g.job[0].epi = rows::EPI_BIAS_TILE; g.job[0].out_tile = Qb;
+      g.job[1].A = XA; g.job[1].W = wb + wsz;     g.job[1].bias = bp.bk; g.job[1].epi = rows::EPI_KMAJ; g.job[1].out_tile = Kb;
+      g.job[2].A = XA; g.job[2].W = wb + 2 * wsz; g.job[2].bias = bp.bv; g.job[2].epi = rows::EPI_VMN; g.job[2].out_tile = Vb;
+      g.job[1].ld_rows = g.job[2].ld_rows = sc.Rp;
+      TRY(launch_gemm_rows<D>(g, st));
+      rows::AttnTcArgs t;
+      memset(&t, 0, sizeof(t));
+      t.Qt = Qb; t.Kk = Kb; t.Vm = Vb; t.Rp = sc.Rp; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
+      t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.S2A = S2A; t.residual = m->residual_sa; t.status = status;
+      TRY((launch_attn_tc<D, H>(t, L, st)));
+    } else {
       rows::GemmArgs g;
       memset(&g, 0, sizeof(g));
       g.n_jobs = 3; g.n_rows = n_rows; g.H = H; g.status = status;
@@ -174,7 +215,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       g.job[2].A = XA; g.job[2].W = wb + 2 * wsz; g.job[2].bias = bp.bv; g.job[2].epi = rows::EPI_ROWS; g.job[2].out_rows = Vb;
       TRY(launch_gemm_rows<D>(g, st));
     }
-    {
+    if (!attn_tc) {
       rows::AttnRowsArgs t;
       t.Q = Qb; t.K = Kb; t.V = Vb; t.ldkv = D; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
       t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.S2A = S2A; t.residual = m->residual_sa;
@@ -212,7 +253,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   d.oc_tgt = ctx_per_user ? 0 : C;
   d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.C = C; d.L = L; d.cat_lo = cat_lo;
   d.residual_ca = m->residual_ca;
-  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
+  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? rows::DecCfg<D>::threads(H) / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
     const bf16* dw = reinterpret_cast<const bf16*>(plan + pl.dw);
@@ -256,7 +297,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
     d.dbf = m->cross.bf;
     auto k = rows::rows_decode_ca_kernel<D, H, false>;
-    CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
+    CARCA_LAUNCH(k, dim3(dgrid), dim3(rows::DecCfg<D>::threads(H)), 0, st, d);
     TRY(check_launch("rows_decode_ca"));
   } else {
     d.PE = QN; d.Tf = Tf; d.Mc = Mc;
@@ -379,7 +420,7 @@ int decode_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, con
   d.oc_tgt = ctx_per_user ? 0 : C;
   d.y = y; d.ldy = ldy; d.col0 = col0; d.B = B; d.T = T; d.C = C; d.L = L; d.cat_lo = cat_lo;
   d.residual_ca = m->residual_ca;
-  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? 128 / H : 128);
+  const long long items = (long long)B * ceil_div(T, m->decoder_kind == 1 ? rows::DecCfg<D>::threads(H) / H : 128);
   const int dgrid = (int)min(items, 148ll * 16);
   if (m->decoder_kind == 1) {
     d.Kd = Kf; d.ldk = 2 * D;
@@ -389,7 +430,7 @@ int decode_f32_t(float* y, int64_t ldy, int col0, const unsigned char* plan, con
     d.mcw = reinterpret_cast<const float*>(plan + pl.mcw);
     d.dbf = m->cross.bf;
     auto k = rows::rows_decode_ca_kernel<D, H, true>;
-    CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
+    CARCA_LAUNCH(k, dim3(dgrid), dim3(rows::DecCfg<D>::threads(H)), 0, st, d);
     TRY(check_launch("rows_decode_ca"));
   } else {
     d.PE = QN; d.Tf = Tf; d.Mc = Mc;

@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(256) rows_fold_kv_kernel(float* __restrict__ U
 }
 
 // ---------------------------------------------------------------------------------------------- tcgen05 GEMM
-enum { EPI_ROWS = 0, EPI_LRELU_TILE = 1, EPI_LN = 2, EPI_VDOT = 3, EPI_KDEC = 4 };
+enum { EPI_ROWS = 0, EPI_LRELU_TILE = 1, EPI_LN = 2, EPI_VDOT = 3, EPI_KDEC = 4, EPI_BIAS_TILE = 5, EPI_KMAJ = 6, EPI_VMN = 7 };
+// EPI_BIAS_TILE / EPI_KMAJ / EPI_VMN feed the tensor-core attention (rows_attn_tc.cuh): Q as operand tiles, K as one
+// K-major operand over all rows [D/8][ld_rows][8], V as MN-major 8 x 8 blocks per head [H][ld_rows/8][DH/8][8][8].
+// They write EVERY row of a tile, rows past the batch as exact zeros (an MMA reads them; 0 * garbage must stay 0).
 
 struct GemmJob {
   const bf16* A;            // operand tiles [n_tiles][D/8][128][8]
@@ -423,7 +426,9 @@ struct GemmJob {
   const float* bias;        // [D]
   int epi;
   bf16* out_rows;           // EPI_ROWS: bf16 rows [R, D]
-  bf16* out_tile;           // EPI_LRELU_TILE: activation tiles; EPI_LN: tiles of the pre-norm value x' (may be null)
+  bf16* out_tile;           // EPI_LRELU_TILE / EPI_BIAS_TILE: activation tiles; EPI_LN: tiles of the pre-norm value x'
+                            //   (may be null); EPI_KMAJ / EPI_VMN: the attention operand
+  long long ld_rows;        // EPI_KMAJ / EPI_VMN: rows of the operand (multiple of 128)
   const float* resid;       // EPI_LN: fp32 rows added before the norm (null: no residual)
   const float *ln_g, *ln_b; // EPI_LN
   float* out_f32;           // EPI_LN: LN rows fp32; EPI_KDEC: key rows fp32 [R, D]
@@ -601,7 +606,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmAr
       umma::fence_after_sync();
       const long long r = (long long)tile * TILE + row_in_tile;
       const bool live = r < R;
-      if (J.epi == EPI_ROWS || J.epi == EPI_LRELU_TILE) {
+      if (J.epi == EPI_ROWS || J.epi == EPI_LRELU_TILE || J.epi >= EPI_BIAS_TILE) {
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
           float v[32];
@@ -610,12 +615,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmAr
           for (int e = 0; e < 32; ++e) {
             v[e] += prm[32 * c + e];
             if (J.epi == EPI_LRELU_TILE) v[e] = v[e] > 0.f ? v[e] : kLeakySlope * v[e];
+            if (J.epi >= EPI_KMAJ) v[e] = live ? v[e] : 0.f;
           }
           if (J.epi == EPI_ROWS) {
             if (live) {   // 64 contiguous bytes of this thread's row as two full-sector stores
               bf16* o = J.out_rows + r * D + 32 * c;
               stg256u(o, pack8(&v[0]), pack8(&v[8]));
               stg256u(o + 16, pack8(&v[16]), pack8(&v[24]));
+            }
+          } else if (J.epi == EPI_KMAJ) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(J.out_tile + ((long long)(4 * c + q) * J.ld_rows + r) * 8) = pack8(&v[8 * q]);
+          } else if (J.epi == EPI_VMN) {
+            const int FG = DH / 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int g = 4 * c + q, h = g / FG, j = g % FG;
+              *reinterpret_cast<uint4*>(J.out_tile + (((long long)h * (J.ld_rows >> 3) + (r >> 3)) * FG + j) * 64 + (r & 7) * 8) =
+                  pack8(&v[8 * q]);
             }
           } else {
 #pragma unroll
@@ -754,7 +772,10 @@ struct DecodeArgs {
   int col0, B, T, C, L, cat_lo, residual_ca;
 };
 // keys staged per pass: the decoder (the stage whose rounding lands directly on the logit) runs in fp32 on fp32 tables
-template <int D> struct DecCfg { static constexpr int KEYS = D >= 128 ? 32 : 64; };
+template <int D> struct DecCfg {
+  static constexpr int KEYS = D >= 128 ? 32 : 64;
+  static constexpr int threads(int H) { return H > 4 ? 32 * H : 128; }
+};
 
 // One CTA per (user, slice of 128 / H candidates); thread = (candidate, head) with the head constant per WARP
 // (warp w serves head w % H), so the key reads from shared memory are warp-wide broadcasts (one address per
@@ -764,8 +785,9 @@ template <int D> struct DecCfg { static constexpr int KEYS = D >= 128 ? 32 : 64;
 // u_h[j] = <V_h[j], wf_h> (src/carca.py:343-345: the scorer is Linear(d, 1) on attn + o); the H partial results of a
 // candidate meet in shared memory.
 template <int D, int H, bool F32>
-__global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a) {
-  constexpr int DH = D / H, DEC_KEYS = DecCfg<D>::KEYS, CPB = 128 / H;
+__global__ void __launch_bounds__(DecCfg<D>::threads(H)) rows_decode_ca_kernel(const DecodeArgs a) {
+  constexpr int NT = DecCfg<D>::threads(H);      // one warp per head at least: 8 heads -> 256 threads
+  constexpr int DH = D / H, DEC_KEYS = DecCfg<D>::KEYS, CPB = NT / H;
   __shared__ __align__(16) float ks[DEC_KEYS][D];
   __shared__ float us[DEC_KEYS][H];
   __shared__ __align__(16) float kms[DEC_KEYS][H][8];
@@ -798,12 +820,12 @@ __global__ void __launch_bounds__(128) rows_decode_ca_kernel(const DecodeArgs a)
     for (int k0 = 0; k0 < sg.y; k0 += DEC_KEYS) {
       const int nk = min(DEC_KEYS, sg.y - k0);
       __syncthreads();
-      for (int i = threadIdx.x; i < nk * (D / 4); i += 128)
+      for (int i = threadIdx.x; i < nk * (D / 4); i += NT)
         reinterpret_cast<float4*>(&ks[0][0])[i] =
             __ldg(reinterpret_cast<const float4*>(a.Kd + (long long)(sg.x + k0 + i / (D / 4)) * a.ldk) + i % (D / 4));
-      for (int i = threadIdx.x; i < nk * H; i += 128) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
-      for (int i = threadIdx.x; i < nk * H * 8; i += 128) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
-      for (int i = threadIdx.x; i < nk; i += 128) kvalid[i] = a.row_src[sg.x + k0 + i] >= 0 ? 1.f : 0.f;
+      for (int i = threadIdx.x; i < nk * H; i += NT) us[i / H][i % H] = a.U[(long long)(sg.x + k0) * H + i];
+      for (int i = threadIdx.x; i < nk * H * 8; i += NT) (&kms[0][0][0])[i] = a.KM[(long long)(sg.x + k0) * H * 8 + i];
+      for (int i = threadIdx.x; i < nk; i += NT) kvalid[i] = a.row_src[sg.x + k0 + i] >= 0 ? 1.f : 0.f;
       __syncthreads();
       if (id != 0) {
         for (int j = 0; j < nk; ++j) {
@@ -1058,6 +1080,10 @@ __global__ void __launch_bounds__((D >= 256 ? DT_THREADS : 384), (D >= 256 ? 1 :
       for (int i = r; i < DT_KEYS * H; i += 128) {
         const int j = i / H, h = i % H;
         float kcv = kMask, uv = 0.f;
+        if (!uctx) {   // masked keys: their context terms are still READ by the epilogue (whole chunks of 8 columns)
+          reinterpret_cast<float4*>(&s.km[st][j][h][0])[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(&s.km[st][j][h][0])[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (j < nk && a.row_src[sg.x + k0 + j] >= 0) {
           const long long row = (long long)sg.x + k0 + j;
           uv = a.U[row * H + h];

@@ -316,11 +316,11 @@ def rows_plan(model, table: ItemAttrTable, n_ctx: int):
 _rows_scratch_cache: dict = {}
 
 
-def _rows_scratch(ent, B: int, L: int, device) -> Tensor:
-    key = (str(device), int(B), int(L), int(ent.m.embed.d), int(ent.m.n_heads))
+def _rows_scratch(ent, B: int, L: int, device, lane: int = 0) -> Tensor:
+    key = (str(device), int(B), int(L), int(ent.m.embed.d), int(ent.m.n_heads), int(lane))
     buf = _rows_scratch_cache.get(key)
     if buf is None:
-        if len(_rows_scratch_cache) > 6:
+        if len(_rows_scratch_cache) > 12:
             _rows_scratch_cache.clear()
         nbytes = int(N.lib().carca_rows_scratch_bytes(C.byref(ent.m), int(B), int(L)))
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -355,12 +355,57 @@ def forward_rows(model, profile, targets: Sequence, precision: str = "bf16", cat
         T = o_x.shape[1]
     ent = rows_plan(model, table, n_ctx)
     y = torch.empty((B, T), dtype=torch.float32, device=p_x.device)
-    N.call("carca_rows_eval_forward", N.f32p(y), T, 0, ent.rows.data_ptr(), N.f32p(ent.plan), C.byref(ent.m), N.i32p(p_x),
-           N.f32p(p_c),
-           None if o_x is None else N.i32p(o_x), N.f32p(o_c), B, L, T, int(per_user_ctx), int(cat_lo),
-           {"bf16": 0, "fp32": 1}[precision], N.i32p(ent.status), _rows_scratch(ent, B, L, p_x.device).data_ptr(),
-           N.stream())
+    prec = {"bf16": 0, "fp32": 1}[precision]
+
+    def run(b0: int, b1: int, lane: int) -> None:
+        N.call("carca_rows_eval_forward", N.f32p(y[b0:b1]), T, 0, ent.rows.data_ptr(), N.f32p(ent.plan), C.byref(ent.m),
+               N.i32p(p_x[b0:b1]), N.f32p(p_c[b0:b1]), None if o_x is None else N.i32p(o_x[b0:b1]), N.f32p(o_c[b0:b1]),
+               b1 - b0, L, T, int(per_user_ctx), int(cat_lo), prec, N.i32p(ent.status),
+               _rows_scratch(ent, b1 - b0, L, p_x.device, lane).data_ptr(), N.stream())
+
+    lanes = rows_lanes(B, L)
+    if lanes <= 1:
+        run(0, B, 0)
+        return y
+    # Users are independent, and with a few thousand users every stage of the pipeline is a short kernel bound by its
+    # own launch / fill / drain latency, not by throughput: slices of the batch run the whole pipeline side by side
+    # on separate streams (fork / join by events; capturable), each with its own scratch.
+    main = torch.cuda.current_stream(p_x.device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    step = -(-B // lanes)
+    for i in range(lanes):
+        b0, b1 = i * step, min(B, (i + 1) * step)
+        if b0 >= b1:
+            break
+        if i == 0:
+            run(b0, b1, 0)
+            continue
+        side = _lane_stream(p_x.device, i)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            run(b0, b1, i)
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
     return y
+
+
+ROWS_LANES = 1            # slices of a large batch that run the rows pipeline concurrently (see forward_rows)
+ROWS_LANE_MIN_USERS = 1024
+_lane_streams: dict = {}
+
+
+def rows_lanes(B: int, L: int) -> int:
+    return max(1, min(int(ROWS_LANES), B // ROWS_LANE_MIN_USERS))
+
+
+def _lane_stream(device, i: int):
+    key = (str(device), i)
+    st = _lane_streams.get(key)
+    if st is None:
+        st = _lane_streams[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def catalog_tc_supported(model, seq_len: int, n_ctx: int) -> bool:

@@ -105,3 +105,46 @@ def test_bf16_needs_a_supported_shape():
     p_x, _, p_c, o_x, _, o_c, _ = [t.to(DEV) for t in S.batch_of(z, "eval")]
     with torch.no_grad(), pytest.raises(RuntimeError, match="bf16"):
         model.forward((p_x, None, p_c), [(o_x, None, o_c)])
+
+
+def _fwd(model, d):
+    with torch.no_grad():
+        y = model.forward((d["p_x"], None, d["p_c"]), [(d["o_x"], None, d["o_c"])])
+    torch.cuda.synchronize()
+    return y.clone()
+
+
+@pytest.mark.parametrize("case", ["beauty_sparse", "beauty_all_valid", "beauty_L129", "beauty_L130_fallback", "men_all_valid",
+                                  "men_h8"])
+def test_tensor_core_attention_matches_cuda_core_attention(case, monkeypatch):
+    """rows_attn_tc_kernel (tcgen05 QK^T / PV with the key window of a 128-row tile, L <= 129) against the CUDA-core
+    attention kernel it replaces (CARCA_ROWS_ATTN_FFMA=1) on the same batch: both are bf16-operand / fp32-softmax
+    computations of src/carca.py:246-256, so they agree to bf16 rounding.  Run twice with the pipeline's scratch
+    filled with NaN patterns in between: no result may depend on memory the step did not write."""
+    from carca_replication_b200 import fused, synth
+
+    men = dataclasses.replace(synth.MEN, n_items=3000, n_attrs=96)
+    shape, B, all_valid = {
+        "beauty_sparse": (_beauty(), 700, False), "beauty_all_valid": (_beauty(), 333, True),
+        "beauty_L129": (_beauty(129), 150, True), "beauty_L130_fallback": (_beauty(130), 40, True),
+        "men_all_valid": (men, 100, True), "men_h8": (dataclasses.replace(men, n_heads=8), 300, False)}[case]
+    model = synth.build_model(shape, "ca", p=0.5, seed=5).to(DEV).eval().set_eval_dtype("bf16")
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=5).to(DEV))
+    d = {k: v.to(DEV) for k, v in synth.make_eval_batch(shape, B, seed=5, all_valid=all_valid).items()}
+    monkeypatch.setenv("CARCA_ROWS_ATTN_FFMA", "1")
+    y_cc = _fwd(model, d)
+    monkeypatch.delenv("CARCA_ROWS_ATTN_FFMA")
+    y_tc = _fwd(model, d)
+    for buf in fused._rows_scratch_cache.values():
+        buf.fill_(255)
+    y_tc2 = _fwd(model, d)
+    assert not fused.mma_timed_out(model)
+    assert not torch.isnan(y_tc).any() and not torch.isnan(y_tc2).any()
+    assert float((y_tc - y_cc).abs().max()) < 5e-3
+    assert float((y_tc2 - y_tc).abs().max()) < 2e-3      # (row order of the packing pass differs from run to run)
+    if case == "men_h8":       # 8 heads: the CUDA-core decoder runs one warp per head (256 threads), fp32 flavour alike
+        model.set_eval_dtype("fp32")
+        model.force_eval_path = "rows_fp32"
+        assert float((_fwd(model, d) - y_tc).abs().max()) < S.BF16_TOL
+    if case == "beauty_L130_fallback":
+        assert torch.equal(y_tc, y_cc)                    # window > 256 keys: the CUDA-core kernel serves both calls
