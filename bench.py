@@ -1058,7 +1058,7 @@ def time_train(shape, args, dev, table):
                             "per_op_kernels": {"value": Bl / (ms_lp * 1e-3), "ms_per_step": ms_lp}}}
 
 
-def time_train_dp(shape, args, dev, table, rank, world):
+def time_train_dp(shape, args, dev, table, rank, world, peer=True):
     """Data-parallel train step: every rank runs the fused step on its own `--train-batch` users
     (weak scaling), the flat gradient buffer is all-reduced in place over NCCL (one collective per step, plus the
     two BCE partial sums), FusedAdam steps the replicated weights.  Timed on the device, max over ranks; as one
@@ -1073,7 +1073,7 @@ def time_train_dp(shape, args, dev, table, rank, world):
     L, Bt = shape.seq_len, args.train_batch
     model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
     model.embeds.set_attr_table(table)
-    dp = UserDataParallel(model)
+    dp = UserDataParallel(model, peer_allreduce=peer)
     optim = cb.FusedAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
     batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=77 + 10 * rank + i).items()}
                for i in range(4)]
@@ -1106,8 +1106,12 @@ def time_train_dp(shape, args, dev, table, rank, world):
 
     n = max(args.steps, 5)
     ms_e, loss_e = clock(lambda i: eager_step(batches[i % 4]), n)
+    peer_on = dp.peer is not None
     out = {"unit": "seqs/s", "batch_per_gpu": Bt, "global_batch": Bt * world, "scaling": "weak",
-           "collective": "one in-place NCCL all-reduce of the flat gradient buffer per step + 2 floats of BCE sums",
+           "collective": ("one peer-memory all-reduce kernel (csrc/peer.cu, NVLink loads / stores on CUDA-IPC mapped "
+                          "buffers, zero-copy: the flat gradient buffer lives in the communication buffer) per step + "
+                          "2 floats of BCE sums the same way; no NCCL kernel in the step") if peer_on else
+                         "one in-place NCCL all-reduce of the flat gradient buffer per step + 2 floats of BCE sums",
            "eager": {"value": world * Bt / (ms_e * 1e-3), "ms_per_step": ms_e, "final_loss": loss_e}}
     ok = torch.ones(1, device=dev)
     try:
@@ -1119,9 +1123,17 @@ def time_train_dp(shape, args, dev, table, rank, world):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if ok.item() > 0:
         out.update({"value": world * Bt / (ms_g * 1e-3), "ms_per_step": ms_g, "final_loss": loss_g,
-                    "mode": "whole data-parallel step (incl. the NCCL all-reduce) replayed as one CUDA graph per rank"})
+                    "mode": "whole data-parallel step (incl. the gradient all-reduce) replayed as one CUDA graph per rank"})
     else:
         out.update({"value": out["eager"]["value"], "ms_per_step": ms_e, "mode": "eager"})
+    if peer_on:
+        out["peer_allreduce_timed_out"] = bool(dp.peer.timed_out() or dp._peer_small.timed_out())
+    from carca_replication_b200 import ops as _ops
+
+    _ops.FLAT_GRAD_ALLOC = None
+    if peer and peer_on:      # the same step with NCCL as the collective, for the comparison
+        nccl = time_train_dp(shape, args, dev, table, rank, world, peer=False)
+        out["nccl_allreduce"] = {k: nccl[k] for k in ("value", "ms_per_step", "mode") if k in nccl}
     return out
 
 

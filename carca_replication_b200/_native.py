@@ -150,6 +150,14 @@ SIGNATURES = {
     "carca_rows_catalog_scratch_bytes": [P(ModelParams), i32, i32],
     "carca_rows_catalog_counts": [vp, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],
+    "carca_peer_buffer_bytes": [i64],
+    "carca_peer_data_offset": [],
+    "carca_peer_alloc": [vp, i64],
+    "carca_peer_free": [vp],
+    "carca_peer_export": [vp, vp],
+    "carca_peer_open": [vp, vp],
+    "carca_peer_close": [vp],
+    "carca_peer_allreduce": [vp, i64, vp, i32, i32, vp, vp],
     "carca_umma_selftest": [vp, vp, vp, i32, i32, i32, vp, vp],
     "carca_umma_probe": [vp, vp, i32, vp, i32, i32, i32, u32, u32, u32, u32, u32, u32, u32, vp, vp],
 }
@@ -168,6 +176,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.carca_eval_plan_floats.restype = C.c_int64
     lib.carca_eval_scratch_bytes.restype = C.c_int64
     lib.carca_rows_plan_bytes.restype = C.c_int64
+    lib.carca_peer_buffer_bytes.restype = C.c_int64
+    lib.carca_peer_data_offset.restype = C.c_int64
     lib.carca_rows_scratch_bytes.restype = C.c_int64
     lib.carca_rows_catalog_scratch_bytes.restype = C.c_int64
     lib.carca_train_core_set_ticks.restype = None

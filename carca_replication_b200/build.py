@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcarca_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "umma_selftest.cu", "rows.cu"]
+SOURCES = ["api.cu", "gemm.cu", "umma_selftest.cu", "rows.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -434,13 +434,19 @@ class CrossScoreFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------- fused training core
+# Optional provider of the flat gradient buffer: (n_floats, device) -> float32 tensor or None.  The data-parallel wrapper
+# installs one that returns peer-mapped communication memory (parallel.PeerAllReduce.buffer).
+FLAT_GRAD_ALLOC = None
+
+
 class _FlatZeros:
     """Carves zero-initialised gradient tensors out of ONE zero-filled buffer (one fill launch instead of one
     per parameter)."""
 
     def __init__(self, shapes, device):
         sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh in shapes]      # 16-byte aligned pieces
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        flat = FLAT_GRAD_ALLOC(sum(sizes), device) if FLAT_GRAD_ALLOC is not None else None
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device) if flat is None else flat.zero_()
         self.views, off = [], 0
         for sh, n in zip(shapes, sizes):
             self.views.append(self.flat[off:off + int(torch.Size(sh).numel())].view(sh))

@@ -25,6 +25,116 @@ from torch import Tensor
 from .carca import BinaryCrossEntropy
 
 
+class PeerAllReduce:
+    """Sum of a flat fp32 CUDA tensor over the ranks of one NVLink / NVSwitch box in ONE kernel on peer-mapped memory
+    (csrc/peer.cu: copy-in, per-block handshake, owner-reduces-and-pushes, handshake, copy-out) — the gradient
+    exchange of the data-parallel step without NCCL in the step: one graph node, bit-identical sums on every rank.
+    torch.distributed is only the bootstrap here (the CUDA IPC handles travel through all_gather_object).
+
+    Collective constructor: every rank of `group` must build it with the same capacity.  `available` is False (and
+    all_reduce_ raises) when the buffers could not be mapped, e.g. ranks on different nodes; callers fall back to
+    dist.all_reduce then."""
+
+    def __init__(self, capacity_floats: int, device, process_group=None):
+        import ctypes as C
+
+        from . import _native as N
+
+        self.group = process_group
+        self.rank = dist.get_rank(process_group)
+        self.world = dist.get_world_size(process_group)
+        self.capacity = int(capacity_floats)
+        self.device = torch.device(device)
+        self.available = False
+        self.error: Optional[str] = None
+        self._base = C.c_void_p()
+        self._peers: List[Optional[int]] = [None] * self.world
+        self._bases = None
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        handle = None
+        try:
+            if self.world > 8 or self.device.type != "cuda":
+                raise RuntimeError("needs 2..8 CUDA ranks of one box")
+            with torch.cuda.device(self.device):
+                nbytes = int(N.lib().carca_peer_buffer_bytes(self.capacity))
+                N.call("carca_peer_alloc", C.byref(self._base), nbytes)
+                buf = C.create_string_buffer(64)
+                N.call("carca_peer_export", self._base, buf)
+                handle = bytes(buf.raw)
+        except (RuntimeError, OSError) as ex:
+            self.error = f"{type(ex).__name__}: {ex}"[:200]
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, handle, group=process_group)        # collective even when a rank failed
+        ok = self.error is None and all(h is not None for h in handles)
+        if ok:
+            try:
+                with torch.cuda.device(self.device):
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            self._peers[r] = self._base.value
+                            continue
+                        ptr = C.c_void_p()
+                        N.call("carca_peer_open", C.create_string_buffer(h, 64), C.byref(ptr))
+                        self._peers[r] = ptr.value
+                self._bases = (C.c_void_p * self.world)(*self._peers)
+            except (RuntimeError, OSError) as ex:
+                self.error = f"{type(ex).__name__}: {ex}"[:200]
+                ok = False
+        flags: List[Optional[bool]] = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=process_group)         # all ranks or none (also the setup barrier)
+        self.available = all(flags)
+        if not self.available and self.error is None:
+            self.error = "a peer rank could not map the buffers"
+
+    def all_reduce_(self, t: Tensor) -> Tensor:
+        from . import _native as N
+
+        if not self.available:
+            raise RuntimeError(f"PeerAllReduce is not available: {self.error}")
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda or t.numel() > self.capacity:
+            raise RuntimeError("PeerAllReduce.all_reduce_: needs a contiguous float32 CUDA tensor within the capacity")
+        N.call("carca_peer_allreduce", t.data_ptr(), t.numel(), self._bases, self.rank, self.world, N.i32p(self.status),
+               N.stream())
+        return t
+
+    def buffer(self, n_floats: int) -> Tensor:
+        """A float32 tensor of n elements that LIVES in this rank's communication buffer: all_reduce_ of it is zero-copy
+        (peers read it and write the sums straight into it).  One tensor at a time: every call returns the same memory."""
+        if not self.available or n_floats > self.capacity:
+            raise RuntimeError("PeerAllReduce.buffer: not available or beyond the capacity")
+        from . import _native as N
+
+        class _Region:          # torch.as_tensor aliases foreign device memory through the CUDA array interface
+            pass
+
+        reg = _Region()
+        reg.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "version": 2, "strides": None,
+                                        "data": (self._base.value + int(N.lib().carca_peer_data_offset()), False)}
+        reg.owner = self        # the buffer outlives every tensor carved from it
+        return torch.as_tensor(reg, device=self.device)
+
+    def data_ptr(self) -> int:
+        from . import _native as N
+
+        return self._base.value + int(N.lib().carca_peer_data_offset())
+
+    def timed_out(self) -> bool:
+        """True if a wait inside an all-reduce gave up (a peer did not arrive within ~20 s).  Host sync."""
+        return bool(int(self.status.item()) & 8)
+
+    def close(self) -> None:
+        from . import _native as N
+
+        if self._base.value is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for r, ptr in enumerate(self._peers):
+            if ptr is not None and r != self.rank:
+                N.lib().carca_peer_close(ptr)
+        N.lib().carca_peer_free(self._base)
+        self._base.value, self._peers, self.available = None, [None] * self.world, False
+
+
 class ShardedLoader:
     """Wraps a loader of GLOBAL batches; yields this rank's slice of each (keeps len() for train())."""
 
@@ -40,7 +150,7 @@ class ShardedLoader:
 
 
 class UserDataParallel:
-    def __init__(self, module: torch.nn.Module, process_group=None, broadcast: bool = True):
+    def __init__(self, module: torch.nn.Module, process_group=None, broadcast: bool = True, peer_allreduce: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("UserDataParallel needs torch.distributed to be initialised")
         self.module = module
@@ -51,6 +161,23 @@ class UserDataParallel:
         self._sizes = [p.numel() for p in self.params]
         self._bucket: Optional[Tensor] = None
         self._queued = False
+        # gradient exchange over peer memory (one kernel, no NCCL in the step) where the ranks share an NVLink box
+        self.peer: Optional[PeerAllReduce] = None
+        self._peer_small: Optional[PeerAllReduce] = None
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        if peer_allreduce and self.world > 1 and dev.type == "cuda":
+            from . import _native
+
+            if not _native.is_emulated():
+                n = sum(self._sizes)
+                self.peer = PeerAllReduce(2 * n + 64, dev, process_group)
+                self._peer_small = PeerAllReduce(256, dev, process_group)
+                if not (self.peer.available and self._peer_small.available):
+                    self.peer = self._peer_small = None
+                else:
+                    from . import ops
+
+                    ops.FLAT_GRAD_ALLOC = self._grad_buffer_in_peer_memory
         self.loss_fn = BinaryCrossEntropy()
         self.loss_fn.reduce_sums = self._allreduce_sum
         from . import ops
@@ -78,7 +205,7 @@ class UserDataParallel:
         if flat is not None:
             # the fused training step (ops.TrainCoreFn) produces every gradient inside one flat buffer:
             # all-reduce it in place — no bucket copies
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._sum(flat)
             return
         if self._bucket is None or self._bucket.device != dev:
             self._bucket = torch.empty(sum(self._sizes), dtype=torch.float32, device=dev)
@@ -88,7 +215,7 @@ class UserDataParallel:
                 v.zero_()
             else:
                 v.copy_(p.grad.reshape(-1))
-        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM, group=self.group)   # the one collective
+        self._sum(self._bucket)                                                  # the one collective
         for p, v in zip(self.params, views):
             if p.grad is None:
                 p.grad = v.reshape(p.shape).clone()
@@ -110,9 +237,30 @@ class UserDataParallel:
             return None
         return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(storage, lo, (hi - lo,))
 
+    def _grad_buffer_in_peer_memory(self, n_floats: int, device) -> Optional[Tensor]:
+        """ops._FlatZeros hook: the fused training step's flat gradient buffer is carved out of the communication
+        buffer, so its all-reduce needs no staging copy.  Not while a parameter still holds gradients of an earlier
+        backward in that memory (gradient accumulation over several backwards): then the step gets ordinary memory."""
+        if self.peer is None or torch.device(device) != self.peer.device or n_floats > self.peer.capacity:
+            return None
+        base = self.peer.data_ptr()
+        for p in self.params:
+            if p.grad is not None and p.grad.untyped_storage().data_ptr() == base:
+                return None
+        return self.peer.buffer(n_floats)
+
+    def _sum(self, t: Tensor) -> None:
+        """In-place sum over ranks: the peer-memory kernel when the ranks share an NVLink box, else NCCL / gloo."""
+        if self.peer is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0:
+            comm = self._peer_small if t.numel() <= self._peer_small.capacity else self.peer
+            if t.numel() <= comm.capacity:
+                comm.all_reduce_(t)
+                return
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
     def _allreduce_sum(self, t: Tensor) -> None:
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._sum(t)
 
     # -------------------------------------------------------------- sharding helpers
     def shard(self, batch: Sequence[Optional[Tensor]]) -> tuple:

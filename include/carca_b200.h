@@ -542,6 +542,28 @@ int carca_umma_probe(float* C, const float* a_img, int a_floats, const float* b_
                      int ksteps, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t b_lbo, uint32_t b_sbo,
                      uint32_t b_step, uint32_t idesc, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Peer all-reduce (csrc/peer.cu): sum of a flat fp32 tensor over the GPUs of one NVLink / NVSwitch box in ONE kernel
+ * on peer-mapped memory — the gradient exchange of the data-parallel training step (the reference is
+ * single-device: src/train.py:90-97 has no counterpart for it).  Every rank allocates a communication buffer of
+ * carca_peer_buffer_bytes(n) bytes, exports its 64-byte CUDA IPC handle, and opens the handles of its peers (the
+ * handles travel through whatever the host uses for bootstrap, e.g. torch.distributed.all_gather_object).
+ * carca_peer_allreduce: `local` (n floats, 16-byte aligned) is summed IN PLACE over all ranks; `bases` is a HOST array
+ * of `world` device pointers (bases[rank] = this rank's own buffer, the others as returned by carca_peer_open); all
+ * ranks must call it with the same n, in the same order.  Every rank receives bit-identical sums (each element is
+ * reduced by one owner rank in rank order).  status (device int32[1]): bit 8 is set if a peer did not arrive within
+ * ~20 s (results invalid) — a wait never hangs the GPU.  world <= 8.  carca_peer_data_offset: byte offset of the data
+ * region inside a communication buffer; a tensor that lives there (local == own base + offset, its tail up to the
+ * next multiple of 4 floats readable and writable) is reduced in place without staging copies.                    */
+int64_t carca_peer_data_offset(void);
+int64_t carca_peer_buffer_bytes(int64_t n_floats);
+int carca_peer_alloc(void** base, int64_t bytes);
+int carca_peer_free(void* base);
+int carca_peer_export(void* base, void* handle64);
+int carca_peer_open(const void* handle64, void** base);
+int carca_peer_close(void* base);
+int carca_peer_allreduce(float* local, int64_t n, void* const* bases, int rank, int world, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

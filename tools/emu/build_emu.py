@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "carca_replication_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "gemm.cu", "umma_selftest.cu", "rows.cu"]
+SOURCES = ["api.cu", "gemm.cu", "umma_selftest.cu", "rows.cu", "peer.cu"]
 
 
 def build(asan: bool = False, force: bool = False) -> str:
