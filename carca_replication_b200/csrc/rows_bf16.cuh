@@ -945,7 +945,7 @@ namespace rows {
 // sigmoid(att + <o, wf> + bf).  Users with more than 64 keys take several key chunks (online softmax across chunks).
 // Two stages: the gather of item i+1 runs under the MMAs / epilogue of item i.
 constexpr int DT_KEYS = 64;
-constexpr int DT_THREADS = 288;   // warps 0..3 epilogue, 4 MMA, 5..8 producers
+constexpr int DT_THREADS = 416;   // warps 0..3 epilogue, 4 MMA, 5..8 producers of stage 0, 9..12 producers of stage 1
 
 template <int D, int H>
 struct DecTcSmem {
@@ -985,8 +985,8 @@ struct DecTcArgs {
 };
 
 template <int D, int H>
-// (d = 64: two CTAs per SM; 9 warps are allocated as 12, so the register budget is that of a 384-thread block)
-__global__ void __launch_bounds__((D >= 256 ? DT_THREADS : 384), (D >= 256 ? 1 : 2)) rows_decode_tc_kernel(const DecTcArgs a) {
+// (d = 64: two CTAs per SM)
+__global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc_kernel(const DecTcArgs a) {
   using SM = DecTcSmem<D, H>;
   constexpr int DH = D / H, KG = D / 8, NST = SM::NST;
   constexpr float kMask = -1.0e30f;
@@ -1027,10 +1027,14 @@ __global__ void __launch_bounds__((D >= 256 ? DT_THREADS : 384), (D >= 256 ? 1 :
   };
 
   if (warp >= 5) {
-    // ===== producers: thread r gathers candidate row r of the tile and helps staging the keys
-    const int r = threadIdx.x - 160;
+    // ===== producers: thread r gathers candidate row r of the tile and helps staging the keys.  A step is a chain of
+    // dependent global loads (candidate id -> table row, user segment -> key rows -> their terms): the two producer
+    // groups each own one stage and take every other step, so two such chains are always in flight per CTA
+    static_assert(NST == 2, "one producer group per stage");
+    const int grp = (warp - 5) >> 2, r = threadIdx.x - 160 - 128 * grp;
     for_each_step([&](uint32_t it, int u, int t0, int2 sg, int k0, int nk, bool last) {
       const int st = it % NST, ph = (it / NST) & 1;
+      if (st != grp) return true;
       if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
       if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
       const int t = t0 + r;
@@ -1103,11 +1107,11 @@ __global__ void __launch_bounds__((D >= 256 ? DT_THREADS : 384), (D >= 256 ? 1 :
         s.kc[st][h][j] = kcv;
         s.uu[st][h][j] = uv;
       }
-      // this thread's copies and stores are complete and visible to the tensor core's (async-proxy) reads
-      // (with two stages a lagged arrival would serialise the steps; at d = 64 two CTAs per SM hide this wait)
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // this thread's stores are visible to the tensor core's (async-proxy) reads; its ARRIVAL is deferred to the
+      // completion of its gather copies (cp.async.mbarrier.arrive.noinc: one of the barrier's 128 expected arrivals,
+      // delivered by the copy unit), so the thread moves on to the next stage's gather without waiting for this one
       umma::fence_smem_to_async();
-      mbar_arrive(&s.full[st]);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(&s.full[st])) : "memory");
       return true;
     });
   } else if (warp == 4) {

@@ -434,7 +434,7 @@ class CrossScoreFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------- fused training core
-# Optional provider of the flat gradient buffer: (n_floats, device) -> float32 tensor or None.  The data-parallel wrapper
+# Optional provider of the flat gradient buffer: (n_floats, device, parameter tensors) -> float32 tensor or None.  The data-parallel wrapper
 # installs one that returns peer-mapped communication memory (parallel.PeerAllReduce.buffer).
 FLAT_GRAD_ALLOC = None
 
@@ -443,9 +443,9 @@ class _FlatZeros:
     """Carves zero-initialised gradient tensors out of ONE zero-filled buffer (one fill launch instead of one
     per parameter)."""
 
-    def __init__(self, shapes, device):
+    def __init__(self, shapes, device, params=()):
         sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh in shapes]      # 16-byte aligned pieces
-        flat = FLAT_GRAD_ALLOC(sum(sizes), device) if FLAT_GRAD_ALLOC is not None else None
+        flat = FLAT_GRAD_ALLOC(sum(sizes), device, params) if FLAT_GRAD_ALLOC is not None else None
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device) if flat is None else flat.zero_()
         self.views, off = [], 0
         for sh, n in zip(shapes, sizes):
@@ -549,7 +549,7 @@ class TrainCoreFn(torch.autograd.Function):
             shapes.append((int(N.lib().carca_train_core_fold_floats(c.embed)),))
         else:
             shapes += [t0.shape, t1.shape] + ([t2.shape] if t2 is not None else [])
-        z = _FlatZeros(shapes, dev)
+        z = _FlatZeros(shapes, dev, params)
         egrads = z.views[:n_emb]
         grads = z.views[n_emb:n_emb + len(core)]
         extra = z.views[n_emb + len(core):]

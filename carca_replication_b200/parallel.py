@@ -237,12 +237,15 @@ class UserDataParallel:
             return None
         return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(storage, lo, (hi - lo,))
 
-    def _grad_buffer_in_peer_memory(self, n_floats: int, device) -> Optional[Tensor]:
+    def _grad_buffer_in_peer_memory(self, n_floats: int, device, params=()) -> Optional[Tensor]:
         """ops._FlatZeros hook: the fused training step's flat gradient buffer is carved out of the communication
         buffer, so its all-reduce needs no staging copy.  Not while a parameter still holds gradients of an earlier
         backward in that memory (gradient accumulation over several backwards): then the step gets ordinary memory."""
         if self.peer is None or torch.device(device) != self.peer.device or n_floats > self.peer.capacity:
             return None
+        mine = {p.data_ptr() for p in self.params}
+        if not params or any(t.data_ptr() not in mine for t in params):
+            return None                       # a backward of some other model in this process
         base = self.peer.data_ptr()
         for p in self.params:
             if p.grad is not None and p.grad.untyped_storage().data_ptr() == base:
