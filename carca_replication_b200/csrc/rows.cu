@@ -10,6 +10,7 @@
 #include "plan_layout.cuh"
 #include "rows_bf16.cuh"
 #include "rows_attn_tc.cuh"
+#include "rows_ffn_chain.cuh"
 #include "catalog_tc.cuh"
 
 using namespace carca;
@@ -144,6 +145,19 @@ int launch_attn_tc(rows::AttnTcArgs& t, int L, cudaStream_t st) {
   return check_launch("rows_attn_tc");
 }
 
+int launch_ffn_chain(const rows::FfnChainArgs& f, cudaStream_t st) {
+  auto k = rows::rows_ffn_chain_kernel;
+  const size_t smem = sizeof(rows::FfnChainSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(-3, "rows_ffn_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CARCA_LAUNCH(k, dim3(148 * 2), dim3(rows::FC_THREADS), smem, st, f);
+  return check_launch("rows_ffn_chain");
+}
+
 template <int D, int H>
 int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const float* Tf, const carca_model_params* m,
               const int32_t* p_x, const float* p_c, const int32_t* o_x, const float* o_c, int B, int L, int T,
@@ -188,11 +202,13 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     TRY(check_launch("rows_embed_ln"));
   }
   const bool attn_tc = attn_tc_window(L) <= 256 && !getenv("CARCA_ROWS_ATTN_FFMA");
+  const bool chain = D == 64 && attn_tc && !getenv("CARCA_ROWS_NO_CHAIN");
   for (int b = 0; b < m->n_blocks; ++b) {
     const carca_block_params& bp = m->blocks[b];
     const bf16* wb = W + (long long)b * 5 * wsz;
     if (attn_tc) {
       // Q / K / V written as the attention's tensor-core operands, then the tcgen05 attention (rows_attn_tc.cuh)
+      if (!(chain && b > 0)) {      // (chained: the previous block's tail kernel has produced them)
       rows::GemmArgs g;
       memset(&g, 0, sizeof(g));
       g.n_jobs = 3; g.n_rows = n_rows; g.H = H; g.status = status;
@@ -201,6 +217,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       g.job[2].A = XA; g.job[2].W = wb + 2 * wsz; g.job[2].bias = bp.bv; g.job[2].epi = rows::EPI_VMN; g.job[2].out_tile = Vb;
       g.job[1].ld_rows = g.job[2].ld_rows = sc.Rp;
       TRY(launch_gemm_rows<D>(g, st));
+      }
       rows::AttnTcArgs t;
       memset(&t, 0, sizeof(t));
       t.Qt = Qb; t.Kk = Kb; t.Vm = Vb; t.Rp = sc.Rp; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
@@ -222,6 +239,28 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       auto k = rows::rows_attn_ln_kernel<D, H, false>;
       CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
       TRY(check_launch("rows_attn_ln"));
+    }
+    if (chain) {
+      // FFN-1 -> FFN-2 + next LayerNorm -> next block's Q / K / V (or the decoder's K / V): one kernel, the intermediate
+      // operands stay in shared memory (rows_ffn_chain.cuh)
+      const bool last = b + 1 == m->n_blocks;
+      rows::FfnChainArgs f;
+      memset(&f, 0, sizeof(f));
+      f.A = S2A; f.W12 = wb + 3 * wsz; f.b1 = bp.b1; f.b2 = bp.b2;
+      f.resid = m->residual_sa ? S2 : nullptr;
+      f.ln_g = last ? m->norm_g : m->blocks[b + 1].ln1_g;
+      f.ln_b = last ? m->norm_b : m->blocks[b + 1].ln1_b;
+      f.out_f32 = QN; f.n_rows = n_rows; f.H = H; f.status = status;
+      if (!last) {
+        const carca_block_params& nb = m->blocks[b + 1];
+        f.tail = 1; f.W3 = wb + 5 * wsz; f.bq = nb.bq; f.bk = nb.bk; f.bv = nb.bv;
+        f.Qt = Qb; f.Kk = Kb; f.Vm = Vb; f.ld_rows = sc.Rp;
+      } else if (m->decoder_kind == 1) {
+        f.tail = 2; f.W3 = reinterpret_cast<const bf16*>(plan + pl.dw); f.bk = m->cross.bk; f.bv = m->cross.bv;
+        f.Kd = S2; f.McQ = reinterpret_cast<const float*>(plan + pl.mcq); f.KM = KM; f.wf = m->cross.wf; f.U = U;
+      }
+      TRY(launch_ffn_chain(f, st));
+      continue;
     }
     {
       rows::GemmArgs g;
@@ -264,7 +303,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     g.job[0].out_f32 = S2; g.job[0].McQ = reinterpret_cast<const float*>(plan + pl.mcq); g.job[0].KM = KM;
     g.job[1].A = QA; g.job[1].W = dw + wsz; g.job[1].bias = m->cross.bv; g.job[1].epi = rows::EPI_VDOT;
     g.job[1].wf = m->cross.wf; g.job[1].U = U;
-    TRY(launch_gemm_rows<D>(g, st));
+    if (!chain) TRY(launch_gemm_rows<D>(g, st));      // (chained: the last block's tail kernel has produced them)
     (void)Kb;
     if (H <= 4 && !getenv("CARCA_ROWS_FFMA_DECODE")) {   // tensor-core decoder (rows_decode_tc_kernel)
       rows::DecTcArgs t;
