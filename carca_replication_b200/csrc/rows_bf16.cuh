@@ -1018,8 +1018,10 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
   // step `it`: user u, tile, key chunk k0 .. k0 + nk
   auto for_each_step = [&](auto&& body) {
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < (long long)a.B * n_tiles; item += gridDim.x) {
-      const int u = (int)(item / n_tiles), t0 = (int)(item % n_tiles) * 128;
+    const unsigned n_items = (unsigned)a.B * (unsigned)n_tiles;       // (B < 2^23, a few tiles per user)
+    for (unsigned item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int u = n_tiles == 1 ? (int)item : (int)(item / (unsigned)n_tiles);
+      const int t0 = n_tiles == 1 ? 0 : (int)(item % (unsigned)n_tiles) * 128;
       const int2 sg = a.useg[u];
       for (int k0 = 0; k0 < max(sg.y, 1); k0 += DT_KEYS, ++it)
         if (!body(it, u, t0, sg, k0, min(DT_KEYS, sg.y - k0), k0 + DT_KEYS >= sg.y)) return;
@@ -1035,12 +1037,23 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
     for_each_step([&](uint32_t it, int u, int t0, int2 sg, int k0, int nk, bool last) {
       const int st = it % NST, ph = (it / NST) & 1;
       if (st != grp) return true;
-      if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
-      if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
+      // Everything that comes from global memory into REGISTERS is requested before the stage is waited for: the id ->
+      // table-row chain and the key rows then overlap the MMAs / epilogue still running on this stage.
       const int t = t0 + r;
       const int id = t < a.T ? (a.cat_lo > 0 ? a.cat_lo + t : __ldg(a.o_x + (long long)u * a.T + t)) : 0;
-      {   // what the epilogue needs of this row, so that it reads no global memory
-        float cv[8], res = 0.f;
+      constexpr int KPT = D == 64 ? KG / 2 : 0;      // key k-groups of this thread held in registers (d = 64 only)
+      uint4 kreg[KPT > 0 ? KPT : 1];
+      if (KPT > 0 && (r >> 1) < nk) {
+        const float* kr = a.Kd + (long long)(sg.x + k0 + (r >> 1)) * D;
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+          float v[8];
+          ldg256(kr + 8 * ((r & 1) * KPT + q), v);
+          kreg[q] = pack8(v);
+        }
+      }
+      float cv[8], res = 0.f;
+      {
 #pragma unroll
         for (int k = 0; k < 8; ++k) cv[k] = 0.f;
         if (id != 0) {
@@ -1051,6 +1064,10 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
             for (int k = 0; k < a.C; ++k) res = fmaf(__ldg(a.mcw + k), cv[k], res);
           }
         }
+      }
+      if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
+      if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
+      {   // what the epilogue needs of this row, so that it reads no global memory
         s.rid[st][r] = t < a.T ? id : -1;
         s.rres[st][r] = res;
         if (!uctx) {
@@ -1071,12 +1088,17 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
         const int j = r >> 1, hf = r & 1;
         uint4* kd = reinterpret_cast<uint4*>(s.k[st]);
         if (j < nk) {
-          const float* kr = a.Kd + (long long)(sg.x + k0 + j) * D;
+          if (KPT > 0) {
+#pragma unroll
+            for (int q = 0; q < KPT; ++q) kd[(hf * KPT + q) * DT_KEYS + j] = kreg[q];
+          } else {
+            const float* kr = a.Kd + (long long)(sg.x + k0 + j) * D;
 #pragma unroll 4
-          for (int kg = hf * (KG / 2); kg < (hf + 1) * (KG / 2); ++kg) {
-            float v[8];
-            ldg256(kr + 8 * kg, v);
-            kd[kg * DT_KEYS + j] = pack8(v);
+            for (int kg = hf * (KG / 2); kg < (hf + 1) * (KG / 2); ++kg) {
+              float v[8];
+              ldg256(kr + 8 * kg, v);
+              kd[kg * DT_KEYS + j] = pack8(v);
+            }
           }
         }
       }
