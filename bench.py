@@ -5,12 +5,15 @@ forward + BCE + HR@10/NDCG@10), Beauty-shaped synthetic data.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one evaluate() batch body (src/train.py:42-51) over `--batch` users per GPU.
+One step = one evaluate() batch body (src/train.py:42-51) over `--batch` users per GPU.  `--dtype bf16` (default:
+BASELINE configs[1] "bf16/fp32", north_star "bf16 within 1e-2") runs the headline legs through the bf16 packed-rows
+pipeline; the fp32 path (3xTF32, within 1e-4) is then the `fp32` section of the line — and vice versa with --dtype fp32.
   value : users/s with the step's inputs already resident in HBM (device-timed, CUDA events)
   e2e   : same metric through the public API from pinned HOST buffers: per step the ids/context
           H2D copies, forward, metrics and the D2H read of the accumulators are inside the timed region
           (the step is replayed through carca_replication_b200.graph.GraphedEvalStep; --e2e-eager: eager calls)
-  roofline / ops : per C-ABI op device time measured live with CUDA events, against MEASURED_PEAKS.json
+  roofline / ops / kernels : per C-ABI op (and, for the rows pipeline, per kernel) device time measured live with
+          CUDA events, against MEASURED_PEAKS.json
   cpu_baseline : the oracle port of the reference timed on this box's host cores (bounded sample)
   train : fwd + BCE + bwd + Adam step seqs/s at the reference's batch size (256 per GPU)
 `--impl reference` times the reference's CPU path (oracle port, all host threads) on a bounded sample.
@@ -39,6 +42,8 @@ def parse():
     ap.add_argument("--shape", default="beauty", choices=["beauty", "men", "tiny"])
     ap.add_argument("--decoder", default="ca", choices=["ca", "dot"])
     ap.add_argument("--batch", type=int, default=8192, help="users per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="arithmetic of the headline legs (BASELINE configs[1] 'bf16/fp32'); the other one is a section")
     ap.add_argument("--train-batch", type=int, default=256)
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,6 +299,10 @@ def run_ours(args):
     model = model.to(dev).eval()
     model.embeds.set_attr_table(table)
     loss_fn = cb.BinaryCrossEntropy()
+    from carca_replication_b200 import fused as fused_
+    if args.dtype == "bf16" and not fused_.rows_supported(model, shape.seq_len, shape.n_ctx, "bf16"):
+        args.dtype = "fp32"                      # (a shape the bf16 pipeline does not cover, e.g. --shape tiny)
+    model.set_eval_dtype(args.dtype)
 
     names = ("p_x", "p_c", "o_x", "o_c", "y_true")
     host = [synth.make_eval_batch(shape, B, seed=1000 * rank + i) for i in range(args.rotate)]
@@ -480,7 +489,12 @@ def run_ours(args):
     pk = peaks()
     roof, ops_table = roofline(op_ms, shape, B, args.decoder, pk)
     _, per_op_table = roofline(op_ms_per_op_path, shape, B, args.decoder, pk)
-    if roof["kernel"] == "fused_forward":
+    stage_ms = None
+    if args.dtype == "bf16":
+        with torch.no_grad():
+            stage_ms = rows_stage_times(model, devb, max(K, 10))
+        roof = rows_roofline(stage_ms, ms_dev / K, op_ms, shape, B, args.decoder, pk)
+    elif roof["kernel"] == "fused_forward":
         # the SAME CUDA-event timing as `value`: kernel time = ms_per_step x the kernel's share of the step (the share
         # from per-op events around the two launches of a step, cross-checked by the committed ncu launch list)
         t_kernel_ms = (ms_dev / K) * roof["share_of_step"]
@@ -500,7 +514,8 @@ def run_ours(args):
 
     out = {
         "metric": "eval_users_per_sec", "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.dtype == "bf16" else "f32",
         "data": "synthetic", "config": dict(workload_config(args, shape, B),
                                             attrs="device-resident item->attribute table (CSR for multi-hot), "
                                                   "ids + context per step",
@@ -523,6 +538,13 @@ def run_ours(args):
         "ops_per_op_path": per_op_table,
         "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1], "host_numa": numa,
     }
+    out["config"]["arithmetic"] = (
+        "bf16 GEMM / attention operands and bf16 candidate table on the tensor cores (tcgen05 kind::f16), fp32 accumulation, "
+        "softmax, LayerNorm, residual stream, embedding gather and scorer (north_star: bf16 within 1e-2; tests/test_gpu_bf16.py); "
+        "the fp32 path (3xTF32, within 1e-4) is the `fp32` section" if args.dtype == "bf16" else
+        "fp32 contract (3xTF32 tensor-core products, scores within 1e-4 of the reference); the bf16 pipeline is the `bf16` section")
+    if stage_ms is not None:
+        out["kernels"] = stage_ms
 
     # worst case for the row packing: every profile position valid (one user per 64-row bin)
     with torch.no_grad():
@@ -549,18 +571,26 @@ def run_ours(args):
 
     if world > 1 and not args.no_train:
         optional("train", lambda: time_train_dp(shape, args, dev, table, rank, world))
+    def in_fp32(fn):          # full-catalog ranking is an fp32 contract (ranks bit-equal to the score-matrix path)
+        model.set_eval_dtype("fp32")
+        try:
+            return fn()
+        finally:
+            model.set_eval_dtype(args.dtype)
+
     if world > 1 and not args.no_catalog:
-        optional("catalog", lambda: time_catalog_sharded(model, shape, args, dev, rank, world))
+        optional("catalog", lambda: in_fp32(lambda: time_catalog_sharded(model, shape, args, dev, rank, world)))
     if world > 1 and not args.no_extra:
         optional("men", lambda: time_men(args, dev, pk, rank=rank, world=world))
     if world == 1 and rank == 0:
         if not args.no_train:
             optional("train", lambda: time_train(shape, args, dev, table))
         if not args.no_catalog:
-            optional("catalog", lambda: time_catalog(model, shape, args, dev))
+            optional("catalog", lambda: in_fp32(lambda: time_catalog(model, shape, args, dev)))
             optional("device_pipeline", lambda: time_device_pipeline(model, shape, args, dev))
         if not args.no_extra:
-            optional("bf16", lambda: time_bf16(model, shape, args, dev, devb, step, pk))
+            other = "fp32" if args.dtype == "bf16" else "bf16"
+            optional(other, lambda: time_other_dtype(model, shape, args, dev, devb, step, pk, other))
             optional("sweep", lambda: time_sweep(shape, args, dev, table))
             optional("men", lambda: time_men(args, dev, pk))
         if not args.no_cpu_baseline:
@@ -762,32 +792,121 @@ def device_batches(shape, B, dev, n=4, seed=0, all_valid=False):
     return out
 
 
-def time_bf16(model, shape, args, dev, devb, step, pk):
-    """BASELINE configs[1] "bf16/fp32": the same eval step with CARCA.eval_dtype = "bf16" (packed-rows pipeline:
-    tcgen05 kind::f16 GEMMs, fp32 accumulation / softmax / LayerNorm / embedding / decoder), and its deviation from the
-    fp32 path on the same batch."""
+def time_other_dtype(model, shape, args, dev, devb, step, pk, other):
+    """BASELINE configs[1] "bf16/fp32": the same eval step in the arithmetic the headline does NOT use, and the deviation
+    between the two on the same batch.  bf16 = packed-rows pipeline (tcgen05 kind::f16 GEMMs / attention / decoder scores,
+    fp32 accumulation / softmax / LayerNorm / embedding / scorer); fp32 = the one-kernel 3xTF32 forward (L <= 64) or
+    the fp32 flavour of the rows pipeline."""
     B = args.batch
+    main = model.eval_dtype
+    b0 = devb[0]
     with torch.no_grad():
-        y32 = step(devb[0]).clone()
-        model.set_eval_dtype("bf16")
+        y_main = step(b0).clone()
+        model.set_eval_dtype(other)
         try:
-            y16 = step(devb[0]).clone()
+            y_other = step(b0).clone()
+            path = model._fused_eval_mode((b0["p_x"], None, b0["p_c"]), [(b0["o_x"], None, b0["o_c"])])
             rate = graphed_rate(step, devb[:4], B, max(args.steps, 10))
             full = device_batches(shape, B, dev, n=2, seed=5000, all_valid=True)
             rate_full = graphed_rate(step, full, B, max(3, args.steps // 2))
         finally:
-            model.set_eval_dtype("fp32")
+            model.set_eval_dtype(main)
+    y32, y16 = (y_other, y_main) if other == "fp32" else (y_main, y_other)
     dp = float((y16 - y32).abs().max().item())
     hr32 = float(((y32[:, 1:] > y32[:, :1]).sum(1) < 10).double().mean().item())
     hr16 = float(((y16[:, 1:] > y16[:, :1]).sum(1) < 10).double().mean().item())
+    top = float(sum(len(set(a.tolist()) & set(b.tolist())) for a, b in
+                    zip(y32[:512].topk(10, dim=1).indices, y16[:512].topk(10, dim=1).indices)) / (10 * min(512, B)))
     fl = fwd_flops_per_user(shape, args.decoder)
-    return {"value": rate, "unit": "users/s", "dtype": "bf16 operands, fp32 accumulate / softmax / LayerNorm / decoder",
-            "path": "packed-rows pipeline (csrc/rows_bf16.cuh), whole step as one CUDA graph",
-            "max_abs_prob_diff_vs_fp32_path": dp, "hr10_fp32": hr32, "hr10_bf16": hr16,
+    return {"value": rate, "unit": "users/s", "path": path,
+            "dtype": ("bf16 operands, fp32 accumulate / softmax / LayerNorm / scorer" if other == "bf16" else
+                      "fp32 contract: 3xTF32 tensor-core products, everything else fp32"),
+            "max_abs_prob_diff_bf16_vs_fp32": dp, "hr10_fp32": hr32, "hr10_bf16": hr16, "top10_overlap_bf16_vs_fp32": top,
             "algorithmic_tflops": fl * rate / 1e12, "frac_of_bf16_peak": fl * rate / 1e12 / pk["bf16_tflops_sustained"],
             "all_valid_profiles": {"value": rate_full, "unit": "users/s",
                                    "algorithmic_tflops": fl * rate_full / 1e12,
                                    "frac_of_bf16_peak": fl * rate_full / 1e12 / pk["bf16_tflops_sustained"]}}
+
+
+ROWS_STAGE_NAMES = {1: "rows_pack", 2: "rows_embed_ln", 3: "rows_gemm(Q|K|V)", 4: "rows_attn", 5: "rows_gemm(FFN-1)",
+                    6: "rows_gemm(FFN-2+LN)", 7: "rows_ffn_chain", 8: "rows_gemm(decoder K|V)", 9: "rows_decode"}
+
+
+def rows_stage_times(model, devb, n):
+    """Average device ms of every kernel of the bf16 rows pipeline over n eager steps on rotated batches, from CUDA events
+    the library records on the launching stream between its launches (carca_rows_set_stage_events)."""
+    import ctypes as C
+
+    from carca_replication_b200 import _native as N
+
+    lib = N.lib()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(48)]
+    for e in evs:
+        e.record()                                # creates the handles
+    torch.cuda.synchronize()
+    arr = (C.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+    ids = (C.c_int32 * 64)()
+    acc = {}
+    try:
+        lib.carca_rows_set_stage_events(arr, len(evs))
+        for i in range(n + 2):
+            b = devb[i % len(devb)]
+            model.forward(profile=(b["p_x"], None, b["p_c"]), targets=[(b["o_x"], None, b["o_c"])])
+            torch.cuda.synchronize()
+            k = lib.carca_rows_stage_ids(ids, 64)
+            if i < 2:
+                continue
+            seen = {}
+            for j in range(1, k):
+                name = ROWS_STAGE_NAMES.get(ids[j], str(ids[j]))
+                seen[name] = seen.get(name, 0) + 1
+                a = acc.setdefault(name, [0.0, 0])
+                a[0] += evs[j - 1].elapsed_time(evs[j])
+                a[1] += 1
+    finally:
+        lib.carca_rows_set_stage_events(None, 0)
+    total = sum(a[0] for a in acc.values()) / n
+    return {"per_step_ms": {k: a[0] / n for k, a in acc.items()}, "launches_per_step": {k: a[1] / n for k, a in acc.items()},
+            "sum_ms": total, "timing": f"CUDA events between the launches of {n} eager steps on the launching stream"}
+
+
+def rows_roofline(stage_ms, ms_step, op_ms, shape, B, decoder, pk):
+    """Roofline line of the bf16 pipeline's dominant kernel.  Its time inside the timed region = ms_per_step x its share
+    of the step (shares from the per-kernel events); algorithmic work per DESIGN.md 4c."""
+    per = stage_ms["per_step_ms"]
+    metrics_ms = op_ms.get("eval_metrics", 0.0)
+    total = stage_ms["sum_ms"] + metrics_ms
+    dom = max(per, key=per.get)
+    n_launch = max(1.0, stage_ms["launches_per_step"][dom])
+    share = per[dom] / total
+    t_kernel = ms_step * share / n_launch * 1e-3                     # seconds per launch
+    L, T, d, C, H = shape.seq_len, shape.n_targets, shape.d, shape.n_ctx, shape.n_heads
+    rows_per_user = shape.mean_valid if hasattr(shape, "mean_valid") else None
+    roof = {"kernel": dom, "share_of_step": share, "kernel_ms": t_kernel * 1e3, "launches_per_step": n_launch,
+            "timing": "ms_per_step of the timed region x the kernel's share of the step (per-kernel CUDA events)",
+            "peak_source": pk["source"]}
+    cap_path = os.path.join(ROOT, "profiles", "r02", "roofline_capture_bf16.json")
+    cap = json.load(open(cap_path)) if os.path.exists(cap_path) else {}
+    if dom == "rows_decode":
+        # candidate scoring: per user T candidate ids + T bf16 table rows gathered + T scores written + one context row;
+        # per valid profile position its fp32 key row and per-head terms.  The table (7.3 MB bf16) is L2-resident by
+        # design, so DRAM traffic is far below the algorithmic bytes: the bound that matters is the gather path.
+        keys = cap.get("rows_per_user", 7.1)
+        byt = T * (4 + 2 * d + 4) + 4 * C + keys * (4 * d + H * 36)
+        gb = byt * B / t_kernel / 1e9
+        roof.update(bound="hbm", achieved=gb, peak=pk["hbm_gbs"], unit="GB/s", frac=gb / pk["hbm_gbs"],
+                    algorithmic_bytes_per_user=byt)
+    else:
+        fl = fwd_flops_per_user(shape, decoder)
+        tf = fl * B / (ms_step * 1e-3) / 1e12
+        roof.update(bound="tensor", achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=tf / pk["bf16_tflops_sustained"], note="whole-step algorithmic FLOPs over the step time")
+    k = cap.get("kernels", {}).get(dom)
+    roof["traffic"] = k["dram_bytes_per_launch"] if k else None
+    if k:
+        roof["traffic_source"] = cap.get("source")
+        roof["tensor_pipe_active_pct"] = k.get("tensor_pipe_active_pct")
+    return roof
 
 
 def time_sweep(shape, args, dev, table):

@@ -147,6 +147,8 @@ SIGNATURES = {
     "carca_rows_scratch_bytes": [P(ModelParams), i32, i32],
     "carca_rows_eval_forward": [vp, i64, i32, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp,
                                 vp, vp],
+    "carca_rows_set_stage_events": [vp, i32],
+    "carca_rows_stage_ids": [vp, i32],
     "carca_rows_catalog_scratch_bytes": [P(ModelParams), i32, i32],
     "carca_rows_catalog_counts": [vp, vp, vp, P(ModelParams), vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     "carca_catalog_rank_count": [vp, vp, i64, vp, vp, i32, i32, i32, vp],

@@ -29,6 +29,8 @@ int carca_rows_prepare(void*, const float*, const carca_model_params*, void*) {
   return fail(-5, "rows pipeline: not available under the CPU emulator");
 }
 int64_t carca_rows_scratch_bytes(const carca_model_params*, int, int) { return 0; }
+int carca_rows_set_stage_events(void* const*, int) { return 0; }
+int carca_rows_stage_ids(int32_t*, int) { return 0; }
 int64_t carca_rows_catalog_scratch_bytes(const carca_model_params*, int, int) { return 0; }
 int carca_rows_catalog_counts(int32_t*, const void*, const float*, const carca_model_params*, const int32_t*, const float*,
                               const float*, const int32_t*, int, int, int, int, int32_t*, void*, void*) {
@@ -44,6 +46,18 @@ namespace {
 
 using rows::bf16;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// measurement aid (carca_rows_set_stage_events): the bf16 forward records the caller's CUDA events between its kernels
+enum { ST_START = 0, ST_PACK, ST_EMBED, ST_QKV, ST_ATTN, ST_FFN1, ST_FFN2, ST_CHAIN, ST_DEC_KV, ST_DECODER };
+cudaEvent_t g_stage_ev[64];
+int g_stage_id[64];
+int g_stage_n = 0, g_stage_used = 0;
+inline void stage_mark(int id, cudaStream_t st) {
+  if (g_stage_used < g_stage_n) {
+    cudaEventRecord(g_stage_ev[g_stage_used], st);
+    g_stage_id[g_stage_used++] = id;
+  }
+}
 inline long long align256(long long x) { return (x + 255) / 256 * 256; }
 
 // byte offsets of the bf16 plan
@@ -115,7 +129,7 @@ int launch_gemm_rows(const rows::GemmArgs& g, cudaStream_t st) {
     if (e != cudaSuccess) return fail(-3, "rows_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int per_sm = D == 256 ? 1 : 3;
+  const int per_sm = D == 256 ? 1 : 2;
   const int slots = max(1, 148 * per_sm / g.n_jobs);
   CARCA_LAUNCH(k, dim3(slots * g.n_jobs), dim3(rows::GEMM_THREADS), smem, st, g);
   return check_launch("rows_gemm");
@@ -185,12 +199,15 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   const bf16* W = reinterpret_cast<const bf16*>(plan + pl.w);
   const long long wsz = (long long)D * D;
 
+  g_stage_used = 0;
+  stage_mark(ST_START, st);
   cudaMemsetAsync(n_rows, 0, 256, st);
   {
     auto k = rows::rows_pack_kernel;
     CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L);
     TRY(check_launch("rows_pack"));
   }
+  stage_mark(ST_PACK, st);
   const int row_grid = 148 * 4;
   {
     rows::EmbedArgs e;
@@ -201,6 +218,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, e);
     TRY(check_launch("rows_embed_ln"));
   }
+  stage_mark(ST_EMBED, st);
   const bool attn_tc = attn_tc_window(L) <= 256 && !getenv("CARCA_ROWS_ATTN_FFMA");
   const bool chain = D == 64 && attn_tc && !getenv("CARCA_ROWS_NO_CHAIN");
   for (int b = 0; b < m->n_blocks; ++b) {
@@ -217,12 +235,14 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       g.job[2].A = XA; g.job[2].W = wb + 2 * wsz; g.job[2].bias = bp.bv; g.job[2].epi = rows::EPI_VMN; g.job[2].out_tile = Vb;
       g.job[1].ld_rows = g.job[2].ld_rows = sc.Rp;
       TRY(launch_gemm_rows<D>(g, st));
+      stage_mark(ST_QKV, st);
       }
       rows::AttnTcArgs t;
       memset(&t, 0, sizeof(t));
       t.Qt = Qb; t.Kk = Kb; t.Vm = Vb; t.Rp = sc.Rp; t.QN = QN; t.row_src = row_src; t.row_seg = row_seg; t.n_rows = n_rows;
       t.ln_g = bp.ln2_g; t.ln_b = bp.ln2_b; t.S2 = S2; t.S2A = S2A; t.residual = m->residual_sa; t.status = status;
       TRY((launch_attn_tc<D, H>(t, L, st)));
+      stage_mark(ST_ATTN, st);
     } else {
       rows::GemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -231,6 +251,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       g.job[1].A = XA; g.job[1].W = wb + wsz;     g.job[1].bias = bp.bk; g.job[1].epi = rows::EPI_ROWS; g.job[1].out_rows = Kb;
       g.job[2].A = XA; g.job[2].W = wb + 2 * wsz; g.job[2].bias = bp.bv; g.job[2].epi = rows::EPI_ROWS; g.job[2].out_rows = Vb;
       TRY(launch_gemm_rows<D>(g, st));
+      stage_mark(ST_QKV, st);
     }
     if (!attn_tc) {
       rows::AttnRowsArgs t;
@@ -239,6 +260,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       auto k = rows::rows_attn_ln_kernel<D, H, false>;
       CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, t);
       TRY(check_launch("rows_attn_ln"));
+      stage_mark(ST_ATTN, st);
     }
     if (chain) {
       // FFN-1 -> FFN-2 + next LayerNorm -> next block's Q / K / V (or the decoder's K / V): one kernel, the intermediate
@@ -260,6 +282,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
         f.Kd = S2; f.McQ = reinterpret_cast<const float*>(plan + pl.mcq); f.KM = KM; f.wf = m->cross.wf; f.U = U;
       }
       TRY(launch_ffn_chain(f, st));
+      stage_mark(ST_CHAIN, st);
       continue;
     }
     {
@@ -269,6 +292,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       g.job[0].A = S2A; g.job[0].W = wb + 3 * wsz; g.job[0].bias = bp.b1; g.job[0].epi = rows::EPI_LRELU_TILE;
       g.job[0].out_tile = F1A;
       TRY(launch_gemm_rows<D>(g, st));
+      stage_mark(ST_FFN1, st);
     }
     {
       const bool last = b + 1 == m->n_blocks;
@@ -283,6 +307,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       j.ln_b = last ? m->norm_b : m->blocks[b + 1].ln1_b;
       j.out_f32 = QN; j.out_tile2 = QA;
       TRY(launch_gemm_rows<D>(g, st));
+      stage_mark(ST_FFN2, st);
     }
   }
   rows::DecodeArgs d;
@@ -303,7 +328,10 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     g.job[0].out_f32 = S2; g.job[0].McQ = reinterpret_cast<const float*>(plan + pl.mcq); g.job[0].KM = KM;
     g.job[1].A = QA; g.job[1].W = dw + wsz; g.job[1].bias = m->cross.bv; g.job[1].epi = rows::EPI_VDOT;
     g.job[1].wf = m->cross.wf; g.job[1].U = U;
-    if (!chain) TRY(launch_gemm_rows<D>(g, st));      // (chained: the last block's tail kernel has produced them)
+    if (!chain) {      // (chained: the last block's tail kernel has produced them)
+      TRY(launch_gemm_rows<D>(g, st));
+      stage_mark(ST_DEC_KV, st);
+    }
     (void)Kb;
     if (H <= 4 && !getenv("CARCA_ROWS_FFMA_DECODE")) {   // tensor-core decoder (rows_decode_tc_kernel)
       rows::DecTcArgs t;
@@ -328,7 +356,9 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       const long long work = (long long)B * ceil_div(T, 128);
       const int per_sm = D == 256 ? 1 : 2;
       CARCA_LAUNCH(k, dim3((unsigned)min(work, 148ll * per_sm)), dim3(rows::DT_THREADS), smem, st, t);
-      return check_launch("rows_decode_tc");
+      TRY(check_launch("rows_decode_tc"));
+      stage_mark(ST_DECODER, st);
+      return 0;
     }
     d.Kd = S2; d.ldk = D; d.U = U; d.KM = KM;   // (the S2 buffer is free after the last block: it holds the fp32 keys)
     d.TQ = reinterpret_cast<const float*>(plan + pl.tq);
@@ -344,6 +374,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     CARCA_LAUNCH(k, dim3(dgrid), dim3(128), 0, st, d);
     TRY(check_launch("rows_decode_dot"));
   }
+  stage_mark(ST_DECODER, st);
   return 0;
 }
 
@@ -659,6 +690,20 @@ int carca_rows_prepare(void* plan_v, const float* plan_f32, const carca_model_pa
 }
 
 int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L) { return rows_scratch(m, B, L).total; }
+
+int carca_rows_set_stage_events(void* const* events, int n) {
+  CARCA_REQUIRE(n >= 0 && n <= 64 && (n == 0 || events != nullptr), "rows_set_stage_events: 0..64 events");
+  for (int i = 0; i < n; ++i) g_stage_ev[i] = reinterpret_cast<cudaEvent_t>(events[i]);
+  g_stage_n = n;
+  g_stage_used = 0;
+  return 0;
+}
+
+int carca_rows_stage_ids(int32_t* ids, int cap) {
+  const int n = g_stage_used < cap ? g_stage_used : cap;
+  for (int i = 0; i < n; ++i) ids[i] = g_stage_id[i];
+  return n;
+}
 
 int64_t carca_rows_catalog_scratch_bytes(const carca_model_params* m, int B, int L) { return cat_scratch(m, B, L).total; }
 

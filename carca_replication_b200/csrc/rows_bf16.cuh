@@ -501,7 +501,9 @@ __device__ __forceinline__ bool wait_or_flag(uint64_t* bar, uint32_t parity, int
 }
 
 template <int D>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) rows_gemm_kernel(const GemmArgs a) {
+// (d = 64: two CTAs per SM — 102 registers per thread; without the bound the kernel takes 160 and, at one CTA per SM,
+// a grid sized for more runs in waves that each pay the prologue)
+__global__ void __launch_bounds__(GEMM_THREADS, (D == 64 ? 2 : 1)) rows_gemm_kernel(const GemmArgs a) {
   using Cfg = GemmCfg<D>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* w_smem = smem_raw;

@@ -486,6 +486,13 @@ int64_t carca_eval_scratch_bytes(int B);
  * whenever the weights change; the forward call takes both plans.                                                   */
 int64_t carca_rows_plan_bytes(const carca_model_params* m);
 int carca_rows_prepare(void* plan, const float* plan_f32, const carca_model_params* m, void* stream);
+/* Measurement aid (bench.py's per-kernel roofline): the next carca_rows_eval_forward calls in bf16 record the given
+ * CUDA events (cudaEvent_t handles, at most 64) on their stream between the kernels of the pipeline, in launch order;
+ * carca_rows_stage_ids returns how many the last call recorded and which stage each one closes (0 start, 1 pack,
+ * 2 embedding + LN, 3 Q/K/V GEMM, 4 attention, 5 FFN-1, 6 FFN-2 + LN, 7 FFN chain (+ next Q/K/V or decoder K/V),
+ * 8 decoder K/V GEMM, 9 decoder).  n = 0 switches the recording off.  Not thread safe; not for use under capture.  */
+int carca_rows_set_stage_events(void* const* events, int n);
+int carca_rows_stage_ids(int32_t* ids, int cap);
 /* Bytes of device scratch for a batch of B users with windows of L positions (worst case: every position valid). */
 int64_t carca_rows_scratch_bytes(const carca_model_params* m, int B, int L);
 /* y[b, col0 + t] = CARCA.forward(profile, [targets]) in eval mode.  p_x [B,L], p_c [B,L,C], o_x [B,T],
