@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <utility>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -46,6 +47,25 @@ namespace {
 
 using rows::bf16;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Launch with programmatic stream serialization (see pdl_wait in rows_bf16.cuh): the kernel may begin while the previous
+// kernel of the stream drains.  Only for kernels that follow a kernel of this pipeline and call pdl_wait() before they
+// touch anything a predecessor wrote.  OFF unless CARCA_ROWS_PDL is set: measured on a B200 (8192 Beauty users, bf16)
+// it helps eager launches (0.251 -> 0.245 ms per step) but not graph replays (0.234 -> 0.239 ms; every position valid
+// 0.976 -> 1.010 ms) — the early CTAs hold shared memory and TMEM while they wait — and replays are how the step runs.
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool off = getenv("CARCA_ROWS_PDL") == nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = off ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
 
 // measurement aid (carca_rows_set_stage_events): the bf16 forward records the caller's CUDA events between its kernels
 enum { ST_START = 0, ST_PACK, ST_EMBED, ST_QKV, ST_ATTN, ST_FFN1, ST_FFN2, ST_CHAIN, ST_DEC_KV, ST_DECODER };
@@ -131,7 +151,7 @@ int launch_gemm_rows(const rows::GemmArgs& g, cudaStream_t st) {
   }
   const int per_sm = D == 256 ? 1 : 2;
   const int slots = max(1, 148 * per_sm / g.n_jobs);
-  CARCA_LAUNCH(k, dim3(slots * g.n_jobs), dim3(rows::GEMM_THREADS), smem, st, g);
+  launch_pdl(k, dim3(slots * g.n_jobs), dim3(rows::GEMM_THREADS), smem, st, g);
   return check_launch("rows_gemm");
 }
 
@@ -155,7 +175,7 @@ int launch_attn_tc(rows::AttnTcArgs& t, int L, cudaStream_t st) {
     attr_smem = smem;
   }
   const int per_sm = (t.tmem_cols == 256 && 2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
-  CARCA_LAUNCH(k, dim3(148 * per_sm), dim3(rows::AT_THREADS), smem, st, t);
+  launch_pdl(k, dim3(148 * per_sm), dim3(rows::AT_THREADS), smem, st, t);
   return check_launch("rows_attn_tc");
 }
 
@@ -168,7 +188,7 @@ int launch_ffn_chain(const rows::FfnChainArgs& f, cudaStream_t st) {
     if (e != cudaSuccess) return fail(-3, "rows_ffn_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  CARCA_LAUNCH(k, dim3(148 * 2), dim3(rows::FC_THREADS), smem, st, f);
+  launch_pdl(k, dim3(148 * 2), dim3(rows::FC_THREADS), smem, st, f);
   return check_launch("rows_ffn_chain");
 }
 
@@ -215,7 +235,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
     e.ln_g = m->blocks[0].ln1_g; e.ln_b = m->blocks[0].ln1_b;
     e.XA = XA; e.QA = QA; e.QN = QN; e.L = L; e.C = C;
     auto k = rows::rows_embed_ln_kernel<D, false>;
-    CARCA_LAUNCH(k, dim3(row_grid), dim3(256), 0, st, e);
+    launch_pdl(k, dim3(row_grid), dim3(256), 0, st, e);
     TRY(check_launch("rows_embed_ln"));
   }
   stage_mark(ST_EMBED, st);
@@ -355,7 +375,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
       }
       const long long work = (long long)B * ceil_div(T, 128);
       const int per_sm = D == 256 ? 1 : 2;
-      CARCA_LAUNCH(k, dim3((unsigned)min(work, 148ll * per_sm)), dim3(rows::DT_THREADS), smem, st, t);
+      launch_pdl(k, dim3((unsigned)min(work, 148ll * per_sm)), dim3(rows::DT_THREADS), smem, st, t);
       TRY(check_launch("rows_decode_tc"));
       stage_mark(ST_DECODER, st);
       return 0;

@@ -85,8 +85,7 @@ __global__ void __launch_bounds__(AT_THREADS, (D == 64 ? 2 : 1)) rows_attn_tc_ke
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = *a.n_rows;
-  const int n_tiles = (R + TILE - 1) / TILE;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < AT_NST; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
@@ -103,6 +102,9 @@ __global__ void __launch_bounds__(AT_THREADS, (D == 64 ? 2 : 1)) rows_attn_tc_ke
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = *tmem_slot;
+  pdl_wait();
+  const int R = *a.n_rows;
+  const int n_tiles = (R + TILE - 1) / TILE;
 
   if (warp == 0) {
     // ===== producer: per (tile, head) the head's Q block, K window (one copy per 8-feature group) and V window

@@ -80,6 +80,13 @@ __device__ __forceinline__ float group_sum(float v) {
   for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): a kernel of the
+// pipeline may start while its predecessor drains — its prologue (barrier init, TMEM allocation, parameter loads) runs
+// under the predecessor's tail instead of after it.  pdl_wait() returns once every prerequisite grid has completed and
+// its writes are visible: NOTHING a predecessor produced (including the device-side row count) is read before it and
+// no global memory is written before it.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -142,10 +149,12 @@ template <int D, bool F32>
 __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
   constexpr int G = D / 8, RPW = 32 / G;
   __shared__ float mct[8][D];
+  pdl_trigger();
   for (int i = threadIdx.x; i < 8 * D; i += blockDim.x) mct[i % 8][i / 8] = a.Mc[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
   const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warps = (int)(gridDim.x * blockDim.x) >> 5;
+  pdl_wait();
   const int R = *a.n_rows;
   for (long long r0 = (long long)warp * RPW; r0 < R; r0 += (long long)n_warps * RPW) {
     const long long r = r0 + sub;
@@ -520,9 +529,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, (D == 64 ? 2 : 1)) rows_gemm_ker
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jid = blockIdx.x % a.n_jobs, slot = blockIdx.x / a.n_jobs, n_slots = gridDim.x / a.n_jobs;
   const GemmJob& J = a.job[jid];
-  const int R = *a.n_rows;
-  const int n_tiles = (R + TILE - 1) / TILE;
   if (slot >= n_slots) return;                 // (gridDim.x not a multiple of n_jobs)
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
@@ -543,6 +551,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, (D == 64 ? 2 : 1)) rows_gemm_ker
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = *tmem_slot;
+  pdl_wait();                                  // the predecessor's rows (and the row count) from here on
+  const int R = *a.n_rows;
+  const int n_tiles = (R + TILE - 1) / TILE;
 
   if (warp == 0) {
     // ===== producer: the weight matrix once, then the A chunks of this CTA's tiles through the stage ring
@@ -998,6 +1009,7 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
   const int n_tiles = (a.T + 127) / 128;
   const bool uctx = a.oc_tgt == 0;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) {
       umma::mbar_init(&s.full[i], 128);       // every producer thread arrives when its copies have landed
@@ -1015,6 +1027,7 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
   umma::fence_after_sync();
   const uint32_t tmem0 = s.tmem_slot;
   const float sc = 1.4426950408889634f * rsqrtf((float)DH);
+  pdl_wait();
 
   // the sequence of (user, candidate tile, key chunk) steps of this CTA: identical in every role
   // step `it`: user u, tile, key chunk k0 .. k0 + nk

@@ -64,9 +64,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) rows_ffn_chain_kernel(const Ffn
   extern __shared__ __align__(128) unsigned char fc_raw[];
   FfnChainSmem& s = *reinterpret_cast<FfnChainSmem*>(fc_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = *a.n_rows;
-  const int n_tiles = (R + TILE - 1) / TILE;
   const int n_w3 = a.tail == 1 ? 3 : (a.tail == 2 ? 2 : 0);
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&s.a_full[i], 1); umma::mbar_init(&s.a_empty[i], 1); }
@@ -94,6 +93,9 @@ __global__ void __launch_bounds__(FC_THREADS, 2) rows_ffn_chain_kernel(const Ffn
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = s.tmem_slot;
+  pdl_wait();
+  const int R = *a.n_rows;
+  const int n_tiles = (R + TILE - 1) / TILE;
 
   if (warp == 0) {
     // ===== producer
