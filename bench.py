@@ -588,6 +588,7 @@ def run_ours(args):
         if not args.no_catalog:
             optional("catalog", lambda: in_fp32(lambda: time_catalog(model, shape, args, dev)))
             optional("device_pipeline", lambda: time_device_pipeline(model, shape, args, dev))
+            optional("dense_attrs", lambda: in_fp32(lambda: time_dense_attrs(model, table, shape, args, dev, pk)))
         if not args.no_extra:
             other = "fp32" if args.dtype == "bf16" else "bf16"
             optional(other, lambda: time_other_dtype(model, shape, args, dev, devb, step, pk, other))
@@ -1058,6 +1059,46 @@ def time_catalog(model, shape, args, dev):
                     "the GEMM epilogue; no [users, items] score matrix)",
             "score_matrix_path": {"scores_per_s": Bc * (shape.n_items - 1) / (ms_ref * 1e-3), "ms": ms_ref,
                                   "ranks_equal": float((ranks == ref).double().mean().item())}}
+
+
+def time_dense_attrs(model, table, shape, args, dev, pk):
+    """The reference API as it is: dense [B, N, A] attribute tensors per batch (src/carca.py:86, src/data.py:119-131)
+    instead of the device-resident item -> attribute table.  These batches are 3.9 MB per Beauty user, so the step is
+    bound by reading them (26,028 B per position); it runs on the per-op kernels (feature projection as a
+    tcgen05 GEMM over the dense rows).  Reference batch size."""
+    from carca_replication_b200 import ops, synth
+
+    B = args.cpu_batch
+    bs = []
+    for i in range(2):
+        b = {k: v.to(dev) for k, v in synth.make_eval_batch(shape, B, seed=7000 + i).items()}
+        b["p_a"], b["o_a"] = table.gather_dense(b["p_x"]).to(dev), table.gather_dense(b["o_x"]).to(dev)
+        bs.append(b)
+    acc4 = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def step(b):
+        y = model.forward(profile=(b["p_x"], b["p_a"], b["p_c"]), targets=[(b["o_x"], b["o_a"], b["o_c"])])
+        ops.eval_metrics_(acc4, y, b["y_true"], b["o_x"], 10)
+        return y
+
+    n = max(3, args.steps // 2)
+    with torch.no_grad():
+        for b in bs:
+            step(b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            step(bs[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    byt = (shape.seq_len + shape.n_targets) * (4 * shape.n_attrs + 8 + 4 * shape.n_ctx)
+    gbs = byt * B / (ms * 1e-3) / 1e9
+    return {"value": B / (ms * 1e-3), "unit": "users/s", "batch": B, "ms_per_step": ms,
+            "bytes_per_user": byt, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"],
+            "what": "CARCA.forward given the reference's dense [B, N, A] attribute tensors (device-resident, fp32), per-op "
+                    "kernels + eval metrics; bound: reading the attribute rows"}
 
 
 def time_device_pipeline(model, shape, args, dev):
