@@ -148,3 +148,57 @@ def test_tensor_core_attention_matches_cuda_core_attention(case, monkeypatch):
         assert float((_fwd(model, d) - y_tc).abs().max()) < S.BF16_TOL
     if case == "beauty_L130_fallback":
         assert torch.equal(y_tc, y_cc)                    # window > 256 keys: the CUDA-core kernel serves both calls
+
+
+@pytest.mark.parametrize("decoder", ["ca", "dot"])
+def test_ffn_chain_kernel_matches_the_separate_gemm_launches(decoder, monkeypatch):
+    """rows_ffn_chain_kernel (FFN-1 -> FFN-2 + LayerNorm -> next block's Q / K / V or the decoder's K / V in one kernel,
+    intermediates in shared memory) against the same pipeline with one GEMM launch per link (CARCA_ROWS_NO_CHAIN=1):
+    the same bf16 roundings at the same places, so the scores agree far inside the bf16 contract."""
+    from carca_replication_b200 import fused, synth
+
+    shape = _beauty()
+    model = synth.build_model(shape, decoder, p=0.5, seed=9).to(DEV).eval().set_eval_dtype("bf16")
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=9).to(DEV))
+    d = {k: v.to(DEV) for k, v in synth.make_eval_batch(shape, 500, seed=9).items()}
+    monkeypatch.setenv("CARCA_ROWS_NO_CHAIN", "1")
+    y_sep = _fwd(model, d)
+    monkeypatch.delenv("CARCA_ROWS_NO_CHAIN")
+    y_chain = _fwd(model, d)
+    assert not fused.mma_timed_out(model)
+    diff = float((y_chain - y_sep).abs().max())
+    print("chain vs separate launches: max |dp|", diff)
+    assert diff < 5e-3          # (fp32 summation order differs in the LayerNorm input: an occasional bf16 ulp downstream)
+
+
+def test_stage_events_time_every_kernel_of_the_bf16_step():
+    """carca_rows_set_stage_events (bench.py's per-kernel roofline): the library records the caller's CUDA events between
+    its launches; the ids name the stages of the chained d = 64 pipeline and the intervals are positive."""
+    import ctypes as C
+
+    from carca_replication_b200 import _native as N
+    from carca_replication_b200 import synth
+
+    shape = _beauty()
+    model = synth.build_model(shape, "ca", p=0.5, seed=9).to(DEV).eval().set_eval_dtype("bf16")
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=9).to(DEV))
+    d = {k: v.to(DEV) for k, v in synth.make_eval_batch(shape, 300, seed=9).items()}
+    _fwd(model, d)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(24)]
+    for e in evs:
+        e.record()
+    torch.cuda.synchronize()
+    arr = (C.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+    lib = N.lib()
+    try:
+        lib.carca_rows_set_stage_events(arr, len(evs))
+        _fwd(model, d)
+        ids = (C.c_int32 * 64)()
+        n = lib.carca_rows_stage_ids(ids, 64)
+    finally:
+        lib.carca_rows_set_stage_events(None, 0)
+    nb = shape.n_blocks
+    assert list(ids[:n]) == [0, 1, 2, 3] + [4, 7] * nb + [9]
+    assert all(evs[i].elapsed_time(evs[i + 1]) > 0 for i in range(n - 1))
+    _fwd(model, d)                      # recording is off again: nothing is recorded
+    assert lib.carca_rows_stage_ids(ids, 64) == 0
