@@ -902,6 +902,16 @@ def rows_roofline(stage_ms, ms_step, op_ms, shape, B, decoder, pk):
         tf = fl * B / (ms_step * 1e-3) / 1e12
         roof.update(bound="tensor", achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=tf / pk["bf16_tflops_sustained"], note="whole-step algorithmic FLOPs over the step time")
+    # the whole step by SURVEY 8d's counting rule (all L positions and the full L x L attention counted, fp32 item rows)
+    attr_b = 36 if shape.attr_kind == "multihot" else 4 * shape.n_attrs
+    step_bytes = (L + T) * (4 + 4 * d + attr_b + 4 * C) + 4 * T
+    step_flops = fwd_flops_per_user(shape, decoder)
+    roof["whole_step"] = {
+        "algorithmic_bytes_per_user": step_bytes, "achieved_gbs": step_bytes * B / (ms_step * 1e-3) / 1e9,
+        "frac_of_hbm_peak": step_bytes * B / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "algorithmic_flops_per_user": step_flops, "achieved_tflops": step_flops * B / (ms_step * 1e-3) / 1e12,
+        "frac_of_bf16_peak": step_flops * B / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+        "note": "SURVEY 8d figures x users per step / ms_per_step; the pipeline executes the valid positions only"}
     k = cap.get("kernels", {}).get(dom)
     roof["traffic"] = k["dram_bytes_per_launch"] if k else None
     if k:

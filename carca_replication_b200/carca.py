@@ -427,6 +427,11 @@ class CARCA(Model):
         _invalidate_plans()
         return super()._apply(fn, *args, **kwargs)
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_eval_graph_steps", None)         # captured CUDA graphs of evaluate(): never pickled / deep-copied
+        return state
+
     def encode(self, profile) -> Tuple[Tensor, Tensor]:
         p_x, p_a, p_c = profile
         p_mask = get_mask(p_x)

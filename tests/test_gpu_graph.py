@@ -1,8 +1,11 @@
 """CUDA-graph train step vs the eager step on a B200 (same weights, same batches)."""
+import dataclasses
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"
 
 
 @pytest.mark.parametrize("decoder", ["ca", "dot"])
@@ -207,3 +210,50 @@ def test_graphed_eval_step_long_windows_replays_every_batch():
             ops.eval_metrics_(ref, y, batch["y_true"], batch["o_x"], 10)
     assert torch.allclose(step.stats, ref, rtol=1e-5, atol=1e-9)
     assert float(ref[2]) == 72
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_evaluate_replays_repeated_batch_shapes_as_graphs(dtype):
+    """evaluate() (src/train.py:35-53) replays a batch shape's body as a CUDA graph from its second occurrence on
+    (train._graphed_eval_batch): same (HR, NDCG, loss) as the eager loop, also after a weight update between two calls
+    and for a trailing batch of another shape."""
+    import copy
+
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import synth, train
+
+    shape = dataclasses.replace(synth.BEAUTY, n_items=3000, n_attrs=200)
+    model = synth.build_model(shape, "ca", p=0.5, seed=21).to(DEV).eval().set_eval_dtype(dtype)
+    model.embeds.set_attr_table(synth.make_attr_table(shape, seed=21).to(DEV))
+
+    def loader():
+        out = []
+        for i, B in enumerate((96, 96, 96, 96, 40)):
+            b = {k: v.to(DEV) for k, v in synth.make_eval_batch(shape, B, seed=50 + i).items()}
+            out.append((b["p_x"], None, b["p_c"], b["o_x"], None, b["o_c"], b["y_true"]))
+        return out
+
+    batches = loader()
+    train.USE_EVAL_GRAPHS = False
+    try:
+        want = cb.evaluate(model, batches, DEV, 10)
+    finally:
+        train.USE_EVAL_GRAPHS = True
+    got = cb.evaluate(model, batches, DEV, 10)
+    assert sum(1 for v in model._eval_graph_steps.values() if not isinstance(v, (int, bool))) == 1
+    assert got[0] == want[0] and got[1] == pytest.approx(want[1], rel=1e-6) and got[2] == pytest.approx(want[2], rel=1e-5)
+    again = cb.evaluate(model, batches, DEV, 10)       # second call: the trailing 40-user batch is captured too
+    assert sum(1 for v in model._eval_graph_steps.values() if not isinstance(v, (int, bool))) == 2
+    assert again[0] == want[0] and again[2] == pytest.approx(want[2], rel=1e-5)
+    with torch.no_grad():
+        model.decoder.ffn.bias.add_(0.5)               # weights change between validation passes
+    train.USE_EVAL_GRAPHS = False
+    try:
+        want2 = cb.evaluate(model, batches, DEV, 10)
+    finally:
+        train.USE_EVAL_GRAPHS = True
+    got2 = cb.evaluate(model, batches, DEV, 10)
+    assert want2[2] != pytest.approx(want[2], rel=1e-3)
+    assert got2[0] == want2[0] and got2[2] == pytest.approx(want2[2], rel=1e-5)
+    clone = copy.deepcopy(model)                       # captured graphs are not part of the module's state
+    assert "_eval_graph_steps" not in clone.__dict__
