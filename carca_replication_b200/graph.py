@@ -146,6 +146,8 @@ class GraphedEvalStep:
             self._body()
         self.graph_is_fused = True
         self.uses_plan = fused._plans.get(model) is not None       # the capture reads the fused inference plan
+        self.struct_epoch = fused._struct_epoch[0]                 # a later Module._apply (.to / .cuda / .float) makes
+                                                                   # the captured plan buffers stale
         self.stats.copy_(keep)                       # warm-up runs do not count
 
     def _body(self) -> None:
@@ -188,6 +190,11 @@ class GraphedEvalStep:
         """Runs the step on the current contents of the static input buffers."""
         from . import fused
 
+        if self.uses_plan and self.struct_epoch != fused._struct_epoch[0]:
+            # (the plan may even look current again — rebuilt by an eager call into NEW buffers — while this graph
+            # still reads the old ones)
+            raise RuntimeError("GraphedEvalStep: a module was moved or cast after capture (Module.to / .cuda / .float); "
+                               "build a new GraphedEvalStep")
         if self.uses_plan and not fused.plan_is_current(self.model):
             self.refresh()
         self.graph.replay()

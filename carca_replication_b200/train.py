@@ -46,7 +46,11 @@ def evaluate(model: Model, loader: DataLoader, device: str, k: int,
     `reduce_fn(tensor)` (data-parallel runs) all-reduces the 5 device accumulators
     [hits, ndcg, users, loss_sum, n_batches] before the single device->host read.
     """
-    model = model.eval().to(device)
+    model = model.eval()
+    if not _on_device(model, device):
+        # (Module.to() re-wraps every parameter even when nothing moves, which invalidates the inference plans and the
+        # captured graphs derived from them: only move a model that is somewhere else)
+        model = model.to(device)
     acc = torch.zeros(4, dtype=torch.float64, device=device)     # hits, ndcg, users, sum of batch losses
     n_batches = 0
     with torch.no_grad():
@@ -74,12 +78,23 @@ def evaluate(model: Model, loader: DataLoader, device: str, k: int,
     return hits / total, ndcg / total, lsum / max(nb, 1.0)
 
 
-USE_EVAL_GRAPHS = True      # evaluate(): replay a batch shape's body as a CUDA graph from its second occurrence on
+def _on_device(model, device) -> bool:
+    want = torch.device(device)
+    for t in list(model.parameters()) + list(model.buffers()):
+        if t.device.type != want.type:
+            return False
+        if want.type == "cuda" and t.device.index != (want.index if want.index is not None else torch.cuda.current_device()):
+            return False
+    return True
+
+
+USE_EVAL_GRAPHS = True      # evaluate(): replay a batch shape's body as a CUDA graph once the shape keeps coming back
+EVAL_GRAPH_AFTER = 2        # eager occurrences of a shape before it is captured (the third one is the capture)
 
 
 def _graphed_eval_batch(model, acc, k, p_x, p_a, p_c, o_x, o_a, o_c, y_true) -> bool:
     """evaluate()'s per-batch body (src/train.py:44-50) as a CUDA-graph replay (graph.GraphedEvalStep) once a batch shape
-    has been seen before on this model: the eager body is ~12 launches whose Python / ctypes dispatch takes longer than
+    has been seen EVAL_GRAPH_AFTER times on this model: the eager body is ~12 launches whose Python / ctypes dispatch takes longer than
     the kernels run, and validation loops see the same one or two shapes every epoch.  Only for the whole-model inference
     paths (device-resident attribute table, nothing decided on the host); anything else, or a failed capture, returns
     False and the caller runs the batch eagerly.  Weight updates between calls are picked up by the step itself."""
@@ -93,14 +108,20 @@ def _graphed_eval_batch(model, acc, k, p_x, p_a, p_c, o_x, o_a, o_c, y_true) -> 
     cache = model.__dict__.setdefault("_eval_graph_steps", {})
     key = (tuple(p_x.shape), tuple(o_x.shape), int(p_c.shape[-1]), int(k), str(p_x.device), str(y_true.dtype),
            getattr(model, "eval_dtype", None), getattr(model, "force_eval_path", None))
-    ent = cache.get(key)
-    if ent is None:
-        cache[key] = 1                      # first sight: eager (a one-off shape is not worth a capture)
-        return False
+    ent = cache.get(key, 0)
     if ent is False:
         return False
+    if isinstance(ent, int) and ent < EVAL_GRAPH_AFTER:
+        cache[key] = ent + 1                # a capture costs ~10 eager batches: not for one-off shapes
+        return False
     batch = {"p_x": p_x, "p_c": p_c, "o_x": o_x, "o_c": o_c, "y_true": y_true}
-    if ent == 1:
+    from . import fused
+
+    if not isinstance(ent, int) and ent.struct_epoch != fused._struct_epoch[0]:
+        # a module was moved / cast since the capture (Module._apply): the plan buffers the graph reads are gone
+        cache.pop(key, None)
+        ent = EVAL_GRAPH_AFTER
+    if isinstance(ent, int):
         from .graph import GraphedEvalStep
 
         if len(cache) > 8:
@@ -194,7 +215,9 @@ def train(
     if is_main:
         os.makedirs(datadir, exist_ok=True)
     loss_fn = loss_fn or BinaryCrossEntropy()
-    model = model.train().to(device)
+    model = model.train()
+    if not _on_device(model, device):
+        model = model.to(device)
     best, no_improve = 0, 0
     start = datetime.now()
     logpath = f"{start.year}-{start.month}-{start.day}T{start.hour}-{start.minute}-{start.second}.csv"
@@ -224,7 +247,9 @@ def train(
         if scheduler is not None:
             scheduler.step()
         HR, NDCG, loss = evaluate(model, val_loader, device, top_k, reduce_fn=reduce_fn)
-        model = model.train().to(device)
+        model = model.train()
+        if not _on_device(model, device):
+            model = model.to(device)
         if NDCG > best:
             best, no_improve = NDCG, 0
             if is_main:

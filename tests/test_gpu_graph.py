@@ -214,7 +214,7 @@ def test_graphed_eval_step_long_windows_replays_every_batch():
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_evaluate_replays_repeated_batch_shapes_as_graphs(dtype):
-    """evaluate() (src/train.py:35-53) replays a batch shape's body as a CUDA graph from its second occurrence on
+    """evaluate() (src/train.py:35-53) replays a batch shape's body as a CUDA graph from its third occurrence on
     (train._graphed_eval_batch): same (HR, NDCG, loss) as the eager loop, also after a weight update between two calls
     and for a trailing batch of another shape."""
     import copy
@@ -239,10 +239,11 @@ def test_evaluate_replays_repeated_batch_shapes_as_graphs(dtype):
         want = cb.evaluate(model, batches, DEV, 10)
     finally:
         train.USE_EVAL_GRAPHS = True
-    got = cb.evaluate(model, batches, DEV, 10)
+    got = cb.evaluate(model, batches, DEV, 10)         # the 96-user shape is captured at its third batch
     assert sum(1 for v in model._eval_graph_steps.values() if not isinstance(v, (int, bool))) == 1
     assert got[0] == want[0] and got[1] == pytest.approx(want[1], rel=1e-6) and got[2] == pytest.approx(want[2], rel=1e-5)
-    again = cb.evaluate(model, batches, DEV, 10)       # second call: the trailing 40-user batch is captured too
+    cb.evaluate(model, batches, DEV, 10)
+    again = cb.evaluate(model, batches, DEV, 10)       # third call: the trailing 40-user batch is captured too
     assert sum(1 for v in model._eval_graph_steps.values() if not isinstance(v, (int, bool))) == 2
     assert again[0] == want[0] and again[2] == pytest.approx(want[2], rel=1e-5)
     with torch.no_grad():
@@ -257,3 +258,11 @@ def test_evaluate_replays_repeated_batch_shapes_as_graphs(dtype):
     assert got2[0] == want2[0] and got2[2] == pytest.approx(want2[2], rel=1e-5)
     clone = copy.deepcopy(model)                       # captured graphs are not part of the module's state
     assert "_eval_graph_steps" not in clone.__dict__
+    # Module.to() re-wraps the parameters even when nothing moves: the plans are rebuilt into new buffers, so the
+    # captured graphs must be dropped (never replayed against freed memory) and the result stays the eager one
+    model.to(DEV)
+    got3 = cb.evaluate(model, batches, DEV, 10)
+    assert got3[0] == want2[0] and got3[2] == pytest.approx(want2[2], rel=1e-5)
+    from carca_replication_b200 import fused
+
+    assert not fused.mma_timed_out(model)
