@@ -949,6 +949,21 @@ def time_sweep(shape, args, dev, table):
                                                                   [(bs[0]["o_x"], None, bs[0]["o_c"])])
                 model.set_eval_dtype("fp32")
             out["rows"].append(row)
+        if L == shape.seq_len:
+            # past the sweep's range: the step is latency-bound at 8192 users (one short wave per kernel), so the rate
+            # keeps growing with the batch
+            with torch.no_grad():
+                for B in (16384, 32768):
+                    bs = device_batches(shp, B, dev, n=2, seed=400 + L)
+                    row = {"maxlen": L, "batch": B, "beyond_the_sweep_range": True}
+                    for dt in ("fp32", "bf16"):
+                        model.set_eval_dtype(dt)
+                        try:
+                            row[dt] = graphed_rate(step, bs, B, max(5, n // 2))
+                        except Exception as ex:  # noqa: BLE001
+                            row[dt] = f"{type(ex).__name__}: {ex}"[:120]
+                    model.set_eval_dtype("fp32")
+                    out["rows"].append(row)
         if L == 100:
             bs = device_batches(shp, 2048, dev, n=2, seed=77, all_valid=True)
             with torch.no_grad():
