@@ -115,7 +115,7 @@ def _fwd(model, d):
 
 
 @pytest.mark.parametrize("case", ["beauty_sparse", "beauty_all_valid", "beauty_L129", "beauty_L130_fallback", "men_all_valid",
-                                  "men_h8"])
+                                  "men_h8", "beauty_h1", "beauty_L10_empty_profiles", "single_user"])
 def test_tensor_core_attention_matches_cuda_core_attention(case, monkeypatch):
     """rows_attn_tc_kernel (tcgen05 QK^T / PV with the key window of a 128-row tile, L <= 129) against the CUDA-core
     attention kernel it replaces (CARCA_ROWS_ATTN_FFMA=1) on the same batch: both are bf16-operand / fp32-softmax
@@ -127,10 +127,15 @@ def test_tensor_core_attention_matches_cuda_core_attention(case, monkeypatch):
     shape, B, all_valid = {
         "beauty_sparse": (_beauty(), 700, False), "beauty_all_valid": (_beauty(), 333, True),
         "beauty_L129": (_beauty(129), 150, True), "beauty_L130_fallback": (_beauty(130), 40, True),
-        "men_all_valid": (men, 100, True), "men_h8": (dataclasses.replace(men, n_heads=8), 300, False)}[case]
+        "men_all_valid": (men, 100, True), "men_h8": (dataclasses.replace(men, n_heads=8), 300, False),
+        "beauty_h1": (dataclasses.replace(_beauty(), n_heads=1), 400, False),
+        "beauty_L10_empty_profiles": (_beauty(10), 300, False), "single_user": (_beauty(), 1, False)}[case]
     model = synth.build_model(shape, "ca", p=0.5, seed=5).to(DEV).eval().set_eval_dtype("bf16")
     model.embeds.set_attr_table(synth.make_attr_table(shape, seed=5).to(DEV))
     d = {k: v.to(DEV) for k, v in synth.make_eval_batch(shape, B, seed=5, all_valid=all_valid).items()}
+    if case == "beauty_L10_empty_profiles":
+        d["p_x"][::7] = 0                                # users without a single valid position (only the L-1 pad row)
+        d["p_x"][3, :-1] = 0                             # and one with exactly one
     monkeypatch.setenv("CARCA_ROWS_ATTN_FFMA", "1")
     y_cc = _fwd(model, d)
     monkeypatch.delenv("CARCA_ROWS_ATTN_FFMA")
