@@ -217,6 +217,10 @@ __global__ void __launch_bounds__(AT_THREADS, (D == 64 ? 2 : 1)) rows_attn_tc_ke
         whi = max(whi, __shfl_xor_sync(kFull, whi, o));
       }
       const int c_lo = wlo >> 4, c_hi = min(whi, win - 1) >> 4;   // 16-column chunks this warp computes (none: c_lo > c_hi)
+      if (a.residual && live) {      // the LayerNorm tail's residual row: into L2 now, it is read after the last head
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.QN + r * D + 32 * c));
+      }
       float zinv[H];
 #pragma unroll
       for (int hh = 0; hh < H; ++hh) zinv[hh] = 0.f;
@@ -267,20 +271,26 @@ __global__ void __launch_bounds__(AT_THREADS, (D == 64 ? 2 : 1)) rows_attn_tc_ke
       }
       if (!ok) break;
       // ----- O / rowsum + residual -> LayerNorm 2 (src/carca.py:302-303), as the EPI_LN epilogue of the GEMM does it
+      // The residual row (fp32, HBM) is the only global read of this tail and a dependent one: its first chunk is
+      // requested before the wait for O (the rest of the row was sent to L2 when the tile started), chunk c + 1 while
+      // chunk c is processed (ncu: a quarter of the kernel's samples sat on this load when it was issued in place).
+      const bool use_res = a.residual && live;
+      float rs[32], rn[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) rs[e] = 0.f;
+      if (use_res) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ldg256(a.QN + r * D + 8 * q, *reinterpret_cast<float(*)[8]>(&rs[8 * q]));
+      }
       ok = wait_or_flag(o_full, tcount & 1u, a.status, 1024);
       if (!ok) break;
       umma::fence_after_sync();
       float sum = 0.f, sq = 0.f;
-      const bool use_res = a.residual && live;
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
-        float rs[32];
-        if (use_res) {
+        if (use_res && c + 1 < D / 32) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ldg256(a.QN + r * D + 32 * c + 8 * q, *reinterpret_cast<float(*)[8]>(&rs[8 * q]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) rs[e] = 0.f;
+          for (int q = 0; q < 4; ++q) ldg256(a.QN + r * D + 32 * (c + 1) + 8 * q, *reinterpret_cast<float(*)[8]>(&rn[8 * q]));
         }
         float v[32];
         umma::tmem_ld_1x32(o_tb + 32 * c, v);
@@ -294,6 +304,10 @@ __global__ void __launch_bounds__(AT_THREADS, (D == 64 ? 2 : 1)) rows_attn_tc_ke
           sq = fmaf(v[e], v[e], sq);
         }
         umma::tmem_st_x32(o_tb + 32 * c, v, 0);
+        if (use_res) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) rs[e] = rn[e];
+        }
       }
       umma::tmem_st_wait();
       const float mean = sum * (1.0f / D);
