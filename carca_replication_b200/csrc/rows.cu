@@ -104,7 +104,7 @@ RowsPlan rows_plan(const carca_model_params* m) {
 
 // byte offsets of the per-call scratch: seven [Rp, d] fp32-sized slots shared by both flavours
 struct RowsScratch {
-  long long counters, row_src, row_seg, useg, slot[7], U, KM, total, Rp;
+  long long counters, row_src, row_seg, row_id, useg, slot[7], U, KM, total, Rp;
 };
 RowsScratch rows_scratch(const carca_model_params* m, int B, int L) {
   RowsScratch s;
@@ -114,7 +114,8 @@ RowsScratch rows_scratch(const carca_model_params* m, int B, int L) {
   s.counters = 0;
   s.row_src = 256;
   s.row_seg = align256(s.row_src + Rp * 4);
-  s.useg = align256(s.row_seg + Rp * 4);
+  s.row_id = align256(s.row_seg + Rp * 4);
+  s.useg = align256(s.row_id + Rp * 4);
   long long off = align256(s.useg + (long long)B * 8);
   for (int i = 0; i < 7; ++i) {
     s.slot[i] = off;
@@ -202,6 +203,7 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   int* n_rows = reinterpret_cast<int*>(scr + sc.counters);
   int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
   int* row_seg = reinterpret_cast<int*>(scr + sc.row_seg);
+  int* row_id = reinterpret_cast<int*>(scr + sc.row_id);
   int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
   const long long half = sc.Rp * D * 2;
   bf16* XA = reinterpret_cast<bf16*>(scr + sc.slot[0]);
@@ -224,14 +226,14 @@ int forward_t(float* y, int64_t ldy, int col0, const unsigned char* plan, const 
   cudaMemsetAsync(n_rows, 0, 256, st);
   {
     auto k = rows::rows_pack_kernel;
-    CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L);
+    CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L, row_id);
     TRY(check_launch("rows_pack"));
   }
   stage_mark(ST_PACK, st);
   const int row_grid = 148 * 4;
   {
     rows::EmbedArgs e;
-    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows;
+    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows; e.row_id = row_id;
     e.ln_g = m->blocks[0].ln1_g; e.ln_b = m->blocks[0].ln1_b;
     e.XA = XA; e.QA = QA; e.QN = QN; e.L = L; e.C = C;
     auto k = rows::rows_embed_ln_kernel<D, false>;
@@ -422,6 +424,7 @@ int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_p
   int* n_rows = reinterpret_cast<int*>(scr + sc.counters);
   int* row_src = reinterpret_cast<int*>(scr + sc.row_src);
   int* row_seg = reinterpret_cast<int*>(scr + sc.row_seg);
+  int* row_id = reinterpret_cast<int*>(scr + sc.row_id);
   int2* useg = reinterpret_cast<int2*>(scr + sc.useg);
   float* Xf = reinterpret_cast<float*>(scr + sc.slot[0]);
   float* QN = reinterpret_cast<float*>(scr + sc.slot[1]);
@@ -438,14 +441,14 @@ int encode_f32_t(const unsigned char* plan, const float* Tf, const carca_model_p
   cudaMemsetAsync(n_rows, 0, 256, st);
   {
     auto k = rows::rows_pack_kernel;
-    CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L);
+    CARCA_LAUNCH(k, dim3(ceil_div(B, 8)), dim3(256), 0, st, row_src, row_seg, useg, n_rows, p_x, B, L, row_id);
     TRY(check_launch("rows_pack"));
   }
   const int row_grid = 148 * 4;
   {
     rows::EmbedArgs e;
     memset(&e, 0, sizeof(e));
-    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows;
+    e.T = Tf; e.Mc = Mc; e.pos = m->embed.pos; e.p_x = p_x; e.p_c = p_c; e.row_src = row_src; e.n_rows = n_rows; e.row_id = row_id;
     e.ln_g = m->blocks[0].ln1_g; e.ln_b = m->blocks[0].ln1_b;
     e.Xf = Xf; e.QN = QN; e.L = L; e.C = C;
     auto k = rows::rows_embed_ln_kernel<D, true>;

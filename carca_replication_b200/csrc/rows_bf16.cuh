@@ -99,7 +99,8 @@ __device__ __forceinline__ float ex2f(float x) {
 // independent and every row-wise stage is position-independent inside a tile).
 __global__ void __launch_bounds__(256) rows_pack_kernel(int* __restrict__ row_src, int* __restrict__ row_seg,
                                                         int2* __restrict__ useg, int* __restrict__ n_rows,
-                                                        const int* __restrict__ p_x, int B, int L) {
+                                                        const int* __restrict__ p_x, int B, int L,
+                                                        int* __restrict__ row_id) {
   const int u = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (u >= B) return;
   const int* px = p_x + (long long)u * L;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(256) rows_pack_kernel(int* __restrict__ row_sr
       const int r = base + k + __popc(m & ((1u << lane) - 1u));
       row_src[r] = p | (u << 8) | (id == 0 ? (int)0x80000000u : 0);
       row_seg[r] = base;
+      row_id[r] = id;                 // (the embedding kernel gathers T[id] without going back to p_x)
     }
     k += __popc(m);
   }
@@ -138,6 +140,7 @@ struct EmbedArgs {
   const int* p_x;
   const float* p_c;
   const int *row_src, *n_rows;
+  const int* row_id;        // item id per row (written by the packing pass)
   const float *ln_g, *ln_b;
   bf16 *XA, *QA;            // operand tiles: x and LN(x)                 (bf16 flavour)
   float* Xf;                // x rows, fp32                                 (fp32 flavour)
@@ -164,9 +167,9 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
     for (int e = 0; e < 8; ++e) x[e] = 0.f;
     if (live) {
       const int src = a.row_src[r];
+      const int id = a.row_id[r];
       const int pos = src & 255, u = (src >> 8) & 0x7fffff;
       if (src >= 0) {
-        const int id = a.p_x[(long long)u * a.L + pos];
         ldg256(a.T + (long long)id * D + 8 * l, x);
         const float* c = a.p_c + ((long long)u * a.L + pos) * a.C;
         for (int k = 0; k < a.C; ++k) {
@@ -615,10 +618,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, (D == 64 ? 2 : 1)) rows_gemm_ker
     for (int tile = slot; tile < n_tiles && ok; tile += n_slots, ++t) {
       if ((int)(t & 1u) != g) continue;
       const uint32_t aph = (t >> 1) & 1u;
-      ok = wait_or_flag(&acc_full[g], aph, a.status);
-      umma::fence_after_sync();
       const long long r = (long long)tile * TILE + row_in_tile;
       const bool live = r < R;
+      if (J.epi == EPI_LN && J.resid != nullptr && live) {
+        // the residual row is the epilogue's one dependent global read: sent to L2 while the tile's MMAs still run
+        // (ncu: 30 % of this kernel's samples sat on its first use when only the next chunk was requested ahead)
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.resid + r * D + 32 * c));
+      }
+      ok = wait_or_flag(&acc_full[g], aph, a.status);
+      umma::fence_after_sync();
       if (J.epi == EPI_ROWS || J.epi == EPI_LRELU_TILE || J.epi >= EPI_BIAS_TILE) {
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
