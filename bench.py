@@ -877,7 +877,9 @@ def rows_roofline(stage_ms, ms_step, op_ms, shape, B, decoder, pk):
     per = stage_ms["per_step_ms"]
     metrics_ms = op_ms.get("eval_metrics", 0.0)
     total = stage_ms["sum_ms"] + metrics_ms
-    dom = max(per, key=per.get)
+    # the dominant kernel = the longest single launch of the step (the decoder: 1 launch; attention and the FFN chain
+    # are 3 launches of a third of its duration each)
+    dom = max(per, key=lambda k_: per[k_] / max(1.0, stage_ms["launches_per_step"][k_]))
     n_launch = max(1.0, stage_ms["launches_per_step"][dom])
     share = per[dom] / total
     t_kernel = ms_step * share / n_launch * 1e-3                     # seconds per launch
