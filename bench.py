@@ -609,6 +609,8 @@ def run_ours(args):
             with torch.no_grad():
                 out["cpu_baseline"]["same_batch_as_ours"]["ours_users_per_s"] = graphed_rate(step, small, cb_B, 50)
             optional("reference_cuda", lambda: time_reference_cuda(shape, args.decoder, sd_cpu, table_cpu, cb_B, 5, dev))
+    if isinstance(out.get("fp32"), dict) and "value" in out["fp32"]:
+        out["value_fp32"] = out["fp32"]["value"]          # the same step under the fp32 contract, next to the headline
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
