@@ -8,6 +8,8 @@
 //
 //   rows_pack        ids -> row list (user, position), segment start per row, (start, length) per user
 //   rows_embed_ln    e = T[id] + Mc c (+ pos)           -> x (bf16 operand tiles), LN1(x) (fp32 rows + bf16 tiles)
+//   (L <= 129: attention on the tensor cores, rows_attn_tc.cuh; d = 64 on top of that: the block tail FFN-1 -> FFN-2 + LN
+//    -> next block's Q / K / V as ONE kernel, rows_ffn_chain.cuh — pack, embed, Q|K|V, 3 x (attention, chain), decoder)
 //   per block:
 //     rows_gemm x3   Q = LN1(x) Wq^T, K = x Wk^T, V = x Wv^T        (one grouped launch, tcgen05 kind::f16)
 //     rows_attn      causal attention inside the row's segment + residual + LN2   (fp32 softmax / LN)
