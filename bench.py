@@ -1013,9 +1013,42 @@ def time_men(args, dev, pk, rank=0, world=1):
                        "all_valid_tflops": fl_all * r_f / 1e12, "all_valid_frac_of_bf16_peak": fl_all * r_f / 1e12 / peak / world}
         model.set_eval_dtype("fp32")
     out["value"] = out["bf16"]["value"]
+    if world == 1:
+        # the Men-shaped train step (fwd + BCE + bwd + Adam, dropout 0.5): d = 256 is outside the fused training kernels,
+        # so this is the per-op path — every projection / input gradient / weight gradient a tcgen05 3xTF32 GEMM
+        try:
+            out["train"] = men_train_rate(shape, args, dev, model.embeds.attr_table)
+        except Exception as ex:  # noqa: BLE001
+            out["train"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
     out["valid_rows_per_user"] = rows_sparse
     out["per_kernel_evidence"] = "profiles/r02/README.md (ncu: tensor-pipe utilisation of rows_gemm_kernel<256> per epilogue)"
     return out
+
+
+def men_train_rate(shape, args, dev, table):
+    import carca_replication_b200 as cb
+    from carca_replication_b200 import synth
+    from carca_replication_b200.graph import GraphedTrainStep
+
+    L, Bt = shape.seq_len, args.train_batch
+    model = synth.build_model(shape, args.decoder, p=0.5).to(dev).train()
+    model.embeds.set_attr_table(table)
+    optim = cb.FusedAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    batches = [{k: v.to(dev) for k, v in synth.make_train_batch(shape, Bt, seed=177 + i).items()} for i in range(2)]
+    step = GraphedTrainStep(model, optim, batches[0])
+    n = max(3, args.steps // 2)
+    for i in range(2):
+        step(batches[i % 2])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(n):
+        loss = step(batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": Bt / (ms * 1e-3), "unit": "seqs/s", "batch_per_gpu": Bt, "ms_per_step": ms, "final_loss": float(loss.item()),
+            "path": "per-op kernels under autograd (tcgen05 3xTF32 GEMMs, attention fwd / bwd kernels), FusedAdam, one CUDA graph"}
 
 
 def time_catalog_sharded(model, shape, args, dev, rank, world):

@@ -246,6 +246,12 @@ static int feats_forward(float* q_out, const carca_embed_params* w, const carca_
     CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, q_out, x, at->csr_rowptr, at->csr_cols,
                  at->csr_vals, ctx, w->feats_wT, w->feats_b, mask, P, g, A, C);
     TRY(check_launch("feat_csr_fwd"));
+  } else if (at->kind == CARCA_ATTR_DENSE && w->feats_wT != nullptr && A >= 1024 && g <= 256) {
+    // dense rows of a large vocabulary (the reference API's multi-hot tensors): scan + gather-sum, bound by the read
+    auto k = feat_dense_scan_fwd_kernel;
+    CARCA_LAUNCH(k, dim3(warp_rows_grid(P)), dim3(256), 0, st, q_out, at->dense, ctx, w->feats_wT, w->feats_b, mask, P, g, A,
+                 C);
+    TRY(check_launch("feat_dense_scan_fwd"));
   } else if (at->kind == CARCA_ATTR_TABLE || at->kind == CARCA_ATTR_DENSE) {
     const int* rows = at->kind == CARCA_ATTR_TABLE ? x : nullptr;
     TRY(linear(q_out, at->dense, w->feats_w, w->feats_b, P, g, A, A + C, st, 0, nullptr, nullptr, 0, nullptr, rows,

@@ -5,6 +5,70 @@
 
 namespace carca {
 
+// q[p] = Wf[:, :A] a[p] + Wf[:, A:] ctx[p] + bf for DENSE attribute rows a[P, A] of a large, mostly-zero vocabulary
+// (the reference API's multi-hot tensors, src/carca.py:86 with src/data.py:119-131: ~8 of 6,507 set).  One warp scans
+// its row with coalesced loads (the read of `a` is the bound: 26 KB per position) and adds value x WT[j] for the
+// non-zeros it finds — the feature projection as a gather-sum instead of a [P, A] x [A, g] GEMM over zeros.  Exact for
+// any input (a fully dense row just costs A rank-1 updates); g <= 256.
+__global__ void __launch_bounds__(256) feat_dense_scan_fwd_kernel(
+    float* __restrict__ q, const float* __restrict__ a, const float* __restrict__ ctx, const float* __restrict__ WT,
+    const float* __restrict__ bias, const float* __restrict__ row_mask, int P, int g, int A, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  if (warp >= P) return;
+  const int p = warp;
+  float* out = q + (long long)p * g;
+  if (row_mask && row_mask[p] == 0.f) {
+    for (int j = lane; j < g; j += kWarp) out[j] = 0.f;
+    return;
+  }
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = u * kWarp + lane;
+    acc[u] = (bias && j < g) ? bias[j] : 0.f;
+  }
+  for (int c = 0; c < C; ++c) {
+    const float cv = ctx[(long long)p * C + c];
+    const float* w = WT + (long long)(A + c) * g;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = u * kWarp + lane;
+      if (j < g) acc[u] = fmaf(cv, w[j], acc[u]);
+    }
+  }
+  const float* row = a + (long long)p * A;
+  constexpr int UN = 8;
+  for (int j0 = 0; j0 < A; j0 += kWarp * UN) {
+    float v[UN];
+#pragma unroll
+    for (int t = 0; t < UN; ++t) {
+      const int jj = j0 + kWarp * t + lane;
+      v[t] = jj < A ? __ldg(row + jj) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < UN; ++t) {
+      unsigned m = __ballot_sync(kFull, v[t] != 0.f);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float av = __shfl_sync(kFull, v[t], src);
+        const float* w = WT + (long long)(j0 + kWarp * t + src) * g;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = u * kWarp + lane;
+          if (j < g) acc[u] = fmaf(av, __ldg(w + j), acc[u]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = u * kWarp + lane;
+    if (j < g) out[j] = acc[u];
+  }
+}
+
 // q[p,:] = (bias) + sum_c ctx[p,c] * WT[A+c,:] + sum_{e in row(item_p)} vals[e] * WT[cols[e],:]
 // One warp per position; lanes sweep g so every WT row read is a coalesced burst.
 // Rows with row_mask[p]==0 are written as zeros (their q is never consumed: the embedding is

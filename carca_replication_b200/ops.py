@@ -128,6 +128,9 @@ def _attr_source(table: Optional[ItemAttrTable], dense: Optional[Tensor]) -> N.A
     return s
 
 
+DENSE_SCAN_MIN_ATTRS = 1024
+
+
 class EmbedFn(torch.autograd.Function):
     """AllEmbedding.forward (src/carca.py:85-95) -> carca_embed_fwd / carca_embed_bwd."""
 
@@ -147,7 +150,9 @@ class EmbedFn(torch.autograd.Function):
             raise RuntimeError(f"AllEmbedding: a has {a_dense.shape[-1]} attributes, weights expect {A}")
         sparse = a_dense is None and table.is_sparse
         WfT = None
-        if sparse:
+        # (dense rows of a large vocabulary — the reference API's multi-hot tensors — are projected by a scan + gather-sum
+        # kernel that reads the transposed weights, as the CSR path does: carca_embed_fwd picks it when feats_wT is given)
+        if sparse or (a_dense is not None and A >= DENSE_SCAN_MIN_ATTRS and g <= 256):
             WfT = torch.empty((A + Cn, g), dtype=torch.float32, device=E.device)
             N.call("carca_transpose", N.f32p(WfT), N.f32p(_c(Wf)), g, A + Cn, 0, N.stream())
         e = torch.empty((n_rows, n_cols, d), dtype=torch.float32, device=E.device)
