@@ -44,15 +44,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = tempfile.mkdtemp(prefix="carca_build_", dir=CSRC)
             try:
-                objs = []
-                for src in SOURCES:
+                objs, procs = [], []
+                for src in SOURCES:                      # the translation units compile side by side
                     obj = os.path.join(tmp, src.replace(".cu", ".o"))
                     cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
                     if verbose:
                         cmd.insert(1, "-Xptxas=-v")
                         print(" ".join(cmd), flush=True)
-                    subprocess.run(cmd, check=True)
+                        subprocess.run(cmd, check=True)  # (one at a time: readable ptxas output)
+                    else:
+                        procs.append((cmd, subprocess.Popen(cmd)))
                     objs.append(obj)
+                for cmd, pr in procs:
+                    if pr.wait() != 0:
+                        raise subprocess.CalledProcessError(pr.returncode, cmd)
                 out = os.path.join(tmp, "libcarca_b200.so")
                 cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs, "-Xcompiler",
                        "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
