@@ -1091,6 +1091,33 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
           }
         }
       }
+      // per-key terms of the user's keys: row flag -> value fold / context terms, another dependent chain
+      constexpr int TERMS = (DT_KEYS * H + 127) / 128;
+      float t_kc[TERMS], t_uu[TERMS];
+      float4 t_m0[TERMS], t_m1[TERMS];
+#pragma unroll
+      for (int q = 0; q < TERMS; ++q) {
+        const int i = r + 128 * q;
+        const int j = i / H, h = i % H;
+        t_kc[q] = kMask; t_uu[q] = 0.f;
+        t_m0[q] = make_float4(0.f, 0.f, 0.f, 0.f); t_m1[q] = t_m0[q];
+        if (i < DT_KEYS * H && j < nk && a.row_src[sg.x + k0 + j] >= 0) {
+          const long long row = (long long)sg.x + k0 + j;
+          t_uu[q] = a.U[row * H + h];
+          const float4* kmp = reinterpret_cast<const float4*>(a.KM + (row * H + h) * 8);
+          const float4 m0 = __ldg(kmp), m1 = __ldg(kmp + 1);
+          if (uctx) {
+            const float* cu = a.o_c + (long long)u * a.oc_user;
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            float kcv = 0.f;
+            for (int k = 0; k < a.C; ++k) kcv = fmaf(mm[k], __ldg(cu + k), kcv);
+            t_kc[q] = kcv;
+          } else {
+            t_kc[q] = 0.f;
+            t_m0[q] = m0; t_m1[q] = m1;
+          }
+        }
+      }
       if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
       if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
       {   // what the epilogue needs of this row, so that it reads no global memory
@@ -1128,32 +1155,19 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
           }
         }
       }
-      // per-key terms
-      for (int i = r; i < DT_KEYS * H; i += 128) {
-        const int j = i / H, h = i % H;
-        float kcv = kMask, uv = 0.f;
-        if (!uctx) {   // masked keys: their context terms are still READ by the epilogue (whole chunks of 8 columns)
-          reinterpret_cast<float4*>(&s.km[st][j][h][0])[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-          reinterpret_cast<float4*>(&s.km[st][j][h][0])[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (j < nk && a.row_src[sg.x + k0 + j] >= 0) {
-          const long long row = (long long)sg.x + k0 + j;
-          uv = a.U[row * H + h];
-          const float4* kmp = reinterpret_cast<const float4*>(a.KM + (row * H + h) * 8);
-          const float4 m0 = __ldg(kmp), m1 = __ldg(kmp + 1);
-          if (uctx) {
-            const float* cu = a.o_c + (long long)u * a.oc_user;
-            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            kcv = 0.f;
-            for (int k = 0; k < a.C; ++k) kcv = fmaf(mm[k], __ldg(cu + k), kcv);
-          } else {
-            kcv = 0.f;
-            reinterpret_cast<float4*>(&s.km[st][j][h][0])[0] = m0;
-            reinterpret_cast<float4*>(&s.km[st][j][h][0])[1] = m1;
+      // per-key terms (loaded before the stage wait, see above)
+#pragma unroll
+      for (int q = 0; q < TERMS; ++q) {
+        const int i = r + 128 * q;
+        if (i < DT_KEYS * H) {
+          const int j = i / H, h = i % H;
+          if (!uctx) {   // masked keys: their context terms are still READ by the epilogue (whole chunks of 8 columns)
+            reinterpret_cast<float4*>(&s.km[st][j][h][0])[0] = t_m0[q];
+            reinterpret_cast<float4*>(&s.km[st][j][h][0])[1] = t_m1[q];
           }
+          s.kc[st][h][j] = t_kc[q];
+          s.uu[st][h][j] = t_uu[q];
         }
-        s.kc[st][h][j] = kcv;
-        s.uu[st][h][j] = uv;
       }
       // this thread's stores are visible to the tensor core's (async-proxy) reads; its ARRIVAL is deferred to the
       // completion of its gather copies (cp.async.mbarrier.arrive.noinc: one of the barrier's 128 expected arrivals,
