@@ -987,6 +987,7 @@ struct DecTcSmem {
   alignas(16) float rcv[NST][128][8];
   uint64_t full[NST], empty[NST], acc_full[NST], acc_empty[NST];
   uint32_t tmem_slot;
+  int2 useg_c[64];                  // (first row, rows) of the users of this CTA's first 64 work items
 };
 
 struct DecTcArgs {
@@ -1039,16 +1040,24 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
   const uint32_t tmem0 = s.tmem_slot;
   const float sc = 1.4426950408889634f * rsqrtf((float)DH);
   pdl_wait();
+  // every role walks the same list of work items and needs each user's segment first: fetched once per CTA, up front
+  // (in the step loop that load headed the producers' chain of dependent loads)
+  for (int i = threadIdx.x; i < 64; i += DT_THREADS) {
+    const unsigned item = blockIdx.x + (unsigned)i * gridDim.x;
+    if (item < (unsigned)a.B * (unsigned)n_tiles) s.useg_c[i] = a.useg[n_tiles == 1 ? item : item / (unsigned)n_tiles];
+  }
+  __syncthreads();
 
   // the sequence of (user, candidate tile, key chunk) steps of this CTA: identical in every role
   // step `it`: user u, tile, key chunk k0 .. k0 + nk
   auto for_each_step = [&](auto&& body) {
     uint32_t it = 0;
     const unsigned n_items = (unsigned)a.B * (unsigned)n_tiles;       // (B < 2^23, a few tiles per user)
-    for (unsigned item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int ic = 0;
+    for (unsigned item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
       const int u = n_tiles == 1 ? (int)item : (int)(item / (unsigned)n_tiles);
       const int t0 = n_tiles == 1 ? 0 : (int)(item % (unsigned)n_tiles) * 128;
-      const int2 sg = a.useg[u];
+      const int2 sg = ic < 64 ? s.useg_c[ic] : a.useg[u];
       for (int k0 = 0; k0 < max(sg.y, 1); k0 += DT_KEYS, ++it)
         if (!body(it, u, t0, sg, k0, min(DT_KEYS, sg.y - k0), k0 + DT_KEYS >= sg.y)) return;
     }
@@ -1060,6 +1069,9 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
     // groups each own one stage and take every other step, so two such chains are always in flight per CTA
     static_assert(NST == 2, "one producer group per stage");
     const int grp = (warp - 5) >> 2, r = threadIdx.x - 160 - 128 * grp;
+    float mcw_r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mcw_r[k] = k < a.C ? __ldg(a.mcw + k) : 0.f;
     for_each_step([&](uint32_t it, int u, int t0, int2 sg, int k0, int nk, bool last) {
       const int st = it % NST, ph = (it / NST) & 1;
       if (st != grp) return true;
@@ -1084,11 +1096,9 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
         for (int k = 0; k < 8; ++k) cv[k] = 0.f;
         if (id != 0) {
           const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
-          for (int k = 0; k < a.C; ++k) cv[k] = __ldg(c + k);
-          if (a.residual_ca) {
-            res = __ldg(a.tw + id);
-            for (int k = 0; k < a.C; ++k) res = fmaf(__ldg(a.mcw + k), cv[k], res);
-          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? __ldg(c + k) : 0.f;
+          if (a.residual_ca) res = __ldg(a.tw + id);     // (second level of the id chain: first USED after the stage wait)
         }
       }
       // per-key terms of the user's keys: row flag -> value fold / context terms, another dependent chain
@@ -1101,16 +1111,26 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
         const int j = i / H, h = i % H;
         t_kc[q] = kMask; t_uu[q] = 0.f;
         t_m0[q] = make_float4(0.f, 0.f, 0.f, 0.f); t_m1[q] = t_m0[q];
-        if (i < DT_KEYS * H && j < nk && a.row_src[sg.x + k0 + j] >= 0) {
+        if (i < DT_KEYS * H && j < nk) {
+          // (the row's flag, value fold and context terms are requested together: one level of latency, not two; and
+          // fixed trip counts — a run-time `k < C` loop issues one load, waits for it, issues the next: the per-role
+          // clocks showed ~3,000 cycles per step in these few loops)
           const long long row = (long long)sg.x + k0 + j;
-          t_uu[q] = a.U[row * H + h];
+          const int flag = a.row_src[row];
+          const float uval = a.U[row * H + h];
           const float4* kmp = reinterpret_cast<const float4*>(a.KM + (row * H + h) * 8);
           const float4 m0 = __ldg(kmp), m1 = __ldg(kmp + 1);
+          if (flag < 0) continue;                    // padding key (position L-1 of a short window): stays masked
+          t_uu[q] = uval;
           if (uctx) {
             const float* cu = a.o_c + (long long)u * a.oc_user;
             const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            float cu8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cu8[k] = k < a.C ? __ldg(cu + k) : 0.f;
             float kcv = 0.f;
-            for (int k = 0; k < a.C; ++k) kcv = fmaf(mm[k], __ldg(cu + k), kcv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) kcv = fmaf(mm[k], cu8[k], kcv);
             t_kc[q] = kcv;
           } else {
             t_kc[q] = 0.f;
@@ -1121,6 +1141,10 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
       if (!wait_or_flag(&s.empty[st], ph ^ 1, a.status, 4)) return false;
       if (!wait_or_flag(&s.acc_empty[st], ph ^ 1, a.status, 4)) return false;
       {   // what the epilogue needs of this row, so that it reads no global memory
+        if (id != 0 && a.residual_ca) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) res = fmaf(mcw_r[k], cv[k], res);      // (cv[k] = 0 for k >= C)
+        }
         s.rid[st][r] = t < a.T ? id : -1;
         s.rres[st][r] = res;
         if (!uctx) {
@@ -1225,10 +1249,14 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
       }
       const float res = s.rres[st][r];
       const uint32_t tb = tmem0 + ((uint32_t)(32 * warp) << 16) + st * (H * DT_KEYS);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
+      // Online softmax per CHUNK of 8 key columns, not per column: the 8 scores, their maximum (a tree), the 8
+      // exponentials and the two sums are independent instructions; only one rescale per chunk sits on the running
+      // (m, z, dd) chain (a per-column update is a serial max -> ex2 -> fma chain per key: per-role clocks showed the
+      // epilogue warps busy 70 % of the kernel with it, 48 % after the change).
 #pragma unroll 1
-        for (int c0 = 0; c0 < nk; c0 += 8) {
+      for (int c0 = 0; c0 < nk; c0 += 8) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
           float v[8];
           umma::tmem_ld_1x8(tb + h * DT_KEYS + c0, v);
 #pragma unroll
@@ -1238,13 +1266,22 @@ __global__ void __launch_bounds__(DT_THREADS, (D >= 256 ? 1 : 2)) rows_decode_tc
 #pragma unroll
               for (int k = 0; k < 8; ++k) sv = fmaf(cv[k], s.km[st][c0 + e][h][k], sv);
             }
-            sv *= sc;
-            const float mn = fmaxf(m[h], sv);
-            const float corr = ex2f(m[h] - mn), p = ex2f(sv - mn);
-            z[h] = fmaf(z[h], corr, p);
-            dd[h] = fmaf(dd[h], corr, p * s.uu[st][h][c0 + e]);
-            m[h] = mn;
+            v[e] = sv * sc;
           }
+          const float cm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+          const float mn = fmaxf(m[h], cm);
+          const float corr = ex2f(m[h] - mn);
+          float ps0 = 0.f, ps1 = 0.f, pd0 = 0.f, pd1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float p0 = ex2f(v[e] - mn), p1 = ex2f(v[e + 1] - mn);
+            ps0 += p0; ps1 += p1;
+            pd0 = fmaf(p0, s.uu[st][h][c0 + e], pd0);
+            pd1 = fmaf(p1, s.uu[st][h][c0 + e + 1], pd1);
+          }
+          z[h] = fmaf(z[h], corr, ps0 + ps1);
+          dd[h] = fmaf(dd[h], corr, pd0 + pd1);
+          m[h] = mn;
         }
       }
       if (last) {
