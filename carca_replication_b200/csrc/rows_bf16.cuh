@@ -173,11 +173,16 @@ __global__ void __launch_bounds__(256) rows_embed_ln_kernel(const EmbedArgs a) {
       const int pos = src & 255, u = (src >> 8) & 0x7fffff;
       if (src >= 0) {
         ldg256(a.T + (long long)id * D + 8 * l, x);
+        // (fixed trip count: all context loads go out together with the table row; a run-time `k < C` loop would
+        // issue one, wait for it, issue the next)
         const float* c = a.p_c + ((long long)u * a.L + pos) * a.C;
-        for (int k = 0; k < a.C; ++k) {
-          const float cv = __ldg(c + k);
+        float cv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = fmaf(mct[k][8 * l + e], cv, x[e]);
+        for (int k = 0; k < 8; ++k) cv[k] = k < a.C ? __ldg(c + k) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = fmaf(mct[k][8 * l + e], cv[k], x[e]);
         }
         if (a.pos) {
           const float4* pp = reinterpret_cast<const float4*>(a.pos + (long long)pos * D + 8 * l);
@@ -925,7 +930,11 @@ __global__ void __launch_bounds__(128) rows_decode_dot_kernel(const DecodeArgs a
         }
         acc = s0 + s1;
         const float* c = a.o_c + (long long)u * a.oc_user + (long long)t * a.oc_tgt;
-        for (int k = 0; k < a.C; ++k) acc = fmaf(pmc[k], __ldg(c + k), acc);
+        float c8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c8[k] = k < a.C ? __ldg(c + k) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(k < a.C ? pmc[k] : 0.f, c8[k], acc);
       }
       a.y[(long long)u * a.ldy + a.col0 + t] = 1.0f / (1.0f + expf(-acc));
     }
