@@ -469,11 +469,12 @@ def run_ours(args):
                     st.copy_(acc4)
                     stats_host[i % NS].copy_(st, non_blocking=True)
                 landed[i % NS].record(cur)
-                if i > 0:                                    # the caller consumes step i-1's metrics
-                    landed[(i - 1) % NS].synchronize()
-                    results.append(float(stats_host[(i - 1) % NS][0]))
-            landed[(n - 1) % NS].synchronize()
-            results.append(float(stats_host[(n - 1) % NS][0]))
+                if i > 1:                                    # the caller consumes step i-2's metrics: two steps stay
+                    landed[(i - 2) % NS].synchronize()       # queued behind the one whose result the host waits for
+                    results.append(float(stats_host[(i - 2) % NS][0]))   # (its slot is rewritten by step i+1, queued later)
+            for j in range(max(0, n - 2), n):
+                landed[j % NS].synchronize()
+                results.append(float(stats_host[j % NS][0]))
 
         e2e_run(max(W, args.rotate))                 # every pinned host arena has crossed PCIe once (the first
                                                      # copy out of a pinned buffer runs at ~1/5 of the link rate)
@@ -532,8 +533,8 @@ def run_ours(args):
                                                   "rank metrics; per step one H2D copy of a pinned PACKED arena (per-user "
                                                   "offsets, candidate ids, one context row per user, (id, context) of "
                                                   "the valid profile positions; issued up to two steps ahead on a second "
-                                                  "stream) and one D2H read of the accumulators (consumed by the host one "
-                                                  "step behind)"},
+                                                  "stream) and one D2H read of the accumulators (consumed by the host two "
+                                                  "steps behind)"},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "ops": ops_table,
         "ops_per_op_path": per_op_table,
         "peaks": pk, "hr10": hr_ndcg[0], "ndcg10": hr_ndcg[1], "host_numa": numa,
