@@ -83,7 +83,7 @@ def main():
     want = src.clone()
     dist.all_reduce(want)
     say(f"graph replay: max |peer - nccl| {(x - want).abs().max().item():.2e} timed out {comm.timed_out()}")
-    for n in (256, 65_536, 1_000_000, big):
+    for n in (() if os.environ.get("PEER_QUICK") else (256, 65_536, 1_000_000, big)):
         y = torch.randn(n, device=dev, generator=g)
         ms_p = clock(lambda: comm.all_reduce_(y))
         ms_n = clock(lambda: dist.all_reduce(y))
